@@ -1,0 +1,1989 @@
+// wave_oracle.cpp — CPU ORACLE.  TEST INFRASTRUCTURE ONLY.
+//
+// A literal CPU restatement of the staggered-grid FD time-stepping path of WAVE-Simulation, in the reference's own
+// formulation: every spatial derivative is an explicit CSR sparse matrix assembled by the rules of
+// `src/ForwardSolver/Derivatives/Derivatives.cpp` (calcDxf/calcDyf/.../calcDybFreeSurface), and every line of the
+// reference `run()` functions is one sparse-matrix-vector product or one full-length vector operation, in the same
+// order and with the same rounding points (compiled with -ffp-contract=off; fp32 by default, fp64 on request).
+// It therefore doubles as the "LAMA-equivalent" CPU timing baseline (same algorithm and same memory traffic as the
+// LAMA host back-end; it is a restatement, not the LAMA binary: LAMA/SCAI is not available in this environment).
+//
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this library.
+// The product (wave-simulation_b200/) never links, imports or calls it.
+//
+// Parity pin: checked against the reference's golden seismograms par/ci/seismogram.*.ref.*.mtx
+// (tests/test_oracle_golden.py; fixtures copied to tests/golden/).
+//
+// All citations `File.cpp:N` are relative to /root/reference/src/.
+#include "../include/wavesim.h"
+
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace {
+
+using Idx = int32_t;
+using std::vector;
+
+thread_local std::string g_err;
+
+#define ORACLE_REQUIRE(cond, msg)                                                                                      \
+    do {                                                                                                               \
+        if (!(cond))                                                                                                   \
+            throw std::runtime_error(std::string(msg));                                                               \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------------------------
+// FD coefficients: Taylor coefficients of the staggered first derivative, orders 2..12
+// (Derivatives.cpp:2001-2042 setFDCoef; the reference stores them as ValueType).
+// ------------------------------------------------------------------------------------------------------------------
+template <typename T>
+vector<T> fdCoef(int q)
+{
+    static const double c2[] = {-1.0, 1.0};
+    static const double c4[] = {1.0 / 24.0, -9.0 / 8.0, 9.0 / 8.0, -1.0 / 24.0};
+    static const double c6[] = {-3.0 / 640.0, 25.0 / 384.0, -75.0 / 64.0, 75.0 / 64.0, -25.0 / 384.0, 3.0 / 640.0};
+    static const double c8[] = {5.0 / 7168.0, -49.0 / 5120.0, 245.0 / 3072.0, -1225.0 / 1024.0,
+                                1225.0 / 1024.0, -245.0 / 3072.0, 49.0 / 5120.0, -5.0 / 7168.0};
+    static const double c10[] = {-35.0 / 294912.0, 405.0 / 229376.0, -567.0 / 40960.0, 735.0 / 8192.0, -19845.0 / 16384.0,
+                                 19845.0 / 16384.0, -735.0 / 8192.0, 567.0 / 40960.0, -405.0 / 229376.0, 35.0 / 294912.0};
+    static const double c12[] = {63.0 / 2883584.0, -847.0 / 2359296.0, 5445.0 / 1835008.0, -22869.0 / 1310720.0,
+                                 12705.0 / 131072.0, -160083.0 / 131072.0, 160083.0 / 131072.0, -12705.0 / 131072.0,
+                                 22869.0 / 1310720.0, -5445.0 / 1835008.0, 847.0 / 2359296.0, -63.0 / 2883584.0};
+    const double *p = nullptr;
+    switch (q) {
+    case 2: p = c2; break;
+    case 4: p = c4; break;
+    case 6: p = c6; break;
+    case 8: p = c8; break;
+    case 10: p = c10; break;
+    case 12: p = c12; break;
+    default: throw std::runtime_error("spatialFDorder = " + std::to_string(q) + " Unsupported spatialFDorder value.");
+    }
+    vector<T> r(q);
+    for (int j = 0; j < q; j++)
+        r[j] = (T)p[j];
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// CSR matrix + SpMV (stand-in for lama::CSRSparseMatrix / StencilMatrix times DenseVector)
+// ------------------------------------------------------------------------------------------------------------------
+template <typename T>
+struct Csr {
+    Idx n = 0;
+    vector<int64_t> ia;
+    vector<Idx> ja;
+    vector<T> va;
+    bool empty() const { return n == 0; }
+};
+
+constexpr int MAXROW = 16;
+
+// rowfn(i, cols, vals) -> nnz of row i (unsorted); rows are sorted by column like LAMA's fillFromAssembly
+template <typename T, typename F>
+Csr<T> assemble(Idx n, F rowfn)
+{
+    vector<Idx> cols((size_t)n * MAXROW);
+    vector<T> vals((size_t)n * MAXROW);
+    vector<int> cnt(n);
+#pragma omp parallel for schedule(static)
+    for (Idx i = 0; i < n; i++) {
+        Idx *c = &cols[(size_t)i * MAXROW];
+        T *v = &vals[(size_t)i * MAXROW];
+        int k = rowfn(i, c, v);
+        // insertion sort by column
+        for (int a = 1; a < k; a++) {
+            Idx cc = c[a];
+            T vv = v[a];
+            int b = a - 1;
+            while (b >= 0 && c[b] > cc) {
+                c[b + 1] = c[b];
+                v[b + 1] = v[b];
+                b--;
+            }
+            c[b + 1] = cc;
+            v[b + 1] = vv;
+        }
+        cnt[i] = k;
+    }
+    Csr<T> A;
+    A.n = n;
+    A.ia.resize((size_t)n + 1);
+    A.ia[0] = 0;
+    for (Idx i = 0; i < n; i++)
+        A.ia[i + 1] = A.ia[i] + cnt[i];
+    A.ja.resize(A.ia[n]);
+    A.va.resize(A.ia[n]);
+#pragma omp parallel for schedule(static)
+    for (Idx i = 0; i < n; i++) {
+        for (int k = 0; k < cnt[i]; k++) {
+            A.ja[A.ia[i] + k] = cols[(size_t)i * MAXROW + k];
+            A.va[A.ia[i] + k] = vals[(size_t)i * MAXROW + k];
+        }
+    }
+    return A;
+}
+
+template <typename T>
+void scaleCsr(Csr<T> &A, T s)
+{
+#pragma omp parallel for schedule(static)
+    for (int64_t k = 0; k < (int64_t)A.va.size(); k++)
+        A.va[k] = A.va[k] * s;
+}
+
+// y = A * x  (row sum in ascending column order, accumulator starts at 0)
+template <typename T>
+void spmv(const Csr<T> &A, const vector<T> &x, vector<T> &y)
+{
+    y.resize(A.n);
+    const int64_t *ia = A.ia.data();
+    const Idx *ja = A.ja.data();
+    const T *va = A.va.data();
+    const T *xp = x.data();
+    T *yp = y.data();
+#pragma omp parallel for schedule(static)
+    for (Idx i = 0; i < A.n; i++) {
+        T s = 0;
+        for (int64_t k = ia[i]; k < ia[i + 1]; k++)
+            s += va[k] * xp[ja[k]];
+        yp[i] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// full-length vector operations (one per reference statement)
+// ------------------------------------------------------------------------------------------------------------------
+#define VFOR(n) _Pragma("omp parallel for schedule(static)") for (Idx i = 0; i < (Idx)(n); i++)
+
+template <typename T> void vadd(vector<T> &a, const vector<T> &b) { T *p = a.data(); const T *q = b.data(); VFOR(a.size()) p[i] = p[i] + q[i]; }
+template <typename T> void vsub(vector<T> &a, const vector<T> &b) { T *p = a.data(); const T *q = b.data(); VFOR(a.size()) p[i] = p[i] - q[i]; }
+template <typename T> void vmul(vector<T> &a, const vector<T> &b) { T *p = a.data(); const T *q = b.data(); VFOR(a.size()) p[i] = p[i] * q[i]; }
+template <typename T> void vscale(vector<T> &a, T s) { T *p = a.data(); VFOR(a.size()) p[i] = p[i] * s; }
+template <typename T> void vset(vector<T> &a, const vector<T> &b) { a = b; }
+// a = b + c
+template <typename T> void vsum(vector<T> &a, const vector<T> &b, const vector<T> &c) { a.resize(b.size()); T *p = a.data(); const T *q = b.data(); const T *r = c.data(); VFOR(b.size()) p[i] = q[i] + r[i]; }
+// a = s * b
+template <typename T> void vscaled(vector<T> &a, T s, const vector<T> &b) { a.resize(b.size()); T *p = a.data(); const T *q = b.data(); VFOR(b.size()) p[i] = s * q[i]; }
+// a += s * b   (a[i] = a[i] + (s*b[i]), two roundings)
+template <typename T> void vaxpy(vector<T> &a, T s, const vector<T> &b) { T *p = a.data(); const T *q = b.data(); VFOR(a.size()) p[i] = p[i] + s * q[i]; }
+// a -= s * b
+template <typename T> void vaxmy(vector<T> &a, T s, const vector<T> &b) { T *p = a.data(); const T *q = b.data(); VFOR(a.size()) p[i] = p[i] - s * q[i]; }
+
+// Common.hpp:128-141 replaceInvalid, Common.hpp:68-120 searchAndReplace (compareType 1 := <)
+template <typename T> void replaceInvalid(vector<T> &a, T v)
+{
+    T *p = a.data();
+    VFOR(a.size()) if (std::isnan(p[i]) || std::isinf(p[i])) p[i] = v;
+}
+template <typename T> void searchAndReplaceLess(vector<T> &a, T thr, T v)
+{
+    T *p = a.data();
+    VFOR(a.size()) if (p[i] < thr) p[i] = v;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// sparse vector (boundary-only) for CPML
+// ------------------------------------------------------------------------------------------------------------------
+template <typename T>
+struct Profile { // pattern + (a,b) full-grid and half-grid coefficient values on that pattern
+    vector<Idx> idx;
+    vector<T> a, b, ah, bh;
+};
+
+template <typename T>
+struct Oracle {
+    ws_desc d{};
+    Idx NX = 0, NY = 0, NZ = 0, N = 0;
+    bool prepared = false;
+    T DT = 0, DH = 0;
+    int L = 0;
+
+    std::map<std::string, vector<T>> mat; // model parameters, raw + derived, by reference getter name
+    std::map<std::string, vector<T>> fld; // wavefields by reference component name
+
+    Csr<T> Dxf, Dxb, Dyf, Dyb, Dzf, Dzb, DyfFS, DybFS;
+
+    // boundaries
+    vector<T> damping;                 // ABS (dense, default 1.0)
+    vector<Idx> surfIdx;               // indices with y == 0
+    vector<T> sH, sV;                  // FreeSurfaceElastic: scaleHorizontalUpdate / scaleVerticalUpdate on surfIdx
+    vector<vector<T>> sRH, sRV;        // FreeSurfaceViscoelastic relaxation scalings
+    Profile<T> px, py, pz;             // CPML coefficient patterns per axis
+    std::map<std::string, vector<T>> psi; // CPML memory variables on the axis pattern
+
+    // visco
+    vector<T> relaxationTime, inverseRelaxationTime, viscoCoeff1, viscoCoeff2;
+    T DThalf = 0;
+    vector<T> onePlusLtauP, onePlusLtauS;
+    // EM
+    vector<T> Cc;
+
+    // acquisition
+    vector<Idx> srcType, srcIdx, recType, recIdx;
+    vector<T> srcSig; // nsrc x nt
+    vector<T> seis;   // nrec x nt
+
+    // temporaries
+    vector<T> update, update_temp, update2, vxx, vyy, vzz;
+
+    Idx index(Idx x, Idx y, Idx z) const { return x + z * NX + y * NX * NZ; } // Coordinates.cpp:687
+    void coord(Idx i, Idx &x, Idx &y, Idx &z) const
+    { // Coordinates.cpp:615-645
+        y = i / (NX * NZ);
+        i -= y * (NX * NZ);
+        z = i / NX;
+        i -= z * NX;
+        x = i;
+    }
+
+    vector<T> &M(const std::string &k)
+    {
+        auto it = mat.find(k);
+        ORACLE_REQUIRE(it != mat.end(), "model parameter '" + k + "' is not set");
+        return it->second;
+    }
+    vector<T> &F(const std::string &k)
+    {
+        auto it = fld.find(k);
+        ORACLE_REQUIRE(it != fld.end(), "wavefield '" + k + "' does not exist");
+        return it->second;
+    }
+    bool isEq(int e) const { return d.eq == e; }
+    bool seismic() const { return d.eq <= WS_EQ_VISCOSH; }
+    bool visco() const { return d.eq == WS_EQ_VISCOELASTIC || d.eq == WS_EQ_VISCOSH || d.eq == WS_EQ_VISCOTMEM || d.eq == WS_EQ_VISCOEMEM; }
+
+    // ------------------------------------------------------------------------------------------------------------
+    // Derivative matrices
+    // ------------------------------------------------------------------------------------------------------------
+    // axis: 0 = x, 1 = y, 2 = z
+    Idx axisN(int axis) const { return axis == 0 ? NX : (axis == 1 ? NY : NZ); }
+    Idx axisStride(int axis) const { return axis == 0 ? 1 : (axis == 1 ? NX * NZ : NX); }
+    Idx axisCoord(Idx i, int axis) const
+    {
+        Idx x, y, z;
+        coord(i, x, y, z);
+        return axis == 0 ? x : (axis == 1 ? y : z);
+    }
+
+    // Sparse assembly with order reduction at the domain edges:
+    // forward: Derivatives.cpp:129-186 (x), :210-280 (y), :304-359 (z); backward: :706-763 (x), :771-843 (y), calcDzb.
+    // Values: coefficient / DH, later scaled by DT (FDTD3D.cpp:252-256, FDTD2D.cpp) -> fl(fl(c/DH)*DT).
+    Csr<T> derivSparse(int axis, bool forward)
+    {
+        const int q = d.fd_order;
+        std::map<int, vector<T>> fdmap;
+        for (int o = 2; o <= q; o += 2)
+            fdmap[o] = fdCoef<T>(o);
+        const Idx n = axisN(axis), st = axisStride(axis);
+        const T dh = DH;
+        Csr<T> A = assemble<T>(N, [&](Idx row, Idx *cols, T *vals) {
+            Idx c = axisCoord(row, axis);
+            const Idx c0 = c;
+            int order = q;
+            int k = 0;
+            for (int j = 0; j < order; j++) {
+                Idx X, Xmin, Xmax;
+                if (forward) {
+                    X = c + (j - order / 2 + 1);
+                    Xmin = c + (-order / 2 + 1);
+                    Xmax = c + order / 2;
+                } else {
+                    X = c + (j - order / 2);
+                    Xmin = c + (-order / 2);
+                    Xmax = c + (order / 2 - 1);
+                }
+                if (Xmin < 0) {
+                    order += 2 * Xmin;
+                    if (!forward && order == 0) { // Derivatives.cpp:745-748
+                        order = 2;
+                        c += 1;
+                    }
+                    j--;
+                } else if (Xmax >= n) {
+                    order -= 2 * (Xmax - n + 1);
+                    if (forward && order == 0) { // Derivatives.cpp:171-174
+                        order = 2;
+                        c -= 1;
+                    }
+                    j--;
+                } else {
+                    cols[k] = row + (X - c0) * st;
+                    vals[k] = fdmap[order][j] / dh;
+                    k++;
+                }
+            }
+            return k;
+        });
+        scaleCsr(A, DT);
+        return A;
+    }
+
+    // StencilMatrix path (useStencilMatrix=1): Derivatives.cpp:112-121,194-201,288-295; off-grid taps are dropped;
+    // backward = -(forward)^T (FDTD3D.cpp:202-207); values scaled by DT/DH (FDTD3D.cpp:211-216).
+    Csr<T> derivStencil(int axis, bool forward)
+    {
+        const int q = d.fd_order;
+        const vector<T> fd = fdCoef<T>(q);
+        const Idx n = axisN(axis), st = axisStride(axis);
+        const T s = DT / DH;
+        return assemble<T>(N, [&](Idx row, Idx *cols, T *vals) {
+            const Idx c = axisCoord(row, axis);
+            int k = 0;
+            for (int j = 0; j < q; j++) {
+                Idx off = forward ? (j - q / 2 + 1) : (j - q / 2);
+                Idx X = c + off;
+                if (X < 0 || X >= n)
+                    continue;
+                cols[k] = row + off * st;
+                vals[k] = fd[j] * s;
+                k++;
+            }
+            return k;
+        });
+    }
+
+    // Image-method matrices, Derivatives.cpp:367-440 (calcDyfFreeSurface), :448-526 (calcDybFreeSurface);
+    // values (c - c_image)/DH then *= DT (FDTD3D.cpp:312-323). No order reduction; off-grid rows dropped.
+    Csr<T> derivFreeSurface(bool forward)
+    {
+        const int q = d.fd_order;
+        const vector<T> fd = fdCoef<T>(q);
+        const Idx st = NX * NZ;
+        const T dh = DH;
+        Csr<T> A = assemble<T>(N, [&](Idx row, Idx *cols, T *vals) {
+            const Idx y = axisCoord(row, 1);
+            int k = 0;
+            for (int j = 0; j < q; j++) {
+                Idx Y = forward ? y + (j - q / 2 + 1) : y + (j - q / 2);
+                T fdCoeff = fd[j];
+                T diffCoeff = 0;
+                if (forward) {
+                    if (q >= (2 + 2 * y + j)) {
+                        int im = q - 2 - 2 * y - j;
+                        diffCoeff = fd[im];
+                    }
+                } else {
+                    if (q >= (1 + 2 * y + j)) {
+                        int im = q - 1 - 2 * y - j;
+                        diffCoeff = fd[im];
+                    }
+                }
+                if (Y >= 0 && Y < NY) {
+                    cols[k] = row + (Y - y) * st;
+                    vals[k] = (fdCoeff - diffCoeff) / dh;
+                    k++;
+                }
+            }
+            return k;
+        });
+        scaleCsr(A, DT);
+        return A;
+    }
+
+    void buildDerivatives()
+    {
+        auto mk = [&](int axis, bool fwd) { return d.edge_policy == 0 ? derivStencil(axis, fwd) : derivSparse(axis, fwd); };
+        Dxf = mk(0, true);
+        Dxb = mk(0, false);
+        Dyf = mk(1, true);
+        Dyb = mk(1, false);
+        if (d.dim == 3) {
+            Dzf = mk(2, true);
+            Dzb = mk(2, false);
+        }
+        if (d.free_surface == 1) {
+            DyfFS = derivFreeSurface(true);
+            DybFS = derivFreeSurface(false);
+        }
+    }
+
+    // ------------------------------------------------------------------------------------------------------------
+    // Model preparation
+    // ------------------------------------------------------------------------------------------------------------
+    // 2-point averaging matrices, Modelparameter.cpp:336-447
+    Csr<T> avg2(int axis)
+    {
+        const Idx n = axisN(axis), st = axisStride(axis);
+        return assemble<T>(N, [&](Idx row, Idx *cols, T *vals) {
+            Idx c = axisCoord(row, axis);
+            if (c + 1 < n) {
+                cols[0] = row;
+                vals[0] = (T)(1.0 / 2.0);
+                cols[1] = row + st;
+                vals[1] = (T)(1.0 / 2.0);
+                return 2;
+            }
+            cols[0] = row;
+            vals[0] = (T)1.0;
+            return 1;
+        });
+    }
+    // 4-point averaging matrices, Modelparameter.cpp:449-624 (calc4PointAverageMatrixRow + calcAverageMatrixXY/XZ/YZ)
+    Csr<T> avg4(int axA, int axB)
+    {
+        return assemble<T>(N, [&](Idx row, Idx *cols, T *vals) {
+            Idx cx, cy, cz;
+            coord(row, cx, cy, cz);
+            Idx c[3] = {cx, cy, cz};
+            // points 1..4: (0,0) (+A,0) (0,+B) (+A,+B)
+            Idx p[5][3];
+            for (int k = 1; k <= 4; k++)
+                for (int a = 0; a < 3; a++)
+                    p[k][a] = c[a];
+            p[2][axA] += 1;
+            p[3][axB] += 1;
+            p[4][axA] += 1;
+            p[4][axB] += 1;
+            Idx mx[3];
+            for (int a = 0; a < 3; a++)
+                mx[a] = std::max(std::max(p[1][a], p[2][a]), std::max(p[3][a], p[4][a]));
+            const bool inX = mx[0] < NX, inY = mx[1] < NY, inZ = mx[2] < NZ;
+            auto id = [&](Idx x, Idx y, Idx z) { return index(x, y, z); };
+            int k = 0;
+            if (inX && inY && inZ) {
+                cols[k] = row; vals[k++] = (T)(1.0 / 4.0);
+                cols[k] = id(p[2][0], p[2][1], p[2][2]); vals[k++] = (T)(1.0 / 4.0);
+                cols[k] = id(p[3][0], p[3][1], p[3][2]); vals[k++] = (T)(1.0 / 4.0);
+                cols[k] = id(p[4][0], p[4][1], p[4][2]); vals[k++] = (T)(1.0 / 4.0);
+            }
+            if (inX && !inY && inZ) { // bottom side
+                cols[k] = id(mx[0], p[1][1], mx[2]); vals[k++] = (T)(1.0 / 2.0);
+                cols[k] = row; vals[k++] = (T)(1.0 / 2.0);
+            }
+            if (!inX && inY && inZ) { // right side
+                cols[k] = id(p[1][0], mx[1], mx[2]); vals[k++] = (T)(1.0 / 2.0);
+                cols[k] = row; vals[k++] = (T)(1.0 / 2.0);
+            }
+            if (inX && inY && !inZ) { // back side
+                cols[k] = id(mx[0], mx[1], p[1][2]); vals[k++] = (T)(1.0 / 2.0);
+                cols[k] = row; vals[k++] = (T)(1.0 / 2.0);
+            }
+            if (!inX && !inY && inZ) { cols[k] = row; vals[k++] = (T)1.0; }
+            if (inX && !inY && !inZ) { cols[k] = row; vals[k++] = (T)1.0; }
+            if (!inX && inY && !inZ) { cols[k] = row; vals[k++] = (T)1.0; }
+            // a diagonal entry pushed twice cannot happen; duplicates of (row,row) in the half cases are distinct columns
+            return k;
+        });
+    }
+
+    // Modelparameter.cpp:633-639
+    void calcInverseAveragedParameter(const vector<T> &par, vector<T> &out, const Csr<T> &A)
+    {
+        spmv(A, par, out);
+        T *p = out.data();
+        VFOR(out.size()) p[i] = (T)1 / p[i];
+        replaceInvalid(out, (T)0.0);
+    }
+    // ModelparameterSeismic.cpp:421-432 (NB: clamps the input vector in place)
+    void calcAveragedSWaveModulus(vector<T> &mu, vector<T> &out, const Csr<T> &A)
+    {
+        searchAndReplaceLess(mu, (T)1.0, (T)1.0);
+        vector<T> inv(mu.size());
+        {
+            T *p = inv.data();
+            const T *q = mu.data();
+            VFOR(mu.size()) p[i] = (T)1 / q[i];
+        }
+        vector<T> tmp;
+        spmv(A, inv, tmp);
+        out.resize(mu.size());
+        {
+            T *p = out.data();
+            const T *q = tmp.data();
+            VFOR(mu.size()) p[i] = (T)1 / q[i];
+        }
+        searchAndReplaceLess(out, (T)4.0, (T)0.0);
+    }
+    // ModelparameterSeismic.cpp:131-136
+    void calcModulusFromVelocity(const vector<T> &v, const vector<T> &rho, vector<T> &modulus)
+    {
+        modulus = rho;
+        vmul(modulus, v);
+        vmul(modulus, v);
+    }
+    bool has(const std::string &k) const { return mat.count(k) > 0; }
+
+    // Viscoelastic.cpp:650-713: relaxed modulus scaling
+    void viscoScaleModulus(vector<T> &modulus, const vector<T> &tau)
+    {
+        T w_ref = (T)(2.0 * M_PI * d.fc_cpml);
+        T sum = 0;
+        for (int l = 0; l < L; l++) {
+            T tauSigma = (T)(1.0 / (2.0 * M_PI * d.relax_freq[l]));
+            sum += (T)(w_ref * w_ref * tauSigma * tauSigma / (1.0 + w_ref * w_ref * tauSigma * tauSigma));
+        }
+        T *p = modulus.data();
+        const T *q = tau.data();
+        VFOR(modulus.size())
+        {
+            T temp = (T)1.0 + sum * q[i];
+            p[i] = p[i] / temp;
+        }
+    }
+
+    void prepareModelSeismic()
+    {
+        const bool needP = (d.eq == WS_EQ_ACOUSTIC || d.eq == WS_EQ_ELASTIC || d.eq == WS_EQ_VISCOELASTIC);
+        const bool needS = (d.eq != WS_EQ_ACOUSTIC);
+        const bool vis = visco();
+        if (needP && !has("pWaveModulus")) {
+            calcModulusFromVelocity(M("velocityP"), M("density"), mat["pWaveModulus"]);
+            if (vis)
+                viscoScaleModulus(mat["pWaveModulus"], M("tauP"));
+        }
+        if (needS && !has("sWaveModulus")) {
+            calcModulusFromVelocity(M("velocityS"), M("density"), mat["sWaveModulus"]);
+            if (vis)
+                viscoScaleModulus(mat["sWaveModulus"], M("tauS"));
+        }
+        if (d.eq == WS_EQ_SH || d.eq == WS_EQ_VISCOSH) {
+            // SH.cpp:424-430: 2-point x / y averaging; un-averaged inverse density (ModelparameterSeismic.cpp:164-172)
+            if (!has("inverseDensity")) {
+                const vector<T> &rho = M("density");
+                vector<T> &o = mat["inverseDensity"];
+                o.resize(N);
+                VFOR(N) o[i] = (T)1 / rho[i];
+            }
+            Csr<T> AX = avg2(0), AY = avg2(1);
+            if (!has("sWaveModulusAverageXZ"))
+                calcAveragedSWaveModulus(M("sWaveModulus"), mat["sWaveModulusAverageXZ"], AX);
+            if (!has("sWaveModulusAverageYZ"))
+                calcAveragedSWaveModulus(M("sWaveModulus"), mat["sWaveModulusAverageYZ"], AY);
+            if (vis) { // ViscoSH: tauS averages with the same matrices
+                if (!has("tauSAverageXZ"))
+                    spmv(AX, M("tauS"), mat["tauSAverageXZ"]);
+                if (!has("tauSAverageYZ"))
+                    spmv(AY, M("tauS"), mat["tauSAverageYZ"]);
+            }
+            return;
+        }
+        // Acoustic.cpp:381-387, Elastic.cpp:576-588, Viscoelastic.cpp:562-577
+        if (!has("inverseDensityAverageX")) {
+            Csr<T> A = avg2(0);
+            calcInverseAveragedParameter(M("density"), mat["inverseDensityAverageX"], A);
+        }
+        if (!has("inverseDensityAverageY")) {
+            Csr<T> A = avg2(1);
+            calcInverseAveragedParameter(M("density"), mat["inverseDensityAverageY"], A);
+        }
+        if (d.dim == 3 && !has("inverseDensityAverageZ")) {
+            Csr<T> A = avg2(2);
+            calcInverseAveragedParameter(M("density"), mat["inverseDensityAverageZ"], A);
+        }
+        if (d.eq == WS_EQ_ACOUSTIC)
+            return;
+        {
+            Csr<T> A = avg4(0, 1);
+            if (!has("sWaveModulusAverageXY"))
+                calcAveragedSWaveModulus(M("sWaveModulus"), mat["sWaveModulusAverageXY"], A);
+            if (vis && !has("tauSAverageXY"))
+                spmv(A, M("tauS"), mat["tauSAverageXY"]);
+        }
+        if (d.dim == 3) {
+            Csr<T> A = avg4(0, 2);
+            if (!has("sWaveModulusAverageXZ"))
+                calcAveragedSWaveModulus(M("sWaveModulus"), mat["sWaveModulusAverageXZ"], A);
+            if (vis && !has("tauSAverageXZ"))
+                spmv(A, M("tauS"), mat["tauSAverageXZ"]);
+            Csr<T> B = avg4(1, 2);
+            if (!has("sWaveModulusAverageYZ"))
+                calcAveragedSWaveModulus(M("sWaveModulus"), mat["sWaveModulusAverageYZ"], B);
+            if (vis && !has("tauSAverageYZ"))
+                spmv(B, M("tauS"), mat["tauSAverageYZ"]);
+        }
+    }
+
+    // ---- EM model preparation + coefficient builders ------------------------------------------------------------
+    // ForwardSolverEM.cpp:14-33
+    vector<T> getAveragedCinv(const vector<T> &eps, const vector<T> &sig)
+    {
+        vector<T> c(N);
+        VFOR(N)
+        {
+            T v = (T)0.5 / eps[i];
+            v = v * sig[i];
+            v = v * DT;
+            v = v + (T)1;
+            c[i] = (T)1 / v;
+        }
+        return c;
+    }
+    // ForwardSolverEM.cpp:35-57
+    vector<T> getAveragedCa(const vector<T> &eps, const vector<T> &sig)
+    {
+        vector<T> cinv = getAveragedCinv(eps, sig);
+        vector<T> c(N);
+        VFOR(N)
+        {
+            T v = (T)0.5 / eps[i];
+            v = v * sig[i];
+            v = v * DT;
+            v = (T)1 - v;
+            c[i] = v * cinv[i];
+        }
+        return c;
+    }
+    // ForwardSolverEM.cpp:59-76
+    vector<T> getAveragedCb(const vector<T> &eps, const vector<T> &sig)
+    {
+        vector<T> cinv = getAveragedCinv(eps, sig);
+        vector<T> c(N);
+        VFOR(N)
+        {
+            T v = (T)1 / eps[i];
+            c[i] = v * cinv[i];
+        }
+        return c;
+    }
+    // ForwardSolverEM.cpp:78-93
+    vector<T> getCc()
+    {
+        vector<T> r;
+        for (int l = 0; l < L; l++)
+            r.push_back((T)((1 - 0.5 * DT / relaxationTime[l]) / (1 + 0.5 * DT / relaxationTime[l])));
+        return r;
+    }
+    // ForwardSolverEM.cpp:95-117
+    vector<T> getAveragedCd(const vector<T> &epsStatic, const vector<T> &tauEps, int l)
+    {
+        T tempValue = (T)(1 / (1 + 0.5 * DT / relaxationTime[l]));
+        tempValue /= (L * relaxationTime[l] * relaxationTime[l]);
+        vector<T> c(N);
+        VFOR(N)
+        {
+            T v = tauEps[i] * tempValue;
+            v = v * epsStatic[i];
+            c[i] = v * (-DT);
+        }
+        return c;
+    }
+    // ForwardSolverEM.cpp:122-135
+    vector<T> sigmaEffectiveOptical(const vector<T> &eps, const vector<T> &sig, const vector<T> &tauEps)
+    {
+        T sum = 0;
+        for (int l = 0; l < L; l++)
+            sum += (T)(1.0 / relaxationTime[l]);
+        sum /= L;
+        vector<T> c(N);
+        VFOR(N)
+        {
+            T v = tauEps[i] * sum;
+            v = v * eps[i];
+            c[i] = v + sig[i];
+        }
+        return c;
+    }
+    // ForwardSolverEM.cpp:140-154; eps0 from Modelparameter.hpp:359-360
+    vector<T> epsEffectiveOptical(const vector<T> &eps, const vector<T> &sig, const vector<T> &tauEps, const vector<T> &tauSig)
+    {
+        const T eps0 = (T)8.8541878176e-12;
+        vector<T> c(N);
+        VFOR(N)
+        {
+            T v = (T)1 - tauEps[i];
+            v = v * eps[i];
+            T t = sig[i] * tauSig[i];
+            c[i] = v + t;
+        }
+        searchAndReplaceLess(c, eps0, eps0);
+        return c;
+    }
+
+    // plain average (ModelparameterEM analogue of calcAveragedParameter) and inverse average
+    void avgPlain(const vector<T> &in, vector<T> &out, const Csr<T> &A) { spmv(A, in, out); }
+
+    void prepareModelEM()
+    {
+        // Inputs are absolute SI values: dielectricPermittivity (eps), electricConductivity (sigma),
+        // magneticPermeability (mu), and for visco: tauDielectricPermittivity, tauElectricConductivity (absolute, s).
+        // TMEM.cpp / ViscoTMEM.cpp:442-450: mu^-1 2-point averaged in x (-> XZ) and y (-> YZ); eps/sigma cell centred.
+        // EMEM.cpp:378-392 / ViscoEMEM.cpp:409-423: mu^-1 4-point on YZ/XZ/XY; sigma, eps (tau*) 2-point in x/y/z.
+        const bool vis = visco();
+        relaxationTime.clear();
+        for (int l = 0; l < L; l++)
+            relaxationTime.push_back((T)(1.0 / (2.0 * M_PI * d.relax_freq[l])));
+        if (vis)
+            Cc = getCc();
+        if (d.eq == WS_EQ_TMEM || d.eq == WS_EQ_VISCOTMEM) {
+            Csr<T> AX = avg2(0), AY = avg2(1);
+            if (!has("inverseMagneticPermeabilityAverageXZ"))
+                calcInverseAveragedParameter(M("magneticPermeability"), mat["inverseMagneticPermeabilityAverageXZ"], AX);
+            if (!has("inverseMagneticPermeabilityAverageYZ"))
+                calcInverseAveragedParameter(M("magneticPermeability"), mat["inverseMagneticPermeabilityAverageYZ"], AY);
+            const vector<T> &eps = M("dielectricPermittivity");
+            const vector<T> &sig = M("electricConductivity");
+            if (!vis) { // ForwardSolver2Dtmem.cpp:70-78
+                mat["CaAverageZ"] = getAveragedCa(eps, sig);
+                mat["CbAverageZ"] = getAveragedCb(eps, sig);
+            } else { // ForwardSolver2Dviscotmem.cpp:79-104
+                const vector<T> &te = M("tauDielectricPermittivity");
+                const vector<T> &ts = M("tauElectricConductivity");
+                vector<T> epsO = epsEffectiveOptical(eps, sig, te, ts);
+                vector<T> sigO = sigmaEffectiveOptical(eps, sig, te);
+                mat["CaAverageZ"] = getAveragedCa(epsO, sigO);
+                mat["CbAverageZ"] = getAveragedCb(epsO, sigO);
+                for (int l = 0; l < L; l++)
+                    mat["CdAverageZ" + std::to_string(l + 1)] = getAveragedCd(eps, te, l);
+            }
+            return;
+        }
+        // EMEM / ViscoEMEM (2D TE and 3D)
+        static const char *AXN[3] = {"X", "Y", "Z"};
+        {
+            Csr<T> A = avg4(0, 1);
+            if (!has("inverseMagneticPermeabilityAverageXY"))
+                calcInverseAveragedParameter(M("magneticPermeability"), mat["inverseMagneticPermeabilityAverageXY"], A);
+        }
+        if (d.dim == 3) {
+            Csr<T> A = avg4(0, 2);
+            if (!has("inverseMagneticPermeabilityAverageXZ"))
+                calcInverseAveragedParameter(M("magneticPermeability"), mat["inverseMagneticPermeabilityAverageXZ"], A);
+            Csr<T> B = avg4(1, 2);
+            if (!has("inverseMagneticPermeabilityAverageYZ"))
+                calcInverseAveragedParameter(M("magneticPermeability"), mat["inverseMagneticPermeabilityAverageYZ"], B);
+        }
+        const int nax = d.dim == 3 ? 3 : 2;
+        for (int a = 0; a < nax; a++) {
+            Csr<T> A = avg2(a);
+            vector<T> eps, sig;
+            avgPlain(M("dielectricPermittivity"), eps, A);
+            avgPlain(M("electricConductivity"), sig, A);
+            std::string ax = AXN[a];
+            if (!vis) { // ForwardSolver2Demem.cpp / 3Demem prepareForModelling
+                mat["CaAverage" + ax] = getAveragedCa(eps, sig);
+                mat["CbAverage" + ax] = getAveragedCb(eps, sig);
+            } else {
+                vector<T> te, ts;
+                avgPlain(M("tauDielectricPermittivity"), te, A);
+                avgPlain(M("tauElectricConductivity"), ts, A);
+                vector<T> epsO = epsEffectiveOptical(eps, sig, te, ts);
+                vector<T> sigO = sigmaEffectiveOptical(eps, sig, te);
+                mat["CaAverage" + ax] = getAveragedCa(epsO, sigO);
+                mat["CbAverage" + ax] = getAveragedCb(epsO, sigO);
+                for (int l = 0; l < L; l++)
+                    mat["CdAverage" + ax + std::to_string(l + 1)] = getAveragedCd(eps, te, l);
+            }
+        }
+    }
+
+    // ------------------------------------------------------------------------------------------------------------
+    // Boundary conditions
+    // ------------------------------------------------------------------------------------------------------------
+    // Coordinates.cpp:734-750 edgeDistance
+    static Idx edgeDist(Idx c, Idx n) { return !((n - 1 - c) < c) ? c : (n - 1 - c); }
+
+    // ABS3D.cpp:154-218, ABS2D.cpp:115-178
+    void initABS()
+    {
+        const int W = d.boundary_width;
+        damping.assign(N, (T)1.0);
+        vector<T> coeff(W);
+        T amp = (T)(1.0 - d.damping_coeff / 100.0);
+        T a = (T)std::sqrt(-std::log(amp) / (T)(W * W));
+        for (int j = 0; j < W; j++)
+            coeff[j] = (T)std::exp(-(a * a * (W - j) * (W - j)));
+        const bool fs = d.free_surface != 0; // ABS*::init takes useFreeSurface (0,1,2) and tests == 0
+        for (Idx i = 0; i < N; i++) {
+            Idx x, y, z;
+            coord(i, x, y, z);
+            Idx dx = edgeDist(x, NX), dy = edgeDist(y, NY), dz = edgeDist(z, NZ);
+            if (d.dim == 3) {
+                Idx mn = dx < dy ? dx : dy;
+                if (dz < mn)
+                    mn = dz;
+                if (!fs) {
+                    if (mn < W)
+                        damping[i] = coeff[mn];
+                } else {
+                    Idx xz = !(dx < dz) ? dz : dx;
+                    if (y < W) {
+                        if (dz < W || dx < W)
+                            damping[i] = coeff[xz];
+                    } else if (mn < W)
+                        damping[i] = coeff[mn];
+                }
+            } else {
+                Idx mn = dx < dy ? dx : dy;
+                if (!fs) {
+                    if (mn < W)
+                        damping[i] = coeff[mn];
+                } else {
+                    if (y < W) {
+                        if (dx < W)
+                            damping[i] = coeff[dx];
+                    } else if (mn < W)
+                        damping[i] = coeff[mn];
+                }
+            }
+        }
+    }
+
+    // CPML.cpp:39-68
+    void calcCoeffCPML(vector<T> &a, vector<T> &b, bool shiftGrid)
+    {
+        const int W = (int)a.size();
+        T shift = shiftGrid ? (T)0.5 : (T)0;
+        T RCoef = (T)0.0008;
+        T alpha_max = (T)(2.0 * M_PI * (d.fc_cpml / 2.0));
+        T NPower = d.npower, VMax = d.vmax_cpml;
+        T d0 = (T)(-(NPower + 1) * VMax * std::log(RCoef) / (2.0 * W * DH));
+        for (int i = 0; i < W; i++) {
+            T pos = (T)(W - i - shift) / W;
+            T dd = d0 * (T)std::pow(pos, NPower);
+            T alpha_prime = (T)(alpha_max * (1.0 - pos));
+            b[i] = (T)std::exp(-(dd + alpha_prime) * DT);
+            if (std::abs(dd) > 1.0e-6)
+                a[i] = (T)(dd * (b[i] - 1.0) / (dd + alpha_prime));
+            else
+                a[i] = 0;
+        }
+    }
+
+    // CPML3D.cpp:222-368, CPML2D.cpp:170-285 (same rules; 2D has no z)
+    void initCPML()
+    {
+        const int W = d.boundary_width;
+        vector<T> a(W), b(W), ah(W), bh(W);
+        calcCoeffCPML(a, b, false);
+        calcCoeffCPML(ah, bh, true);
+        const int fs = d.free_surface; // useFreeSurface; only "== 0" enables the top layer
+        px = Profile<T>();
+        py = Profile<T>();
+        pz = Profile<T>();
+        for (Idx i = 0; i < N; i++) {
+            Idx x, y, z;
+            coord(i, x, y, z);
+            Idx dx = edgeDist(x, NX), dy = edgeDist(y, NY), dz = edgeDist(z, NZ);
+            auto push = [&](Profile<T> &p, Idx dist, bool low) {
+                p.idx.push_back(i);
+                if (low) {
+                    p.a.push_back(a[dist]); p.b.push_back(b[dist]); p.ah.push_back(ah[dist]); p.bh.push_back(bh[dist]);
+                } else { // swapped on the high-coordinate side, CPML3D.cpp:304-317
+                    p.a.push_back(ah[dist]); p.b.push_back(bh[dist]); p.ah.push_back(a[dist]); p.bh.push_back(b[dist]);
+                }
+            };
+            if (dx < W)
+                push(px, dx, x < W);
+            if (dy < W) {
+                if (y < W) {
+                    if (fs == 0)
+                        push(py, dy, true);
+                } else
+                    push(py, dy, false);
+            }
+            if (d.dim == 3 && dz < W)
+                push(pz, dz, z < W);
+        }
+    }
+    vector<T> &psiOf(const std::string &name, const Profile<T> &p)
+    {
+        vector<T> &v = psi[name];
+        if (v.size() != p.idx.size())
+            v.assign(p.idx.size(), (T)0);
+        return v;
+    }
+    // CPML.cpp:84-95 applyCPML: temp = a; Psi *= b; temp *= Vec; Psi += temp; Vec += Psi
+    void applyCPML(vector<T> &vec, const std::string &psiName, const Profile<T> &p, bool half)
+    {
+        if (d.damping != 2)
+            return;
+        vector<T> &ps = psiOf(psiName, p);
+        const vector<T> &A = half ? p.ah : p.a;
+        const vector<T> &B = half ? p.bh : p.b;
+        const Idx n = (Idx)p.idx.size();
+        T *v = vec.data();
+#pragma omp parallel for schedule(static)
+        for (Idx k = 0; k < n; k++) {
+            Idx i = p.idx[k];
+            T temp = A[k];
+            ps[k] = ps[k] * B[k];
+            temp = temp * v[i];
+            ps[k] = ps[k] + temp;
+            v[i] = v[i] + ps[k];
+        }
+    }
+
+    void initFreeSurface()
+    {
+        surfIdx.clear();
+        for (Idx i = 0; i < N; i++) {
+            Idx x, y, z;
+            coord(i, x, y, z);
+            if (y == 0)
+                surfIdx.push_back(i); // Coordinates.cpp:598-607
+        }
+    }
+    // FreeSurface.cpp:13-20
+    void setSurfaceZero(vector<T> &v)
+    {
+        for (Idx i : surfIdx)
+            v[i] = v[i] * (T)0;
+    }
+    // FreeSurfaceElastic.cpp:11-47
+    void fsSetModelElastic()
+    {
+        const vector<T> &pw = M("pWaveModulus");
+        const vector<T> &sw = M("sWaveModulus");
+        sH.resize(surfIdx.size());
+        sV.resize(surfIdx.size());
+        for (size_t k = 0; k < surfIdx.size(); k++) {
+            Idx i = surfIdx[k];
+            ORACLE_REQUIRE(sw[i] > 0, "S wave modulus can't be zero when using image method");
+            T temp = pw[i] - (T)2 * sw[i];
+            sV[k] = (T)1 * temp;
+            temp = temp * temp;
+            temp = temp / pw[i];
+            temp = temp * (T)-1;
+            sH[k] = (T)1 * temp;
+        }
+    }
+    // FreeSurfaceViscoelastic.cpp:12-96
+    vector<T> sSH, sSV; // scaleStressHorizontalUpdate / scaleStressVerticalUpdate
+    void fsSetModelVisco()
+    {
+        const vector<T> &pw = M("pWaveModulus");
+        const vector<T> &sw = M("sWaveModulus");
+        const vector<T> &tauS = M("tauS");
+        const vector<T> &tauP = M("tauP");
+        const size_t ns = surfIdx.size();
+        sSH.resize(ns);
+        sSV.resize(ns);
+        sRH.assign(L, vector<T>(ns));
+        sRV.assign(L, vector<T>(ns));
+        for (size_t k = 0; k < ns; k++) {
+            Idx i = surfIdx[k];
+            ORACLE_REQUIRE(sw[i] > 0, "S wave modulus can't be zero when using image method");
+            T temp = ((T)-2 * sw[i]) * onePlusLtauS[i];
+            T temp2 = pw[i] * onePlusLtauP[i];
+            temp = temp + temp2;
+            temp2 = (T)1 / temp2;
+            sSV[k] = (T)1 * temp;
+            T h = (T)-1 * (T)1;
+            h = h * temp;
+            h = h * temp;
+            h = h * temp2;
+            sSH[k] = h;
+            for (int l = 0; l < L; l++) {
+                T relTime = (T)(1.0 / (2.0 * M_PI * d.relax_freq[l]));
+                T vc2 = (T)(1.0 / (1.0 + DT / (2.0 * relTime)));
+                T t = (T)2 * sw[i];
+                T t2 = pw[i];
+                T t3 = t * tauS[i];
+                t3 = t3 - t2 * tauP[i];
+                T rv = (T)1 * t3;
+                rv = rv * vc2;
+                rv = rv / relTime;
+                sRV[l][k] = rv;
+                t = t * onePlusLtauS[i];
+                t2 = t2 * onePlusLtauP[i];
+                t = t / t2;
+                t = t - (T)1;
+                T rh = (T)1 * t3;
+                rh = rh * t;
+                rh = rh * vc2;
+                rh = rh / relTime;
+                sRH[l][k] = rh;
+            }
+        }
+    }
+
+    // ------------------------------------------------------------------------------------------------------------
+    // setup
+    // ------------------------------------------------------------------------------------------------------------
+    std::string Rn(const char *base, int l) const { return std::string(base) + std::to_string(l + 1); }
+
+    void create(const ws_desc &desc)
+    {
+        d = desc;
+        ORACLE_REQUIRE(d.dim == 2 || d.dim == 3, "dimension must be 2 or 3");
+        ORACLE_REQUIRE(d.nranks <= 1, "the oracle is single-domain");
+        NX = d.nx;
+        NY = d.ny;
+        NZ = d.dim == 2 ? 1 : d.nz;
+        ORACLE_REQUIRE(NX > 0 && NY > 0 && NZ > 0, "invalid grid");
+        ORACLE_REQUIRE((int64_t)NX * NY * NZ < (int64_t)1 << 31, "grid too large for int32 indices");
+        N = NX * NY * NZ;
+        DT = d.dt;
+        DH = d.dh;
+        L = visco() ? d.n_relax : 0;
+        ORACLE_REQUIRE(L <= WS_MAX_RELAX, "numRelaxationMechanisms more than 4 is not available here!");
+        ORACLE_REQUIRE(!visco() || L >= 1, "visco solvers need numRelaxationMechanisms >= 1");
+        auto mkf = [&](const std::string &n) { fld[n].assign(N, (T)0); };
+        switch (d.eq) {
+        case WS_EQ_ACOUSTIC:
+            mkf("VX"); mkf("VY"); if (d.dim == 3) mkf("VZ"); mkf("P");
+            break;
+        case WS_EQ_ELASTIC:
+        case WS_EQ_VISCOELASTIC:
+            mkf("VX"); mkf("VY"); mkf("Sxx"); mkf("Syy"); mkf("Sxy");
+            if (d.dim == 3) { mkf("VZ"); mkf("Szz"); mkf("Sxz"); mkf("Syz"); }
+            for (int l = 0; l < L; l++) {
+                mkf(Rn("Rxx", l)); mkf(Rn("Ryy", l)); mkf(Rn("Rxy", l));
+                if (d.dim == 3) { mkf(Rn("Rzz", l)); mkf(Rn("Rxz", l)); mkf(Rn("Ryz", l)); }
+            }
+            break;
+        case WS_EQ_SH:
+        case WS_EQ_VISCOSH:
+            ORACLE_REQUIRE(d.dim == 2, "sh is 2D only");
+            mkf("VZ"); mkf("Sxz"); mkf("Syz");
+            for (int l = 0; l < L; l++) { mkf(Rn("Rxz", l)); mkf(Rn("Ryz", l)); }
+            break;
+        case WS_EQ_TMEM:
+        case WS_EQ_VISCOTMEM:
+            ORACLE_REQUIRE(d.dim == 2, "tmem is 2D only");
+            mkf("HX"); mkf("HY"); mkf("EZ");
+            for (int l = 0; l < L; l++) mkf(Rn("RZ", l));
+            break;
+        case WS_EQ_EMEM:
+        case WS_EQ_VISCOEMEM:
+            mkf("HZ"); mkf("EX"); mkf("EY");
+            if (d.dim == 3) { mkf("HX"); mkf("HY"); mkf("EZ"); }
+            for (int l = 0; l < L; l++) {
+                mkf(Rn("RX", l)); mkf(Rn("RY", l));
+                if (d.dim == 3) mkf(Rn("RZ", l));
+            }
+            break;
+        default:
+            throw std::runtime_error("unknown equationType");
+        }
+    }
+
+    void prepare()
+    {
+        buildDerivatives();
+        if (seismic())
+            prepareModelSeismic();
+        else
+            prepareModelEM();
+        if (visco() && seismic()) {
+            // ForwardSolver3Dviscoelastic.cpp:55-66, :103-118
+            relaxationTime.clear(); inverseRelaxationTime.clear(); viscoCoeff1.clear(); viscoCoeff2.clear();
+            for (int l = 0; l < L; l++) {
+                relaxationTime.push_back((T)(1.0 / (2.0 * M_PI * d.relax_freq[l])));
+                inverseRelaxationTime.push_back((T)(1.0 / relaxationTime[l]));
+                viscoCoeff1.push_back((T)(1.0 - DT / (2.0 * relaxationTime[l])));
+                viscoCoeff2.push_back((T)(1.0 / (1.0 + DT / (2.0 * relaxationTime[l]))));
+            }
+            DThalf = (T)(DT / 2.0);
+            const vector<T> &tauS = M("tauS");
+            onePlusLtauS.resize(N);
+            VFOR(N) onePlusLtauS[i] = (T)1.0 + (T)L * tauS[i];
+            if (d.eq == WS_EQ_VISCOELASTIC) {
+                const vector<T> &tauP = M("tauP");
+                onePlusLtauP.resize(N);
+                VFOR(N) onePlusLtauP[i] = (T)1.0 + (T)L * tauP[i];
+            }
+        }
+        const bool emSolver = !seismic();
+        if (d.free_surface == 1 && !emSolver) {
+            initFreeSurface();
+            if (d.eq == WS_EQ_ELASTIC)
+                fsSetModelElastic();
+            if (d.eq == WS_EQ_VISCOELASTIC)
+                fsSetModelVisco();
+        }
+        if (d.damping == 1)
+            initABS();
+        if (d.damping == 2)
+            initCPML();
+        psi.clear();
+        update.assign(N, 0); update_temp.assign(N, 0); update2.assign(N, 0);
+        vxx.assign(N, 0); vyy.assign(N, 0); vzz.assign(N, 0);
+        prepared = true;
+    }
+
+    void reset()
+    {
+        for (auto &kv : fld)
+            std::fill(kv.second.begin(), kv.second.end(), (T)0);
+        for (auto &kv : psi)
+            std::fill(kv.second.begin(), kv.second.end(), (T)0);
+        std::fill(seis.begin(), seis.end(), (T)0);
+    }
+
+    // ------------------------------------------------------------------------------------------------------------
+    // sources / receivers (SourceReceiverImpl.cpp:12-37, FDTD3Delastic.cpp:12-53, FDTD2Delastic.cpp, FDTDacoustic.cpp,
+    // ForwardSolverEM/SourceReceiverImpl/SourceReceiverImplEM.cpp)
+    // ------------------------------------------------------------------------------------------------------------
+    void addAt(const char *f, Idx i, T v) { vector<T> &w = F(f); w[i] = w[i] + v; }
+    void applySource(Idx t)
+    {
+        const Idx ns = (Idx)srcIdx.size();
+        for (int type = 1; type <= 4; type++) // reference order: P, VX, VY, VZ (EZ, EX, EY, HZ)
+            for (Idx s = 0; s < ns; s++) {
+                if (srcType[s] != type)
+                    continue;
+                T v = srcSig[(size_t)s * d.nt + t];
+                Idx i = srcIdx[s];
+                if (seismic()) {
+                    switch (type) {
+                    case WS_TYPE_P:
+                        if (d.eq == WS_EQ_ACOUSTIC)
+                            addAt("P", i, v);
+                        else if (d.eq == WS_EQ_ELASTIC || d.eq == WS_EQ_VISCOELASTIC) {
+                            addAt("Sxx", i, v); addAt("Syy", i, v);
+                            if (d.dim == 3) addAt("Szz", i, v);
+                        } else
+                            throw std::runtime_error("Pressure sources can not be implemented in SH modeling");
+                        break;
+                    case WS_TYPE_VX:
+                        ORACLE_REQUIRE(d.eq != WS_EQ_SH && d.eq != WS_EQ_VISCOSH, "VX sources can not be implemented in SH modeling");
+                        addAt("VX", i, v);
+                        break;
+                    case WS_TYPE_VY:
+                        ORACLE_REQUIRE(d.eq != WS_EQ_SH && d.eq != WS_EQ_VISCOSH, "VY sources can not be implemented in SH modeling");
+                        addAt("VY", i, v);
+                        break;
+                    case WS_TYPE_VZ:
+                        ORACLE_REQUIRE(fld.count("VZ"), "no VZ wavefield in this modelling");
+                        addAt("VZ", i, v);
+                        break;
+                    }
+                } else {
+                    static const char *nm[5] = {"", "EZ", "EX", "EY", "HZ"};
+                    ORACLE_REQUIRE(fld.count(nm[type]), std::string("no ") + nm[type] + " wavefield in this modelling");
+                    addAt(nm[type], i, v);
+                }
+            }
+    }
+    void gatherSeismogram(Idx t)
+    {
+        const Idx nr = (Idx)recIdx.size();
+        for (Idx r = 0; r < nr; r++) {
+            Idx i = recIdx[r];
+            T v = 0;
+            const int type = recType[r];
+            if (seismic()) {
+                switch (type) {
+                case WS_TYPE_P:
+                    if (d.eq == WS_EQ_ACOUSTIC)
+                        v = F("P")[i] * (T)1;
+                    else if (d.eq == WS_EQ_ELASTIC || d.eq == WS_EQ_VISCOELASTIC) {
+                        if (d.dim == 3) {
+                            v = F("Sxx")[i];
+                            v = v + F("Syy")[i];
+                            v = v + F("Szz")[i];
+                            v = v / (T)3;
+                        } else {
+                            v = F("Sxx")[i];
+                            v = v + F("Syy")[i];
+                            v = v * (T)0.5;
+                        }
+                    } else
+                        throw std::runtime_error("Pressure receivers can not be implemented in SH modeling");
+                    break;
+                case WS_TYPE_VX: v = F("VX")[i]; break;
+                case WS_TYPE_VY: v = F("VY")[i]; break;
+                case WS_TYPE_VZ: v = F("VZ")[i]; break;
+                default: throw std::runtime_error("unknown receiver type");
+                }
+            } else {
+                static const char *nm[5] = {"", "EZ", "EX", "EY", "HZ"};
+                ORACLE_REQUIRE(type >= 1 && type <= 4, "unknown receiver type");
+                v = F(nm[type])[i];
+            }
+            seis[(size_t)r * d.nt + t] = v;
+        }
+    }
+
+    // ------------------------------------------------------------------------------------------------------------
+    // time steps — one statement per reference statement
+    // ------------------------------------------------------------------------------------------------------------
+    void absApply(std::initializer_list<const char *> names)
+    {
+        if (d.damping != 1)
+            return;
+        for (const char *n : names)
+            vmul(F(n), damping);
+    }
+
+    // ForwardSolver3Dacoustic.cpp:131-229, ForwardSolver2Dacoustic.cpp:121-193
+    void stepAcoustic(Idx t)
+    {
+        const bool fs = d.free_surface == 1, d3 = d.dim == 3;
+        vector<T> &p = F("P"), &vX = F("VX"), &vY = F("VY");
+        spmv(Dxf, p, update);
+        applyCPML(update, "p_x", px, true);
+        vmul(update, M("inverseDensityAverageX"));
+        vadd(vX, update);
+        spmv(fs ? DyfFS : Dyf, p, update);
+        applyCPML(update, "p_y", py, true);
+        vmul(update, M("inverseDensityAverageY"));
+        vadd(vY, update);
+        if (d3) {
+            spmv(Dzf, p, update);
+            applyCPML(update, "p_z", pz, true);
+            vmul(update, M("inverseDensityAverageZ"));
+            vadd(F("VZ"), update);
+        }
+        spmv(Dxb, vX, update);
+        applyCPML(update, "vxx", px, false);
+        spmv(Dyb, vY, update_temp);
+        applyCPML(update_temp, "vyy", py, false);
+        vadd(update, update_temp);
+        if (d3) {
+            spmv(Dzb, F("VZ"), update_temp);
+            applyCPML(update_temp, "vzz", pz, false);
+            vadd(update, update_temp);
+        }
+        vmul(update, M("pWaveModulus"));
+        vadd(p, update);
+        if (d3)
+            absApply({"P", "VX", "VY", "VZ"});
+        else
+            absApply({"P", "VX", "VY"});
+        if (fs)
+            setSurfaceZero(p);
+        applySource(t);
+        gatherSeismogram(t);
+    }
+
+    // velocity half-step shared by elastic and viscoelastic
+    // ForwardSolver3Delastic.cpp:181-277, ForwardSolver2Delastic.cpp:163-208, ForwardSolver3Dviscoelastic.cpp:188-262
+    void velocityElastic()
+    {
+        const bool fs = d.free_surface == 1, d3 = d.dim == 3;
+        vector<T> &vX = F("VX"), &vY = F("VY");
+        vector<T> &Sxx = F("Sxx"), &Syy = F("Syy"), &Sxy = F("Sxy");
+        // vx
+        spmv(Dxf, Sxx, update);
+        applyCPML(update, "sxx_x", px, true);
+        spmv(fs ? DybFS : Dyb, Sxy, update_temp);
+        applyCPML(update_temp, "sxy_y", py, false);
+        vadd(update, update_temp);
+        if (d3) {
+            spmv(Dzb, F("Sxz"), update_temp);
+            applyCPML(update_temp, "sxz_z", pz, false);
+            vadd(update, update_temp);
+        }
+        vmul(update, M("inverseDensityAverageX"));
+        vadd(vX, update);
+        // vy
+        spmv(Dxb, Sxy, update);
+        applyCPML(update, "sxy_x", px, false);
+        spmv(fs ? DyfFS : Dyf, Syy, update_temp);
+        applyCPML(update_temp, "syy_y", py, true);
+        vadd(update, update_temp);
+        if (d3) {
+            spmv(Dzb, F("Syz"), update_temp);
+            applyCPML(update_temp, "syz_z", pz, false);
+            vadd(update, update_temp);
+        }
+        vmul(update, M("inverseDensityAverageY"));
+        vadd(vY, update);
+        // vz
+        if (d3) {
+            vector<T> &vZ = F("VZ");
+            spmv(Dxb, F("Sxz"), update);
+            applyCPML(update, "sxz_x", px, false);
+            spmv(fs ? DybFS : Dyb, F("Syz"), update_temp);
+            applyCPML(update_temp, "syz_y", py, false);
+            vadd(update, update_temp);
+            spmv(Dzf, F("Szz"), update_temp);
+            applyCPML(update_temp, "szz_z", pz, true);
+            vadd(update, update_temp);
+            vmul(update, M("inverseDensityAverageZ"));
+            vadd(vZ, update);
+        }
+    }
+
+    void normalStrainRates()
+    {
+        const bool d3 = d.dim == 3;
+        spmv(Dxb, F("VX"), vxx);
+        spmv(Dyb, F("VY"), vyy);
+        if (d3)
+            spmv(Dzb, F("VZ"), vzz);
+        applyCPML(vxx, "vxx", px, false);
+        applyCPML(vyy, "vyy", py, false);
+        if (d3)
+            applyCPML(vzz, "vzz", pz, false);
+    }
+
+    // ForwardSolver3Delastic.cpp:120-414, ForwardSolver2Delastic.cpp:117-294
+    void stepElastic(Idx t)
+    {
+        const bool fs = d.free_surface == 1, d3 = d.dim == 3;
+        velocityElastic();
+        vector<T> &Sxx = F("Sxx"), &Syy = F("Syy"), &Sxy = F("Sxy");
+        const vector<T> &pw = M("pWaveModulus"), &sw = M("sWaveModulus");
+        normalStrainRates();
+        if (d3) {
+            vector<T> &Szz = F("Szz");
+            vset(update, vxx);
+            vadd(update, vyy);
+            vadd(update, vzz);
+            vmul(update, pw);
+            vadd(Sxx, update);
+            vadd(Syy, update);
+            vadd(Szz, update);
+            vsum(update, vyy, vzz);
+            vmul(update, sw);
+            vaxmy(Sxx, (T)2.0, update);
+            vsum(update, vxx, vzz);
+            vmul(update, sw);
+            vaxmy(Syy, (T)2.0, update);
+            vsum(update, vxx, vyy);
+            vmul(update, sw);
+            vaxmy(Szz, (T)2.0, update);
+        } else {
+            vset(update, vxx);
+            vadd(update, vyy);
+            vmul(update, pw);
+            vadd(Sxx, update);
+            vadd(Syy, update);
+            vset(update, vyy);
+            vmul(update, sw);
+            vaxmy(Sxx, (T)2.0, update);
+            vset(update, vxx);
+            vmul(update, sw);
+            vaxmy(Syy, (T)2.0, update);
+        }
+        // shear
+        spmv(Dyf, F("VX"), update);
+        applyCPML(update, "vxy", py, true);
+        spmv(Dxf, F("VY"), update_temp);
+        applyCPML(update_temp, "vyx", px, true);
+        vadd(update, update_temp);
+        vmul(update, M("sWaveModulusAverageXY"));
+        vadd(Sxy, update);
+        if (d3) {
+            spmv(Dzf, F("VX"), update);
+            applyCPML(update, "vxz", pz, true);
+            spmv(Dxf, F("VZ"), update_temp);
+            applyCPML(update_temp, "vzx", px, true);
+            vadd(update, update_temp);
+            vmul(update, M("sWaveModulusAverageXZ"));
+            vadd(F("Sxz"), update);
+
+            spmv(Dzf, F("VY"), update);
+            applyCPML(update, "vyz", pz, true);
+            spmv(Dyf, F("VZ"), update_temp);
+            applyCPML(update_temp, "vzy", py, true);
+            vadd(update, update_temp);
+            vmul(update, M("sWaveModulusAverageYZ"));
+            vadd(F("Syz"), update);
+        }
+        if (fs) {
+            // FreeSurface3Delastic.cpp:15-47 / FreeSurface2Delastic.cpp:14-46
+            if (d3) {
+                vsum(update, vxx, vzz);
+                setSurfaceZero(Syy);
+                vector<T> &Szz = F("Szz");
+                for (size_t k = 0; k < surfIdx.size(); k++) {
+                    Idx i = surfIdx[k];
+                    T temp = sH[k] * update[i];
+                    Sxx[i] = Sxx[i] + temp;
+                    Szz[i] = Szz[i] + temp;
+                    temp = sV[k] * vyy[i];
+                    Sxx[i] = Sxx[i] - temp;
+                    Szz[i] = Szz[i] - temp;
+                }
+            } else {
+                for (size_t k = 0; k < surfIdx.size(); k++) {
+                    Idx i = surfIdx[k];
+                    T temp = sH[k] * vxx[i];
+                    Sxx[i] = Sxx[i] + temp;
+                    temp = sV[k] * vyy[i];
+                    Sxx[i] = Sxx[i] - temp;
+                }
+                setSurfaceZero(Syy);
+            }
+        }
+        if (d3)
+            absApply({"Sxx", "Syy", "Szz", "Sxy", "Sxz", "Syz", "VX", "VY", "VZ"});
+        else
+            absApply({"Sxx", "Syy", "Sxy", "VX", "VY"});
+        applySource(t);
+        gatherSeismogram(t);
+    }
+
+    // one shear component of the viscoelastic update, ForwardSolver3Dviscoelastic.cpp:355-416
+    void viscoShear(vector<T> &S, const char *Rbase, const vector<T> &muAvg, const vector<T> &tauAvg)
+    {
+        vmul(update, muAvg);
+        for (int l = 0; l < L; l++) {
+            vector<T> &R = F(Rn(Rbase, l));
+            vaxpy(S, DThalf, R);
+            vscale(R, viscoCoeff1[l]);
+            vscaled(update2, inverseRelaxationTime[l], update);
+            vmul(update2, tauAvg);
+            vsub(R, update2);
+            vscale(R, viscoCoeff2[l]);
+            vaxpy(S, DThalf, R);
+        }
+        vmul(update, onePlusLtauS);
+        vadd(S, update);
+    }
+    // one normal component, second half: ForwardSolver3Dviscoelastic.cpp:307-352
+    void viscoNormalShearPart(vector<T> &S, const char *Rbase)
+    {
+        vmul(update, M("sWaveModulus"));
+        vscale(update, (T)2.0);
+        for (int l = 0; l < L; l++) {
+            vector<T> &R = F(Rn(Rbase, l));
+            vscaled(update2, inverseRelaxationTime[l], update);
+            vmul(update2, M("tauS"));
+            vadd(R, update2);
+            vscale(R, viscoCoeff2[l]);
+            vaxpy(S, DThalf, R);
+        }
+        vmul(update, onePlusLtauS);
+        vsub(S, update);
+    }
+
+    // ForwardSolver3Dviscoelastic.cpp:132-454, ForwardSolver2Dviscoelastic.cpp:130-318
+    void stepViscoelastic(Idx t)
+    {
+        const bool fs = d.free_surface == 1, d3 = d.dim == 3;
+        velocityElastic();
+        vector<T> &Sxx = F("Sxx"), &Syy = F("Syy"), &Sxy = F("Sxy");
+        normalStrainRates();
+        vset(update, vxx);
+        vadd(update, vyy);
+        if (d3)
+            vadd(update, vzz);
+        vmul(update, M("pWaveModulus"));
+        for (int l = 0; l < L; l++) {
+            vscaled(update2, inverseRelaxationTime[l], update);
+            vmul(update2, M("tauP"));
+            vaxpy(Sxx, DThalf, F(Rn("Rxx", l)));
+            vscale(F(Rn("Rxx", l)), viscoCoeff1[l]);
+            vsub(F(Rn("Rxx", l)), update2);
+            vaxpy(Syy, DThalf, F(Rn("Ryy", l)));
+            vscale(F(Rn("Ryy", l)), viscoCoeff1[l]);
+            vsub(F(Rn("Ryy", l)), update2);
+            if (d3) {
+                vaxpy(F("Szz"), DThalf, F(Rn("Rzz", l)));
+                vscale(F(Rn("Rzz", l)), viscoCoeff1[l]);
+                vsub(F(Rn("Rzz", l)), update2);
+            }
+        }
+        vmul(update, onePlusLtauP);
+        vadd(Sxx, update);
+        vadd(Syy, update);
+        if (d3)
+            vadd(F("Szz"), update);
+        if (d3) {
+            vsum(update, vyy, vzz);
+            viscoNormalShearPart(Sxx, "Rxx");
+            vsum(update, vxx, vzz);
+            viscoNormalShearPart(Syy, "Ryy");
+            vsum(update, vxx, vyy);
+            viscoNormalShearPart(F("Szz"), "Rzz");
+        } else {
+            vset(update, vyy);
+            viscoNormalShearPart(Sxx, "Rxx");
+            vset(update, vxx);
+            viscoNormalShearPart(Syy, "Ryy");
+        }
+        // shear
+        spmv(Dyf, F("VX"), update);
+        applyCPML(update, "vxy", py, true);
+        spmv(Dxf, F("VY"), update_temp);
+        applyCPML(update_temp, "vyx", px, true);
+        vadd(update, update_temp);
+        viscoShear(Sxy, "Rxy", M("sWaveModulusAverageXY"), M("tauSAverageXY"));
+        if (d3) {
+            spmv(Dzf, F("VX"), update);
+            applyCPML(update, "vxz", pz, true);
+            spmv(Dxf, F("VZ"), update_temp);
+            applyCPML(update_temp, "vzx", px, true);
+            vadd(update, update_temp);
+            viscoShear(F("Sxz"), "Rxz", M("sWaveModulusAverageXZ"), M("tauSAverageXZ"));
+            spmv(Dzf, F("VY"), update);
+            applyCPML(update, "vyz", pz, true);
+            spmv(Dyf, F("VZ"), update_temp);
+            applyCPML(update_temp, "vzy", py, true);
+            vadd(update, update_temp);
+            viscoShear(F("Syz"), "Ryz", M("sWaveModulusAverageYZ"), M("tauSAverageYZ"));
+        }
+        if (fs) {
+            // FreeSurface3Dviscoelastic.cpp:17-75, FreeSurface2Dviscoelastic.cpp:15-63
+            if (d3)
+                vsum(update, vxx, vzz);
+            const vector<T> &hor = d3 ? update : vxx;
+            const int ncomp = d3 ? 2 : 1;
+            vector<T> *S[2] = {&Sxx, d3 ? &F("Szz") : nullptr};
+            const char *Rb[2] = {"Rxx", "Rzz"};
+            for (size_t k = 0; k < surfIdx.size(); k++) {
+                Idx i = surfIdx[k];
+                for (int l = 0; l < L; l++)
+                    for (int c = 0; c < ncomp; c++) {
+                        T temp = (T)1 * F(Rn(Rb[c], l))[i];
+                        (*S[c])[i] = (*S[c])[i] - DThalf * temp;
+                    }
+                T temp = sSH[k] * hor[i];
+                for (int c = 0; c < ncomp; c++)
+                    (*S[c])[i] = (*S[c])[i] + temp;
+                temp = sSV[k] * vyy[i];
+                for (int c = 0; c < ncomp; c++)
+                    (*S[c])[i] = (*S[c])[i] - temp;
+                for (int l = 0; l < L; l++) {
+                    T th = sRH[l][k] * hor[i];
+                    for (int c = 0; c < ncomp; c++) {
+                        vector<T> &R = F(Rn(Rb[c], l));
+                        R[i] = R[i] + th;
+                    }
+                    T tv = sRV[l][k] * vyy[i];
+                    for (int c = 0; c < ncomp; c++) {
+                        vector<T> &R = F(Rn(Rb[c], l));
+                        R[i] = R[i] - tv;
+                    }
+                    for (int c = 0; c < ncomp; c++) {
+                        T tt = (T)1 * F(Rn(Rb[c], l))[i];
+                        (*S[c])[i] = (*S[c])[i] + DThalf * tt;
+                    }
+                }
+            }
+            setSurfaceZero(Syy);
+            for (int l = 0; l < L; l++)
+                setSurfaceZero(F(Rn("Ryy", l)));
+        }
+        if (d3)
+            absApply({"Sxx", "Syy", "Szz", "Sxy", "Sxz", "Syz", "VX", "VY", "VZ"});
+        else
+            absApply({"Sxx", "Syy", "Sxy", "VX", "VY"});
+        applySource(t);
+        gatherSeismogram(t);
+    }
+
+    // ForwardSolver2Dsh.cpp:108-193, ForwardSolver2Dviscosh.cpp:126-241
+    void stepSH(Idx t)
+    {
+        const bool fs = d.free_surface == 1;
+        vector<T> &vZ = F("VZ"), &Sxz = F("Sxz"), &Syz = F("Syz");
+        spmv(Dxb, Sxz, update);
+        spmv(fs ? DybFS : Dyb, Syz, update_temp);
+        applyCPML(update, "sxz_x", px, false);
+        applyCPML(update_temp, "syz_y", py, false);
+        vadd(update, update_temp);
+        vmul(update, M("inverseDensity"));
+        vadd(vZ, update);
+        spmv(Dxf, vZ, update);
+        applyCPML(update, "vzx", px, true);
+        if (d.eq == WS_EQ_SH) {
+            vmul(update, M("sWaveModulusAverageXZ"));
+            vadd(Sxz, update);
+        } else
+            viscoShear(Sxz, "Rxz", M("sWaveModulusAverageXZ"), M("tauSAverageXZ"));
+        spmv(Dyf, vZ, update);
+        applyCPML(update, "vzy", py, true);
+        if (d.eq == WS_EQ_SH) {
+            vmul(update, M("sWaveModulusAverageYZ"));
+            vadd(Syz, update);
+        } else
+            viscoShear(Syz, "Ryz", M("sWaveModulusAverageYZ"), M("tauSAverageYZ"));
+        absApply({"Sxz", "Syz", "VZ"});
+        applySource(t);
+        gatherSeismogram(t);
+    }
+
+    // ForwardSolver2Dtmem.cpp:108-171, ForwardSolver2Dviscotmem.cpp:130-207; CPML map CPMLEM2D.cpp:21-73
+    void stepTMEM(Idx t)
+    {
+        vector<T> &hX = F("HX"), &hY = F("HY"), &eZ = F("EZ");
+        spmv(Dyf, eZ, update);
+        applyCPML(update, "ezy", py, true);
+        vmul(update, M("inverseMagneticPermeabilityAverageYZ"));
+        vsub(hX, update);
+        spmv(Dxf, eZ, update_temp);
+        applyCPML(update_temp, "ezx", px, true);
+        vscaled(update, (T)-1, update_temp);
+        vmul(update, M("inverseMagneticPermeabilityAverageXZ"));
+        vsub(hY, update);
+        for (int l = 0; l < L; l++) {
+            vector<T> &r = F(Rn("RZ", l));
+            vscaled(update, Cc[l], r);
+            vset(update_temp, M("CdAverageZ" + std::to_string(l + 1)));
+            vmul(update_temp, eZ);
+            vsum(r, update_temp, update);
+        }
+        spmv(Dxb, hY, update);
+        spmv(Dyb, hX, update_temp);
+        applyCPML(update, "hyx", px, false);
+        applyCPML(update_temp, "hxy", py, false);
+        vsub(update, update_temp);
+        for (int l = 0; l < L; l++)
+            vaxmy(update, DT, F(Rn("RZ", l)));
+        vmul(update, M("CbAverageZ"));
+        vset(update_temp, M("CaAverageZ"));
+        vmul(update_temp, eZ);
+        vsum(eZ, update_temp, update);
+        absApply({"EZ", "HX", "HY"});
+        applySource(t);
+        gatherSeismogram(t);
+    }
+
+    // r_l = Cc_l * r_l + Cd_l (.) e   (ForwardSolver2Dviscoemem.cpp:186-193, ForwardSolver3Dviscoemem.cpp:236-246)
+    void relaxEM(const char *Rbase, const char *CdBase, const vector<T> &e)
+    {
+        for (int l = 0; l < L; l++) {
+            vector<T> &r = F(Rn(Rbase, l));
+            vscaled(update, Cc[l], r);
+            vset(update_temp, M(std::string(CdBase) + std::to_string(l + 1)));
+            vmul(update_temp, e);
+            vsum(r, update_temp, update);
+        }
+    }
+    // e = Ca (.) e + Cb (.) (update - DT * sum_l r_l)
+    void updateE(vector<T> &e, const char *Rbase, const char *Ca, const char *Cb)
+    {
+        for (int l = 0; l < L; l++)
+            vaxmy(update, DT, F(Rn(Rbase, l)));
+        vmul(update, M(Cb));
+        vset(update_temp, M(Ca));
+        vmul(update_temp, e);
+        vsum(e, update_temp, update);
+    }
+
+    // ForwardSolver2Demem.cpp:112-176, ForwardSolver2Dviscoemem.cpp:142-228; CPML map CPMLEM2D.cpp:21-73
+    void stepEMEM2D(Idx t)
+    {
+        vector<T> &hZ = F("HZ"), &eX = F("EX"), &eY = F("EY");
+        spmv(Dxf, eY, update);
+        spmv(Dyf, eX, update_temp);
+        applyCPML(update, "eyx", px, true);
+        applyCPML(update_temp, "exy", py, true);
+        vsub(update, update_temp);
+        vmul(update, M("inverseMagneticPermeabilityAverageXY"));
+        vsub(hZ, update);
+        for (int l = 0; l < L; l++) { // interleaved X/Y per mechanism as in the reference
+            vector<T> &rx = F(Rn("RX", l)), &ry = F(Rn("RY", l));
+            vscaled(update, Cc[l], rx);
+            vset(update_temp, M("CdAverageX" + std::to_string(l + 1)));
+            vmul(update_temp, eX);
+            vsum(rx, update_temp, update);
+            vscaled(update, Cc[l], ry);
+            vset(update_temp, M("CdAverageY" + std::to_string(l + 1)));
+            vmul(update_temp, eY);
+            vsum(ry, update_temp, update);
+        }
+        spmv(Dyb, hZ, update);
+        applyCPML(update, "hzy", py, false);
+        updateE(eX, "RX", "CaAverageX", "CbAverageX");
+        // non-visco: eY = Ca*eY - Cb*(Dxb hZ); visco: update = -(Dxb hZ) - DT*r; eY = Ca*eY + Cb*update  (bit-identical forms)
+        spmv(Dxb, hZ, update_temp);
+        applyCPML(update_temp, "hzx", px, false);
+        vscaled(update, (T)-1, update_temp);
+        updateE(eY, "RY", "CaAverageY", "CbAverageY");
+        absApply({"EY", "EX", "HZ"});
+        applySource(t);
+        gatherSeismogram(t);
+    }
+
+    // ForwardSolver3Demem.cpp:119-240, ForwardSolver3Dviscoemem.cpp:161-312; CPML map CPMLEM3D.cpp:27-104
+    // (all E-derivatives use the half profile; H-derivatives the full profile except hyx, CPMLEM3D.cpp:69)
+    void stepEMEM3D(Idx t)
+    {
+        vector<T> &hX = F("HX"), &hY = F("HY"), &hZ = F("HZ"), &eX = F("EX"), &eY = F("EY"), &eZ = F("EZ");
+        spmv(Dyf, eZ, update);
+        spmv(Dzf, eY, update_temp);
+        applyCPML(update, "ezy", py, true);
+        applyCPML(update_temp, "eyz", pz, true);
+        vsub(update, update_temp);
+        vmul(update, M("inverseMagneticPermeabilityAverageYZ"));
+        vsub(hX, update);
+        spmv(Dzf, eX, update);
+        spmv(Dxf, eZ, update_temp);
+        applyCPML(update, "exz", pz, true);
+        applyCPML(update_temp, "ezx", px, true);
+        vsub(update, update_temp);
+        vmul(update, M("inverseMagneticPermeabilityAverageXZ"));
+        vsub(hY, update);
+        spmv(Dxf, eY, update);
+        spmv(Dyf, eX, update_temp);
+        applyCPML(update, "eyx", px, true);
+        applyCPML(update_temp, "exy", py, true);
+        vsub(update, update_temp);
+        vmul(update, M("inverseMagneticPermeabilityAverageXY"));
+        vsub(hZ, update);
+        for (int l = 0; l < L; l++) {
+            const char *rb[3] = {"RX", "RY", "RZ"};
+            const char *cd[3] = {"CdAverageX", "CdAverageY", "CdAverageZ"};
+            vector<T> *e[3] = {&eX, &eY, &eZ};
+            for (int c = 0; c < 3; c++) {
+                vector<T> &r = F(Rn(rb[c], l));
+                vscaled(update, Cc[l], r);
+                vset(update_temp, M(std::string(cd[c]) + std::to_string(l + 1)));
+                vmul(update_temp, *e[c]);
+                vsum(r, update_temp, update);
+            }
+        }
+        spmv(Dyb, hZ, update);
+        spmv(Dzb, hY, update_temp);
+        applyCPML(update, "hzy", py, false);
+        applyCPML(update_temp, "hyz", pz, false);
+        vsub(update, update_temp);
+        updateE(eX, "RX", "CaAverageX", "CbAverageX");
+        spmv(Dzb, hX, update);
+        spmv(Dxb, hZ, update_temp);
+        applyCPML(update, "hxz", pz, false);
+        applyCPML(update_temp, "hzx", px, false);
+        vsub(update, update_temp);
+        updateE(eY, "RY", "CaAverageY", "CbAverageY");
+        spmv(Dxb, hY, update);
+        spmv(Dyb, hX, update_temp);
+        applyCPML(update, "hyx", px, true);
+        applyCPML(update_temp, "hxy", py, false);
+        vsub(update, update_temp);
+        updateE(eZ, "RZ", "CaAverageZ", "CbAverageZ");
+        absApply({"EZ", "EY", "EX", "HX", "HY", "HZ"});
+        applySource(t);
+        gatherSeismogram(t);
+    }
+
+    void step(Idx t)
+    {
+        ORACLE_REQUIRE(prepared, "call prepare before step");
+        ORACLE_REQUIRE(t >= 0 && t < d.nt, "time step out of range");
+        switch (d.eq) {
+        case WS_EQ_ACOUSTIC: stepAcoustic(t); break;
+        case WS_EQ_ELASTIC: stepElastic(t); break;
+        case WS_EQ_VISCOELASTIC: stepViscoelastic(t); break;
+        case WS_EQ_SH:
+        case WS_EQ_VISCOSH: stepSH(t); break;
+        case WS_EQ_TMEM:
+        case WS_EQ_VISCOTMEM: stepTMEM(t); break;
+        case WS_EQ_EMEM:
+        case WS_EQ_VISCOEMEM:
+            if (d.dim == 3)
+                stepEMEM3D(t);
+            else
+                stepEMEM2D(t);
+            break;
+        default: throw std::runtime_error("unknown equationType");
+        }
+    }
+};
+
+struct Handle {
+    int precision = 32;
+    std::unique_ptr<Oracle<float>> f;
+    std::unique_ptr<Oracle<double>> dd;
+};
+
+template <typename F>
+int guard(F fn)
+{
+    try {
+        fn();
+        return WS_OK;
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return WS_EINVAL;
+    }
+}
+
+template <typename T>
+void setVec(vector<T> &dst, const float *src, size_t n)
+{
+    dst.resize(n);
+    for (size_t i = 0; i < n; i++)
+        dst[i] = (T)src[i];
+}
+template <typename T>
+void getVec(const vector<T> &src, float *dst, size_t n)
+{
+    ORACLE_REQUIRE(src.size() == n, "size mismatch");
+    for (size_t i = 0; i < n; i++)
+        dst[i] = (float)src[i];
+}
+
+} // namespace
+
+#define DISPATCH(h, expr)                                                                                              \
+    do {                                                                                                               \
+        if ((h)->precision == 64) {                                                                                    \
+            auto &o = *(h)->dd;                                                                                        \
+            expr;                                                                                                      \
+        } else {                                                                                                       \
+            auto &o = *(h)->f;                                                                                         \
+            expr;                                                                                                      \
+        }                                                                                                              \
+    } while (0)
+
+extern "C" {
+
+struct wso_solver;
+
+const char *wso_last_error(void) { return g_err.c_str(); }
+
+// precision: 32 (reference build, ValueType = float, Configuration/ValueType.hpp:5) or 64 (accuracy yardstick)
+int wso_create(const ws_desc *desc, int precision, wso_solver **out)
+{
+    return guard([&] {
+        ORACLE_REQUIRE(desc && out, "null argument");
+        ORACLE_REQUIRE(precision == 32 || precision == 64, "precision must be 32 or 64");
+        auto h = std::make_unique<Handle>();
+        h->precision = precision;
+        if (precision == 64) {
+            h->dd = std::make_unique<Oracle<double>>();
+            h->dd->create(*desc);
+        } else {
+            h->f = std::make_unique<Oracle<float>>();
+            h->f->create(*desc);
+        }
+        *out = reinterpret_cast<wso_solver *>(h.release());
+    });
+}
+void wso_destroy(wso_solver *s) { delete reinterpret_cast<Handle *>(s); }
+
+int wso_set_material(wso_solver *s, const char *name, const float *host, size_t n)
+{
+    Handle *h = reinterpret_cast<Handle *>(s);
+    return guard([&] { DISPATCH(h, { ORACLE_REQUIRE(n == (size_t)o.N, "material size mismatch"); setVec(o.mat[name], host, n); o.prepared = false; }); });
+}
+int wso_get_material(wso_solver *s, const char *name, float *host, size_t n)
+{
+    Handle *h = reinterpret_cast<Handle *>(s);
+    return guard([&] { DISPATCH(h, getVec(o.M(name), host, n)); });
+}
+int wso_prepare(wso_solver *s)
+{
+    Handle *h = reinterpret_cast<Handle *>(s);
+    return guard([&] { DISPATCH(h, o.prepare()); });
+}
+int wso_set_sources(wso_solver *s, int32_t n, const int32_t *type, const int32_t *idx, const float *sig)
+{
+    Handle *h = reinterpret_cast<Handle *>(s);
+    return guard([&] {
+        DISPATCH(h, {
+            o.srcType.assign(type, type + n);
+            o.srcIdx.assign(idx, idx + n);
+            for (int32_t k = 0; k < n; k++)
+                ORACLE_REQUIRE(idx[k] >= 0 && idx[k] < o.N, "source index out of range");
+            setVec(o.srcSig, sig, (size_t)n * o.d.nt);
+        });
+    });
+}
+int wso_set_receivers(wso_solver *s, int32_t n, const int32_t *type, const int32_t *idx)
+{
+    Handle *h = reinterpret_cast<Handle *>(s);
+    return guard([&] {
+        DISPATCH(h, {
+            o.recType.assign(type, type + n);
+            o.recIdx.assign(idx, idx + n);
+            for (int32_t k = 0; k < n; k++)
+                ORACLE_REQUIRE(idx[k] >= 0 && idx[k] < o.N, "receiver index out of range");
+            o.seis.assign((size_t)n * o.d.nt, 0);
+        });
+    });
+}
+int wso_reset(wso_solver *s)
+{
+    Handle *h = reinterpret_cast<Handle *>(s);
+    return guard([&] { DISPATCH(h, o.reset()); });
+}
+int wso_step(wso_solver *s, int32_t t)
+{
+    Handle *h = reinterpret_cast<Handle *>(s);
+    return guard([&] { DISPATCH(h, o.step(t)); });
+}
+int wso_run(wso_solver *s, int32_t t0, int32_t t1)
+{
+    Handle *h = reinterpret_cast<Handle *>(s);
+    return guard([&] {
+        for (int32_t t = t0; t < t1; t++)
+            DISPATCH(h, o.step(t));
+    });
+}
+int wso_get_seismogram(wso_solver *s, float *host)
+{
+    Handle *h = reinterpret_cast<Handle *>(s);
+    return guard([&] { DISPATCH(h, getVec(o.seis, host, o.seis.size())); });
+}
+int wso_get_wavefield(wso_solver *s, const char *comp, float *host, size_t n)
+{
+    Handle *h = reinterpret_cast<Handle *>(s);
+    return guard([&] { DISPATCH(h, getVec(o.F(comp), host, n)); });
+}
+int wso_set_wavefield(wso_solver *s, const char *comp, const float *host, size_t n)
+{
+    Handle *h = reinterpret_cast<Handle *>(s);
+    return guard([&] { DISPATCH(h, { ORACLE_REQUIRE(n == (size_t)o.N, "size mismatch"); setVec(o.F(comp), host, n); }); });
+}
+
+// Row `row` of a derivative matrix as dense taps (for checking the product's coefficient tables):
+// which: 0 Dxf 1 Dxb 2 Dyf 3 Dyb 4 Dzf 5 Dzb 6 DyfFreeSurface 7 DybFreeSurface.  Returns nnz, cols/vals need >= 16 entries.
+int wso_deriv_row(wso_solver *s, int which, int32_t row, int32_t *cols, float *vals)
+{
+    Handle *h = reinterpret_cast<Handle *>(s);
+    int nnz = -1;
+    int rc = guard([&] {
+        DISPATCH(h, {
+            ORACLE_REQUIRE(o.prepared, "call prepare first");
+            auto *A = &o.Dxf;
+            switch (which) {
+            case 0: A = &o.Dxf; break;
+            case 1: A = &o.Dxb; break;
+            case 2: A = &o.Dyf; break;
+            case 3: A = &o.Dyb; break;
+            case 4: A = &o.Dzf; break;
+            case 5: A = &o.Dzb; break;
+            case 6: A = &o.DyfFS; break;
+            case 7: A = &o.DybFS; break;
+            default: throw std::runtime_error("bad matrix id");
+            }
+            ORACLE_REQUIRE(!A->empty(), "matrix not built for this configuration");
+            ORACLE_REQUIRE(row >= 0 && row < A->n, "row out of range");
+            nnz = (int)(A->ia[row + 1] - A->ia[row]);
+            for (int k = 0; k < nnz; k++) {
+                cols[k] = A->ja[A->ia[row] + k];
+                vals[k] = (float)A->va[A->ia[row] + k];
+            }
+        });
+    });
+    return rc == WS_OK ? nnz : rc;
+}
+
+// Wavelets (Acquisition/SourceSignal/*.cpp), evaluated like the reference in ValueType = float.
+// shape: 1 Ricker (Ricker.cpp:29-53), 7 Ricker_GprMax
+int wso_wavelet(int shape, int32_t nt, float dt, float fc, float amp, float tshift, float *out)
+{
+    return guard([&] {
+        ORACLE_REQUIRE(nt > 0 && dt > 0 && fc > 0, "NT, DT, FC must be positive");
+        if (shape == 1) {
+            float help = (float)(1.5 / fc + tshift);
+            float w = (float)(M_PI * fc);
+            for (int32_t k = 0; k < nt; k++) {
+                float t = 0.0f + (float)k * dt;
+                float tau = t - help;
+                tau = tau * w;
+                float h2 = tau * tau;
+                float e = std::exp(-1.0f * h2);
+                float hh = 1.0f - 2.0f * h2;
+                out[k] = (amp * hh) * e;
+            }
+        } else
+            throw std::runtime_error("Unknown wavelet shape ");
+    });
+}
+
+int wso_num_threads(void)
+{
+    int n = 1;
+#ifdef _OPENMP
+#pragma omp parallel
+    {
+#pragma omp master
+        n = omp_get_num_threads();
+    }
+#endif
+    return n;
+}
+}
