@@ -137,6 +137,10 @@ uint64_t ws_launch_count(const ws_solver *s);
  * which = 0 first half-step kernel (velocity / H), 1 second half-step kernel (stress / E), 2 whole step         */
 int ws_last_timing(ws_solver *s, int which, float *ms);
 void *ws_stream(ws_solver *s); /* cudaStream_t the kernels are launched on */
+/* enable = 1: ws_run launches directly and brackets both half-step kernels of every step with CUDA events */
+int ws_set_timing(ws_solver *s, int enable);
+/* 1 if the tiled TMA kernels (not the general per-point kernels) serve this configuration */
+int ws_uses_fast_kernels(const ws_solver *s);
 
 #ifdef __cplusplus
 }

@@ -16,6 +16,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_SO = os.path.join(ROOT, "oracle", "_ref", "libwave_oracle.so")
 PRODUCT_SO = os.path.join(ROOT, "wave-simulation_b200", "csrc", "libwavesim_cuda.so")
+EMU_SO = os.path.join(ROOT, "tests", "emu", "libwavesim_emu.so")
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 EQ = dict(acoustic=0, elastic=1, viscoelastic=2, sh=3, viscosh=4, tmem=5, emem=6, viscotmem=7, viscoemem=8)
@@ -206,22 +207,34 @@ def ricker_np(nt, dt, fc, amp, tshift=0.0):
     return ((f(amp) * (f(1.0) - f(2.0) * h2)) * e).astype(np.float32)
 
 
+def _load_ws_lib(path):
+    lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
+    lib.ws_destroy.argtypes = [C.c_void_p]
+    lib.ws_launch_count.restype = C.c_uint64
+    lib.ws_launch_count.argtypes = [C.c_void_p]
+    lib.ws_estimate_memory.restype = C.c_size_t
+    lib.ws_stream.restype = C.c_void_p
+    lib.ws_stream.argtypes = [C.c_void_p]
+    lib.ws_uses_fast_kernels.argtypes = [C.c_void_p]
+    return lib
+
+
 class Solver(_Base):
     """The product through its C ABI. Fails loudly if the CUDA library is missing: there is no CPU fallback."""
     prefix = "ws_"
+    so_path = PRODUCT_SO
+
+    @classmethod
+    def _ensure_lib(cls):
+        if cls.lib is None:
+            if not os.path.exists(cls.so_path):
+                raise RuntimeError("CUDA library %s is missing: run `python -c 'import __graft_entry__ as g; g.build()'`"
+                                   % cls.so_path)
+            cls.lib = _load_ws_lib(cls.so_path)
+        return cls.lib
 
     def __init__(self, desc):
-        if Solver.lib is None:
-            if not os.path.exists(PRODUCT_SO):
-                raise RuntimeError("CUDA library %s is missing: run `python -c 'import __graft_entry__ as g; g.build()'`"
-                                   % PRODUCT_SO)
-            Solver.lib = C.CDLL(PRODUCT_SO, mode=C.RTLD_GLOBAL)
-            Solver.lib.ws_destroy.argtypes = [C.c_void_p]
-            Solver.lib.ws_launch_count.restype = C.c_uint64
-            Solver.lib.ws_launch_count.argtypes = [C.c_void_p]
-            Solver.lib.ws_estimate_memory.restype = C.c_size_t
-            Solver.lib.ws_stream.restype = C.c_void_p
-            Solver.lib.ws_stream.argtypes = [C.c_void_p]
+        self._ensure_lib()
         self.desc = desc
         self.h = C.c_void_p()
         self.n_rec = 0
@@ -242,6 +255,12 @@ class Solver(_Base):
         sp = _fp(src_samples) if src_samples is not None else None
         self._check(self.lib.ws_step_host(self.h, t, sp, _fp(rec_samples)), "step_host")
 
+    def set_timing(self, enable):
+        self._check(self.lib.ws_set_timing(self.h, int(enable)), "set_timing")
+
+    def uses_fast_kernels(self):
+        return bool(self.lib.ws_uses_fast_kernels(self.h))
+
     def launch_count(self):
         return int(self.lib.ws_launch_count(self.h))
 
@@ -259,15 +278,38 @@ class Solver(_Base):
         buf = (C.c_char * 128).from_buffer_copy(id_bytes)
         self._check(self.lib.ws_comm_init(self.h, buf), "comm_init")
 
-    @staticmethod
-    def comm_unique_id():
-        if Solver.lib is None:
-            Solver.lib = C.CDLL(PRODUCT_SO, mode=C.RTLD_GLOBAL)
+    @classmethod
+    def comm_unique_id(cls):
+        lib = cls._ensure_lib()
         buf = (C.c_char * 128)()
-        rc = Solver.lib.ws_comm_unique_id(buf)
+        rc = lib.ws_comm_unique_id(buf)
         if rc != 0:
             raise RuntimeError("ws_comm_unique_id failed")
         return bytes(buf)
+
+
+def build_emu(force=False):
+    """TEST INFRASTRUCTURE: host emulation build (-DWS_EMULATE) of the C ABI and the general kernels, tests/emu/."""
+    src = os.path.join(ROOT, "wave-simulation_b200", "csrc")
+    newest = max(os.path.getmtime(os.path.join(src, f)) for f in os.listdir(src) if f.endswith((".cu", ".cuh", ".hpp", ".cpp")))
+    newest = max(newest, os.path.getmtime(os.path.join(ROOT, "tests", "emu", "cuda_emu.hpp")),
+                 os.path.getmtime(os.path.join(ROOT, "include", "wavesim.h")))
+    if force or not os.path.exists(EMU_SO) or os.path.getmtime(EMU_SO) < newest:
+        subprocess.check_call(["make", "-s", "-B", "-C", os.path.join(ROOT, "tests", "emu")])
+    return EMU_SO
+
+
+class EmuSolver(Solver):
+    """Same C ABI, host emulation build: checks kernel LOGIC on the CPU-only box. Never used by product or GPU tests."""
+    lib = None
+    so_path = EMU_SO
+
+    @classmethod
+    def _ensure_lib(cls):
+        if cls.lib is None:
+            build_emu()
+            cls.lib = _load_ws_lib(cls.so_path)
+        return cls.lib
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -1,0 +1,1536 @@
+// ws_api.cu — C ABI (include/wavesim.h) of the B200-native FD time-stepping library: solver object, HBM layout,
+// model preparation, acquisition, time-step orchestration (streams, CUDA graphs, y-slab halo exchange over NCCL).
+//
+// Reference interfaces replaced (relative to src/): ForwardSolver/ForwardSolver.hpp:38-52 (run, prepareForModelling,
+// resetCPML, initForwardSolver), Wavefields/Wavefields.hpp (resetWavefields, getRef*), Modelparameter/*.cpp
+// (prepareForModelling), ForwardSolver/SourceReceiverImpl/*.cpp, Partitioning/Partitioning.hpp (replaced by y-slabs).
+#include "../../include/wavesim.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <dlfcn.h>
+#include <exception>
+#include <map>
+#include <string>
+#include <vector>
+
+struct WsError : public std::exception {
+    int code;
+    std::string msg;
+    WsError(int c, std::string m) : code(c), msg(std::move(m)) {}
+    const char *what() const noexcept override { return msg.c_str(); }
+};
+
+#include "ws_common.cuh"
+#include "ws_launch.hpp"
+#include "ws_prepare.cuh"
+#include "ws_tables.hpp"
+
+namespace {
+
+thread_local std::string g_lastError;
+
+#define WS_REQUIRE(cond, code, msg)                                                                                    \
+    do {                                                                                                               \
+        if (!(cond))                                                                                                   \
+            throw WsError(code, msg);                                                                                  \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------------------------------
+// NCCL through dlopen: if the host process already carries a libnccl.so.2 (e.g. torch's), that one is reused.
+// ---------------------------------------------------------------------------------------------------------------------
+struct NcclApi {
+    void *lib = nullptr;
+    typedef struct { char internal[128]; } UniqueId;
+    int (*GetUniqueId)(UniqueId *) = nullptr;
+    int (*CommInitRank)(void **, int, UniqueId, int) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    int (*Send)(const void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*Recv)(void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    void load()
+    {
+        if (lib)
+            return;
+        const char *names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char *n : names) {
+            lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (lib)
+                break;
+        }
+        WS_REQUIRE(lib, WS_ECOMM, std::string("cannot load libnccl: ") + dlerror());
+#define NCCL_SYM(field, name)                                                                                          \
+    field = reinterpret_cast<decltype(field)>(dlsym(lib, name));                                                       \
+    WS_REQUIRE(field, WS_ECOMM, std::string("missing NCCL symbol ") + name);
+        NCCL_SYM(GetUniqueId, "ncclGetUniqueId")
+        NCCL_SYM(CommInitRank, "ncclCommInitRank")
+        NCCL_SYM(CommDestroy, "ncclCommDestroy")
+        NCCL_SYM(Send, "ncclSend")
+        NCCL_SYM(Recv, "ncclRecv")
+        NCCL_SYM(GroupStart, "ncclGroupStart")
+        NCCL_SYM(GroupEnd, "ncclGroupEnd")
+        NCCL_SYM(AllReduce, "ncclAllReduce")
+        NCCL_SYM(GetErrorString, "ncclGetErrorString")
+#undef NCCL_SYM
+    }
+    void check(int rc, const char *what)
+    {
+        if (rc != 0)
+            throw WsError(WS_ECOMM, std::string(what) + ": " + (GetErrorString ? GetErrorString(rc) : "nccl error"));
+    }
+};
+NcclApi g_nccl;
+constexpr int kNcclFloat = 7; // ncclFloat32
+constexpr int kNcclInt = 2;   // ncclInt32
+constexpr int kNcclMax = 2;   // ncclMax
+
+// ---------------------------------------------------------------------------------------------------------------------
+// acquisition kernels (SourceReceiverImpl.cpp:12-37, FDTD3Delastic.cpp:12-53, FDTD2Delastic.cpp, FDTDacoustic.cpp,
+// ForwardSolverEM/SourceReceiverImpl/SourceReceiverImplEM.cpp)
+// ---------------------------------------------------------------------------------------------------------------------
+struct WsAcq {
+    int nsrc, nrec, nt;
+    const int *srcType;
+    const long long *srcOff; // padded offset, -1 if the source is not on this rank
+    const float *srcSig;     // nsrc x nt
+    const float *srcStep;    // nsrc samples of the current step (ws_step_host) or null
+    const int *recType;
+    const long long *recOff;
+    float *seis;             // nrec x nt
+    float *recStep;          // nrec samples of the current step
+    int *tdev;               // device-resident time-step counter
+};
+
+__device__ __forceinline__ void wsInject(const WsParams &P, int type, long long off, float v)
+{
+    const int eq = P.eq;
+    if (eq <= WS_EQ_VISCOSH) {
+        switch (type) {
+        case WS_TYPE_P:
+            if (eq == WS_EQ_ACOUSTIC)
+                P.fld[F_P][off] = __fadd_rn(P.fld[F_P][off], v);
+            else {
+                P.fld[F_SXX][off] = __fadd_rn(P.fld[F_SXX][off], v);
+                P.fld[F_SYY][off] = __fadd_rn(P.fld[F_SYY][off], v);
+                if (P.dim == 3)
+                    P.fld[F_SZZ][off] = __fadd_rn(P.fld[F_SZZ][off], v);
+            }
+            break;
+        case WS_TYPE_VX: P.fld[F_VX][off] = __fadd_rn(P.fld[F_VX][off], v); break;
+        case WS_TYPE_VY: P.fld[F_VY][off] = __fadd_rn(P.fld[F_VY][off], v); break;
+        case WS_TYPE_VZ: P.fld[F_VZ][off] = __fadd_rn(P.fld[F_VZ][off], v); break;
+        }
+    } else {
+        const int slot = type == WS_TYPE_EZ ? F_EZ : (type == WS_TYPE_EX ? F_EX : (type == WS_TYPE_EY ? F_EY : F_HZ));
+        P.fld[slot][off] = __fadd_rn(P.fld[slot][off], v);
+    }
+}
+
+// sequential = 1: one thread applies all sources in reference order (types P,VX,VY,VZ; ascending trace) so that
+// coincident sources accumulate deterministically; sequential = 0: all (target,index) pairs are distinct -> parallel.
+__global__ void kSources(const __grid_constant__ WsParams P, WsAcq a, int sequential)
+{
+    const int t = *a.tdev;
+    if (sequential) {
+        if (blockIdx.x != 0 || threadIdx.x != 0)
+            return;
+        for (int type = 1; type <= 4; type++)
+            for (int s = 0; s < a.nsrc; s++) {
+                if (a.srcType[s] != type || a.srcOff[s] < 0)
+                    continue;
+                const float v = a.srcStep ? a.srcStep[s] : a.srcSig[(size_t)s * a.nt + t];
+                wsInject(P, type, a.srcOff[s], v);
+            }
+    } else {
+        const int s = blockIdx.x * blockDim.x + threadIdx.x;
+        if (s >= a.nsrc || a.srcOff[s] < 0)
+            return;
+        const float v = a.srcStep ? a.srcStep[s] : a.srcSig[(size_t)s * a.nt + t];
+        wsInject(P, a.srcType[s], a.srcOff[s], v);
+    }
+}
+
+__global__ void kReceivers(const __grid_constant__ WsParams P, WsAcq a)
+{
+    const int t = *a.tdev;
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.nrec || a.recOff[r] < 0)
+        return;
+    const long long off = a.recOff[r];
+    const int type = a.recType[r];
+    float v = 0.0f;
+    if (P.eq <= WS_EQ_VISCOSH) {
+        switch (type) {
+        case WS_TYPE_P:
+            if (P.eq == WS_EQ_ACOUSTIC)
+                v = __fmul_rn(P.fld[F_P][off], 1.0f);
+            else if (P.dim == 3) {
+                v = __fadd_rn(P.fld[F_SXX][off], P.fld[F_SYY][off]);
+                v = __fadd_rn(v, P.fld[F_SZZ][off]);
+                v = __fdiv_rn(v, 3.0f);
+            } else {
+                v = __fadd_rn(P.fld[F_SXX][off], P.fld[F_SYY][off]);
+                v = __fmul_rn(v, 0.5f);
+            }
+            break;
+        case WS_TYPE_VX: v = P.fld[F_VX][off]; break;
+        case WS_TYPE_VY: v = P.fld[F_VY][off]; break;
+        case WS_TYPE_VZ: v = P.fld[F_VZ][off]; break;
+        }
+    } else {
+        const int slot = type == WS_TYPE_EZ ? F_EZ : (type == WS_TYPE_EX ? F_EX : (type == WS_TYPE_EY ? F_EY : F_HZ));
+        v = P.fld[slot][off];
+    }
+    a.seis[(size_t)r * a.nt + t] = v;
+    if (a.recStep)
+        a.recStep[r] = v;
+}
+// the time index lives in device memory so that a captured CUDA graph is step-invariant
+__global__ void kAdvance(int *tdev) { *tdev = *tdev + 1; }
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    void alloc(size_t count)
+    {
+        release();
+        n = count;
+        if (count) {
+            cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+            if (e != cudaSuccess)
+                throw WsError(WS_ENOMEM, std::string("cudaMalloc of ") + std::to_string(count * sizeof(T)) + " bytes failed: " + cudaGetErrorString(e));
+        }
+    }
+    void upload(const std::vector<T> &h)
+    {
+        alloc(h.size());
+        if (!h.empty())
+            WS_CUDA_CHECK(cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    }
+    void zero(cudaStream_t st = 0)
+    {
+        if (p)
+            WS_CUDA_CHECK(cudaMemsetAsync(p, 0, n * sizeof(T), st));
+    }
+    void release()
+    {
+        if (p)
+            cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    ~DevBuf() { release(); }
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+};
+
+struct NameSlot {
+    const char *name;
+    int slot;
+};
+const NameSlot kMatNames[] = {
+    {"velocityP", M_VP}, {"velocityS", M_VS}, {"density", M_RHO}, {"tauP", M_TAUP}, {"tauS", M_TAUS},
+    {"pWaveModulus", M_PW}, {"sWaveModulus", M_MU},
+    {"inverseDensityAverageX", M_RIX}, {"inverseDensityAverageY", M_RIY}, {"inverseDensityAverageZ", M_RIZ},
+    {"sWaveModulusAverageXY", M_MUXY}, {"sWaveModulusAverageXZ", M_MUXZ}, {"sWaveModulusAverageYZ", M_MUYZ},
+    {"tauSAverageXY", M_TSXY}, {"tauSAverageXZ", M_TSXZ}, {"tauSAverageYZ", M_TSYZ}, {"inverseDensity", M_INVRHO},
+    {"dielectricPermittivity", M_EPS}, {"electricConductivity", M_SIG}, {"magneticPermeability", M_MUM},
+    {"tauDielectricPermittivity", M_TAUEPS}, {"tauElectricConductivity", M_TAUSIG},
+    {"inverseMagneticPermeabilityAverageXY", M_MIXY}, {"inverseMagneticPermeabilityAverageXZ", M_MIXZ},
+    {"inverseMagneticPermeabilityAverageYZ", M_MIYZ},
+    {"CaAverageX", M_CAX}, {"CaAverageY", M_CAY}, {"CaAverageZ", M_CAZ},
+    {"CbAverageX", M_CBX}, {"CbAverageY", M_CBY}, {"CbAverageZ", M_CBZ},
+    {"CdAverageX1", M_CD0 + 0}, {"CdAverageY1", M_CD0 + 1}, {"CdAverageZ1", M_CD0 + 2},
+    {"CdAverageX2", M_CD0 + 3}, {"CdAverageY2", M_CD0 + 4}, {"CdAverageZ2", M_CD0 + 5},
+    {"CdAverageX3", M_CD0 + 6}, {"CdAverageY3", M_CD0 + 7}, {"CdAverageZ3", M_CD0 + 8},
+    {"CdAverageX4", M_CD0 + 9}, {"CdAverageY4", M_CD0 + 10}, {"CdAverageZ4", M_CD0 + 11},
+};
+
+} // namespace
+
+struct ws_solver {
+    ws_desc d{};
+    int nx = 0, gny = 0, nz = 0, y0 = 0, nyl = 0;
+    int pitch = 0, nzp = 0;
+    long long plane = 0, base = 0, total = 0;
+    int q = 0, h = 0, L = 0, W = 0;
+    bool seismic = true, visco = false, exact = false;
+    cudaStream_t stream = nullptr, commStream = nullptr;
+    cudaEvent_t evCompute = nullptr, evComm = nullptr;
+    DevBuf<float> fld[F_COUNT], mat[M_COUNT], psi[PSI_COUNT];
+    bool matGiven[M_COUNT] = {};
+    int psiAxis[PSI_COUNT];
+    std::map<std::string, int> fldSlot;
+    DevBuf<float> tab, cax, cbx, caxh, cbxh, cay, cby, cayh, cbyh, caz, cbz, cazh, cbzh, absCoeff;
+    DevBuf<float> sH, sV, sRH[4], sRV[4];
+    DevBuf<float> scratch; // dense staging buffer for pack/unpack
+    DevBuf<int> flag;
+    WsParams P{};
+    bool prepared = false;
+    // acquisition
+    int nsrc = 0, nrec = 0;
+    bool srcSequential = true;
+    DevBuf<int> srcType, recType, tdev;
+    DevBuf<long long> srcOff, recOff;
+    DevBuf<float> srcSig, srcStep, seis, recStep;
+    std::vector<int> recOwned; // 1 if the receiver lives on this rank
+    float *pinSrc = nullptr, *pinRec = nullptr;
+    WsAcq acq{};
+    // halo exchange lists
+    std::vector<int> exchA, exchB; // field slots whose y-ghost planes are needed after pass A / pass B
+    void *ncclComm = nullptr;
+    // instrumentation
+    uint64_t launches = 0;
+    bool timing = false;
+    std::vector<cudaEvent_t> evPool;
+    float msA = 0, msB = 0, msStep = 0;
+    bool useFast = false;
+    // CUDA graph of one time step
+    cudaGraphExec_t graphExec = nullptr;
+    int graphSteps = 0;
+
+    ~ws_solver()
+    {
+        if (graphExec)
+            cudaGraphExecDestroy(graphExec);
+        for (auto e : evPool)
+            cudaEventDestroy(e);
+        if (evCompute)
+            cudaEventDestroy(evCompute);
+        if (evComm)
+            cudaEventDestroy(evComm);
+        if (ncclComm && g_nccl.CommDestroy)
+            g_nccl.CommDestroy(ncclComm);
+        if (pinSrc)
+            cudaFreeHost(pinSrc);
+        if (pinRec)
+            cudaFreeHost(pinRec);
+        if (commStream)
+            cudaStreamDestroy(commStream);
+        if (stream)
+            cudaStreamDestroy(stream);
+    }
+
+    wsprep::Geo geo(int ylo, int yhi) const
+    {
+        wsprep::Geo g;
+        g.nx = nx; g.nyl = nyl; g.nz = nz; g.gny = gny; g.gy0 = y0; g.pitch = pitch; g.nzp = nzp;
+        g.plane = plane; g.base = base; g.ylo = ylo; g.yhi = yhi;
+        return g;
+    }
+    void gridFor(int ylo, int yhi, dim3 &grid, dim3 &block) const
+    {
+        block = nz > 1 ? dim3(64, 4, 1) : dim3(128, 1, 1);
+        grid = dim3((nx + block.x - 1) / block.x, (nz + block.y - 1) / block.y, std::max(0, yhi - ylo));
+    }
+    long long offsetOf(int x, int ly, int z) const { return base + x + (long long)z * pitch + (long long)ly * plane; }
+};
+
+namespace {
+
+void setDevice(const ws_solver *s) { WS_CUDA_CHECK(cudaSetDevice(s->d.device)); }
+
+bool eqIsVisco(int eq) { return eq == WS_EQ_VISCOELASTIC || eq == WS_EQ_VISCOSH || eq == WS_EQ_VISCOTMEM || eq == WS_EQ_VISCOEMEM; }
+
+void validateDesc(const ws_desc &d)
+{
+    WS_REQUIRE(d.dim == 2 || d.dim == 3, WS_EINVAL, "dimension must be 2D or 3D");
+    WS_REQUIRE(d.eq >= WS_EQ_ACOUSTIC && d.eq <= WS_EQ_VISCOEMEM, WS_EINVAL, "unknown equationType");
+    if (d.dim == 3)
+        WS_REQUIRE(d.eq != WS_EQ_SH && d.eq != WS_EQ_VISCOSH && d.eq != WS_EQ_TMEM && d.eq != WS_EQ_VISCOTMEM, WS_EINVAL,
+                   "sh, viscosh, tmem and viscotmem exist in 2D only (ForwardSolverFactory.cpp:4-66)");
+    WS_REQUIRE(d.nx > 0 && d.ny > 0 && (d.dim == 2 || d.nz > 0), WS_EINVAL, "NX, NY, NZ must be positive");
+    WS_REQUIRE(d.dh > 0 && d.dt > 0 && d.nt > 0, WS_EINVAL, "DH, DT, NT must be positive");
+    WS_REQUIRE(d.fd_order >= 2 && d.fd_order <= WS_MAXQ && d.fd_order % 2 == 0, WS_EINVAL,
+               "spatialFDorder = " + std::to_string(d.fd_order) + " Unsupported spatialFDorder value.");
+    WS_REQUIRE(d.edge_policy == 0 || d.edge_policy == 1, WS_EINVAL, "edge_policy must be 0 or 1");
+    WS_REQUIRE(d.damping >= 0 && d.damping <= 2, WS_EINVAL, "DampingBoundary must be 0, 1 or 2");
+    if (d.damping) {
+        WS_REQUIRE(d.boundary_width > 0, WS_EINVAL, "BoundaryWidth must be positive");
+        WS_REQUIRE(2 * d.boundary_width <= d.nx && 2 * d.boundary_width <= d.ny && (d.dim == 2 || 2 * d.boundary_width <= d.nz),
+                   WS_EINVAL, "2*BoundaryWidth must not exceed the grid extent");
+    }
+    if (eqIsVisco(d.eq))
+        WS_REQUIRE(d.n_relax >= 1 && d.n_relax <= WS_MAX_RELAX, WS_EINVAL, "numRelaxationMechanisms more than 4 is not available here!");
+    WS_REQUIRE(d.nranks >= 1 && d.rank >= 0 && d.rank < d.nranks, WS_EINVAL, "invalid rank / nranks");
+    const int nz = d.dim == 2 ? 1 : d.nz;
+    WS_REQUIRE((long long)d.nx * d.ny * nz < (1LL << 31), WS_EINVAL, "global grid exceeds int32 linear indices (scai::IndexType)");
+    WS_REQUIRE(d.ny / d.nranks >= std::max(d.fd_order / 2, 1) * 2 || d.nranks == 1, WS_EINVAL, "y-slabs thinner than the stencil");
+}
+
+void slabRange(const ws_desc &d, int rank, int &y0, int &nyl)
+{
+    // block distribution of planes, remainder to the first ranks (same rule as dmemo::BlockDistribution)
+    const int base = d.ny / d.nranks, rem = d.ny % d.nranks;
+    nyl = base + (rank < rem ? 1 : 0);
+    y0 = rank * base + std::min(rank, rem);
+}
+
+struct FieldList {
+    std::vector<std::pair<std::string, int>> f;
+    void add(const std::string &n, int slot) { f.emplace_back(n, slot); }
+};
+
+FieldList fieldsFor(const ws_desc &d)
+{
+    FieldList fl;
+    const int L = eqIsVisco(d.eq) ? d.n_relax : 0;
+    const bool d3 = d.dim == 3;
+    auto rname = [](const char *b, int l) { return std::string(b) + std::to_string(l + 1); };
+    switch (d.eq) {
+    case WS_EQ_ACOUSTIC:
+        fl.add("VX", F_VX); fl.add("VY", F_VY); if (d3) fl.add("VZ", F_VZ); fl.add("P", F_P);
+        break;
+    case WS_EQ_ELASTIC:
+    case WS_EQ_VISCOELASTIC:
+        fl.add("VX", F_VX); fl.add("VY", F_VY); fl.add("Sxx", F_SXX); fl.add("Syy", F_SYY); fl.add("Sxy", F_SXY);
+        if (d3) { fl.add("VZ", F_VZ); fl.add("Szz", F_SZZ); fl.add("Sxz", F_SXZ); fl.add("Syz", F_SYZ); }
+        for (int l = 0; l < L; l++) {
+            fl.add(rname("Rxx", l), F_R0 + 6 * l + RC_XX); fl.add(rname("Ryy", l), F_R0 + 6 * l + RC_YY); fl.add(rname("Rxy", l), F_R0 + 6 * l + RC_XY);
+            if (d3) { fl.add(rname("Rzz", l), F_R0 + 6 * l + RC_ZZ); fl.add(rname("Rxz", l), F_R0 + 6 * l + RC_XZ); fl.add(rname("Ryz", l), F_R0 + 6 * l + RC_YZ); }
+        }
+        break;
+    case WS_EQ_SH:
+    case WS_EQ_VISCOSH:
+        fl.add("VZ", F_VZ); fl.add("Sxz", F_SXZ); fl.add("Syz", F_SYZ);
+        for (int l = 0; l < L; l++) { fl.add(rname("Rxz", l), F_R0 + 6 * l + RC_XZ); fl.add(rname("Ryz", l), F_R0 + 6 * l + RC_YZ); }
+        break;
+    case WS_EQ_TMEM:
+    case WS_EQ_VISCOTMEM:
+        fl.add("HX", F_HX); fl.add("HY", F_HY); fl.add("EZ", F_EZ);
+        for (int l = 0; l < L; l++) fl.add(rname("RZ", l), F_R0 + 6 * l + RC_Z);
+        break;
+    case WS_EQ_EMEM:
+    case WS_EQ_VISCOEMEM:
+        fl.add("HZ", F_HZ); fl.add("EX", F_EX); fl.add("EY", F_EY);
+        if (d3) { fl.add("HX", F_HX); fl.add("HY", F_HY); fl.add("EZ", F_EZ); }
+        for (int l = 0; l < L; l++) {
+            fl.add(rname("RX", l), F_R0 + 6 * l + RC_X); fl.add(rname("RY", l), F_R0 + 6 * l + RC_Y);
+            if (d3) fl.add(rname("RZ", l), F_R0 + 6 * l + RC_Z);
+        }
+        break;
+    }
+    return fl;
+}
+
+// CPML memory variables used by an equation type and the axis each one lives on
+std::vector<std::pair<int, int>> psiFor(const ws_desc &d)
+{
+    std::vector<std::pair<int, int>> v;
+    const bool d3 = d.dim == 3;
+    auto add = [&](int slot, int axis) { if (axis != 2 || d3) v.emplace_back(slot, axis); };
+    switch (d.eq) {
+    case WS_EQ_ACOUSTIC:
+        add(PSI_P_X, 0); add(PSI_P_Y, 1); add(PSI_P_Z, 2); add(PSI_VXX, 0); add(PSI_VYY, 1); add(PSI_VZZ, 2);
+        break;
+    case WS_EQ_ELASTIC:
+    case WS_EQ_VISCOELASTIC:
+        add(PSI_SXX_X, 0); add(PSI_SXY_X, 0); add(PSI_SXY_Y, 1); add(PSI_SYY_Y, 1);
+        add(PSI_VXX, 0); add(PSI_VYX, 0); add(PSI_VXY, 1); add(PSI_VYY, 1);
+        if (d3) {
+            add(PSI_SXZ_X, 0); add(PSI_SYZ_Y, 1); add(PSI_SXZ_Z, 2); add(PSI_SYZ_Z, 2); add(PSI_SZZ_Z, 2);
+            add(PSI_VZX, 0); add(PSI_VZY, 1); add(PSI_VXZ, 2); add(PSI_VYZ, 2); add(PSI_VZZ, 2);
+        }
+        break;
+    case WS_EQ_SH:
+    case WS_EQ_VISCOSH:
+        add(PSI_SXZ_X, 0); add(PSI_SYZ_Y, 1); add(PSI_VZX, 0); add(PSI_VZY, 1);
+        break;
+    case WS_EQ_TMEM:
+    case WS_EQ_VISCOTMEM:
+        add(PSI_EZX, 0); add(PSI_EZY, 1); add(PSI_HYX, 0); add(PSI_HXY, 1);
+        break;
+    case WS_EQ_EMEM:
+    case WS_EQ_VISCOEMEM:
+        add(PSI_EYX, 0); add(PSI_EXY, 1); add(PSI_HZX, 0); add(PSI_HZY, 1);
+        if (d3) {
+            add(PSI_EZX, 0); add(PSI_EZY, 1); add(PSI_EXZ, 2); add(PSI_EYZ, 2);
+            add(PSI_HYX, 0); add(PSI_HXY, 1); add(PSI_HXZ, 2); add(PSI_HYZ, 2);
+        }
+        break;
+    }
+    return v;
+}
+
+size_t psiSize(const ws_solver *s, int axis)
+{
+    const size_t W2 = 2 * (size_t)s->W;
+    if (axis == 0)
+        return (size_t)s->nyl * s->nz * W2;
+    if (axis == 1)
+        return W2 * s->nz * s->nx;
+    return (size_t)s->nyl * W2 * s->nx;
+}
+
+int matSlotOf(const char *name)
+{
+    for (const auto &ns : kMatNames)
+        if (std::strcmp(ns.name, name) == 0)
+            return ns.slot;
+    throw WsError(WS_EINVAL, std::string("unknown model parameter '") + name + "'");
+}
+
+float *matBuf(ws_solver *s, int slot)
+{
+    if (!s->mat[slot].p) {
+        s->mat[slot].alloc((size_t)s->total);
+        s->mat[slot].zero();
+    }
+    return s->mat[slot].p;
+}
+
+void ensureScratch(ws_solver *s, size_t n)
+{
+    if (s->scratch.n < n)
+        s->scratch.alloc(n);
+}
+
+// dense (reference linear order) host/device slab -> padded array; planes [ylo,yhi) local, dense plane 0 = local ylo
+void packPlanes(ws_solver *s, const float *denseDev, float *padded, int ylo, int yhi)
+{
+    dim3 grid, block;
+    s->gridFor(ylo, yhi, grid, block);
+    if (grid.z == 0)
+        return;
+    WS_LAUNCH(wsprep::kPack, grid, block, 0, s->stream, s->geo(ylo, yhi), denseDev, padded, ylo);
+    s->launches++;
+}
+
+void uploadGlobal(ws_solver *s, const float *hostGlobal, float *padded)
+{
+    // planes [y0-HALO, y0+nyl+HALO) ∩ [0, NY) of the global vector, staged in chunks
+    const int glo = std::max(0, s->y0 - WS_HALO), ghi = std::min(s->gny, s->y0 + s->nyl + WS_HALO);
+    const size_t planeDense = (size_t)s->nx * s->nz;
+    const int chunk = std::max(1, (int)std::min<size_t>((size_t)(ghi - glo), (size_t)(256u << 20) / (planeDense * sizeof(float)) + 1));
+    ensureScratch(s, planeDense * chunk);
+    for (int g0 = glo; g0 < ghi; g0 += chunk) {
+        const int g1 = std::min(ghi, g0 + chunk);
+        WS_CUDA_CHECK(cudaMemcpyAsync(s->scratch.p, hostGlobal + (size_t)g0 * planeDense, (size_t)(g1 - g0) * planeDense * sizeof(float),
+                                      cudaMemcpyHostToDevice, s->stream));
+        packPlanes(s, s->scratch.p, padded, g0 - s->y0, g1 - s->y0);
+        WS_CUDA_CHECK(cudaStreamSynchronize(s->stream));
+    }
+}
+
+void downloadLocal(ws_solver *s, const float *padded, float *hostLocal)
+{
+    const size_t planeDense = (size_t)s->nx * s->nz;
+    const int chunk = std::max(1, (int)std::min<size_t>((size_t)s->nyl, (size_t)(256u << 20) / (planeDense * sizeof(float)) + 1));
+    ensureScratch(s, planeDense * chunk);
+    for (int l0 = 0; l0 < s->nyl; l0 += chunk) {
+        const int l1 = std::min(s->nyl, l0 + chunk);
+        dim3 grid, block;
+        s->gridFor(l0, l1, grid, block);
+        WS_LAUNCH(wsprep::kUnpack, grid, block, 0, s->stream, s->geo(l0, l1), padded, s->scratch.p);
+        s->launches++;
+        WS_CUDA_CHECK(cudaMemcpyAsync(hostLocal + (size_t)l0 * planeDense, s->scratch.p, (size_t)(l1 - l0) * planeDense * sizeof(float),
+                                      cudaMemcpyDeviceToHost, s->stream));
+        WS_CUDA_CHECK(cudaStreamSynchronize(s->stream));
+    }
+}
+
+// y-ghost exchange of one padded array set (h planes each way) on stream `st`
+void exchangeHalos(ws_solver *s, const std::vector<float *> &arrays, int h, cudaStream_t st)
+{
+    if (s->d.nranks <= 1 || arrays.empty())
+        return;
+    WS_REQUIRE(s->ncclComm, WS_ESTATE, "multi-rank solver used before ws_comm_init");
+    const size_t count = (size_t)h * s->plane;
+    const int up = s->d.rank - 1, down = s->d.rank + 1;
+    g_nccl.check(g_nccl.GroupStart(), "ncclGroupStart");
+    for (float *a : arrays) {
+        float *origin = a + s->base - WS_PADX - (long long)(s->nzp > 1 ? WS_HALO : 0) * s->pitch; // start of local plane 0
+        if (up >= 0) {
+            g_nccl.check(g_nccl.Send(origin, count, kNcclFloat, up, s->ncclComm, st), "ncclSend");
+            g_nccl.check(g_nccl.Recv(origin - (long long)h * s->plane, count, kNcclFloat, up, s->ncclComm, st), "ncclRecv");
+        }
+        if (down < s->d.nranks) {
+            g_nccl.check(g_nccl.Send(origin + (long long)(s->nyl - h) * s->plane, count, kNcclFloat, down, s->ncclComm, st), "ncclSend");
+            g_nccl.check(g_nccl.Recv(origin + (long long)s->nyl * s->plane, count, kNcclFloat, down, s->ncclComm, st), "ncclRecv");
+        }
+    }
+    g_nccl.check(g_nccl.GroupEnd(), "ncclGroupEnd");
+}
+
+void refreshParams(ws_solver *s)
+{
+    WsParams &P = s->P;
+    P.nx = s->nx; P.nyl = s->nyl; P.nz = s->nz; P.gny = s->gny; P.gy0 = s->y0;
+    P.pitch = s->pitch; P.nzp = s->nzp; P.plane = s->plane; P.base = s->base;
+    P.dim = s->d.dim; P.eq = s->d.eq; P.q = s->q; P.h = s->h; P.L = s->L;
+    P.free_surface = s->seismic ? s->d.free_surface : 0; // EM solvers ignore FreeSurface (ForwardSolver2Dtmem.cpp:31-33)
+    P.damping = s->d.damping; P.W = s->W;
+    P.ylo = 0; P.yhi = s->nyl;
+    P.tab = s->tab.p;
+    P.cax = s->cax.p; P.cbx = s->cbx.p; P.caxh = s->caxh.p; P.cbxh = s->cbxh.p;
+    P.cay = s->cay.p; P.cby = s->cby.p; P.cayh = s->cayh.p; P.cbyh = s->cbyh.p;
+    P.caz = s->caz.p; P.cbz = s->cbz.p; P.cazh = s->cazh.p; P.cbzh = s->cbzh.p;
+    P.absCoeff = s->absCoeff.p;
+    for (int k = 0; k < PSI_COUNT; k++) P.psi[k] = s->psi[k].p;
+    for (int k = 0; k < F_COUNT; k++) P.fld[k] = s->fld[k].p;
+    for (int k = 0; k < M_COUNT; k++) P.mat[k] = s->mat[k].p;
+    P.sH = s->sH.p; P.sV = s->sV.p;
+    for (int l = 0; l < 4; l++) { P.sRH[l] = s->sRH[l].p; P.sRV[l] = s->sRV[l].p; }
+    P.DT = s->d.dt;
+    P.fL = (float)s->L;
+}
+
+void refreshAcq(ws_solver *s)
+{
+    WsAcq &a = s->acq;
+    a.nsrc = s->nsrc; a.nrec = s->nrec; a.nt = s->d.nt;
+    a.srcType = s->srcType.p; a.srcOff = s->srcOff.p; a.srcSig = s->srcSig.p; a.srcStep = nullptr;
+    a.recType = s->recType.p; a.recOff = s->recOff.p; a.seis = s->seis.p; a.recStep = nullptr;
+    a.tdev = s->tdev.p;
+}
+
+void invalidateGraph(ws_solver *s)
+{
+    if (s->graphExec) {
+        cudaGraphExecDestroy(s->graphExec);
+        s->graphExec = nullptr;
+        s->graphSteps = 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// model preparation
+// ---------------------------------------------------------------------------------------------------------------------
+void launchPrep(ws_solver *s, int ylo, int yhi, dim3 &grid, dim3 &block) { s->gridFor(ylo, yhi, grid, block); s->launches++; }
+
+void requireMat(ws_solver *s, int slot, const char *name)
+{
+    WS_REQUIRE(s->mat[slot].p && s->matGiven[slot], WS_ESTATE, std::string("model parameter '") + name + "' is not set");
+}
+
+void prepareSeismic(ws_solver *s)
+{
+    const ws_desc &d = s->d;
+    const bool needP = d.eq == WS_EQ_ACOUSTIC || d.eq == WS_EQ_ELASTIC || d.eq == WS_EQ_VISCOELASTIC;
+    const bool needS = d.eq != WS_EQ_ACOUSTIC;
+    const bool d3 = d.dim == 3;
+    dim3 grid, block;
+    const int elo = -WS_HALO, ehi = s->nyl + WS_HALO; // extended range (needs ghost planes of the raw parameters)
+    const wsprep::Geo gExt = s->geo(elo, ehi), gLoc = s->geo(0, s->nyl);
+    // relaxed-modulus scaling sum, Viscoelastic.cpp:657-665
+    float sum = 0;
+    if (s->visco) {
+        float w_ref = (float)(2.0 * M_PI * d.fc_cpml);
+        for (int l = 0; l < s->L; l++) {
+            float tauSigma = (float)(1.0 / (2.0 * M_PI * d.relax_freq[l]));
+            sum += (float)(w_ref * w_ref * tauSigma * tauSigma / (1.0 + w_ref * w_ref * tauSigma * tauSigma));
+        }
+    }
+    if (needP && !s->matGiven[M_PW]) {
+        requireMat(s, M_VP, "velocityP");
+        requireMat(s, M_RHO, "density");
+        if (s->visco)
+            requireMat(s, M_TAUP, "tauP");
+        float *out = matBuf(s, M_PW);
+        launchPrep(s, elo, ehi, grid, block);
+        WS_LAUNCH(wsprep::kModulus, grid, block, 0, s->stream, gExt, s->mat[M_VP].p, s->mat[M_RHO].p, s->visco ? s->mat[M_TAUP].p : nullptr, sum, out);
+    }
+    if (needS && !s->matGiven[M_MU]) {
+        requireMat(s, M_VS, "velocityS");
+        requireMat(s, M_RHO, "density");
+        if (s->visco)
+            requireMat(s, M_TAUS, "tauS");
+        float *out = matBuf(s, M_MU);
+        launchPrep(s, elo, ehi, grid, block);
+        WS_LAUNCH(wsprep::kModulus, grid, block, 0, s->stream, gExt, s->mat[M_VS].p, s->mat[M_RHO].p, s->visco ? s->mat[M_TAUS].p : nullptr, sum, out);
+    }
+    if (needS) {
+        // calcAveragedSWaveModulus clamps the modulus itself first (ModelparameterSeismic.cpp:424)
+        launchPrep(s, elo, ehi, grid, block);
+        WS_LAUNCH(wsprep::kClampLess, grid, block, 0, s->stream, gExt, matBuf(s, M_MU), 1.0f, 1.0f);
+    }
+    auto avg2 = [&](int in, int out, int axis, int mode) {
+        float *o = matBuf(s, out);
+        launchPrep(s, 0, s->nyl, grid, block);
+        WS_LAUNCH(wsprep::kAvg2, grid, block, 0, s->stream, gLoc, s->mat[in].p, o, axis, mode);
+    };
+    auto avg4 = [&](int in, int out, int axA, int axB, int mode) {
+        float *o = matBuf(s, out);
+        launchPrep(s, 0, s->nyl, grid, block);
+        WS_LAUNCH(wsprep::kAvg4, grid, block, 0, s->stream, gLoc, s->mat[in].p, o, axA, axB, mode);
+    };
+    if (d.eq == WS_EQ_SH || d.eq == WS_EQ_VISCOSH) {
+        if (!s->matGiven[M_INVRHO]) {
+            requireMat(s, M_RHO, "density");
+            float *o = matBuf(s, M_INVRHO);
+            launchPrep(s, 0, s->nyl, grid, block);
+            WS_LAUNCH(wsprep::kInverse, grid, block, 0, s->stream, gLoc, s->mat[M_RHO].p, o);
+        }
+        if (!s->matGiven[M_MUXZ]) avg2(M_MU, M_MUXZ, 0, 2); // SH.cpp:424-430
+        if (!s->matGiven[M_MUYZ]) avg2(M_MU, M_MUYZ, 1, 2);
+        if (s->visco) {
+            requireMat(s, M_TAUS, "tauS");
+            if (!s->matGiven[M_TSXZ]) avg2(M_TAUS, M_TSXZ, 0, 0);
+            if (!s->matGiven[M_TSYZ]) avg2(M_TAUS, M_TSYZ, 1, 0);
+        }
+        return;
+    }
+    if (!s->matGiven[M_RIX] || !s->matGiven[M_RIY] || (d3 && !s->matGiven[M_RIZ]))
+        requireMat(s, M_RHO, "density");
+    if (!s->matGiven[M_RIX]) avg2(M_RHO, M_RIX, 0, 1);
+    if (!s->matGiven[M_RIY]) avg2(M_RHO, M_RIY, 1, 1);
+    if (d3 && !s->matGiven[M_RIZ]) avg2(M_RHO, M_RIZ, 2, 1);
+    if (d.eq == WS_EQ_ACOUSTIC)
+        return;
+    if (s->visco) {
+        requireMat(s, M_TAUS, "tauS");
+        requireMat(s, M_TAUP, "tauP");
+    }
+    if (!s->matGiven[M_MUXY]) avg4(M_MU, M_MUXY, 0, 1, 2);
+    if (s->visco && !s->matGiven[M_TSXY]) avg4(M_TAUS, M_TSXY, 0, 1, 0);
+    if (d3) {
+        if (!s->matGiven[M_MUXZ]) avg4(M_MU, M_MUXZ, 0, 2, 2);
+        if (!s->matGiven[M_MUYZ]) avg4(M_MU, M_MUYZ, 2, 1, 2);
+        if (s->visco) {
+            if (!s->matGiven[M_TSXZ]) avg4(M_TAUS, M_TSXZ, 0, 2, 0);
+            if (!s->matGiven[M_TSYZ]) avg4(M_TAUS, M_TSYZ, 2, 1, 0);
+        }
+    }
+}
+
+void prepareEM(ws_solver *s)
+{
+    const ws_desc &d = s->d;
+    const bool d3 = d.dim == 3;
+    dim3 grid, block;
+    const wsprep::Geo gLoc = s->geo(0, s->nyl);
+    std::vector<float> relaxTime(s->L);
+    for (int l = 0; l < s->L; l++)
+        relaxTime[l] = (float)(1.0 / (2.0 * M_PI * d.relax_freq[l]));
+    const float DT = d.dt;
+    wsprep::EmCoef c{};
+    c.L = s->L;
+    c.DT = DT;
+    c.eps0 = (float)8.8541878176e-12; // Modelparameter.hpp:359-360
+    {
+        float sum = 0;
+        for (int l = 0; l < s->L; l++)
+            sum += (float)(1.0 / relaxTime[l]);
+        if (s->L)
+            sum /= s->L;
+        c.sumInvRelax = sum;
+    }
+    for (int l = 0; l < s->L; l++) {
+        float tempValue = (float)(1 / (1 + 0.5 * DT / relaxTime[l]));
+        tempValue /= (s->L * relaxTime[l] * relaxTime[l]);
+        c.cdScalar[l] = tempValue;
+        s->P.Cc[l] = (float)((1 - 0.5 * DT / relaxTime[l]) / (1 + 0.5 * DT / relaxTime[l]));
+    }
+    requireMat(s, M_MUM, "magneticPermeability");
+    requireMat(s, M_EPS, "dielectricPermittivity");
+    requireMat(s, M_SIG, "electricConductivity");
+    if (s->visco) {
+        requireMat(s, M_TAUEPS, "tauDielectricPermittivity");
+        requireMat(s, M_TAUSIG, "tauElectricConductivity");
+    }
+    auto avg2 = [&](const float *in, float *out, int axis, int mode) {
+        launchPrep(s, 0, s->nyl, grid, block);
+        WS_LAUNCH(wsprep::kAvg2, grid, block, 0, s->stream, gLoc, in, out, axis, mode);
+    };
+    auto avg4 = [&](const float *in, float *out, int axA, int axB, int mode) {
+        launchPrep(s, 0, s->nyl, grid, block);
+        WS_LAUNCH(wsprep::kAvg4, grid, block, 0, s->stream, gLoc, in, out, axA, axB, mode);
+    };
+    auto coef = [&](const float *eps, const float *sig, const float *te, const float *ts, int axis) {
+        for (int l = 0; l < s->L; l++)
+            c.cd[l] = matBuf(s, M_CD0 + 3 * l + axis);
+        float *Ca = matBuf(s, M_CAX + axis), *Cb = matBuf(s, M_CBX + axis);
+        launchPrep(s, 0, s->nyl, grid, block);
+        WS_LAUNCH(wsprep::kEmCoefficients, grid, block, 0, s->stream, gLoc, eps, sig, te, ts, s->visco ? 1 : 0, c, Ca, Cb);
+    };
+    if (d.eq == WS_EQ_TMEM || d.eq == WS_EQ_VISCOTMEM) {
+        if (!s->matGiven[M_MIXZ]) avg2(s->mat[M_MUM].p, matBuf(s, M_MIXZ), 0, 1); // ViscoTMEM.cpp:442-450
+        if (!s->matGiven[M_MIYZ]) avg2(s->mat[M_MUM].p, matBuf(s, M_MIYZ), 1, 1);
+        coef(s->mat[M_EPS].p, s->mat[M_SIG].p, s->mat[M_TAUEPS].p, s->mat[M_TAUSIG].p, RC_Z);
+        return;
+    }
+    // EMEM.cpp:378-392, ViscoEMEM.cpp:409-423
+    if (!s->matGiven[M_MIXY]) avg4(s->mat[M_MUM].p, matBuf(s, M_MIXY), 0, 1, 1);
+    if (d3) {
+        if (!s->matGiven[M_MIXZ]) avg4(s->mat[M_MUM].p, matBuf(s, M_MIXZ), 0, 2, 1);
+        if (!s->matGiven[M_MIYZ]) avg4(s->mat[M_MUM].p, matBuf(s, M_MIYZ), 2, 1, 1);
+    }
+    DevBuf<float> e, g, te, ts;
+    e.alloc((size_t)s->total); g.alloc((size_t)s->total);
+    e.zero(s->stream); g.zero(s->stream);
+    if (s->visco) { te.alloc((size_t)s->total); ts.alloc((size_t)s->total); te.zero(s->stream); ts.zero(s->stream); }
+    const int nax = d3 ? 3 : 2;
+    for (int a = 0; a < nax; a++) {
+        avg2(s->mat[M_EPS].p, e.p, a, 0);
+        avg2(s->mat[M_SIG].p, g.p, a, 0);
+        if (s->visco) {
+            avg2(s->mat[M_TAUEPS].p, te.p, a, 0);
+            avg2(s->mat[M_TAUSIG].p, ts.p, a, 0);
+        }
+        coef(e.p, g.p, te.p, ts.p, a);
+    }
+    WS_CUDA_CHECK(cudaStreamSynchronize(s->stream));
+}
+
+void prepareBoundaries(ws_solver *s)
+{
+    const ws_desc &d = s->d;
+    // derivative tables = Derivatives::init (FDTD3D.cpp:51-61)
+    const bool fsTables = s->seismic && d.free_surface == 1;
+    std::vector<float> tab = wstab::buildTables(s->q, d.edge_policy, fsTables, s->nx, s->gny, s->nz, d.dim, d.dh, d.dt);
+    s->tab.upload(tab);
+    if (d.damping == 2) {
+        // CPML*.init (CPML3D.cpp:222-368): same 1-D profile on every axis (regular grid)
+        wstab::CpmlAxis c = wstab::buildCpmlAxis(s->W, d.npower, d.fc_cpml, d.vmax_cpml, d.dt, d.dh);
+        s->cax.upload(c.a); s->cbx.upload(c.b); s->caxh.upload(c.ah); s->cbxh.upload(c.bh);
+        s->cay.upload(c.a); s->cby.upload(c.b); s->cayh.upload(c.ah); s->cbyh.upload(c.bh);
+        s->caz.upload(c.a); s->cbz.upload(c.b); s->cazh.upload(c.ah); s->cbzh.upload(c.bh);
+        for (auto &pa : psiFor(d)) {
+            s->psi[pa.first].alloc(psiSize(s, pa.second));
+            s->psi[pa.first].zero();
+        }
+    }
+    if (d.damping == 1)
+        s->absCoeff.upload(wstab::buildAbsCoeff(s->W, d.damping_coeff));
+    // free surface scalings (only the rank that owns y = 0 evaluates them)
+    if (s->seismic && d.free_surface == 1 && (d.eq == WS_EQ_ELASTIC || d.eq == WS_EQ_VISCOELASTIC)) {
+        const size_t ns = (size_t)s->nx * s->nz;
+        s->sH.alloc(ns); s->sV.alloc(ns);
+        s->sH.zero(); s->sV.zero();
+        for (int l = 0; l < s->L; l++) {
+            s->sRH[l].alloc(ns); s->sRV[l].alloc(ns);
+            s->sRH[l].zero(); s->sRV[l].zero();
+        }
+        if (s->y0 == 0) {
+            dim3 block = s->nz > 1 ? dim3(64, 4, 1) : dim3(128, 1, 1);
+            dim3 grid((s->nx + block.x - 1) / block.x, (s->nz + block.y - 1) / block.y, 1);
+            s->flag.zero(s->stream);
+            s->launches++;
+            if (d.eq == WS_EQ_ELASTIC) {
+                WS_LAUNCH(wsprep::kFreeSurfaceElastic, grid, block, 0, s->stream, s->geo(0, 1), s->mat[M_PW].p, s->mat[M_MU].p, s->sH.p, s->sV.p, s->flag.p);
+            } else {
+                wsprep::ViscoFS v{};
+                v.L = s->L;
+                v.fL = (float)s->L;
+                for (int l = 0; l < s->L; l++) {
+                    v.relaxTime[l] = (float)(1.0 / (2.0 * M_PI * d.relax_freq[l]));
+                    v.viscoCoeff2[l] = (float)(1.0 / (1.0 + d.dt / (2.0 * v.relaxTime[l])));
+                    v.sRH[l] = s->sRH[l].p;
+                    v.sRV[l] = s->sRV[l].p;
+                }
+                WS_LAUNCH(wsprep::kFreeSurfaceVisco, grid, block, 0, s->stream, s->geo(0, 1), s->mat[M_PW].p, s->mat[M_MU].p, s->mat[M_TAUP].p, s->mat[M_TAUS].p,
+                                                                             s->sH.p, s->sV.p, v, s->flag.p);
+            }
+            int bad = 0;
+            WS_CUDA_CHECK(cudaMemcpyAsync(&bad, s->flag.p, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+            WS_CUDA_CHECK(cudaStreamSynchronize(s->stream));
+            WS_REQUIRE(!bad, WS_EINVAL, "S wave modulus can't be zero when using image method");
+        }
+    }
+    if (s->visco && s->seismic) {
+        // ForwardSolver3Dviscoelastic.cpp:55-66
+        for (int l = 0; l < s->L; l++) {
+            float relaxationTime = (float)(1.0 / (2.0 * M_PI * d.relax_freq[l]));
+            s->P.invRelaxTime[l] = (float)(1.0 / relaxationTime);
+            s->P.viscoCoeff1[l] = (float)(1.0 - d.dt / (2.0 * relaxationTime));
+            s->P.viscoCoeff2[l] = (float)(1.0 / (1.0 + d.dt / (2.0 * relaxationTime)));
+        }
+        s->P.DThalf = (float)(d.dt / 2.0);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// time stepping
+// ---------------------------------------------------------------------------------------------------------------------
+void firstHalfFields(const ws_solver *s, int f[3])
+{
+    f[0] = f[1] = f[2] = -1;
+    switch (s->d.eq) {
+    case WS_EQ_ACOUSTIC:
+    case WS_EQ_ELASTIC:
+    case WS_EQ_VISCOELASTIC:
+        f[0] = F_VX; f[1] = F_VY; if (s->d.dim == 3) f[2] = F_VZ;
+        break;
+    case WS_EQ_SH:
+    case WS_EQ_VISCOSH: f[0] = F_VZ; break;
+    case WS_EQ_TMEM:
+    case WS_EQ_VISCOTMEM: f[0] = F_HX; f[1] = F_HY; break;
+    default:
+        f[0] = F_HZ; if (s->d.dim == 3) { f[1] = F_HX; f[2] = F_HY; }
+        break;
+    }
+}
+
+void launchPass(ws_solver *s, int pass, int ylo, int yhi)
+{
+    if (yhi <= ylo)
+        return;
+    WsParams P = s->P;
+    P.ylo = ylo;
+    P.yhi = yhi;
+    if (s->useFast && wsLaunchFast(P, pass, s->stream)) {
+        s->launches++;
+        return;
+    }
+    wsLaunchGeneral(P, s->exact, pass, s->stream);
+    s->launches++;
+}
+
+void launchAcquisition(ws_solver *s, const float *srcStepDev, float *recStepDev)
+{
+    WsAcq a = s->acq;
+    a.srcStep = srcStepDev;
+    a.recStep = recStepDev;
+    if (s->nsrc > 0) {
+        if (s->srcSequential)
+            WS_LAUNCH(kSources, 1, 32, 0, s->stream, s->P, a, 1);
+        else
+            WS_LAUNCH(kSources, (s->nsrc + 127) / 128, 128, 0, s->stream, s->P, a, 0);
+        s->launches++;
+    }
+    if (s->nrec > 0) {
+        WS_LAUNCH(kReceivers, (s->nrec + 127) / 128, 128, 0, s->stream, s->P, a);
+        s->launches++;
+    }
+    WS_LAUNCH(kAdvance, 1, 1, 0, s->stream, s->tdev.p);
+    s->launches++;
+}
+
+// one reference time step = ForwardSolver::run(...), enqueued asynchronously
+void enqueueStep(ws_solver *s, const float *srcStepDev, float *recStepDev, cudaEvent_t *ev /* 4 events or null */)
+{
+    const bool multi = s->d.nranks > 1;
+    const int h = s->h, n = s->nyl;
+    int fA[3];
+    firstHalfFields(s, fA);
+    auto gather = [&](const std::vector<int> &slots) {
+        std::vector<float *> v;
+        for (int k : slots)
+            v.push_back(s->fld[k].p);
+        return v;
+    };
+    if (ev)
+        WS_CUDA_CHECK(cudaEventRecord(ev[0], s->stream));
+    if (!multi) {
+        launchPass(s, 0, 0, n);
+    } else {
+        // interior first (needs no ghost planes), then the edge slabs once the previous exchange has landed
+        launchPass(s, 0, h, n - h);
+        WS_CUDA_CHECK(cudaStreamWaitEvent(s->stream, s->evComm, 0));
+        launchPass(s, 0, 0, std::min(h, n));
+        launchPass(s, 0, std::max(n - h, h), n);
+        WS_CUDA_CHECK(cudaEventRecord(s->evCompute, s->stream));
+        WS_CUDA_CHECK(cudaStreamWaitEvent(s->commStream, s->evCompute, 0));
+        exchangeHalos(s, gather(s->exchA), h, s->commStream);
+        WS_CUDA_CHECK(cudaEventRecord(s->evComm, s->commStream));
+    }
+    if (ev) {
+        WS_CUDA_CHECK(cudaEventRecord(ev[1], s->stream));
+        WS_CUDA_CHECK(cudaEventRecord(ev[2], s->stream));
+    }
+    if (!multi) {
+        launchPass(s, 1, 0, n);
+    } else {
+        launchPass(s, 1, h, n - h);
+        WS_CUDA_CHECK(cudaStreamWaitEvent(s->stream, s->evComm, 0));
+        launchPass(s, 1, 0, std::min(h, n));
+        launchPass(s, 1, std::max(n - h, h), n);
+    }
+    if (ev)
+        WS_CUDA_CHECK(cudaEventRecord(ev[3], s->stream));
+    if (s->d.damping == 1) {
+        WsParams P = s->P;
+        wsLaunchAbsFirstHalf(P, s->exact, fA[0], fA[1], fA[2], s->stream);
+        s->launches++;
+    }
+    launchAcquisition(s, srcStepDev, recStepDev);
+    if (multi) {
+        WS_CUDA_CHECK(cudaEventRecord(s->evCompute, s->stream));
+        WS_CUDA_CHECK(cudaStreamWaitEvent(s->commStream, s->evCompute, 0));
+        exchangeHalos(s, gather(s->exchB), h, s->commStream);
+        WS_CUDA_CHECK(cudaEventRecord(s->evComm, s->commStream));
+    }
+}
+
+void setTime(ws_solver *s, int t)
+{
+    WS_REQUIRE(t >= 0 && t < s->d.nt, WS_EINVAL, "time step out of range");
+    WS_CUDA_CHECK(cudaMemcpyAsync(s->tdev.p, &t, sizeof(int), cudaMemcpyHostToDevice, s->stream));
+}
+
+template <typename F>
+int guarded(F fn)
+{
+    try {
+        fn();
+        return WS_OK;
+    } catch (const WsError &e) {
+        g_lastError = e.msg;
+        return e.code;
+    } catch (const std::exception &e) {
+        g_lastError = e.what();
+        return WS_EINVAL;
+    }
+}
+
+} // namespace
+
+// =====================================================================================================================
+// C ABI
+// =====================================================================================================================
+extern "C" {
+
+const char *ws_last_error(void) { return g_lastError.c_str(); }
+const char *ws_version(void) { return "wavesim-b200 0.1 (sm_100a)"; }
+
+size_t ws_estimate_memory(const ws_desc *desc)
+{
+    if (!desc)
+        return 0;
+    try {
+        validateDesc(*desc);
+    } catch (...) {
+        return 0;
+    }
+    int y0, nyl;
+    slabRange(*desc, desc->rank, y0, nyl);
+    const int nz = desc->dim == 2 ? 1 : desc->nz;
+    const size_t pitch = ((size_t)desc->nx + WS_PADX + WS_HALO + 31) / 32 * 32;
+    const size_t nzp = nz > 1 ? nz + 2 * WS_HALO : 1;
+    const size_t total = pitch * nzp * (nyl + 2 * WS_HALO);
+    const size_t nf = fieldsFor(*desc).f.size();
+    size_t nm = 8;
+    switch (desc->eq) {
+    case WS_EQ_ACOUSTIC: nm = 2 + 1 + desc->dim; break;
+    case WS_EQ_ELASTIC: nm = 3 + 2 + desc->dim + (desc->dim == 3 ? 3 : 1); break;
+    case WS_EQ_VISCOELASTIC: nm = 5 + 2 + desc->dim + 2 * (desc->dim == 3 ? 3 : 1); break;
+    case WS_EQ_SH: nm = 2 + 4; break;
+    case WS_EQ_VISCOSH: nm = 3 + 6; break;
+    default: nm = 5 + 3 + 2 * desc->dim + desc->n_relax * desc->dim; break;
+    }
+    size_t bytes = (nf + nm) * total * sizeof(float);
+    if (desc->damping == 2) {
+        const size_t W2 = 2 * (size_t)desc->boundary_width;
+        for (auto &pa : psiFor(*desc)) {
+            const size_t n = pa.second == 0 ? (size_t)nyl * nz * W2 : (pa.second == 1 ? W2 * nz * desc->nx : (size_t)nyl * W2 * desc->nx);
+            bytes += n * sizeof(float);
+        }
+    }
+    return bytes;
+}
+
+int ws_create(const ws_desc *desc, ws_solver **out)
+{
+    return guarded([&] {
+        WS_REQUIRE(desc && out, WS_EINVAL, "null argument");
+        validateDesc(*desc);
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        WS_REQUIRE(e == cudaSuccess && ndev > 0, WS_ECUDA,
+                   std::string("no CUDA device available (there is no CPU fallback): ") + cudaGetErrorString(e));
+        WS_REQUIRE(desc->device >= 0 && desc->device < ndev, WS_EINVAL, "device ordinal out of range");
+        ws_solver *s = new ws_solver();
+        try {
+            s->d = *desc;
+            if (s->d.dim == 2)
+                s->d.nz = 1;
+            setDevice(s);
+            s->nx = s->d.nx; s->gny = s->d.ny; s->nz = s->d.nz;
+            slabRange(s->d, s->d.rank, s->y0, s->nyl);
+            s->q = s->d.fd_order; s->h = s->q / 2;
+            s->seismic = s->d.eq <= WS_EQ_VISCOSH;
+            s->visco = eqIsVisco(s->d.eq);
+            s->L = s->visco ? s->d.n_relax : 0;
+            s->W = s->d.damping ? s->d.boundary_width : 0;
+            s->exact = s->d.exact_arith != 0;
+            s->pitch = (s->nx + WS_PADX + WS_HALO + 31) / 32 * 32;
+            s->nzp = s->nz > 1 ? s->nz + 2 * WS_HALO : 1;
+            s->plane = (long long)s->pitch * s->nzp;
+            s->total = s->plane * (s->nyl + 2 * WS_HALO);
+            s->base = WS_PADX + (long long)(s->nzp > 1 ? WS_HALO : 0) * s->pitch + (long long)WS_HALO * s->plane;
+            WS_CUDA_CHECK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+            WS_CUDA_CHECK(cudaStreamCreateWithFlags(&s->commStream, cudaStreamNonBlocking));
+            WS_CUDA_CHECK(cudaEventCreateWithFlags(&s->evCompute, cudaEventDisableTiming));
+            WS_CUDA_CHECK(cudaEventCreateWithFlags(&s->evComm, cudaEventDisableTiming));
+            WS_CUDA_CHECK(cudaEventRecord(s->evComm, s->commStream));
+            for (auto &kv : fieldsFor(s->d).f) {
+                s->fld[kv.second].alloc((size_t)s->total);
+                s->fld[kv.second].zero();
+                s->fldSlot[kv.first] = kv.second;
+            }
+            for (int k = 0; k < PSI_COUNT; k++)
+                s->psiAxis[k] = -1;
+            for (auto &pa : psiFor(s->d))
+                s->psiAxis[pa.first] = pa.second;
+            s->tdev.alloc(1);
+            s->tdev.zero();
+            s->flag.alloc(1);
+            // ghost exchange lists: the fields differentiated along y by the NEXT half-step
+            const bool d3 = s->d.dim == 3;
+            switch (s->d.eq) {
+            case WS_EQ_ACOUSTIC: s->exchA = {F_VY}; s->exchB = {F_P}; break;
+            case WS_EQ_ELASTIC:
+            case WS_EQ_VISCOELASTIC:
+                s->exchA = d3 ? std::vector<int>{F_VX, F_VY, F_VZ} : std::vector<int>{F_VX, F_VY};
+                s->exchB = d3 ? std::vector<int>{F_SXY, F_SYY, F_SYZ} : std::vector<int>{F_SXY, F_SYY};
+                break;
+            case WS_EQ_SH:
+            case WS_EQ_VISCOSH: s->exchA = {F_VZ}; s->exchB = {F_SYZ}; break;
+            case WS_EQ_TMEM:
+            case WS_EQ_VISCOTMEM: s->exchA = {F_HX}; s->exchB = {F_EZ}; break;
+            default:
+                s->exchA = d3 ? std::vector<int>{F_HZ, F_HX} : std::vector<int>{F_HZ};
+                s->exchB = d3 ? std::vector<int>{F_EX, F_EZ} : std::vector<int>{F_EX};
+                break;
+            }
+            WS_CUDA_CHECK(cudaDeviceSynchronize());
+            refreshParams(s);
+        } catch (...) {
+            delete s;
+            throw;
+        }
+        *out = s;
+    });
+}
+
+void ws_destroy(ws_solver *s)
+{
+    if (!s)
+        return;
+    cudaSetDevice(s->d.device);
+    cudaDeviceSynchronize();
+    delete s;
+}
+
+int ws_local_range(const ws_solver *s, int32_t *y0, int32_t *nyl)
+{
+    return guarded([&] {
+        WS_REQUIRE(s && y0 && nyl, WS_EINVAL, "null argument");
+        *y0 = s->y0;
+        *nyl = s->nyl;
+    });
+}
+
+int ws_set_material(ws_solver *s, const char *name, const float *host, size_t n)
+{
+    return guarded([&] {
+        WS_REQUIRE(s && name && host, WS_EINVAL, "null argument");
+        setDevice(s);
+        WS_REQUIRE(n == (size_t)s->nx * s->gny * s->nz, WS_EINVAL, "model vector must hold NX*NY*NZ values");
+        const int slot = matSlotOf(name);
+        uploadGlobal(s, host, matBuf(s, slot));
+        s->matGiven[slot] = true;
+        s->prepared = false;
+    });
+}
+
+int ws_set_material_device(ws_solver *s, const char *name, const float *dev, size_t n_local)
+{
+    return guarded([&] {
+        WS_REQUIRE(s && name && dev, WS_EINVAL, "null argument");
+        setDevice(s);
+        WS_REQUIRE(n_local == (size_t)s->nx * s->nyl * s->nz, WS_EINVAL, "device model slab must hold NX*NYlocal*NZ values");
+        const int slot = matSlotOf(name);
+        float *dst = matBuf(s, slot);
+        WS_CUDA_CHECK(cudaDeviceSynchronize()); // the producer may have used another stream
+        packPlanes(s, dev, dst, 0, s->nyl);
+        WS_CUDA_CHECK(cudaStreamSynchronize(s->stream));
+        if (s->d.nranks > 1) { // ghost planes of raw parameters are needed by the averaging passes
+            exchangeHalos(s, {dst}, WS_HALO, s->stream);
+            WS_CUDA_CHECK(cudaStreamSynchronize(s->stream));
+        }
+        s->matGiven[slot] = true;
+        s->prepared = false;
+    });
+}
+
+int ws_get_material(ws_solver *s, const char *name, float *host, size_t n)
+{
+    return guarded([&] {
+        WS_REQUIRE(s && name && host, WS_EINVAL, "null argument");
+        setDevice(s);
+        WS_REQUIRE(n == (size_t)s->nx * s->nyl * s->nz, WS_EINVAL, "size mismatch");
+        const int slot = matSlotOf(name);
+        WS_REQUIRE(s->mat[slot].p, WS_ESTATE, std::string("model parameter '") + name + "' is not available");
+        downloadLocal(s, s->mat[slot].p, host);
+    });
+}
+
+int ws_prepare(ws_solver *s)
+{
+    return guarded([&] {
+        WS_REQUIRE(s, WS_EINVAL, "null argument");
+        setDevice(s);
+        invalidateGraph(s);
+        if (s->seismic)
+            prepareSeismic(s);
+        else
+            prepareEM(s);
+        WS_CUDA_CHECK(cudaStreamSynchronize(s->stream));
+        prepareBoundaries(s);
+        refreshParams(s);
+        s->useFast = s->d.kernel_variant == 0 && wsFastSupported(s->P, s->exact);
+        WS_CUDA_CHECK(cudaStreamSynchronize(s->stream));
+        WS_CUDA_CHECK(cudaGetLastError());
+        s->prepared = true;
+    });
+}
+
+int ws_set_sources(ws_solver *s, int32_t n, const int32_t *type, const int32_t *idx1d, const float *signals)
+{
+    return guarded([&] {
+        WS_REQUIRE(s && n >= 0 && (n == 0 || (type && idx1d && signals)), WS_EINVAL, "invalid source arguments");
+        setDevice(s);
+        invalidateGraph(s);
+        std::vector<int> types(type, type + n);
+        std::vector<long long> off(n);
+        const long long N = (long long)s->nx * s->gny * s->nz;
+        std::map<std::pair<int, long long>, int> seen;
+        bool unique = true;
+        for (int k = 0; k < n; k++) {
+            WS_REQUIRE(idx1d[k] >= 0 && idx1d[k] < N, WS_EINVAL, "source coordinate outside the grid");
+            WS_REQUIRE(type[k] >= 1 && type[k] <= 4, WS_EINVAL, "unknown source type");
+            if (s->d.eq == WS_EQ_SH || s->d.eq == WS_EQ_VISCOSH)
+                WS_REQUIRE(type[k] == WS_TYPE_VZ, WS_EINVAL, "Pressure, VX and VY sources can not be implemented in SH modeling");
+            if (s->seismic && type[k] == WS_TYPE_VZ)
+                WS_REQUIRE(s->fld[F_VZ].p, WS_EINVAL, "no VZ wavefield in this modelling");
+            if (!s->seismic) {
+                const int slot = type[k] == WS_TYPE_EZ ? F_EZ : (type[k] == WS_TYPE_EX ? F_EX : (type[k] == WS_TYPE_EY ? F_EY : F_HZ));
+                WS_REQUIRE(s->fld[slot].p, WS_EINVAL, "source type has no wavefield in this modelling");
+            }
+            const int y = idx1d[k] / (s->nx * s->nz), r = idx1d[k] % (s->nx * s->nz), z = r / s->nx, x = r % s->nx;
+            off[k] = (y >= s->y0 && y < s->y0 + s->nyl) ? s->offsetOf(x, y - s->y0, z) : -1;
+            if (++seen[{type[k], (long long)idx1d[k]}] > 1)
+                unique = false;
+        }
+        // a P source touches Sxx/Syy/Szz: distinct from V targets, so uniqueness per (type, index) is sufficient
+        s->nsrc = n;
+        s->srcSequential = !unique;
+        s->srcType.upload(types);
+        s->srcOff.upload(off);
+        std::vector<float> sig(signals, signals + (size_t)n * s->d.nt);
+        s->srcSig.upload(sig);
+        s->srcStep.alloc(std::max(1, n));
+        if (s->pinSrc)
+            cudaFreeHost(s->pinSrc);
+        WS_CUDA_CHECK(cudaMallocHost(&s->pinSrc, std::max(1, n) * sizeof(float)));
+        refreshAcq(s);
+    });
+}
+
+int ws_set_receivers(ws_solver *s, int32_t n, const int32_t *type, const int32_t *idx1d)
+{
+    return guarded([&] {
+        WS_REQUIRE(s && n >= 0 && (n == 0 || (type && idx1d)), WS_EINVAL, "invalid receiver arguments");
+        setDevice(s);
+        invalidateGraph(s);
+        std::vector<int> types(type, type + n);
+        std::vector<long long> off(n);
+        s->recOwned.assign(n, 0);
+        const long long N = (long long)s->nx * s->gny * s->nz;
+        for (int k = 0; k < n; k++) {
+            WS_REQUIRE(idx1d[k] >= 0 && idx1d[k] < N, WS_EINVAL, "receiver coordinate outside the grid");
+            WS_REQUIRE(type[k] >= 1 && type[k] <= 4, WS_EINVAL, "unknown receiver type");
+            if (s->d.eq == WS_EQ_SH || s->d.eq == WS_EQ_VISCOSH)
+                WS_REQUIRE(type[k] == WS_TYPE_VZ, WS_EINVAL, "Pressure, VX and VY receivers can not be implemented in SH modeling");
+            if (s->seismic && type[k] == WS_TYPE_VZ)
+                WS_REQUIRE(s->fld[F_VZ].p, WS_EINVAL, "no VZ wavefield in this modelling");
+            if (!s->seismic) {
+                const int slot = type[k] == WS_TYPE_EZ ? F_EZ : (type[k] == WS_TYPE_EX ? F_EX : (type[k] == WS_TYPE_EY ? F_EY : F_HZ));
+                WS_REQUIRE(s->fld[slot].p, WS_EINVAL, "receiver type has no wavefield in this modelling");
+            }
+            const int y = idx1d[k] / (s->nx * s->nz), r = idx1d[k] % (s->nx * s->nz), z = r / s->nx, x = r % s->nx;
+            const bool mine = y >= s->y0 && y < s->y0 + s->nyl;
+            off[k] = mine ? s->offsetOf(x, y - s->y0, z) : -1;
+            s->recOwned[k] = mine ? 1 : 0;
+        }
+        s->nrec = n;
+        s->recType.upload(types);
+        s->recOff.upload(off);
+        s->seis.alloc(std::max<size_t>(1, (size_t)n * s->d.nt));
+        s->seis.zero();
+        s->recStep.alloc(std::max(1, n));
+        s->recStep.zero();
+        if (s->pinRec)
+            cudaFreeHost(s->pinRec);
+        WS_CUDA_CHECK(cudaMallocHost(&s->pinRec, std::max(1, n) * sizeof(float)));
+        WS_CUDA_CHECK(cudaDeviceSynchronize());
+        refreshAcq(s);
+    });
+}
+
+int ws_reset(ws_solver *s)
+{
+    return guarded([&] {
+        WS_REQUIRE(s, WS_EINVAL, "null argument");
+        setDevice(s);
+        for (int k = 0; k < F_COUNT; k++)
+            s->fld[k].zero(s->stream); // Wavefields::resetWavefields (Wavefields3Delastic.cpp:111-122)
+        for (int k = 0; k < PSI_COUNT; k++)
+            s->psi[k].zero(s->stream); // ForwardSolver::resetCPML (CPML3D.cpp:6-26)
+        s->seis.zero(s->stream);
+        s->tdev.zero(s->stream);
+        WS_CUDA_CHECK(cudaStreamSynchronize(s->stream));
+    });
+}
+
+int ws_step(ws_solver *s, int32_t t)
+{
+    return guarded([&] {
+        WS_REQUIRE(s, WS_EINVAL, "null argument");
+        WS_REQUIRE(s->prepared, WS_ESTATE, "ws_prepare must be called before time stepping");
+        setDevice(s);
+        setTime(s, t);
+        enqueueStep(s, nullptr, nullptr, nullptr);
+        WS_CUDA_CHECK(cudaGetLastError());
+    });
+}
+
+int ws_step_host(ws_solver *s, int32_t t, const float *src_samples, float *rec_samples)
+{
+    return guarded([&] {
+        WS_REQUIRE(s, WS_EINVAL, "null argument");
+        WS_REQUIRE(s->prepared, WS_ESTATE, "ws_prepare must be called before time stepping");
+        setDevice(s);
+        setTime(s, t);
+        const float *srcDev = nullptr;
+        if (src_samples && s->nsrc > 0) {
+            std::memcpy(s->pinSrc, src_samples, s->nsrc * sizeof(float));
+            WS_CUDA_CHECK(cudaMemcpyAsync(s->srcStep.p, s->pinSrc, s->nsrc * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+            srcDev = s->srcStep.p;
+        }
+        enqueueStep(s, srcDev, s->recStep.p, nullptr);
+        if (rec_samples && s->nrec > 0) {
+            WS_CUDA_CHECK(cudaMemcpyAsync(s->pinRec, s->recStep.p, s->nrec * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+            WS_CUDA_CHECK(cudaStreamSynchronize(s->stream));
+            std::memcpy(rec_samples, s->pinRec, s->nrec * sizeof(float));
+        } else
+            WS_CUDA_CHECK(cudaStreamSynchronize(s->stream));
+        WS_CUDA_CHECK(cudaGetLastError());
+    });
+}
+
+int ws_set_timing(ws_solver *s, int enable)
+{
+    return guarded([&] {
+        WS_REQUIRE(s, WS_EINVAL, "null argument");
+        s->timing = enable != 0;
+    });
+}
+
+int ws_run(ws_solver *s, int32_t t0, int32_t t1)
+{
+    return guarded([&] {
+        WS_REQUIRE(s, WS_EINVAL, "null argument");
+        WS_REQUIRE(s->prepared, WS_ESTATE, "ws_prepare must be called before time stepping");
+        WS_REQUIRE(t0 >= 0 && t1 <= s->d.nt && t0 <= t1, WS_EINVAL, "time range out of bounds");
+        setDevice(s);
+        if (t0 == t1)
+            return;
+        setTime(s, t0);
+        const int nsteps = t1 - t0;
+        if (s->timing) {
+            // direct launches with CUDA events around both half-step kernels of every step
+            const size_t need = (size_t)4 * nsteps + 2;
+            while (s->evPool.size() < need) {
+                cudaEvent_t e;
+                WS_CUDA_CHECK(cudaEventCreate(&e));
+                s->evPool.push_back(e);
+            }
+            WS_CUDA_CHECK(cudaEventRecord(s->evPool[need - 2], s->stream));
+            for (int k = 0; k < nsteps; k++)
+                enqueueStep(s, nullptr, nullptr, &s->evPool[(size_t)4 * k]);
+            WS_CUDA_CHECK(cudaEventRecord(s->evPool[need - 1], s->stream));
+            WS_CUDA_CHECK(cudaStreamSynchronize(s->stream));
+            double a = 0, b = 0;
+            for (int k = 0; k < nsteps; k++) {
+                float ms = 0;
+                WS_CUDA_CHECK(cudaEventElapsedTime(&ms, s->evPool[4 * k], s->evPool[4 * k + 1]));
+                a += ms;
+                WS_CUDA_CHECK(cudaEventElapsedTime(&ms, s->evPool[4 * k + 2], s->evPool[4 * k + 3]));
+                b += ms;
+            }
+            float tot = 0;
+            WS_CUDA_CHECK(cudaEventElapsedTime(&tot, s->evPool[need - 2], s->evPool[need - 1]));
+            s->msA = (float)(a / nsteps);
+            s->msB = (float)(b / nsteps);
+            s->msStep = tot / nsteps;
+            return;
+        }
+#ifdef WS_EMULATE
+        const bool canGraph = false;
+#else
+        const bool canGraph = s->d.nranks == 1;
+#endif
+        if (!canGraph || nsteps < 4) {
+            for (int k = 0; k < nsteps; k++)
+                enqueueStep(s, nullptr, nullptr, nullptr);
+            WS_CUDA_CHECK(cudaGetLastError());
+            return;
+        }
+        // CUDA graph of G consecutive steps (the time index lives in device memory, so the graph is step-invariant)
+        const int G = 8;
+        if (!s->graphExec) {
+            cudaGraph_t graph;
+            WS_CUDA_CHECK(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+            const uint64_t before = s->launches;
+            for (int k = 0; k < G; k++)
+                enqueueStep(s, nullptr, nullptr, nullptr);
+            s->launches = before;
+            WS_CUDA_CHECK(cudaStreamEndCapture(s->stream, &graph));
+            WS_CUDA_CHECK(cudaGraphInstantiate(&s->graphExec, graph, 0));
+            WS_CUDA_CHECK(cudaGraphDestroy(graph));
+            s->graphSteps = G;
+        }
+        int done = 0;
+        const uint64_t perStep = 2 + (s->d.damping == 1 ? 1 : 0) + (s->nsrc > 0 ? 1 : 0) + (s->nrec > 0 ? 1 : 0) + 1;
+        while (nsteps - done >= G) {
+            WS_CUDA_CHECK(cudaGraphLaunch(s->graphExec, s->stream));
+            s->launches += perStep * G;
+            done += G;
+        }
+        for (; done < nsteps; done++)
+            enqueueStep(s, nullptr, nullptr, nullptr);
+        WS_CUDA_CHECK(cudaGetLastError());
+    });
+}
+
+int ws_sync(ws_solver *s)
+{
+    return guarded([&] {
+        WS_REQUIRE(s, WS_EINVAL, "null argument");
+        setDevice(s);
+        WS_CUDA_CHECK(cudaStreamSynchronize(s->stream));
+        WS_CUDA_CHECK(cudaStreamSynchronize(s->commStream));
+        WS_CUDA_CHECK(cudaGetLastError());
+    });
+}
+
+int ws_get_seismogram(ws_solver *s, float *host)
+{
+    return guarded([&] {
+        WS_REQUIRE(s && host, WS_EINVAL, "null argument");
+        setDevice(s);
+        WS_CUDA_CHECK(cudaStreamSynchronize(s->stream));
+        if (s->nrec == 0)
+            return;
+        std::vector<float> tmp((size_t)s->nrec * s->d.nt);
+        WS_CUDA_CHECK(cudaMemcpy(tmp.data(), s->seis.p, tmp.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        for (int r = 0; r < s->nrec; r++)
+            if (s->recOwned[r])
+                std::memcpy(host + (size_t)r * s->d.nt, tmp.data() + (size_t)r * s->d.nt, s->d.nt * sizeof(float));
+    });
+}
+
+int ws_get_wavefield(ws_solver *s, const char *comp, float *host, size_t n)
+{
+    return guarded([&] {
+        WS_REQUIRE(s && comp && host, WS_EINVAL, "null argument");
+        setDevice(s);
+        auto it = s->fldSlot.find(comp);
+        WS_REQUIRE(it != s->fldSlot.end(), WS_EINVAL, std::string("wavefield '") + comp + "' does not exist in this modelling");
+        WS_REQUIRE(n == (size_t)s->nx * s->nyl * s->nz, WS_EINVAL, "size mismatch");
+        downloadLocal(s, s->fld[it->second].p, host);
+    });
+}
+
+int ws_set_wavefield(ws_solver *s, const char *comp, const float *host, size_t n)
+{
+    return guarded([&] {
+        WS_REQUIRE(s && comp && host, WS_EINVAL, "null argument");
+        setDevice(s);
+        auto it = s->fldSlot.find(comp);
+        WS_REQUIRE(it != s->fldSlot.end(), WS_EINVAL, std::string("wavefield '") + comp + "' does not exist in this modelling");
+        WS_REQUIRE(n == (size_t)s->nx * s->nyl * s->nz, WS_EINVAL, "size mismatch");
+        ensureScratch(s, n);
+        WS_CUDA_CHECK(cudaMemcpyAsync(s->scratch.p, host, n * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+        packPlanes(s, s->scratch.p, s->fld[it->second].p, 0, s->nyl);
+        WS_CUDA_CHECK(cudaStreamSynchronize(s->stream));
+        if (s->d.nranks > 1) {
+            exchangeHalos(s, {s->fld[it->second].p}, WS_HALO, s->stream);
+            WS_CUDA_CHECK(cudaStreamSynchronize(s->stream));
+        }
+    });
+}
+
+int ws_is_finite(ws_solver *s, int32_t *flag)
+{
+    return guarded([&] {
+        WS_REQUIRE(s && flag, WS_EINVAL, "null argument");
+        setDevice(s);
+        s->flag.zero(s->stream);
+        dim3 grid, block;
+        s->gridFor(0, s->nyl, grid, block);
+        for (int k = 0; k < F_COUNT; k++)
+            if (s->fld[k].p) {
+                WS_LAUNCH(wsprep::kIsFinite, grid, block, 0, s->stream, s->geo(0, s->nyl), s->fld[k].p, s->flag.p);
+                s->launches++;
+            }
+        int bad = 0;
+        WS_CUDA_CHECK(cudaMemcpyAsync(&bad, s->flag.p, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+        WS_CUDA_CHECK(cudaStreamSynchronize(s->stream));
+        if (s->nrec > 0) { // SeismogramHandler::isFinite
+            std::vector<float> tmp((size_t)s->nrec * s->d.nt);
+            WS_CUDA_CHECK(cudaMemcpy(tmp.data(), s->seis.p, tmp.size() * sizeof(float), cudaMemcpyDeviceToHost));
+            for (float v : tmp)
+                if (!std::isfinite(v)) {
+                    bad = 1;
+                    break;
+                }
+        }
+        if (s->d.nranks > 1 && s->ncclComm) { // commShot->all(...)
+            WS_CUDA_CHECK(cudaMemcpyAsync(s->flag.p, &bad, sizeof(int), cudaMemcpyHostToDevice, s->stream));
+            g_nccl.check(g_nccl.AllReduce(s->flag.p, s->flag.p, 1, kNcclInt, kNcclMax, s->ncclComm, s->stream), "ncclAllReduce");
+            WS_CUDA_CHECK(cudaMemcpyAsync(&bad, s->flag.p, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+            WS_CUDA_CHECK(cudaStreamSynchronize(s->stream));
+        }
+        *flag = bad ? 0 : 1;
+    });
+}
+
+int ws_comm_unique_id(void *id128)
+{
+    return guarded([&] {
+        WS_REQUIRE(id128, WS_EINVAL, "null argument");
+        g_nccl.load();
+        NcclApi::UniqueId id;
+        g_nccl.check(g_nccl.GetUniqueId(&id), "ncclGetUniqueId");
+        std::memcpy(id128, &id, 128);
+    });
+}
+
+int ws_comm_init(ws_solver *s, const void *id128)
+{
+    return guarded([&] {
+        WS_REQUIRE(s && id128, WS_EINVAL, "null argument");
+        setDevice(s);
+        g_nccl.load();
+        NcclApi::UniqueId id;
+        std::memcpy(&id, id128, 128);
+        g_nccl.check(g_nccl.CommInitRank(&s->ncclComm, s->d.nranks, id, s->d.rank), "ncclCommInitRank");
+    });
+}
+
+uint64_t ws_launch_count(const ws_solver *s) { return s ? s->launches : 0; }
+
+int ws_last_timing(ws_solver *s, int which, float *ms)
+{
+    return guarded([&] {
+        WS_REQUIRE(s && ms, WS_EINVAL, "null argument");
+        *ms = which == 0 ? s->msA : (which == 1 ? s->msB : s->msStep);
+    });
+}
+
+void *ws_stream(ws_solver *s) { return s ? (void *)s->stream : nullptr; }
+
+int ws_uses_fast_kernels(const ws_solver *s) { return s && s->useFast ? 1 : 0; }
+
+} // extern "C"

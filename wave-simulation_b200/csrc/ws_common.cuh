@@ -1,0 +1,134 @@
+// ws_common.cuh — shared device/host definitions of the B200-native FD time-stepping library.
+//
+// HBM layout (private to the library): every wavefield / model array is a padded 3-D box
+//     [nyl + 2*WS_HALO planes][nz + 2*WS_HALO rows (1 row in 2D)][pitch floats]
+// with x fastest (reference linear index x + z*NX + y*NX*NZ, Acquisition/Coordinates.cpp:687), WS_PADX zero floats
+// left of x = 0 (so row starts are 128-byte aligned) and >= WS_HALO zero floats right of x = nx-1.  The pads are
+// never written by the stepping kernels, so off-grid stencil taps read exact zeros: this reproduces LAMA's
+// StencilMatrix "drop off-grid taps" behaviour without any branch, and the y pads double as the ghost planes of the
+// y-slab domain decomposition.
+#pragma once
+#include <cstdint>
+#ifdef WS_EMULATE
+// tests/emu/cuda_emu.hpp: host-side stand-in for the CUDA runtime and the device intrinsics used here, so that the
+// kernels and the whole C ABI can be exercised by the CPU-only test suite.  Never defined in the product build.
+#include "cuda_emu.hpp"
+#define WS_LAUNCH(kern, grid, block, smem, stream, ...) wsemu::launch(kern, dim3(grid), dim3(block), __VA_ARGS__)
+#else
+#include <cuda_runtime.h>
+#define WS_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#endif
+#include "../../include/wavesim.h"
+
+#define WS_HALO 6  /* max spatialFDorder / 2 (orders 2..12, Derivatives.cpp:2001-2042) */
+#define WS_PADX 32 /* floats left of x = 0: one 128-byte line */
+#define WS_MAXQ 12
+#define WS_NOPS 8 /* xf xb yf yb zf zb yfFreeSurface ybFreeSurface */
+
+enum { OP_XF = 0, OP_XB = 1, OP_YF = 2, OP_YB = 3, OP_ZF = 4, OP_ZB = 5, OP_YF_FS = 6, OP_YB_FS = 7 };
+
+// wavefield slots
+enum {
+    F_VX = 0, F_VY, F_VZ, F_SXX, F_SYY, F_SZZ, F_SXY, F_SXZ, F_SYZ, F_P,
+    F_HX, F_HY, F_HZ, F_EX, F_EY, F_EZ,
+    F_R0, // memory variables: F_R0 + 6*l + c ; c = xx,yy,zz,xy,xz,yz (seismic) or c = x,y,z (EM)
+    F_COUNT = F_R0 + 6 * 4
+};
+enum { RC_XX = 0, RC_YY, RC_ZZ, RC_XY, RC_XZ, RC_YZ, RC_X = 0, RC_Y = 1, RC_Z = 2 };
+
+// model slots
+enum {
+    M_VP = 0, M_VS, M_RHO, M_TAUP, M_TAUS,                 // raw seismic
+    M_PW, M_MU, M_RIX, M_RIY, M_RIZ, M_MUXY, M_MUXZ, M_MUYZ, // derived seismic
+    M_TSXY, M_TSXZ, M_TSYZ, M_INVRHO,
+    M_EPS, M_SIG, M_MUM, M_TAUEPS, M_TAUSIG,               // raw EM (absolute SI)
+    M_MIXY, M_MIXZ, M_MIYZ,                                // inverse magnetic permeability averages
+    M_CAX, M_CAY, M_CAZ, M_CBX, M_CBY, M_CBZ,
+    M_CD0,                                                 // M_CD0 + 3*l + axis
+    M_COUNT = M_CD0 + 3 * 4
+};
+
+// CPML memory-variable slots (18 seismic terms, CPML3D.hpp:61-79; EM terms share the table)
+enum {
+    PSI_SXX_X = 0, PSI_SXY_X, PSI_SXZ_X, PSI_SXY_Y, PSI_SYY_Y, PSI_SYZ_Y, PSI_SXZ_Z, PSI_SYZ_Z, PSI_SZZ_Z,
+    PSI_VXX, PSI_VYX, PSI_VZX, PSI_VXY, PSI_VYY, PSI_VZY, PSI_VXZ, PSI_VYZ, PSI_VZZ,
+    PSI_COUNT,
+    // acoustic aliases (CPML3DAcoustic.cpp:21-56)
+    PSI_P_X = PSI_SXX_X, PSI_P_Y = PSI_SYY_Y, PSI_P_Z = PSI_SZZ_Z,
+    // EM aliases (CPMLEM3D.cpp:27-104)
+    PSI_EYX = PSI_SXX_X, PSI_EZX = PSI_SXY_X, PSI_HYX = PSI_VXX, PSI_HZX = PSI_VYX,
+    PSI_EXY = PSI_SXY_Y, PSI_EZY = PSI_SYY_Y, PSI_HXY = PSI_VXY, PSI_HZY = PSI_VYY,
+    PSI_EXZ = PSI_SXZ_Z, PSI_EYZ = PSI_SYZ_Z, PSI_HXZ = PSI_VXZ, PSI_HYZ = PSI_VYZ
+};
+
+struct WsParams {
+    // geometry of this rank's slab
+    int nx, nyl, nz;  // local interior extent
+    int gny, gy0;     // global NY and global y of local plane 0
+    int pitch, nzp;   // padded row length, padded number of rows per plane
+    long long plane;  // pitch * nzp
+    long long base;   // offset of (x=0, y=0 local, z=0)
+    int dim, eq, q, h, L;
+    int free_surface, damping, W;
+    int ylo, yhi;     // local y range [ylo, yhi) processed by this launch (interior/boundary split for overlap)
+    const float *tab; // derivative weight tables [WS_NOPS][2h+1][q+1], already scaled by DT/DH
+    // CPML coefficients, 2W entries per array: k < W low-coordinate side, k >= W high-coordinate side (CPML3D.cpp:297-317)
+    const float *cax, *cbx, *caxh, *cbxh, *cay, *cby, *cayh, *cbyh, *caz, *cbz, *cazh, *cbzh;
+    const float *absCoeff; // W entries (ABS3D.cpp:174-179)
+    float *psi[PSI_COUNT];
+    float *fld[F_COUNT];
+    const float *mat[M_COUNT];
+    // free surface scalings on the y = 0 plane, dense nz*nx (FreeSurfaceElastic.cpp:35-46, FreeSurfaceViscoelastic.cpp:38-95)
+    const float *sH, *sV;
+    const float *sRH[4], *sRV[4];
+    // viscoelastic scalars (ForwardSolver3Dviscoelastic.cpp:60-66)
+    float viscoCoeff1[4], viscoCoeff2[4], invRelaxTime[4], DThalf;
+    float Cc[4]; // EM relaxation (ForwardSolverEM.cpp:78-93)
+    float DT;
+    float fL;    // (float) L
+};
+
+// arithmetic policy: EXACT keeps every rounding of the reference statement sequence (no FMA contraction)
+template <bool EXACT> struct Ar;
+template <> struct Ar<true> {
+    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+    static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+    static __device__ __forceinline__ float madd(float a, float b, float c) { return __fadd_rn(c, __fmul_rn(a, b)); } // c + a*b
+    static __device__ __forceinline__ float msub(float a, float b, float c) { return __fsub_rn(c, __fmul_rn(a, b)); } // c - a*b
+    static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+};
+template <> struct Ar<false> {
+    static __device__ __forceinline__ float mul(float a, float b) { return a * b; }
+    static __device__ __forceinline__ float add(float a, float b) { return a + b; }
+    static __device__ __forceinline__ float sub(float a, float b) { return a - b; }
+    static __device__ __forceinline__ float madd(float a, float b, float c) { return fmaf(a, b, c); }
+    static __device__ __forceinline__ float msub(float a, float b, float c) { return fmaf(-a, b, c); }
+    static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+};
+
+// row class of coordinate `pos` on an axis of length n: 0..h-1 low edge rows, h interior, h+1..2h high edge rows
+__host__ __device__ __forceinline__ int wsRowClass(int pos, int n, int h)
+{
+    if (pos < h)
+        return pos;
+    if (pos >= n - h)
+        return h + 1 + (pos - (n - h));
+    return h;
+}
+// CPML slab index: 0..W-1 low side, W..2W-1 high side, -1 outside the layer
+__host__ __device__ __forceinline__ int wsCpmlIndex(int pos, int n, int W)
+{
+    if (pos < W)
+        return pos;
+    if (pos >= n - W)
+        return W + (pos - (n - W));
+    return -1;
+}
+
+#define WS_CUDA_CHECK(expr)                                                                                           \
+    do {                                                                                                               \
+        cudaError_t _e = (expr);                                                                                       \
+        if (_e != cudaSuccess)                                                                                         \
+            throw WsError(WS_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));                               \
+    } while (0)

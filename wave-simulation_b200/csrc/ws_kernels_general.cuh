@@ -1,0 +1,581 @@
+// ws_kernels_general.cuh — general matrix-free kernels: every equation type, every FD order (2..12), both edge
+// policies, image-method free surface, CPML and ABS, one thread per grid point.  These kernels are the correctness
+// workhorse (bit-exact against the CPU oracle in EXACT mode) and the fallback for configurations the tiled fast
+// kernels (ws_kernels_fast.cu) do not cover.
+//
+// Statement order follows the reference run() functions line by line; citations are relative to src/.
+#pragma once
+#include "ws_common.cuh"
+
+namespace wsgen {
+
+template <bool EXACT>
+struct Pt {
+    using A = Ar<EXACT>;
+    const WsParams &P;
+    int x, ly, z, gy;
+    long long i;    // padded linear index
+    int rx, ry, rz; // derivative row classes
+    int kx, ky, kz; // CPML slab indices (-1 outside)
+    long long px, py, pz; // psi offsets
+
+    __device__ __forceinline__ Pt(const WsParams &P_, int x_, int ly_, int z_) : P(P_), x(x_), ly(ly_), z(z_)
+    {
+        gy = P.gy0 + ly;
+        i = P.base + x + (long long)z * P.pitch + (long long)ly * P.plane;
+        rx = wsRowClass(x, P.nx, P.h);
+        ry = wsRowClass(gy, P.gny, P.h);
+        rz = wsRowClass(z, P.nz, P.h);
+        kx = ky = kz = -1;
+        px = py = pz = 0;
+        if (P.damping == 2) {
+            const int W = P.W;
+            kx = wsCpmlIndex(x, P.nx, W);
+            ky = wsCpmlIndex(gy, P.gny, W);
+            if (P.free_surface != 0 && gy < W)
+                ky = -1; // no CPML in the top layer with a free surface (CPML3D.cpp:320-328)
+            if (P.dim == 3)
+                kz = wsCpmlIndex(z, P.nz, W);
+            px = ((long long)ly * P.nz + z) * (2 * W) + kx;
+            py = ((long long)ky * P.nz + z) * P.nx + x;
+            pz = ((long long)ly * (2 * W) + kz) * P.nx + x;
+        }
+    }
+
+    // row of matrix `op` applied to field f: ascending-column accumulation like a CSR SpMV
+    __device__ __forceinline__ float D(const float *__restrict__ f, int op) const
+    {
+        const int axis = (op < 6) ? (op >> 1) : 1;
+        const int r = axis == 0 ? rx : (axis == 1 ? ry : rz);
+        const long long s = axis == 0 ? 1 : (axis == 1 ? P.plane : (long long)P.pitch);
+        const float *__restrict__ w = P.tab + ((size_t)op * (2 * P.h + 1) + r) * (P.q + 1);
+        const float *__restrict__ p = f + i - (long long)P.h * s;
+        float acc = 0.0f;
+        for (int j = 0; j <= P.q; j++) {
+            acc = A::madd(__ldg(w + j), p[0], acc);
+            p += s;
+        }
+        return acc;
+    }
+    // CPML.cpp:84-95 applyCPML
+    __device__ __forceinline__ float cp(float d, int slot, int k, long long off, const float *__restrict__ ca, const float *__restrict__ cb) const
+    {
+        if (k < 0)
+            return d;
+        float *ps = P.psi[slot] + off;
+        float v = A::mul(*ps, __ldg(cb + k));
+        const float t = A::mul(__ldg(ca + k), d);
+        v = A::add(v, t);
+        *ps = v;
+        return A::add(d, v);
+    }
+    __device__ __forceinline__ float cpx(float d, int slot, bool half) const { return cp(d, slot, kx, px, half ? P.caxh : P.cax, half ? P.cbxh : P.cbx); }
+    __device__ __forceinline__ float cpy(float d, int slot, bool half) const { return cp(d, slot, ky, py, half ? P.cayh : P.cay, half ? P.cbyh : P.cby); }
+    __device__ __forceinline__ float cpz(float d, int slot, bool half) const { return cp(d, slot, kz, pz, half ? P.cazh : P.caz, half ? P.cbzh : P.cbz); }
+
+    // ABS3D.cpp:182-213 / ABS2D.cpp:141-172: damping factor of this point (1 outside the frame)
+    __device__ __forceinline__ float absFactor() const
+    {
+        if (P.damping != 1)
+            return 1.0f;
+        const int W = P.W;
+        const int dx = min(x, P.nx - 1 - x), dy = min(gy, P.gny - 1 - gy);
+        int m;
+        if (P.dim == 3) {
+            const int dz = min(z, P.nz - 1 - z);
+            if (P.free_surface == 0) {
+                m = min(min(dx, dy), dz);
+            } else if (gy < W) {
+                m = (dz < W || dx < W) ? min(dx, dz) : W;
+            } else
+                m = min(min(dx, dy), dz);
+        } else {
+            if (P.free_surface == 0)
+                m = min(dx, dy);
+            else if (gy < W)
+                m = dx;
+            else
+                m = min(dx, dy);
+        }
+        return m < W ? __ldg(P.absCoeff + m) : 1.0f;
+    }
+    __device__ __forceinline__ int surfaceIndex() const { return z * P.nx + x; }
+};
+
+template <bool EXACT>
+__device__ __forceinline__ float &FL(const WsParams &P, int slot, long long i) { return P.fld[slot][i]; }
+
+// --------------------------------------------------------------------------------------------------------------------
+// first half-step: particle velocities / magnetic field
+// --------------------------------------------------------------------------------------------------------------------
+template <int EQ, int DIM, bool EXACT>
+__device__ __forceinline__ void passA(const WsParams &P, const Pt<EXACT> &t)
+{
+    using A = Ar<EXACT>;
+    const long long i = t.i;
+    const bool fs = P.free_surface == 1;
+    if (EQ == WS_EQ_ACOUSTIC) {
+        // ForwardSolver3Dacoustic.cpp:131-187, ForwardSolver2Dacoustic.cpp:121-160
+        const float *p = P.fld[F_P];
+        float u = t.D(p, OP_XF);
+        u = t.cpx(u, PSI_P_X, true);
+        u = A::mul(u, P.mat[M_RIX][i]);
+        P.fld[F_VX][i] = A::add(P.fld[F_VX][i], u);
+        u = t.D(p, fs ? OP_YF_FS : OP_YF);
+        u = t.cpy(u, PSI_P_Y, true);
+        u = A::mul(u, P.mat[M_RIY][i]);
+        P.fld[F_VY][i] = A::add(P.fld[F_VY][i], u);
+        if (DIM == 3) {
+            u = t.D(p, OP_ZF);
+            u = t.cpz(u, PSI_P_Z, true);
+            u = A::mul(u, P.mat[M_RIZ][i]);
+            P.fld[F_VZ][i] = A::add(P.fld[F_VZ][i], u);
+        }
+    } else if (EQ == WS_EQ_ELASTIC || EQ == WS_EQ_VISCOELASTIC) {
+        // ForwardSolver3Delastic.cpp:181-277, ForwardSolver2Delastic.cpp:163-208, ForwardSolver3Dviscoelastic.cpp:188-262
+        const float *sxx = P.fld[F_SXX], *syy = P.fld[F_SYY], *sxy = P.fld[F_SXY];
+        const float *szz = P.fld[F_SZZ], *sxz = P.fld[F_SXZ], *syz = P.fld[F_SYZ];
+        float u = t.D(sxx, OP_XF);
+        u = t.cpx(u, PSI_SXX_X, true);
+        float w = t.D(sxy, fs ? OP_YB_FS : OP_YB);
+        w = t.cpy(w, PSI_SXY_Y, false);
+        u = A::add(u, w);
+        if (DIM == 3) {
+            w = t.D(sxz, OP_ZB);
+            w = t.cpz(w, PSI_SXZ_Z, false);
+            u = A::add(u, w);
+        }
+        u = A::mul(u, P.mat[M_RIX][i]);
+        P.fld[F_VX][i] = A::add(P.fld[F_VX][i], u);
+
+        u = t.D(sxy, OP_XB);
+        u = t.cpx(u, PSI_SXY_X, false);
+        w = t.D(syy, fs ? OP_YF_FS : OP_YF);
+        w = t.cpy(w, PSI_SYY_Y, true);
+        u = A::add(u, w);
+        if (DIM == 3) {
+            w = t.D(syz, OP_ZB);
+            w = t.cpz(w, PSI_SYZ_Z, false);
+            u = A::add(u, w);
+        }
+        u = A::mul(u, P.mat[M_RIY][i]);
+        P.fld[F_VY][i] = A::add(P.fld[F_VY][i], u);
+
+        if (DIM == 3) {
+            u = t.D(sxz, OP_XB);
+            u = t.cpx(u, PSI_SXZ_X, false);
+            w = t.D(syz, fs ? OP_YB_FS : OP_YB);
+            w = t.cpy(w, PSI_SYZ_Y, false);
+            u = A::add(u, w);
+            w = t.D(szz, OP_ZF);
+            w = t.cpz(w, PSI_SZZ_Z, true);
+            u = A::add(u, w);
+            u = A::mul(u, P.mat[M_RIZ][i]);
+            P.fld[F_VZ][i] = A::add(P.fld[F_VZ][i], u);
+        }
+    } else if (EQ == WS_EQ_SH || EQ == WS_EQ_VISCOSH) {
+        // ForwardSolver2Dsh.cpp:140-158
+        float u = t.D(P.fld[F_SXZ], OP_XB);
+        float w = t.D(P.fld[F_SYZ], fs ? OP_YB_FS : OP_YB);
+        u = t.cpx(u, PSI_SXZ_X, false);
+        w = t.cpy(w, PSI_SYZ_Y, false);
+        u = A::add(u, w);
+        u = A::mul(u, P.mat[M_INVRHO][i]);
+        P.fld[F_VZ][i] = A::add(P.fld[F_VZ][i], u);
+    } else if (EQ == WS_EQ_TMEM || EQ == WS_EQ_VISCOTMEM) {
+        // ForwardSolver2Dtmem.cpp:131-146
+        const float *ez = P.fld[F_EZ];
+        float u = t.D(ez, OP_YF);
+        u = t.cpy(u, PSI_EZY, true);
+        u = A::mul(u, P.mat[M_MIYZ][i]);
+        P.fld[F_HX][i] = A::sub(P.fld[F_HX][i], u);
+        float w = t.D(ez, OP_XF);
+        w = t.cpx(w, PSI_EZX, true);
+        u = A::mul(-1.0f, w);
+        u = A::mul(u, P.mat[M_MIXZ][i]);
+        P.fld[F_HY][i] = A::sub(P.fld[F_HY][i], u);
+    } else if (EQ == WS_EQ_EMEM || EQ == WS_EQ_VISCOEMEM) {
+        const float *ex = P.fld[F_EX], *ey = P.fld[F_EY], *ez = P.fld[F_EZ];
+        if (DIM == 3) {
+            // ForwardSolver3Demem.cpp:154-187
+            float u = t.D(ez, OP_YF);
+            float w = t.D(ey, OP_ZF);
+            u = t.cpy(u, PSI_EZY, true);
+            w = t.cpz(w, PSI_EYZ, true);
+            u = A::sub(u, w);
+            u = A::mul(u, P.mat[M_MIYZ][i]);
+            P.fld[F_HX][i] = A::sub(P.fld[F_HX][i], u);
+            u = t.D(ex, OP_ZF);
+            w = t.D(ez, OP_XF);
+            u = t.cpz(u, PSI_EXZ, true);
+            w = t.cpx(w, PSI_EZX, true);
+            u = A::sub(u, w);
+            u = A::mul(u, P.mat[M_MIXZ][i]);
+            P.fld[F_HY][i] = A::sub(P.fld[F_HY][i], u);
+        }
+        // ForwardSolver2Demem.cpp:136-146
+        float u = t.D(ey, OP_XF);
+        float w = t.D(ex, OP_YF);
+        u = t.cpx(u, PSI_EYX, true);
+        w = t.cpy(w, PSI_EXY, true);
+        u = A::sub(u, w);
+        u = A::mul(u, P.mat[M_MIXY][i]);
+        P.fld[F_HZ][i] = A::sub(P.fld[F_HZ][i], u);
+    }
+}
+
+// viscoelastic helpers (ForwardSolver3Dviscoelastic.cpp:284-416) -------------------------------------------------------
+template <bool EXACT>
+__device__ __forceinline__ float viscoShear(const WsParams &P, long long i, float S, int rc, float u, float muAvg, float tauAvg, float onePlusLtauS)
+{
+    using A = Ar<EXACT>;
+    u = A::mul(u, muAvg);
+    for (int l = 0; l < P.L; l++) {
+        float *Rp = P.fld[F_R0 + 6 * l + rc] + i;
+        float R = *Rp;
+        S = A::madd(P.DThalf, R, S);
+        R = A::mul(R, P.viscoCoeff1[l]);
+        float u2 = A::mul(P.invRelaxTime[l], u);
+        u2 = A::mul(u2, tauAvg);
+        R = A::sub(R, u2);
+        R = A::mul(R, P.viscoCoeff2[l]);
+        S = A::madd(P.DThalf, R, S);
+        *Rp = R;
+    }
+    u = A::mul(u, onePlusLtauS);
+    return A::add(S, u);
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// second half-step: stresses / pressure / electric field, free surface, ABS on the fields written here
+// --------------------------------------------------------------------------------------------------------------------
+template <int EQ, int DIM, bool EXACT>
+__device__ __forceinline__ void passB(const WsParams &P, const Pt<EXACT> &t)
+{
+    using A = Ar<EXACT>;
+    const long long i = t.i;
+    const bool fs = P.free_surface == 1;
+    const float damp = t.absFactor();
+    const bool surf = fs && t.gy == 0;
+    if (EQ == WS_EQ_ACOUSTIC) {
+        // ForwardSolver3Dacoustic.cpp:192-225
+        float u = t.D(P.fld[F_VX], OP_XB);
+        u = t.cpx(u, PSI_VXX, false);
+        float w = t.D(P.fld[F_VY], OP_YB);
+        w = t.cpy(w, PSI_VYY, false);
+        u = A::add(u, w);
+        if (DIM == 3) {
+            w = t.D(P.fld[F_VZ], OP_ZB);
+            w = t.cpz(w, PSI_VZZ, false);
+            u = A::add(u, w);
+        }
+        u = A::mul(u, P.mat[M_PW][i]);
+        float p = A::add(P.fld[F_P][i], u);
+        p = A::mul(p, damp);
+        if (surf)
+            p = A::mul(p, 0.0f);
+        P.fld[F_P][i] = p;
+    } else if (EQ == WS_EQ_ELASTIC || EQ == WS_EQ_VISCOELASTIC) {
+        const float *vx = P.fld[F_VX], *vy = P.fld[F_VY], *vz = P.fld[F_VZ];
+        float vxx = t.D(vx, OP_XB);
+        float vyy = t.D(vy, OP_YB); // plain Dyb even with a free surface (ForwardSolver3Delastic.cpp:289)
+        float vzz = 0.0f;
+        if (DIM == 3)
+            vzz = t.D(vz, OP_ZB);
+        vxx = t.cpx(vxx, PSI_VXX, false);
+        vyy = t.cpy(vyy, PSI_VYY, false);
+        if (DIM == 3)
+            vzz = t.cpz(vzz, PSI_VZZ, false);
+        float sxx = P.fld[F_SXX][i], syy = P.fld[F_SYY][i], szz = 0.0f;
+        if (DIM == 3)
+            szz = P.fld[F_SZZ][i];
+        const float pi = P.mat[M_PW][i], mu = P.mat[M_MU][i];
+        float optp = 0.f, opts = 0.f, tauP = 0.f, tauS = 0.f;
+        if (EQ == WS_EQ_ELASTIC) {
+            // ForwardSolver3Delastic.cpp:297-314, ForwardSolver2Delastic.cpp:224-241
+            float u = A::add(vxx, vyy);
+            if (DIM == 3)
+                u = A::add(u, vzz);
+            u = A::mul(u, pi);
+            sxx = A::add(sxx, u);
+            syy = A::add(syy, u);
+            if (DIM == 3)
+                szz = A::add(szz, u);
+            if (DIM == 3) {
+                u = A::mul(A::add(vyy, vzz), mu);
+                sxx = A::msub(2.0f, u, sxx);
+                u = A::mul(A::add(vxx, vzz), mu);
+                syy = A::msub(2.0f, u, syy);
+                u = A::mul(A::add(vxx, vyy), mu);
+                szz = A::msub(2.0f, u, szz);
+            } else {
+                u = A::mul(vyy, mu);
+                sxx = A::msub(2.0f, u, sxx);
+                u = A::mul(vxx, mu);
+                syy = A::msub(2.0f, u, syy);
+            }
+        } else {
+            // ForwardSolver3Dviscoelastic.cpp:279-352, ForwardSolver2Dviscoelastic.cpp:220-262
+            tauP = P.mat[M_TAUP][i];
+            tauS = P.mat[M_TAUS][i];
+            optp = A::add(1.0f, A::mul(P.fL, tauP)); // onePlusLtauP = 1 + L*tauP (:109-112)
+            opts = A::add(1.0f, A::mul(P.fL, tauS));
+            float u = A::add(vxx, vyy);
+            if (DIM == 3)
+                u = A::add(u, vzz);
+            u = A::mul(u, pi);
+            for (int l = 0; l < P.L; l++) {
+                float u2 = A::mul(P.invRelaxTime[l], u);
+                u2 = A::mul(u2, tauP);
+                float *r = P.fld[F_R0 + 6 * l + RC_XX] + i;
+                sxx = A::madd(P.DThalf, *r, sxx);
+                *r = A::sub(A::mul(*r, P.viscoCoeff1[l]), u2);
+                r = P.fld[F_R0 + 6 * l + RC_YY] + i;
+                syy = A::madd(P.DThalf, *r, syy);
+                *r = A::sub(A::mul(*r, P.viscoCoeff1[l]), u2);
+                if (DIM == 3) {
+                    r = P.fld[F_R0 + 6 * l + RC_ZZ] + i;
+                    szz = A::madd(P.DThalf, *r, szz);
+                    *r = A::sub(A::mul(*r, P.viscoCoeff1[l]), u2);
+                }
+            }
+            u = A::mul(u, optp);
+            sxx = A::add(sxx, u);
+            syy = A::add(syy, u);
+            if (DIM == 3)
+                szz = A::add(szz, u);
+            auto normalPart = [&](float S, int rc, float e) {
+                float uu = A::mul(e, mu);
+                uu = A::mul(uu, 2.0f);
+                for (int l = 0; l < P.L; l++) {
+                    float u2 = A::mul(P.invRelaxTime[l], uu);
+                    u2 = A::mul(u2, tauS);
+                    float *r = P.fld[F_R0 + 6 * l + rc] + i;
+                    float R = A::add(*r, u2);
+                    R = A::mul(R, P.viscoCoeff2[l]);
+                    S = A::madd(P.DThalf, R, S);
+                    *r = R;
+                }
+                uu = A::mul(uu, opts);
+                return A::sub(S, uu);
+            };
+            if (DIM == 3) {
+                sxx = normalPart(sxx, RC_XX, A::add(vyy, vzz));
+                syy = normalPart(syy, RC_YY, A::add(vxx, vzz));
+                szz = normalPart(szz, RC_ZZ, A::add(vxx, vyy));
+            } else {
+                sxx = normalPart(sxx, RC_XX, vyy);
+                syy = normalPart(syy, RC_YY, vxx);
+            }
+        }
+        // shear stresses: ForwardSolver3Delastic.cpp:331-382, ForwardSolver3Dviscoelastic.cpp:355-416
+        {
+            float u = t.D(vx, OP_YF);
+            u = t.cpy(u, PSI_VXY, true);
+            float w = t.D(vy, OP_XF);
+            w = t.cpx(w, PSI_VYX, true);
+            u = A::add(u, w);
+            float s = P.fld[F_SXY][i];
+            if (EQ == WS_EQ_ELASTIC)
+                s = A::add(s, A::mul(u, P.mat[M_MUXY][i]));
+            else
+                s = viscoShear<EXACT>(P, i, s, RC_XY, u, P.mat[M_MUXY][i], P.mat[M_TSXY][i], opts);
+            P.fld[F_SXY][i] = A::mul(s, damp);
+        }
+        if (DIM == 3) {
+            float u = t.D(vx, OP_ZF);
+            u = t.cpz(u, PSI_VXZ, true);
+            float w = t.D(vz, OP_XF);
+            w = t.cpx(w, PSI_VZX, true);
+            u = A::add(u, w);
+            float s = P.fld[F_SXZ][i];
+            if (EQ == WS_EQ_ELASTIC)
+                s = A::add(s, A::mul(u, P.mat[M_MUXZ][i]));
+            else
+                s = viscoShear<EXACT>(P, i, s, RC_XZ, u, P.mat[M_MUXZ][i], P.mat[M_TSXZ][i], opts);
+            P.fld[F_SXZ][i] = A::mul(s, damp);
+
+            u = t.D(vy, OP_ZF);
+            u = t.cpz(u, PSI_VYZ, true);
+            w = t.D(vz, OP_YF);
+            w = t.cpy(w, PSI_VZY, true);
+            u = A::add(u, w);
+            s = P.fld[F_SYZ][i];
+            if (EQ == WS_EQ_ELASTIC)
+                s = A::add(s, A::mul(u, P.mat[M_MUYZ][i]));
+            else
+                s = viscoShear<EXACT>(P, i, s, RC_YZ, u, P.mat[M_MUYZ][i], P.mat[M_TSYZ][i], opts);
+            P.fld[F_SYZ][i] = A::mul(s, damp);
+        }
+        if (surf) {
+            const int k = t.surfaceIndex();
+            const float hor = DIM == 3 ? A::add(vxx, vzz) : vxx;
+            if (EQ == WS_EQ_ELASTIC) {
+                // FreeSurface3Delastic.cpp:15-47, FreeSurface2Delastic.cpp:14-46, FreeSurface.cpp:13-20
+                float tmp = A::mul(P.sH[k], hor);
+                sxx = A::add(sxx, tmp);
+                if (DIM == 3)
+                    szz = A::add(szz, tmp);
+                tmp = A::mul(P.sV[k], vyy);
+                sxx = A::sub(sxx, tmp);
+                if (DIM == 3)
+                    szz = A::sub(szz, tmp);
+                syy = A::mul(syy, 0.0f);
+            } else {
+                // FreeSurface3Dviscoelastic.cpp:17-75, FreeSurface2Dviscoelastic.cpp:15-63
+                for (int l = 0; l < P.L; l++) {
+                    sxx = A::msub(P.DThalf, A::mul(1.0f, P.fld[F_R0 + 6 * l + RC_XX][i]), sxx);
+                    if (DIM == 3)
+                        szz = A::msub(P.DThalf, A::mul(1.0f, P.fld[F_R0 + 6 * l + RC_ZZ][i]), szz);
+                }
+                float tmp = A::mul(P.sH[k], hor);
+                sxx = A::add(sxx, tmp);
+                if (DIM == 3)
+                    szz = A::add(szz, tmp);
+                tmp = A::mul(P.sV[k], vyy);
+                sxx = A::sub(sxx, tmp);
+                if (DIM == 3)
+                    szz = A::sub(szz, tmp);
+                for (int l = 0; l < P.L; l++) {
+                    const float th = A::mul(P.sRH[l][k], hor);
+                    const float tv = A::mul(P.sRV[l][k], vyy);
+                    float *r = P.fld[F_R0 + 6 * l + RC_XX] + i;
+                    float R = A::sub(A::add(*r, th), tv);
+                    *r = R;
+                    sxx = A::madd(P.DThalf, A::mul(1.0f, R), sxx);
+                    if (DIM == 3) {
+                        r = P.fld[F_R0 + 6 * l + RC_ZZ] + i;
+                        R = A::sub(A::add(*r, th), tv);
+                        *r = R;
+                        szz = A::madd(P.DThalf, A::mul(1.0f, R), szz);
+                    }
+                    r = P.fld[F_R0 + 6 * l + RC_YY] + i;
+                    *r = A::mul(*r, 0.0f);
+                }
+                syy = A::mul(syy, 0.0f);
+            }
+        }
+        P.fld[F_SXX][i] = A::mul(sxx, damp);
+        P.fld[F_SYY][i] = A::mul(syy, damp);
+        if (DIM == 3)
+            P.fld[F_SZZ][i] = A::mul(szz, damp);
+    } else if (EQ == WS_EQ_SH || EQ == WS_EQ_VISCOSH) {
+        // ForwardSolver2Dsh.cpp:162-192, ForwardSolver2Dviscosh.cpp:190-236
+        const float *vz = P.fld[F_VZ];
+        float opts = 0.f;
+        if (EQ == WS_EQ_VISCOSH)
+            opts = A::add(1.0f, A::mul(P.fL, P.mat[M_TAUS][i]));
+        float u = t.D(vz, OP_XF);
+        u = t.cpx(u, PSI_VZX, true);
+        float s = P.fld[F_SXZ][i];
+        if (EQ == WS_EQ_SH)
+            s = A::add(s, A::mul(u, P.mat[M_MUXZ][i]));
+        else
+            s = viscoShear<EXACT>(P, i, s, RC_XZ, u, P.mat[M_MUXZ][i], P.mat[M_TSXZ][i], opts);
+        P.fld[F_SXZ][i] = A::mul(s, damp);
+        u = t.D(vz, OP_YF);
+        u = t.cpy(u, PSI_VZY, true);
+        s = P.fld[F_SYZ][i];
+        if (EQ == WS_EQ_SH)
+            s = A::add(s, A::mul(u, P.mat[M_MUYZ][i]));
+        else
+            s = viscoShear<EXACT>(P, i, s, RC_YZ, u, P.mat[M_MUYZ][i], P.mat[M_TSYZ][i], opts);
+        P.fld[F_SYZ][i] = A::mul(s, damp);
+    } else {
+        // EM: r_l = Cc_l r_l + Cd_l e ;  e = Ca e + Cb (curl - DT sum r_l)
+        auto updateE = [&](int fslot, int axis, float curl) {
+            float e = P.fld[fslot][i];
+            for (int l = 0; l < P.L; l++) {
+                float *r = P.fld[F_R0 + 6 * l + axis] + i;
+                const float a = A::mul(P.Cc[l], *r);
+                const float b = A::mul(P.mat[M_CD0 + 3 * l + axis][i], e);
+                *r = A::add(b, a);
+            }
+            for (int l = 0; l < P.L; l++)
+                curl = A::msub(P.DT, P.fld[F_R0 + 6 * l + axis][i], curl);
+            curl = A::mul(curl, P.mat[M_CBX + axis][i]);
+            const float ca = A::mul(P.mat[M_CAX + axis][i], e);
+            e = A::add(ca, curl);
+            P.fld[fslot][i] = A::mul(e, damp);
+        };
+        if (EQ == WS_EQ_TMEM || EQ == WS_EQ_VISCOTMEM) {
+            // ForwardSolver2Dtmem.cpp:148-163, ForwardSolver2Dviscotmem.cpp:176-197
+            float u = t.D(P.fld[F_HY], OP_XB);
+            float w = t.D(P.fld[F_HX], OP_YB);
+            u = t.cpx(u, PSI_HYX, false);
+            w = t.cpy(w, PSI_HXY, false);
+            u = A::sub(u, w);
+            updateE(F_EZ, RC_Z, u);
+        } else {
+            const float *hx = P.fld[F_HX], *hy = P.fld[F_HY], *hz = P.fld[F_HZ];
+            if (DIM == 3) {
+                // ForwardSolver3Demem.cpp:189-232
+                float u = t.D(hz, OP_YB);
+                float w = t.D(hy, OP_ZB);
+                u = t.cpy(u, PSI_HZY, false);
+                w = t.cpz(w, PSI_HYZ, false);
+                u = A::sub(u, w);
+                updateE(F_EX, RC_X, u);
+                u = t.D(hx, OP_ZB);
+                w = t.D(hz, OP_XB);
+                u = t.cpz(u, PSI_HXZ, false);
+                w = t.cpx(w, PSI_HZX, false);
+                u = A::sub(u, w);
+                updateE(F_EY, RC_Y, u);
+                u = t.D(hy, OP_XB);
+                w = t.D(hx, OP_YB);
+                u = t.cpx(u, PSI_HYX, true); // half profile: CPMLEM3D.cpp:69
+                w = t.cpy(w, PSI_HXY, false);
+                u = A::sub(u, w);
+                updateE(F_EZ, RC_Z, u);
+            } else {
+                // ForwardSolver2Demem.cpp:148-169, ForwardSolver2Dviscoemem.cpp:195-222
+                float u = t.D(hz, OP_YB);
+                u = t.cpy(u, PSI_HZY, false);
+                updateE(F_EX, RC_X, u);
+                float w = t.D(hz, OP_XB);
+                w = t.cpx(w, PSI_HZX, false);
+                u = A::mul(-1.0f, w);
+                updateE(F_EY, RC_Y, u);
+            }
+        }
+    }
+}
+
+template <int EQ, int DIM, bool EXACT, int PASS>
+__global__ void __launch_bounds__(256) kGeneral(const __grid_constant__ WsParams P)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int z = blockIdx.y * blockDim.y + threadIdx.y;
+    const int ly = P.ylo + blockIdx.z;
+    if (x >= P.nx || z >= P.nz || ly >= P.yhi)
+        return;
+    Pt<EXACT> t(P, x, ly, z);
+    if (PASS == 0)
+        passA<EQ, DIM, EXACT>(P, t);
+    else
+        passB<EQ, DIM, EXACT>(P, t);
+}
+
+// ABS on the fields of the first half-step (they are read as neighbours by the second half-step, so they are damped
+// afterwards, only inside the frame): ABS3D.cpp:15-90 apply(...)
+template <bool EXACT>
+__global__ void __launch_bounds__(256) kAbsFirstHalf(const __grid_constant__ WsParams P, int f0, int f1, int f2)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int z = blockIdx.y * blockDim.y + threadIdx.y;
+    const int ly = P.ylo + blockIdx.z;
+    if (x >= P.nx || z >= P.nz || ly >= P.yhi)
+        return;
+    Pt<EXACT> t(P, x, ly, z);
+    const float d = t.absFactor();
+    if (d == 1.0f)
+        return;
+    const int fs[3] = {f0, f1, f2};
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+        if (fs[k] >= 0)
+            P.fld[fs[k]][t.i] = Ar<EXACT>::mul(P.fld[fs[k]][t.i], d);
+}
+
+} // namespace wsgen

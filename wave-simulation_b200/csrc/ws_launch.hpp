@@ -1,0 +1,12 @@
+// ws_launch.hpp — launch entry points shared between translation units
+#pragma once
+#include "ws_common.cuh"
+
+// general kernels (ws_kernels_general.cu)
+void wsGeneralGrid(const WsParams &P, dim3 &grid, dim3 &block);
+void wsLaunchGeneral(const WsParams &P, bool exact, int pass, cudaStream_t st);
+void wsLaunchAbsFirstHalf(const WsParams &P, bool exact, int f0, int f1, int f2, cudaStream_t st);
+
+// tiled fast kernels (ws_kernels_fast.cu); return false when the configuration is not covered
+bool wsFastSupported(const WsParams &P, bool exact);
+bool wsLaunchFast(const WsParams &P, int pass, cudaStream_t st);
