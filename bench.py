@@ -1,0 +1,259 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the FD time-stepping hot path (BASELINE.json: Gpt-updates/s, 3D elastic FD8).
+
+`python bench.py --gpus N --steps K --warmup W` (torchrun for N > 1).  A "step" is one time step (velocity half-step +
+stress half-step + source injection + receiver recording) over this rank's y-slab.  N = 1: 3D elastic, FD order 8,
+1024^3, image-method free surface + CPML (W = 20) — the north-star configuration; N > 1: weak scaling, 1024 planes per
+GPU (global NY = 1024 N).  `--impl reference` times the reference's CPU formulation (oracle: explicit CSR derivative
+matrices + one SpMV / vector op per reference statement, all host threads) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+B_PER_UPDATE = {"elastic3d": 140.0}  # 60 B velocity pass + 80 B stress pass
+B_PASS = {"elastic3d": (60.0, 80.0)}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        mx = max(float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(r[2 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons}
+
+
+def cpu_oracle_throughput(n, steps, warmup=1):
+    """Reference CPU formulation on a bounded sample: 3D elastic FD8, free surface + CPML, n^3 grid."""
+    from wsharness import Oracle, make_desc, idx1d, ricker_np
+    nt = steps + warmup
+    d = make_desc(3, "elastic", n, n, n, dh=10.0, dt=8e-4, nt=nt, fd_order=8, edge_policy=0, free_surface=1, damping=2,
+                  boundary_width=min(20, n // 4), vmax_cpml=5000.0, fc_cpml=10.0, npower=4.0)
+    o = Oracle(d)
+    y = np.arange(n, dtype=np.float32)[:, None, None] / n
+    vp = np.broadcast_to(2000.0 + 3000.0 * y, (n, n, n)).astype(np.float32).ravel()
+    o.set_material("velocityP", vp)
+    o.set_material("velocityS", (vp / np.float32(np.sqrt(3.0))).astype(np.float32))
+    o.set_material("density", (2000.0 + 0.2 * (vp - 2000.0)).astype(np.float32))
+    o.prepare()
+    o.set_sources([3], [idx1d(n // 2, 1, n // 2, n, n)], ricker_np(nt, d.dt, 10.0, 1.0)[None, :])
+    o.set_receivers([3] * 8, [idx1d(n // 4 + 4 * i, 1, n // 2, n, n) for i in range(8)])
+    o.reset()
+    o.run(0, warmup)
+    t0 = time.perf_counter()
+    o.run(warmup, nt)
+    dt = time.perf_counter() - t0
+    return float(n) ** 3 * steps / dt / 1e9, dt / steps, Oracle.num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = args.ref_n
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    # bound the run: the CSR formulation moves ~2 kB per grid point and step
+    while n > 64 and (steps + warm) * (n ** 3) / 8.0e6 > 240.0:
+        n -= 32
+    gpts, sec_step, cores = cpu_oracle_throughput(n, steps, max(1, warm))
+    line = {
+        "impl": "reference", "metric": "Gpt-updates/s", "value": gpts, "unit": "Gpt/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": sec_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "3D elastic FD8, free surface + CPML(20), synthetic gradient model; CPU sample %d^3 of the 1024^3 workload" % n},
+        "cpu_baseline": {"value": gpts, "unit": "Gpt/s", "cores": cores, "kind": "port",
+                         "sample": "%d^3 grid, %d steps, oracle CSR formulation (restatement of the LAMA sparse path, not the LAMA binary)" % (n, steps)},
+        "e2e": {"value": gpts, "unit": "Gpt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--nx", type=int, default=1024)
+    ap.add_argument("--ny", type=int, default=1024, help="planes PER GPU")
+    ap.add_argument("--nz", type=int, default=1024)
+    ap.add_argument("--ref-n", type=int, default=192)
+    ap.add_argument("--cpu-n", type=int, default=160)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--variant", type=int, default=0, help="0 auto (fast kernels), 1 force general kernels")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from wsharness import Solver, make_desc, ricker_np
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+    W, K = max(3, args.warmup), max(1, args.steps)
+    nx, nyl, nz = args.nx, args.ny, args.nz
+    gny = nyl * world
+    nt = 2 * (W + K) + 8
+    dt_, dh = 8e-4, 10.0
+    d = make_desc(3, "elastic", nx, gny, nz, dh=dh, dt=dt_, nt=nt, fd_order=8, edge_policy=0, free_surface=1, damping=2,
+                  boundary_width=20, vmax_cpml=5000.0, fc_cpml=10.0, npower=4.0, exact_arith=0, kernel_variant=args.variant,
+                  rank=rank, nranks=world, device=local)
+    s = Solver(d)
+    if world > 1:
+        ids = [Solver.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        s.comm_init(ids[0])
+    # synthetic model generated on the device: vp 2000..5000 m/s linear in depth, vs = vp/sqrt(3), rho = 2000 + 0.2 (vp-2000)
+    with torch.no_grad():
+        y = (torch.arange(s.y0, s.y0 + s.nyl, device="cuda", dtype=torch.float32) / gny).view(-1, 1, 1)
+        vp = (2000.0 + 3000.0 * y).expand(s.nyl, nz, nx).contiguous()
+        torch.cuda.synchronize()
+        s.set_material_device("velocityP", vp.data_ptr(), vp.numel())
+        vs = vp / float(np.sqrt(3.0))
+        torch.cuda.synchronize()
+        s.set_material_device("velocityS", vs.data_ptr(), vs.numel())
+        rho = 2000.0 + 0.2 * (vp - 2000.0)
+        torch.cuda.synchronize()
+        s.set_material_device("density", rho.data_ptr(), rho.numel())
+        del vp, vs, rho, y
+        torch.cuda.empty_cache()
+    s.prepare()
+    pl = nx * nz
+    nrec = min(1024, nx)
+    src_idx = np.array([(nx // 2) + (nz // 2) * nx + 1 * pl], dtype=np.int64)
+    rec_idx = np.array([(nx // 2 - nrec // 2 + i) + (nz // 2) * nx + 1 * pl for i in range(nrec)], dtype=np.int64)
+    s.set_sources64([3], src_idx, ricker_np(nt, dt_, 10.0, 1.0e6)[None, :])
+    s.set_receivers64([3] * nrec, rec_idx)
+    s.reset()
+
+    stream = torch.cuda.ExternalStream(s.stream_ptr())
+
+    def barrier():
+        s.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    # ---- device-resident run: W warm-up steps, then exactly K timed steps --------------------------------------------
+    s.set_timing(False)
+    s.run(0, W)
+    barrier()
+    l0 = s.launch_count()
+    sampler = ClockSampler(local)
+    sampler.start()
+    s.set_timing(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    s.run(W, W + K)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = s.launch_count() - l0
+    msA, msB, msStep = s.last_timing(0), s.last_timing(1), s.last_timing(2)
+    # ---- end-to-end run through host buffers: per step H2D of the source samples, D2H of the receiver samples --------
+    s.set_timing(False)
+    sig = ricker_np(nt, dt_, 10.0, 1.0e6)
+    rec = np.zeros(nrec, np.float32)
+    t_base = W + K
+    for t in range(t_base, t_base + 3):
+        s.step_host(t, sig[t:t + 1], rec)
+    barrier()
+    t0 = time.perf_counter()
+    for t in range(t_base + 3, t_base + 3 + K):
+        s.step_host(t, sig[t:t + 1], rec)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    sampler.stop_flag = True
+    sampler.join()
+    finite = s.is_finite()
+
+    t_ms = torch.tensor([ms, e2e_s * 1e3, msA, msB], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        lt = torch.tensor([launches], device="cuda", dtype=torch.int64)
+        dist.all_reduce(lt)
+        launches = int(lt.item())
+    ms, e2e_ms, msA, msB = (float(v) for v in t_ms.tolist())
+    npts_local = float(nx) * nyl * nz
+    npts = npts_local * world
+    value = npts * K / (ms * 1e-3) / 1e9
+    e2e = npts * K / (e2e_ms * 1e-3) / 1e9
+    if rank == 0:
+        peak, which = measured_peak()
+        bA, bB = B_PASS["elastic3d"]
+        dom = 1 if msB >= msA else 0
+        achieved = (bB if dom else bA) * npts_local / ((msB if dom else msA) * 1e-3) / 1e9
+        cpu = None
+        if not args.no_cpu and world == 1:
+            g, sec, cores = cpu_oracle_throughput(args.cpu_n, 3, 1)
+            cpu = {"value": g, "unit": "Gpt/s", "cores": cores, "kind": "port",
+                   "sample": "%d^3 grid, 3 steps, oracle CSR formulation (restatement of the LAMA sparse path)" % args.cpu_n}
+        line = {
+            "metric": "Gpt-updates/s", "value": value, "unit": "Gpt/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "3D elastic FD8 %dx%dx%d per GPU (global NY %d), free surface + CPML(20), y-slab decomposition" % (nx, nyl, nz, gny),
+                       "l2": "inputs (%.0f GB/GPU of wavefields+model) far exceed the 126 MB L2" % (20 * npts_local * 4 / 1e9),
+                       "kernels": "fast-tiled" if s.uses_fast_kernels() else "general", "finite": bool(finite)},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "stress half-step" if dom else "velocity half-step", "peak_source": which,
+                         "ms_velocity": msA, "ms_stress": msB,
+                         "whole_step_frac": B_PER_UPDATE["elastic3d"] * npts_local / (ms / K * 1e-3) / 1e9 / peak},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e, "unit": "Gpt/s", "h2d_bytes_per_step": 4 * world, "d2h_bytes_per_step": 4 * nrec},
+            "gpu_launches": launches,
+            "clocks": sampler.summary(),
+        }
+        print(json.dumps(line), flush=True)
+    s.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

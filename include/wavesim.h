@@ -103,6 +103,10 @@ int ws_prepare(ws_solver *s);
  * idx1d are GLOBAL linear indices; signals is n x nt row-major (one row per source trace).                   */
 int ws_set_sources(ws_solver *s, int32_t n, const int32_t *type, const int32_t *idx1d, const float *signals);
 int ws_set_receivers(ws_solver *s, int32_t n, const int32_t *type, const int32_t *idx1d);
+/* same with 64-bit linear indices, for global grids beyond 2^31 points (the reference's IndexType is int32, so this
+ * has no reference counterpart; used by the multi-GPU weak-scaling runs) */
+int ws_set_sources64(ws_solver *s, int32_t n, const int32_t *type, const int64_t *idx1d, const float *signals);
+int ws_set_receivers64(ws_solver *s, int32_t n, const int32_t *type, const int64_t *idx1d);
 
 /* --- time stepping ------------------------------------------------------------------------------------------ */
 int ws_reset(ws_solver *s);                   /* Wavefields::resetWavefields + ForwardSolver::resetCPML + clear traces */

@@ -1,0 +1,88 @@
+"""CPU-only logic check of the PRODUCT sources: wave-simulation_b200/csrc (C ABI, model preparation, general kernels,
+tables) compiled with -DWS_EMULATE against tests/emu/cuda_emu.hpp and compared with the oracle.  In exact-arithmetic
+mode the product's statement order equals the reference's, so results must be BIT-IDENTICAL; in the default FMA mode they
+must agree to well below the 1e-5 relative-L2 bar of BASELINE.json.  (GPU execution itself is covered by `-m gpu`.)"""
+import numpy as np
+import pytest
+
+from cases import SWEEP, fields_of, make_case, sweep_id
+from wsharness import EmuSolver, Oracle, ci_case, rel_l2
+
+
+@pytest.mark.parametrize("cfg", SWEEP, ids=[sweep_id(c) for c in SWEEP])
+def test_emulated_kernels_bit_exact(cfg):
+    eq, dim, nx, ny, nz, q, pol, fs, damp, W, L = cfg
+    case = make_case(eq, dim, nx, ny, nz, q, pol, fs, damp, W, L, nt=30, exact=1)
+    o = case.setup(Oracle(case.desc))
+    e = case.setup(EmuSolver(case.desc))
+    o.run(0, 30)
+    e.run(0, 30)
+    so, se = o.seismogram(), e.seismogram()
+    assert np.abs(so).max() > 0
+    assert np.array_equal(so, se)
+    for f in fields_of(eq, dim, L):
+        assert np.array_equal(o.wavefield(f), e.wavefield(f)), f
+
+
+@pytest.mark.parametrize("cfg", SWEEP[::3], ids=[sweep_id(c) for c in SWEEP[::3]])
+def test_emulated_kernels_fma_mode(cfg):
+    eq, dim, nx, ny, nz, q, pol, fs, damp, W, L = cfg
+    case = make_case(eq, dim, nx, ny, nz, q, pol, fs, damp, W, L, nt=30, exact=0)
+    o = case.setup(Oracle(case.desc))
+    e = case.setup(EmuSolver(case.desc))
+    o.run(0, 30)
+    e.run(0, 30)
+    assert rel_l2(e.seismogram(), o.seismogram()) <= 1.0e-5
+
+
+def test_emulated_ci_case_2d_elastic_full_trace():
+    case = ci_case("2D.elastic")
+    for exact, tol in ((1, 0.0), (0, 1.0e-5)):
+        case.desc.exact_arith = exact
+        o = case.setup(Oracle(case.desc))
+        e = case.setup(EmuSolver(case.desc))
+        o.run(0, 1000)
+        e.run(0, 1000)
+        assert rel_l2(e.seismogram(), o.seismogram()) <= tol
+
+
+def test_derived_model_parameters_match():
+    case = make_case("viscoelastic", 3, 14, 15, 13, 4, 1, 1, 2, 4, 2, nt=4)
+    o = case.setup(Oracle(case.desc))
+    e = case.setup(EmuSolver(case.desc))
+    for name in ("pWaveModulus", "sWaveModulus", "inverseDensityAverageX", "inverseDensityAverageY", "inverseDensityAverageZ",
+                 "sWaveModulusAverageXY", "sWaveModulusAverageXZ", "sWaveModulusAverageYZ", "tauSAverageXY", "tauSAverageXZ",
+                 "tauSAverageYZ"):
+        assert np.array_equal(o.get_material(name), e.get_material(name)), name
+
+
+def test_step_host_and_reset():
+    case = make_case("elastic", 2, 30, 28, 1, 4, 0, 1, 1, 6, 0, nt=12)
+    e = case.setup(EmuSolver(case.desc))
+    e.run(0, 12)
+    ref = e.seismogram()
+    e.reset()
+    sig = case.src[2]
+    rec = np.zeros(4, np.float32)
+    got = np.zeros_like(ref)
+    for t in range(12):
+        e.step_host(t, np.ascontiguousarray(sig[:, t]), rec)
+        got[:, t] = rec
+    assert np.array_equal(got, ref)
+    assert np.array_equal(e.seismogram(), ref)
+    assert e.is_finite()
+
+
+def test_error_behaviour():
+    from wsharness import make_desc
+    with pytest.raises(RuntimeError, match="Unsupported spatialFDorder"):
+        EmuSolver(make_desc(2, "acoustic", 30, 30, fd_order=7))
+    with pytest.raises(RuntimeError, match="2D only"):
+        EmuSolver(make_desc(3, "sh", 30, 30, 30))
+    s = EmuSolver(make_desc(2, "sh", 30, 30, nt=5))
+    with pytest.raises(RuntimeError, match="SH modeling"):
+        s.set_sources([1], [5], np.zeros((1, 5), np.float32))
+    with pytest.raises(RuntimeError, match="not set"):
+        s.prepare()
+    with pytest.raises(RuntimeError, match="ws_prepare must be called"):
+        s.step(0)

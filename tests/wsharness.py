@@ -14,62 +14,32 @@ import subprocess
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def load_pkg():
+    """Import the hyphenated package directory wave-simulation_b200/ under the module name wave_simulation_b200."""
+    import importlib.util
+    import sys
+    name = "wave_simulation_b200"
+    if name in sys.modules:
+        return sys.modules[name]
+    path = os.path.join(ROOT, "wave-simulation_b200", "__init__.py")
+    spec = importlib.util.spec_from_file_location(name, path, submodule_search_locations=[os.path.dirname(path)])
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+_pkg = load_pkg()
+Desc, make_desc, Solver, SolverBase = _pkg.Desc, _pkg.make_desc, _pkg.Solver, _pkg.SolverBase
+EQ, TYPE, idx1d, ricker_np, PRODUCT_SO = _pkg.EQ, _pkg.TYPE, _pkg.idx1d, _pkg.ricker_np, _pkg.PRODUCT_SO
+_f32, _i32, _fp, _ip, _load_ws_lib = _pkg._f32, _pkg._i32, _pkg._fp, _pkg._ip, _pkg._load_ws_lib
 ORACLE_SO = os.path.join(ROOT, "oracle", "_ref", "libwave_oracle.so")
-PRODUCT_SO = os.path.join(ROOT, "wave-simulation_b200", "csrc", "libwavesim_cuda.so")
 EMU_SO = os.path.join(ROOT, "tests", "emu", "libwavesim_emu.so")
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
-EQ = dict(acoustic=0, elastic=1, viscoelastic=2, sh=3, viscosh=4, tmem=5, emem=6, viscotmem=7, viscoemem=8)
-TYPE = dict(P=1, VX=2, VY=3, VZ=4, EZ=1, EX=2, EY=3, HZ=4)
 
-
-class Desc(C.Structure):
-    """Mirror of ws_desc (include/wavesim.h)."""
-    _fields_ = [
-        ("dim", C.c_int32), ("eq", C.c_int32),
-        ("nx", C.c_int32), ("ny", C.c_int32), ("nz", C.c_int32),
-        ("dh", C.c_float), ("dt", C.c_float),
-        ("nt", C.c_int32), ("fd_order", C.c_int32), ("edge_policy", C.c_int32),
-        ("free_surface", C.c_int32), ("damping", C.c_int32), ("boundary_width", C.c_int32),
-        ("damping_coeff", C.c_float), ("vmax_cpml", C.c_float), ("fc_cpml", C.c_float), ("npower", C.c_float),
-        ("n_relax", C.c_int32), ("relax_freq", C.c_float * 4),
-        ("exact_arith", C.c_int32), ("kernel_variant", C.c_int32),
-        ("rank", C.c_int32), ("nranks", C.c_int32), ("device", C.c_int32),
-    ]
-
-
-def make_desc(dim, eq, nx, ny, nz=1, dh=50.0, dt=2e-3, nt=100, fd_order=2, edge_policy=1, free_surface=0,
-              damping=0, boundary_width=10, damping_coeff=8.0, vmax_cpml=3500.0, fc_cpml=5.0, npower=4.0,
-              relax_freq=(), exact_arith=0, kernel_variant=0, rank=0, nranks=1, device=0):
-    d = Desc()
-    d.dim, d.eq = dim, EQ[eq] if isinstance(eq, str) else eq
-    d.nx, d.ny, d.nz = nx, ny, (1 if dim == 2 else nz)
-    d.dh, d.dt, d.nt = dh, dt, nt
-    d.fd_order, d.edge_policy, d.free_surface = fd_order, edge_policy, free_surface
-    d.damping, d.boundary_width, d.damping_coeff = damping, boundary_width, damping_coeff
-    d.vmax_cpml, d.fc_cpml, d.npower = vmax_cpml, fc_cpml, npower
-    d.n_relax = len(relax_freq)
-    for i, f in enumerate(relax_freq):
-        d.relax_freq[i] = f
-    d.exact_arith, d.kernel_variant = exact_arith, kernel_variant
-    d.rank, d.nranks, d.device = rank, nranks, device
-    return d
-
-
-def _f32(a):
-    return np.ascontiguousarray(a, dtype=np.float32)
-
-
-def _i32(a):
-    return np.ascontiguousarray(a, dtype=np.int32)
-
-
-def _fp(a):
-    return a.ctypes.data_as(C.POINTER(C.c_float))
-
-
-def _ip(a):
-    return a.ctypes.data_as(C.POINTER(C.c_int32))
 
 
 def build_oracle(force=False):
@@ -80,78 +50,7 @@ def build_oracle(force=False):
     return ORACLE_SO
 
 
-class _Base:
-    """Common method set over a `<prefix>_*` C API."""
-    prefix = None
-    lib = None
-
-    def _fn(self, name):
-        return getattr(self.lib, self.prefix + name)
-
-    def _check(self, rc, what):
-        if rc != 0:
-            err = self._fn("last_error")
-            err.restype = C.c_char_p
-            raise RuntimeError("%s%s failed (%d): %s" % (self.prefix, what, rc, (err() or b"").decode()))
-
-    def set_material(self, name, arr):
-        a = _f32(arr).ravel()
-        self._check(self._fn("set_material")(self.h, name.encode(), _fp(a), C.c_size_t(a.size)), "set_material")
-
-    def get_material(self, name, n=None):
-        out = np.empty(self.n_local if n is None else n, dtype=np.float32)
-        self._check(self._fn("get_material")(self.h, name.encode(), _fp(out), C.c_size_t(out.size)), "get_material")
-        return out
-
-    def prepare(self):
-        self._check(self._fn("prepare")(self.h), "prepare")
-
-    def set_sources(self, types, idx, signals):
-        t, i, s = _i32(types), _i32(idx), _f32(signals)
-        assert s.shape == (len(t), self.desc.nt), s.shape
-        self._check(self._fn("set_sources")(self.h, len(t), _ip(t), _ip(i), _fp(s)), "set_sources")
-
-    def set_receivers(self, types, idx):
-        t, i = _i32(types), _i32(idx)
-        self.n_rec = len(t)
-        self._check(self._fn("set_receivers")(self.h, len(t), _ip(t), _ip(i)), "set_receivers")
-
-    def reset(self):
-        self._check(self._fn("reset")(self.h), "reset")
-
-    def step(self, t):
-        self._check(self._fn("step")(self.h, t), "step")
-
-    def run(self, t0, t1):
-        self._check(self._fn("run")(self.h, t0, t1), "run")
-
-    def seismogram(self):
-        out = np.zeros((self.n_rec, self.desc.nt), dtype=np.float32)
-        self._check(self._fn("get_seismogram")(self.h, _fp(out)), "get_seismogram")
-        return out
-
-    def wavefield(self, comp):
-        out = np.empty(self.n_local, dtype=np.float32)
-        self._check(self._fn("get_wavefield")(self.h, comp.encode(), _fp(out), C.c_size_t(out.size)), "get_wavefield")
-        return out
-
-    def set_wavefield(self, comp, arr):
-        a = _f32(arr).ravel()
-        self._check(self._fn("set_wavefield")(self.h, comp.encode(), _fp(a), C.c_size_t(a.size)), "set_wavefield")
-
-    def close(self):
-        if getattr(self, "h", None):
-            self._fn("destroy")(self.h)
-            self.h = None
-
-    def __del__(self):
-        try:
-            self.close()
-        except Exception:
-            pass
-
-
-class Oracle(_Base):
+class Oracle(SolverBase):
     prefix = "wso_"
 
     def __init__(self, desc, precision=32):
@@ -195,99 +94,6 @@ def ricker(nt, dt, fc, amp, tshift=0.0):
     return out
 
 
-def ricker_np(nt, dt, fc, amp, tshift=0.0):
-    """Independent numpy statement of the same wavelet (float32 op by op); used by bench/product code paths that must
-    not touch oracle/."""
-    f = np.float32
-    t = np.arange(nt, dtype=np.float32) * f(dt)
-    helpv = f(1.5 / fc + tshift)
-    tau = (t - helpv) * f(np.pi * fc)
-    h2 = tau * tau
-    e = np.exp(-h2).astype(np.float32)
-    return ((f(amp) * (f(1.0) - f(2.0) * h2)) * e).astype(np.float32)
-
-
-def _load_ws_lib(path):
-    lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
-    lib.ws_destroy.argtypes = [C.c_void_p]
-    lib.ws_launch_count.restype = C.c_uint64
-    lib.ws_launch_count.argtypes = [C.c_void_p]
-    lib.ws_estimate_memory.restype = C.c_size_t
-    lib.ws_stream.restype = C.c_void_p
-    lib.ws_stream.argtypes = [C.c_void_p]
-    lib.ws_uses_fast_kernels.argtypes = [C.c_void_p]
-    return lib
-
-
-class Solver(_Base):
-    """The product through its C ABI. Fails loudly if the CUDA library is missing: there is no CPU fallback."""
-    prefix = "ws_"
-    so_path = PRODUCT_SO
-
-    @classmethod
-    def _ensure_lib(cls):
-        if cls.lib is None:
-            if not os.path.exists(cls.so_path):
-                raise RuntimeError("CUDA library %s is missing: run `python -c 'import __graft_entry__ as g; g.build()'`"
-                                   % cls.so_path)
-            cls.lib = _load_ws_lib(cls.so_path)
-        return cls.lib
-
-    def __init__(self, desc):
-        self._ensure_lib()
-        self.desc = desc
-        self.h = C.c_void_p()
-        self.n_rec = 0
-        self._check(self.lib.ws_create(C.byref(desc), C.byref(self.h)), "create")
-        y0, nyl = C.c_int32(), C.c_int32()
-        self._check(self.lib.ws_local_range(self.h, C.byref(y0), C.byref(nyl)), "local_range")
-        self.y0, self.nyl = y0.value, nyl.value
-        self.n_local = desc.nx * desc.nz * self.nyl
-
-    def set_material_device(self, name, dev_ptr, n_local):
-        self._check(self.lib.ws_set_material_device(self.h, name.encode(), C.c_void_p(dev_ptr), C.c_size_t(n_local)),
-                    "set_material_device")
-
-    def sync(self):
-        self._check(self.lib.ws_sync(self.h), "sync")
-
-    def step_host(self, t, src_samples, rec_samples):
-        sp = _fp(src_samples) if src_samples is not None else None
-        self._check(self.lib.ws_step_host(self.h, t, sp, _fp(rec_samples)), "step_host")
-
-    def set_timing(self, enable):
-        self._check(self.lib.ws_set_timing(self.h, int(enable)), "set_timing")
-
-    def uses_fast_kernels(self):
-        return bool(self.lib.ws_uses_fast_kernels(self.h))
-
-    def launch_count(self):
-        return int(self.lib.ws_launch_count(self.h))
-
-    def last_timing(self, which):
-        ms = C.c_float()
-        self._check(self.lib.ws_last_timing(self.h, which, C.byref(ms)), "last_timing")
-        return ms.value
-
-    def is_finite(self):
-        f = C.c_int32()
-        self._check(self.lib.ws_is_finite(self.h, C.byref(f)), "is_finite")
-        return bool(f.value)
-
-    def comm_init(self, id_bytes):
-        buf = (C.c_char * 128).from_buffer_copy(id_bytes)
-        self._check(self.lib.ws_comm_init(self.h, buf), "comm_init")
-
-    @classmethod
-    def comm_unique_id(cls):
-        lib = cls._ensure_lib()
-        buf = (C.c_char * 128)()
-        rc = lib.ws_comm_unique_id(buf)
-        if rc != 0:
-            raise RuntimeError("ws_comm_unique_id failed")
-        return bytes(buf)
-
-
 def build_emu(force=False):
     """TEST INFRASTRUCTURE: host emulation build (-DWS_EMULATE) of the C ABI and the general kernels, tests/emu/."""
     src = os.path.join(ROOT, "wave-simulation_b200", "csrc")
@@ -315,11 +121,6 @@ class EmuSolver(Solver):
 # ---------------------------------------------------------------------------------------------------------------------
 # cases
 # ---------------------------------------------------------------------------------------------------------------------
-def idx1d(x, y, z, nx, nz):
-    """Acquisition/Coordinates.cpp:687."""
-    return x + z * nx + y * nx * nz
-
-
 def two_layer(nx, ny, nz, depth=40, visco=False):
     """Tools/CreateModel/TwoLayer.cpp:25-62 (vp 3500/4550, vs 2000/2600, rho 2000/2600, tau 0.1; interface at y=depth)."""
     shape = (ny, nz, nx)

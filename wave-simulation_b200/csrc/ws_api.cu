@@ -362,7 +362,7 @@ void validateDesc(const ws_desc &d)
         WS_REQUIRE(d.n_relax >= 1 && d.n_relax <= WS_MAX_RELAX, WS_EINVAL, "numRelaxationMechanisms more than 4 is not available here!");
     WS_REQUIRE(d.nranks >= 1 && d.rank >= 0 && d.rank < d.nranks, WS_EINVAL, "invalid rank / nranks");
     const int nz = d.dim == 2 ? 1 : d.nz;
-    WS_REQUIRE((long long)d.nx * d.ny * nz < (1LL << 31), WS_EINVAL, "global grid exceeds int32 linear indices (scai::IndexType)");
+    (void)nz; // grids beyond 2^31 points are accepted; they need the 64-bit acquisition entry points
     WS_REQUIRE(d.ny / d.nranks >= std::max(d.fd_order / 2, 1) * 2 || d.nranks == 1, WS_EINVAL, "y-slabs thinner than the stencil");
 }
 
@@ -1184,7 +1184,9 @@ int ws_prepare(ws_solver *s)
     });
 }
 
-int ws_set_sources(ws_solver *s, int32_t n, const int32_t *type, const int32_t *idx1d, const float *signals)
+} // extern "C"
+template <typename IdxT>
+static int setSourcesImpl(ws_solver *s, int32_t n, const int32_t *type, const IdxT *idx1d, const float *signals)
 {
     return guarded([&] {
         WS_REQUIRE(s && n >= 0 && (n == 0 || (type && idx1d && signals)), WS_EINVAL, "invalid source arguments");
@@ -1206,7 +1208,8 @@ int ws_set_sources(ws_solver *s, int32_t n, const int32_t *type, const int32_t *
                 const int slot = type[k] == WS_TYPE_EZ ? F_EZ : (type[k] == WS_TYPE_EX ? F_EX : (type[k] == WS_TYPE_EY ? F_EY : F_HZ));
                 WS_REQUIRE(s->fld[slot].p, WS_EINVAL, "source type has no wavefield in this modelling");
             }
-            const int y = idx1d[k] / (s->nx * s->nz), r = idx1d[k] % (s->nx * s->nz), z = r / s->nx, x = r % s->nx;
+            const long long pl = (long long)s->nx * s->nz;
+            const int y = (int)(idx1d[k] / pl), r = (int)(idx1d[k] % pl), z = r / s->nx, x = r % s->nx;
             off[k] = (y >= s->y0 && y < s->y0 + s->nyl) ? s->offsetOf(x, y - s->y0, z) : -1;
             if (++seen[{type[k], (long long)idx1d[k]}] > 1)
                 unique = false;
@@ -1226,7 +1229,8 @@ int ws_set_sources(ws_solver *s, int32_t n, const int32_t *type, const int32_t *
     });
 }
 
-int ws_set_receivers(ws_solver *s, int32_t n, const int32_t *type, const int32_t *idx1d)
+template <typename IdxT>
+static int setReceiversImpl(ws_solver *s, int32_t n, const int32_t *type, const IdxT *idx1d)
 {
     return guarded([&] {
         WS_REQUIRE(s && n >= 0 && (n == 0 || (type && idx1d)), WS_EINVAL, "invalid receiver arguments");
@@ -1247,7 +1251,8 @@ int ws_set_receivers(ws_solver *s, int32_t n, const int32_t *type, const int32_t
                 const int slot = type[k] == WS_TYPE_EZ ? F_EZ : (type[k] == WS_TYPE_EX ? F_EX : (type[k] == WS_TYPE_EY ? F_EY : F_HZ));
                 WS_REQUIRE(s->fld[slot].p, WS_EINVAL, "receiver type has no wavefield in this modelling");
             }
-            const int y = idx1d[k] / (s->nx * s->nz), r = idx1d[k] % (s->nx * s->nz), z = r / s->nx, x = r % s->nx;
+            const long long pl = (long long)s->nx * s->nz;
+            const int y = (int)(idx1d[k] / pl), r = (int)(idx1d[k] % pl), z = r / s->nx, x = r % s->nx;
             const bool mine = y >= s->y0 && y < s->y0 + s->nyl;
             off[k] = mine ? s->offsetOf(x, y - s->y0, z) : -1;
             s->recOwned[k] = mine ? 1 : 0;
@@ -1265,6 +1270,32 @@ int ws_set_receivers(ws_solver *s, int32_t n, const int32_t *type, const int32_t
         WS_CUDA_CHECK(cudaDeviceSynchronize());
         refreshAcq(s);
     });
+}
+
+extern "C" {
+int ws_set_sources(ws_solver *s, int32_t n, const int32_t *type, const int32_t *idx1d, const float *signals)
+{
+    if (s && (long long)s->nx * s->gny * s->nz >= (1LL << 31)) {
+        g_lastError = "grid exceeds int32 linear indices (scai::IndexType): use ws_set_sources64";
+        return WS_EINVAL;
+    }
+    return setSourcesImpl<int32_t>(s, n, type, idx1d, signals);
+}
+int ws_set_sources64(ws_solver *s, int32_t n, const int32_t *type, const int64_t *idx1d, const float *signals)
+{
+    return setSourcesImpl<int64_t>(s, n, type, idx1d, signals);
+}
+int ws_set_receivers(ws_solver *s, int32_t n, const int32_t *type, const int32_t *idx1d)
+{
+    if (s && (long long)s->nx * s->gny * s->nz >= (1LL << 31)) {
+        g_lastError = "grid exceeds int32 linear indices (scai::IndexType): use ws_set_receivers64";
+        return WS_EINVAL;
+    }
+    return setReceiversImpl<int32_t>(s, n, type, idx1d);
+}
+int ws_set_receivers64(ws_solver *s, int32_t n, const int32_t *type, const int64_t *idx1d)
+{
+    return setReceiversImpl<int64_t>(s, n, type, idx1d);
 }
 
 int ws_reset(ws_solver *s)
