@@ -293,6 +293,7 @@ struct ws_solver {
     std::vector<cudaEvent_t> evPool;
     float msA = 0, msB = 0, msStep = 0;
     bool useFast = false;
+    void *fastMaps = nullptr;
     // CUDA graph of one time step
     cudaGraphExec_t graphExec = nullptr;
     int graphSteps = 0;
@@ -301,6 +302,8 @@ struct ws_solver {
     {
         if (graphExec)
             cudaGraphExecDestroy(graphExec);
+        if (fastMaps)
+            wsFastRelease(fastMaps);
         for (auto e : evPool)
             cudaEventDestroy(e);
         if (evCompute)
@@ -569,6 +572,7 @@ void refreshParams(ws_solver *s)
     P.free_surface = s->seismic ? s->d.free_surface : 0; // EM solvers ignore FreeSurface (ForwardSolver2Dtmem.cpp:31-33)
     P.damping = s->d.damping; P.W = s->W;
     P.ylo = 0; P.yhi = s->nyl;
+    P.edge_policy = s->d.edge_policy;
     P.tab = s->tab.p;
     P.cax = s->cax.p; P.cbx = s->cbx.p; P.caxh = s->caxh.p; P.cbxh = s->cbxh.p;
     P.cay = s->cay.p; P.cby = s->cby.p; P.cayh = s->cayh.p; P.cbyh = s->cbyh.p;
@@ -1178,6 +1182,12 @@ int ws_prepare(ws_solver *s)
         prepareBoundaries(s);
         refreshParams(s);
         s->useFast = s->d.kernel_variant == 0 && wsFastSupported(s->P, s->exact);
+        if (s->fastMaps) {
+            wsFastRelease(s->fastMaps);
+            s->fastMaps = nullptr;
+        }
+        if (s->useFast)
+            s->fastMaps = wsFastPrepare(s->P, s->nyl + 2 * WS_HALO);
         WS_CUDA_CHECK(cudaStreamSynchronize(s->stream));
         WS_CUDA_CHECK(cudaGetLastError());
         s->prepared = true;

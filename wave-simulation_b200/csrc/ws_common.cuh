@@ -71,6 +71,9 @@ struct WsParams {
     int dim, eq, q, h, L;
     int free_surface, damping, W;
     int ylo, yhi;     // local y range [ylo, yhi) processed by this launch (interior/boundary split for overlap)
+    int edge_policy;  // 0 truncate | 1 order-reduce
+    int fastChunk;    // planes per thread block of the tiled kernels
+    const void *fastMaps; // device array of CUtensorMap (tiled kernels)
     const float *tab; // derivative weight tables [WS_NOPS][2h+1][q+1], already scaled by DT/DH
     // CPML coefficients, 2W entries per array: k < W low-coordinate side, k >= W high-coordinate side (CPML3D.cpp:297-317)
     const float *cax, *cbx, *caxh, *cbxh, *cay, *cby, *cayh, *cbyh, *caz, *cbz, *cazh, *cbzh;
@@ -99,9 +102,11 @@ template <> struct Ar<true> {
     static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
 };
 template <> struct Ar<false> {
-    static __device__ __forceinline__ float mul(float a, float b) { return a * b; }
-    static __device__ __forceinline__ float add(float a, float b) { return a + b; }
-    static __device__ __forceinline__ float sub(float a, float b) { return a - b; }
+    // only the explicit multiply-adds fuse; everything else keeps its own rounding, so the result does not depend on
+    // the compiler's contraction choices (general kernels, tiled kernels and the host emulation agree bit for bit)
+    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+    static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
     static __device__ __forceinline__ float madd(float a, float b, float c) { return fmaf(a, b, c); }
     static __device__ __forceinline__ float msub(float a, float b, float c) { return fmaf(-a, b, c); }
     static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }

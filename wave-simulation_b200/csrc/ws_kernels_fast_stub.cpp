@@ -2,4 +2,6 @@
 // cannot be emulated on the host, so that build always takes the general kernels.
 #include "ws_launch.hpp"
 bool wsFastSupported(const WsParams &, bool) { return false; }
+void *wsFastPrepare(WsParams &, int) { return nullptr; }
+void wsFastRelease(void *) {}
 bool wsLaunchFast(const WsParams &, int, cudaStream_t) { return false; }

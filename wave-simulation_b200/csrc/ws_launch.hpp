@@ -9,4 +9,8 @@ void wsLaunchAbsFirstHalf(const WsParams &P, bool exact, int f0, int f1, int f2,
 
 // tiled fast kernels (ws_kernels_fast.cu); return false when the configuration is not covered
 bool wsFastSupported(const WsParams &P, bool exact);
+// builds the TMA tensor maps for this solver's arrays into a device buffer (returned, owned by the caller; freed with
+// wsFastRelease) and fills P.fastMaps / P.fastChunk
+void *wsFastPrepare(WsParams &P, int nyp);
+void wsFastRelease(void *maps);
 bool wsLaunchFast(const WsParams &P, int pass, cudaStream_t st);
