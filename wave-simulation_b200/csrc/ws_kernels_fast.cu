@@ -1,17 +1,20 @@
-// ws_kernels_fast.cu — tiled sm_100a kernels for the 3-D elastic hot path (FD3Delastic::run,
+// ws_kernels_fast.cu — warp-specialised sm_100a kernels for the 3-D elastic hot path (FD3Delastic::run,
 // ForwardSolver/ForwardSolver3Delastic.cpp:120-414): one fused kernel per half-step.
 //
-// Structure (2.5-D blocking):
+// Structure (2.5-D blocking, producer / consumer pipeline):
 //   * a thread block owns a TX x TZ tile of the x-z plane and marches along y (the slowest axis);
-//   * every thread owns 4 consecutive x points (128-bit accesses) of one z row;
-//   * the 3 fields that are differentiated along y in this half-step live in REGISTER QUEUES (Q planes deep);
-//   * the tiles needed for the x and z stencils (with their halos) are staged in SHARED MEMORY by TMA
-//     (cp.async.bulk.tensor.3d + mbarrier, 3-stage ring), prefetched two planes ahead of the compute;
-//   * operands touched only at the own point (updated fields, model parameters, queue feed) are plain coalesced
-//     128-bit global accesses issued at the top of the iteration, consumed at its end;
+//   * ONE PRODUCER WARP streams, per plane, every operand of that plane into a ring of NST shared-memory stages with TMA
+//     (cp.async.bulk.tensor.3d, completion on a "full" mbarrier per stage): halo tiles for the x / z stencils, the plane
+//     that enters the y-derivative window, and the own-point operands (updated fields, model parameters).  Consumer
+//     threads never wait on DRAM: up to NST-1 planes (~100 KB per SM) are in flight while one is being computed;
+//   * CONSUMER GROUPS split the work by OUTPUT COMPONENT (velocity half-step: vx | vy | vz; stress half-step:
+//     sxx,syy,szz | sxy | sxz | syz).  Every thread owns 4 consecutive x points (128-bit shared / global accesses) and
+//     keeps only the ONE field it differentiates along y in a register queue (Q planes deep), so the kernels run with
+//     ~100 registers and 13-17 warps per SM instead of 230 registers and 8 warps;
+//   * a stage is handed back to the producer through an "empty" mbarrier (one arrival per consumer warp);
 //   * off-grid taps read the zero pads of the HBM layout (StencilMatrix "drop off-grid taps", edge_policy 0);
-//   * image-method free surface: per-plane y weights for the first q/2 planes + surface correction in the stress kernel;
-//   * CPML: memory variables in compact boundary slabs, touched only by tiles / planes / rows inside the layers.
+//   * image-method free surface: per-plane y weights (the reference's DyfFreeSurface / DybFreeSurface rows) + surface
+//     correction in the stress kernel; CPML: memory variables in compact boundary slabs, loaded before the stage wait.
 // The arithmetic sequence is the one of the general kernels (ws_kernels_general.cuh) in FMA mode, so both produce
 // bit-identical results.
 #include "../../include/wavesim.h"
@@ -25,20 +28,29 @@
 
 namespace {
 
-constexpr int TX = 64, TZ = 16, NTHREADS = 256, NSTAGE = 3;
+constexpr int TX = 64, TZ = 8, NST = 4;
+constexpr int NG_VEL = 3, NG_STR = 3;
 
 template <int Q> struct Cfg {
     static constexpr int H = Q / 2;
     static constexpr int HX = (H <= 4) ? 4 : 8; // x halo rounded to a float4
     static constexpr int TXH = TX + 2 * HX;
     static constexpr int TZH = TZ + 2 * H;
+    static constexpr int LXN = TX / 4;
+    static constexpr int NTG = LXN * TZ; // threads per consumer group
+    static constexpr int WPG = NTG / 32; // warps per group
+    // tile sizes (floats); all are multiples of 32 floats = 128 bytes
+    static constexpr int N_P = TX * TZ, N_X = TXH * TZ, N_Z = TX * TZH, N_XZ = TXH * TZH;
+    static_assert(NTG % 32 == 0, "consumer groups must be whole warps");
+    static_assert(N_P % 32 == 0 && N_X % 32 == 0 && N_Z % 32 == 0 && N_XZ % 32 == 0, "TMA destinations must stay 128-byte aligned");
 };
-constexpr uint32_t al128(uint32_t v) { return (v + 127u) & ~127u; }
 
 // tensor-map slots (one CUtensorMap per array and box shape)
 enum {
-    TM_SXX_X = 0, TM_SXY_X, TM_SXZ_XZ, TM_SYZ_Z, TM_SZZ_Z, // velocity half-step
-    TM_VX_XZ, TM_VY_XZ, TM_VZ_XZ,                           // stress half-step
+    TM_SXX_X = 0, TM_SXY_X, TM_SXZ_XZ, TM_SYZ_Z, TM_SZZ_Z, TM_SXY_P, TM_SYY_P, TM_SYZ_P, // velocity half-step
+    TM_VX_P, TM_VY_P, TM_VZ_P, TM_RIX_P, TM_RIY_P, TM_RIZ_P,
+    TM_VX_XZ, TM_VY_XZ, TM_VZ_XZ,                                                         // stress half-step
+    TM_SXX_P, TM_SZZ_P, TM_SXZ_P, TM_PW_P, TM_MU_P, TM_MUXY_P, TM_MUXZ_P, TM_MUYZ_P,
     TM_COUNT
 };
 
@@ -51,16 +63,20 @@ __device__ __forceinline__ void mbarExpectTx(uint64_t *bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemU32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbarArrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smemU32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbarWait(uint64_t *bar, uint32_t parity)
 {
     asm volatile(
         "{\n"
         ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
+        "LAB_WAIT_%=:\n"
         "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
+        "@P1 bra DONE_%=;\n"
+        "bra LAB_WAIT_%=;\n"
+        "DONE_%=:\n"
         "}\n" ::"r"(smemU32(bar)),
         "r"(parity)
         : "memory");
@@ -70,6 +86,10 @@ __device__ __forceinline__ void tmaLoad3D(void *dst, const CUtensorMap *map, uin
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smemU32(dst)),
                  "l"((unsigned long long)map), "r"(smemU32(bar)), "r"(c0), "r"(c1), "r"(c2)
                  : "memory");
+}
+__device__ __forceinline__ void tmaPrefetchDesc(const CUtensorMap *map)
+{
+    asm volatile("prefetch.tensormap [%0];" ::"l"((unsigned long long)map) : "memory");
 }
 
 struct F4 {
@@ -90,6 +110,8 @@ __device__ __forceinline__ F4 ldg4(const float *p)
     return r;
 }
 __device__ __forceinline__ void st4(float *p, const F4 &a) { *reinterpret_cast<float4 *>(p) = make_float4(a.v[0], a.v[1], a.v[2], a.v[3]); }
+// streaming store: the written plane is not read again before the whole grid has been swept
+__device__ __forceinline__ void st4cs(float *p, const F4 &a) { __stcs(reinterpret_cast<float4 *>(p), make_float4(a.v[0], a.v[1], a.v[2], a.v[3])); }
 __device__ __forceinline__ F4 zero4()
 {
     F4 r;
@@ -144,91 +166,279 @@ template <int Q> __device__ __forceinline__ F4 dY(const F4 (&q)[Q], const float 
             r.v[p] = A::madd(w[j], q[j].v[p], r.v[p]);
     return r;
 }
-// CPML.cpp:84-95 on one value
-__device__ __forceinline__ float cpml1(float d, float *ps, float a, float b)
-{
-    float v = A::mul(*ps, b);
-    const float t = A::mul(a, d);
-    v = A::add(v, t);
-    *ps = v;
-    return A::add(d, v);
-}
 
-struct Cp { // per-thread CPML bookkeeping
-    int kx[4];
-    int kz, ky;
-    long long pxBase, pzBase; // psi offsets without the ly-dependent part
+// ---------------------------------------------------------------------------------------------------------------------
+// CPML (CPML.cpp:84-95 applyCPML): psi = b psi + a d ; d = d + psi.  The memory variables live in compact slabs
+// (x: [ly][z][2W], y: [2W][z][x], z: [ly][2W][x]); their loads are issued before the stage wait.
+// ---------------------------------------------------------------------------------------------------------------------
+struct CpT { // per-thread, constant over the march
+    bool active, anyX;
+    int kx[4], kz;
+    long long pxBase, pzBase;
+    float xa[4], xb[4], za, zb;
+};
+struct CpI { // per iteration
+    int ky;
+    float ya, yb;
+    long long pxOff, pyOff, pzOff;
+    float px[4];
+    F4 py, pz, pz2;
 };
 
-template <bool CPML> __device__ __forceinline__ void cpX(const WsParams &P, const Cp &cp, F4 &d, int slot, bool half, long long lyTerm)
+template <bool CPML> __device__ __forceinline__ void cpSetup(const WsParams &P, CpT &t, bool active, int x0, int z, bool halfX, bool halfZ)
 {
-    if (!CPML)
+    t.active = active;
+    t.anyX = false;
+    t.kz = -1;
+    t.pxBase = t.pzBase = 0;
+    t.za = t.zb = 0.0f;
+#pragma unroll
+    for (int p = 0; p < 4; p++) {
+        t.kx[p] = -1;
+        t.xa[p] = t.xb[p] = 0.0f;
+    }
+    if (!CPML || !active)
         return;
-    const float *ca = half ? P.caxh : P.cax, *cb = half ? P.cbxh : P.cbx;
+    const int W = P.W;
+    const float *ca = halfX ? P.caxh : P.cax, *cb = halfX ? P.cbxh : P.cbx;
+#pragma unroll
+    for (int p = 0; p < 4; p++) {
+        t.kx[p] = wsCpmlIndex(x0 + p, P.nx, W);
+        if (t.kx[p] >= 0) {
+            t.anyX = true;
+            t.xa[p] = __ldg(ca + t.kx[p]);
+            t.xb[p] = __ldg(cb + t.kx[p]);
+        }
+    }
+    t.kz = wsCpmlIndex(z, P.nz, W);
+    if (t.kz >= 0) {
+        t.za = __ldg((halfZ ? P.cazh : P.caz) + t.kz);
+        t.zb = __ldg((halfZ ? P.cbzh : P.cbz) + t.kz);
+    }
+    t.pxBase = (long long)z * (2 * W);
+    t.pzBase = (long long)t.kz * P.nx + x0;
+}
+// issue the loads of this plane's memory variables (x slot sx, y slot sy, z slot sz)
+template <bool CPML, int sx, int sy, int sz, int sz2 = -1> __device__ __forceinline__ void cpLoad(const WsParams &P, const CpT &t, CpI &it, int ly, int gy, int x0, int z, bool halfY)
+{
+    it.ky = -1;
+    if (!CPML || !t.active)
+        return;
+    const int W = P.W;
+    it.ky = wsCpmlIndex(gy, P.gny, W);
+    if (P.free_surface != 0 && gy < W)
+        it.ky = -1; // no CPML in the top layer below a free surface (CPML3D.cpp:320-328)
+    it.pxOff = (long long)ly * P.nz * (2 * W) + t.pxBase;
+    it.pzOff = (long long)ly * (2 * W) * P.nx + t.pzBase;
+    it.pyOff = ((long long)it.ky * P.nz + z) * P.nx + x0;
+    if (sx >= 0 && t.anyX) {
+#pragma unroll
+        for (int p = 0; p < 4; p++)
+            if (t.kx[p] >= 0)
+                it.px[p] = P.psi[sx >= 0 ? sx : 0][it.pxOff + t.kx[p]];
+    }
+    if (sy >= 0 && it.ky >= 0) {
+        it.ya = __ldg((halfY ? P.cayh : P.cay) + it.ky);
+        it.yb = __ldg((halfY ? P.cbyh : P.cby) + it.ky);
+        it.py = ld4(P.psi[sy >= 0 ? sy : 0] + it.pyOff);
+    }
+    if (sz >= 0 && t.kz >= 0)
+        it.pz = ld4(P.psi[sz >= 0 ? sz : 0] + it.pzOff);
+    if (sz2 >= 0 && t.kz >= 0)
+        it.pz2 = ld4(P.psi[sz2 >= 0 ? sz2 : 0] + it.pzOff);
+}
+template <bool CPML> __device__ __forceinline__ void cpApplyX(const WsParams &P, const CpT &t, const CpI &it, F4 &d, int slot)
+{
+    if (!CPML || !t.anyX)
+        return;
 #pragma unroll
     for (int p = 0; p < 4; p++)
-        if (cp.kx[p] >= 0)
-            d.v[p] = cpml1(d.v[p], P.psi[slot] + lyTerm + cp.pxBase + cp.kx[p], __ldg(ca + cp.kx[p]), __ldg(cb + cp.kx[p]));
+        if (t.kx[p] >= 0) {
+            float v = A::mul(it.px[p], t.xb[p]);
+            v = A::add(v, A::mul(t.xa[p], d.v[p]));
+            P.psi[slot][it.pxOff + t.kx[p]] = v;
+            d.v[p] = A::add(d.v[p], v);
+        }
 }
-template <bool CPML> __device__ __forceinline__ void cpY(const WsParams &P, const Cp &cp, F4 &d, int slot, bool half, long long pyOff)
+__device__ __forceinline__ void cpApply4(float *ps, const F4 &old, float a, float b, F4 &d)
 {
-    if (!CPML || cp.ky < 0)
-        return;
-    const float a = __ldg((half ? P.cayh : P.cay) + cp.ky), b = __ldg((half ? P.cbyh : P.cby) + cp.ky);
-    float *ps = P.psi[slot] + pyOff;
-    F4 old = ld4(ps), nw;
+    F4 nw;
 #pragma unroll
     for (int p = 0; p < 4; p++) {
         float v = A::mul(old.v[p], b);
-        const float t = A::mul(a, d.v[p]);
-        v = A::add(v, t);
+        v = A::add(v, A::mul(a, d.v[p]));
         nw.v[p] = v;
         d.v[p] = A::add(d.v[p], v);
     }
     st4(ps, nw);
 }
-template <bool CPML> __device__ __forceinline__ void cpZ(const WsParams &P, const Cp &cp, F4 &d, int slot, bool half, long long pzOff)
+template <bool CPML> __device__ __forceinline__ void cpApplyY(const WsParams &P, const CpT &t, const CpI &it, F4 &d, int slot)
 {
-    if (!CPML || cp.kz < 0)
+    if (!CPML || !t.active || it.ky < 0)
         return;
-    const float a = __ldg((half ? P.cazh : P.caz) + cp.kz), b = __ldg((half ? P.cbzh : P.cbz) + cp.kz);
-    float *ps = P.psi[slot] + pzOff;
-    F4 old = ld4(ps), nw;
+    cpApply4(P.psi[slot] + it.pyOff, it.py, it.ya, it.yb, d);
+}
+template <bool CPML> __device__ __forceinline__ void cpApplyZ(const WsParams &P, const CpT &t, const CpI &it, F4 &d, int slot)
+{
+    if (!CPML || t.kz < 0)
+        return;
+    cpApply4(P.psi[slot] + it.pzOff, it.pz, t.za, t.zb, d);
+}
+template <bool CPML> __device__ __forceinline__ void cpApplyZ2(const WsParams &P, const CpT &t, const CpI &it, F4 &d, int slot)
+{
+    if (!CPML || t.kz < 0)
+        return;
+    cpApply4(P.psi[slot] + it.pzOff, it.pz2, t.za, t.zb, d);
+}
+// interior weights (same on every axis; policy 0): forward taps are table indices 1..Q of the interior row
+template <int Q> __device__ __forceinline__ void loadInterior(const WsParams &P, float (&c)[Q])
+{
+    constexpr int H = Q / 2;
+    const float *w = P.tab + ((size_t)OP_XF * (2 * H + 1) + H) * (Q + 1);
 #pragma unroll
-    for (int p = 0; p < 4; p++) {
-        float v = A::mul(old.v[p], b);
-        const float t = A::mul(a, d.v[p]);
-        v = A::add(v, t);
-        nw.v[p] = v;
-        d.v[p] = A::add(d.v[p], v);
-    }
-    st4(ps, nw);
+    for (int j = 0; j < Q; j++)
+        c[j] = __ldg(w + 1 + j);
+}
+// y weights of the velocity half-step for global plane gy: with a free surface every row comes from the image-method
+// operators (their interior rows are scaled (c/DH)*DT, not c*(DT/DH): Derivatives.cpp:407-425 vs FDTD3D.cpp:211-216)
+template <int Q, bool FWD> __device__ __forceinline__ void loadYWeights(const WsParams &P, int gy, float (&w)[Q])
+{
+    constexpr int H = Q / 2;
+    const int op = P.free_surface == 1 ? (FWD ? OP_YF_FS : OP_YB_FS) : (FWD ? OP_YF : OP_YB);
+    const int row = (P.free_surface == 1 && gy < H) ? max(gy, 0) : H;
+    const float *t = P.tab + ((size_t)op * (2 * H + 1) + row) * (Q + 1) + (FWD ? 1 : 0);
+#pragma unroll
+    for (int j = 0; j < Q; j++)
+        w[j] = __ldg(t + j);
 }
 
-template <int Q> struct SmemA { // velocity half-step stage layout (bytes)
+// ---------------------------------------------------------------------------------------------------------------------
+// shared-memory stage layouts (offsets in floats)
+// ---------------------------------------------------------------------------------------------------------------------
+template <int Q> struct StageV { // velocity half-step
     using C = Cfg<Q>;
-    static constexpr uint32_t SZ_X = al128(TZ * C::TXH * 4), SZ_XZ = al128(C::TZH * C::TXH * 4), SZ_Z = al128(C::TZH * TX * 4);
-    static constexpr uint32_t OFF_SXX = 0, OFF_SXY = SZ_X, OFF_SXZ = 2 * SZ_X, OFF_SYZ = 2 * SZ_X + SZ_XZ, OFF_SZZ = OFF_SYZ + SZ_Z;
-    static constexpr uint32_t STAGE = OFF_SZZ + SZ_Z;
-    static constexpr uint32_t TXBYTES = 2 * TZ * C::TXH * 4 + C::TZH * C::TXH * 4 + 2 * C::TZH * TX * 4;
+    static constexpr int SXX = 0, SXY = SXX + C::N_X, SXZ = SXY + C::N_X, SYZ = SXZ + C::N_XZ, SZZ = SYZ + C::N_Z;
+    static constexpr int FEED = SZZ + C::N_Z;      // 3 plain tiles: Sxy(y+H-1), Syy(y+H), Syz(y+H-1)
+    static constexpr int OWNV = FEED + 3 * C::N_P; // vx vy vz
+    static constexpr int OWNR = OWNV + 3 * C::N_P; // rix riy riz
+    static constexpr int SIZE = OWNR + 3 * C::N_P;
+    static constexpr uint32_t BYTES_FEED = 3u * C::N_P * 4u;
+    static constexpr uint32_t BYTES_FULL = (uint32_t)SIZE * 4u;
 };
-template <int Q> struct SmemB { // stress half-step stage layout
+template <int Q> struct StageS { // stress half-step
     using C = Cfg<Q>;
-    static constexpr uint32_t SZ_XZ = al128(C::TZH * C::TXH * 4);
-    static constexpr uint32_t OFF_VX = 0, OFF_VY = SZ_XZ, OFF_VZ = 2 * SZ_XZ, STAGE = 3 * SZ_XZ;
-    static constexpr uint32_t TXBYTES = 3 * C::TZH * C::TXH * 4;
+    static constexpr int TV = 0;                    // 3 XZ tiles: vx vy vz
+    static constexpr int FEED = TV + 3 * C::N_XZ;   // 3 plain tiles: vx(y+H), vy(y+H-1), vz(y+H)
+    static constexpr int OWNS = FEED + 3 * C::N_P;  // sxx syy szz sxy sxz syz
+    static constexpr int OWNM = OWNS + 6 * C::N_P;  // pi mu muxy muxz muyz
+    static constexpr int SIZE = OWNM + 5 * C::N_P;
+    static constexpr uint32_t BYTES_FEED = 3u * C::N_P * 4u;
+    static constexpr uint32_t BYTES_FULL = (uint32_t)SIZE * 4u;
+};
+
+struct Bars {
+    uint64_t full[NST], empty[NST];
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
 // velocity half-step (ForwardSolver3Delastic.cpp:181-277)
+//   group 0: vx += rix * (Dxf Sxx + Dyb* Sxy + Dzb Sxz)      group 1: vy += riy * (Dxb Sxy + Dyf* Syy + Dzb Syz)
+//   group 2: vz += riz * (Dxb Sxz + Dyb* Syz + Dzf Szz)
 // ---------------------------------------------------------------------------------------------------------------------
-template <int Q, bool CPML> __global__ void __launch_bounds__(NTHREADS, 1) kFastVel(const __grid_constant__ WsParams P)
+template <int Q, bool CPML, int G>
+__device__ __forceinline__ void velConsumer(const WsParams &P, const float *sm, Bars *bars, int tg, int tx0, int tz0, int yc0, int yc1)
 {
     using C = Cfg<Q>;
-    using S = SmemA<Q>;
+    using S = StageV<Q>;
     constexpr int H = C::H, HX = C::HX, TXH = C::TXH;
+    constexpr bool YFWD = (G == 1);
+    const int lx = tg % C::LXN, lz = tg / C::LXN;
+    const int x0 = tx0 + 4 * lx, z = tz0 + lz;
+    const bool active = (x0 < P.nx) && (z < P.nz);
+    const int lane = threadIdx.x & 31;
+
+    float c[Q], wy[Q];
+    loadInterior<Q>(P, c);
+    loadYWeights<Q, YFWD>(P, H, wy);
+    const long long rowOff = P.base + x0 + (long long)z * P.pitch;
+    float *gv = P.fld[F_VX + G] + rowOff;
+
+    constexpr int sx = (G == 0) ? PSI_SXX_X : (G == 1 ? PSI_SXY_X : PSI_SXZ_X);
+    constexpr int sy = (G == 0) ? PSI_SXY_Y : (G == 1 ? PSI_SYY_Y : PSI_SYZ_Y);
+    constexpr int sz = (G == 0) ? PSI_SXZ_Z : (G == 1 ? PSI_SYZ_Z : PSI_SZZ_Z);
+    CpT cpt;
+    cpSetup<CPML>(P, cpt, active, x0, z, /*halfX*/ G == 0, /*halfZ*/ G == 2);
+
+    // shared-memory offsets of this thread inside a stage
+    const int oX = (G == 0 ? S::SXX : (G == 1 ? S::SXY : S::SXZ + H * TXH)) + lz * TXH + 4 * lx; // column of x0 - HX
+    const int oZ = (G == 0 ? S::SXZ + lz * TXH + 4 * lx + HX : (G == 1 ? S::SYZ : S::SZZ) + lz * TX + 4 * lx);
+    constexpr int ldZ = (G == 0) ? TXH : TX;
+    const int oP = lz * TX + 4 * lx;
+
+    F4 q[Q];
+#pragma unroll
+    for (int k = 0; k < Q; k++)
+        q[k] = zero4();
+
+    const int nIter = (Q - 1) + (yc1 - yc0);
+    int stage = 0;
+    uint32_t parity = 0;
+    for (int it = 0; it < nIter; it++) {
+        const int ly = yc0 - (Q - 1) + it;
+        const int gy = P.gy0 + ly;
+        const bool comp = it >= Q - 1;
+        CpI cpi;
+        cpi.ky = -1;
+        if (comp) {
+            cpLoad<CPML, sx, sy, sz>(P, cpt, cpi, ly, gy, x0, z, /*halfY*/ G == 1);
+            if (P.free_surface == 1 && gy <= H)
+                loadYWeights<Q, YFWD>(P, gy, wy);
+        }
+        mbarWait(&bars->full[stage], parity);
+        const float *st = sm + stage * S::SIZE;
+        q[Q - 1] = ld4(st + S::FEED + G * C::N_P + oP);
+        if (comp) {
+            F4 u = dX<Q, G == 0>(st + oX, c);
+            cpApplyX<CPML>(P, cpt, cpi, u, sx);
+            F4 w = dY<Q>(q, wy);
+            cpApplyY<CPML>(P, cpt, cpi, w, sy);
+#pragma unroll
+            for (int p = 0; p < 4; p++)
+                u.v[p] = A::add(u.v[p], w.v[p]);
+            w = dZ<Q, G == 2>(st + oZ, ldZ, c);
+            cpApplyZ<CPML>(P, cpt, cpi, w, sz);
+            F4 v = ld4(st + S::OWNV + G * C::N_P + oP);
+            const F4 r = ld4(st + S::OWNR + G * C::N_P + oP);
+#pragma unroll
+            for (int p = 0; p < 4; p++) {
+                u.v[p] = A::add(u.v[p], w.v[p]);
+                u.v[p] = A::mul(u.v[p], r.v[p]);
+                v.v[p] = A::add(v.v[p], u.v[p]);
+            }
+            if (active)
+                st4cs(gv + (long long)ly * P.plane, v);
+        }
+        __syncwarp();
+        if (lane == 0)
+            mbarArrive(&bars->empty[stage]);
+#pragma unroll
+        for (int k = 0; k < Q - 1; k++)
+            q[k] = q[k + 1];
+        if (++stage == NST) {
+            stage = 0;
+            parity ^= 1;
+        }
+    }
+}
+
+template <int Q, bool CPML> __global__ void __launch_bounds__(NG_VEL *Cfg<Q>::NTG + 32, 1) kFastVel(const __grid_constant__ WsParams P)
+{
+    using C = Cfg<Q>;
+    using S = StageV<Q>;
+    constexpr int H = C::H, HX = C::HX;
     extern __shared__ __align__(1024) unsigned char smraw[];
-    __shared__ __align__(8) uint64_t bars[NSTAGE];
+    __shared__ __align__(8) Bars bars;
+    float *sm = reinterpret_cast<float *>(smraw);
     const CUtensorMap *maps = reinterpret_cast<const CUtensorMap *>(P.fastMaps);
 
     const int tid = threadIdx.x;
@@ -237,207 +447,228 @@ template <int Q, bool CPML> __global__ void __launch_bounds__(NTHREADS, 1) kFast
     const int yc1 = min(P.yhi, yc0 + P.fastChunk);
     if (yc0 >= yc1)
         return;
-    const int lx = tid & 15, lz = tid >> 4;
-    const int x0 = tx0 + 4 * lx, z = tz0 + lz;
-    const bool active = (x0 < P.nx) && (z < P.nz);
-    const int HZP = (P.nzp > 1) ? WS_HALO : 0;
-
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < NSTAGE; s++)
-            mbarInit(&bars[s], 1);
+        for (int s = 0; s < NST; s++) {
+            mbarInit(&bars.full[s], 1);
+            mbarInit(&bars.empty[s], NG_VEL * C::WPG);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    auto issue = [&](int ly, int stage) {
-        unsigned char *st = smraw + stage * S::STAGE;
-        uint64_t *bar = &bars[stage];
-        mbarExpectTx(bar, S::TXBYTES);
-        const int cy = WS_HALO + ly, cx = WS_PADX + tx0, cz = HZP + tz0;
-        tmaLoad3D(st + S::OFF_SXX, &maps[TM_SXX_X], bar, cx - HX, cz, cy);
-        tmaLoad3D(st + S::OFF_SXY, &maps[TM_SXY_X], bar, cx - HX, cz, cy);
-        tmaLoad3D(st + S::OFF_SXZ, &maps[TM_SXZ_XZ], bar, cx - HX, cz - H, cy);
-        tmaLoad3D(st + S::OFF_SYZ, &maps[TM_SYZ_Z], bar, cx, cz - H, cy);
-        tmaLoad3D(st + S::OFF_SZZ, &maps[TM_SZZ_Z], bar, cx, cz - H, cy);
-    };
-    if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < NSTAGE - 1; s++)
-            if (yc0 + s < yc1)
-                issue(yc0 + s, s);
-    }
-
-    // interior weights (same on every axis; policy 0): forward taps are table indices 1..Q of the interior row
-    float c[Q];
-    {
-        const float *w = P.tab + ((size_t)OP_XF * (2 * H + 1) + H) * (Q + 1);
-#pragma unroll
-        for (int j = 0; j < Q; j++)
-            c[j] = __ldg(w + 1 + j);
-    }
-    const long long rowOff = P.base + x0 + (long long)z * P.pitch;
-    const float *gsxy = P.fld[F_SXY] + rowOff, *gsyy = P.fld[F_SYY] + rowOff, *gsyz = P.fld[F_SYZ] + rowOff;
-    float *gvx = P.fld[F_VX] + rowOff, *gvy = P.fld[F_VY] + rowOff, *gvz = P.fld[F_VZ] + rowOff;
-    const float *grx = P.mat[M_RIX] + rowOff, *gry = P.mat[M_RIY] + rowOff, *grz = P.mat[M_RIZ] + rowOff;
-
-    Cp cp;
-    cp.kz = cp.ky = -1;
-    cp.pxBase = cp.pzBase = 0;
-#pragma unroll
-    for (int p = 0; p < 4; p++)
-        cp.kx[p] = -1;
-    bool anyX = false;
-    if (CPML && active) {
-        const int W = P.W;
-#pragma unroll
-        for (int p = 0; p < 4; p++) {
-            cp.kx[p] = wsCpmlIndex(x0 + p, P.nx, W);
-            anyX |= cp.kx[p] >= 0;
-        }
-        cp.kz = wsCpmlIndex(z, P.nz, W);
-        cp.pxBase = (long long)z * (2 * W);
-        cp.pzBase = (long long)cp.kz * P.nx + x0;
-    }
-
-    // register queues: qxy/qyz[k] = plane y-H+k (backward window), qyy[k] = plane y-H+1+k (forward window)
-    F4 qxy[Q], qyy[Q], qyz[Q];
-#pragma unroll
-    for (int k = 0; k < Q - 1; k++) {
-        if (active) {
-            qxy[k] = ldg4(gsxy + (long long)(yc0 - H + k) * P.plane);
-            qyz[k] = ldg4(gsyz + (long long)(yc0 - H + k) * P.plane);
-            qyy[k] = ldg4(gsyy + (long long)(yc0 - H + 1 + k) * P.plane);
-        } else {
-            qxy[k] = zero4(); qyz[k] = zero4(); qyy[k] = zero4();
-        }
-    }
-
-    int stage = 0;
-    uint32_t parity = 0;
-    for (int ly = yc0; ly < yc1; ly++) {
-        const int gy = P.gy0 + ly;
-        const long long po = (long long)ly * P.plane;
-        // own-point operands of this plane, issued before the barrier wait
-        F4 vx, vy, vz, rx, ry, rz;
-        if (active) {
-            qxy[Q - 1] = ldg4(gsxy + (long long)(ly + H - 1) * P.plane);
-            qyz[Q - 1] = ldg4(gsyz + (long long)(ly + H - 1) * P.plane);
-            qyy[Q - 1] = ldg4(gsyy + (long long)(ly + H) * P.plane);
-            vx = ld4(gvx + po); vy = ld4(gvy + po); vz = ld4(gvz + po);
-            rx = ldg4(grx + po); ry = ldg4(gry + po); rz = ldg4(grz + po);
-        } else {
-            qxy[Q - 1] = zero4(); qyz[Q - 1] = zero4(); qyy[Q - 1] = zero4();
-            vx = vy = vz = rx = ry = rz = zero4();
-        }
-        // per-plane y weights: image method on the first H planes below the free surface, interior weights elsewhere
-        float wyb[Q], wyf[Q];
-        if (P.free_surface == 1 && gy < H) {
-            const float *tb = P.tab + ((size_t)OP_YB_FS * (2 * H + 1) + gy) * (Q + 1);
-            const float *tf = P.tab + ((size_t)OP_YF_FS * (2 * H + 1) + gy) * (Q + 1);
-#pragma unroll
-            for (int j = 0; j < Q; j++) {
-                wyb[j] = __ldg(tb + j);
-                wyf[j] = __ldg(tf + 1 + j);
+    const int grp = tid / C::NTG;
+    if (grp == 0)
+        velConsumer<Q, CPML, 0>(P, sm, &bars, tid, tx0, tz0, yc0, yc1);
+    else if (grp == 1)
+        velConsumer<Q, CPML, 1>(P, sm, &bars, tid - C::NTG, tx0, tz0, yc0, yc1);
+    else if (grp == 2)
+        velConsumer<Q, CPML, 2>(P, sm, &bars, tid - 2 * C::NTG, tx0, tz0, yc0, yc1);
+    else if (tid == NG_VEL * C::NTG) {
+        // ---- producer: one elected thread streams the planes ----
+        const int HZP = (P.nzp > 1) ? WS_HALO : 0;
+        const int cx = WS_PADX + tx0, cz = HZP + tz0;
+        const int nIter = (Q - 1) + (yc1 - yc0);
+        int stage = 0;
+        uint32_t parity = 1; // first pass over the ring: the stages are free
+        for (int it = 0; it < nIter; it++) {
+            const int cy = WS_HALO + yc0 - (Q - 1) + it;
+            const bool comp = it >= Q - 1;
+            if (it >= NST)
+                mbarWait(&bars.empty[stage], parity);
+            float *st = sm + stage * S::SIZE;
+            uint64_t *bar = &bars.full[stage];
+            mbarExpectTx(bar, comp ? S::BYTES_FULL : S::BYTES_FEED);
+            tmaLoad3D(st + S::FEED, &maps[TM_SXY_P], bar, cx, cz, cy + H - 1);
+            tmaLoad3D(st + S::FEED + C::N_P, &maps[TM_SYY_P], bar, cx, cz, cy + H);
+            tmaLoad3D(st + S::FEED + 2 * C::N_P, &maps[TM_SYZ_P], bar, cx, cz, cy + H - 1);
+            if (comp) {
+                tmaLoad3D(st + S::SXX, &maps[TM_SXX_X], bar, cx - HX, cz, cy);
+                tmaLoad3D(st + S::SXY, &maps[TM_SXY_X], bar, cx - HX, cz, cy);
+                tmaLoad3D(st + S::SXZ, &maps[TM_SXZ_XZ], bar, cx - HX, cz - H, cy);
+                tmaLoad3D(st + S::SYZ, &maps[TM_SYZ_Z], bar, cx, cz - H, cy);
+                tmaLoad3D(st + S::SZZ, &maps[TM_SZZ_Z], bar, cx, cz - H, cy);
+                tmaLoad3D(st + S::OWNV, &maps[TM_VX_P], bar, cx, cz, cy);
+                tmaLoad3D(st + S::OWNV + C::N_P, &maps[TM_VY_P], bar, cx, cz, cy);
+                tmaLoad3D(st + S::OWNV + 2 * C::N_P, &maps[TM_VZ_P], bar, cx, cz, cy);
+                tmaLoad3D(st + S::OWNR, &maps[TM_RIX_P], bar, cx, cz, cy);
+                tmaLoad3D(st + S::OWNR + C::N_P, &maps[TM_RIY_P], bar, cx, cz, cy);
+                tmaLoad3D(st + S::OWNR + 2 * C::N_P, &maps[TM_RIZ_P], bar, cx, cz, cy);
             }
-        } else {
-#pragma unroll
-            for (int j = 0; j < Q; j++) {
-                wyb[j] = c[j];
-                wyf[j] = c[j];
+            if (++stage == NST) {
+                stage = 0;
+                parity ^= 1;
             }
-        }
-        if (CPML) {
-            cp.ky = wsCpmlIndex(gy, P.gny, P.W);
-            if (P.free_surface != 0 && gy < P.W)
-                cp.ky = -1;
-        }
-        const long long pxLy = (long long)ly * P.nz * (2 * P.W);
-        const long long pyOff = ((long long)cp.ky * P.nz + z) * P.nx + x0;
-        const long long pzOff = (long long)ly * (2 * P.W) * P.nx + cp.pzBase;
-
-        mbarWait(&bars[stage], parity);
-        const unsigned char *st = smraw + stage * S::STAGE;
-        const float *tSxx = reinterpret_cast<const float *>(st + S::OFF_SXX) + lz * TXH + 4 * lx;
-        const float *tSxy = reinterpret_cast<const float *>(st + S::OFF_SXY) + lz * TXH + 4 * lx;
-        const float *tSxzX = reinterpret_cast<const float *>(st + S::OFF_SXZ) + (lz + H) * TXH + 4 * lx;
-        const float *tSxzZ = reinterpret_cast<const float *>(st + S::OFF_SXZ) + lz * TXH + 4 * lx + HX;
-        const float *tSyz = reinterpret_cast<const float *>(st + S::OFF_SYZ) + lz * TX + 4 * lx;
-        const float *tSzz = reinterpret_cast<const float *>(st + S::OFF_SZZ) + lz * TX + 4 * lx;
-
-        // ---- vx ----
-        F4 u = dX<Q, true>(tSxx, c);
-        if (anyX) cpX<CPML>(P, cp, u, PSI_SXX_X, true, pxLy);
-        F4 w = dY<Q>(qxy, wyb);
-        cpY<CPML>(P, cp, w, PSI_SXY_Y, false, pyOff);
-#pragma unroll
-        for (int p = 0; p < 4; p++) u.v[p] = A::add(u.v[p], w.v[p]);
-        w = dZ<Q, false>(tSxzZ, TXH, c);
-        cpZ<CPML>(P, cp, w, PSI_SXZ_Z, false, pzOff);
-#pragma unroll
-        for (int p = 0; p < 4; p++) {
-            u.v[p] = A::add(u.v[p], w.v[p]);
-            u.v[p] = A::mul(u.v[p], rx.v[p]);
-            vx.v[p] = A::add(vx.v[p], u.v[p]);
-        }
-        // ---- vy ----
-        u = dX<Q, false>(tSxy, c);
-        if (anyX) cpX<CPML>(P, cp, u, PSI_SXY_X, false, pxLy);
-        w = dY<Q>(qyy, wyf);
-        cpY<CPML>(P, cp, w, PSI_SYY_Y, true, pyOff);
-#pragma unroll
-        for (int p = 0; p < 4; p++) u.v[p] = A::add(u.v[p], w.v[p]);
-        w = dZ<Q, false>(tSyz, TX, c);
-        cpZ<CPML>(P, cp, w, PSI_SYZ_Z, false, pzOff);
-#pragma unroll
-        for (int p = 0; p < 4; p++) {
-            u.v[p] = A::add(u.v[p], w.v[p]);
-            u.v[p] = A::mul(u.v[p], ry.v[p]);
-            vy.v[p] = A::add(vy.v[p], u.v[p]);
-        }
-        // ---- vz ----
-        u = dX<Q, false>(tSxzX, c);
-        if (anyX) cpX<CPML>(P, cp, u, PSI_SXZ_X, false, pxLy);
-        w = dY<Q>(qyz, wyb);
-        cpY<CPML>(P, cp, w, PSI_SYZ_Y, false, pyOff);
-#pragma unroll
-        for (int p = 0; p < 4; p++) u.v[p] = A::add(u.v[p], w.v[p]);
-        w = dZ<Q, true>(tSzz, TX, c);
-        cpZ<CPML>(P, cp, w, PSI_SZZ_Z, true, pzOff);
-#pragma unroll
-        for (int p = 0; p < 4; p++) {
-            u.v[p] = A::add(u.v[p], w.v[p]);
-            u.v[p] = A::mul(u.v[p], rz.v[p]);
-            vz.v[p] = A::add(vz.v[p], u.v[p]);
-        }
-        if (active) {
-            st4(gvx + po, vx); st4(gvy + po, vy); st4(gvz + po, vz);
-        }
-#pragma unroll
-        for (int k = 0; k < Q - 1; k++) {
-            qxy[k] = qxy[k + 1]; qyy[k] = qyy[k + 1]; qyz[k] = qyz[k + 1];
-        }
-        __syncthreads(); // everybody is done with this stage
-        if (tid == 0 && ly + NSTAGE - 1 < yc1)
-            issue(ly + NSTAGE - 1, (stage + NSTAGE - 1) % NSTAGE);
-        stage++;
-        if (stage == NSTAGE) {
-            stage = 0;
-            parity ^= 1;
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
 // stress half-step (ForwardSolver3Delastic.cpp:288-404) incl. free-surface correction
+//   group 0: vxx = Dxb vx, vyy = Dyb vy, vzz = Dzb vz -> sxx, syy, szz (+ free surface)
+//   group 1: sxy += muxy (Dyf vx + Dxf vy)    group 2: sxz += muxz (Dzf vx + Dxf vz), syz += muyz (Dzf vy + Dyf vz)
 // ---------------------------------------------------------------------------------------------------------------------
-template <int Q, bool CPML> __global__ void __launch_bounds__(NTHREADS, 1) kFastStress(const __grid_constant__ WsParams P)
+template <int Q, bool CPML, int G>
+__device__ __forceinline__ void strConsumer(const WsParams &P, const float *sm, Bars *bars, int tg, int tx0, int tz0, int yc0, int yc1)
 {
     using C = Cfg<Q>;
-    using S = SmemB<Q>;
-    constexpr int H = C::H, HX = C::HX, TXH = C::TXH;
+    using S = StageS<Q>;
+    constexpr int H = C::H, HX = C::HX, TXH = C::TXH, NXZ = C::N_XZ, NP = C::N_P;
+    constexpr int FEEDSLOT = (G == 0) ? 1 : (G == 1 ? 0 : 2); // vy | vx | vz
+    const int lx = tg % C::LXN, lz = tg / C::LXN;
+    const int x0 = tx0 + 4 * lx, z = tz0 + lz;
+    const bool active = (x0 < P.nx) && (z < P.nz);
+    const int lane = threadIdx.x & 31;
+
+    float c[Q];
+    loadInterior<Q>(P, c);
+    const long long rowOff = P.base + x0 + (long long)z * P.pitch;
+
+    CpT cpt;
+    // group 0 uses the full-grid profiles (vxx, vyy, vzz), the shear groups the half-grid ones (CPML3D.cpp:31-153)
+    cpSetup<CPML>(P, cpt, active, x0, z, /*halfX*/ G != 0, /*halfZ*/ G != 0);
+
+    const int oX = (lz + H) * TXH + 4 * lx; // x stencil: own row, column of x0 - HX   (inside an XZ tile)
+    const int oZ = lz * TXH + 4 * lx + HX;  // z stencil: row z - H, own column
+    const int oP = lz * TX + 4 * lx;
+
+    F4 q[Q];
+#pragma unroll
+    for (int k = 0; k < Q; k++)
+        q[k] = zero4();
+
+    const int nIter = (Q - 1) + (yc1 - yc0);
+    int stage = 0;
+    uint32_t parity = 0;
+    for (int it = 0; it < nIter; it++) {
+        const int ly = yc0 - (Q - 1) + it;
+        const int gy = P.gy0 + ly;
+        const bool comp = it >= Q - 1;
+        CpI cpi;
+        cpi.ky = -1;
+        if (comp) {
+            if (G == 0)
+                cpLoad<CPML, PSI_VXX, PSI_VYY, PSI_VZZ>(P, cpt, cpi, ly, gy, x0, z, false);
+            else if (G == 1)
+                cpLoad<CPML, PSI_VYX, PSI_VXY, -1>(P, cpt, cpi, ly, gy, x0, z, true);
+            else
+                cpLoad<CPML, PSI_VZX, PSI_VZY, PSI_VXZ, PSI_VYZ>(P, cpt, cpi, ly, gy, x0, z, true);
+        }
+        mbarWait(&bars->full[stage], parity);
+        const float *st = sm + stage * S::SIZE;
+        const float *tvx = st + S::TV, *tvy = st + S::TV + NXZ, *tvz = st + S::TV + 2 * NXZ;
+        q[Q - 1] = ld4(st + S::FEED + FEEDSLOT * NP + oP);
+        if (comp) {
+            const long long o = rowOff + (long long)ly * P.plane;
+            if (G == 0) {
+                // normal strain rates; the y derivative of vy is the plain operator even below a free surface (:289)
+                F4 vxx = dX<Q, false>(tvx + oX, c);
+                F4 vyy = dY<Q>(q, c);
+                F4 vzz = dZ<Q, false>(tvz + oZ, TXH, c);
+                cpApplyX<CPML>(P, cpt, cpi, vxx, PSI_VXX);
+                cpApplyY<CPML>(P, cpt, cpi, vyy, PSI_VYY);
+                cpApplyZ<CPML>(P, cpt, cpi, vzz, PSI_VZZ);
+                F4 sxx = ld4(st + S::OWNS + 0 * NP + oP), syy = ld4(st + S::OWNS + 1 * NP + oP), szz = ld4(st + S::OWNS + 2 * NP + oP);
+                const F4 pi = ld4(st + S::OWNM + 0 * NP + oP), mu = ld4(st + S::OWNM + 1 * NP + oP);
+#pragma unroll
+                for (int p = 0; p < 4; p++) {
+                    float u = A::add(vxx.v[p], vyy.v[p]);
+                    u = A::add(u, vzz.v[p]);
+                    u = A::mul(u, pi.v[p]);
+                    sxx.v[p] = A::add(sxx.v[p], u);
+                    syy.v[p] = A::add(syy.v[p], u);
+                    szz.v[p] = A::add(szz.v[p], u);
+                    u = A::mul(A::add(vyy.v[p], vzz.v[p]), mu.v[p]);
+                    sxx.v[p] = A::msub(2.0f, u, sxx.v[p]);
+                    u = A::mul(A::add(vxx.v[p], vzz.v[p]), mu.v[p]);
+                    syy.v[p] = A::msub(2.0f, u, syy.v[p]);
+                    u = A::mul(A::add(vxx.v[p], vyy.v[p]), mu.v[p]);
+                    szz.v[p] = A::msub(2.0f, u, szz.v[p]);
+                }
+                if (P.free_surface == 1 && gy == 0 && active) {
+                    // FreeSurface3Delastic.cpp:15-47, FreeSurface.cpp:13-20
+                    const F4 sH = ldg4(P.sH + (long long)z * P.nx + x0), sV = ldg4(P.sV + (long long)z * P.nx + x0);
+#pragma unroll
+                    for (int p = 0; p < 4; p++) {
+                        const float hor = A::add(vxx.v[p], vzz.v[p]);
+                        float t = A::mul(sH.v[p], hor);
+                        sxx.v[p] = A::add(sxx.v[p], t);
+                        szz.v[p] = A::add(szz.v[p], t);
+                        t = A::mul(sV.v[p], vyy.v[p]);
+                        sxx.v[p] = A::sub(sxx.v[p], t);
+                        szz.v[p] = A::sub(szz.v[p], t);
+                        syy.v[p] = A::mul(syy.v[p], 0.0f);
+                    }
+                }
+                if (active) {
+                    st4cs(P.fld[F_SXX] + o, sxx);
+                    st4cs(P.fld[F_SYY] + o, syy);
+                    st4cs(P.fld[F_SZZ] + o, szz);
+                }
+            } else if (G == 1) {
+                F4 u = dY<Q>(q, c);
+                cpApplyY<CPML>(P, cpt, cpi, u, PSI_VXY);
+                F4 w = dX<Q, true>(tvy + oX, c);
+                cpApplyX<CPML>(P, cpt, cpi, w, PSI_VYX);
+                F4 s = ld4(st + S::OWNS + 3 * NP + oP);
+                const F4 m = ld4(st + S::OWNM + 2 * NP + oP);
+#pragma unroll
+                for (int p = 0; p < 4; p++) {
+                    const float t = A::add(u.v[p], w.v[p]);
+                    s.v[p] = A::add(s.v[p], A::mul(t, m.v[p]));
+                }
+                if (active)
+                    st4cs(P.fld[F_SXY] + o, s);
+            } else {
+                F4 u = dZ<Q, true>(tvx + oZ, TXH, c);
+                cpApplyZ<CPML>(P, cpt, cpi, u, PSI_VXZ);
+                F4 w = dX<Q, true>(tvz + oX, c);
+                cpApplyX<CPML>(P, cpt, cpi, w, PSI_VZX);
+                F4 s = ld4(st + S::OWNS + 4 * NP + oP);
+                const F4 m = ld4(st + S::OWNM + 3 * NP + oP);
+#pragma unroll
+                for (int p = 0; p < 4; p++) {
+                    const float t = A::add(u.v[p], w.v[p]);
+                    s.v[p] = A::add(s.v[p], A::mul(t, m.v[p]));
+                }
+                if (active)
+                    st4cs(P.fld[F_SXZ] + o, s);
+                u = dZ<Q, true>(tvy + oZ, TXH, c);
+                cpApplyZ2<CPML>(P, cpt, cpi, u, PSI_VYZ);
+                w = dY<Q>(q, c);
+                cpApplyY<CPML>(P, cpt, cpi, w, PSI_VZY);
+                s = ld4(st + S::OWNS + 5 * NP + oP);
+                const F4 m2 = ld4(st + S::OWNM + 4 * NP + oP);
+#pragma unroll
+                for (int p = 0; p < 4; p++) {
+                    const float t = A::add(u.v[p], w.v[p]);
+                    s.v[p] = A::add(s.v[p], A::mul(t, m2.v[p]));
+                }
+                if (active)
+                    st4cs(P.fld[F_SYZ] + o, s);
+            }
+        }
+        __syncwarp();
+        if (lane == 0)
+            mbarArrive(&bars->empty[stage]);
+#pragma unroll
+        for (int k = 0; k < Q - 1; k++)
+            q[k] = q[k + 1];
+        if (++stage == NST) {
+            stage = 0;
+            parity ^= 1;
+        }
+    }
+}
+
+template <int Q, bool CPML> __global__ void __launch_bounds__(NG_STR *Cfg<Q>::NTG + 32, 1) kFastStress(const __grid_constant__ WsParams P)
+{
+    using C = Cfg<Q>;
+    using S = StageS<Q>;
+    constexpr int H = C::H, HX = C::HX;
     extern __shared__ __align__(1024) unsigned char smraw[];
-    __shared__ __align__(8) uint64_t bars[NSTAGE];
+    __shared__ __align__(8) Bars bars;
+    float *sm = reinterpret_cast<float *>(smraw);
     const CUtensorMap *maps = reinterpret_cast<const CUtensorMap *>(P.fastMaps);
 
     const int tid = threadIdx.x;
@@ -446,189 +677,60 @@ template <int Q, bool CPML> __global__ void __launch_bounds__(NTHREADS, 1) kFast
     const int yc1 = min(P.yhi, yc0 + P.fastChunk);
     if (yc0 >= yc1)
         return;
-    const int lx = tid & 15, lz = tid >> 4;
-    const int x0 = tx0 + 4 * lx, z = tz0 + lz;
-    const bool active = (x0 < P.nx) && (z < P.nz);
-    const int HZP = (P.nzp > 1) ? WS_HALO : 0;
-
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < NSTAGE; s++)
-            mbarInit(&bars[s], 1);
+        for (int s = 0; s < NST; s++) {
+            mbarInit(&bars.full[s], 1);
+            mbarInit(&bars.empty[s], NG_STR * C::WPG);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    auto issue = [&](int ly, int stage) {
-        unsigned char *st = smraw + stage * S::STAGE;
-        uint64_t *bar = &bars[stage];
-        mbarExpectTx(bar, S::TXBYTES);
-        const int cy = WS_HALO + ly, cx = WS_PADX + tx0 - HX, cz = HZP + tz0 - H;
-        tmaLoad3D(st + S::OFF_VX, &maps[TM_VX_XZ], bar, cx, cz, cy);
-        tmaLoad3D(st + S::OFF_VY, &maps[TM_VY_XZ], bar, cx, cz, cy);
-        tmaLoad3D(st + S::OFF_VZ, &maps[TM_VZ_XZ], bar, cx, cz, cy);
-    };
-    if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < NSTAGE - 1; s++)
-            if (yc0 + s < yc1)
-                issue(yc0 + s, s);
-    }
-    float c[Q];
-    {
-        const float *w = P.tab + ((size_t)OP_XF * (2 * H + 1) + H) * (Q + 1);
-#pragma unroll
-        for (int j = 0; j < Q; j++)
-            c[j] = __ldg(w + 1 + j);
-    }
-    const long long rowOff = P.base + x0 + (long long)z * P.pitch;
-    const float *gvx = P.fld[F_VX] + rowOff, *gvy = P.fld[F_VY] + rowOff, *gvz = P.fld[F_VZ] + rowOff;
 
-    Cp cp;
-    cp.kz = cp.ky = -1;
-    cp.pxBase = cp.pzBase = 0;
-#pragma unroll
-    for (int p = 0; p < 4; p++)
-        cp.kx[p] = -1;
-    bool anyX = false;
-    if (CPML && active) {
-        const int W = P.W;
-#pragma unroll
-        for (int p = 0; p < 4; p++) {
-            cp.kx[p] = wsCpmlIndex(x0 + p, P.nx, W);
-            anyX |= cp.kx[p] >= 0;
-        }
-        cp.kz = wsCpmlIndex(z, P.nz, W);
-        cp.pxBase = (long long)z * (2 * W);
-        cp.pzBase = (long long)cp.kz * P.nx + x0;
-    }
-    // queues: qvx/qvz[k] = plane y-H+1+k (forward window), qvy[k] = plane y-H+k (backward window)
-    F4 qvx[Q], qvy[Q], qvz[Q];
-#pragma unroll
-    for (int k = 0; k < Q - 1; k++) {
-        if (active) {
-            qvx[k] = ldg4(gvx + (long long)(yc0 - H + 1 + k) * P.plane);
-            qvz[k] = ldg4(gvz + (long long)(yc0 - H + 1 + k) * P.plane);
-            qvy[k] = ldg4(gvy + (long long)(yc0 - H + k) * P.plane);
-        } else {
-            qvx[k] = zero4(); qvy[k] = zero4(); qvz[k] = zero4();
-        }
-    }
-    int stage = 0;
-    uint32_t parity = 0;
-    for (int ly = yc0; ly < yc1; ly++) {
-        const int gy = P.gy0 + ly;
-        const long long o = rowOff + (long long)ly * P.plane;
-        F4 sxx, syy, szz, sxy, sxz, syz, pi, mu, mxy, mxz, myz;
-        if (active) {
-            qvx[Q - 1] = ldg4(gvx + (long long)(ly + H) * P.plane);
-            qvz[Q - 1] = ldg4(gvz + (long long)(ly + H) * P.plane);
-            qvy[Q - 1] = ldg4(gvy + (long long)(ly + H - 1) * P.plane);
-            sxx = ld4(P.fld[F_SXX] + o); syy = ld4(P.fld[F_SYY] + o); szz = ld4(P.fld[F_SZZ] + o);
-            sxy = ld4(P.fld[F_SXY] + o); sxz = ld4(P.fld[F_SXZ] + o); syz = ld4(P.fld[F_SYZ] + o);
-            pi = ldg4(P.mat[M_PW] + o); mu = ldg4(P.mat[M_MU] + o);
-            mxy = ldg4(P.mat[M_MUXY] + o); mxz = ldg4(P.mat[M_MUXZ] + o); myz = ldg4(P.mat[M_MUYZ] + o);
-        } else {
-            qvx[Q - 1] = zero4(); qvy[Q - 1] = zero4(); qvz[Q - 1] = zero4();
-            sxx = syy = szz = sxy = sxz = syz = pi = mu = mxy = mxz = myz = zero4();
-        }
-        if (CPML) {
-            cp.ky = wsCpmlIndex(gy, P.gny, P.W);
-            if (P.free_surface != 0 && gy < P.W)
-                cp.ky = -1;
-        }
-        const long long pxLy = (long long)ly * P.nz * (2 * P.W);
-        const long long pyOff = ((long long)cp.ky * P.nz + z) * P.nx + x0;
-        const long long pzOff = (long long)ly * (2 * P.W) * P.nx + cp.pzBase;
-
-        mbarWait(&bars[stage], parity);
-        const unsigned char *st = smraw + stage * S::STAGE;
-        const float *bvx = reinterpret_cast<const float *>(st + S::OFF_VX), *bvy = reinterpret_cast<const float *>(st + S::OFF_VY),
-                    *bvz = reinterpret_cast<const float *>(st + S::OFF_VZ);
-        const int oX = (lz + H) * TXH + 4 * lx;     // x stencil: own row, column of x0 - HX
-        const int oZ = lz * TXH + 4 * lx + HX;      // z stencil: row z - H, own column
-
-        // normal strain rates; the y derivative of vy is the plain operator even below a free surface (:289)
-        F4 vxx = dX<Q, false>(bvx + oX, c);
-        F4 vyy = dY<Q>(qvy, c);
-        F4 vzz = dZ<Q, false>(bvz + oZ, TXH, c);
-        if (anyX) cpX<CPML>(P, cp, vxx, PSI_VXX, false, pxLy);
-        cpY<CPML>(P, cp, vyy, PSI_VYY, false, pyOff);
-        cpZ<CPML>(P, cp, vzz, PSI_VZZ, false, pzOff);
-#pragma unroll
-        for (int p = 0; p < 4; p++) {
-            float u = A::add(vxx.v[p], vyy.v[p]);
-            u = A::add(u, vzz.v[p]);
-            u = A::mul(u, pi.v[p]);
-            sxx.v[p] = A::add(sxx.v[p], u);
-            syy.v[p] = A::add(syy.v[p], u);
-            szz.v[p] = A::add(szz.v[p], u);
-            u = A::mul(A::add(vyy.v[p], vzz.v[p]), mu.v[p]);
-            sxx.v[p] = A::msub(2.0f, u, sxx.v[p]);
-            u = A::mul(A::add(vxx.v[p], vzz.v[p]), mu.v[p]);
-            syy.v[p] = A::msub(2.0f, u, syy.v[p]);
-            u = A::mul(A::add(vxx.v[p], vyy.v[p]), mu.v[p]);
-            szz.v[p] = A::msub(2.0f, u, szz.v[p]);
-        }
-        // shear stresses
-        {
-            F4 u = dY<Q>(qvx, c);
-            cpY<CPML>(P, cp, u, PSI_VXY, true, pyOff);
-            F4 w = dX<Q, true>(bvy + oX, c);
-            if (anyX) cpX<CPML>(P, cp, w, PSI_VYX, true, pxLy);
-#pragma unroll
-            for (int p = 0; p < 4; p++) {
-                const float t = A::add(u.v[p], w.v[p]);
-                sxy.v[p] = A::add(sxy.v[p], A::mul(t, mxy.v[p]));
+    const int grp = tid / C::NTG;
+    if (grp == 0)
+        strConsumer<Q, CPML, 0>(P, sm, &bars, tid, tx0, tz0, yc0, yc1);
+    else if (grp == 1)
+        strConsumer<Q, CPML, 1>(P, sm, &bars, tid - C::NTG, tx0, tz0, yc0, yc1);
+    else if (grp == 2)
+        strConsumer<Q, CPML, 2>(P, sm, &bars, tid - 2 * C::NTG, tx0, tz0, yc0, yc1);
+    else if (tid == NG_STR * C::NTG) {
+        const int HZP = (P.nzp > 1) ? WS_HALO : 0;
+        const int cx = WS_PADX + tx0, cz = HZP + tz0;
+        const int nIter = (Q - 1) + (yc1 - yc0);
+        int stage = 0;
+        uint32_t parity = 1;
+        for (int it = 0; it < nIter; it++) {
+            const int cy = WS_HALO + yc0 - (Q - 1) + it;
+            const bool comp = it >= Q - 1;
+            if (it >= NST)
+                mbarWait(&bars.empty[stage], parity);
+            float *st = sm + stage * S::SIZE;
+            uint64_t *bar = &bars.full[stage];
+            mbarExpectTx(bar, comp ? S::BYTES_FULL : S::BYTES_FEED);
+            tmaLoad3D(st + S::FEED, &maps[TM_VX_P], bar, cx, cz, cy + H);
+            tmaLoad3D(st + S::FEED + C::N_P, &maps[TM_VY_P], bar, cx, cz, cy + H - 1);
+            tmaLoad3D(st + S::FEED + 2 * C::N_P, &maps[TM_VZ_P], bar, cx, cz, cy + H);
+            if (comp) {
+                tmaLoad3D(st + S::TV, &maps[TM_VX_XZ], bar, cx - HX, cz - H, cy);
+                tmaLoad3D(st + S::TV + C::N_XZ, &maps[TM_VY_XZ], bar, cx - HX, cz - H, cy);
+                tmaLoad3D(st + S::TV + 2 * C::N_XZ, &maps[TM_VZ_XZ], bar, cx - HX, cz - H, cy);
+                tmaLoad3D(st + S::OWNS, &maps[TM_SXX_P], bar, cx, cz, cy);
+                tmaLoad3D(st + S::OWNS + C::N_P, &maps[TM_SYY_P], bar, cx, cz, cy);
+                tmaLoad3D(st + S::OWNS + 2 * C::N_P, &maps[TM_SZZ_P], bar, cx, cz, cy);
+                tmaLoad3D(st + S::OWNS + 3 * C::N_P, &maps[TM_SXY_P], bar, cx, cz, cy);
+                tmaLoad3D(st + S::OWNS + 4 * C::N_P, &maps[TM_SXZ_P], bar, cx, cz, cy);
+                tmaLoad3D(st + S::OWNS + 5 * C::N_P, &maps[TM_SYZ_P], bar, cx, cz, cy);
+                tmaLoad3D(st + S::OWNM, &maps[TM_PW_P], bar, cx, cz, cy);
+                tmaLoad3D(st + S::OWNM + C::N_P, &maps[TM_MU_P], bar, cx, cz, cy);
+                tmaLoad3D(st + S::OWNM + 2 * C::N_P, &maps[TM_MUXY_P], bar, cx, cz, cy);
+                tmaLoad3D(st + S::OWNM + 3 * C::N_P, &maps[TM_MUXZ_P], bar, cx, cz, cy);
+                tmaLoad3D(st + S::OWNM + 4 * C::N_P, &maps[TM_MUYZ_P], bar, cx, cz, cy);
             }
-            u = dZ<Q, true>(bvx + oZ, TXH, c);
-            cpZ<CPML>(P, cp, u, PSI_VXZ, true, pzOff);
-            w = dX<Q, true>(bvz + oX, c);
-            if (anyX) cpX<CPML>(P, cp, w, PSI_VZX, true, pxLy);
-#pragma unroll
-            for (int p = 0; p < 4; p++) {
-                const float t = A::add(u.v[p], w.v[p]);
-                sxz.v[p] = A::add(sxz.v[p], A::mul(t, mxz.v[p]));
+            if (++stage == NST) {
+                stage = 0;
+                parity ^= 1;
             }
-            u = dZ<Q, true>(bvy + oZ, TXH, c);
-            cpZ<CPML>(P, cp, u, PSI_VYZ, true, pzOff);
-            w = dY<Q>(qvz, c);
-            cpY<CPML>(P, cp, w, PSI_VZY, true, pyOff);
-#pragma unroll
-            for (int p = 0; p < 4; p++) {
-                const float t = A::add(u.v[p], w.v[p]);
-                syz.v[p] = A::add(syz.v[p], A::mul(t, myz.v[p]));
-            }
-        }
-        if (P.free_surface == 1 && gy == 0 && active) {
-            // FreeSurface3Delastic.cpp:15-47, FreeSurface.cpp:13-20
-            const F4 sH = ldg4(P.sH + (long long)z * P.nx + x0), sV = ldg4(P.sV + (long long)z * P.nx + x0);
-#pragma unroll
-            for (int p = 0; p < 4; p++) {
-                const float hor = A::add(vxx.v[p], vzz.v[p]);
-                float t = A::mul(sH.v[p], hor);
-                sxx.v[p] = A::add(sxx.v[p], t);
-                szz.v[p] = A::add(szz.v[p], t);
-                t = A::mul(sV.v[p], vyy.v[p]);
-                sxx.v[p] = A::sub(sxx.v[p], t);
-                szz.v[p] = A::sub(szz.v[p], t);
-                syy.v[p] = A::mul(syy.v[p], 0.0f);
-            }
-        }
-        if (active) {
-            st4(P.fld[F_SXX] + o, sxx); st4(P.fld[F_SYY] + o, syy); st4(P.fld[F_SZZ] + o, szz);
-            st4(P.fld[F_SXY] + o, sxy); st4(P.fld[F_SXZ] + o, sxz); st4(P.fld[F_SYZ] + o, syz);
-        }
-#pragma unroll
-        for (int k = 0; k < Q - 1; k++) {
-            qvx[k] = qvx[k + 1]; qvy[k] = qvy[k + 1]; qvz[k] = qvz[k + 1];
-        }
-        __syncthreads();
-        if (tid == 0 && ly + NSTAGE - 1 < yc1)
-            issue(ly + NSTAGE - 1, (stage + NSTAGE - 1) % NSTAGE);
-        stage++;
-        if (stage == NSTAGE) {
-            stage = 0;
-            parity ^= 1;
         }
     }
 }
@@ -673,10 +775,11 @@ template <int Q> void setAttrs()
     static bool done = false;
     if (done)
         return;
-    cudaFuncSetAttribute(kFastVel<Q, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NSTAGE * SmemA<Q>::STAGE);
-    cudaFuncSetAttribute(kFastVel<Q, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NSTAGE * SmemA<Q>::STAGE);
-    cudaFuncSetAttribute(kFastStress<Q, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NSTAGE * SmemB<Q>::STAGE);
-    cudaFuncSetAttribute(kFastStress<Q, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NSTAGE * SmemB<Q>::STAGE);
+    const int smV = NST * StageV<Q>::SIZE * 4, smS = NST * StageS<Q>::SIZE * 4;
+    cudaFuncSetAttribute(kFastVel<Q, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smV);
+    cudaFuncSetAttribute(kFastVel<Q, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smV);
+    cudaFuncSetAttribute(kFastStress<Q, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smS);
+    cudaFuncSetAttribute(kFastStress<Q, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smS);
     done = true;
 }
 
@@ -687,17 +790,19 @@ template <int Q> void launchQ(const WsParams &P, int pass, cudaStream_t st)
     dim3 grid((P.nx + TX - 1) / TX, (P.nz + TZ - 1) / TZ, (ny + P.fastChunk - 1) / P.fastChunk);
     const bool cpml = P.damping == 2;
     if (pass == 0) {
-        const size_t sm = NSTAGE * SmemA<Q>::STAGE;
+        const size_t sm = (size_t)NST * StageV<Q>::SIZE * 4;
+        const int nt = NG_VEL * Cfg<Q>::NTG + 32;
         if (cpml)
-            kFastVel<Q, true><<<grid, NTHREADS, sm, st>>>(P);
+            kFastVel<Q, true><<<grid, nt, sm, st>>>(P);
         else
-            kFastVel<Q, false><<<grid, NTHREADS, sm, st>>>(P);
+            kFastVel<Q, false><<<grid, nt, sm, st>>>(P);
     } else {
-        const size_t sm = NSTAGE * SmemB<Q>::STAGE;
+        const size_t sm = (size_t)NST * StageS<Q>::SIZE * 4;
+        const int nt = NG_STR * Cfg<Q>::NTG + 32;
         if (cpml)
-            kFastStress<Q, true><<<grid, NTHREADS, sm, st>>>(P);
+            kFastStress<Q, true><<<grid, nt, sm, st>>>(P);
         else
-            kFastStress<Q, false><<<grid, NTHREADS, sm, st>>>(P);
+            kFastStress<Q, false><<<grid, nt, sm, st>>>(P);
     }
 }
 
@@ -727,22 +832,40 @@ void *wsFastPrepare(WsParams &P, int nyp)
     mk(TM_SXZ_XZ, P.fld[F_SXZ], TXH, TZH);
     mk(TM_SYZ_Z, P.fld[F_SYZ], TX, TZH);
     mk(TM_SZZ_Z, P.fld[F_SZZ], TX, TZH);
+    mk(TM_SXY_P, P.fld[F_SXY], TX, TZ);
+    mk(TM_SYY_P, P.fld[F_SYY], TX, TZ);
+    mk(TM_SYZ_P, P.fld[F_SYZ], TX, TZ);
+    mk(TM_VX_P, P.fld[F_VX], TX, TZ);
+    mk(TM_VY_P, P.fld[F_VY], TX, TZ);
+    mk(TM_VZ_P, P.fld[F_VZ], TX, TZ);
+    mk(TM_RIX_P, P.mat[M_RIX], TX, TZ);
+    mk(TM_RIY_P, P.mat[M_RIY], TX, TZ);
+    mk(TM_RIZ_P, P.mat[M_RIZ], TX, TZ);
     mk(TM_VX_XZ, P.fld[F_VX], TXH, TZH);
     mk(TM_VY_XZ, P.fld[F_VY], TXH, TZH);
     mk(TM_VZ_XZ, P.fld[F_VZ], TXH, TZH);
+    mk(TM_SXX_P, P.fld[F_SXX], TX, TZ);
+    mk(TM_SZZ_P, P.fld[F_SZZ], TX, TZ);
+    mk(TM_SXZ_P, P.fld[F_SXZ], TX, TZ);
+    mk(TM_PW_P, P.mat[M_PW], TX, TZ);
+    mk(TM_MU_P, P.mat[M_MU], TX, TZ);
+    mk(TM_MUXY_P, P.mat[M_MUXY], TX, TZ);
+    mk(TM_MUXZ_P, P.mat[M_MUXZ], TX, TZ);
+    mk(TM_MUYZ_P, P.mat[M_MUYZ], TX, TZ);
     void *dev = nullptr;
     if (cudaMalloc(&dev, sizeof(CUtensorMap) * TM_COUNT) != cudaSuccess)
         throw std::runtime_error("cudaMalloc for tensor maps failed");
     cudaMemcpy(dev, maps.data(), sizeof(CUtensorMap) * TM_COUNT, cudaMemcpyHostToDevice);
     P.fastMaps = dev;
-    // planes per block: enough blocks to fill 148 SMs a few times over, long enough marches to amortise the prologue
+    // planes per block: enough blocks to fill the 148 SMs several times over, long enough marches to amortise the
+    // Q-1 feed-only iterations of the prologue
     const int tiles = ((P.nx + TX - 1) / TX) * ((P.nz + TZ - 1) / TZ);
-    int chunks = (4 * 148 + tiles - 1) / tiles;
+    int chunks = (6 * 148 + tiles - 1) / tiles;
     if (chunks < 1)
         chunks = 1;
     int chunk = (P.nyl + chunks - 1) / chunks;
-    if (chunk < 16)
-        chunk = 16;
+    if (chunk < 32)
+        chunk = 32;
     P.fastChunk = chunk;
     return dev;
 }
