@@ -121,6 +121,8 @@ def main():
     ap.add_argument("--cpu-n", type=int, default=160)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--variant", type=int, default=0, help="0 auto (fast kernels), 1 force general kernels")
+    ap.add_argument("--damping", type=int, default=2, help="developer switch: 2 = CPML (the benchmark configuration), 0 = none")
+    ap.add_argument("--free-surface", type=int, default=1, help="developer switch: 1 = image method (the benchmark configuration)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -140,7 +142,7 @@ def main():
     gny = nyl * world
     nt = 2 * (W + K) + 8
     dt_, dh = 8e-4, 10.0
-    d = make_desc(3, "elastic", nx, gny, nz, dh=dh, dt=dt_, nt=nt, fd_order=8, edge_policy=0, free_surface=1, damping=2,
+    d = make_desc(3, "elastic", nx, gny, nz, dh=dh, dt=dt_, nt=nt, fd_order=8, edge_policy=0, free_surface=args.free_surface, damping=args.damping,
                   boundary_width=20, vmax_cpml=5000.0, fc_cpml=10.0, npower=4.0, exact_arith=0, kernel_variant=args.variant,
                   rank=rank, nranks=world, device=local)
     s = Solver(d)

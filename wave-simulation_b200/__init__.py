@@ -11,7 +11,8 @@ import numpy as np
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG_DIR)
-PRODUCT_SO = os.path.join(PKG_DIR, "csrc", "libwavesim_cuda.so")
+# WAVESIM_LIB: developer override used to A/B kernel build variants on the GPU box
+PRODUCT_SO = os.environ.get("WAVESIM_LIB") or os.path.join(PKG_DIR, "csrc", "libwavesim_cuda.so")
 
 EQ = dict(acoustic=0, elastic=1, viscoelastic=2, sh=3, viscosh=4, tmem=5, emem=6, viscotmem=7, viscoemem=8)
 TYPE = dict(P=1, VX=2, VY=3, VZ=4, EZ=1, EX=2, EY=3, HZ=4)

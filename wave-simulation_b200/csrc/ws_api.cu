@@ -198,9 +198,19 @@ template <typename T>
 struct DevBuf {
     T *p = nullptr;
     size_t n = 0;
+    bool owned = true;
+    // slot of an arena owned by another DevBuf
+    void borrow(T *ptr, size_t count)
+    {
+        release();
+        p = ptr;
+        n = count;
+        owned = false;
+    }
     void alloc(size_t count)
     {
         release();
+        owned = true;
         n = count;
         if (count) {
             cudaError_t e = cudaMalloc(&p, count * sizeof(T));
@@ -221,10 +231,11 @@ struct DevBuf {
     }
     void release()
     {
-        if (p)
+        if (p && owned)
             cudaFree(p);
         p = nullptr;
         n = 0;
+        owned = true;
     }
     ~DevBuf() { release(); }
     DevBuf() = default;
@@ -265,6 +276,7 @@ struct ws_solver {
     bool seismic = true, visco = false, exact = false;
     cudaStream_t stream = nullptr, commStream = nullptr;
     cudaEvent_t evCompute = nullptr, evComm = nullptr;
+    DevBuf<float> fldArena, matArena; // declared first: the slots below borrow from them
     DevBuf<float> fld[F_COUNT], mat[M_COUNT], psi[PSI_COUNT];
     bool matGiven[M_COUNT] = {};
     int psiAxis[PSI_COUNT];
@@ -574,6 +586,9 @@ void refreshParams(ws_solver *s)
     P.ylo = 0; P.yhi = s->nyl;
     P.edge_policy = s->d.edge_policy;
     P.tab = s->tab.p;
+    P.fldArena = s->fldArena.p;
+    P.matArena = s->matArena.p;
+    P.arenaStride = s->total;
     P.cax = s->cax.p; P.cbx = s->cbx.p; P.caxh = s->caxh.p; P.cbxh = s->cbxh.p;
     P.cay = s->cay.p; P.cby = s->cby.p; P.cayh = s->cayh.p; P.cbyh = s->cbyh.p;
     P.caz = s->caz.p; P.cbz = s->cbz.p; P.cazh = s->cazh.p; P.cbzh = s->cbzh.p;
@@ -791,6 +806,15 @@ void prepareBoundaries(ws_solver *s)
     const bool fsTables = s->seismic && d.free_surface == 1;
     std::vector<float> tab = wstab::buildTables(s->q, d.edge_policy, fsTables, s->nx, s->gny, s->nz, d.dim, d.dh, d.dt);
     s->tab.upload(tab);
+    {
+        // interior rows as kernel parameters (constant bank) for the tiled kernels: forward taps are entries 1..q
+        const int rows = 2 * s->h + 1, taps = s->q + 1;
+        const float *xf = &tab[((size_t)OP_XF * rows + s->h) * taps], *yf = &tab[((size_t)(fsTables ? OP_YF_FS : OP_YF) * rows + s->h) * taps];
+        for (int j = 0; j < WS_MAXQ; j++) {
+            s->P.cw[j] = j < s->q ? xf[1 + j] : 0.0f;
+            s->P.cwy[j] = j < s->q ? yf[1 + j] : 0.0f;
+        }
+    }
     if (d.damping == 2) {
         // CPML*.init (CPML3D.cpp:222-368): same 1-D profile on every axis (regular grid)
         wstab::CpmlAxis c = wstab::buildCpmlAxis(s->W, d.npower, d.fc_cpml, d.vmax_cpml, d.dt, d.dh);
@@ -1065,10 +1089,26 @@ int ws_create(const ws_desc *desc, ws_solver **out)
             WS_CUDA_CHECK(cudaEventCreateWithFlags(&s->evCompute, cudaEventDisableTiming));
             WS_CUDA_CHECK(cudaEventCreateWithFlags(&s->evComm, cudaEventDisableTiming));
             WS_CUDA_CHECK(cudaEventRecord(s->evComm, s->commStream));
-            for (auto &kv : fieldsFor(s->d).f) {
-                s->fld[kv.second].alloc((size_t)s->total);
-                s->fld[kv.second].zero();
-                s->fldSlot[kv.first] = kv.second;
+            if (s->d.eq == WS_EQ_ELASTIC && s->d.dim == 3) {
+                // arena order of the tiled kernels (ws_kernels_fast.cu): neighbours are fetched by one TMA box
+                static const int fo[9] = {F_VX, F_VY, F_VZ, F_SXX, F_SXY, F_SYY, F_SYZ, F_SZZ, F_SXZ};
+                static const int mo[8] = {M_RIX, M_RIY, M_RIZ, M_PW, M_MU, M_MUXY, M_MUXZ, M_MUYZ};
+                s->fldArena.alloc((size_t)s->total * 9);
+                s->fldArena.zero();
+                for (int k = 0; k < 9; k++)
+                    s->fld[fo[k]].borrow(s->fldArena.p + (size_t)k * s->total, (size_t)s->total);
+                s->matArena.alloc((size_t)s->total * 8);
+                s->matArena.zero();
+                for (int k = 0; k < 8; k++)
+                    s->mat[mo[k]].borrow(s->matArena.p + (size_t)k * s->total, (size_t)s->total);
+                for (auto &kv : fieldsFor(s->d).f)
+                    s->fldSlot[kv.first] = kv.second;
+            } else {
+                for (auto &kv : fieldsFor(s->d).f) {
+                    s->fld[kv.second].alloc((size_t)s->total);
+                    s->fld[kv.second].zero();
+                    s->fldSlot[kv.first] = kv.second;
+                }
             }
             for (int k = 0; k < PSI_COUNT; k++)
                 s->psiAxis[k] = -1;

@@ -73,7 +73,14 @@ struct WsParams {
     int ylo, yhi;     // local y range [ylo, yhi) processed by this launch (interior/boundary split for overlap)
     int edge_policy;  // 0 truncate | 1 order-reduce
     int fastChunk;    // planes per thread block of the tiled kernels
+    int fastDebug;    // developer switch (env WS_FAST_DEBUG): 1 = consumers skip the arithmetic and the stores (memory-side ceiling of the tiling)
     const void *fastMaps; // device array of CUtensorMap (tiled kernels)
+    // arenas of the tiled kernels: wavefields / model parameters that one TMA box fetches together are slots of one
+    // allocation with a constant stride (`total` floats); null when the arrays are allocated one by one
+    const float *fldArena, *matArena;
+    long long arenaStride;
+    float cw[WS_MAXQ];  // interior weights of the plain operators, c_j * (DT/DH) (policy 0)
+    float cwy[WS_MAXQ]; // interior weights of the y operators of the first half-step (image-method rows with a free surface)
     const float *tab; // derivative weight tables [WS_NOPS][2h+1][q+1], already scaled by DT/DH
     // CPML coefficients, 2W entries per array: k < W low-coordinate side, k >= W high-coordinate side (CPML3D.cpp:297-317)
     const float *cax, *cbx, *caxh, *cbxh, *cay, *cby, *cayh, *cbyh, *caz, *cbz, *cazh, *cbzh;

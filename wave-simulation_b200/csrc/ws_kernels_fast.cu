@@ -4,17 +4,19 @@
 // Structure (2.5-D blocking, producer / consumer pipeline):
 //   * a thread block owns a TX x TZ tile of the x-z plane and marches along y (the slowest axis);
 //   * ONE PRODUCER WARP streams, per plane, every operand of that plane into a ring of NST shared-memory stages with TMA
-//     (cp.async.bulk.tensor.3d, completion on a "full" mbarrier per stage): halo tiles for the x / z stencils, the plane
-//     that enters the y-derivative window, and the own-point operands (updated fields, model parameters).  Consumer
-//     threads never wait on DRAM: up to NST-1 planes (~100 KB per SM) are in flight while one is being computed;
+//     (cp.async.bulk.tensor.4d over field arenas, completion on a "full" mbarrier per stage): halo tiles for the x / z
+//     stencils, the planes that enter the y-derivative windows, and the own-point operands (updated fields, model
+//     parameters).  Consumer threads never wait on DRAM: up to NST-1 planes (~100 KB per SM) are in flight while one
+//     is being computed;
 //   * CONSUMER GROUPS split the work by OUTPUT COMPONENT (velocity half-step: vx | vy | vz; stress half-step:
-//     sxx,syy,szz | sxy | sxz | syz).  Every thread owns 4 consecutive x points (128-bit shared / global accesses) and
-//     keeps only the ONE field it differentiates along y in a register queue (Q planes deep), so the kernels run with
-//     ~100 registers and 13-17 warps per SM instead of 230 registers and 8 warps;
+//     sxx,syy,szz | sxy | sxz,syz).  Every thread owns 4 consecutive x points (128-bit shared / global accesses) and
+//     keeps only the ONE field it differentiates along y in a register queue (Q planes deep);
+//   * the march is unrolled Q times with a rotating queue index (no register moves), with the FD weights as
+//     constant-bank operands; planes that need per-plane treatment (image-method rows below the free surface, the
+//     y-CPML layers, the queue prologue, the remainder) take a generic step with run-time weights;
 //   * a stage is handed back to the producer through an "empty" mbarrier (one arrival per consumer warp);
 //   * off-grid taps read the zero pads of the HBM layout (StencilMatrix "drop off-grid taps", edge_policy 0);
-//   * image-method free surface: per-plane y weights (the reference's DyfFreeSurface / DybFreeSurface rows) + surface
-//     correction in the stress kernel; CPML: memory variables in compact boundary slabs, loaded before the stage wait.
+//   * CPML memory variables live in compact boundary slabs; their loads are issued before the stage wait.
 // The arithmetic sequence is the one of the general kernels (ws_kernels_general.cuh) in FMA mode, so both produce
 // bit-identical results.
 #include "../../include/wavesim.h"
@@ -22,14 +24,28 @@
 
 #include <cuda.h>
 #include <cstdio>
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
 #include <vector>
 
 namespace {
 
-constexpr int TX = 64, TZ = 8, NST = 4;
-constexpr int NG_VEL = 3, NG_STR = 3;
+#ifndef WS_NSTV
+#define WS_NSTV 4
+#endif
+#ifndef WS_NSTS
+#define WS_NSTS 4
+#endif
+constexpr int TX = 64, TZ = 8;
+constexpr int NSTV = WS_NSTV, NSTS = WS_NSTS, NSTMAX = NSTV > NSTS ? NSTV : NSTS; // ring depth of the velocity / stress kernel
+constexpr int NGROUPS = 3;
+// planes per trip of the unrolled march: the y queue holds Q + UNR - 1 planes and is shifted by UNR once per trip
+// (full rotation, UNR = Q, needs no moves but its code overflows the instruction cache: measured)
+#ifndef WS_UNR
+#define WS_UNR 2
+#endif
+constexpr int UNR = WS_UNR;
 
 template <int Q> struct Cfg {
     static constexpr int H = Q / 2;
@@ -39,35 +55,50 @@ template <int Q> struct Cfg {
     static constexpr int LXN = TX / 4;
     static constexpr int NTG = LXN * TZ; // threads per consumer group
     static constexpr int WPG = NTG / 32; // warps per group
+    // warps are dealt round-robin to the 4 SM sub-partitions (warp id % 4): group g owns sub-partition g, so each
+    // sub-partition's instruction cache holds ONE group's march (with interleaved groups the three code streams
+    // evict each other: measured); sub-partition 3 hosts the producer warp (its other warps exit at once)
+    static constexpr int NTHREADS = 4 * NTG;
     // tile sizes (floats); all are multiples of 32 floats = 128 bytes
     static constexpr int N_P = TX * TZ, N_X = TXH * TZ, N_Z = TX * TZH, N_XZ = TXH * TZH;
     static_assert(NTG % 32 == 0, "consumer groups must be whole warps");
     static_assert(N_P % 32 == 0 && N_X % 32 == 0 && N_Z % 32 == 0 && N_XZ % 32 == 0, "TMA destinations must stay 128-byte aligned");
+    static constexpr int QL = Q + UNR - 1; // physical length of the y queue
+    static_assert(Q % UNR == 0 && NSTV % UNR == 0 && NSTS % UNR == 0, "trips must tile the queue prologue and the stage ring");
 };
 
-// tensor-map slots (one CUtensorMap per array and box shape)
+// tensor-map slots.  Arena order of the wavefields: vx vy vz sxx sxy syy syz szz sxz; of the model parameters:
+// rix riy riz pi mu muxy muxz muyz (ws_api.cu) — arrays that one box fetches together are neighbours.
 enum {
-    TM_SXX_X = 0, TM_SXY_X, TM_SXZ_XZ, TM_SYZ_Z, TM_SZZ_Z, TM_SXY_P, TM_SYY_P, TM_SYZ_P, // velocity half-step
-    TM_VX_P, TM_VY_P, TM_VZ_P, TM_RIX_P, TM_RIY_P, TM_RIZ_P,
-    TM_VX_XZ, TM_VY_XZ, TM_VZ_XZ,                                                         // stress half-step
-    TM_SXX_P, TM_SZZ_P, TM_SXZ_P, TM_PW_P, TM_MU_P, TM_MUXY_P, TM_MUXZ_P, TM_MUYZ_P,
+    TM_V_P = 0,   // {vx,vy,vz} plain            (velocity: own operands)
+    TM_R_P,       // {rix,riy,riz} plain
+    TM_SX_X,      // {sxx,sxy} with x halo
+    TM_SXZ_XZ,    // sxz with x and z halo
+    TM_SZ_XZ,     // {syz,szz} with x and z halo
+    TM_F1_P,      // one field, plain: planes entering the y windows (4th coordinate selects the field)
+    TM_V_XZ,      // {vx,vy,vz} with x and z halo (stress half-step)
+    TM_S_P,       // {sxx,sxy,syy,syz,szz,sxz} plain (stress: own operands)
+    TM_M_P,       // {pi,mu,muxy,muxz,muyz} plain
     TM_COUNT
 };
+// positions inside the arenas
+enum { AF_VX = 0, AF_VY, AF_VZ, AF_SXX, AF_SXY, AF_SYY, AF_SYZ, AF_SZZ, AF_SXZ, AF_COUNT };
+enum { AM_RIX = 0, AM_RIY, AM_RIZ, AM_PW, AM_MU, AM_MUXY, AM_MUXZ, AM_MUYZ, AM_COUNT };
 
 __device__ __forceinline__ uint32_t smemU32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbarInit(uint64_t *bar, int count)
+__device__ __forceinline__ void mbarInit(uint32_t bar, int count)
 {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemU32(bar)), "r"(count) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbarExpectTx(uint64_t *bar, uint32_t bytes)
+__device__ __forceinline__ void mbarExpectTx(uint32_t bar, uint32_t bytes)
 {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemU32(bar)), "r"(bytes) : "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbarArrive(uint64_t *bar)
+__device__ __forceinline__ void mbarArrive(uint32_t bar)
 {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smemU32(bar)) : "memory");
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbarWait(uint64_t *bar, uint32_t parity)
+__device__ __forceinline__ void mbarWait(uint32_t bar, uint32_t parity)
 {
     asm volatile(
         "{\n"
@@ -77,19 +108,15 @@ __device__ __forceinline__ void mbarWait(uint64_t *bar, uint32_t parity)
         "@P1 bra DONE_%=;\n"
         "bra LAB_WAIT_%=;\n"
         "DONE_%=:\n"
-        "}\n" ::"r"(smemU32(bar)),
+        "}\n" ::"r"(bar),
         "r"(parity)
         : "memory");
 }
-__device__ __forceinline__ void tmaLoad3D(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2)
+__device__ __forceinline__ void tmaLoad4D(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2, int c3)
 {
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smemU32(dst)),
-                 "l"((unsigned long long)map), "r"(smemU32(bar)), "r"(c0), "r"(c1), "r"(c2)
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+                 "l"((unsigned long long)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                  : "memory");
-}
-__device__ __forceinline__ void tmaPrefetchDesc(const CUtensorMap *map)
-{
-    asm volatile("prefetch.tensormap [%0];" ::"l"((unsigned long long)map) : "memory");
 }
 
 struct F4 {
@@ -122,7 +149,7 @@ __device__ __forceinline__ F4 zero4()
 using A = Ar<false>;
 
 // x derivative of 4 consecutive points from a shared-memory row; `row` points at the tile column of x0 - HX
-template <int Q, bool FWD> __device__ __forceinline__ F4 dX(const float *row, const float (&c)[Q])
+template <int Q, bool FWD> __device__ __forceinline__ F4 dX(const float *row, const float *__restrict__ c)
 {
     constexpr int H = Q / 2, HX = Cfg<Q>::HX, NV = (2 * HX + 4) / 4;
     float w[NV * 4];
@@ -142,55 +169,44 @@ template <int Q, bool FWD> __device__ __forceinline__ F4 dX(const float *row, co
     }
     return r;
 }
-// z derivative: `col` points at (row of z - H, column of x0) of a tile with z halo; rows are `ld` floats apart
-template <int Q, bool FWD> __device__ __forceinline__ F4 dZ(const float *col, int ld, const float (&c)[Q])
+// z derivative: `col` points at (row of z - H, column of x0) of a tile with z halo; rows are LD floats apart
+template <int Q, bool FWD, int LD> __device__ __forceinline__ F4 dZ(const float *col, const float *__restrict__ c)
 {
     F4 r = zero4();
 #pragma unroll
     for (int j = 0; j < Q; j++) {
-        const F4 t = ld4(col + (FWD ? j + 1 : j) * ld);
+        const F4 t = ld4(col + (FWD ? j + 1 : j) * LD);
 #pragma unroll
         for (int p = 0; p < 4; p++)
             r.v[p] = A::madd(c[j], t.v[p], r.v[p]);
     }
     return r;
 }
-// y derivative from a register queue (q[k] = plane of the k-th tap), weights w[k]
-template <int Q> __device__ __forceinline__ F4 dY(const F4 (&q)[Q], const float (&w)[Q])
+// y derivative from the register queue; tap k of the R-th plane of a trip lives in q[k + R]
+template <int Q, int R> __device__ __forceinline__ F4 dY(const F4 (&q)[Cfg<Q>::QL], const float *__restrict__ w)
 {
     F4 r = zero4();
 #pragma unroll
     for (int j = 0; j < Q; j++)
 #pragma unroll
         for (int p = 0; p < 4; p++)
-            r.v[p] = A::madd(w[j], q[j].v[p], r.v[p]);
+            r.v[p] = A::madd(w[j], q[j + R].v[p], r.v[p]);
     return r;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
 // CPML (CPML.cpp:84-95 applyCPML): psi = b psi + a d ; d = d + psi.  The memory variables live in compact slabs
-// (x: [ly][z][2W], y: [2W][z][x], z: [ly][2W][x]); their loads are issued before the stage wait.
+// (x: [ly][z][2W], y: [2W][z][x], z: [ly][2W][x]).
 // ---------------------------------------------------------------------------------------------------------------------
-struct CpT { // per-thread, constant over the march
-    bool active, anyX;
+struct CpT { // per thread, constant over the march
+    bool anyX;
     int kx[4], kz;
-    long long pxBase, pzBase;
     float xa[4], xb[4], za, zb;
 };
-struct CpI { // per iteration
-    int ky;
-    float ya, yb;
-    long long pxOff, pyOff, pzOff;
-    float px[4];
-    F4 py, pz, pz2;
-};
-
 template <bool CPML> __device__ __forceinline__ void cpSetup(const WsParams &P, CpT &t, bool active, int x0, int z, bool halfX, bool halfZ)
 {
-    t.active = active;
     t.anyX = false;
     t.kz = -1;
-    t.pxBase = t.pzBase = 0;
     t.za = t.zb = 0.0f;
 #pragma unroll
     for (int p = 0; p < 4; p++) {
@@ -215,48 +231,23 @@ template <bool CPML> __device__ __forceinline__ void cpSetup(const WsParams &P, 
         t.za = __ldg((halfZ ? P.cazh : P.caz) + t.kz);
         t.zb = __ldg((halfZ ? P.cbzh : P.cbz) + t.kz);
     }
-    t.pxBase = (long long)z * (2 * W);
-    t.pzBase = (long long)t.kz * P.nx + x0;
 }
-// issue the loads of this plane's memory variables (x slot sx, y slot sy, z slot sz)
-template <bool CPML, int sx, int sy, int sz, int sz2 = -1> __device__ __forceinline__ void cpLoad(const WsParams &P, const CpT &t, CpI &it, int ly, int gy, int x0, int z, bool halfY)
+// one x term: ps points at the slab row of this thread's (ly, z); entries kx[p]
+__device__ __forceinline__ void cpLoadX(const CpT &t, const float *ps, float (&px)[4])
 {
-    it.ky = -1;
-    if (!CPML || !t.active)
-        return;
-    const int W = P.W;
-    it.ky = wsCpmlIndex(gy, P.gny, W);
-    if (P.free_surface != 0 && gy < W)
-        it.ky = -1; // no CPML in the top layer below a free surface (CPML3D.cpp:320-328)
-    it.pxOff = (long long)ly * P.nz * (2 * W) + t.pxBase;
-    it.pzOff = (long long)ly * (2 * W) * P.nx + t.pzBase;
-    it.pyOff = ((long long)it.ky * P.nz + z) * P.nx + x0;
-    if (sx >= 0 && t.anyX) {
 #pragma unroll
-        for (int p = 0; p < 4; p++)
-            if (t.kx[p] >= 0)
-                it.px[p] = P.psi[sx >= 0 ? sx : 0][it.pxOff + t.kx[p]];
-    }
-    if (sy >= 0 && it.ky >= 0) {
-        it.ya = __ldg((halfY ? P.cayh : P.cay) + it.ky);
-        it.yb = __ldg((halfY ? P.cbyh : P.cby) + it.ky);
-        it.py = ld4(P.psi[sy >= 0 ? sy : 0] + it.pyOff);
-    }
-    if (sz >= 0 && t.kz >= 0)
-        it.pz = ld4(P.psi[sz >= 0 ? sz : 0] + it.pzOff);
-    if (sz2 >= 0 && t.kz >= 0)
-        it.pz2 = ld4(P.psi[sz2 >= 0 ? sz2 : 0] + it.pzOff);
+    for (int p = 0; p < 4; p++)
+        if (t.kx[p] >= 0)
+            px[p] = ps[t.kx[p]];
 }
-template <bool CPML> __device__ __forceinline__ void cpApplyX(const WsParams &P, const CpT &t, const CpI &it, F4 &d, int slot)
+__device__ __forceinline__ void cpApplyX(const CpT &t, float *ps, const float (&px)[4], F4 &d)
 {
-    if (!CPML || !t.anyX)
-        return;
 #pragma unroll
     for (int p = 0; p < 4; p++)
         if (t.kx[p] >= 0) {
-            float v = A::mul(it.px[p], t.xb[p]);
+            float v = A::mul(px[p], t.xb[p]);
             v = A::add(v, A::mul(t.xa[p], d.v[p]));
-            P.psi[slot][it.pxOff + t.kx[p]] = v;
+            ps[t.kx[p]] = v;
             d.v[p] = A::add(d.v[p], v);
         }
 }
@@ -272,36 +263,16 @@ __device__ __forceinline__ void cpApply4(float *ps, const F4 &old, float a, floa
     }
     st4(ps, nw);
 }
-template <bool CPML> __device__ __forceinline__ void cpApplyY(const WsParams &P, const CpT &t, const CpI &it, F4 &d, int slot)
-{
-    if (!CPML || !t.active || it.ky < 0)
-        return;
-    cpApply4(P.psi[slot] + it.pyOff, it.py, it.ya, it.yb, d);
-}
-template <bool CPML> __device__ __forceinline__ void cpApplyZ(const WsParams &P, const CpT &t, const CpI &it, F4 &d, int slot)
-{
-    if (!CPML || t.kz < 0)
-        return;
-    cpApply4(P.psi[slot] + it.pzOff, it.pz, t.za, t.zb, d);
-}
-template <bool CPML> __device__ __forceinline__ void cpApplyZ2(const WsParams &P, const CpT &t, const CpI &it, F4 &d, int slot)
-{
-    if (!CPML || t.kz < 0)
-        return;
-    cpApply4(P.psi[slot] + it.pzOff, it.pz2, t.za, t.zb, d);
-}
-// interior weights (same on every axis; policy 0): forward taps are table indices 1..Q of the interior row
-template <int Q> __device__ __forceinline__ void loadInterior(const WsParams &P, float (&c)[Q])
-{
-    constexpr int H = Q / 2;
-    const float *w = P.tab + ((size_t)OP_XF * (2 * H + 1) + H) * (Q + 1);
-#pragma unroll
-    for (int j = 0; j < Q; j++)
-        c[j] = __ldg(w + 1 + j);
-}
-// y weights of the velocity half-step for global plane gy: with a free surface every row comes from the image-method
+
+// per-plane (run-time) y quantities of the generic step
+template <int Q> struct YDyn {
+    float w[Q]; // y weights of this plane
+    int ky;     // y-CPML slab index or -1
+    float ya, yb;
+};
+// y weights of the first half-step for global plane gy: with a free surface every row comes from the image-method
 // operators (their interior rows are scaled (c/DH)*DT, not c*(DT/DH): Derivatives.cpp:407-425 vs FDTD3D.cpp:211-216)
-template <int Q, bool FWD> __device__ __forceinline__ void loadYWeights(const WsParams &P, int gy, float (&w)[Q])
+template <int Q, bool FWD> __device__ __forceinline__ void loadYWeightsVel(const WsParams &P, int gy, float (&w)[Q])
 {
     constexpr int H = Q / 2;
     const int op = P.free_surface == 1 ? (FWD ? OP_YF_FS : OP_YB_FS) : (FWD ? OP_YF : OP_YB);
@@ -311,127 +282,286 @@ template <int Q, bool FWD> __device__ __forceinline__ void loadYWeights(const Ws
     for (int j = 0; j < Q; j++)
         w[j] = __ldg(t + j);
 }
+__device__ __forceinline__ int yCpmlIndex(const WsParams &P, int gy)
+{
+    int ky = wsCpmlIndex(gy, P.gny, P.W);
+    if (P.free_surface != 0 && gy < P.W)
+        ky = -1; // no CPML in the top layer below a free surface (CPML3D.cpp:320-328)
+    return ky;
+}
+// true if planes [gy0, gy1] need the generic step (image-method rows or a y-CPML layer)
+template <bool CPML> __device__ __forceinline__ bool needsGeneric(const WsParams &P, int gy0, int gy1, int H, bool velocity)
+{
+    if (velocity && P.free_surface == 1 && gy0 < H)
+        return true;
+    if (CPML) {
+        if (P.free_surface == 0 && gy0 < P.W)
+            return true;
+        if (gy1 >= P.gny - P.W)
+            return true;
+    }
+    return false;
+}
 
 // ---------------------------------------------------------------------------------------------------------------------
-// shared-memory stage layouts (offsets in floats)
+// shared-memory stage layouts (offsets in floats); the order inside a multi-field box is the arena order
 // ---------------------------------------------------------------------------------------------------------------------
 template <int Q> struct StageV { // velocity half-step
     using C = Cfg<Q>;
-    static constexpr int SXX = 0, SXY = SXX + C::N_X, SXZ = SXY + C::N_X, SYZ = SXZ + C::N_XZ, SZZ = SYZ + C::N_Z;
-    static constexpr int FEED = SZZ + C::N_Z;      // 3 plain tiles: Sxy(y+H-1), Syy(y+H), Syz(y+H-1)
-    static constexpr int OWNV = FEED + 3 * C::N_P; // vx vy vz
-    static constexpr int OWNR = OWNV + 3 * C::N_P; // rix riy riz
+    static constexpr int SXX = 0, SXY = SXX + C::N_X;               // TM_SX_X   {sxx,sxy}, x halo
+    static constexpr int SYZ = SXY + C::N_X, SZZ = SYZ + C::N_XZ;   // TM_SZ_XZ  {syz,szz}, x and z halo
+    static constexpr int SXZ = SZZ + C::N_XZ;                       // TM_SXZ_XZ sxz, x and z halo
+    static constexpr int FEED = SXZ + C::N_XZ;                      // 3 plain tiles: Sxy(y+H-1), Syy(y+H), Syz(y+H-1)
+    static constexpr int OWNV = FEED + 3 * C::N_P;                  // vx vy vz
+    static constexpr int OWNR = OWNV + 3 * C::N_P;                  // rix riy riz
     static constexpr int SIZE = OWNR + 3 * C::N_P;
     static constexpr uint32_t BYTES_FEED = 3u * C::N_P * 4u;
     static constexpr uint32_t BYTES_FULL = (uint32_t)SIZE * 4u;
 };
 template <int Q> struct StageS { // stress half-step
     using C = Cfg<Q>;
-    static constexpr int TV = 0;                    // 3 XZ tiles: vx vy vz
-    static constexpr int FEED = TV + 3 * C::N_XZ;   // 3 plain tiles: vx(y+H), vy(y+H-1), vz(y+H)
-    static constexpr int OWNS = FEED + 3 * C::N_P;  // sxx syy szz sxy sxz syz
-    static constexpr int OWNM = OWNS + 6 * C::N_P;  // pi mu muxy muxz muyz
+    static constexpr int TV = 0;                   // 3 XZ tiles: vx vy vz
+    static constexpr int FEED = TV + 3 * C::N_XZ;  // 3 plain tiles: vx(y+H), vy(y+H-1), vz(y+H)
+    static constexpr int OWNS = FEED + 3 * C::N_P; // sxx sxy syy syz szz sxz
+    static constexpr int OWNM = OWNS + 6 * C::N_P; // pi mu muxy muxz muyz
     static constexpr int SIZE = OWNM + 5 * C::N_P;
     static constexpr uint32_t BYTES_FEED = 3u * C::N_P * 4u;
     static constexpr uint32_t BYTES_FULL = (uint32_t)SIZE * 4u;
+    // positions of the own stresses inside the TM_S_P box
+    static constexpr int O_SXX = 0, O_SXY = 1, O_SYY = 2, O_SYZ = 3, O_SZZ = 4, O_SXZ = 5;
 };
 
 struct Bars {
-    uint64_t full[NST], empty[NST];
+    uint64_t full[NSTMAX], empty[NSTMAX];
 };
+
+// consumer bookkeeping shared by both half-steps
+struct Thr {
+    int lx, lz, x0, z, lane;
+    bool active;
+    uint32_t barFull, barEmpty; // shared addresses of full[0] / empty[0]
+};
+__device__ __forceinline__ void consumerRelease(const Thr &t, int stage)
+{
+    __syncwarp();
+    if (t.lane == 0)
+        mbarArrive(t.barEmpty + 8u * stage);
+}
 
 // ---------------------------------------------------------------------------------------------------------------------
 // velocity half-step (ForwardSolver3Delastic.cpp:181-277)
-//   group 0: vx += rix * (Dxf Sxx + Dyb* Sxy + Dzb Sxz)      group 1: vy += riy * (Dxb Sxy + Dyf* Syy + Dzb Syz)
-//   group 2: vz += riz * (Dxb Sxz + Dyb* Syz + Dzf Szz)
+//   role 0: vx += rix * (Dxf Sxx + Dyb* Sxy + Dzb Sxz)      role 1: vy += riy * (Dxb Sxy + Dyf* Syy + Dzb Syz)
+//   role 2: vz += riz * (Dxb Sxz + Dyb* Syz + Dzf Szz)
+// The three roles have the same shape (one x, one y, one z derivative), so they share ONE instruction stream whose
+// operands are run-time offsets: three role-specific code streams of this size evict each other from the instruction
+// cache (measured).  The forward / backward choice of the x operator is folded into a 9-tap weight vector with a
+// leading or trailing zero (adding 0*w leaves every partial sum unchanged), of the z operator into the start row, of
+// the y operator into the plane the producer feeds.
 // ---------------------------------------------------------------------------------------------------------------------
-template <int Q, bool CPML, int G>
-__device__ __forceinline__ void velConsumer(const WsParams &P, const float *sm, Bars *bars, int tg, int tx0, int tz0, int yc0, int yc1)
+struct VRole {
+    int oX, oZ, oF, oV, oR; // shared-memory offsets inside a stage
+    float cx[WS_MAXQ + 1];  // x weights over offsets -H..+H
+    float *out;             // own row of the output field at plane 0
+    float *psx, *psy, *psz; // memory-variable slabs of the x / y / z term
+    int opY;                // OP_YF or OP_YB (+ image-method variant) for the generic step
+    bool yFwd, halfY;
+};
+
+// x derivative with 9-tap weights (see above); `row` points at the tile column of x0 - HX
+template <int Q> __device__ __forceinline__ F4 dX9(const float *row, const float *__restrict__ c)
+{
+    constexpr int H = Q / 2, HX = Cfg<Q>::HX, NV = (2 * HX + 4) / 4;
+    float w[NV * 4];
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+        const F4 t = ld4(row + 4 * k);
+        w[4 * k] = t.v[0]; w[4 * k + 1] = t.v[1]; w[4 * k + 2] = t.v[2]; w[4 * k + 3] = t.v[3];
+    }
+    F4 r;
+#pragma unroll
+    for (int p = 0; p < 4; p++) {
+        float acc = 0.0f;
+#pragma unroll
+        for (int j = 0; j <= Q; j++)
+            acc = A::madd(c[j], w[HX + p + j - H], acc);
+        r.v[p] = acc;
+    }
+    return r;
+}
+
+// one plane of one velocity component.  R = position inside a trip; GENERIC = run-time y weights / y-CPML; XZ = this
+// warp may sit in an x or z CPML layer.
+template <int Q, int R, bool GENERIC, bool XZ>
+__device__ __forceinline__ void velPlane(const WsParams &P, const Thr &t, const CpT &cpt, const VRole &ro, F4 (&q)[Cfg<Q>::QL], const float *st, float *gout, float *psx,
+                                         float *psz, const YDyn<Q> &yd, float *psy)
 {
     using C = Cfg<Q>;
-    using S = StageV<Q>;
-    constexpr int H = C::H, HX = C::HX, TXH = C::TXH;
-    constexpr bool YFWD = (G == 1);
-    const int lx = tg % C::LXN, lz = tg / C::LXN;
-    const int x0 = tx0 + 4 * lx, z = tz0 + lz;
-    const bool active = (x0 < P.nx) && (z < P.nz);
-    const int lane = threadIdx.x & 31;
-
-    float c[Q], wy[Q];
-    loadInterior<Q>(P, c);
-    loadYWeights<Q, YFWD>(P, H, wy);
-    const long long rowOff = P.base + x0 + (long long)z * P.pitch;
-    float *gv = P.fld[F_VX + G] + rowOff;
-
-    constexpr int sx = (G == 0) ? PSI_SXX_X : (G == 1 ? PSI_SXY_X : PSI_SXZ_X);
-    constexpr int sy = (G == 0) ? PSI_SXY_Y : (G == 1 ? PSI_SYY_Y : PSI_SYZ_Y);
-    constexpr int sz = (G == 0) ? PSI_SXZ_Z : (G == 1 ? PSI_SYZ_Z : PSI_SZZ_Z);
-    CpT cpt;
-    cpSetup<CPML>(P, cpt, active, x0, z, /*halfX*/ G == 0, /*halfZ*/ G == 2);
-
-    // shared-memory offsets of this thread inside a stage
-    const int oX = (G == 0 ? S::SXX : (G == 1 ? S::SXY : S::SXZ + H * TXH)) + lz * TXH + 4 * lx; // column of x0 - HX
-    const int oZ = (G == 0 ? S::SXZ + lz * TXH + 4 * lx + HX : (G == 1 ? S::SYZ : S::SZZ) + lz * TX + 4 * lx);
-    constexpr int ldZ = (G == 0) ? TXH : TX;
-    const int oP = lz * TX + 4 * lx;
-
-    F4 q[Q];
+    const bool ycp = GENERIC && yd.ky >= 0 && t.active;
+    float px[4];
+    F4 pz, py;
+    if (XZ) {
+        if (cpt.anyX)
+            cpLoadX(cpt, psx, px);
+        if (cpt.kz >= 0)
+            pz = ld4(psz);
+    }
+    if (ycp)
+        py = ld4(psy);
+    F4 u = dX9<Q>(st + ro.oX, ro.cx);
+    if (XZ && cpt.anyX)
+        cpApplyX(cpt, psx, px, u);
+    F4 w = dY<Q, R>(q, GENERIC ? yd.w : P.cwy);
+    if (ycp)
+        cpApply4(psy, py, yd.ya, yd.yb, w);
 #pragma unroll
-    for (int k = 0; k < Q; k++)
+    for (int p = 0; p < 4; p++)
+        u.v[p] = A::add(u.v[p], w.v[p]);
+    w = dZ<Q, false, C::TXH>(st + ro.oZ, P.cw);
+    if (XZ && cpt.kz >= 0)
+        cpApply4(psz, pz, cpt.za, cpt.zb, w);
+    F4 v = ld4(st + ro.oV);
+    const F4 r = ld4(st + ro.oR);
+#pragma unroll
+    for (int p = 0; p < 4; p++) {
+        u.v[p] = A::add(u.v[p], w.v[p]);
+        u.v[p] = A::mul(u.v[p], r.v[p]);
+        v.v[p] = A::add(v.v[p], u.v[p]);
+    }
+    if (t.active && P.fastDebug != 2)
+        st4cs(gout, v);
+}
+
+// UNR consecutive planes of a trip (template recursion keeps the queue offset R a compile-time constant)
+template <int Q, bool XZ, int R> struct VelUnroll {
+    static __device__ __forceinline__ void run(const WsParams &P, const Thr &t, const CpT &cpt, const VRole &ro, F4 (&q)[Cfg<Q>::QL], const float *sm, int stage0,
+                                               uint32_t parity, float *gout, float *psx, float *psz, long long sxStride, long long szStride)
+    {
+        using S = StageV<Q>;
+        const int stage = stage0 + R;
+        mbarWait(t.barFull + 8u * stage, parity);
+        const float *st = sm + stage * S::SIZE;
+        q[Q - 1 + R] = ld4(st + ro.oF);
+        YDyn<Q> yd;
+        yd.ky = -1;
+        if (P.fastDebug == 3) { // stores without arithmetic
+            if (t.active)
+                st4cs(gout, ld4(st + ro.oV));
+        } else if (P.fastDebug != 1)
+            velPlane<Q, R, false, XZ>(P, t, cpt, ro, q, st, gout, psx, psz, yd, nullptr);
+        consumerRelease(t, stage);
+        VelUnroll<Q, XZ, R + 1>::run(P, t, cpt, ro, q, sm, stage0, parity, gout + P.plane, XZ ? psx + sxStride : psx, XZ ? psz + szStride : psz, sxStride, szStride);
+    }
+};
+template <int Q, bool XZ> struct VelUnroll<Q, XZ, UNR> {
+    static __device__ __forceinline__ void run(const WsParams &, const Thr &, const CpT &, const VRole &, F4 (&)[Cfg<Q>::QL], const float *, int, uint32_t, float *,
+                                               float *, float *, long long, long long)
+    {
+    }
+};
+
+template <int Q, bool CPML>
+__device__ __forceinline__ void velConsumer(const WsParams &P, const float *sm, Thr t, int G, int yc0, int yc1)
+{
+    using S = StageV<Q>;
+    using C = Cfg<Q>;
+    constexpr int H = C::H, HX = C::HX, TXH = C::TXH;
+    // ---- role set-up (run-time; CPML slots and profiles: CPML3D.cpp:31-153) ----
+    VRole ro;
+    const int oP = t.lz * TX + 4 * t.lx;
+    const int oXrow = t.lz * TXH + 4 * t.lx; // column of x0 - HX in a tile without z halo
+    ro.oX = G == 0 ? S::SXX + oXrow : (G == 1 ? S::SXY + oXrow : S::SXZ + H * TXH + oXrow);
+    // z stencil: row z - H (backward) or z - H + 1 (forward, role 2), own column of a tile with x and z halo
+    ro.oZ = (G == 0 ? S::SXZ : (G == 1 ? S::SYZ : S::SZZ + TXH)) + oXrow + HX;
+    ro.oF = S::FEED + G * C::N_P + oP;
+    ro.oV = S::OWNV + G * C::N_P + oP;
+    ro.oR = S::OWNR + G * C::N_P + oP;
+#pragma unroll
+    for (int j = 0; j <= Q; j++) // forward (role 0): offsets -H+1..H; backward: -H..H-1
+        ro.cx[j] = G == 0 ? (j >= 1 ? P.cw[j - 1] : 0.0f) : (j < Q ? P.cw[j] : 0.0f);
+    ro.yFwd = G == 1;
+    ro.halfY = G == 1;
+    ro.opY = P.free_surface == 1 ? (ro.yFwd ? OP_YF_FS : OP_YB_FS) : (ro.yFwd ? OP_YF : OP_YB);
+    const int sx = G == 0 ? PSI_SXX_X : (G == 1 ? PSI_SXY_X : PSI_SXZ_X);
+    const int sy = G == 0 ? PSI_SXY_Y : (G == 1 ? PSI_SYY_Y : PSI_SYZ_Y);
+    const int sz = G == 0 ? PSI_SXZ_Z : (G == 1 ? PSI_SYZ_Z : PSI_SZZ_Z);
+    CpT cpt;
+    cpSetup<CPML>(P, cpt, t.active, t.x0, t.z, /*halfX*/ G == 0, /*halfZ*/ G == 2);
+    // warp-uniform: the unrolled march contains warp-level synchronisation
+    const bool warpXZ = CPML && __any_sync(0xffffffffu, cpt.anyX || cpt.kz >= 0);
+    const int W2 = 2 * P.W;
+    // strides of the memory-variable slabs per plane
+    const long long sxStride = (long long)P.nz * W2, szStride = (long long)W2 * P.nx;
+    ro.out = P.fld[F_VX + G] + P.base + t.x0 + (long long)t.z * P.pitch;
+    ro.psx = CPML ? P.psi[sx] + (long long)t.z * W2 : nullptr;
+    ro.psz = CPML ? P.psi[sz] + (long long)cpt.kz * P.nx + t.x0 : nullptr;
+    ro.psy = CPML ? P.psi[sy] + (long long)t.z * P.nx + t.x0 : nullptr;
+
+    F4 q[C::QL];
+#pragma unroll
+    for (int k = 0; k < C::QL; k++)
         q[k] = zero4();
 
     const int nIter = (Q - 1) + (yc1 - yc0);
-    int stage = 0;
-    uint32_t parity = 0;
-    for (int it = 0; it < nIter; it++) {
-        const int ly = yc0 - (Q - 1) + it;
-        const int gy = P.gy0 + ly;
+    // generic step: queue in canonical order, shifted by register moves
+    auto generic = [&](int it) {
+        const int ly = yc0 - (Q - 1) + it, gy = P.gy0 + ly;
         const bool comp = it >= Q - 1;
-        CpI cpi;
-        cpi.ky = -1;
+        const int stage = it % NSTV;
+        YDyn<Q> yd;
+        yd.ky = -1;
         if (comp) {
-            cpLoad<CPML, sx, sy, sz>(P, cpt, cpi, ly, gy, x0, z, /*halfY*/ G == 1);
-            if (P.free_surface == 1 && gy <= H)
-                loadYWeights<Q, YFWD>(P, gy, wy);
-        }
-        mbarWait(&bars->full[stage], parity);
-        const float *st = sm + stage * S::SIZE;
-        q[Q - 1] = ld4(st + S::FEED + G * C::N_P + oP);
-        if (comp) {
-            F4 u = dX<Q, G == 0>(st + oX, c);
-            cpApplyX<CPML>(P, cpt, cpi, u, sx);
-            F4 w = dY<Q>(q, wy);
-            cpApplyY<CPML>(P, cpt, cpi, w, sy);
+            // y weights of this plane: with a free surface every row comes from the image-method operators (their
+            // interior rows are scaled (c/DH)*DT, not c*(DT/DH): Derivatives.cpp:407-425 vs FDTD3D.cpp:211-216)
+            const int row = (P.free_surface == 1 && gy < H) ? max(gy, 0) : H;
+            const float *tw = P.tab + ((size_t)ro.opY * (2 * H + 1) + row) * (Q + 1) + (ro.yFwd ? 1 : 0);
 #pragma unroll
-            for (int p = 0; p < 4; p++)
-                u.v[p] = A::add(u.v[p], w.v[p]);
-            w = dZ<Q, G == 2>(st + oZ, ldZ, c);
-            cpApplyZ<CPML>(P, cpt, cpi, w, sz);
-            F4 v = ld4(st + S::OWNV + G * C::N_P + oP);
-            const F4 r = ld4(st + S::OWNR + G * C::N_P + oP);
-#pragma unroll
-            for (int p = 0; p < 4; p++) {
-                u.v[p] = A::add(u.v[p], w.v[p]);
-                u.v[p] = A::mul(u.v[p], r.v[p]);
-                v.v[p] = A::add(v.v[p], u.v[p]);
+            for (int j = 0; j < Q; j++)
+                yd.w[j] = __ldg(tw + j);
+            if (CPML) {
+                yd.ky = yCpmlIndex(P, gy);
+                if (yd.ky >= 0) {
+                    yd.ya = __ldg((ro.halfY ? P.cayh : P.cay) + yd.ky);
+                    yd.yb = __ldg((ro.halfY ? P.cbyh : P.cby) + yd.ky);
+                }
             }
-            if (active)
-                st4cs(gv + (long long)ly * P.plane, v);
         }
-        __syncwarp();
-        if (lane == 0)
-            mbarArrive(&bars->empty[stage]);
+        mbarWait(t.barFull + 8u * stage, (it / NSTV) & 1);
+        const float *st = sm + stage * S::SIZE;
+        q[Q - 1] = ld4(st + ro.oF);
+        if (comp)
+            velPlane<Q, 0, true, CPML>(P, t, cpt, ro, q, st, ro.out + (long long)ly * P.plane, CPML ? ro.psx + (long long)ly * sxStride : nullptr,
+                                       CPML ? ro.psz + (long long)ly * szStride : nullptr, yd, CPML ? ro.psy + (long long)yd.ky * P.nz * P.nx : nullptr);
+        consumerRelease(t, stage);
 #pragma unroll
         for (int k = 0; k < Q - 1; k++)
             q[k] = q[k + 1];
-        if (++stage == NST) {
-            stage = 0;
-            parity ^= 1;
+    };
+
+    int it = 0;
+    while (it < nIter) {
+        const int ly0 = yc0 - (Q - 1) + it, gy0 = P.gy0 + ly0;
+        // the first Q iterations (queue prologue + first plane) are generic; afterwards aligned trips of UNR planes
+        if (it >= Q && it % UNR == 0 && it + UNR <= nIter && !needsGeneric<CPML>(P, gy0, gy0 + UNR - 1, H, true)) {
+            float *gout = ro.out + (long long)ly0 * P.plane;
+            const int stage0 = it % NSTV;
+            const uint32_t parity = (it / NSTV) & 1;
+            if (warpXZ)
+                VelUnroll<Q, CPML, 0>::run(P, t, cpt, ro, q, sm, stage0, parity, gout, ro.psx + (long long)ly0 * sxStride, ro.psz + (long long)ly0 * szStride, sxStride,
+                                           szStride);
+            else
+                VelUnroll<Q, false, 0>::run(P, t, cpt, ro, q, sm, stage0, parity, gout, nullptr, nullptr, 0, 0);
+#pragma unroll
+            for (int k = 0; k < Q - 1; k++)
+                q[k] = q[k + UNR];
+            it += UNR;
+        } else {
+            generic(it);
+            it++;
         }
     }
 }
 
-template <int Q, bool CPML> __global__ void __launch_bounds__(NG_VEL *Cfg<Q>::NTG + 32, 1) kFastVel(const __grid_constant__ WsParams P)
+template <int Q, bool CPML> __global__ void __launch_bounds__(NGROUPS *Cfg<Q>::NTG + 32, 1) kFastVel(const __grid_constant__ WsParams P)
 {
     using C = Cfg<Q>;
     using S = StageV<Q>;
@@ -447,55 +577,57 @@ template <int Q, bool CPML> __global__ void __launch_bounds__(NG_VEL *Cfg<Q>::NT
     const int yc1 = min(P.yhi, yc0 + P.fastChunk);
     if (yc0 >= yc1)
         return;
+    const uint32_t barFull = smemU32(&bars.full[0]), barEmpty = smemU32(&bars.empty[0]);
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < NST; s++) {
-            mbarInit(&bars.full[s], 1);
-            mbarInit(&bars.empty[s], NG_VEL * C::WPG);
+        for (int s = 0; s < NSTV; s++) {
+            mbarInit(barFull + 8u * s, 1);
+            mbarInit(barEmpty + 8u * s, NGROUPS * C::WPG);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
     const int grp = tid / C::NTG;
-    if (grp == 0)
-        velConsumer<Q, CPML, 0>(P, sm, &bars, tid, tx0, tz0, yc0, yc1);
-    else if (grp == 1)
-        velConsumer<Q, CPML, 1>(P, sm, &bars, tid - C::NTG, tx0, tz0, yc0, yc1);
-    else if (grp == 2)
-        velConsumer<Q, CPML, 2>(P, sm, &bars, tid - 2 * C::NTG, tx0, tz0, yc0, yc1);
-    else if (tid == NG_VEL * C::NTG) {
+    if (grp < NGROUPS) {
+        Thr t;
+        const int tg = tid - grp * C::NTG;
+        t.lx = tg % C::LXN;
+        t.lz = tg / C::LXN;
+        t.x0 = tx0 + 4 * t.lx;
+        t.z = tz0 + t.lz;
+        t.lane = tid & 31;
+        t.active = (t.x0 < P.nx) && (t.z < P.nz);
+        t.barFull = barFull;
+        t.barEmpty = barEmpty;
+        velConsumer<Q, CPML>(P, sm, t, grp, yc0, yc1);
+    } else if (tid == NGROUPS * C::NTG) {
         // ---- producer: one elected thread streams the planes ----
         const int HZP = (P.nzp > 1) ? WS_HALO : 0;
         const int cx = WS_PADX + tx0, cz = HZP + tz0;
         const int nIter = (Q - 1) + (yc1 - yc0);
+        const uint32_t smBase = smemU32(sm);
         int stage = 0;
         uint32_t parity = 1; // first pass over the ring: the stages are free
         for (int it = 0; it < nIter; it++) {
             const int cy = WS_HALO + yc0 - (Q - 1) + it;
             const bool comp = it >= Q - 1;
-            if (it >= NST)
-                mbarWait(&bars.empty[stage], parity);
-            float *st = sm + stage * S::SIZE;
-            uint64_t *bar = &bars.full[stage];
+            if (it >= NSTV)
+                mbarWait(barEmpty + 8u * stage, parity);
+            const uint32_t st = smBase + (uint32_t)(stage * S::SIZE) * 4u;
+            const uint32_t bar = barFull + 8u * stage;
             mbarExpectTx(bar, comp ? S::BYTES_FULL : S::BYTES_FEED);
-            tmaLoad3D(st + S::FEED, &maps[TM_SXY_P], bar, cx, cz, cy + H - 1);
-            tmaLoad3D(st + S::FEED + C::N_P, &maps[TM_SYY_P], bar, cx, cz, cy + H);
-            tmaLoad3D(st + S::FEED + 2 * C::N_P, &maps[TM_SYZ_P], bar, cx, cz, cy + H - 1);
+            tmaLoad4D(st + 4u * S::FEED, &maps[TM_F1_P], bar, cx, cz, cy + H - 1, AF_SXY);
+            tmaLoad4D(st + 4u * (S::FEED + C::N_P), &maps[TM_F1_P], bar, cx, cz, cy + H, AF_SYY);
+            tmaLoad4D(st + 4u * (S::FEED + 2 * C::N_P), &maps[TM_F1_P], bar, cx, cz, cy + H - 1, AF_SYZ);
             if (comp) {
-                tmaLoad3D(st + S::SXX, &maps[TM_SXX_X], bar, cx - HX, cz, cy);
-                tmaLoad3D(st + S::SXY, &maps[TM_SXY_X], bar, cx - HX, cz, cy);
-                tmaLoad3D(st + S::SXZ, &maps[TM_SXZ_XZ], bar, cx - HX, cz - H, cy);
-                tmaLoad3D(st + S::SYZ, &maps[TM_SYZ_Z], bar, cx, cz - H, cy);
-                tmaLoad3D(st + S::SZZ, &maps[TM_SZZ_Z], bar, cx, cz - H, cy);
-                tmaLoad3D(st + S::OWNV, &maps[TM_VX_P], bar, cx, cz, cy);
-                tmaLoad3D(st + S::OWNV + C::N_P, &maps[TM_VY_P], bar, cx, cz, cy);
-                tmaLoad3D(st + S::OWNV + 2 * C::N_P, &maps[TM_VZ_P], bar, cx, cz, cy);
-                tmaLoad3D(st + S::OWNR, &maps[TM_RIX_P], bar, cx, cz, cy);
-                tmaLoad3D(st + S::OWNR + C::N_P, &maps[TM_RIY_P], bar, cx, cz, cy);
-                tmaLoad3D(st + S::OWNR + 2 * C::N_P, &maps[TM_RIZ_P], bar, cx, cz, cy);
+                tmaLoad4D(st + 4u * S::SXX, &maps[TM_SX_X], bar, cx - HX, cz, cy, AF_SXX);
+                tmaLoad4D(st + 4u * S::SYZ, &maps[TM_SZ_XZ], bar, cx - HX, cz - H, cy, AF_SYZ);
+                tmaLoad4D(st + 4u * S::SXZ, &maps[TM_SXZ_XZ], bar, cx - HX, cz - H, cy, AF_SXZ);
+                tmaLoad4D(st + 4u * S::OWNV, &maps[TM_V_P], bar, cx, cz, cy, AF_VX);
+                tmaLoad4D(st + 4u * S::OWNR, &maps[TM_R_P], bar, cx, cz, cy, AM_RIX);
             }
-            if (++stage == NST) {
+            if (++stage == NSTV) {
                 stage = 0;
                 parity ^= 1;
             }
@@ -507,161 +639,261 @@ template <int Q, bool CPML> __global__ void __launch_bounds__(NG_VEL *Cfg<Q>::NT
 // stress half-step (ForwardSolver3Delastic.cpp:288-404) incl. free-surface correction
 //   group 0: vxx = Dxb vx, vyy = Dyb vy, vzz = Dzb vz -> sxx, syy, szz (+ free surface)
 //   group 1: sxy += muxy (Dyf vx + Dxf vy)    group 2: sxz += muxz (Dzf vx + Dxf vz), syz += muyz (Dzf vy + Dyf vz)
+// All y operators of this half-step are the plain ones (ForwardSolver3Delastic.cpp:289), so only the y-CPML layers and
+// the free-surface plane need the generic step.
 // ---------------------------------------------------------------------------------------------------------------------
-template <int Q, bool CPML, int G>
-__device__ __forceinline__ void strConsumer(const WsParams &P, const float *sm, Bars *bars, int tg, int tx0, int tz0, int yc0, int yc1)
+struct StrPsi { // memory-variable pointers of one plane (x, z, second z term) and the y term
+    float *x, *z, *z2, *y;
+};
+
+template <int Q, int G, int R, bool GENERIC, bool XZ>
+__device__ __forceinline__ void strPlane(const WsParams &P, const Thr &t, const CpT &cpt, F4 (&q)[Cfg<Q>::QL], const float *st, int oX, int oZ, int oP, long long o,
+                                         const StrPsi &ps, const YDyn<Q> &yd, int gy)
 {
-    using C = Cfg<Q>;
     using S = StageS<Q>;
-    constexpr int H = C::H, HX = C::HX, TXH = C::TXH, NXZ = C::N_XZ, NP = C::N_P;
-    constexpr int FEEDSLOT = (G == 0) ? 1 : (G == 1 ? 0 : 2); // vy | vx | vz
-    const int lx = tg % C::LXN, lz = tg / C::LXN;
-    const int x0 = tx0 + 4 * lx, z = tz0 + lz;
-    const bool active = (x0 < P.nx) && (z < P.nz);
-    const int lane = threadIdx.x & 31;
-
-    float c[Q];
-    loadInterior<Q>(P, c);
-    const long long rowOff = P.base + x0 + (long long)z * P.pitch;
-
-    CpT cpt;
-    // group 0 uses the full-grid profiles (vxx, vyy, vzz), the shear groups the half-grid ones (CPML3D.cpp:31-153)
-    cpSetup<CPML>(P, cpt, active, x0, z, /*halfX*/ G != 0, /*halfZ*/ G != 0);
-
-    const int oX = (lz + H) * TXH + 4 * lx; // x stencil: own row, column of x0 - HX   (inside an XZ tile)
-    const int oZ = lz * TXH + 4 * lx + HX;  // z stencil: row z - H, own column
-    const int oP = lz * TX + 4 * lx;
-
-    F4 q[Q];
-#pragma unroll
-    for (int k = 0; k < Q; k++)
-        q[k] = zero4();
-
-    const int nIter = (Q - 1) + (yc1 - yc0);
-    int stage = 0;
-    uint32_t parity = 0;
-    for (int it = 0; it < nIter; it++) {
-        const int ly = yc0 - (Q - 1) + it;
-        const int gy = P.gy0 + ly;
-        const bool comp = it >= Q - 1;
-        CpI cpi;
-        cpi.ky = -1;
-        if (comp) {
-            if (G == 0)
-                cpLoad<CPML, PSI_VXX, PSI_VYY, PSI_VZZ>(P, cpt, cpi, ly, gy, x0, z, false);
-            else if (G == 1)
-                cpLoad<CPML, PSI_VYX, PSI_VXY, -1>(P, cpt, cpi, ly, gy, x0, z, true);
-            else
-                cpLoad<CPML, PSI_VZX, PSI_VZY, PSI_VXZ, PSI_VYZ>(P, cpt, cpi, ly, gy, x0, z, true);
+    using C = Cfg<Q>;
+    constexpr int TXH = C::TXH, NXZ = C::N_XZ, NP = C::N_P;
+    const float *tvx = st + S::TV, *tvy = st + S::TV + NXZ, *tvz = st + S::TV + 2 * NXZ;
+    const bool ycp = GENERIC && yd.ky >= 0 && t.active;
+    float px[4];
+    F4 pz, pz2, py;
+    if (XZ) {
+        if (cpt.anyX)
+            cpLoadX(cpt, ps.x, px);
+        if (cpt.kz >= 0 && G != 1) {
+            pz = ld4(ps.z);
+            if (G == 2)
+                pz2 = ld4(ps.z2);
         }
-        mbarWait(&bars->full[stage], parity);
-        const float *st = sm + stage * S::SIZE;
-        const float *tvx = st + S::TV, *tvy = st + S::TV + NXZ, *tvz = st + S::TV + 2 * NXZ;
-        q[Q - 1] = ld4(st + S::FEED + FEEDSLOT * NP + oP);
-        if (comp) {
-            const long long o = rowOff + (long long)ly * P.plane;
-            if (G == 0) {
-                // normal strain rates; the y derivative of vy is the plain operator even below a free surface (:289)
-                F4 vxx = dX<Q, false>(tvx + oX, c);
-                F4 vyy = dY<Q>(q, c);
-                F4 vzz = dZ<Q, false>(tvz + oZ, TXH, c);
-                cpApplyX<CPML>(P, cpt, cpi, vxx, PSI_VXX);
-                cpApplyY<CPML>(P, cpt, cpi, vyy, PSI_VYY);
-                cpApplyZ<CPML>(P, cpt, cpi, vzz, PSI_VZZ);
-                F4 sxx = ld4(st + S::OWNS + 0 * NP + oP), syy = ld4(st + S::OWNS + 1 * NP + oP), szz = ld4(st + S::OWNS + 2 * NP + oP);
-                const F4 pi = ld4(st + S::OWNM + 0 * NP + oP), mu = ld4(st + S::OWNM + 1 * NP + oP);
+    }
+    if (ycp)
+        py = ld4(ps.y);
+    if (G == 0) {
+        // normal strain rates
+        F4 vxx = dX<Q, false>(tvx + oX, P.cw);
+        F4 vyy = dY<Q, R>(q, P.cw);
+        F4 vzz = dZ<Q, false, TXH>(tvz + oZ, P.cw);
+        if (XZ && cpt.anyX)
+            cpApplyX(cpt, ps.x, px, vxx);
+        if (ycp)
+            cpApply4(ps.y, py, yd.ya, yd.yb, vyy);
+        if (XZ && cpt.kz >= 0)
+            cpApply4(ps.z, pz, cpt.za, cpt.zb, vzz);
+        F4 sxx = ld4(st + S::OWNS + S::O_SXX * NP + oP), syy = ld4(st + S::OWNS + S::O_SYY * NP + oP), szz = ld4(st + S::OWNS + S::O_SZZ * NP + oP);
+        const F4 pi = ld4(st + S::OWNM + 0 * NP + oP), mu = ld4(st + S::OWNM + 1 * NP + oP);
 #pragma unroll
-                for (int p = 0; p < 4; p++) {
-                    float u = A::add(vxx.v[p], vyy.v[p]);
-                    u = A::add(u, vzz.v[p]);
-                    u = A::mul(u, pi.v[p]);
-                    sxx.v[p] = A::add(sxx.v[p], u);
-                    syy.v[p] = A::add(syy.v[p], u);
-                    szz.v[p] = A::add(szz.v[p], u);
-                    u = A::mul(A::add(vyy.v[p], vzz.v[p]), mu.v[p]);
-                    sxx.v[p] = A::msub(2.0f, u, sxx.v[p]);
-                    u = A::mul(A::add(vxx.v[p], vzz.v[p]), mu.v[p]);
-                    syy.v[p] = A::msub(2.0f, u, syy.v[p]);
-                    u = A::mul(A::add(vxx.v[p], vyy.v[p]), mu.v[p]);
-                    szz.v[p] = A::msub(2.0f, u, szz.v[p]);
-                }
-                if (P.free_surface == 1 && gy == 0 && active) {
-                    // FreeSurface3Delastic.cpp:15-47, FreeSurface.cpp:13-20
-                    const F4 sH = ldg4(P.sH + (long long)z * P.nx + x0), sV = ldg4(P.sV + (long long)z * P.nx + x0);
+        for (int p = 0; p < 4; p++) {
+            float u = A::add(vxx.v[p], vyy.v[p]);
+            u = A::add(u, vzz.v[p]);
+            u = A::mul(u, pi.v[p]);
+            sxx.v[p] = A::add(sxx.v[p], u);
+            syy.v[p] = A::add(syy.v[p], u);
+            szz.v[p] = A::add(szz.v[p], u);
+            u = A::mul(A::add(vyy.v[p], vzz.v[p]), mu.v[p]);
+            sxx.v[p] = A::msub(2.0f, u, sxx.v[p]);
+            u = A::mul(A::add(vxx.v[p], vzz.v[p]), mu.v[p]);
+            syy.v[p] = A::msub(2.0f, u, syy.v[p]);
+            u = A::mul(A::add(vxx.v[p], vyy.v[p]), mu.v[p]);
+            szz.v[p] = A::msub(2.0f, u, szz.v[p]);
+        }
+        if (GENERIC && P.free_surface == 1 && gy == 0 && t.active) {
+            // FreeSurface3Delastic.cpp:15-47, FreeSurface.cpp:13-20
+            const F4 sH = ldg4(P.sH + (long long)t.z * P.nx + t.x0), sV = ldg4(P.sV + (long long)t.z * P.nx + t.x0);
 #pragma unroll
-                    for (int p = 0; p < 4; p++) {
-                        const float hor = A::add(vxx.v[p], vzz.v[p]);
-                        float t = A::mul(sH.v[p], hor);
-                        sxx.v[p] = A::add(sxx.v[p], t);
-                        szz.v[p] = A::add(szz.v[p], t);
-                        t = A::mul(sV.v[p], vyy.v[p]);
-                        sxx.v[p] = A::sub(sxx.v[p], t);
-                        szz.v[p] = A::sub(szz.v[p], t);
-                        syy.v[p] = A::mul(syy.v[p], 0.0f);
-                    }
-                }
-                if (active) {
-                    st4cs(P.fld[F_SXX] + o, sxx);
-                    st4cs(P.fld[F_SYY] + o, syy);
-                    st4cs(P.fld[F_SZZ] + o, szz);
-                }
-            } else if (G == 1) {
-                F4 u = dY<Q>(q, c);
-                cpApplyY<CPML>(P, cpt, cpi, u, PSI_VXY);
-                F4 w = dX<Q, true>(tvy + oX, c);
-                cpApplyX<CPML>(P, cpt, cpi, w, PSI_VYX);
-                F4 s = ld4(st + S::OWNS + 3 * NP + oP);
-                const F4 m = ld4(st + S::OWNM + 2 * NP + oP);
-#pragma unroll
-                for (int p = 0; p < 4; p++) {
-                    const float t = A::add(u.v[p], w.v[p]);
-                    s.v[p] = A::add(s.v[p], A::mul(t, m.v[p]));
-                }
-                if (active)
-                    st4cs(P.fld[F_SXY] + o, s);
-            } else {
-                F4 u = dZ<Q, true>(tvx + oZ, TXH, c);
-                cpApplyZ<CPML>(P, cpt, cpi, u, PSI_VXZ);
-                F4 w = dX<Q, true>(tvz + oX, c);
-                cpApplyX<CPML>(P, cpt, cpi, w, PSI_VZX);
-                F4 s = ld4(st + S::OWNS + 4 * NP + oP);
-                const F4 m = ld4(st + S::OWNM + 3 * NP + oP);
-#pragma unroll
-                for (int p = 0; p < 4; p++) {
-                    const float t = A::add(u.v[p], w.v[p]);
-                    s.v[p] = A::add(s.v[p], A::mul(t, m.v[p]));
-                }
-                if (active)
-                    st4cs(P.fld[F_SXZ] + o, s);
-                u = dZ<Q, true>(tvy + oZ, TXH, c);
-                cpApplyZ2<CPML>(P, cpt, cpi, u, PSI_VYZ);
-                w = dY<Q>(q, c);
-                cpApplyY<CPML>(P, cpt, cpi, w, PSI_VZY);
-                s = ld4(st + S::OWNS + 5 * NP + oP);
-                const F4 m2 = ld4(st + S::OWNM + 4 * NP + oP);
-#pragma unroll
-                for (int p = 0; p < 4; p++) {
-                    const float t = A::add(u.v[p], w.v[p]);
-                    s.v[p] = A::add(s.v[p], A::mul(t, m2.v[p]));
-                }
-                if (active)
-                    st4cs(P.fld[F_SYZ] + o, s);
+            for (int p = 0; p < 4; p++) {
+                const float hor = A::add(vxx.v[p], vzz.v[p]);
+                float tt = A::mul(sH.v[p], hor);
+                sxx.v[p] = A::add(sxx.v[p], tt);
+                szz.v[p] = A::add(szz.v[p], tt);
+                tt = A::mul(sV.v[p], vyy.v[p]);
+                sxx.v[p] = A::sub(sxx.v[p], tt);
+                szz.v[p] = A::sub(szz.v[p], tt);
+                syy.v[p] = A::mul(syy.v[p], 0.0f);
             }
         }
-        __syncwarp();
-        if (lane == 0)
-            mbarArrive(&bars->empty[stage]);
+        if (t.active) {
+            st4cs(P.fld[F_SXX] + o, sxx);
+            st4cs(P.fld[F_SYY] + o, syy);
+            st4cs(P.fld[F_SZZ] + o, szz);
+        }
+    } else if (G == 1) {
+        F4 u = dY<Q, R>(q, P.cw);
+        if (ycp)
+            cpApply4(ps.y, py, yd.ya, yd.yb, u);
+        F4 w = dX<Q, true>(tvy + oX, P.cw);
+        if (XZ && cpt.anyX)
+            cpApplyX(cpt, ps.x, px, w);
+        F4 s = ld4(st + S::OWNS + S::O_SXY * NP + oP);
+        const F4 m = ld4(st + S::OWNM + 2 * NP + oP);
+#pragma unroll
+        for (int p = 0; p < 4; p++) {
+            const float tt = A::add(u.v[p], w.v[p]);
+            s.v[p] = A::add(s.v[p], A::mul(tt, m.v[p]));
+        }
+        if (t.active)
+            st4cs(P.fld[F_SXY] + o, s);
+    } else {
+        F4 u = dZ<Q, true, TXH>(tvx + oZ, P.cw);
+        if (XZ && cpt.kz >= 0)
+            cpApply4(ps.z, pz, cpt.za, cpt.zb, u);
+        F4 w = dX<Q, true>(tvz + oX, P.cw);
+        if (XZ && cpt.anyX)
+            cpApplyX(cpt, ps.x, px, w);
+        F4 s = ld4(st + S::OWNS + S::O_SXZ * NP + oP);
+        const F4 m = ld4(st + S::OWNM + 3 * NP + oP);
+#pragma unroll
+        for (int p = 0; p < 4; p++) {
+            const float tt = A::add(u.v[p], w.v[p]);
+            s.v[p] = A::add(s.v[p], A::mul(tt, m.v[p]));
+        }
+        if (t.active)
+            st4cs(P.fld[F_SXZ] + o, s);
+        u = dZ<Q, true, TXH>(tvy + oZ, P.cw);
+        if (XZ && cpt.kz >= 0)
+            cpApply4(ps.z2, pz2, cpt.za, cpt.zb, u);
+        w = dY<Q, R>(q, P.cw);
+        if (ycp)
+            cpApply4(ps.y, py, yd.ya, yd.yb, w);
+        s = ld4(st + S::OWNS + S::O_SYZ * NP + oP);
+        const F4 m2 = ld4(st + S::OWNM + 4 * NP + oP);
+#pragma unroll
+        for (int p = 0; p < 4; p++) {
+            const float tt = A::add(u.v[p], w.v[p]);
+            s.v[p] = A::add(s.v[p], A::mul(tt, m2.v[p]));
+        }
+        if (t.active)
+            st4cs(P.fld[F_SYZ] + o, s);
+    }
+}
+
+template <int Q, int G, bool XZ, int R> struct StrUnroll {
+    static __device__ __forceinline__ void run(const WsParams &P, const Thr &t, const CpT &cpt, F4 (&q)[Cfg<Q>::QL], const float *sm, int stage0, uint32_t parity,
+                                               int oX, int oZ, int oP, int oF, long long o, StrPsi ps, long long sxStride, long long szStride)
+    {
+        using S = StageS<Q>;
+        const int stage = stage0 + R;
+        mbarWait(t.barFull + 8u * stage, parity);
+        const float *st = sm + stage * S::SIZE;
+        q[Q - 1 + R] = ld4(st + oF);
+        YDyn<Q> yd;
+        yd.ky = -1;
+        if (P.fastDebug != 1)
+            strPlane<Q, G, R, false, XZ>(P, t, cpt, q, st, oX, oZ, oP, o, ps, yd, 1);
+        consumerRelease(t, stage);
+        if (XZ) {
+            ps.x += sxStride;
+            if (G != 1)
+                ps.z += szStride;
+            if (G == 2)
+                ps.z2 += szStride;
+        }
+        StrUnroll<Q, G, XZ, R + 1>::run(P, t, cpt, q, sm, stage0, parity, oX, oZ, oP, oF, o + P.plane, ps, sxStride, szStride);
+    }
+};
+template <int Q, int G, bool XZ> struct StrUnroll<Q, G, XZ, UNR> {
+    static __device__ __forceinline__ void run(const WsParams &, const Thr &, const CpT &, F4 (&)[Cfg<Q>::QL], const float *, int, uint32_t, int, int, int, int, long long,
+                                               StrPsi, long long, long long)
+    {
+    }
+};
+
+template <int Q, bool CPML, int G>
+__device__ __forceinline__ void strConsumer(const WsParams &P, const float *sm, Thr t, int yc0, int yc1)
+{
+    using S = StageS<Q>;
+    using C = Cfg<Q>;
+    constexpr int H = C::H, HX = C::HX, TXH = C::TXH;
+    constexpr int FEEDSLOT = (G == 0) ? 1 : (G == 1 ? 0 : 2); // vy | vx | vz
+    // memory-variable slots (CPML3D.cpp:31-153): group 0 full-grid profiles, shear groups half-grid profiles
+    constexpr int sx = (G == 0) ? PSI_VXX : (G == 1 ? PSI_VYX : PSI_VZX);
+    constexpr int sy = (G == 0) ? PSI_VYY : (G == 1 ? PSI_VXY : PSI_VZY);
+    constexpr int sz = (G == 0) ? PSI_VZZ : PSI_VXZ; // unused in group 1
+    constexpr int sz2 = PSI_VYZ;                      // group 2 only
+    constexpr bool half = (G != 0);
+    CpT cpt;
+    cpSetup<CPML>(P, cpt, t.active, t.x0, t.z, half, half);
+    const bool warpXZ = CPML && __any_sync(0xffffffffu, cpt.anyX || cpt.kz >= 0);
+    const int oX = (t.lz + H) * TXH + 4 * t.lx; // x stencil: own row, column of x0 - HX   (inside an XZ tile)
+    const int oZ = t.lz * TXH + 4 * t.lx + HX;  // z stencil: row z - H, own column
+    const int oP = t.lz * TX + 4 * t.lx, oF = S::FEED + FEEDSLOT * C::N_P + oP;
+    const long long rowOff = P.base + t.x0 + (long long)t.z * P.pitch;
+    const int W2 = 2 * P.W;
+    const long long sxStride = (long long)P.nz * W2, szStride = (long long)W2 * P.nx;
+
+    F4 q[C::QL];
+#pragma unroll
+    for (int k = 0; k < C::QL; k++)
+        q[k] = zero4();
+
+    auto psiAt = [&](int ly, int ky) {
+        StrPsi ps;
+        ps.x = ps.z = ps.z2 = ps.y = nullptr;
+        if (CPML) {
+            ps.x = P.psi[sx] + (long long)ly * sxStride + (long long)t.z * W2;
+            const long long zo = (long long)ly * szStride + (long long)cpt.kz * P.nx + t.x0;
+            if (G != 1)
+                ps.z = P.psi[sz] + zo;
+            if (G == 2)
+                ps.z2 = P.psi[sz2] + zo;
+            ps.y = P.psi[sy] + ((long long)ky * P.nz + t.z) * P.nx + t.x0;
+        }
+        return ps;
+    };
+
+    const int nIter = (Q - 1) + (yc1 - yc0);
+    auto generic = [&](int it) {
+        const int ly = yc0 - (Q - 1) + it, gy = P.gy0 + ly;
+        const bool comp = it >= Q - 1;
+        const int stage = it % NSTS;
+        YDyn<Q> yd;
+        yd.ky = -1;
+        if (comp && CPML) {
+            yd.ky = yCpmlIndex(P, gy);
+            if (yd.ky >= 0) {
+                yd.ya = __ldg((half ? P.cayh : P.cay) + yd.ky);
+                yd.yb = __ldg((half ? P.cbyh : P.cby) + yd.ky);
+            }
+        }
+        mbarWait(t.barFull + 8u * stage, (it / NSTS) & 1);
+        const float *st = sm + stage * S::SIZE;
+        q[Q - 1] = ld4(st + oF);
+        if (comp) {
+            const StrPsi ps = psiAt(ly, yd.ky);
+            strPlane<Q, G, 0, true, CPML>(P, t, cpt, q, st, oX, oZ, oP, rowOff + (long long)ly * P.plane, ps, yd, gy);
+        }
+        consumerRelease(t, stage);
 #pragma unroll
         for (int k = 0; k < Q - 1; k++)
             q[k] = q[k + 1];
-        if (++stage == NST) {
-            stage = 0;
-            parity ^= 1;
+    };
+
+    int it = 0;
+    while (it < nIter) {
+        const int ly0 = yc0 - (Q - 1) + it, gy0 = P.gy0 + ly0;
+        // the first Q iterations (queue prologue + first plane, which may be the free-surface plane) are generic
+        if (it >= Q && it % UNR == 0 && it + UNR <= nIter && !needsGeneric<CPML>(P, gy0, gy0 + UNR - 1, H, false)) {
+            const long long o = rowOff + (long long)ly0 * P.plane;
+            const int stage0 = it % NSTS;
+            const uint32_t parity = (it / NSTS) & 1;
+            if (warpXZ)
+                StrUnroll<Q, G, CPML, 0>::run(P, t, cpt, q, sm, stage0, parity, oX, oZ, oP, oF, o, psiAt(ly0, 0), sxStride, szStride);
+            else {
+                StrPsi ps;
+                ps.x = ps.z = ps.z2 = ps.y = nullptr;
+                StrUnroll<Q, G, false, 0>::run(P, t, cpt, q, sm, stage0, parity, oX, oZ, oP, oF, o, ps, 0, 0);
+            }
+#pragma unroll
+            for (int k = 0; k < Q - 1; k++)
+                q[k] = q[k + UNR];
+            it += UNR;
+        } else {
+            generic(it);
+            it++;
         }
     }
 }
 
-template <int Q, bool CPML> __global__ void __launch_bounds__(NG_STR *Cfg<Q>::NTG + 32, 1) kFastStress(const __grid_constant__ WsParams P)
+template <int Q, bool CPML> __global__ void __launch_bounds__(Cfg<Q>::NTHREADS, 1) kFastStress(const __grid_constant__ WsParams P)
 {
     using C = Cfg<Q>;
     using S = StageS<Q>;
@@ -677,57 +909,60 @@ template <int Q, bool CPML> __global__ void __launch_bounds__(NG_STR *Cfg<Q>::NT
     const int yc1 = min(P.yhi, yc0 + P.fastChunk);
     if (yc0 >= yc1)
         return;
+    const uint32_t barFull = smemU32(&bars.full[0]), barEmpty = smemU32(&bars.empty[0]);
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < NST; s++) {
-            mbarInit(&bars.full[s], 1);
-            mbarInit(&bars.empty[s], NG_STR * C::WPG);
+        for (int s = 0; s < NSTS; s++) {
+            mbarInit(barFull + 8u * s, 1);
+            mbarInit(barEmpty + 8u * s, NGROUPS * C::WPG);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    const int grp = tid / C::NTG;
-    if (grp == 0)
-        strConsumer<Q, CPML, 0>(P, sm, &bars, tid, tx0, tz0, yc0, yc1);
-    else if (grp == 1)
-        strConsumer<Q, CPML, 1>(P, sm, &bars, tid - C::NTG, tx0, tz0, yc0, yc1);
-    else if (grp == 2)
-        strConsumer<Q, CPML, 2>(P, sm, &bars, tid - 2 * C::NTG, tx0, tz0, yc0, yc1);
-    else if (tid == NG_STR * C::NTG) {
+    const int warp = tid >> 5;
+    const int grp = warp & 3;
+    if (grp < NGROUPS) {
+        Thr t;
+        const int tg = (warp >> 2) * 32 + (tid & 31);
+        t.lx = tg % C::LXN;
+        t.lz = tg / C::LXN;
+        t.x0 = tx0 + 4 * t.lx;
+        t.z = tz0 + t.lz;
+        t.lane = tid & 31;
+        t.active = (t.x0 < P.nx) && (t.z < P.nz);
+        t.barFull = barFull;
+        t.barEmpty = barEmpty;
+        if (grp == 0)
+            strConsumer<Q, CPML, 0>(P, sm, t, yc0, yc1);
+        else if (grp == 1)
+            strConsumer<Q, CPML, 1>(P, sm, t, yc0, yc1);
+        else
+            strConsumer<Q, CPML, 2>(P, sm, t, yc0, yc1);
+    } else if (tid == 3 * 32) {
         const int HZP = (P.nzp > 1) ? WS_HALO : 0;
         const int cx = WS_PADX + tx0, cz = HZP + tz0;
         const int nIter = (Q - 1) + (yc1 - yc0);
+        const uint32_t smBase = smemU32(sm);
         int stage = 0;
         uint32_t parity = 1;
         for (int it = 0; it < nIter; it++) {
             const int cy = WS_HALO + yc0 - (Q - 1) + it;
             const bool comp = it >= Q - 1;
-            if (it >= NST)
-                mbarWait(&bars.empty[stage], parity);
-            float *st = sm + stage * S::SIZE;
-            uint64_t *bar = &bars.full[stage];
+            if (it >= NSTS)
+                mbarWait(barEmpty + 8u * stage, parity);
+            const uint32_t st = smBase + (uint32_t)(stage * S::SIZE) * 4u;
+            const uint32_t bar = barFull + 8u * stage;
             mbarExpectTx(bar, comp ? S::BYTES_FULL : S::BYTES_FEED);
-            tmaLoad3D(st + S::FEED, &maps[TM_VX_P], bar, cx, cz, cy + H);
-            tmaLoad3D(st + S::FEED + C::N_P, &maps[TM_VY_P], bar, cx, cz, cy + H - 1);
-            tmaLoad3D(st + S::FEED + 2 * C::N_P, &maps[TM_VZ_P], bar, cx, cz, cy + H);
+            tmaLoad4D(st + 4u * S::FEED, &maps[TM_F1_P], bar, cx, cz, cy + H, AF_VX);
+            tmaLoad4D(st + 4u * (S::FEED + C::N_P), &maps[TM_F1_P], bar, cx, cz, cy + H - 1, AF_VY);
+            tmaLoad4D(st + 4u * (S::FEED + 2 * C::N_P), &maps[TM_F1_P], bar, cx, cz, cy + H, AF_VZ);
             if (comp) {
-                tmaLoad3D(st + S::TV, &maps[TM_VX_XZ], bar, cx - HX, cz - H, cy);
-                tmaLoad3D(st + S::TV + C::N_XZ, &maps[TM_VY_XZ], bar, cx - HX, cz - H, cy);
-                tmaLoad3D(st + S::TV + 2 * C::N_XZ, &maps[TM_VZ_XZ], bar, cx - HX, cz - H, cy);
-                tmaLoad3D(st + S::OWNS, &maps[TM_SXX_P], bar, cx, cz, cy);
-                tmaLoad3D(st + S::OWNS + C::N_P, &maps[TM_SYY_P], bar, cx, cz, cy);
-                tmaLoad3D(st + S::OWNS + 2 * C::N_P, &maps[TM_SZZ_P], bar, cx, cz, cy);
-                tmaLoad3D(st + S::OWNS + 3 * C::N_P, &maps[TM_SXY_P], bar, cx, cz, cy);
-                tmaLoad3D(st + S::OWNS + 4 * C::N_P, &maps[TM_SXZ_P], bar, cx, cz, cy);
-                tmaLoad3D(st + S::OWNS + 5 * C::N_P, &maps[TM_SYZ_P], bar, cx, cz, cy);
-                tmaLoad3D(st + S::OWNM, &maps[TM_PW_P], bar, cx, cz, cy);
-                tmaLoad3D(st + S::OWNM + C::N_P, &maps[TM_MU_P], bar, cx, cz, cy);
-                tmaLoad3D(st + S::OWNM + 2 * C::N_P, &maps[TM_MUXY_P], bar, cx, cz, cy);
-                tmaLoad3D(st + S::OWNM + 3 * C::N_P, &maps[TM_MUXZ_P], bar, cx, cz, cy);
-                tmaLoad3D(st + S::OWNM + 4 * C::N_P, &maps[TM_MUYZ_P], bar, cx, cz, cy);
+                tmaLoad4D(st + 4u * S::TV, &maps[TM_V_XZ], bar, cx - HX, cz - H, cy, AF_VX);
+                tmaLoad4D(st + 4u * S::OWNS, &maps[TM_S_P], bar, cx, cz, cy, AF_SXX);
+                tmaLoad4D(st + 4u * S::OWNM, &maps[TM_M_P], bar, cx, cz, cy, AM_PW);
             }
-            if (++stage == NST) {
+            if (++stage == NSTS) {
                 stage = 0;
                 parity ^= 1;
             }
@@ -756,14 +991,15 @@ EncodeTiledFn encodeFn()
     return fn;
 }
 
-CUtensorMap makeMap(const float *base, int pitch, int nzp, int nyp, int boxX, int boxZ)
+// 4-D map over an arena: (x, z, y, array); box = boxX x boxZ x 1 plane x boxF arrays
+CUtensorMap makeMap(const float *arena, int pitch, int nzp, int nyp, long long arrayStride, int nArrays, int boxX, int boxZ, int boxF)
 {
     CUtensorMap m;
-    const cuuint64_t dims[3] = {(cuuint64_t)pitch, (cuuint64_t)nzp, (cuuint64_t)nyp};
-    const cuuint64_t strides[2] = {(cuuint64_t)pitch * 4, (cuuint64_t)pitch * nzp * 4};
-    const cuuint32_t box[3] = {(cuuint32_t)boxX, (cuuint32_t)boxZ, 1};
-    const cuuint32_t es[3] = {1, 1, 1};
-    CUresult r = encodeFn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    const cuuint64_t dims[4] = {(cuuint64_t)pitch, (cuuint64_t)nzp, (cuuint64_t)nyp, (cuuint64_t)nArrays};
+    const cuuint64_t strides[3] = {(cuuint64_t)pitch * 4, (cuuint64_t)pitch * nzp * 4, (cuuint64_t)arrayStride * 4};
+    const cuuint32_t box[4] = {(cuuint32_t)boxX, (cuuint32_t)boxZ, 1, (cuuint32_t)boxF};
+    const cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = encodeFn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(arena), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
         throw std::runtime_error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
@@ -775,7 +1011,7 @@ template <int Q> void setAttrs()
     static bool done = false;
     if (done)
         return;
-    const int smV = NST * StageV<Q>::SIZE * 4, smS = NST * StageS<Q>::SIZE * 4;
+    const int smV = NSTV * StageV<Q>::SIZE * 4, smS = NSTS * StageS<Q>::SIZE * 4;
     cudaFuncSetAttribute(kFastVel<Q, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smV);
     cudaFuncSetAttribute(kFastVel<Q, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smV);
     cudaFuncSetAttribute(kFastStress<Q, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smS);
@@ -789,16 +1025,16 @@ template <int Q> void launchQ(const WsParams &P, int pass, cudaStream_t st)
     const int ny = P.yhi - P.ylo;
     dim3 grid((P.nx + TX - 1) / TX, (P.nz + TZ - 1) / TZ, (ny + P.fastChunk - 1) / P.fastChunk);
     const bool cpml = P.damping == 2;
+    const int nt = Cfg<Q>::NTHREADS;
     if (pass == 0) {
-        const size_t sm = (size_t)NST * StageV<Q>::SIZE * 4;
-        const int nt = NG_VEL * Cfg<Q>::NTG + 32;
+        const size_t sm = (size_t)NSTV * StageV<Q>::SIZE * 4;
+        const int ntv = NGROUPS * Cfg<Q>::NTG + 32;
         if (cpml)
-            kFastVel<Q, true><<<grid, nt, sm, st>>>(P);
+            kFastVel<Q, true><<<grid, ntv, sm, st>>>(P);
         else
-            kFastVel<Q, false><<<grid, nt, sm, st>>>(P);
+            kFastVel<Q, false><<<grid, ntv, sm, st>>>(P);
     } else {
-        const size_t sm = (size_t)NST * StageS<Q>::SIZE * 4;
-        const int nt = NG_STR * Cfg<Q>::NTG + 32;
+        const size_t sm = (size_t)NSTS * StageS<Q>::SIZE * 4;
         if (cpml)
             kFastStress<Q, true><<<grid, nt, sm, st>>>(P);
         else
@@ -818,6 +1054,8 @@ bool wsFastSupported(const WsParams &P, bool exact)
         return false;
     if (P.nx % 4 != 0)
         return false;
+    if (!P.fldArena || !P.matArena)
+        return false;
     return true;
 }
 
@@ -826,37 +1064,23 @@ void *wsFastPrepare(WsParams &P, int nyp)
     const int H = P.h, HX = H <= 4 ? 4 : 8;
     const int TXH = TX + 2 * HX, TZH = TZ + 2 * H;
     std::vector<CUtensorMap> maps(TM_COUNT);
-    auto mk = [&](int slot, const float *base, int bx, int bz) { maps[slot] = makeMap(base, P.pitch, P.nzp, nyp, bx, bz); };
-    mk(TM_SXX_X, P.fld[F_SXX], TXH, TZ);
-    mk(TM_SXY_X, P.fld[F_SXY], TXH, TZ);
-    mk(TM_SXZ_XZ, P.fld[F_SXZ], TXH, TZH);
-    mk(TM_SYZ_Z, P.fld[F_SYZ], TX, TZH);
-    mk(TM_SZZ_Z, P.fld[F_SZZ], TX, TZH);
-    mk(TM_SXY_P, P.fld[F_SXY], TX, TZ);
-    mk(TM_SYY_P, P.fld[F_SYY], TX, TZ);
-    mk(TM_SYZ_P, P.fld[F_SYZ], TX, TZ);
-    mk(TM_VX_P, P.fld[F_VX], TX, TZ);
-    mk(TM_VY_P, P.fld[F_VY], TX, TZ);
-    mk(TM_VZ_P, P.fld[F_VZ], TX, TZ);
-    mk(TM_RIX_P, P.mat[M_RIX], TX, TZ);
-    mk(TM_RIY_P, P.mat[M_RIY], TX, TZ);
-    mk(TM_RIZ_P, P.mat[M_RIZ], TX, TZ);
-    mk(TM_VX_XZ, P.fld[F_VX], TXH, TZH);
-    mk(TM_VY_XZ, P.fld[F_VY], TXH, TZH);
-    mk(TM_VZ_XZ, P.fld[F_VZ], TXH, TZH);
-    mk(TM_SXX_P, P.fld[F_SXX], TX, TZ);
-    mk(TM_SZZ_P, P.fld[F_SZZ], TX, TZ);
-    mk(TM_SXZ_P, P.fld[F_SXZ], TX, TZ);
-    mk(TM_PW_P, P.mat[M_PW], TX, TZ);
-    mk(TM_MU_P, P.mat[M_MU], TX, TZ);
-    mk(TM_MUXY_P, P.mat[M_MUXY], TX, TZ);
-    mk(TM_MUXZ_P, P.mat[M_MUXZ], TX, TZ);
-    mk(TM_MUYZ_P, P.mat[M_MUYZ], TX, TZ);
+    auto mkF = [&](int slot, int bx, int bz, int bf) { maps[slot] = makeMap(P.fldArena, P.pitch, P.nzp, nyp, P.arenaStride, AF_COUNT, bx, bz, bf); };
+    auto mkM = [&](int slot, int bx, int bz, int bf) { maps[slot] = makeMap(P.matArena, P.pitch, P.nzp, nyp, P.arenaStride, AM_COUNT, bx, bz, bf); };
+    mkF(TM_V_P, TX, TZ, 3);
+    mkM(TM_R_P, TX, TZ, 3);
+    mkF(TM_SX_X, TXH, TZ, 2);
+    mkF(TM_SXZ_XZ, TXH, TZH, 1);
+    mkF(TM_SZ_XZ, TXH, TZH, 2);
+    mkF(TM_F1_P, TX, TZ, 1);
+    mkF(TM_V_XZ, TXH, TZH, 3);
+    mkF(TM_S_P, TX, TZ, 6);
+    mkM(TM_M_P, TX, TZ, 5);
     void *dev = nullptr;
     if (cudaMalloc(&dev, sizeof(CUtensorMap) * TM_COUNT) != cudaSuccess)
         throw std::runtime_error("cudaMalloc for tensor maps failed");
     cudaMemcpy(dev, maps.data(), sizeof(CUtensorMap) * TM_COUNT, cudaMemcpyHostToDevice);
     P.fastMaps = dev;
+    P.fastDebug = getenv("WS_FAST_DEBUG") ? atoi(getenv("WS_FAST_DEBUG")) : 0;
     // planes per block: enough blocks to fill the 148 SMs several times over, long enough marches to amortise the
     // Q-1 feed-only iterations of the prologue
     const int tiles = ((P.nx + TX - 1) / TX) * ((P.nz + TZ - 1) / TZ);
