@@ -133,6 +133,12 @@ int ws_is_finite(ws_solver *s, int32_t *flag); /* Wavefields::isFinite + Seismog
  * with the interior kernels.                                                                                      */
 int ws_comm_unique_id(void *id128);
 int ws_comm_init(ws_solver *s, const void *id128);
+/* Bring-your-own transport instead of NCCL (e.g. CUDA-aware MPI, the dmemo::Communicator role; gloo in the CPU tests):
+ * `fn` must send `count` floats from `send` to rank `peer` and receive `count` floats from it into `recv` (device
+ * pointers on this handle's GPU), returning 0 on success.  Synchronous: the library drains its streams before each
+ * call, so there is no compute/communication overlap on this path.                                                */
+typedef int (*ws_sendrecv_fn)(void *user, const float *send, float *recv, size_t count, int peer);
+int ws_comm_init_external(ws_solver *s, ws_sendrecv_fn fn, void *user);
 
 /* --- instrumentation --------------------------------------------------------------------------------------------- */
 /* number of kernel launches issued by this handle since creation */

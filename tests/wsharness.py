@@ -117,6 +117,20 @@ class EmuSolver(Solver):
             cls.lib = _load_ws_lib(cls.so_path)
         return cls.lib
 
+    SENDRECV = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_size_t, C.c_int)
+
+    def comm_init_external(self, sendrecv):
+        """sendrecv(send: np.ndarray, recv: np.ndarray, peer: int) exchanges ghost planes with a neighbour rank."""
+        def thunk(_user, send, recv, count, peer):
+            try:
+                sendrecv(np.ctypeslib.as_array(send, shape=(count,)), np.ctypeslib.as_array(recv, shape=(count,)), peer)
+                return 0
+            except Exception as exc:  # surfaces as WS_ECOMM
+                print("sendrecv failed:", exc, flush=True)
+                return 1
+        self._cb = EmuSolver.SENDRECV(thunk)  # keep alive
+        self._check(self.lib.ws_comm_init_external(self.h, self._cb, None), "comm_init_external")
+
 
 # ---------------------------------------------------------------------------------------------------------------------
 # cases

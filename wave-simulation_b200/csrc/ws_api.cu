@@ -276,7 +276,7 @@ struct ws_solver {
     bool seismic = true, visco = false, exact = false;
     cudaStream_t stream = nullptr, commStream = nullptr;
     cudaEvent_t evCompute = nullptr, evComm = nullptr;
-    DevBuf<float> fldArena, matArena; // declared first: the slots below borrow from them
+    DevBuf<float> fldArena, matArena, psiXArena, psiZArena; // declared first: the slots below borrow from them
     DevBuf<float> fld[F_COUNT], mat[M_COUNT], psi[PSI_COUNT];
     bool matGiven[M_COUNT] = {};
     int psiAxis[PSI_COUNT];
@@ -299,6 +299,8 @@ struct ws_solver {
     // halo exchange lists
     std::vector<int> exchA, exchB; // field slots whose y-ghost planes are needed after pass A / pass B
     void *ncclComm = nullptr;
+    ws_sendrecv_fn extFn = nullptr; // bring-your-own transport (ws_comm_init_external)
+    void *extUser = nullptr;
     // instrumentation
     uint64_t launches = 0;
     bool timing = false;
@@ -557,9 +559,23 @@ void exchangeHalos(ws_solver *s, const std::vector<float *> &arrays, int h, cuda
 {
     if (s->d.nranks <= 1 || arrays.empty())
         return;
-    WS_REQUIRE(s->ncclComm, WS_ESTATE, "multi-rank solver used before ws_comm_init");
+    WS_REQUIRE(s->ncclComm || s->extFn, WS_ESTATE, "multi-rank solver used before ws_comm_init");
     const size_t count = (size_t)h * s->plane;
     const int up = s->d.rank - 1, down = s->d.rank + 1;
+    if (s->extFn) {
+        // synchronous pairwise exchange; every rank talks to its upper neighbour first, so the chain cannot deadlock
+        WS_CUDA_CHECK(cudaStreamSynchronize(s->stream));
+        WS_CUDA_CHECK(cudaStreamSynchronize(st));
+        for (float *a : arrays) {
+            float *origin = a + s->base - WS_PADX - (long long)(s->nzp > 1 ? WS_HALO : 0) * s->pitch;
+            if (up >= 0)
+                WS_REQUIRE(s->extFn(s->extUser, origin, origin - (long long)h * s->plane, count, up) == 0, WS_ECOMM, "external transport failed");
+            if (down < s->d.nranks)
+                WS_REQUIRE(s->extFn(s->extUser, origin + (long long)(s->nyl - h) * s->plane, origin + (long long)s->nyl * s->plane, count, down) == 0, WS_ECOMM,
+                           "external transport failed");
+        }
+        return;
+    }
     g_nccl.check(g_nccl.GroupStart(), "ncclGroupStart");
     for (float *a : arrays) {
         float *origin = a + s->base - WS_PADX - (long long)(s->nzp > 1 ? WS_HALO : 0) * s->pitch; // start of local plane 0
@@ -589,6 +605,8 @@ void refreshParams(ws_solver *s)
     P.fldArena = s->fldArena.p;
     P.matArena = s->matArena.p;
     P.arenaStride = s->total;
+    P.psiXArena = s->psiXArena.p;
+    P.psiZArena = s->psiZArena.p;
     P.cax = s->cax.p; P.cbx = s->cbx.p; P.caxh = s->caxh.p; P.cbxh = s->cbxh.p;
     P.cay = s->cay.p; P.cby = s->cby.p; P.cayh = s->cayh.p; P.cbyh = s->cbyh.p;
     P.caz = s->caz.p; P.cbz = s->cbz.p; P.cazh = s->cazh.p; P.cbzh = s->cbzh.p;
@@ -821,8 +839,24 @@ void prepareBoundaries(ws_solver *s)
         s->cax.upload(c.a); s->cbx.upload(c.b); s->caxh.upload(c.ah); s->cbxh.upload(c.bh);
         s->cay.upload(c.a); s->cby.upload(c.b); s->cayh.upload(c.ah); s->cbyh.upload(c.bh);
         s->caz.upload(c.a); s->cbz.upload(c.b); s->cazh.upload(c.ah); s->cbzh.upload(c.bh);
+        if (s->fldArena.p) {
+            // 3D elastic: the memory variables of the x and of the z terms are slots of two arenas, in the order the
+            // tiled kernels fetch them (ws_kernels_fast.cu: velocity half-step roles, then stress half-step groups)
+            static const int ox[6] = {PSI_SXX_X, PSI_SXY_X, PSI_SXZ_X, PSI_VXX, PSI_VYX, PSI_VZX};
+            static const int oz[6] = {PSI_SXZ_Z, PSI_SYZ_Z, PSI_SZZ_Z, PSI_VZZ, PSI_VXZ, PSI_VYZ};
+            const size_t nxs = psiSize(s, 0), nzs = psiSize(s, 2);
+            s->psiXArena.alloc(6 * nxs);
+            s->psiXArena.zero();
+            s->psiZArena.alloc(6 * nzs);
+            s->psiZArena.zero();
+            for (int k = 0; k < 6; k++) {
+                s->psi[ox[k]].borrow(s->psiXArena.p + k * nxs, nxs);
+                s->psi[oz[k]].borrow(s->psiZArena.p + k * nzs, nzs);
+            }
+        }
         for (auto &pa : psiFor(d)) {
-            s->psi[pa.first].alloc(psiSize(s, pa.second));
+            if (!s->psi[pa.first].p)
+                s->psi[pa.first].alloc(psiSize(s, pa.second));
             s->psi[pa.first].zero();
         }
     }
@@ -1597,6 +1631,15 @@ int ws_comm_init(ws_solver *s, const void *id128)
         NcclApi::UniqueId id;
         std::memcpy(&id, id128, 128);
         g_nccl.check(g_nccl.CommInitRank(&s->ncclComm, s->d.nranks, id, s->d.rank), "ncclCommInitRank");
+    });
+}
+
+int ws_comm_init_external(ws_solver *s, ws_sendrecv_fn fn, void *user)
+{
+    return guarded([&] {
+        WS_REQUIRE(s && fn, WS_EINVAL, "null argument");
+        s->extFn = fn;
+        s->extUser = user;
     });
 }
 

@@ -74,11 +74,14 @@ struct WsParams {
     int edge_policy;  // 0 truncate | 1 order-reduce
     int fastChunk;    // planes per thread block of the tiled kernels
     int fastDebug;    // developer switch (env WS_FAST_DEBUG): 1 = consumers skip the arithmetic and the stores (memory-side ceiling of the tiling)
+    int fastFlags;    // developer switch (env WS_FAST_FLAGS): bit 0 = L2 eviction-priority hints on the TMA loads (default on)
     const void *fastMaps; // device array of CUtensorMap (tiled kernels)
     // arenas of the tiled kernels: wavefields / model parameters that one TMA box fetches together are slots of one
     // allocation with a constant stride (`total` floats); null when the arrays are allocated one by one
     const float *fldArena, *matArena;
     long long arenaStride;
+    // arenas of the CPML memory variables of the x / z terms (6 slabs each, tiled kernels stage them by TMA); null otherwise
+    const float *psiXArena, *psiZArena;
     float cw[WS_MAXQ];  // interior weights of the plain operators, c_j * (DT/DH) (policy 0)
     float cwy[WS_MAXQ]; // interior weights of the y operators of the first half-step (image-method rows with a free surface)
     const float *tab; // derivative weight tables [WS_NOPS][2h+1][q+1], already scaled by DT/DH

@@ -25,6 +25,7 @@
 #include <cuda.h>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -79,11 +80,16 @@ enum {
     TM_V_XZ,      // {vx,vy,vz} with x and z halo (stress half-step)
     TM_S_P,       // {sxx,sxy,syy,syz,szz,sxz} plain (stress: own operands)
     TM_M_P,       // {pi,mu,muxy,muxz,muyz} plain
+    TM_PX,        // CPML memory variables of the x terms: slab rows (2W wide) of the tile's z rows, 3 arrays
+    TM_PZ,        // CPML memory variables of the z terms: slab rows of the tile, 3 arrays
     TM_COUNT
 };
 // positions inside the arenas
 enum { AF_VX = 0, AF_VY, AF_VZ, AF_SXX, AF_SXY, AF_SYY, AF_SYZ, AF_SZZ, AF_SXZ, AF_COUNT };
 enum { AM_RIX = 0, AM_RIY, AM_RIZ, AM_PW, AM_MU, AM_MUXY, AM_MUXZ, AM_MUYZ, AM_COUNT };
+// memory-variable arenas (ws_api.cu): x terms {sxx_x, sxy_x, sxz_x | vxx, vyx, vzx}, z terms {sxz_z, syz_z, szz_z | vzz, vxz, vyz};
+// the first three of each belong to the velocity half-step (role order), the last three to the stress half-step
+enum { APS_COUNT = 6 };
 
 __device__ __forceinline__ uint32_t smemU32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbarInit(uint32_t bar, int count)
@@ -117,6 +123,28 @@ __device__ __forceinline__ void tmaLoad4D(uint32_t dst, const CUtensorMap *map, 
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
                  "l"((unsigned long long)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                  : "memory");
+}
+
+// same with an L2 eviction-priority hint: operands that no thread block reads again before the grid has been swept
+// (own-point wavefields and model parameters) are fetched evict-first, so that L2 keeps the halo rows shared with the
+// neighbouring tiles and the planes that re-enter as stencil tiles
+__device__ __forceinline__ void tmaLoad4DHint(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2, int c3, uint64_t policy)
+{
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6}], [%2], %7;" ::"r"(dst),
+                 "l"((unsigned long long)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(policy)
+                 : "memory");
+}
+__device__ __forceinline__ uint64_t policyEvictFirst()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t policyEvictLast()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
 }
 
 struct F4 {
@@ -232,7 +260,7 @@ template <bool CPML> __device__ __forceinline__ void cpSetup(const WsParams &P, 
         t.zb = __ldg((halfZ ? P.cbzh : P.cbz) + t.kz);
     }
 }
-// one x term: ps points at the slab row of this thread's (ly, z); entries kx[p]
+// one x term: ps points at the (staged) slab row of this thread's (ly, z); entries kx[p]
 __device__ __forceinline__ void cpLoadX(const CpT &t, const float *ps, float (&px)[4])
 {
 #pragma unroll
@@ -340,7 +368,12 @@ struct Thr {
     int lx, lz, x0, z, lane;
     bool active;
     uint32_t barFull, barEmpty; // shared addresses of full[0] / empty[0]
+    int stride;                 // floats per stage (operands + staged CPML memory variables)
+    int oPX, oPZ, oPZ2;         // offsets inside a stage of this thread's staged memory variables (x row, z term, 2nd z term)
 };
+// floats of the staged memory variables per stage: 3 x-term slab rows sets (TZ rows of 2W) + 3 z-term tiles
+__host__ __device__ __forceinline__ int psxFloats(int W) { return (3 * TZ * 2 * W + 31) / 32 * 32; }
+__host__ __device__ __forceinline__ int psiStageFloats(int W) { return psxFloats(W) + 3 * TX * TZ; }
 __device__ __forceinline__ void consumerRelease(const Thr &t, int stage)
 {
     __syncwarp();
@@ -399,11 +432,11 @@ __device__ __forceinline__ void velPlane(const WsParams &P, const Thr &t, const 
     const bool ycp = GENERIC && yd.ky >= 0 && t.active;
     float px[4];
     F4 pz, py;
-    if (XZ) {
+    if (XZ) { // staged by the producer together with the operands of this plane
         if (cpt.anyX)
-            cpLoadX(cpt, psx, px);
+            cpLoadX(cpt, st + t.oPX, px);
         if (cpt.kz >= 0)
-            pz = ld4(psz);
+            pz = ld4(st + t.oPZ);
     }
     if (ycp)
         py = ld4(psy);
@@ -439,7 +472,7 @@ template <int Q, bool XZ, int R> struct VelUnroll {
         using S = StageV<Q>;
         const int stage = stage0 + R;
         mbarWait(t.barFull + 8u * stage, parity);
-        const float *st = sm + stage * S::SIZE;
+        const float *st = sm + stage * t.stride;
         q[Q - 1 + R] = ld4(st + ro.oF);
         YDyn<Q> yd;
         yd.ky = -1;
@@ -495,6 +528,8 @@ __device__ __forceinline__ void velConsumer(const WsParams &P, const float *sm, 
     ro.psx = CPML ? P.psi[sx] + (long long)t.z * W2 : nullptr;
     ro.psz = CPML ? P.psi[sz] + (long long)cpt.kz * P.nx + t.x0 : nullptr;
     ro.psy = CPML ? P.psi[sy] + (long long)t.z * P.nx + t.x0 : nullptr;
+    t.oPX = S::SIZE + (G * TZ + t.lz) * W2;
+    t.oPZ = S::SIZE + psxFloats(P.W) + G * C::N_P + oP;
 
     F4 q[C::QL];
 #pragma unroll
@@ -526,7 +561,7 @@ __device__ __forceinline__ void velConsumer(const WsParams &P, const float *sm, 
             }
         }
         mbarWait(t.barFull + 8u * stage, (it / NSTV) & 1);
-        const float *st = sm + stage * S::SIZE;
+        const float *st = sm + stage * t.stride;
         q[Q - 1] = ld4(st + ro.oF);
         if (comp)
             velPlane<Q, 0, true, CPML>(P, t, cpt, ro, q, st, ro.out + (long long)ly * P.plane, CPML ? ro.psx + (long long)ly * sxStride : nullptr,
@@ -600,6 +635,8 @@ template <int Q, bool CPML> __global__ void __launch_bounds__(NGROUPS *Cfg<Q>::N
         t.active = (t.x0 < P.nx) && (t.z < P.nz);
         t.barFull = barFull;
         t.barEmpty = barEmpty;
+        t.stride = S::SIZE + (CPML ? psiStageFloats(P.W) : 0);
+        t.oPX = t.oPZ = t.oPZ2 = 0;
         velConsumer<Q, CPML>(P, sm, t, grp, yc0, yc1);
     } else if (tid == NGROUPS * C::NTG) {
         // ---- producer: one elected thread streams the planes ----
@@ -609,23 +646,47 @@ template <int Q, bool CPML> __global__ void __launch_bounds__(NGROUPS *Cfg<Q>::N
         const uint32_t smBase = smemU32(sm);
         int stage = 0;
         uint32_t parity = 1; // first pass over the ring: the stages are free
+        const bool hints = (P.fastFlags & 1) != 0;
+        const uint64_t polOnce = policyEvictFirst(), polKeep = policyEvictLast();
+        const int stride = S::SIZE + (CPML ? psiStageFloats(P.W) : 0);
+        // memory variables of the x / z CPML layers this tile touches (slab rows, ws_api.cu)
+        const bool tileX = CPML && (tx0 < P.W || tx0 + TX > P.nx - P.W), tileZ = CPML && (tz0 < P.W || tz0 + TZ > P.nz - P.W);
+        const int kz0 = tz0 < P.W ? tz0 : tz0 - (P.nz - 2 * P.W);
+        const uint32_t bytesPX = 3u * TZ * 2u * (uint32_t)P.W * 4u, bytesPZ = 3u * C::N_P * 4u;
+        const uint32_t bytesFull = S::BYTES_FULL + (tileX ? bytesPX : 0u) + (tileZ ? bytesPZ : 0u);
         for (int it = 0; it < nIter; it++) {
             const int cy = WS_HALO + yc0 - (Q - 1) + it;
             const bool comp = it >= Q - 1;
             if (it >= NSTV)
                 mbarWait(barEmpty + 8u * stage, parity);
-            const uint32_t st = smBase + (uint32_t)(stage * S::SIZE) * 4u;
+            const uint32_t st = smBase + (uint32_t)(stage * stride) * 4u;
             const uint32_t bar = barFull + 8u * stage;
-            mbarExpectTx(bar, comp ? S::BYTES_FULL : S::BYTES_FEED);
-            tmaLoad4D(st + 4u * S::FEED, &maps[TM_F1_P], bar, cx, cz, cy + H - 1, AF_SXY);
-            tmaLoad4D(st + 4u * (S::FEED + C::N_P), &maps[TM_F1_P], bar, cx, cz, cy + H, AF_SYY);
-            tmaLoad4D(st + 4u * (S::FEED + 2 * C::N_P), &maps[TM_F1_P], bar, cx, cz, cy + H - 1, AF_SYZ);
+            mbarExpectTx(bar, comp ? bytesFull : S::BYTES_FEED);
+            if (comp && tileX)
+                tmaLoad4D(st + 4u * S::SIZE, &maps[TM_PX], bar, 0, tz0, cy - WS_HALO, 0);
+            if (comp && tileZ)
+                tmaLoad4D(st + 4u * (S::SIZE + psxFloats(P.W)), &maps[TM_PZ], bar, tx0, kz0, cy - WS_HALO, 0);
+            if (hints) {
+                // Sxy and Syz come back H-1 planes later as stencil tiles; Syy is used by this feed only
+                tmaLoad4DHint(st + 4u * S::FEED, &maps[TM_F1_P], bar, cx, cz, cy + H - 1, AF_SXY, polKeep);
+                tmaLoad4DHint(st + 4u * (S::FEED + C::N_P), &maps[TM_F1_P], bar, cx, cz, cy + H, AF_SYY, polOnce);
+                tmaLoad4DHint(st + 4u * (S::FEED + 2 * C::N_P), &maps[TM_F1_P], bar, cx, cz, cy + H - 1, AF_SYZ, polKeep);
+            } else {
+                tmaLoad4D(st + 4u * S::FEED, &maps[TM_F1_P], bar, cx, cz, cy + H - 1, AF_SXY);
+                tmaLoad4D(st + 4u * (S::FEED + C::N_P), &maps[TM_F1_P], bar, cx, cz, cy + H, AF_SYY);
+                tmaLoad4D(st + 4u * (S::FEED + 2 * C::N_P), &maps[TM_F1_P], bar, cx, cz, cy + H - 1, AF_SYZ);
+            }
             if (comp) {
                 tmaLoad4D(st + 4u * S::SXX, &maps[TM_SX_X], bar, cx - HX, cz, cy, AF_SXX);
                 tmaLoad4D(st + 4u * S::SYZ, &maps[TM_SZ_XZ], bar, cx - HX, cz - H, cy, AF_SYZ);
                 tmaLoad4D(st + 4u * S::SXZ, &maps[TM_SXZ_XZ], bar, cx - HX, cz - H, cy, AF_SXZ);
-                tmaLoad4D(st + 4u * S::OWNV, &maps[TM_V_P], bar, cx, cz, cy, AF_VX);
-                tmaLoad4D(st + 4u * S::OWNR, &maps[TM_R_P], bar, cx, cz, cy, AM_RIX);
+                if (hints) {
+                    tmaLoad4DHint(st + 4u * S::OWNV, &maps[TM_V_P], bar, cx, cz, cy, AF_VX, polOnce);
+                    tmaLoad4DHint(st + 4u * S::OWNR, &maps[TM_R_P], bar, cx, cz, cy, AM_RIX, polOnce);
+                } else {
+                    tmaLoad4D(st + 4u * S::OWNV, &maps[TM_V_P], bar, cx, cz, cy, AF_VX);
+                    tmaLoad4D(st + 4u * S::OWNR, &maps[TM_R_P], bar, cx, cz, cy, AM_RIX);
+                }
             }
             if (++stage == NSTV) {
                 stage = 0;
@@ -657,13 +718,13 @@ __device__ __forceinline__ void strPlane(const WsParams &P, const Thr &t, const 
     const bool ycp = GENERIC && yd.ky >= 0 && t.active;
     float px[4];
     F4 pz, pz2, py;
-    if (XZ) {
+    if (XZ) { // staged by the producer together with the operands of this plane
         if (cpt.anyX)
-            cpLoadX(cpt, ps.x, px);
+            cpLoadX(cpt, st + t.oPX, px);
         if (cpt.kz >= 0 && G != 1) {
-            pz = ld4(ps.z);
+            pz = ld4(st + t.oPZ);
             if (G == 2)
-                pz2 = ld4(ps.z2);
+                pz2 = ld4(st + t.oPZ2);
         }
     }
     if (ycp)
@@ -773,7 +834,7 @@ template <int Q, int G, bool XZ, int R> struct StrUnroll {
         using S = StageS<Q>;
         const int stage = stage0 + R;
         mbarWait(t.barFull + 8u * stage, parity);
-        const float *st = sm + stage * S::SIZE;
+        const float *st = sm + stage * t.stride;
         q[Q - 1 + R] = ld4(st + oF);
         YDyn<Q> yd;
         yd.ky = -1;
@@ -819,6 +880,10 @@ __device__ __forceinline__ void strConsumer(const WsParams &P, const float *sm, 
     const long long rowOff = P.base + t.x0 + (long long)t.z * P.pitch;
     const int W2 = 2 * P.W;
     const long long sxStride = (long long)P.nz * W2, szStride = (long long)W2 * P.nx;
+    // staged memory variables: x arena order {vxx, vyx, vzx} = group order; z arena order {vzz | vxz, vyz}
+    t.oPX = S::SIZE + (G * TZ + t.lz) * W2;
+    t.oPZ = S::SIZE + psxFloats(P.W) + (G == 0 ? 0 : 1) * C::N_P + oP;
+    t.oPZ2 = S::SIZE + psxFloats(P.W) + 2 * C::N_P + oP;
 
     F4 q[C::QL];
 #pragma unroll
@@ -855,7 +920,7 @@ __device__ __forceinline__ void strConsumer(const WsParams &P, const float *sm, 
             }
         }
         mbarWait(t.barFull + 8u * stage, (it / NSTS) & 1);
-        const float *st = sm + stage * S::SIZE;
+        const float *st = sm + stage * t.stride;
         q[Q - 1] = ld4(st + oF);
         if (comp) {
             const StrPsi ps = psiAt(ly, yd.ky);
@@ -933,6 +998,8 @@ template <int Q, bool CPML> __global__ void __launch_bounds__(Cfg<Q>::NTHREADS, 
         t.active = (t.x0 < P.nx) && (t.z < P.nz);
         t.barFull = barFull;
         t.barEmpty = barEmpty;
+        t.stride = S::SIZE + (CPML ? psiStageFloats(P.W) : 0);
+        t.oPX = t.oPZ = t.oPZ2 = 0;
         if (grp == 0)
             strConsumer<Q, CPML, 0>(P, sm, t, yc0, yc1);
         else if (grp == 1)
@@ -946,21 +1013,43 @@ template <int Q, bool CPML> __global__ void __launch_bounds__(Cfg<Q>::NTHREADS, 
         const uint32_t smBase = smemU32(sm);
         int stage = 0;
         uint32_t parity = 1;
+        const bool hints = (P.fastFlags & 1) != 0;
+        const uint64_t polOnce = policyEvictFirst(), polKeep = policyEvictLast();
+        const int stride = S::SIZE + (CPML ? psiStageFloats(P.W) : 0);
+        const bool tileX = CPML && (tx0 < P.W || tx0 + TX > P.nx - P.W), tileZ = CPML && (tz0 < P.W || tz0 + TZ > P.nz - P.W);
+        const int kz0 = tz0 < P.W ? tz0 : tz0 - (P.nz - 2 * P.W);
+        const uint32_t bytesPX = 3u * TZ * 2u * (uint32_t)P.W * 4u, bytesPZ = 3u * C::N_P * 4u;
+        const uint32_t bytesFull = S::BYTES_FULL + (tileX ? bytesPX : 0u) + (tileZ ? bytesPZ : 0u);
         for (int it = 0; it < nIter; it++) {
             const int cy = WS_HALO + yc0 - (Q - 1) + it;
             const bool comp = it >= Q - 1;
             if (it >= NSTS)
                 mbarWait(barEmpty + 8u * stage, parity);
-            const uint32_t st = smBase + (uint32_t)(stage * S::SIZE) * 4u;
+            const uint32_t st = smBase + (uint32_t)(stage * stride) * 4u;
             const uint32_t bar = barFull + 8u * stage;
-            mbarExpectTx(bar, comp ? S::BYTES_FULL : S::BYTES_FEED);
-            tmaLoad4D(st + 4u * S::FEED, &maps[TM_F1_P], bar, cx, cz, cy + H, AF_VX);
-            tmaLoad4D(st + 4u * (S::FEED + C::N_P), &maps[TM_F1_P], bar, cx, cz, cy + H - 1, AF_VY);
-            tmaLoad4D(st + 4u * (S::FEED + 2 * C::N_P), &maps[TM_F1_P], bar, cx, cz, cy + H, AF_VZ);
+            mbarExpectTx(bar, comp ? bytesFull : S::BYTES_FEED);
+            if (comp && tileX)
+                tmaLoad4D(st + 4u * S::SIZE, &maps[TM_PX], bar, 0, tz0, cy - WS_HALO, 3);
+            if (comp && tileZ)
+                tmaLoad4D(st + 4u * (S::SIZE + psxFloats(P.W)), &maps[TM_PZ], bar, tx0, kz0, cy - WS_HALO, 3);
+            if (hints) { // the velocities come back H (H-1) planes later as stencil tiles
+                tmaLoad4DHint(st + 4u * S::FEED, &maps[TM_F1_P], bar, cx, cz, cy + H, AF_VX, polKeep);
+                tmaLoad4DHint(st + 4u * (S::FEED + C::N_P), &maps[TM_F1_P], bar, cx, cz, cy + H - 1, AF_VY, polKeep);
+                tmaLoad4DHint(st + 4u * (S::FEED + 2 * C::N_P), &maps[TM_F1_P], bar, cx, cz, cy + H, AF_VZ, polKeep);
+            } else {
+                tmaLoad4D(st + 4u * S::FEED, &maps[TM_F1_P], bar, cx, cz, cy + H, AF_VX);
+                tmaLoad4D(st + 4u * (S::FEED + C::N_P), &maps[TM_F1_P], bar, cx, cz, cy + H - 1, AF_VY);
+                tmaLoad4D(st + 4u * (S::FEED + 2 * C::N_P), &maps[TM_F1_P], bar, cx, cz, cy + H, AF_VZ);
+            }
             if (comp) {
                 tmaLoad4D(st + 4u * S::TV, &maps[TM_V_XZ], bar, cx - HX, cz - H, cy, AF_VX);
-                tmaLoad4D(st + 4u * S::OWNS, &maps[TM_S_P], bar, cx, cz, cy, AF_SXX);
-                tmaLoad4D(st + 4u * S::OWNM, &maps[TM_M_P], bar, cx, cz, cy, AM_PW);
+                if (hints) {
+                    tmaLoad4DHint(st + 4u * S::OWNS, &maps[TM_S_P], bar, cx, cz, cy, AF_SXX, polOnce);
+                    tmaLoad4DHint(st + 4u * S::OWNM, &maps[TM_M_P], bar, cx, cz, cy, AM_PW, polOnce);
+                } else {
+                    tmaLoad4D(st + 4u * S::OWNS, &maps[TM_S_P], bar, cx, cz, cy, AF_SXX);
+                    tmaLoad4D(st + 4u * S::OWNM, &maps[TM_M_P], bar, cx, cz, cy, AM_PW);
+                }
             }
             if (++stage == NSTS) {
                 stage = 0;
@@ -1006,15 +1095,37 @@ CUtensorMap makeMap(const float *arena, int pitch, int nzp, int nyp, long long a
     return m;
 }
 
+constexpr int kMaxDynSmem = 227 * 1024 - 1024; // 227 KB per block minus the static barriers
+template <int Q> size_t smemBytes(int pass, bool cpml, int W)
+{
+    const size_t stage = (pass == 0 ? StageV<Q>::SIZE : StageS<Q>::SIZE) + (cpml ? psiStageFloats(W) : 0);
+    return (size_t)(pass == 0 ? NSTV : NSTS) * stage * 4;
+}
+
+// dense 4-D map (d0 fastest, arrays outermost); box = b0 x b1 x 1 x bA
+CUtensorMap makeMapG(const float *arena, int d0, int d1, int d2, int nArrays, int b0, int b1, int bA)
+{
+    CUtensorMap m;
+    const cuuint64_t dims[4] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2, (cuuint64_t)nArrays};
+    const cuuint64_t strides[3] = {(cuuint64_t)d0 * 4, (cuuint64_t)d0 * d1 * 4, (cuuint64_t)d0 * d1 * d2 * 4};
+    const cuuint32_t box[4] = {(cuuint32_t)b0, (cuuint32_t)b1, 1, (cuuint32_t)bA};
+    const cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = encodeFn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(arena), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        throw std::runtime_error("cuTensorMapEncodeTiled (memory variables) failed with code " + std::to_string((int)r));
+    return m;
+}
+
 template <int Q> void setAttrs()
 {
     static bool done = false;
     if (done)
         return;
     const int smV = NSTV * StageV<Q>::SIZE * 4, smS = NSTS * StageS<Q>::SIZE * 4;
-    cudaFuncSetAttribute(kFastVel<Q, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smV);
+    cudaFuncSetAttribute(kFastVel<Q, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
     cudaFuncSetAttribute(kFastVel<Q, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smV);
-    cudaFuncSetAttribute(kFastStress<Q, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smS);
+    cudaFuncSetAttribute(kFastStress<Q, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
     cudaFuncSetAttribute(kFastStress<Q, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smS);
     done = true;
 }
@@ -1027,14 +1138,14 @@ template <int Q> void launchQ(const WsParams &P, int pass, cudaStream_t st)
     const bool cpml = P.damping == 2;
     const int nt = Cfg<Q>::NTHREADS;
     if (pass == 0) {
-        const size_t sm = (size_t)NSTV * StageV<Q>::SIZE * 4;
+        const size_t sm = smemBytes<Q>(0, cpml, P.W);
         const int ntv = NGROUPS * Cfg<Q>::NTG + 32;
         if (cpml)
             kFastVel<Q, true><<<grid, ntv, sm, st>>>(P);
         else
             kFastVel<Q, false><<<grid, ntv, sm, st>>>(P);
     } else {
-        const size_t sm = (size_t)NSTS * StageS<Q>::SIZE * 4;
+        const size_t sm = smemBytes<Q>(1, cpml, P.W);
         if (cpml)
             kFastStress<Q, true><<<grid, nt, sm, st>>>(P);
         else
@@ -1056,6 +1167,18 @@ bool wsFastSupported(const WsParams &P, bool exact)
         return false;
     if (!P.fldArena || !P.matArena)
         return false;
+    if (P.damping == 2) {
+        // the x / z memory variables are staged by TMA: 16-byte slab rows (even W), a tile touches one side of an axis only,
+        // and the staged rows must fit next to the operands
+        if (!P.psiXArena || !P.psiZArena || P.W % 2 != 0)
+            return false;
+        for (int tz0 = 0; tz0 < P.nz; tz0 += TZ)
+            if (tz0 < P.W && tz0 + TZ > P.nz - P.W)
+                return false;
+        const size_t need = P.q == 8 ? std::max(smemBytes<8>(0, true, P.W), smemBytes<8>(1, true, P.W)) : std::max(smemBytes<4>(0, true, P.W), smemBytes<4>(1, true, P.W));
+        if (need > (size_t)kMaxDynSmem)
+            return false;
+    }
     return true;
 }
 
@@ -1075,12 +1198,18 @@ void *wsFastPrepare(WsParams &P, int nyp)
     mkF(TM_V_XZ, TXH, TZH, 3);
     mkF(TM_S_P, TX, TZ, 6);
     mkM(TM_M_P, TX, TZ, 5);
+    if (P.damping == 2) {
+        const int W2 = 2 * P.W;
+        maps[TM_PX] = makeMapG(P.psiXArena, W2, P.nz, P.nyl, APS_COUNT, W2, TZ, 3);
+        maps[TM_PZ] = makeMapG(P.psiZArena, P.nx, W2, P.nyl, APS_COUNT, TX, TZ, 3);
+    }
     void *dev = nullptr;
     if (cudaMalloc(&dev, sizeof(CUtensorMap) * TM_COUNT) != cudaSuccess)
         throw std::runtime_error("cudaMalloc for tensor maps failed");
     cudaMemcpy(dev, maps.data(), sizeof(CUtensorMap) * TM_COUNT, cudaMemcpyHostToDevice);
     P.fastMaps = dev;
     P.fastDebug = getenv("WS_FAST_DEBUG") ? atoi(getenv("WS_FAST_DEBUG")) : 0;
+    P.fastFlags = getenv("WS_FAST_FLAGS") ? atoi(getenv("WS_FAST_FLAGS")) : 1;
     // planes per block: enough blocks to fill the 148 SMs several times over, long enough marches to amortise the
     // Q-1 feed-only iterations of the prologue
     const int tiles = ((P.nx + TX - 1) / TX) * ((P.nz + TZ - 1) / TZ);
