@@ -281,6 +281,7 @@ struct ws_solver {
     bool matGiven[M_COUNT] = {};
     int psiAxis[PSI_COUNT];
     std::map<std::string, int> fldSlot;
+    DevBuf<float> cxTab;
     DevBuf<float> tab, cax, cbx, caxh, cbxh, cay, cby, cayh, cbyh, caz, cbz, cazh, cbzh, absCoeff;
     DevBuf<float> sH, sV, sRH[4], sRV[4];
     DevBuf<float> scratch; // dense staging buffer for pack/unpack
@@ -311,6 +312,7 @@ struct ws_solver {
     // CUDA graph of one time step
     cudaGraphExec_t graphExec = nullptr;
     int graphSteps = 0;
+    uint64_t graphLaunchesPerStep = 0;
 
     ~ws_solver()
     {
@@ -477,11 +479,22 @@ std::vector<std::pair<int, int>> psiFor(const ws_desc &d)
     return v;
 }
 
+// row layout of the x-term slabs (ws_common.cuh wsPsiXIndex): shift D of the high side and row length PX
+void psiXLayout(int nx, int W, int &D, int &PX)
+{
+    const int W4 = (W + 3) / 4 * 4;
+    D = nx - W - W4 >= 0 ? (nx - W - W4) / 4 * 4 : 0;
+    PX = (nx - D + 3) / 4 * 4;
+}
+
 size_t psiSize(const ws_solver *s, int axis)
 {
     const size_t W2 = 2 * (size_t)s->W;
-    if (axis == 0)
-        return (size_t)s->nyl * s->nz * W2;
+    if (axis == 0) {
+        int D, PX;
+        psiXLayout(s->nx, s->W, D, PX);
+        return (size_t)s->nyl * s->nz * PX;
+    }
     if (axis == 1)
         return W2 * s->nz * s->nx;
     return (size_t)s->nyl * W2 * s->nx;
@@ -605,6 +618,8 @@ void refreshParams(ws_solver *s)
     P.fldArena = s->fldArena.p;
     P.matArena = s->matArena.p;
     P.arenaStride = s->total;
+    psiXLayout(s->nx, s->W, P.psiDX, P.psiPitchX);
+    P.cxTab = s->cxTab.p;
     P.psiXArena = s->psiXArena.p;
     P.psiZArena = s->psiZArena.p;
     P.cax = s->cax.p; P.cbx = s->cbx.p; P.caxh = s->caxh.p; P.cbxh = s->cbxh.p;
@@ -839,11 +854,25 @@ void prepareBoundaries(ws_solver *s)
         s->cax.upload(c.a); s->cbx.upload(c.b); s->caxh.upload(c.ah); s->cbxh.upload(c.bh);
         s->cay.upload(c.a); s->cby.upload(c.b); s->cayh.upload(c.ah); s->cbyh.upload(c.bh);
         s->caz.upload(c.a); s->cbz.upload(c.b); s->cazh.upload(c.ah); s->cbzh.upload(c.bh);
+        {
+            // coefficient rows in slab-row order for the tiled kernels: {a, b, a half, b half}[PX], zero on the padding
+            int D, PX;
+            psiXLayout(s->nx, s->W, D, PX);
+            std::vector<float> t(4 * (size_t)PX, 0.0f);
+            for (int x = 0; x < s->nx; x++) {
+                const int k = wsCpmlIndex(x, s->nx, s->W);
+                if (k < 0)
+                    continue;
+                const int kp = wsPsiXIndex(x, s->W, D);
+                t[kp] = c.a[k]; t[PX + kp] = c.b[k]; t[2 * PX + kp] = c.ah[k]; t[3 * PX + kp] = c.bh[k];
+            }
+            s->cxTab.upload(t);
+        }
         if (s->fldArena.p) {
             // 3D elastic: the memory variables of the x and of the z terms are slots of two arenas, in the order the
             // tiled kernels fetch them (ws_kernels_fast.cu: velocity half-step roles, then stress half-step groups)
             static const int ox[6] = {PSI_SXX_X, PSI_SXY_X, PSI_SXZ_X, PSI_VXX, PSI_VYX, PSI_VZX};
-            static const int oz[6] = {PSI_SXZ_Z, PSI_SYZ_Z, PSI_SZZ_Z, PSI_VZZ, PSI_VXZ, PSI_VYZ};
+            static const int oz[6] = {PSI_SXZ_Z, PSI_SYZ_Z, PSI_SZZ_Z, PSI_VXZ, PSI_VYZ, PSI_VZZ};
             const size_t nxs = psiSize(s, 0), nzs = psiSize(s, 2);
             s->psiXArena.alloc(6 * nxs);
             s->psiXArena.zero();
@@ -938,9 +967,12 @@ void launchPass(ws_solver *s, int pass, int ylo, int yhi)
     WsParams P = s->P;
     P.ylo = ylo;
     P.yhi = yhi;
-    if (s->useFast && wsLaunchFast(P, pass, s->stream)) {
-        s->launches++;
-        return;
+    if (s->useFast) {
+        const int n = wsLaunchFast(P, pass, s->stream);
+        if (n > 0) {
+            s->launches += n;
+            return;
+        }
     }
     wsLaunchGeneral(P, s->exact, pass, s->stream);
     s->launches++;
@@ -1082,7 +1114,9 @@ size_t ws_estimate_memory(const ws_desc *desc)
     if (desc->damping == 2) {
         const size_t W2 = 2 * (size_t)desc->boundary_width;
         for (auto &pa : psiFor(*desc)) {
-            const size_t n = pa.second == 0 ? (size_t)nyl * nz * W2 : (pa.second == 1 ? W2 * nz * desc->nx : (size_t)nyl * W2 * desc->nx);
+            int D, PX;
+            psiXLayout(desc->nx, desc->boundary_width, D, PX);
+            const size_t n = pa.second == 0 ? (size_t)nyl * nz * PX : (pa.second == 1 ? W2 * nz * desc->nx : (size_t)nyl * W2 * desc->nx);
             bytes += n * sizeof(float);
         }
     }
@@ -1499,6 +1533,7 @@ int ws_run(ws_solver *s, int32_t t0, int32_t t1)
             const uint64_t before = s->launches;
             for (int k = 0; k < G; k++)
                 enqueueStep(s, nullptr, nullptr, nullptr);
+            s->graphLaunchesPerStep = (s->launches - before) / G;
             s->launches = before;
             WS_CUDA_CHECK(cudaStreamEndCapture(s->stream, &graph));
             WS_CUDA_CHECK(cudaGraphInstantiate(&s->graphExec, graph, 0));
@@ -1506,7 +1541,7 @@ int ws_run(ws_solver *s, int32_t t0, int32_t t1)
             s->graphSteps = G;
         }
         int done = 0;
-        const uint64_t perStep = 2 + (s->d.damping == 1 ? 1 : 0) + (s->nsrc > 0 ? 1 : 0) + (s->nrec > 0 ? 1 : 0) + 1;
+        const uint64_t perStep = s->graphLaunchesPerStep;
         while (nsteps - done >= G) {
             WS_CUDA_CHECK(cudaGraphLaunch(s->graphExec, s->stream));
             s->launches += perStep * G;

@@ -72,9 +72,12 @@ struct WsParams {
     int free_surface, damping, W;
     int ylo, yhi;     // local y range [ylo, yhi) processed by this launch (interior/boundary split for overlap)
     int edge_policy;  // 0 truncate | 1 order-reduce
-    int fastChunk;    // planes per thread block of the tiled kernels
+    int fastChunk, fastChunkEdge; // planes per thread block of the tiled kernels (interior / CPML-layer launch)
     int fastDebug;    // developer switch (env WS_FAST_DEBUG): 1 = consumers skip the arithmetic and the stores (memory-side ceiling of the tiling)
-    int fastFlags;    // developer switch (env WS_FAST_FLAGS): bit 0 = L2 eviction-priority hints on the TMA loads (default on)
+    int fastFlags;    // developer switch (env WS_FAST_FLAGS): bit 0 = L2 eviction-priority hints on the TMA loads, bit 1 = CPML-layer tiles in a launch of their own (default 3)
+    const int *fastTiles; // tile list of the tiled kernels ((z tile << 16) | x tile), layer tiles first
+    int fastNEdge, fastNTiles, fastTileBase;
+    unsigned long long *fastTrace; // developer trace buffer (env WS_FAST_TRACE) or null
     const void *fastMaps; // device array of CUtensorMap (tiled kernels)
     // arenas of the tiled kernels: wavefields / model parameters that one TMA box fetches together are slots of one
     // allocation with a constant stride (`total` floats); null when the arrays are allocated one by one
@@ -82,6 +85,12 @@ struct WsParams {
     long long arenaStride;
     // arenas of the CPML memory variables of the x / z terms (6 slabs each, tiled kernels stage them by TMA); null otherwise
     const float *psiXArena, *psiZArena;
+    // x-term slabs [ly][z][psiPitchX]: row entry k' of grid column x is wsPsiXIndex(x, W, psiDX) (low side k' = x, high
+    // side k' = x - psiDX with psiDX a multiple of 4, padding in between: ws_kernels_fast.cu); cxTab = coefficient rows
+    // {a, b, a half, b half}[psiPitchX] in k' order, zero on the padding (tiled kernels)
+    int psiPitchX, psiDX;
+    int psiBoxX; // entries of an x row a tile of the tiled kernels stages (its own side of the layer, or the whole row)
+    const float *cxTab;
     float cw[WS_MAXQ];  // interior weights of the plain operators, c_j * (DT/DH) (policy 0)
     float cwy[WS_MAXQ]; // interior weights of the y operators of the first half-step (image-method rows with a free surface)
     const float *tab; // derivative weight tables [WS_NOPS][2h+1][q+1], already scaled by DT/DH
@@ -140,6 +149,9 @@ __host__ __device__ __forceinline__ int wsCpmlIndex(int pos, int n, int W)
         return W + (pos - (n - W));
     return -1;
 }
+
+// entry of grid column x (inside an x layer) in a row of the x-term slabs
+__host__ __device__ __forceinline__ int wsPsiXIndex(int x, int W, int D) { return x < W ? x : x - D; }
 
 #define WS_CUDA_CHECK(expr)                                                                                           \
     do {                                                                                                               \

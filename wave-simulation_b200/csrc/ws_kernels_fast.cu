@@ -26,6 +26,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <algorithm>
+#include <cmath>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -39,12 +40,13 @@ namespace {
 #define WS_NSTS 4
 #endif
 constexpr int TX = 64, TZ = 8;
+constexpr int WS_TRACE_MAX = 1 << 16; // thread blocks per half-step covered by the developer trace
 constexpr int NSTV = WS_NSTV, NSTS = WS_NSTS, NSTMAX = NSTV > NSTS ? NSTV : NSTS; // ring depth of the velocity / stress kernel
 constexpr int NGROUPS = 3;
 // planes per trip of the unrolled march: the y queue holds Q + UNR - 1 planes and is shifted by UNR once per trip
 // (full rotation, UNR = Q, needs no moves but its code overflows the instruction cache: measured)
 #ifndef WS_UNR
-#define WS_UNR 2
+#define WS_UNR 1
 #endif
 constexpr int UNR = WS_UNR;
 
@@ -56,10 +58,6 @@ template <int Q> struct Cfg {
     static constexpr int LXN = TX / 4;
     static constexpr int NTG = LXN * TZ; // threads per consumer group
     static constexpr int WPG = NTG / 32; // warps per group
-    // warps are dealt round-robin to the 4 SM sub-partitions (warp id % 4): group g owns sub-partition g, so each
-    // sub-partition's instruction cache holds ONE group's march (with interleaved groups the three code streams
-    // evict each other: measured); sub-partition 3 hosts the producer warp (its other warps exit at once)
-    static constexpr int NTHREADS = 4 * NTG;
     // tile sizes (floats); all are multiples of 32 floats = 128 bytes
     static constexpr int N_P = TX * TZ, N_X = TXH * TZ, N_Z = TX * TZH, N_XZ = TXH * TZH;
     static_assert(NTG % 32 == 0, "consumer groups must be whole warps");
@@ -224,60 +222,52 @@ template <int Q, int R> __device__ __forceinline__ F4 dY(const F4 (&q)[Cfg<Q>::Q
 
 // ---------------------------------------------------------------------------------------------------------------------
 // CPML (CPML.cpp:84-95 applyCPML): psi = b psi + a d ; d = d + psi.  The memory variables live in compact slabs
-// (x: [ly][z][2W], y: [2W][z][x], z: [ly][2W][x]).
+// (x: [ly][z][PX], y: [2W][z][x], z: [ly][2W][x]).
+// Row layout of the x slabs (wsPsiXIndex, ws_common.cuh): the low-side entries sit at k' = x, the high-side entries at
+// k' = x - D with D a multiple of 4, and the entries between the two sides are padding.  A thread's 4 points therefore
+// map to ONE aligned float4 of the row, whose entries are either its own layer points or padding nobody else touches:
+// the x term is a branch-free vector update with coefficient rows that are zero on the padding (a = b = 0 leaves the
+// derivative unchanged and stores psi = 0).
 // ---------------------------------------------------------------------------------------------------------------------
+constexpr int PXMAX = 80; // floats per x-slab row the coefficient table in shared memory can hold (W <= 36)
 struct CpT { // per thread, constant over the march
-    bool anyX;
-    int kx[4], kz;
-    float xa[4], xb[4], za, zb;
+    int kxv;  // k' of the thread's first point, or -1 if none of its 4 points lies in an x layer
+    int oXA;  // offset of this role's a' row in the shared coefficient table (b' row follows PX later)
+    int kz;
+    float za, zb;
 };
 template <bool CPML> __device__ __forceinline__ void cpSetup(const WsParams &P, CpT &t, bool active, int x0, int z, bool halfX, bool halfZ)
 {
-    t.anyX = false;
+    t.kxv = -1;
+    t.oXA = 0;
     t.kz = -1;
     t.za = t.zb = 0.0f;
-#pragma unroll
-    for (int p = 0; p < 4; p++) {
-        t.kx[p] = -1;
-        t.xa[p] = t.xb[p] = 0.0f;
-    }
     if (!CPML || !active)
         return;
     const int W = P.W;
-    const float *ca = halfX ? P.caxh : P.cax, *cb = halfX ? P.cbxh : P.cbx;
-#pragma unroll
-    for (int p = 0; p < 4; p++) {
-        t.kx[p] = wsCpmlIndex(x0 + p, P.nx, W);
-        if (t.kx[p] >= 0) {
-            t.anyX = true;
-            t.xa[p] = __ldg(ca + t.kx[p]);
-            t.xb[p] = __ldg(cb + t.kx[p]);
-        }
-    }
+    if (x0 < W || x0 + 3 >= P.nx - W)
+        t.kxv = x0 < W ? x0 : x0 - P.psiDX;
+    t.oXA = (halfX ? 2 : 0) * P.psiPitchX;
     t.kz = wsCpmlIndex(z, P.nz, W);
     if (t.kz >= 0) {
         t.za = __ldg((halfZ ? P.cazh : P.caz) + t.kz);
         t.zb = __ldg((halfZ ? P.cbzh : P.cbz) + t.kz);
     }
 }
-// one x term: ps points at the (staged) slab row of this thread's (ly, z); entries kx[p]
-__device__ __forceinline__ void cpLoadX(const CpT &t, const float *ps, float (&px)[4])
+// one x term: sps = staged slab row of this thread's (ly, z) in shared memory, gps = the same row in the slab, tab = shared
+// coefficient table {a', b', a'half, b'half}[PX]
+__device__ __forceinline__ void cpApplyXv(const CpT &t, const float *sps, float *gps, const float *tab, int PX, F4 &d)
 {
+    const F4 old = ld4(sps + t.kxv), a = ld4(tab + t.oXA + t.kxv), b = ld4(tab + t.oXA + PX + t.kxv);
+    F4 nw;
 #pragma unroll
-    for (int p = 0; p < 4; p++)
-        if (t.kx[p] >= 0)
-            px[p] = ps[t.kx[p]];
-}
-__device__ __forceinline__ void cpApplyX(const CpT &t, float *ps, const float (&px)[4], F4 &d)
-{
-#pragma unroll
-    for (int p = 0; p < 4; p++)
-        if (t.kx[p] >= 0) {
-            float v = A::mul(px[p], t.xb[p]);
-            v = A::add(v, A::mul(t.xa[p], d.v[p]));
-            ps[t.kx[p]] = v;
-            d.v[p] = A::add(d.v[p], v);
-        }
+    for (int p = 0; p < 4; p++) {
+        float v = A::mul(old.v[p], b.v[p]);
+        v = A::add(v, A::mul(a.v[p], d.v[p]));
+        nw.v[p] = v;
+        d.v[p] = A::add(d.v[p], v);
+    }
+    st4(gps + t.kxv, nw);
 }
 __device__ __forceinline__ void cpApply4(float *ps, const F4 &old, float a, float b, F4 &d)
 {
@@ -355,12 +345,11 @@ template <int Q> struct StageS { // stress half-step
     static constexpr int SIZE = OWNM + 5 * C::N_P;
     static constexpr uint32_t BYTES_FEED = 3u * C::N_P * 4u;
     static constexpr uint32_t BYTES_FULL = (uint32_t)SIZE * 4u;
-    // positions of the own stresses inside the TM_S_P box
-    static constexpr int O_SXX = 0, O_SXY = 1, O_SYY = 2, O_SYZ = 3, O_SZZ = 4, O_SXZ = 5;
 };
 
 struct Bars {
     uint64_t full[NSTMAX], empty[NSTMAX];
+    uint64_t xfull, xfree; // stress half-step: derivative exchange between the roles
 };
 
 // consumer bookkeeping shared by both half-steps
@@ -368,12 +357,43 @@ struct Thr {
     int lx, lz, x0, z, lane;
     bool active;
     uint32_t barFull, barEmpty; // shared addresses of full[0] / empty[0]
+    uint32_t barXFull, barXFree;
     int stride;                 // floats per stage (operands + staged CPML memory variables)
+    const float *cxTab;         // shared coefficient table of the x layers
     int oPX, oPZ, oPZ2;         // offsets inside a stage of this thread's staged memory variables (x row, z term, 2nd z term)
 };
 // floats of the staged memory variables per stage: 3 x-term slab rows sets (TZ rows of 2W) + 3 z-term tiles
-__host__ __device__ __forceinline__ int psxFloats(int W) { return (3 * TZ * 2 * W + 31) / 32 * 32; }
-__host__ __device__ __forceinline__ int psiStageFloats(int W) { return psxFloats(W) + 3 * TX * TZ; }
+// (PX = row length of the x-term slabs, 2W rounded up to a 16-byte multiple)
+__host__ __device__ __forceinline__ int psxFloats(int PX) { return (3 * TZ * PX + 31) / 32 * 32; }
+__host__ __device__ __forceinline__ int psiStageFloats(int PX) { return psxFloats(PX) + 3 * TX * TZ; }
+// developer trace (env WS_FAST_TRACE=file): per thread block {start ns, end ns, SM id} of the last launch of each half-step
+__device__ __forceinline__ unsigned long long globalTimer()
+{
+    unsigned long long v;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
+    return v;
+}
+__device__ __forceinline__ void traceStart(const WsParams &P, int pass)
+{
+    if (P.fastTrace && threadIdx.x == 0) {
+        const size_t b = (size_t)pass * WS_TRACE_MAX + (P.fastTileBase + blockIdx.x + (size_t)P.fastNTiles * blockIdx.z);
+        if (b < (size_t)(pass + 1) * WS_TRACE_MAX) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            P.fastTrace[3 * b] = globalTimer();
+            P.fastTrace[3 * b + 1] = 0;
+            P.fastTrace[3 * b + 2] = smid;
+        }
+    }
+}
+__device__ __forceinline__ void traceEnd(const WsParams &P, int pass, int lane)
+{
+    if (P.fastTrace && lane == 0) {
+        const size_t b = (size_t)pass * WS_TRACE_MAX + (P.fastTileBase + blockIdx.x + (size_t)P.fastNTiles * blockIdx.z);
+        if (b < (size_t)(pass + 1) * WS_TRACE_MAX)
+            atomicMax(P.fastTrace + 3 * b + 1, globalTimer());
+    }
+}
 __device__ __forceinline__ void consumerRelease(const Thr &t, int stage)
 {
     __syncwarp();
@@ -430,19 +450,14 @@ __device__ __forceinline__ void velPlane(const WsParams &P, const Thr &t, const 
 {
     using C = Cfg<Q>;
     const bool ycp = GENERIC && yd.ky >= 0 && t.active;
-    float px[4];
     F4 pz, py;
-    if (XZ) { // staged by the producer together with the operands of this plane
-        if (cpt.anyX)
-            cpLoadX(cpt, st + t.oPX, px);
-        if (cpt.kz >= 0)
-            pz = ld4(st + t.oPZ);
-    }
+    if (XZ && cpt.kz >= 0) // staged by the producer together with the operands of this plane
+        pz = ld4(st + t.oPZ);
     if (ycp)
         py = ld4(psy);
     F4 u = dX9<Q>(st + ro.oX, ro.cx);
-    if (XZ && cpt.anyX)
-        cpApplyX(cpt, psx, px, u);
+    if (XZ && cpt.kxv >= 0)
+        cpApplyXv(cpt, st + t.oPX, psx, t.cxTab, P.psiPitchX, u);
     F4 w = dY<Q, R>(q, GENERIC ? yd.w : P.cwy);
     if (ycp)
         cpApply4(psy, py, yd.ya, yd.yb, w);
@@ -460,8 +475,14 @@ __device__ __forceinline__ void velPlane(const WsParams &P, const Thr &t, const 
         u.v[p] = A::mul(u.v[p], r.v[p]);
         v.v[p] = A::add(v.v[p], u.v[p]);
     }
-    if (t.active && P.fastDebug != 2)
-        st4cs(gout, v);
+    if (t.active && P.fastDebug != 2) {
+        if (P.fastFlags & 4)
+            st4(gout, v);
+        else if (P.fastFlags & 8)
+            __stcg(reinterpret_cast<float4 *>(gout), make_float4(v.v[0], v.v[1], v.v[2], v.v[3]));
+        else
+            st4cs(gout, v);
+    }
 }
 
 // UNR consecutive planes of a trip (template recursion keeps the queue offset R a compile-time constant)
@@ -492,12 +513,13 @@ template <int Q, bool XZ> struct VelUnroll<Q, XZ, UNR> {
     }
 };
 
-template <int Q, bool CPML>
+template <int Q, bool CPML, bool EDGE>
 __device__ __forceinline__ void velConsumer(const WsParams &P, const float *sm, Thr t, int G, int yc0, int yc1)
 {
     using S = StageV<Q>;
     using C = Cfg<Q>;
     constexpr int H = C::H, HX = C::HX, TXH = C::TXH;
+    constexpr bool XZC = CPML && EDGE; // tiles of this launch may touch an x / z CPML layer
     // ---- role set-up (run-time; CPML slots and profiles: CPML3D.cpp:31-153) ----
     VRole ro;
     const int oP = t.lz * TX + 4 * t.lx;
@@ -518,18 +540,20 @@ __device__ __forceinline__ void velConsumer(const WsParams &P, const float *sm, 
     const int sy = G == 0 ? PSI_SXY_Y : (G == 1 ? PSI_SYY_Y : PSI_SYZ_Y);
     const int sz = G == 0 ? PSI_SXZ_Z : (G == 1 ? PSI_SYZ_Z : PSI_SZZ_Z);
     CpT cpt;
-    cpSetup<CPML>(P, cpt, t.active, t.x0, t.z, /*halfX*/ G == 0, /*halfZ*/ G == 2);
+    cpSetup<XZC>(P, cpt, t.active, t.x0, t.z, /*halfX*/ G == 0, /*halfZ*/ G == 2);
     // warp-uniform: the unrolled march contains warp-level synchronisation
-    const bool warpXZ = CPML && __any_sync(0xffffffffu, cpt.anyX || cpt.kz >= 0);
-    const int W2 = 2 * P.W;
+    const bool warpXZ = XZC && P.fastDebug != 4 && __any_sync(0xffffffffu, cpt.kxv >= 0 || cpt.kz >= 0);
+    const int W2 = 2 * P.W, PX = P.psiPitchX;
     // strides of the memory-variable slabs per plane
-    const long long sxStride = (long long)P.nz * W2, szStride = (long long)W2 * P.nx;
+    const long long sxStride = (long long)P.nz * PX, szStride = (long long)W2 * P.nx;
     ro.out = P.fld[F_VX + G] + P.base + t.x0 + (long long)t.z * P.pitch;
-    ro.psx = CPML ? P.psi[sx] + (long long)t.z * W2 : nullptr;
-    ro.psz = CPML ? P.psi[sz] + (long long)cpt.kz * P.nx + t.x0 : nullptr;
+    ro.psx = XZC ? P.psi[sx] + (long long)t.z * PX : nullptr;
+    ro.psz = XZC ? P.psi[sz] + (long long)cpt.kz * P.nx + t.x0 : nullptr;
     ro.psy = CPML ? P.psi[sy] + (long long)t.z * P.nx + t.x0 : nullptr;
-    t.oPX = S::SIZE + (G * TZ + t.lz) * W2;
-    t.oPZ = S::SIZE + psxFloats(P.W) + G * C::N_P + oP;
+    // staged x rows: the box holds psiBoxX entries from entry xs of the row (the tile's side of the layer)
+    const int xs = (P.psiBoxX == PX || t.x0 - 4 * t.lx < P.W) ? 0 : PX - P.psiBoxX;
+    t.oPX = S::SIZE + (G * TZ + t.lz) * P.psiBoxX - xs;
+    t.oPZ = S::SIZE + psxFloats(P.psiBoxX) + G * C::N_P + oP;
 
     F4 q[C::QL];
 #pragma unroll
@@ -564,8 +588,8 @@ __device__ __forceinline__ void velConsumer(const WsParams &P, const float *sm, 
         const float *st = sm + stage * t.stride;
         q[Q - 1] = ld4(st + ro.oF);
         if (comp)
-            velPlane<Q, 0, true, CPML>(P, t, cpt, ro, q, st, ro.out + (long long)ly * P.plane, CPML ? ro.psx + (long long)ly * sxStride : nullptr,
-                                       CPML ? ro.psz + (long long)ly * szStride : nullptr, yd, CPML ? ro.psy + (long long)yd.ky * P.nz * P.nx : nullptr);
+            velPlane<Q, 0, true, XZC>(P, t, cpt, ro, q, st, ro.out + (long long)ly * P.plane, XZC ? ro.psx + (long long)ly * sxStride : nullptr,
+                                      XZC ? ro.psz + (long long)ly * szStride : nullptr, yd, CPML ? ro.psy + (long long)yd.ky * P.nz * P.nx : nullptr);
         consumerRelease(t, stage);
 #pragma unroll
         for (int k = 0; k < Q - 1; k++)
@@ -581,7 +605,7 @@ __device__ __forceinline__ void velConsumer(const WsParams &P, const float *sm, 
             const int stage0 = it % NSTV;
             const uint32_t parity = (it / NSTV) & 1;
             if (warpXZ)
-                VelUnroll<Q, CPML, 0>::run(P, t, cpt, ro, q, sm, stage0, parity, gout, ro.psx + (long long)ly0 * sxStride, ro.psz + (long long)ly0 * szStride, sxStride,
+                VelUnroll<Q, XZC, 0>::run(P, t, cpt, ro, q, sm, stage0, parity, gout, ro.psx + (long long)ly0 * sxStride, ro.psz + (long long)ly0 * szStride, sxStride,
                                            szStride);
             else
                 VelUnroll<Q, false, 0>::run(P, t, cpt, ro, q, sm, stage0, parity, gout, nullptr, nullptr, 0, 0);
@@ -596,22 +620,29 @@ __device__ __forceinline__ void velConsumer(const WsParams &P, const float *sm, 
     }
 }
 
-template <int Q, bool CPML> __global__ void __launch_bounds__(NGROUPS *Cfg<Q>::NTG + 32, 1) kFastVel(const __grid_constant__ WsParams P)
+template <int Q, bool CPML, bool EDGE> __global__ void __launch_bounds__(NGROUPS *Cfg<Q>::NTG + 32, 1) kFastVel(const __grid_constant__ WsParams P)
 {
     using C = Cfg<Q>;
     using S = StageV<Q>;
     constexpr int H = C::H, HX = C::HX;
+    constexpr bool XZC = CPML && EDGE;
     extern __shared__ __align__(1024) unsigned char smraw[];
     __shared__ __align__(8) Bars bars;
+    __shared__ __align__(16) float cxTab[XZC ? 4 * PXMAX : 4];
     float *sm = reinterpret_cast<float *>(smraw);
     const CUtensorMap *maps = reinterpret_cast<const CUtensorMap *>(P.fastMaps);
+    if (XZC)
+        for (int k = threadIdx.x; k < 4 * P.psiPitchX; k += blockDim.x)
+            cxTab[k] = __ldg(P.cxTab + k);
 
     const int tid = threadIdx.x;
-    const int tx0 = blockIdx.x * TX, tz0 = blockIdx.y * TZ;
+    const int tile = P.fastTiles[P.fastTileBase + blockIdx.x]; // (z tile << 16) | x tile, see wsFastPrepare
+    const int tx0 = (tile & 0xffff) * TX, tz0 = (tile >> 16) * TZ;
     const int yc0 = P.ylo + blockIdx.z * P.fastChunk;
     const int yc1 = min(P.yhi, yc0 + P.fastChunk);
     if (yc0 >= yc1)
         return;
+    traceStart(P, 0);
     const uint32_t barFull = smemU32(&bars.full[0]), barEmpty = smemU32(&bars.empty[0]);
     if (tid == 0) {
 #pragma unroll
@@ -635,9 +666,12 @@ template <int Q, bool CPML> __global__ void __launch_bounds__(NGROUPS *Cfg<Q>::N
         t.active = (t.x0 < P.nx) && (t.z < P.nz);
         t.barFull = barFull;
         t.barEmpty = barEmpty;
-        t.stride = S::SIZE + (CPML ? psiStageFloats(P.W) : 0);
+        t.barXFull = t.barXFree = 0;
+        t.stride = S::SIZE + (XZC ? psiStageFloats(P.psiBoxX) : 0);
+        t.cxTab = cxTab;
         t.oPX = t.oPZ = t.oPZ2 = 0;
-        velConsumer<Q, CPML>(P, sm, t, grp, yc0, yc1);
+        velConsumer<Q, CPML, EDGE>(P, sm, t, grp, yc0, yc1);
+        traceEnd(P, 0, t.lane);
     } else if (tid == NGROUPS * C::NTG) {
         // ---- producer: one elected thread streams the planes ----
         const int HZP = (P.nzp > 1) ? WS_HALO : 0;
@@ -648,11 +682,12 @@ template <int Q, bool CPML> __global__ void __launch_bounds__(NGROUPS *Cfg<Q>::N
         uint32_t parity = 1; // first pass over the ring: the stages are free
         const bool hints = (P.fastFlags & 1) != 0;
         const uint64_t polOnce = policyEvictFirst(), polKeep = policyEvictLast();
-        const int stride = S::SIZE + (CPML ? psiStageFloats(P.W) : 0);
+        const int stride = S::SIZE + (XZC ? psiStageFloats(P.psiBoxX) : 0);
         // memory variables of the x / z CPML layers this tile touches (slab rows, ws_api.cu)
-        const bool tileX = CPML && (tx0 < P.W || tx0 + TX > P.nx - P.W), tileZ = CPML && (tz0 < P.W || tz0 + TZ > P.nz - P.W);
+        const bool tileX = XZC && P.fastDebug != 4 && (tx0 < P.W || tx0 + TX > P.nx - P.W), tileZ = XZC && P.fastDebug != 4 && (tz0 < P.W || tz0 + TZ > P.nz - P.W);
         const int kz0 = tz0 < P.W ? tz0 : tz0 - (P.nz - 2 * P.W);
-        const uint32_t bytesPX = 3u * TZ * 2u * (uint32_t)P.W * 4u, bytesPZ = 3u * C::N_P * 4u;
+        const uint32_t bytesPX = 3u * TZ * (uint32_t)P.psiBoxX * 4u, bytesPZ = 3u * C::N_P * 4u;
+        const int xs = (P.psiBoxX == P.psiPitchX || tx0 < P.W) ? 0 : P.psiPitchX - P.psiBoxX;
         const uint32_t bytesFull = S::BYTES_FULL + (tileX ? bytesPX : 0u) + (tileZ ? bytesPZ : 0u);
         for (int it = 0; it < nIter; it++) {
             const int cy = WS_HALO + yc0 - (Q - 1) + it;
@@ -663,9 +698,9 @@ template <int Q, bool CPML> __global__ void __launch_bounds__(NGROUPS *Cfg<Q>::N
             const uint32_t bar = barFull + 8u * stage;
             mbarExpectTx(bar, comp ? bytesFull : S::BYTES_FEED);
             if (comp && tileX)
-                tmaLoad4D(st + 4u * S::SIZE, &maps[TM_PX], bar, 0, tz0, cy - WS_HALO, 0);
+                tmaLoad4D(st + 4u * S::SIZE, &maps[TM_PX], bar, xs, tz0, cy - WS_HALO, 0);
             if (comp && tileZ)
-                tmaLoad4D(st + 4u * (S::SIZE + psxFloats(P.W)), &maps[TM_PZ], bar, tx0, kz0, cy - WS_HALO, 0);
+                tmaLoad4D(st + 4u * (S::SIZE + psxFloats(P.psiBoxX)), &maps[TM_PZ], bar, tx0, kz0, cy - WS_HALO, 0);
             if (hints) {
                 // Sxy and Syz come back H-1 planes later as stencil tiles; Syy is used by this feed only
                 tmaLoad4DHint(st + 4u * S::FEED, &maps[TM_F1_P], bar, cx, cz, cy + H - 1, AF_SXY, polKeep);
@@ -697,215 +732,195 @@ template <int Q, bool CPML> __global__ void __launch_bounds__(NGROUPS *Cfg<Q>::N
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// stress half-step (ForwardSolver3Delastic.cpp:288-404) incl. free-surface correction
-//   group 0: vxx = Dxb vx, vyy = Dyb vy, vzz = Dzb vz -> sxx, syy, szz (+ free surface)
-//   group 1: sxy += muxy (Dyf vx + Dxf vy)    group 2: sxz += muxz (Dzf vx + Dxf vz), syz += muyz (Dzf vy + Dyf vz)
+// stress half-step (ForwardSolver3Delastic.cpp:288-404) incl. free-surface correction.
+// Role r = velocity component: role 0 differentiates vx (Dxb vx = vxx, Dyf vx, Dzf vx), role 1 vy (Dxf vy, Dyb vy = vyy,
+// Dzf vy), role 2 vz (Dxf vz, Dyf vz, Dzb vz = vzz) — one x, one y and one z derivative each, the shape of the velocity
+// roles, so the three roles again share ONE instruction stream (three role-specific streams do not fit the instruction
+// cache: measured) and carry equal work.  Every stress needs derivatives of two or three components, so the roles swap
+// them through shared memory with split-phase mbarriers (publish, fetch the own-point operands, then wait):
+//   every role publishes its normal strain rate and one shear term and updates its normal stress and one shear stress
+//   role 0: sxx, sxy += muxy (Dyf vx + Dxf vy[role 1])    role 1: syy, syz += muyz (Dzf vy + Dyf vz[role 2])
+//   role 2: szz, sxz += muxz (Dxf vz + Dzf vx[role 0])
 // All y operators of this half-step are the plain ones (ForwardSolver3Delastic.cpp:289), so only the y-CPML layers and
 // the free-surface plane need the generic step.
 // ---------------------------------------------------------------------------------------------------------------------
-struct StrPsi { // memory-variable pointers of one plane (x, z, second z term) and the y term
-    float *x, *z, *z2, *y;
+struct SRole {
+    int r;
+    int oP;             // own point inside a plain tile
+    int oX, oZ, oF;     // stage offsets: x stencil row, z stencil start, feed tile
+    int oSN, oSS, oMS;  // own normal stress, own shear stress, modulus of the shear stress
+    int oED, oES, oIS;  // exchange buffer: published normal strain rate / shear term, fetched shear term
+    float cx[WS_MAXQ + 1];
+    float *outN, *outS; // output fields
+    float *psx, *psy, *psz;
+    bool halfY;
 };
 
-template <int Q, int G, int R, bool GENERIC, bool XZ>
-__device__ __forceinline__ void strPlane(const WsParams &P, const Thr &t, const CpT &cpt, F4 (&q)[Cfg<Q>::QL], const float *st, int oX, int oZ, int oP, long long o,
-                                         const StrPsi &ps, const YDyn<Q> &yd, int gy)
+template <int Q, int R, bool GENERIC, bool XZ>
+__device__ __forceinline__ void strPlane(const WsParams &P, const Thr &t, const CpT &cpt, const SRole &ro, F4 (&q)[Cfg<Q>::QL], const float *st, float *xch, int n,
+                                         long long o, float *psx, float *psz, const YDyn<Q> &yd, float *psy, int gy)
 {
     using S = StageS<Q>;
     using C = Cfg<Q>;
-    constexpr int TXH = C::TXH, NXZ = C::N_XZ, NP = C::N_P;
-    const float *tvx = st + S::TV, *tvy = st + S::TV + NXZ, *tvz = st + S::TV + 2 * NXZ;
+    constexpr int NP = C::N_P;
     const bool ycp = GENERIC && yd.ky >= 0 && t.active;
-    float px[4];
-    F4 pz, pz2, py;
-    if (XZ) { // staged by the producer together with the operands of this plane
-        if (cpt.anyX)
-            cpLoadX(cpt, st + t.oPX, px);
-        if (cpt.kz >= 0 && G != 1) {
-            pz = ld4(st + t.oPZ);
-            if (G == 2)
-                pz2 = ld4(st + t.oPZ2);
-        }
-    }
+    F4 pz, py;
+    if (XZ && cpt.kz >= 0) // staged by the producer together with the operands of this plane
+        pz = ld4(st + t.oPZ);
     if (ycp)
-        py = ld4(ps.y);
-    if (G == 0) {
-        // normal strain rates
-        F4 vxx = dX<Q, false>(tvx + oX, P.cw);
-        F4 vyy = dY<Q, R>(q, P.cw);
-        F4 vzz = dZ<Q, false, TXH>(tvz + oZ, P.cw);
-        if (XZ && cpt.anyX)
-            cpApplyX(cpt, ps.x, px, vxx);
-        if (ycp)
-            cpApply4(ps.y, py, yd.ya, yd.yb, vyy);
-        if (XZ && cpt.kz >= 0)
-            cpApply4(ps.z, pz, cpt.za, cpt.zb, vzz);
-        F4 sxx = ld4(st + S::OWNS + S::O_SXX * NP + oP), syy = ld4(st + S::OWNS + S::O_SYY * NP + oP), szz = ld4(st + S::OWNS + S::O_SZZ * NP + oP);
-        const F4 pi = ld4(st + S::OWNM + 0 * NP + oP), mu = ld4(st + S::OWNM + 1 * NP + oP);
+        py = ld4(psy);
+    F4 a = dX9<Q>(st + ro.oX, ro.cx);
+    if (XZ && cpt.kxv >= 0)
+        cpApplyXv(cpt, st + t.oPX, psx, t.cxTab, P.psiPitchX, a);
+    F4 b = dY<Q, R>(q, P.cw);
+    if (ycp)
+        cpApply4(psy, py, yd.ya, yd.yb, b);
+    F4 c = dZ<Q, false, C::TXH>(st + ro.oZ, P.cw);
+    if (XZ && cpt.kz >= 0)
+        cpApply4(psz, pz, cpt.za, cpt.zb, c);
+    // publish the normal strain rate and the shear term another role needs; keep the shear term of the own shear stress
+    F4 dg, ex, kp;
 #pragma unroll
-        for (int p = 0; p < 4; p++) {
-            float u = A::add(vxx.v[p], vyy.v[p]);
-            u = A::add(u, vzz.v[p]);
-            u = A::mul(u, pi.v[p]);
-            sxx.v[p] = A::add(sxx.v[p], u);
-            syy.v[p] = A::add(syy.v[p], u);
-            szz.v[p] = A::add(szz.v[p], u);
-            u = A::mul(A::add(vyy.v[p], vzz.v[p]), mu.v[p]);
-            sxx.v[p] = A::msub(2.0f, u, sxx.v[p]);
-            u = A::mul(A::add(vxx.v[p], vzz.v[p]), mu.v[p]);
-            syy.v[p] = A::msub(2.0f, u, syy.v[p]);
-            u = A::mul(A::add(vxx.v[p], vyy.v[p]), mu.v[p]);
-            szz.v[p] = A::msub(2.0f, u, szz.v[p]);
-        }
-        if (GENERIC && P.free_surface == 1 && gy == 0 && t.active) {
-            // FreeSurface3Delastic.cpp:15-47, FreeSurface.cpp:13-20
+    for (int p = 0; p < 4; p++) {
+        dg.v[p] = ro.r == 0 ? a.v[p] : (ro.r == 1 ? b.v[p] : c.v[p]);
+        ex.v[p] = ro.r == 0 ? c.v[p] : (ro.r == 1 ? a.v[p] : b.v[p]);
+        kp.v[p] = ro.r == 0 ? b.v[p] : (ro.r == 1 ? c.v[p] : a.v[p]);
+    }
+    if (n > 0)
+        mbarWait(t.barXFree, (uint32_t)(n - 1) & 1u); // every warp has fetched the terms of the previous plane
+    st4(xch + ro.oED, dg);
+    st4(xch + ro.oES, ex);
+    __syncwarp();
+    if (t.lane == 0)
+        mbarArrive(t.barXFull);
+    F4 sN = ld4(st + ro.oSN), sS = ld4(st + ro.oSS);
+    const F4 pi = ld4(st + S::OWNM + ro.oP), mu = ld4(st + S::OWNM + NP + ro.oP), ms = ld4(st + ro.oMS);
+    mbarWait(t.barXFull, (uint32_t)n & 1u);
+    const F4 d0 = ld4(xch + ro.oP), d1 = ld4(xch + NP + ro.oP), d2 = ld4(xch + 2 * NP + ro.oP), im = ld4(xch + ro.oIS);
+    __syncwarp();
+    if (t.lane == 0)
+        mbarArrive(t.barXFree);
+#pragma unroll
+    for (int p = 0; p < 4; p++) {
+        // ForwardSolver3Delastic.cpp:297-314: S_ii += pi (vxx+vyy+vzz); S_ii -= 2 mu (sum of the other two)
+        float u = A::add(d0.v[p], d1.v[p]);
+        u = A::add(u, d2.v[p]);
+        u = A::mul(u, pi.v[p]);
+        sN.v[p] = A::add(sN.v[p], u);
+        const float lo = ro.r == 0 ? d1.v[p] : d0.v[p], hi = ro.r == 2 ? d1.v[p] : d2.v[p];
+        u = A::mul(A::add(lo, hi), mu.v[p]);
+        sN.v[p] = A::msub(2.0f, u, sN.v[p]);
+        // :331-382: S_ij += mu_ij (D_j v_i + D_i v_j)
+        const float tt = A::add(kp.v[p], im.v[p]);
+        sS.v[p] = A::add(sS.v[p], A::mul(tt, ms.v[p]));
+    }
+    if (GENERIC && P.free_surface == 1 && gy == 0 && t.active) {
+        // FreeSurface3Delastic.cpp:15-47, FreeSurface.cpp:13-20
+        if (ro.r == 1) {
+#pragma unroll
+            for (int p = 0; p < 4; p++)
+                sN.v[p] = A::mul(sN.v[p], 0.0f);
+        } else {
             const F4 sH = ldg4(P.sH + (long long)t.z * P.nx + t.x0), sV = ldg4(P.sV + (long long)t.z * P.nx + t.x0);
 #pragma unroll
             for (int p = 0; p < 4; p++) {
-                const float hor = A::add(vxx.v[p], vzz.v[p]);
+                const float hor = A::add(d0.v[p], d2.v[p]);
                 float tt = A::mul(sH.v[p], hor);
-                sxx.v[p] = A::add(sxx.v[p], tt);
-                szz.v[p] = A::add(szz.v[p], tt);
-                tt = A::mul(sV.v[p], vyy.v[p]);
-                sxx.v[p] = A::sub(sxx.v[p], tt);
-                szz.v[p] = A::sub(szz.v[p], tt);
-                syy.v[p] = A::mul(syy.v[p], 0.0f);
+                sN.v[p] = A::add(sN.v[p], tt);
+                tt = A::mul(sV.v[p], d1.v[p]);
+                sN.v[p] = A::sub(sN.v[p], tt);
             }
         }
-        if (t.active) {
-            st4cs(P.fld[F_SXX] + o, sxx);
-            st4cs(P.fld[F_SYY] + o, syy);
-            st4cs(P.fld[F_SZZ] + o, szz);
+    }
+    if (t.active && P.fastDebug != 2) {
+        if (P.fastFlags & 4) {
+            st4(ro.outN + o, sN);
+            st4(ro.outS + o, sS);
+        } else if (P.fastFlags & 8) {
+            __stcg(reinterpret_cast<float4 *>(ro.outN + o), make_float4(sN.v[0], sN.v[1], sN.v[2], sN.v[3]));
+            __stcg(reinterpret_cast<float4 *>(ro.outS + o), make_float4(sS.v[0], sS.v[1], sS.v[2], sS.v[3]));
+        } else {
+            st4cs(ro.outN + o, sN);
+            st4cs(ro.outS + o, sS);
         }
-    } else if (G == 1) {
-        F4 u = dY<Q, R>(q, P.cw);
-        if (ycp)
-            cpApply4(ps.y, py, yd.ya, yd.yb, u);
-        F4 w = dX<Q, true>(tvy + oX, P.cw);
-        if (XZ && cpt.anyX)
-            cpApplyX(cpt, ps.x, px, w);
-        F4 s = ld4(st + S::OWNS + S::O_SXY * NP + oP);
-        const F4 m = ld4(st + S::OWNM + 2 * NP + oP);
-#pragma unroll
-        for (int p = 0; p < 4; p++) {
-            const float tt = A::add(u.v[p], w.v[p]);
-            s.v[p] = A::add(s.v[p], A::mul(tt, m.v[p]));
-        }
-        if (t.active)
-            st4cs(P.fld[F_SXY] + o, s);
-    } else {
-        F4 u = dZ<Q, true, TXH>(tvx + oZ, P.cw);
-        if (XZ && cpt.kz >= 0)
-            cpApply4(ps.z, pz, cpt.za, cpt.zb, u);
-        F4 w = dX<Q, true>(tvz + oX, P.cw);
-        if (XZ && cpt.anyX)
-            cpApplyX(cpt, ps.x, px, w);
-        F4 s = ld4(st + S::OWNS + S::O_SXZ * NP + oP);
-        const F4 m = ld4(st + S::OWNM + 3 * NP + oP);
-#pragma unroll
-        for (int p = 0; p < 4; p++) {
-            const float tt = A::add(u.v[p], w.v[p]);
-            s.v[p] = A::add(s.v[p], A::mul(tt, m.v[p]));
-        }
-        if (t.active)
-            st4cs(P.fld[F_SXZ] + o, s);
-        u = dZ<Q, true, TXH>(tvy + oZ, P.cw);
-        if (XZ && cpt.kz >= 0)
-            cpApply4(ps.z2, pz2, cpt.za, cpt.zb, u);
-        w = dY<Q, R>(q, P.cw);
-        if (ycp)
-            cpApply4(ps.y, py, yd.ya, yd.yb, w);
-        s = ld4(st + S::OWNS + S::O_SYZ * NP + oP);
-        const F4 m2 = ld4(st + S::OWNM + 4 * NP + oP);
-#pragma unroll
-        for (int p = 0; p < 4; p++) {
-            const float tt = A::add(u.v[p], w.v[p]);
-            s.v[p] = A::add(s.v[p], A::mul(tt, m2.v[p]));
-        }
-        if (t.active)
-            st4cs(P.fld[F_SYZ] + o, s);
     }
 }
 
-template <int Q, int G, bool XZ, int R> struct StrUnroll {
-    static __device__ __forceinline__ void run(const WsParams &P, const Thr &t, const CpT &cpt, F4 (&q)[Cfg<Q>::QL], const float *sm, int stage0, uint32_t parity,
-                                               int oX, int oZ, int oP, int oF, long long o, StrPsi ps, long long sxStride, long long szStride)
+template <int Q, bool XZ, int R> struct StrUnroll {
+    static __device__ __forceinline__ void run(const WsParams &P, const Thr &t, const CpT &cpt, const SRole &ro, F4 (&q)[Cfg<Q>::QL], const float *sm, float *xch, int n,
+                                               int stage0, uint32_t parity, long long o, float *psx, float *psz, long long sxStride, long long szStride)
     {
-        using S = StageS<Q>;
         const int stage = stage0 + R;
         mbarWait(t.barFull + 8u * stage, parity);
         const float *st = sm + stage * t.stride;
-        q[Q - 1 + R] = ld4(st + oF);
+        q[Q - 1 + R] = ld4(st + ro.oF);
         YDyn<Q> yd;
         yd.ky = -1;
-        if (P.fastDebug != 1)
-            strPlane<Q, G, R, false, XZ>(P, t, cpt, q, st, oX, oZ, oP, o, ps, yd, 1);
+        strPlane<Q, R, false, XZ>(P, t, cpt, ro, q, st, xch, n, o, psx, psz, yd, nullptr, 1);
         consumerRelease(t, stage);
-        if (XZ) {
-            ps.x += sxStride;
-            if (G != 1)
-                ps.z += szStride;
-            if (G == 2)
-                ps.z2 += szStride;
-        }
-        StrUnroll<Q, G, XZ, R + 1>::run(P, t, cpt, q, sm, stage0, parity, oX, oZ, oP, oF, o + P.plane, ps, sxStride, szStride);
+        StrUnroll<Q, XZ, R + 1>::run(P, t, cpt, ro, q, sm, xch, n + 1, stage0, parity, o + P.plane, XZ ? psx + sxStride : psx, XZ ? psz + szStride : psz, sxStride,
+                                     szStride);
     }
 };
-template <int Q, int G, bool XZ> struct StrUnroll<Q, G, XZ, UNR> {
-    static __device__ __forceinline__ void run(const WsParams &, const Thr &, const CpT &, F4 (&)[Cfg<Q>::QL], const float *, int, uint32_t, int, int, int, int, long long,
-                                               StrPsi, long long, long long)
+template <int Q, bool XZ> struct StrUnroll<Q, XZ, UNR> {
+    static __device__ __forceinline__ void run(const WsParams &, const Thr &, const CpT &, const SRole &, F4 (&)[Cfg<Q>::QL], const float *, float *, int, int, uint32_t,
+                                               long long, float *, float *, long long, long long)
     {
     }
 };
 
-template <int Q, bool CPML, int G>
-__device__ __forceinline__ void strConsumer(const WsParams &P, const float *sm, Thr t, int yc0, int yc1)
+template <int Q, bool CPML, bool EDGE>
+__device__ __forceinline__ void strConsumer(const WsParams &P, const float *sm, float *xch, Thr t, int G, int yc0, int yc1)
 {
     using S = StageS<Q>;
     using C = Cfg<Q>;
-    constexpr int H = C::H, HX = C::HX, TXH = C::TXH;
-    constexpr int FEEDSLOT = (G == 0) ? 1 : (G == 1 ? 0 : 2); // vy | vx | vz
-    // memory-variable slots (CPML3D.cpp:31-153): group 0 full-grid profiles, shear groups half-grid profiles
-    constexpr int sx = (G == 0) ? PSI_VXX : (G == 1 ? PSI_VYX : PSI_VZX);
-    constexpr int sy = (G == 0) ? PSI_VYY : (G == 1 ? PSI_VXY : PSI_VZY);
-    constexpr int sz = (G == 0) ? PSI_VZZ : PSI_VXZ; // unused in group 1
-    constexpr int sz2 = PSI_VYZ;                      // group 2 only
-    constexpr bool half = (G != 0);
+    constexpr int H = C::H, HX = C::HX, TXH = C::TXH, NP = C::N_P;
+    constexpr bool XZC = CPML && EDGE;
+    SRole ro;
+    ro.r = G;
+    const int oP = t.lz * TX + 4 * t.lx;
+    ro.oP = oP;
+    const int tv = S::TV + G * C::N_XZ; // own velocity component with x and z halo
+    ro.oX = tv + (t.lz + H) * TXH + 4 * t.lx;                    // x stencil: own row, column of x0 - HX
+    ro.oZ = tv + (t.lz + (G == 2 ? 0 : 1)) * TXH + 4 * t.lx + HX; // z stencil: row z - H (backward, role 2) or z - H + 1 (forward)
+    ro.oF = S::FEED + G * NP + oP;
+#pragma unroll
+    for (int j = 0; j <= Q; j++) // offsets -H..H: backward (role 0) -H..H-1, forward -H+1..H
+        ro.cx[j] = G == 0 ? (j < Q ? P.cw[j] : 0.0f) : (j >= 1 ? P.cw[j - 1] : 0.0f);
+    // own-point tiles: stresses in arena order sxx sxy syy syz szz sxz, moduli in arena order pi mu muxy muxz muyz
+    ro.oSN = S::OWNS + (2 * G) * NP + oP;
+    ro.oSS = S::OWNS + (2 * G + 1) * NP + oP;
+    ro.oMS = S::OWNM + (G == 0 ? 2 : (G == 1 ? 4 : 3)) * NP + oP;
+    ro.oED = G * NP + oP;
+    ro.oES = (3 + G) * NP + oP;
+    ro.oIS = (3 + (G + 1) % 3) * NP + oP;
+    ro.outN = P.fld[G == 0 ? F_SXX : (G == 1 ? F_SYY : F_SZZ)];
+    ro.outS = P.fld[G == 0 ? F_SXY : (G == 1 ? F_SYZ : F_SXZ)];
+    ro.halfY = G != 1;
+    // memory-variable slots and profiles (CPML3D.cpp:31-153): normal strain rates full-grid, shear terms half-grid profiles
+    const int sx = G == 0 ? PSI_VXX : (G == 1 ? PSI_VYX : PSI_VZX);
+    const int sy = G == 0 ? PSI_VXY : (G == 1 ? PSI_VYY : PSI_VZY);
+    const int sz = G == 0 ? PSI_VXZ : (G == 1 ? PSI_VYZ : PSI_VZZ);
     CpT cpt;
-    cpSetup<CPML>(P, cpt, t.active, t.x0, t.z, half, half);
-    const bool warpXZ = CPML && __any_sync(0xffffffffu, cpt.anyX || cpt.kz >= 0);
-    const int oX = (t.lz + H) * TXH + 4 * t.lx; // x stencil: own row, column of x0 - HX   (inside an XZ tile)
-    const int oZ = t.lz * TXH + 4 * t.lx + HX;  // z stencil: row z - H, own column
-    const int oP = t.lz * TX + 4 * t.lx, oF = S::FEED + FEEDSLOT * C::N_P + oP;
+    cpSetup<XZC>(P, cpt, t.active, t.x0, t.z, /*halfX*/ G != 0, /*halfZ*/ G != 2);
+    const bool warpXZ = XZC && P.fastDebug != 4 && __any_sync(0xffffffffu, cpt.kxv >= 0 || cpt.kz >= 0);
+    const int W2 = 2 * P.W, PX = P.psiPitchX;
+    const long long sxStride = (long long)P.nz * PX, szStride = (long long)W2 * P.nx;
     const long long rowOff = P.base + t.x0 + (long long)t.z * P.pitch;
-    const int W2 = 2 * P.W;
-    const long long sxStride = (long long)P.nz * W2, szStride = (long long)W2 * P.nx;
-    // staged memory variables: x arena order {vxx, vyx, vzx} = group order; z arena order {vzz | vxz, vyz}
-    t.oPX = S::SIZE + (G * TZ + t.lz) * W2;
-    t.oPZ = S::SIZE + psxFloats(P.W) + (G == 0 ? 0 : 1) * C::N_P + oP;
-    t.oPZ2 = S::SIZE + psxFloats(P.W) + 2 * C::N_P + oP;
+    ro.psx = XZC ? P.psi[sx] + (long long)t.z * PX : nullptr;
+    ro.psz = XZC ? P.psi[sz] + (long long)cpt.kz * P.nx + t.x0 : nullptr;
+    ro.psy = CPML ? P.psi[sy] + (long long)t.z * P.nx + t.x0 : nullptr;
+    const int xs = (P.psiBoxX == PX || t.x0 - 4 * t.lx < P.W) ? 0 : PX - P.psiBoxX;
+    t.oPX = S::SIZE + (G * TZ + t.lz) * P.psiBoxX - xs;
+    t.oPZ = S::SIZE + psxFloats(P.psiBoxX) + G * NP + oP;
 
     F4 q[C::QL];
 #pragma unroll
     for (int k = 0; k < C::QL; k++)
         q[k] = zero4();
 
-    auto psiAt = [&](int ly, int ky) {
-        StrPsi ps;
-        ps.x = ps.z = ps.z2 = ps.y = nullptr;
-        if (CPML) {
-            ps.x = P.psi[sx] + (long long)ly * sxStride + (long long)t.z * W2;
-            const long long zo = (long long)ly * szStride + (long long)cpt.kz * P.nx + t.x0;
-            if (G != 1)
-                ps.z = P.psi[sz] + zo;
-            if (G == 2)
-                ps.z2 = P.psi[sz2] + zo;
-            ps.y = P.psi[sy] + ((long long)ky * P.nz + t.z) * P.nx + t.x0;
-        }
-        return ps;
-    };
-
     const int nIter = (Q - 1) + (yc1 - yc0);
+    int n = 0; // planes computed so far (phase of the exchange barriers)
     auto generic = [&](int it) {
         const int ly = yc0 - (Q - 1) + it, gy = P.gy0 + ly;
         const bool comp = it >= Q - 1;
@@ -915,16 +930,17 @@ __device__ __forceinline__ void strConsumer(const WsParams &P, const float *sm, 
         if (comp && CPML) {
             yd.ky = yCpmlIndex(P, gy);
             if (yd.ky >= 0) {
-                yd.ya = __ldg((half ? P.cayh : P.cay) + yd.ky);
-                yd.yb = __ldg((half ? P.cbyh : P.cby) + yd.ky);
+                yd.ya = __ldg((ro.halfY ? P.cayh : P.cay) + yd.ky);
+                yd.yb = __ldg((ro.halfY ? P.cbyh : P.cby) + yd.ky);
             }
         }
         mbarWait(t.barFull + 8u * stage, (it / NSTS) & 1);
         const float *st = sm + stage * t.stride;
-        q[Q - 1] = ld4(st + oF);
+        q[Q - 1] = ld4(st + ro.oF);
         if (comp) {
-            const StrPsi ps = psiAt(ly, yd.ky);
-            strPlane<Q, G, 0, true, CPML>(P, t, cpt, q, st, oX, oZ, oP, rowOff + (long long)ly * P.plane, ps, yd, gy);
+            strPlane<Q, 0, true, XZC>(P, t, cpt, ro, q, st, xch, n, rowOff + (long long)ly * P.plane, XZC ? ro.psx + (long long)ly * sxStride : nullptr,
+                                      XZC ? ro.psz + (long long)ly * szStride : nullptr, yd, CPML ? ro.psy + (long long)yd.ky * P.nz * P.nx : nullptr, gy);
+            n++;
         }
         consumerRelease(t, stage);
 #pragma unroll
@@ -941,12 +957,11 @@ __device__ __forceinline__ void strConsumer(const WsParams &P, const float *sm, 
             const int stage0 = it % NSTS;
             const uint32_t parity = (it / NSTS) & 1;
             if (warpXZ)
-                StrUnroll<Q, G, CPML, 0>::run(P, t, cpt, q, sm, stage0, parity, oX, oZ, oP, oF, o, psiAt(ly0, 0), sxStride, szStride);
-            else {
-                StrPsi ps;
-                ps.x = ps.z = ps.z2 = ps.y = nullptr;
-                StrUnroll<Q, G, false, 0>::run(P, t, cpt, q, sm, stage0, parity, oX, oZ, oP, oF, o, ps, 0, 0);
-            }
+                StrUnroll<Q, XZC, 0>::run(P, t, cpt, ro, q, sm, xch, n, stage0, parity, o, ro.psx + (long long)ly0 * sxStride, ro.psz + (long long)ly0 * szStride, sxStride,
+                                          szStride);
+            else
+                StrUnroll<Q, false, 0>::run(P, t, cpt, ro, q, sm, xch, n, stage0, parity, o, nullptr, nullptr, 0, 0);
+            n += UNR;
 #pragma unroll
             for (int k = 0; k < Q - 1; k++)
                 q[k] = q[k + UNR];
@@ -958,22 +973,29 @@ __device__ __forceinline__ void strConsumer(const WsParams &P, const float *sm, 
     }
 }
 
-template <int Q, bool CPML> __global__ void __launch_bounds__(Cfg<Q>::NTHREADS, 1) kFastStress(const __grid_constant__ WsParams P)
+template <int Q, bool CPML, bool EDGE> __global__ void __launch_bounds__(NGROUPS *Cfg<Q>::NTG + 32, 1) kFastStress(const __grid_constant__ WsParams P)
 {
     using C = Cfg<Q>;
     using S = StageS<Q>;
     constexpr int H = C::H, HX = C::HX;
+    constexpr bool XZC = CPML && EDGE;
     extern __shared__ __align__(1024) unsigned char smraw[];
     __shared__ __align__(8) Bars bars;
+    __shared__ __align__(16) float cxTab[XZC ? 4 * PXMAX : 4];
     float *sm = reinterpret_cast<float *>(smraw);
     const CUtensorMap *maps = reinterpret_cast<const CUtensorMap *>(P.fastMaps);
+    if (XZC)
+        for (int k = threadIdx.x; k < 4 * P.psiPitchX; k += blockDim.x)
+            cxTab[k] = __ldg(P.cxTab + k);
 
     const int tid = threadIdx.x;
-    const int tx0 = blockIdx.x * TX, tz0 = blockIdx.y * TZ;
+    const int tile = P.fastTiles[P.fastTileBase + blockIdx.x]; // (z tile << 16) | x tile, see wsFastPrepare
+    const int tx0 = (tile & 0xffff) * TX, tz0 = (tile >> 16) * TZ;
     const int yc0 = P.ylo + blockIdx.z * P.fastChunk;
     const int yc1 = min(P.yhi, yc0 + P.fastChunk);
     if (yc0 >= yc1)
         return;
+    traceStart(P, 1);
     const uint32_t barFull = smemU32(&bars.full[0]), barEmpty = smemU32(&bars.empty[0]);
     if (tid == 0) {
 #pragma unroll
@@ -981,15 +1003,17 @@ template <int Q, bool CPML> __global__ void __launch_bounds__(Cfg<Q>::NTHREADS, 
             mbarInit(barFull + 8u * s, 1);
             mbarInit(barEmpty + 8u * s, NGROUPS * C::WPG);
         }
+        mbarInit(smemU32(&bars.xfull), NGROUPS * C::WPG);
+        mbarInit(smemU32(&bars.xfree), NGROUPS * C::WPG);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    const int warp = tid >> 5;
-    const int grp = warp & 3;
+    const int stride = S::SIZE + (XZC ? psiStageFloats(P.psiBoxX) : 0);
+    const int grp = tid / C::NTG;
     if (grp < NGROUPS) {
         Thr t;
-        const int tg = (warp >> 2) * 32 + (tid & 31);
+        const int tg = tid - grp * C::NTG;
         t.lx = tg % C::LXN;
         t.lz = tg / C::LXN;
         t.x0 = tx0 + 4 * t.lx;
@@ -998,15 +1022,14 @@ template <int Q, bool CPML> __global__ void __launch_bounds__(Cfg<Q>::NTHREADS, 
         t.active = (t.x0 < P.nx) && (t.z < P.nz);
         t.barFull = barFull;
         t.barEmpty = barEmpty;
-        t.stride = S::SIZE + (CPML ? psiStageFloats(P.W) : 0);
+        t.barXFull = smemU32(&bars.xfull);
+        t.barXFree = smemU32(&bars.xfree);
+        t.stride = stride;
+        t.cxTab = cxTab;
         t.oPX = t.oPZ = t.oPZ2 = 0;
-        if (grp == 0)
-            strConsumer<Q, CPML, 0>(P, sm, t, yc0, yc1);
-        else if (grp == 1)
-            strConsumer<Q, CPML, 1>(P, sm, t, yc0, yc1);
-        else
-            strConsumer<Q, CPML, 2>(P, sm, t, yc0, yc1);
-    } else if (tid == 3 * 32) {
+        strConsumer<Q, CPML, EDGE>(P, sm, sm + NSTS * stride, t, grp, yc0, yc1);
+        traceEnd(P, 1, t.lane);
+    } else if (tid == NGROUPS * C::NTG) {
         const int HZP = (P.nzp > 1) ? WS_HALO : 0;
         const int cx = WS_PADX + tx0, cz = HZP + tz0;
         const int nIter = (Q - 1) + (yc1 - yc0);
@@ -1015,10 +1038,10 @@ template <int Q, bool CPML> __global__ void __launch_bounds__(Cfg<Q>::NTHREADS, 
         uint32_t parity = 1;
         const bool hints = (P.fastFlags & 1) != 0;
         const uint64_t polOnce = policyEvictFirst(), polKeep = policyEvictLast();
-        const int stride = S::SIZE + (CPML ? psiStageFloats(P.W) : 0);
-        const bool tileX = CPML && (tx0 < P.W || tx0 + TX > P.nx - P.W), tileZ = CPML && (tz0 < P.W || tz0 + TZ > P.nz - P.W);
+        const bool tileX = XZC && P.fastDebug != 4 && (tx0 < P.W || tx0 + TX > P.nx - P.W), tileZ = XZC && P.fastDebug != 4 && (tz0 < P.W || tz0 + TZ > P.nz - P.W);
         const int kz0 = tz0 < P.W ? tz0 : tz0 - (P.nz - 2 * P.W);
-        const uint32_t bytesPX = 3u * TZ * 2u * (uint32_t)P.W * 4u, bytesPZ = 3u * C::N_P * 4u;
+        const uint32_t bytesPX = 3u * TZ * (uint32_t)P.psiBoxX * 4u, bytesPZ = 3u * C::N_P * 4u;
+        const int xs = (P.psiBoxX == P.psiPitchX || tx0 < P.W) ? 0 : P.psiPitchX - P.psiBoxX;
         const uint32_t bytesFull = S::BYTES_FULL + (tileX ? bytesPX : 0u) + (tileZ ? bytesPZ : 0u);
         for (int it = 0; it < nIter; it++) {
             const int cy = WS_HALO + yc0 - (Q - 1) + it;
@@ -1029,9 +1052,9 @@ template <int Q, bool CPML> __global__ void __launch_bounds__(Cfg<Q>::NTHREADS, 
             const uint32_t bar = barFull + 8u * stage;
             mbarExpectTx(bar, comp ? bytesFull : S::BYTES_FEED);
             if (comp && tileX)
-                tmaLoad4D(st + 4u * S::SIZE, &maps[TM_PX], bar, 0, tz0, cy - WS_HALO, 3);
+                tmaLoad4D(st + 4u * S::SIZE, &maps[TM_PX], bar, xs, tz0, cy - WS_HALO, 3);
             if (comp && tileZ)
-                tmaLoad4D(st + 4u * (S::SIZE + psxFloats(P.W)), &maps[TM_PZ], bar, tx0, kz0, cy - WS_HALO, 3);
+                tmaLoad4D(st + 4u * (S::SIZE + psxFloats(P.psiBoxX)), &maps[TM_PZ], bar, tx0, kz0, cy - WS_HALO, 3);
             if (hints) { // the velocities come back H (H-1) planes later as stencil tiles
                 tmaLoad4DHint(st + 4u * S::FEED, &maps[TM_F1_P], bar, cx, cz, cy + H, AF_VX, polKeep);
                 tmaLoad4DHint(st + 4u * (S::FEED + C::N_P), &maps[TM_F1_P], bar, cx, cz, cy + H - 1, AF_VY, polKeep);
@@ -1095,11 +1118,13 @@ CUtensorMap makeMap(const float *arena, int pitch, int nzp, int nyp, long long a
     return m;
 }
 
-constexpr int kMaxDynSmem = 227 * 1024 - 1024; // 227 KB per block minus the static barriers
-template <int Q> size_t smemBytes(int pass, bool cpml, int W)
+constexpr int kMaxDynSmem = 227 * 1024 - 2048; // 227 KB per block minus the static barriers and coefficient table
+// cpmlEdge: the launch covers tiles in x / z CPML layers (staged memory variables); the stress half-step appends the
+// derivative exchange buffer (6 plain tiles)
+template <int Q> size_t smemBytes(int pass, bool cpmlEdge, int PX)
 {
-    const size_t stage = (pass == 0 ? StageV<Q>::SIZE : StageS<Q>::SIZE) + (cpml ? psiStageFloats(W) : 0);
-    return (size_t)(pass == 0 ? NSTV : NSTS) * stage * 4;
+    const size_t stage = (pass == 0 ? StageV<Q>::SIZE : StageS<Q>::SIZE) + (cpmlEdge ? psiStageFloats(PX) : 0);
+    return ((size_t)(pass == 0 ? NSTV : NSTS) * stage + (pass == 1 ? 6 * Cfg<Q>::N_P : 0)) * 4;
 }
 
 // dense 4-D map (d0 fastest, arrays outermost); box = b0 x b1 x 1 x bA
@@ -1122,38 +1147,61 @@ template <int Q> void setAttrs()
     static bool done = false;
     if (done)
         return;
-    const int smV = NSTV * StageV<Q>::SIZE * 4, smS = NSTS * StageS<Q>::SIZE * 4;
-    cudaFuncSetAttribute(kFastVel<Q, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
-    cudaFuncSetAttribute(kFastVel<Q, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smV);
-    cudaFuncSetAttribute(kFastStress<Q, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
-    cudaFuncSetAttribute(kFastStress<Q, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smS);
+    cudaFuncSetAttribute(kFastVel<Q, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+    cudaFuncSetAttribute(kFastVel<Q, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+    cudaFuncSetAttribute(kFastVel<Q, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+    cudaFuncSetAttribute(kFastStress<Q, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+    cudaFuncSetAttribute(kFastStress<Q, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+    cudaFuncSetAttribute(kFastStress<Q, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
     done = true;
 }
 
-template <int Q> void launchQ(const WsParams &P, int pass, cudaStream_t st)
+template <int Q> int launchQ(const WsParams &P, int pass, cudaStream_t st)
 {
     setAttrs<Q>();
+    int launched = 0;
     const int ny = P.yhi - P.ylo;
-    dim3 grid((P.nx + TX - 1) / TX, (P.nz + TZ - 1) / TZ, (ny + P.fastChunk - 1) / P.fastChunk);
     const bool cpml = P.damping == 2;
-    const int nt = Cfg<Q>::NTHREADS;
-    if (pass == 0) {
-        const size_t sm = smemBytes<Q>(0, cpml, P.W);
-        const int ntv = NGROUPS * Cfg<Q>::NTG + 32;
-        if (cpml)
-            kFastVel<Q, true><<<grid, ntv, sm, st>>>(P);
-        else
-            kFastVel<Q, false><<<grid, ntv, sm, st>>>(P);
-    } else {
-        const size_t sm = smemBytes<Q>(1, cpml, P.W);
-        if (cpml)
-            kFastStress<Q, true><<<grid, nt, sm, st>>>(P);
-        else
-            kFastStress<Q, false><<<grid, nt, sm, st>>>(P);
+    const int nt = NGROUPS * Cfg<Q>::NTG + 32;
+    // Tiles that touch an x / z CPML layer move up to 1.5x the bytes of an interior tile.  Launched together, the slow
+    // tiles desynchronise the marches of neighbouring thread blocks, and halo rows that neighbours would share in L2
+    // are fetched from HBM twice (measured: +20 % DRAM reads).  So the layer tiles (longest first) and the interior
+    // tiles run as two launches: each is homogeneous enough for its waves of thread blocks to stay in step.
+    for (int part = 0; part < 2; part++) {
+        WsParams Q2 = P;
+        Q2.fastTileBase = part == 0 ? 0 : P.fastNEdge;
+        const int n = part == 0 ? P.fastNEdge : P.fastNTiles - P.fastNEdge;
+        if (n <= 0)
+            continue;
+        launched++;
+        const int chunk = part == 0 && P.fastNEdge > 0 ? P.fastChunkEdge : P.fastChunk;
+        dim3 grid(n, 1, (ny + chunk - 1) / chunk);
+        // the second part holds the interior tiles when the layer tiles have a launch of their own (fastNEdge > 0)
+        const bool edge = cpml && (part == 0 || P.fastNEdge == 0);
+        const size_t sm = smemBytes<Q>(pass, edge, P.psiBoxX);
+        Q2.fastChunk = chunk;
+        if (pass == 0) {
+            if (edge)
+                kFastVel<Q, true, true><<<grid, nt, sm, st>>>(Q2);
+            else if (cpml)
+                kFastVel<Q, true, false><<<grid, nt, sm, st>>>(Q2);
+            else
+                kFastVel<Q, false, false><<<grid, nt, sm, st>>>(Q2);
+        } else {
+            if (edge)
+                kFastStress<Q, true, true><<<grid, nt, sm, st>>>(Q2);
+            else if (cpml)
+                kFastStress<Q, true, false><<<grid, nt, sm, st>>>(Q2);
+            else
+                kFastStress<Q, false, false><<<grid, nt, sm, st>>>(Q2);
+        }
     }
+    return launched;
 }
 
 } // namespace
+
+static unsigned long long *g_trace = nullptr;
 
 bool wsFastSupported(const WsParams &P, bool exact)
 {
@@ -1170,12 +1218,13 @@ bool wsFastSupported(const WsParams &P, bool exact)
     if (P.damping == 2) {
         // the x / z memory variables are staged by TMA: 16-byte slab rows (even W), a tile touches one side of an axis only,
         // and the staged rows must fit next to the operands
-        if (!P.psiXArena || !P.psiZArena || P.W % 2 != 0)
+        if (!P.psiXArena || !P.psiZArena || !P.cxTab || P.psiPitchX > PXMAX || P.nx - P.W - (P.W + 3) / 4 * 4 < 0)
             return false;
         for (int tz0 = 0; tz0 < P.nz; tz0 += TZ)
             if (tz0 < P.W && tz0 + TZ > P.nz - P.W)
                 return false;
-        const size_t need = P.q == 8 ? std::max(smemBytes<8>(0, true, P.W), smemBytes<8>(1, true, P.W)) : std::max(smemBytes<4>(0, true, P.W), smemBytes<4>(1, true, P.W));
+        const int PX = P.psiPitchX;
+        const size_t need = P.q == 8 ? std::max(smemBytes<8>(0, true, PX), smemBytes<8>(1, true, PX)) : std::max(smemBytes<4>(0, true, PX), smemBytes<4>(1, true, PX));
         if (need > (size_t)kMaxDynSmem)
             return false;
     }
@@ -1200,44 +1249,94 @@ void *wsFastPrepare(WsParams &P, int nyp)
     mkM(TM_M_P, TX, TZ, 5);
     if (P.damping == 2) {
         const int W2 = 2 * P.W;
-        maps[TM_PX] = makeMapG(P.psiXArena, W2, P.nz, P.nyl, APS_COUNT, W2, TZ, 3);
+        // a tile stages its own side of the x rows only (entries [0, W4) or [PX - box, PX)) unless one tile spans both layers
+        const int W4 = (P.W + 3) / 4 * 4;
+        const bool oneSided = TX <= P.nx - P.W; // the first tile ends before the high layer starts, so no tile touches both
+        P.psiBoxX = oneSided ? std::max(W4, P.psiPitchX - W4) : P.psiPitchX;
+        maps[TM_PX] = makeMapG(P.psiXArena, P.psiPitchX, P.nz, P.nyl, APS_COUNT, P.psiBoxX, TZ, 3);
         maps[TM_PZ] = makeMapG(P.psiZArena, P.nx, W2, P.nyl, APS_COUNT, TX, TZ, 3);
     }
+    P.fastFlags = getenv("WS_FAST_FLAGS") ? atoi(getenv("WS_FAST_FLAGS")) : 3;
+    // tile list: layer tiles first (z layers and corners, then x layers: longest first; neighbours adjacent), then interior
+    const int ntx = (P.nx + TX - 1) / TX, ntz = (P.nz + TZ - 1) / TZ;
+    std::vector<int> tilesCorner, tilesZ, tilesX, tilesIn;
+    const bool split = P.damping == 2 && (P.fastFlags & 2);
+    for (int bz = 0; bz < ntz; bz++)
+        for (int bx = 0; bx < ntx; bx++) {
+            const bool ex = split && (bx * TX < P.W || bx * TX + TX > P.nx - P.W), ez = split && (bz * TZ < P.W || bz * TZ + TZ > P.nz - P.W);
+            (ex && ez ? tilesCorner : (ez ? tilesZ : (ex ? tilesX : tilesIn))).push_back((bz << 16) | bx);
+        }
+    std::stable_sort(tilesX.begin(), tilesX.end(), [](int a, int b) { return (a & 0xffff) < (b & 0xffff); }); // column by column
+    std::vector<int> tiles(tilesCorner);
+    tiles.insert(tiles.end(), tilesZ.begin(), tilesZ.end());
+    tiles.insert(tiles.end(), tilesX.begin(), tilesX.end());
+    P.fastNEdge = (int)tiles.size();
+    tiles.insert(tiles.end(), tilesIn.begin(), tilesIn.end());
+    P.fastNTiles = (int)tiles.size();
+    P.fastTileBase = 0;
     void *dev = nullptr;
-    if (cudaMalloc(&dev, sizeof(CUtensorMap) * TM_COUNT) != cudaSuccess)
+    if (cudaMalloc(&dev, sizeof(CUtensorMap) * TM_COUNT + sizeof(int) * tiles.size()) != cudaSuccess)
         throw std::runtime_error("cudaMalloc for tensor maps failed");
     cudaMemcpy(dev, maps.data(), sizeof(CUtensorMap) * TM_COUNT, cudaMemcpyHostToDevice);
+    cudaMemcpy(static_cast<char *>(dev) + sizeof(CUtensorMap) * TM_COUNT, tiles.data(), sizeof(int) * tiles.size(), cudaMemcpyHostToDevice);
     P.fastMaps = dev;
+    P.fastTiles = reinterpret_cast<const int *>(static_cast<char *>(dev) + sizeof(CUtensorMap) * TM_COUNT);
     P.fastDebug = getenv("WS_FAST_DEBUG") ? atoi(getenv("WS_FAST_DEBUG")) : 0;
-    P.fastFlags = getenv("WS_FAST_FLAGS") ? atoi(getenv("WS_FAST_FLAGS")) : 1;
-    // planes per block: enough blocks to fill the 148 SMs several times over, long enough marches to amortise the
-    // Q-1 feed-only iterations of the prologue
-    const int tiles = ((P.nx + TX - 1) / TX) * ((P.nz + TZ - 1) / TZ);
-    int chunks = (6 * 148 + tiles - 1) / tiles;
-    if (chunks < 1)
-        chunks = 1;
-    int chunk = (P.nyl + chunks - 1) / chunks;
-    if (chunk < 32)
-        chunk = 32;
-    P.fastChunk = chunk;
+    P.fastTrace = nullptr;
+    if (getenv("WS_FAST_TRACE")) {
+        cudaMalloc(&g_trace, sizeof(unsigned long long) * 3 * 2 * WS_TRACE_MAX);
+        cudaMemset(g_trace, 0, sizeof(unsigned long long) * 3 * 2 * WS_TRACE_MAX);
+        P.fastTrace = g_trace;
+    }
+    // planes per block: the march is cut into chunks so that the last round of thread blocks on the 148 SMs is short;
+    // every chunk pays Q-1 feed-only planes plus the pipeline fill
+    auto pickChunk = [&](int nTiles) {
+        int best = P.nyl;
+        double bestCost = 1e30;
+        for (int k = 1; k <= 8; k++) {
+            const int len = (P.nyl + k - 1) / k;
+            if (k > 1 && len < 64)
+                break;
+            const double rounds = std::ceil((double)nTiles * k / 148.0);
+            const double cost = rounds * (len + P.q + 3);
+            if (cost < bestCost * 0.995) {
+                bestCost = cost;
+                best = len;
+            }
+        }
+        return best;
+    };
+    P.fastChunk = pickChunk(P.fastNTiles - P.fastNEdge);
+    P.fastChunkEdge = P.fastNEdge > 0 ? pickChunk(P.fastNEdge) : P.fastChunk;
+    if (getenv("WS_FAST_CHUNK"))
+        P.fastChunk = P.fastChunkEdge = atoi(getenv("WS_FAST_CHUNK"));
     return dev;
 }
 
 void wsFastRelease(void *maps)
 {
+    if (g_trace && getenv("WS_FAST_TRACE")) {
+        std::vector<unsigned long long> h((size_t)3 * 2 * WS_TRACE_MAX);
+        cudaDeviceSynchronize();
+        cudaMemcpy(h.data(), g_trace, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+        if (FILE *f = fopen(getenv("WS_FAST_TRACE"), "wb")) {
+            fwrite(h.data(), sizeof(unsigned long long), h.size(), f);
+            fclose(f);
+        }
+        cudaFree(g_trace);
+        g_trace = nullptr;
+    }
     if (maps)
         cudaFree(maps);
 }
 
-bool wsLaunchFast(const WsParams &P, int pass, cudaStream_t st)
+int wsLaunchFast(const WsParams &P, int pass, cudaStream_t st)
 {
     if (!P.fastMaps || P.yhi <= P.ylo)
-        return false;
+        return 0;
     if (P.q == 8)
-        launchQ<8>(P, pass, st);
-    else if (P.q == 4)
-        launchQ<4>(P, pass, st);
-    else
-        return false;
-    return true;
+        return launchQ<8>(P, pass, st);
+    if (P.q == 4)
+        return launchQ<4>(P, pass, st);
+    return 0;
 }

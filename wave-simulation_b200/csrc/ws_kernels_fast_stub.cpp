@@ -4,4 +4,4 @@
 bool wsFastSupported(const WsParams &, bool) { return false; }
 void *wsFastPrepare(WsParams &, int) { return nullptr; }
 void wsFastRelease(void *) {}
-bool wsLaunchFast(const WsParams &, int, cudaStream_t) { return false; }
+int wsLaunchFast(const WsParams &, int, cudaStream_t) { return 0; }

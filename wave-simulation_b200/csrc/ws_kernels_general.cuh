@@ -36,7 +36,7 @@ struct Pt {
                 ky = -1; // no CPML in the top layer with a free surface (CPML3D.cpp:320-328)
             if (P.dim == 3)
                 kz = wsCpmlIndex(z, P.nz, W);
-            px = ((long long)ly * P.nz + z) * (2 * W) + kx;
+            px = ((long long)ly * P.nz + z) * P.psiPitchX + wsPsiXIndex(x, W, P.psiDX);
             py = ((long long)ky * P.nz + z) * P.nx + x;
             pz = ((long long)ly * (2 * W) + kz) * P.nx + x;
         }

@@ -13,4 +13,4 @@ bool wsFastSupported(const WsParams &P, bool exact);
 // wsFastRelease) and fills P.fastMaps / P.fastChunk
 void *wsFastPrepare(WsParams &P, int nyp);
 void wsFastRelease(void *maps);
-bool wsLaunchFast(const WsParams &P, int pass, cudaStream_t st);
+int wsLaunchFast(const WsParams &P, int pass, cudaStream_t st); // number of kernels launched (0 = not served)
