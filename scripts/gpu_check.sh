@@ -15,5 +15,5 @@ echo "== bench"; timeout 900 python bench.py --steps ${BENCH_STEPS:-10} --warmup
 fi
 if [ -z "$SKIP_NCU" ]; then
 echo "== ncu launches"; timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu --nx 512 --ny 512 --nz 512 ${BENCH_ARGS} > gpurun_out/bench_ncu.log 2>&1; echo "ncu rc=$?"; tail -2 gpurun_out/bench_ncu.log
-echo "== ncu full"; timeout 1200 ncu --set full --clock-control none --import-source on -k regex:${NCU_KERNEL:-kFast} -s 6 -c 2 -f -o gpurun_out/prof python bench.py --steps 2 --warmup 3 --no-cpu --nx 512 --ny 512 --nz 512 ${BENCH_ARGS} > gpurun_out/bench_ncufull.log 2>&1; echo "ncu full rc=$?"; tail -2 gpurun_out/bench_ncufull.log
+echo "== ncu full"; timeout 1200 ncu --set full --clock-control none --import-source on -k regex:${NCU_KERNEL:-kFast} -s 8 -c 4 -f -o gpurun_out/prof python bench.py --steps 2 --warmup 3 --no-cpu --nx 512 --ny 512 --nz 512 ${BENCH_ARGS} > gpurun_out/bench_ncufull.log 2>&1; echo "ncu full rc=$?"; tail -2 gpurun_out/bench_ncufull.log
 fi
