@@ -78,6 +78,7 @@ int ws_create(const ws_desc *desc, ws_solver **out);     /* = Factory::Create + 
 void ws_destroy(ws_solver *s);
 const char *ws_last_error(void);
 const char *ws_version(void);
+int ws_device_count(void);                               /* CUDA devices visible to this process (0 = none: nothing can run) */
 size_t ws_estimate_memory(const ws_desc *desc);          /* bytes of HBM one rank will allocate (estimateMemory) */
 
 /* y-range [y0, y0+nyl) of the global grid owned by this rank */

@@ -1,0 +1,214 @@
+"""The LAMA-free C++ host layer (wave-simulation_b200/host): the reference's Configuration / Coordinates / Acquisition /
+Modelparameter / Wavefields / Derivatives / ForwardSolver classes and the `Simulation` driver on top of the C ABI.
+
+CPU part: unit tests with the reference's known answers (tests/host/test_host.cpp) and the driver run end to end on
+par/ci-style inputs against the golden seismograms — linked, FOR THESE TESTS ONLY, against the host emulation build of
+the library (tests/emu).  GPU part (`-m gpu`): the product binary `host/Simulation` on the CUDA library."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from wsharness import ROOT, EmuSolver, Oracle, build_emu, ci_case, golden, rel_l2, two_layer
+
+HOST = os.path.join(ROOT, "wave-simulation_b200", "host")
+EMU_DIR = os.path.join(ROOT, "tests", "emu")
+
+CONFIG_2D_ELASTIC = """# 2D elastic CI case of the reference (par/ci/configuration_ci.2D.elastic.txt), transcribed
+dimension=2D
+equationType=elastic
+NX=100 # horizontal 1
+NY=100 # depth
+NZ=1
+UseVariableGrid=0
+useVariableFDoperators=0
+useStencilMatrix={stencil}
+NumShotDomains=1
+DH=50
+DT=2.0e-03                   # temporal sampling in seconds
+T={T}
+spatialFDorder=12
+ModelRead=1
+ModelFilename=model/model
+fileFormat={fmt}
+numRelaxationMechanisms=0;
+FreeSurface=1
+DampingBoundary=1
+BoundaryWidth=9
+DampingCoeff=8.0
+VMaxCPML=3500
+CenterFrequencyCPML=5
+NPower=4
+SourceFilename=acq/sources
+ReceiverFilename=acq/receiver
+SeismogramFilename=seismograms/seismogram
+initSourcesFromSU=0
+initReceiverFromSU=0
+SeismogramFormat={sfmt}
+normalizeTraces={norm}
+useReceiversPerShot={rps}
+writeSource=0
+seismoDT={sdt}
+snapType={snap}
+WavefieldFileName=wavefields/wavefield
+tFirstSnapshot=0
+tLastSnapshot=2
+tIncSnapshot=0.1
+verbose=0
+"""
+
+
+def write_mtx_vector(path, v):
+    with open(path, "w") as f:
+        f.write("%%MatrixMarket matrix array real general\n%d 1\n" % v.size)
+        f.write("\n".join("%.9g" % x for x in v))
+        f.write("\n")
+
+
+def write_lmf_vector(path, v):
+    with open(path, "wb") as f:
+        f.write(struct.pack("<5i", 0x4711E01, 0, 2, 1, v.size))
+        f.write(np.asarray(v, "<f4").tobytes())
+
+
+def read_mtx(path):
+    with open(path) as f:
+        lines = [ln for ln in f if not ln.startswith("%")]
+    r, c = (int(x) for x in lines[0].split())
+    return np.array([float(x) for x in lines[1:1 + r * c]]).reshape(c, r).T
+
+
+def read_lmf_matrix(path):
+    raw = open(path, "rb").read()
+    ident, itype, vtype, ndims, r, c = struct.unpack("<6i", raw[:24])
+    assert (ident, itype, vtype, ndims) == (0x4711E01, 0, 2, 2)
+    return np.frombuffer(raw[24:], "<f4").reshape(r, c)
+
+
+@pytest.fixture(scope="module")
+def driver():
+    build_emu()
+    subprocess.check_call(["make", "-s", "-C", HOST, "libSimulation_host.a", "Simulation.o"])
+    subprocess.check_call(["make", "-s", "-C", HOST, "emu"])
+    return os.path.join(EMU_DIR, "Simulation_emu")
+
+
+def setup_case(tmp, fmt=1, sources="1 20  0   0   2   1   1   5.0   5.0   0.0\n", receivers="30 0 0 3\n", **kw):
+    for d in ("model", "acq", "seismograms", "wavefields"):
+        os.makedirs(os.path.join(tmp, d), exist_ok=True)
+    m = two_layer(100, 100, 1)
+    w = write_mtx_vector if fmt == 1 else write_lmf_vector
+    ext = ".mtx" if fmt == 1 else ".lmf"
+    for key, suffix in (("velocityP", "vp"), ("velocityS", "vs"), ("density", "density")):
+        w(os.path.join(tmp, "model", "model." + suffix + ext), m[key])
+    open(os.path.join(tmp, "acq", "sources.txt"), "w").write("# sourceNo X Y Z type wType wShape fc amp tShift\n" + sources)
+    open(os.path.join(tmp, "acq", "receiver.txt"), "w").write("# X Y Z type\n" + receivers)
+    par = dict(stencil=1, T=2, fmt=fmt, sfmt=1, norm=0, rps=0, sdt="2.0e-03", snap=0)
+    par.update(kw)
+    cfg = os.path.join(tmp, "configuration.txt")
+    open(cfg, "w").write(CONFIG_2D_ELASTIC.format(**par))
+    return cfg
+
+
+def run(driver, cfg, cwd, expect_ok=True):
+    p = subprocess.run([driver, cfg], cwd=cwd, capture_output=True, text=True, timeout=900)
+    if expect_ok:
+        assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    return p
+
+
+def test_host_unit_tests(tmp_path):
+    subprocess.check_call(["make", "-s", "-C", HOST, "libSimulation_host.a"])
+    exe = str(tmp_path / "test_host")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-I" + HOST, os.path.join(ROOT, "tests", "host", "test_host.cpp"),
+                           os.path.join(HOST, "libSimulation_host.a"), "-o", exe])
+    out = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout
+    assert "host unit tests OK" in out.stdout
+
+
+def test_driver_reproduces_reference_golden_2d_elastic(driver, tmp_path):
+    """par/ci 2D elastic case end to end through the driver: config file, source / receiver files, .mtx model files,
+    .mtx seismogram; golden = the reference's own par/ci/seismogram.2D.elastic.ref.vy.mtx."""
+    cfg = setup_case(str(tmp_path))
+    run(driver, cfg, str(tmp_path))
+    s = read_mtx(str(tmp_path / "seismograms" / "seismogram.shot_1.vy.mtx"))
+    g = golden("seismogram.2D.elastic.ref.vy.mtx")
+    assert s.shape == g.shape == (1, 1000)
+    assert rel_l2(s, g) <= 1.0e-5
+
+
+def test_driver_sparse_policy_lmf_and_oracle(driver, tmp_path):
+    """useStencilMatrix=0 selects the order-reducing operators (Derivatives.cpp:129-186); .lmf model and seismogram files;
+    compared with the oracle on the same case."""
+    cfg = setup_case(str(tmp_path), fmt=2, stencil=0, sfmt=2, T=0.8)
+    run(driver, cfg, str(tmp_path))
+    s = read_lmf_matrix(str(tmp_path / "seismograms" / "seismogram.shot_1.vy.lmf"))
+    case = ci_case("2D.elastic", nt=400)
+    o = case.setup(Oracle(case.desc))
+    o.run(0, 400)
+    assert s.shape == (1, 400)
+    assert rel_l2(s, o.seismogram()) <= 1.0e-5
+
+
+def test_driver_multishot_receivers_per_shot_resampling_normalisation_snapshots(driver, tmp_path):
+    tmp = str(tmp_path)
+    src = "1 20 0 0 2 1 1 5.0 5.0 0.0\n2 40 5 0 1 1 1 8.0 1.0 0.0\n-2 60 5 0 3 1 4 6.0 2.0 0.05\n"
+    cfg = setup_case(tmp, sources=src, rps=1, sdt="4.0e-03", norm=1, T=0.4, snap=1)
+    open(os.path.join(tmp, "acq", "receiver.shot_1.txt"), "w").write("30 0 0 3\n50 2 0 2\n")
+    open(os.path.join(tmp, "acq", "receiver.shot_2.txt"), "w").write("35 3 0 1\n36 3 0 3\n37 3 0 3\n")
+    run(driver, cfg, tmp)
+    files = sorted(os.listdir(os.path.join(tmp, "seismograms")))
+    assert files == ["seismogram.shot_1.vx.mtx", "seismogram.shot_1.vy.mtx", "seismogram.shot_2.p.mtx", "seismogram.shot_2.vy.mtx"]
+    vy2 = read_mtx(os.path.join(tmp, "seismograms", "seismogram.shot_2.vy.mtx"))
+    assert vy2.shape == (2, 100)  # NT = 200 resampled by 2
+    assert np.abs(vy2).max() <= 1.0  # normalizeTraces = 1 acts on the full-rate trace, resampling on the output
+    # same shot through the Python binding of the same (emulated) library: two sources fire together in shot 2
+    case = ci_case("2D.elastic", nt=200)
+    case.desc.edge_policy = 0
+    from wsharness import idx1d, ricker
+    fg = np.zeros(200, np.float32)
+    t = np.arange(200, dtype=np.float32) * np.float32(2e-3)
+    tau = (t - np.float32(1.2 / 6.0 + 0.05)) * np.float32(np.pi * 6.0)
+    fg = (np.float32(2.0) * (np.float32(-2.0) * tau) * np.exp(-tau * tau)).astype(np.float32)
+    case.src = ([1, 3], [idx1d(40, 5, 0, 100, 1), idx1d(60, 5, 0, 100, 1)], np.stack([ricker(200, 2e-3, 8.0, 1.0, 0.0), fg]))
+    case.rec = ([1, 3, 3], [idx1d(35, 3, 0, 100, 1), idx1d(36, 3, 0, 100, 1), idx1d(37, 3, 0, 100, 1)])
+    e = case.setup(EmuSolver(case.desc))
+    e.run(0, 200)
+    ref = e.seismogram()[1:]
+    ref = (ref / np.abs(ref).max(axis=1, keepdims=True))[:, ::2]
+    assert rel_l2(vy2, ref) <= 1.0e-4  # plumbing check: the FGaussian wavelet above is a numpy re-evaluation (libm vs numpy exp)
+    snaps = [f for f in os.listdir(os.path.join(tmp, "wavefields")) if f.startswith("wavefield.shot_1.VX.")]
+    assert "wavefield.shot_1.VX.0.mtx" in snaps and "wavefield.shot_1.VX.150.mtx" in snaps and len(snaps) == 4
+
+
+def test_driver_error_behaviour(driver, tmp_path):
+    tmp = str(tmp_path)
+    cfg = setup_case(tmp)
+    text = open(cfg).read()
+    open(cfg, "w").write(text.replace("DT=2.0e-03", "DT=2.0e-02"))
+    p = run(driver, cfg, tmp, expect_ok=False)
+    assert p.returncode != 0 and "Courant-Friedrichs-Lewy-Criterion is not met" in p.stdout + p.stderr
+    open(cfg, "w").write(text.replace("spatialFDorder=12", "spatialFDorder=7"))
+    p = run(driver, cfg, tmp, expect_ok=False)
+    assert p.returncode != 0 and "Unsupported spatialFDorder" in p.stderr
+    open(cfg, "w").write(text.replace("equationType=elastic", "equationType=visco"))
+    p = run(driver, cfg, tmp, expect_ok=False)
+    assert p.returncode != 0 and "Unkown" in p.stderr
+    open(cfg, "w").write(text.replace("NX=100", "#NX=100"))
+    p = run(driver, cfg, tmp, expect_ok=False)
+    assert p.returncode != 0 and "Parameter NX: Not found in Configuration file!" in p.stderr
+    p = subprocess.run([driver], capture_output=True, text=True)
+    assert p.returncode != 0 and "No configuration file given" in p.stdout
+
+
+@pytest.mark.gpu
+def test_product_driver_on_gpu(tmp_path):
+    """The product binary host/Simulation (CUDA library) on the same par/ci case; golden from the reference."""
+    subprocess.check_call(["make", "-s", "-C", HOST])
+    cfg = setup_case(str(tmp_path))
+    run(os.path.join(HOST, "Simulation"), cfg, str(tmp_path))
+    s = read_mtx(str(tmp_path / "seismograms" / "seismogram.shot_1.vy.mtx"))
+    assert rel_l2(s, golden("seismogram.2D.elastic.ref.vy.mtx")) <= 1.0e-5

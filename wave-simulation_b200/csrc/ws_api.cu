@@ -1084,6 +1084,11 @@ extern "C" {
 
 const char *ws_last_error(void) { return g_lastError.c_str(); }
 const char *ws_version(void) { return "wavesim-b200 0.1 (sm_100a)"; }
+int ws_device_count(void)
+{
+    int n = 0;
+    return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
+}
 
 size_t ws_estimate_memory(const ws_desc *desc)
 {

@@ -1,0 +1,479 @@
+#include "Acquisition.hpp"
+#include "IO.hpp"
+#include <algorithm>
+#include <fstream>
+
+using namespace KITGPI;
+
+const char *const Acquisition::SeismogramTypeString[4] = {"p", "vx", "vy", "vz"};
+const char *const Acquisition::SeismogramTypeStringEM[4] = {"ez", "ex", "ey", "hz"};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// acquisition files
+// ---------------------------------------------------------------------------------------------------------------------
+namespace
+{
+    // tokens of the data lines of an acquisition file: `#` lines and blank lines are skipped (AcquisitionSettings.hpp:68-72)
+    std::vector<std::vector<std::string>> tokenLines(std::string const &fileName, const char *what)
+    {
+        std::ifstream in(fileName, std::ios::binary);
+        if (!in.is_open())
+            COMMON_THROWEXCEPTION("Could not open " << what << " acquisition file " << fileName)
+        std::vector<std::vector<std::string>> rows;
+        std::string line;
+        while (std::getline(in, line)) {
+            if (line.empty() || line[0] == '#' || std::all_of(line.begin(), line.end(), [](unsigned char c) { return std::isspace(c); }))
+                continue;
+            std::istringstream ss(line);
+            std::vector<std::string> tok;
+            std::string t;
+            while (ss >> t)
+                tok.push_back(t);
+            rows.push_back(tok);
+        }
+        return rows;
+    }
+}
+
+template <typename ValueType> void Acquisition::readAllSettings(std::vector<sourceSettings<ValueType>> &allSettings, std::string fileName)
+{
+    allSettings.clear();
+    IndexType row = 0;
+    for (auto const &tok : tokenLines(fileName, "source")) {
+        if (tok.size() != 10)
+            COMMON_THROWEXCEPTION("Wrong number of parameters in line of source acquisition file (" << fileName << ")")
+        sourceSettings<ValueType> s;
+        try {
+            s.sourceNo = std::stoi(tok[0]);
+            s.sourceCoords.x = std::stoi(tok[1]);
+            s.sourceCoords.y = std::stoi(tok[2]);
+            s.sourceCoords.z = std::stoi(tok[3]);
+            s.sourceType = std::stoi(tok[4]);
+            s.waveletType = std::stoi(tok[5]);
+            s.waveletShape = std::stoi(tok[6]);
+            s.fc = std::stof(tok[7]);
+            s.amp = std::stof(tok[8]);
+            s.tShift = std::stof(tok[9]);
+        } catch (const std::exception &e) {
+            COMMON_THROWEXCEPTION("Invalid argument while reading file " << fileName << " Message: " << e.what())
+        }
+        s.row = row++;
+        allSettings.push_back(s);
+    }
+}
+
+void Acquisition::readAllSettings(std::vector<receiverSettings> &allSettings, std::string const &fileName)
+{
+    allSettings.clear();
+    for (auto const &tok : tokenLines(fileName, "receiver")) {
+        if (tok.size() != 4)
+            COMMON_THROWEXCEPTION("Wrong number of parameters in line of receiver acquisition file (" << fileName << ")")
+        receiverSettings r;
+        try {
+            r.receiverCoords.x = std::stoi(tok[0]);
+            r.receiverCoords.y = std::stoi(tok[1]);
+            r.receiverCoords.z = std::stoi(tok[2]);
+            r.receiverType = std::stoi(tok[3]);
+        } catch (const std::exception &e) {
+            COMMON_THROWEXCEPTION("Invalid argument while reading file " << fileName << " Message: " << e.what())
+        }
+        allSettings.push_back(r);
+    }
+}
+
+template <typename ValueType> void Acquisition::calcuniqueShotNo(std::vector<IndexType> &uniqueShotNo, std::vector<sourceSettings<ValueType>> const &settings)
+{
+    uniqueShotNo.clear();
+    for (auto const &s : settings) {
+        const IndexType no = std::abs(s.sourceNo);
+        if (std::find(uniqueShotNo.begin(), uniqueShotNo.end(), no) == uniqueShotNo.end())
+            uniqueShotNo.push_back(no);
+    }
+}
+
+template <typename ValueType>
+void Acquisition::createSettingsForShot(std::vector<sourceSettings<ValueType>> &settings, std::vector<sourceSettings<ValueType>> const &allSettings, IndexType shotNumber)
+{
+    settings.clear();
+    for (auto const &s : allSettings)
+        if (std::abs(s.sourceNo) == shotNumber)
+            settings.push_back(s);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// wavelets: float arithmetic statement by statement as the LAMA vector expressions of Acquisition/SourceSignal/*.cpp
+// ---------------------------------------------------------------------------------------------------------------------
+void Acquisition::SourceSignal::calc(IndexType shape, std::vector<ValueType> &signal, IndexType NT, ValueType DT, ValueType FC, ValueType AMP, ValueType Tshift)
+{
+    typedef ValueType T;
+    signal.assign(NT, T(0));
+    auto window = [&](IndexType &i1, IndexType &i2) { // SinW / SinThree / IntgSinThree: one period after Tshift
+        i1 = (IndexType)std::floor(Tshift / DT);
+        i2 = i1 + (IndexType)std::floor(1.0 / FC / DT);
+        if (i2 > NT)
+            i2 = NT - 1;
+    };
+    switch (shape) {
+    case 1: { // Ricker.cpp:41-52
+        const T help = (T)(1.5 / FC + Tshift), w = (T)(M_PI * FC);
+        for (IndexType k = 0; k < NT; k++) {
+            T tau = (T(0) + (T)k * DT) - help;
+            tau *= w;
+            const T h2 = tau * tau;
+            const T e = std::exp(T(-1.0) * h2);
+            signal[k] = (AMP * (T(1.0) - T(2.0) * h2)) * e;
+        }
+        break;
+    }
+    case 2: { // SinW.cpp
+        IndexType i1, i2;
+        window(i1, i2);
+        IndexType count = 0;
+        for (IndexType i = i1; i <= i2 && i < NT; i++, count++) {
+            if (i < 0)
+                continue;
+            double temp = 2.0 * count * DT * M_PI * FC;
+            const T a = (T)std::sin(temp), b = (T)std::sin(2.0 * temp);
+            signal[i] = AMP * (a - b / T(2.0));
+        }
+        break;
+    }
+    case 3: { // SinThree.cpp
+        IndexType i1, i2;
+        window(i1, i2);
+        IndexType count = 0;
+        for (IndexType i = i1; i <= i2 && i < NT; i++, count++) {
+            if (i < 0)
+                continue;
+            double temp = std::sin(count * DT * M_PI * FC);
+            signal[i] = AMP * (T)std::pow(temp, 3);
+        }
+        break;
+    }
+    case 4: { // FGaussian.cpp
+        const T help0 = (T)(1.2 / FC + Tshift), w = (T)(M_PI * FC);
+        for (IndexType k = 0; k < NT; k++) {
+            T tau = ((T)k * DT - help0) * w;
+            const T help = T(-2.0) * tau;
+            tau = std::exp(T(-1.0) * tau * tau);
+            signal[k] = AMP * help * tau;
+        }
+        break;
+    }
+    case 5: { // Spike.cpp
+        const IndexType idx = (IndexType)std::floor(Tshift / DT);
+        SCAI_ASSERT_ERROR(idx >= 0 && idx < NT, "Spike wavelet: tShift outside the time axis")
+        signal[idx] = AMP * T(1.0);
+        break;
+    }
+    case 6: { // IntgSinThree.cpp
+        IndexType i1, i2;
+        window(i1, i2);
+        std::vector<T> help(NT, T(0)), zero(NT, T(0));
+        IndexType count = 0;
+        for (IndexType i = i1; i <= i2 && i < NT; i++, count++) {
+            if (i < 0)
+                continue;
+            double temp = std::cos(count * DT * M_PI * FC);
+            help[i] = (T)temp;
+            zero[i] = (T)std::pow(temp, 3);
+        }
+        for (IndexType k = 0; k < NT; k++) {
+            T z = T(0.25) * zero[k] - T(0.75) * help[k];
+            z = T(0.5) + z;
+            z = z / FC;
+            z = z / (T)M_PI;
+            z = z / T(0.75);
+            signal[k] = AMP * z;
+        }
+        break;
+    }
+    case 7: { // Ricker_GprMax.cpp
+        const T help0 = (T)(1 / FC + Tshift), zeta = (T)(2.0 * M_PI * M_PI * FC * FC);
+        T h = T(1.0) / zeta;
+        h = h / 4;
+        h = std::exp(h);
+        const T z2 = T(-2.0) * (zeta * h);
+        for (IndexType k = 0; k < NT; k++) {
+            const T tau = (T)k * DT - help0;
+            T help = std::exp(T(-1.0) * (zeta * (tau * tau)));
+            signal[k] = AMP * z2 * (help * tau);
+        }
+        break;
+    }
+    case 8: { // Berlage.cpp
+        const T help0 = (T)(1.0 / FC + Tshift), alpha = 2 * FC;
+        T maxNorm = 0;
+        for (IndexType k = 0; k < NT; k++) {
+            const T tau = (T)k * DT - help0;
+            const T c = std::cos((T)(2 * M_PI * FC) * tau);
+            T sgn = tau > 0 ? T(1) : (tau < 0 ? T(-1) : T(0));
+            sgn += 1;
+            const T heaviside = sgn > 0 ? T(1) : T(0);
+            T v = c * std::pow(tau, T(2));
+            v *= std::exp(tau * -alpha);
+            v *= heaviside;
+            signal[k] = v;
+            maxNorm = std::max(maxNorm, std::abs(v));
+        }
+        for (auto &v : signal)
+            v *= AMP / maxNorm;
+        break;
+    }
+    case 9: { // Sin.cpp
+        const T w = (T)(2.0 * M_PI * FC);
+        for (IndexType k = 0; k < NT; k++)
+            signal[k] = AMP * std::sin(((T)k * DT - Tshift) * w);
+        break;
+    }
+    default: COMMON_THROWEXCEPTION("Unknown wavelet shape ")
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Common
+// ---------------------------------------------------------------------------------------------------------------------
+void Common::resampleRows(std::vector<ValueType> &data, IndexType numRows, IndexType numCols, ValueType resamplingCoeff, IndexType &numColsNew)
+{
+    numColsNew = IndexType(std::floor(ValueType(numCols - 1) / resamplingCoeff)) + 1;
+    if (resamplingCoeff == ValueType(1)) {
+        numColsNew = numCols;
+        return; // identity matrix
+    }
+    std::vector<ValueType> out((size_t)numRows * numColsNew, ValueType(0));
+    for (IndexType j = 0; j < numColsNew; j++) {
+        const ValueType rel = j * resamplingCoeff;
+        const IndexType left = (IndexType)std::floor(rel);
+        const ValueType fr = std::fmod(rel, ValueType(1.0));
+        for (IndexType r = 0; r < numRows; r++) {
+            ValueType v = 0;
+            if (left < numCols)
+                v += (1 - fr) * data[(size_t)r * numCols + left];
+            if (left + 1 < numCols)
+                v += fr * data[(size_t)r * numCols + left + 1];
+            out[(size_t)r * numColsNew + j] = v;
+        }
+    }
+    data.swap(out);
+}
+
+bool Common::checkEquationType(std::string type)
+{
+    std::transform(type.begin(), type.end(), type.begin(), ::tolower);
+    for (const char *s : {"acoustic", "elastic", "viscoelastic", "sh", "viscosh"})
+        if (type == s)
+            return true;
+    for (const char *s : {"emem", "tmem", "viscoemem", "viscotmem"})
+        if (type == s)
+            return false;
+    COMMON_THROWEXCEPTION("Unkown equation type " << type)
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Seismogram / SeismogramHandler
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename ValueType> void Acquisition::Seismogram<ValueType>::allocate(IndexType numTraces, IndexType NT)
+{
+    numSamples = NT;
+    data.assign((size_t)numTraces * NT, ValueType(0));
+}
+
+template <typename ValueType> void Acquisition::Seismogram<ValueType>::normalizeTrace(IndexType normalizeTraces)
+{
+    if (data.empty() || normalizeTraces <= 0)
+        return;
+    SCAI_ASSERT_ERROR(normalizeTraces <= 2, "normalizeTraces = 3 (AGC) and 4 (envelope) belong to the inversion workflow and are not available here")
+    for (IndexType i = 0; i < getNumTraces(); i++) {
+        ValueType *row = &data[(size_t)i * numSamples];
+        ValueType norm = 0;
+        if (normalizeTraces == 1) {
+            for (IndexType k = 0; k < numSamples; k++)
+                norm = std::max(norm, std::abs(row[k]));
+        } else {
+            double s = 0;
+            for (IndexType k = 0; k < numSamples; k++)
+                s += (double)row[k] * row[k];
+            norm = (ValueType)std::sqrt(s);
+        }
+        if (norm == 0)
+            norm = 1;
+        for (IndexType k = 0; k < numSamples; k++)
+            row[k] /= norm;
+    }
+}
+
+template <typename ValueType> bool Acquisition::Seismogram<ValueType>::isFinite() const
+{
+    for (ValueType v : data)
+        if (!std::isfinite(v))
+            return false;
+    return true;
+}
+
+template <typename ValueType> void Acquisition::Seismogram<ValueType>::write(IndexType seismogramFormat, std::string const &filename) const
+{
+    if (data.empty())
+        return;
+    SCAI_ASSERT_ERROR(seismogramFormat == 1 || seismogramFormat == 2, "SeismogramFormat " << seismogramFormat << " (frv / SU) is not available in the B200 host layer")
+    const std::string name = filename + "." + (isSeismic ? SeismogramTypeString[type] : SeismogramTypeStringEM[type]);
+    std::vector<ValueType> out(data);
+    IndexType ns = numSamples;
+    if (outputDT > 0 && DT > 0)
+        Common::resampleRows(out, getNumTraces(), numSamples, outputDT / DT, ns); // Seismogram.cpp:610-618 setSeismoDT
+    IO::writeMatrix(out, getNumTraces(), ns, name, seismogramFormat);
+}
+
+template <typename ValueType> void Acquisition::Seismogram<ValueType>::read(IndexType seismogramFormat, std::string const &filename)
+{
+    const std::string name = filename + "." + (isSeismic ? SeismogramTypeString[type] : SeismogramTypeStringEM[type]);
+    IndexType r, c;
+    IO::readMatrix(data, r, c, name, seismogramFormat);
+    numSamples = c;
+}
+
+template <typename ValueType> IndexType Acquisition::SeismogramHandler<ValueType>::getNumTracesTotal() const
+{
+    IndexType n = 0;
+    for (auto const &s : seismo)
+        n += s.getNumTraces();
+    return n;
+}
+template <typename ValueType> void Acquisition::SeismogramHandler<ValueType>::setDT(ValueType dt)
+{
+    for (auto &s : seismo)
+        s.setDT(dt);
+}
+template <typename ValueType> void Acquisition::SeismogramHandler<ValueType>::setSeismoDT(ValueType dt)
+{
+    for (auto &s : seismo)
+        s.setSeismoDT(dt);
+}
+template <typename ValueType> void Acquisition::SeismogramHandler<ValueType>::resetData()
+{
+    for (auto &s : seismo)
+        s.resetData();
+}
+template <typename ValueType> void Acquisition::SeismogramHandler<ValueType>::normalize(IndexType normalizeTraces)
+{
+    for (auto &s : seismo)
+        s.normalizeTrace(normalizeTraces);
+}
+template <typename ValueType> bool Acquisition::SeismogramHandler<ValueType>::isFinite() const
+{
+    for (auto const &s : seismo)
+        if (!s.isFinite())
+            return false;
+    return true;
+}
+template <typename ValueType> void Acquisition::SeismogramHandler<ValueType>::write(IndexType seismogramFormat, std::string const &filename) const
+{
+    for (auto const &s : seismo)
+        s.write(seismogramFormat, filename);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// geometry
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename ValueType>
+template <typename Settings>
+void Acquisition::AcquisitionGeometry<ValueType>::setAcquisition(std::vector<Settings> const &allSettings, Coordinates<ValueType> const &modelCoordinates, IndexType NT)
+{
+    SCAI_ASSERT_ERROR(!allSettings.empty(), "The acquisition is empty")
+    coordinates1D.clear();
+    types.clear();
+    traceOfEntry.clear();
+    IndexType count[NUM_ELEMENTS_SEISMOGRAMTYPE] = {0, 0, 0, 0};
+    for (auto const &s : allSettings) {
+        const IndexType type = s.getType();
+        SCAI_ASSERT_ERROR(type >= 1 && type <= NUM_ELEMENTS_SEISMOGRAMTYPE, "Unkown Seismogram Type " << type)
+        coordinates1D.push_back(modelCoordinates.coordinate2index(s.getCoords())); // throws outside the grid
+        types.push_back(type);
+        traceOfEntry.push_back(count[type - 1]++);
+    }
+    for (IndexType t = 0; t < NUM_ELEMENTS_SEISMOGRAMTYPE; t++) {
+        auto &sg = seismograms.getSeismogram(t);
+        sg.setTraceType(t, seismograms.getIsSeismic());
+        sg.getCoordinates1D().clear();
+        for (size_t k = 0; k < types.size(); k++)
+            if (types[k] == t + 1)
+                sg.getCoordinates1D().push_back(coordinates1D[k]);
+        sg.allocate(count[t], NT);
+    }
+    version++;
+}
+
+template <typename ValueType> void Acquisition::Sources<ValueType>::getAcquisitionSettings(Configuration::Configuration const &config)
+{
+    SCAI_ASSERT_ERROR(!config.getAndCatch("initSourcesFromSU", false), "initSourcesFromSU=1 (SU input) is not available in the B200 host layer")
+    readAllSettings(allSourceSettings, config.get<std::string>("SourceFilename") + ".txt");
+}
+
+template <typename ValueType>
+void Acquisition::Sources<ValueType>::init(std::vector<sourceSettings<ValueType>> const &shotSettings, Configuration::Configuration const &config,
+                                           Coordinates<ValueType> const &modelCoordinates)
+{
+    this->seismograms.setIsSeismic(Common::checkEquationType(config.get<std::string>("equationType")));
+    const ValueType DT = config.get<ValueType>("DT");
+    const IndexType NT = static_cast<IndexType>((config.get<ValueType>("T") / DT) + 0.5);
+    this->setAcquisition(shotSettings, modelCoordinates, NT);
+    this->seismograms.setDT(DT);
+    this->seismograms.setSeismoDT(DT);
+    // signals (Sources.cpp:99-145): 1 = synthetic, 2 = one row of <SourceSignalFilename> for all, 3 = one row per source
+    std::vector<ValueType> fileSignals;
+    IndexType fileRows = 0, fileCols = 0;
+    std::vector<ValueType> sig;
+    bool flag2 = false, flag3 = false;
+    for (size_t k = 0; k < shotSettings.size(); k++) {
+        auto const &s = shotSettings[k];
+        auto &sg = this->seismograms.getSeismogram(s.sourceType - 1);
+        ValueType *row = &sg.getData()[(size_t)this->traceOfEntry[k] * NT];
+        if (s.waveletType == 1) {
+            SourceSignal::calc(s.waveletShape, sig, NT, DT, s.fc, s.amp, s.tShift);
+            std::copy(sig.begin(), sig.end(), row);
+        } else if (s.waveletType == 2 || s.waveletType == 3) {
+            (s.waveletType == 2 ? flag2 : flag3) = true;
+            SCAI_ASSERT_ERROR(!(flag2 && flag3), "Combination of wavelet type 2 and 3 not supported")
+            if (fileSignals.empty())
+                IO::readMatrix(fileSignals, fileRows, fileCols, config.get<std::string>("SourceSignalFilename"), config.get<IndexType>("SeismogramFormat"));
+            const IndexType r = s.waveletType == 2 ? 0 : s.row;
+            SCAI_ASSERT_ERROR(r < fileRows && fileCols == NT, "source signal file must hold one row of " << NT << " samples per source")
+            std::copy(fileSignals.begin() + (size_t)r * fileCols, fileSignals.begin() + (size_t)(r + 1) * fileCols, row);
+        } else
+            COMMON_THROWEXCEPTION("Unknown wavelet type ")
+    }
+}
+
+template <typename ValueType>
+void Acquisition::Receivers<ValueType>::init(std::vector<receiverSettings> const &allSettings, Configuration::Configuration const &config, Coordinates<ValueType> const &modelCoordinates)
+{
+    this->seismograms.setIsSeismic(Common::checkEquationType(config.get<std::string>("equationType")));
+    const IndexType NT = static_cast<IndexType>((config.get<ValueType>("T") / config.get<ValueType>("DT")) + 0.5);
+    this->setAcquisition(allSettings, modelCoordinates, NT);
+    this->seismograms.setDT(config.get<ValueType>("DT"));
+    this->seismograms.setSeismoDT(config.get<ValueType>("seismoDT"));
+}
+
+template <typename ValueType> void Acquisition::Receivers<ValueType>::init(Configuration::Configuration const &config, Coordinates<ValueType> const &modelCoordinates)
+{
+    SCAI_ASSERT_ERROR(!config.getAndCatch("initReceiverFromSU", false), "initReceiverFromSU=1 (SU input) is not available in the B200 host layer")
+    std::vector<receiverSettings> all;
+    readAllSettings(all, config.get<std::string>("ReceiverFilename") + ".txt");
+    init(all, config, modelCoordinates);
+}
+
+template <typename ValueType>
+void Acquisition::Receivers<ValueType>::init(Configuration::Configuration const &config, Coordinates<ValueType> const &modelCoordinates, IndexType shotNumber)
+{
+    std::vector<receiverSettings> all;
+    readAllSettings(all, config.get<std::string>("ReceiverFilename") + ".shot_" + std::to_string(shotNumber) + ".txt");
+    init(all, config, modelCoordinates);
+}
+
+template void Acquisition::readAllSettings<float>(std::vector<sourceSettings<float>> &, std::string);
+template void Acquisition::calcuniqueShotNo<float>(std::vector<IndexType> &, std::vector<sourceSettings<float>> const &);
+template void Acquisition::createSettingsForShot<float>(std::vector<sourceSettings<float>> &, std::vector<sourceSettings<float>> const &, IndexType);
+template class Acquisition::Seismogram<float>;
+template class Acquisition::SeismogramHandler<float>;
+template class Acquisition::AcquisitionGeometry<float>;
+template class Acquisition::Sources<float>;
+template class Acquisition::Receivers<float>;

@@ -1,0 +1,145 @@
+// Acquisition.hpp — sources, receivers and seismograms of the reference (mirror of src/Acquisition/*).
+//   * source file  `<SourceFilename>.txt`: 10 columns  sourceNo X Y Z sourceType waveletType waveletShape fc amp tShift
+//     (AcquisitionSettings.hpp:55-109); receiver file `<ReceiverFilename>.txt`: 4 columns X Y Z receiverType;
+//     per-shot receivers `<ReceiverFilename>.shot_<n>.txt` (Receivers.cpp:209-239)
+//   * types 1..4 = P,VX,VY,VZ (seismic) or EZ,EX,EY,HZ (EM)                     (Acquisition.hpp:17-55)
+//   * the nine analytic wavelets of Acquisition/SourceSignal/*.cpp              (Sources.cpp:165-214)
+//   * seismograms are nTraces x NT matrices per type, resampled to seismoDT on output and written as
+//     `<SeismogramFilename>.shot_<n>.<p|vx|vy|vz|ez|ex|ey|hz>.<mtx|lmf>`        (Seismogram.cpp:82-147, Simulation.cpp:531)
+#pragma once
+#include "Common.hpp"
+#include "Configuration.hpp"
+#include "Coordinates.hpp"
+#include <array>
+
+namespace KITGPI
+{
+    namespace Acquisition
+    {
+        enum SeismogramType { P, VX, VY, VZ };
+        enum SeismogramTypeEM { EZ, EX, EY, HZ };
+        constexpr IndexType NUM_ELEMENTS_SEISMOGRAMTYPE = 4;
+        extern const char *const SeismogramTypeString[4];
+        extern const char *const SeismogramTypeStringEM[4];
+
+        template <typename ValueType> struct sourceSettings {
+            IndexType sourceNo;
+            coordinate3D sourceCoords;
+            IndexType sourceType, waveletType, waveletShape;
+            ValueType fc, amp, tShift;
+            IndexType row;
+            coordinate3D getCoords() const { return sourceCoords; }
+            IndexType getType() const { return sourceType; }
+        };
+        struct receiverSettings {
+            coordinate3D receiverCoords;
+            IndexType receiverType;
+            coordinate3D getCoords() const { return receiverCoords; }
+            IndexType getType() const { return receiverType; }
+        };
+
+        template <typename ValueType> void readAllSettings(std::vector<sourceSettings<ValueType>> &allSettings, std::string fileName);
+        void readAllSettings(std::vector<receiverSettings> &allSettings, std::string const &fileName);
+        //! unique |sourceNo| values in order of first appearance (AcquisitionSettings.hpp calcuniqueShotNo)
+        template <typename ValueType> void calcuniqueShotNo(std::vector<IndexType> &uniqueShotNo, std::vector<sourceSettings<ValueType>> const &sourceSettings);
+        template <typename ValueType>
+        void createSettingsForShot(std::vector<sourceSettings<ValueType>> &settings, std::vector<sourceSettings<ValueType>> const &allSettings, IndexType shotNumber);
+
+        namespace SourceSignal
+        {
+            //! waveletShape 1 Ricker, 2 SinW, 3 SinThree, 4 FGaussian, 5 Spike, 6 IntgSinThree, 7 Ricker_GprMax, 8 Berlage, 9 Sin
+            void calc(IndexType waveletShape, std::vector<ValueType> &signal, IndexType NT, ValueType DT, ValueType FC, ValueType AMP, ValueType Tshift);
+        }
+
+        //! traces of one type
+        template <typename ValueType> class Seismogram
+        {
+          public:
+            void allocate(IndexType numTraces, IndexType NT);
+            void resetData() { std::fill(data.begin(), data.end(), ValueType(0)); }
+            IndexType getNumTraces() const { return (IndexType)coordinates1D.size(); }
+            IndexType getNumSamples() const { return numSamples; }
+            std::vector<ValueType> &getData() { return data; }             // row-major nTraces x NT
+            std::vector<ValueType> const &getData() const { return data; }
+            std::vector<IndexType> &getCoordinates1D() { return coordinates1D; }
+            std::vector<IndexType> const &getCoordinates1D() const { return coordinates1D; }
+            void setDT(ValueType dt) { DT = dt; }
+            void setSeismoDT(ValueType dt) { outputDT = dt; }
+            void setTraceType(IndexType t, bool seismic) { type = t; isSeismic = seismic; }
+            IndexType getTraceType() const { return type; }
+            void normalizeTrace(IndexType normalizeTraces);
+            bool isFinite() const;
+            void write(IndexType seismogramFormat, std::string const &filename) const;
+            void read(IndexType seismogramFormat, std::string const &filename);
+
+          private:
+            std::vector<ValueType> data;
+            std::vector<IndexType> coordinates1D;
+            IndexType numSamples = 0, type = 0;
+            bool isSeismic = true;
+            ValueType DT = 0, outputDT = 0;
+        };
+
+        template <typename ValueType> class SeismogramHandler
+        {
+          public:
+            Seismogram<ValueType> &getSeismogram(IndexType type) { return seismo[type]; }
+            Seismogram<ValueType> const &getSeismogram(IndexType type) const { return seismo[type]; }
+            IndexType getNumTracesTotal() const;
+            IndexType getNumTracesGlobal(IndexType type) const { return seismo[type].getNumTraces(); }
+            void setIsSeismic(bool s) { isSeismic = s; }
+            bool getIsSeismic() const { return isSeismic; }
+            void setDT(ValueType dt);
+            void setSeismoDT(ValueType dt);
+            void resetData();
+            void normalize(IndexType normalizeTraces);
+            bool isFinite() const;
+            void write(IndexType seismogramFormat, std::string const &filename) const;
+
+          private:
+            std::array<Seismogram<ValueType>, NUM_ELEMENTS_SEISMOGRAMTYPE> seismo;
+            bool isSeismic = true;
+        };
+
+        //! coordinates + types -> per-type 1-D coordinate lists (AcquisitionGeometry.hpp:76-120, AcquisitionGeometry.cpp:18-76)
+        template <typename ValueType> class AcquisitionGeometry
+        {
+          public:
+            SeismogramHandler<ValueType> &getSeismogramHandler() { return seismograms; }
+            SeismogramHandler<ValueType> const &getSeismogramHandler() const { return seismograms; }
+            IndexType getNumTracesGlobal() const { return (IndexType)coordinates1D.size(); }
+            std::vector<IndexType> const &get1DCoordinates() const { return coordinates1D; }
+            std::vector<IndexType> const &getSeismogramTypes() const { return types; }
+            unsigned long getVersion() const { return version; } // bumped whenever the geometry or the signals change
+
+          protected:
+            template <typename Settings> void setAcquisition(std::vector<Settings> const &allSettings, Coordinates<ValueType> const &modelCoordinates, IndexType NT);
+            SeismogramHandler<ValueType> seismograms;
+            std::vector<IndexType> coordinates1D, types; // in file order; types 1..4
+            std::vector<IndexType> traceOfEntry;        // row inside the seismogram of its type
+            unsigned long version = 0;
+        };
+
+        template <typename ValueType> class Sources : public AcquisitionGeometry<ValueType>
+        {
+          public:
+            void getAcquisitionSettings(Configuration::Configuration const &config);
+            std::vector<sourceSettings<ValueType>> const &getSourceSettings() const { return allSourceSettings; }
+            //! sources of one shot: geometry + signals (Sources.cpp:16-46, 99-145)
+            void init(std::vector<sourceSettings<ValueType>> const &shotSettings, Configuration::Configuration const &config, Coordinates<ValueType> const &modelCoordinates);
+            IndexType getRowOfEntry(IndexType k) const { return this->traceOfEntry[k]; }
+
+          private:
+            std::vector<sourceSettings<ValueType>> allSourceSettings;
+        };
+
+        template <typename ValueType> class Receivers : public AcquisitionGeometry<ValueType>
+        {
+          public:
+            void init(Configuration::Configuration const &config, Coordinates<ValueType> const &modelCoordinates);                       // <ReceiverFilename>.txt
+            void init(Configuration::Configuration const &config, Coordinates<ValueType> const &modelCoordinates, IndexType shotNumber); // .shot_<n>.txt
+            void init(std::vector<receiverSettings> const &allSettings, Configuration::Configuration const &config, Coordinates<ValueType> const &modelCoordinates);
+            IndexType getRowOfEntry(IndexType k) const { return this->traceOfEntry[k]; }
+        };
+    }
+}

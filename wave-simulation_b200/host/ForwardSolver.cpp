@@ -1,0 +1,186 @@
+#include "ForwardSolver.hpp"
+#include "../../include/wavesim.h"
+#include <algorithm>
+#include <cstring>
+
+using namespace KITGPI;
+
+namespace
+{
+    void check(int rc)
+    {
+        if (rc != WS_OK)
+            COMMON_THROWEXCEPTION(ws_last_error())
+    }
+    int eqCode(std::string const &t)
+    {
+        const char *names[] = {"acoustic", "elastic", "viscoelastic", "sh", "viscosh", "tmem", "emem", "viscotmem", "viscoemem"};
+        for (int k = 0; k < 9; k++)
+            if (t == names[k])
+                return k;
+        COMMON_THROWEXCEPTION("Unkown type")
+    }
+    ws_desc makeDesc(Configuration::Configuration const &config, std::string const &dimension, std::string const &type, int device)
+    {
+        ws_desc d;
+        std::memset(&d, 0, sizeof(d));
+        d.dim = dimension == "3d" ? 3 : 2;
+        d.eq = eqCode(type);
+        d.nx = config.get<IndexType>("NX");
+        d.ny = config.get<IndexType>("NY");
+        d.nz = d.dim == 3 ? config.get<IndexType>("NZ") : 1;
+        d.dh = config.get<ValueType>("DH");
+        d.dt = config.get<ValueType>("DT");
+        d.nt = Common::time2index(config.get<ValueType>("T"), d.dt); // Simulation.cpp:304
+        d.fd_order = config.get<IndexType>("spatialFDorder");
+        d.edge_policy = config.getAndCatch("useStencilMatrix", 0) ? 0 : 1;
+        d.free_surface = config.get<IndexType>("FreeSurface") == 1 ? 1 : 0;
+        d.damping = config.get<IndexType>("DampingBoundary");
+        d.boundary_width = config.getAndCatch("BoundaryWidth", 0);
+        d.damping_coeff = config.getAndCatch("DampingCoeff", ValueType(0));
+        d.vmax_cpml = config.getAndCatch("VMaxCPML", ValueType(0));
+        d.fc_cpml = config.getAndCatch("CenterFrequencyCPML", ValueType(0));
+        d.npower = config.getAndCatch("NPower", ValueType(0));
+        const bool visco = type.compare(0, 5, "visco") == 0;
+        d.n_relax = visco ? config.get<IndexType>("numRelaxationMechanisms") : 0;
+        const char *keys[4] = {"relaxationFrequency", "relaxationFrequency2", "relaxationFrequency3", "relaxationFrequency4"};
+        for (int l = 0; l < d.n_relax && l < 4; l++)
+            d.relax_freq[l] = config.get<ValueType>(keys[l]);
+        d.exact_arith = config.getAndCatch("exactArithmetic", 0); // B200 extension: reference operation order, no FMA contraction
+        d.kernel_variant = config.getAndCatch("kernelVariant", 0);
+        d.rank = 0;
+        d.nranks = 1;
+        d.device = device;
+        return d;
+    }
+}
+
+template <typename ValueType> ForwardSolver::ForwardSolver<ValueType>::ForwardSolver(std::string const &dim, std::string const &type) : dimension(dim), equationType(type)
+{
+    SCAI_ASSERT_ERROR(dimension == "2d" || dimension == "3d", "Unkown dimension")
+    const int eq = eqCode(type);
+    // ForwardSolverFactory.cpp:4-66: sh, viscosh, tmem and viscotmem exist in 2D only
+    if (dimension == "3d" && (eq == WS_EQ_SH || eq == WS_EQ_VISCOSH || eq == WS_EQ_TMEM || eq == WS_EQ_VISCOTMEM))
+        COMMON_THROWEXCEPTION("Unkown type")
+}
+
+template <typename ValueType> ForwardSolver::ForwardSolver<ValueType>::~ForwardSolver()
+{
+    if (h)
+        ws_destroy(h);
+}
+
+template <typename ValueType>
+ValueType ForwardSolver::ForwardSolver<ValueType>::estimateMemory(Configuration::Configuration const &config, Acquisition::Coordinates<ValueType> const &)
+{
+    ws_desc d = makeDesc(config, dimension, equationType, deviceId);
+    return (ValueType)(ws_estimate_memory(&d) / 1024.0 / 1024.0);
+}
+
+template <typename ValueType>
+void ForwardSolver::ForwardSolver<ValueType>::initForwardSolver(Configuration::Configuration const &config, Derivatives::Derivatives<ValueType> &derivatives,
+                                                                Wavefields::Wavefields<ValueType> &wavefield, Modelparameter::Modelparameter<ValueType> &model,
+                                                                Acquisition::Coordinates<ValueType> const &modelCoordinates, ValueType DT)
+{
+    SCAI_ASSERT_ERROR(derivatives.getSpatialFDorder() == config.get<IndexType>("spatialFDorder"), "Derivatives::init must be called with the same configuration")
+    SCAI_ASSERT_ERROR(model.getEquationType() == equationType && wavefield.getEquationType() == equationType, "model / wavefield type differs from the solver type")
+    if (h) {
+        ws_destroy(h);
+        h = nullptr;
+    }
+    ws_desc d = makeDesc(config, dimension, equationType, deviceId);
+    d.dt = DT;
+    check(ws_create(&d, &h));
+    NT = d.nt;
+    nLocal = (size_t)modelCoordinates.getNGridpoints();
+    for (auto const &kv : model.getRawParameters())
+        check(ws_set_material(h, kv.first.c_str(), kv.second.data(), kv.second.size()));
+    wavefield.init(d.n_relax);
+    wavefield.bind(h, nLocal);
+    model.bind(h, nLocal);
+    srcVersion = recVersion = ~0ul;
+}
+
+template <typename ValueType> void ForwardSolver::ForwardSolver<ValueType>::prepareForModelling(Modelparameter::Modelparameter<ValueType> const &, ValueType)
+{
+    SCAI_ASSERT_ERROR(h, "initForwardSolver must be called before prepareForModelling")
+    check(ws_prepare(h));
+}
+
+template <typename ValueType> void ForwardSolver::ForwardSolver<ValueType>::resetCPML()
+{
+    SCAI_ASSERT_ERROR(h, "initForwardSolver must be called first")
+    check(ws_reset(h)); // memory variables (and wavefields, traces: both are re-initialised per shot anyway)
+}
+
+template <typename ValueType>
+void ForwardSolver::ForwardSolver<ValueType>::bindAcquisition(Acquisition::Receivers<ValueType> &receiver, Acquisition::Sources<ValueType> const &sources)
+{
+    if (srcObj != &sources || srcVersion != sources.getVersion()) {
+        auto const &types = sources.getSeismogramTypes();
+        auto const &idx = sources.get1DCoordinates();
+        std::vector<ValueType> signals((size_t)types.size() * NT);
+        for (size_t k = 0; k < types.size(); k++) {
+            auto const &sg = sources.getSeismogramHandler().getSeismogram(types[k] - 1);
+            SCAI_ASSERT_ERROR(sg.getNumSamples() == NT, "source signals must hold NT samples")
+            std::memcpy(&signals[k * NT], &sg.getData()[(size_t)sources.getRowOfEntry((IndexType)k) * NT], sizeof(ValueType) * NT);
+        }
+        check(ws_set_sources(h, (int32_t)types.size(), types.data(), idx.data(), signals.data()));
+        srcObj = &sources;
+        srcVersion = sources.getVersion();
+    }
+    if (recObj != &receiver || recVersion != receiver.getVersion()) {
+        check(ws_set_receivers(h, (int32_t)receiver.getSeismogramTypes().size(), receiver.getSeismogramTypes().data(), receiver.get1DCoordinates().data()));
+        recObj = &receiver;
+        recVersion = receiver.getVersion();
+    }
+}
+
+template <typename ValueType> void ForwardSolver::ForwardSolver<ValueType>::fetchSeismograms(Acquisition::Receivers<ValueType> &receiver)
+{
+    auto const &types = receiver.getSeismogramTypes();
+    std::vector<ValueType> all((size_t)types.size() * NT);
+    check(ws_get_seismogram(h, all.data()));
+    for (size_t k = 0; k < types.size(); k++) {
+        auto &sg = receiver.getSeismogramHandler().getSeismogram(types[k] - 1);
+        std::memcpy(&sg.getData()[(size_t)receiver.getRowOfEntry((IndexType)k) * NT], &all[k * NT], sizeof(ValueType) * NT);
+    }
+}
+
+template <typename ValueType>
+void ForwardSolver::ForwardSolver<ValueType>::run(Acquisition::Receivers<ValueType> &receiver, Acquisition::Sources<ValueType> const &sources,
+                                                  Modelparameter::Modelparameter<ValueType> const &, Wavefields::Wavefields<ValueType> &,
+                                                  Derivatives::Derivatives<ValueType> const &, IndexType t)
+{
+    SCAI_ASSERT_ERROR(h, "initForwardSolver must be called before run")
+    bindAcquisition(receiver, sources);
+    check(ws_step(h, t));
+    if (t == NT - 1)
+        fetchSeismograms(receiver);
+}
+
+template <typename ValueType>
+void ForwardSolver::ForwardSolver<ValueType>::run(Acquisition::Receivers<ValueType> &receiver, Acquisition::Sources<ValueType> const &sources, IndexType t0, IndexType t1)
+{
+    SCAI_ASSERT_ERROR(h, "initForwardSolver must be called before run")
+    bindAcquisition(receiver, sources);
+    check(ws_run(h, t0, t1));
+    if (t1 == NT)
+        fetchSeismograms(receiver);
+}
+
+template <typename ValueType> void ForwardSolver::ForwardSolver<ValueType>::sync()
+{
+    if (h)
+        check(ws_sync(h));
+}
+
+template <typename ValueType> typename ForwardSolver::ForwardSolver<ValueType>::ForwardSolverPtr ForwardSolver::Factory<ValueType>::Create(std::string dimension, std::string type)
+{
+    std::transform(dimension.begin(), dimension.end(), dimension.begin(), ::tolower);
+    std::transform(type.begin(), type.end(), type.begin(), ::tolower);
+    return std::make_shared<ForwardSolver<ValueType>>(dimension, type);
+}
+
+template class ForwardSolver::ForwardSolver<float>;
+template class ForwardSolver::Factory<float>;

@@ -1,0 +1,143 @@
+#include "Modelparameter.hpp"
+#include "../../include/wavesim.h"
+#include "IO.hpp"
+#include <algorithm>
+
+using namespace KITGPI;
+
+namespace
+{
+    struct ParDef {
+        const char *name;   // C-ABI / reference getter name
+        const char *suffix; // file suffix after ModelFilename
+        const char *key;    // configuration key of the homogeneous model
+    };
+    const ParDef kVp = {"velocityP", "vp", "velocityP"}, kVs = {"velocityS", "vs", "velocityS"}, kRho = {"density", "density", "rho"},
+                 kTauP = {"tauP", "tauP", "tauP"}, kTauS = {"tauS", "tauS", "tauS"}, kMu = {"magneticPermeability", "mur", "mur"},
+                 kSig = {"electricConductivity", "sigma", "sigma"}, kEps = {"dielectricPermittivity", "epsilonr", "epsilonr"},
+                 kTSig = {"tauElectricConductivity", "tauSigmar", "tauSigmar"}, kTEps = {"tauDielectricPermittivity", "tauEpsilon", "tauEpsilon"};
+
+    std::vector<ParDef> parsOf(std::string const &t)
+    {
+        if (t == "acoustic") return {kVp, kRho};
+        if (t == "elastic") return {kVp, kVs, kRho};
+        if (t == "viscoelastic") return {kVp, kVs, kRho, kTauP, kTauS};
+        if (t == "sh") return {kVs, kRho};
+        if (t == "viscosh") return {kVs, kRho, kTauS};
+        if (t == "tmem" || t == "emem") return {kMu, kSig, kEps};
+        if (t == "viscotmem" || t == "viscoemem") return {kMu, kSig, kEps, kTSig, kTEps};
+        COMMON_THROWEXCEPTION("Unkown type: " << t)
+    }
+}
+
+template <typename ValueType> Modelparameter::Modelparameter<ValueType>::Modelparameter(std::string const &type) : equationType(type)
+{
+    seismic = Common::checkEquationType(type);
+    parsOf(type);
+}
+
+template <typename ValueType>
+void Modelparameter::Modelparameter<ValueType>::init(Configuration::Configuration const &config, Acquisition::Coordinates<ValueType> const &modelCoordinates)
+{
+    const IndexType modelRead = config.get<IndexType>("ModelRead");
+    SCAI_ASSERT_ERROR(modelRead == 0 || modelRead == 1, "ModelRead=" << modelRead << ": variable-grid models are not available in the B200 path")
+    const bool visco = equationType.compare(0, 5, "visco") == 0;
+    relaxationFrequency.clear();
+    if (visco) {
+        const IndexType L = config.get<IndexType>("numRelaxationMechanisms");
+        SCAI_ASSERT_ERROR(L >= 1 && L <= 4, "numRelaxationMechanisms more than 4 is not available here!")
+        const char *keys[4] = {"relaxationFrequency", "relaxationFrequency2", "relaxationFrequency3", "relaxationFrequency4"};
+        for (IndexType l = 0; l < L; l++)
+            relaxationFrequency.push_back(config.get<ValueType>(keys[l]));
+    }
+    const size_t N = (size_t)modelCoordinates.getNGridpoints();
+    raw.clear();
+    for (auto const &p : parsOf(equationType)) {
+        std::vector<ValueType> v(N);
+        if (modelRead == 1) {
+            SCAI_ASSERT_ERROR(seismic || !visco, "ModelRead=1 for visco-EM models (effective -> static conversion, ViscoTMEM.cpp:320-350) is not available yet")
+            IO::readVector(v, config.get<std::string>("ModelFilename") + "." + p.suffix, config.get<IndexType>("FileFormat"));
+        } else
+            std::fill(v.begin(), v.end(), config.get<ValueType>(p.key));
+        // EM inputs are relative: scale to SI (TMEM.cpp:262-292, ViscoTMEM.cpp:274-293)
+        ValueType scale = 1;
+        if (std::string(p.name) == "magneticPermeability") scale = MagneticPermeabilityVacuum;
+        if (std::string(p.name) == "dielectricPermittivity") scale = DielectricPermittivityVacuum;
+        if (std::string(p.name) == "tauElectricConductivity") scale = (ValueType)(1.0 / (2.0 * M_PI * config.get<ValueType>("CenterFrequencyCPML")));
+        if (scale != 1)
+            for (auto &x : v)
+                x *= scale;
+        raw[p.name] = std::move(v);
+    }
+    dirtyFlag = true;
+}
+
+template <typename ValueType> void Modelparameter::Modelparameter<ValueType>::init(std::string const &name, std::vector<ValueType> const &values)
+{
+    raw[name] = values;
+    dirtyFlag = true;
+}
+
+template <typename ValueType> void Modelparameter::Modelparameter<ValueType>::write(std::string filename, IndexType fileFormat) const
+{
+    for (auto const &p : parsOf(equationType)) {
+        SCAI_ASSERT_ERROR(seismic, "Modelparameter::write is implemented for seismic models")
+        IO::writeVector(at(p.name), filename + "." + p.suffix, fileFormat);
+    }
+}
+
+template <typename ValueType> std::vector<ValueType> const &Modelparameter::Modelparameter<ValueType>::at(std::string const &name) const
+{
+    auto it = raw.find(name);
+    if (it == raw.end())
+        COMMON_THROWEXCEPTION("There is no " << name << " parameter in an " << equationType << " modelling")
+    return it->second;
+}
+
+template <typename ValueType> std::vector<ValueType> Modelparameter::Modelparameter<ValueType>::getParameter(std::string const &name) const
+{
+    SCAI_ASSERT_ERROR(h, "The model is not bound to a forward solver yet (initForwardSolver)")
+    std::vector<ValueType> out(n);
+    if (ws_get_material(h, name.c_str(), out.data(), out.size()) != WS_OK)
+        COMMON_THROWEXCEPTION(ws_last_error())
+    return out;
+}
+
+template <typename ValueType> ValueType Modelparameter::Modelparameter<ValueType>::getMaxVelocity() const
+{
+    if (seismic) {
+        auto const &v = (equationType == "sh" || equationType == "viscosh") ? getVelocityS() : getVelocityP();
+        return *std::max_element(v.begin(), v.end());
+    }
+    auto const &e = getDielectricPermittivity(), &m = getMagneticPermeability();
+    ValueType vmax = 0;
+    for (size_t i = 0; i < e.size(); i++)
+        vmax = std::max(vmax, (ValueType)(1.0 / std::sqrt((double)e[i] * m[i])));
+    return vmax;
+}
+
+template <typename ValueType> ValueType Modelparameter::Modelparameter<ValueType>::getMinVelocity() const
+{
+    if (seismic) {
+        auto const &v = equationType == "acoustic" ? getVelocityP() : getVelocityS();
+        ValueType vmin = 3e8f;
+        for (ValueType x : v)
+            if (x > 0)
+                vmin = std::min(vmin, x);
+        return vmin;
+    }
+    auto const &e = getDielectricPermittivity(), &m = getMagneticPermeability();
+    ValueType vmin = 3e8f;
+    for (size_t i = 0; i < e.size(); i++)
+        vmin = std::min(vmin, (ValueType)(1.0 / std::sqrt((double)e[i] * m[i])));
+    return vmin;
+}
+
+template <typename ValueType> typename Modelparameter::Modelparameter<ValueType>::ModelparameterPtr Modelparameter::Factory<ValueType>::Create(std::string type)
+{
+    std::transform(type.begin(), type.end(), type.begin(), ::tolower);
+    return std::make_shared<Modelparameter<ValueType>>(type); // throws "Unkown type" for anything else
+}
+
+template class Modelparameter::Modelparameter<float>;
+template class Modelparameter::Factory<float>;

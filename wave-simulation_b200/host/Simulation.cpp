@@ -1,0 +1,193 @@
+// Simulation.cpp — forward-modelling driver with the flow of the reference's src/Simulation.cpp:36-574:
+// configuration -> factories -> acquisition -> model -> forward solver -> loop over shots -> loop over time steps ->
+// seismograms.  Runs the `par/` configurations unchanged on the CUDA library (include/wavesim.h); NumShotDomains maps
+// to GPUs: every shot domain is one GPU working on its block of the shots (Simulation.cpp:116-121, 369).
+#include "Acquisition.hpp"
+#include "CheckParameter.hpp"
+#include "Configuration.hpp"
+#include "Coordinates.hpp"
+#include "Derivatives.hpp"
+#include "ForwardSolver.hpp"
+#include "Modelparameter.hpp"
+#include "Wavefields.hpp"
+#include "../../include/wavesim.h"
+#include <chrono>
+#include <mutex>
+#include <thread>
+
+using namespace KITGPI;
+
+namespace
+{
+    double now()
+    {
+        return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    }
+    std::mutex printMutex;
+}
+
+// one shot domain = one GPU: shots [lb, ub) of the unique shot list (dmemo::blockDistribution(numshots, commInterShot))
+static void runShotDomain(Configuration::Configuration const &config, IndexType shotDomain, IndexType device, IndexType lb, IndexType ub,
+                          std::vector<Acquisition::sourceSettings<ValueType>> const &sourceSettings, std::vector<IndexType> const &uniqueShotNos,
+                          Modelparameter::Modelparameter<ValueType>::ModelparameterPtr model, Acquisition::Coordinates<ValueType> const &modelCoordinates, double globalStart_t,
+                          std::string *error)
+{
+    try {
+        std::string dimension = config.get<std::string>("dimension"), equationType = config.get<std::string>("equationType");
+        std::transform(dimension.begin(), dimension.end(), dimension.begin(), ::tolower);
+        std::transform(equationType.begin(), equationType.end(), equationType.begin(), ::tolower);
+        const ValueType DT = config.get<ValueType>("DT");
+        const IndexType tStepEnd = Common::time2index(config.get<ValueType>("T"), DT);
+        const IndexType numshots = (IndexType)uniqueShotNos.size();
+
+        auto derivatives = ForwardSolver::Derivatives::Factory<ValueType>::Create(dimension);
+        auto wavefields = Wavefields::Factory<ValueType>::Create(dimension, equationType);
+        auto solver = ForwardSolver::Factory<ValueType>::Create(dimension, equationType);
+        solver->setDevice(device);
+        derivatives->init(config);
+
+        // every domain works on its own copy of the model object (binding to its solver); the raw vectors are shared data
+        Modelparameter::Modelparameter<ValueType> modelLocal(*model);
+        double start_t = now();
+        solver->initForwardSolver(config, *derivatives, *wavefields, modelLocal, modelCoordinates, DT);
+        modelLocal.prepareForModelling();
+        solver->prepareForModelling(modelLocal, DT);
+        HOST_PRINT("", "Finished initializing forward solver of shot domain " << shotDomain << " in " << now() - start_t << " sec.\n\n")
+
+        Acquisition::Sources<ValueType> sources;
+        Acquisition::Receivers<ValueType> receivers;
+        if (config.get<IndexType>("useReceiversPerShot") == 0)
+            receivers.init(config, modelCoordinates);
+
+        const IndexType snapType = config.get<IndexType>("snapType");
+        const double tInit = now() - globalStart_t;
+        for (IndexType shotInd = lb; shotInd < ub; shotInd++) {
+            const IndexType shotNumber = uniqueShotNos[shotInd];
+            std::vector<Acquisition::sourceSettings<ValueType>> sourceSettingsShot;
+            Acquisition::createSettingsForShot(sourceSettingsShot, sourceSettings, shotNumber);
+            sources.init(sourceSettingsShot, config, modelCoordinates);
+            CheckParameter::checkNumericalArtefactsAndInstabilities<ValueType>(config, sourceSettingsShot, modelLocal, modelCoordinates, shotNumber);
+            if (config.getAndCatch("writeSource", false))
+                sources.getSeismogramHandler().write(config.get<IndexType>("SeismogramFormat"), config.get<std::string>("writeSourceFilename") + ".shot_" + std::to_string(shotNumber));
+            if (config.get<IndexType>("useReceiversPerShot") != 0)
+                receivers.init(config, modelCoordinates, shotNumber);
+            receivers.getSeismogramHandler().resetData();
+
+            {
+                std::lock_guard<std::mutex> lock(printMutex);
+                HOST_PRINT("Start time stepping for shot number " << shotNumber << " (domain " << shotDomain << ", index " << shotInd + 1 << " of " << numshots << ")\n",
+                           "\nTotal Number of time steps: " << tStepEnd << "\n")
+            }
+            start_t = now();
+            wavefields->resetWavefields();
+            double start_t2 = start_t;
+            for (IndexType tStep = 0; tStep < tStepEnd; tStep++) {
+                if ((tStep - 1) % 100 == 0)
+                    start_t2 = now();
+                solver->run(receivers, sources, modelLocal, *wavefields, *derivatives, tStep);
+                if (tStep % 100 == 0 && tStep != 0 && verbose) {
+                    solver->sync(); // the steps are enqueued asynchronously: time what has actually run
+                    const double end_t2 = now();
+                    std::lock_guard<std::mutex> lock(printMutex);
+                    HOST_PRINT("", "Calculated " << tStep << " time steps in shot  " << shotNumber << " at t = " << end_t2 - globalStart_t << "\nLast 100 timesteps calculated in "
+                                                 << end_t2 - start_t2 << " sec. - Estimated runtime (Simulation/total): " << (int)((tStepEnd / 100) * (end_t2 - start_t2)) << " / "
+                                                 << (int)((tStepEnd / 100) * (end_t2 - start_t2) + tInit) << " sec.\n\n")
+                }
+                if (snapType > 0) {
+                    const IndexType tFirst = Common::time2index(config.get<ValueType>("tFirstSnapshot"), DT), tLast = Common::time2index(config.get<ValueType>("tlastSnapshot"), DT),
+                                    tInc = Common::time2index(config.get<ValueType>("tincSnapshot"), DT);
+                    if (tStep >= tFirst && tStep <= tLast && tInc > 0 && (tStep - tFirst) % tInc == 0)
+                        wavefields->write(snapType, config.get<std::string>("WavefieldFileName") + ".shot_" + std::to_string(shotNumber), tStep, config.get<IndexType>("FileFormat"));
+                }
+            }
+            solver->sync();
+            // Simulation.cpp:519: every value of the wavefields and of the seismograms must be finite
+            SCAI_ASSERT_ERROR(wavefields->isFinite() && receivers.getSeismogramHandler().isFinite(), "Infinite or NaN value in seismogram or/and velocity wavefield!")
+            solver->resetCPML();
+            {
+                std::lock_guard<std::mutex> lock(printMutex);
+                HOST_PRINT("Finished time stepping for shot number: " << shotNumber << " in " << now() - start_t << " sec.\n")
+            }
+            receivers.getSeismogramHandler().normalize(config.get<IndexType>("normalizeTraces"));
+            receivers.getSeismogramHandler().write(config.get<IndexType>("SeismogramFormat"), config.get<std::string>("SeismogramFilename") + ".shot_" + std::to_string(shotNumber));
+        }
+    } catch (std::exception const &e) {
+        *error = e.what();
+    }
+}
+
+int main(int argc, const char *argv[])
+{
+    const double globalStart_t = now();
+    if (argc != 2) {
+        std::cout << "\n\nNo configuration file given!\n\n" << std::endl;
+        return 2;
+    }
+    try {
+        Configuration::Configuration config(argv[1]);
+        verbose = config.getAndCatch("verbose", 0);
+        std::string dimension = config.get<std::string>("dimension"), equationType = config.get<std::string>("equationType");
+        std::transform(dimension.begin(), dimension.end(), dimension.begin(), ::tolower);
+        std::transform(equationType.begin(), equationType.end(), equationType.begin(), ::tolower);
+        SCAI_ASSERT_ERROR(config.getAndCatch("useStreamConfig", 0) == 0, "useStreamConfig=1 (model cut-outs per shot) is not available in the B200 host layer")
+
+        HOST_PRINT("\nWAVE-Simulation " << dimension << " " << equationType << " - LAMA-free host layer on " << ws_version() << "\n\n")
+        if (verbose)
+            config.print();
+
+        const IndexType nDevices = ws_device_count();
+        SCAI_ASSERT_ERROR(nDevices > 0, "no CUDA device available (there is no CPU fallback)")
+
+        Acquisition::Coordinates<ValueType> modelCoordinates(config);
+        const IndexType numRelaxationMechanisms = config.getAndCatch("numRelaxationMechanisms", 0);
+        (void)numRelaxationMechanisms;
+
+        /* memory estimation (Simulation.cpp:168-185) */
+        {
+            auto solver = ForwardSolver::Factory<ValueType>::Create(dimension, equationType);
+            HOST_PRINT(" ========== " << dimension << " " << equationType << " Memory Estimation: ===========\n\n")
+            HOST_PRINT(" Wavefields, model and boundary slabs in HBM: " << solver->estimateMemory(config, modelCoordinates) << " MB per shot domain (derivatives are matrix-free: 0 MB)\n\n")
+        }
+
+        /* acquisition geometry (Simulation.cpp:233-282) */
+        Acquisition::Sources<ValueType> sources;
+        sources.getAcquisitionSettings(config);
+        std::vector<Acquisition::sourceSettings<ValueType>> sourceSettings = sources.getSourceSettings();
+        CheckParameter::checkAcquisition<ValueType>(sourceSettings, modelCoordinates, "source");
+        std::vector<IndexType> uniqueShotNos;
+        Acquisition::calcuniqueShotNo(uniqueShotNos, sourceSettings);
+        const IndexType numshots = (IndexType)uniqueShotNos.size();
+        SCAI_ASSERT_ERROR(config.getAndCatch("useSourceEncode", 0) == 0 && config.getAndCatch("useRandomSource", 0) == 0, "source encoding / random shots belong to the inversion workflow")
+
+        /* model (Simulation.cpp:284-295) */
+        double start_t = now();
+        auto model = Modelparameter::Factory<ValueType>::Create(equationType);
+        model->init(config, modelCoordinates);
+        HOST_PRINT("", "Finished initializing model in " << now() - start_t << " sec.\n\n")
+
+        /* shot domains: block distribution of the shots over min(NumShotDomains, GPUs) domains */
+        IndexType numShotDomains = std::max<IndexType>(1, config.getAndCatch("NumShotDomains", 1));
+        numShotDomains = std::min(numShotDomains, std::min(numshots, nDevices));
+        std::vector<std::thread> threads;
+        std::vector<std::string> errors(numShotDomains);
+        for (IndexType dom = 0; dom < numShotDomains; dom++) {
+            const IndexType base = numshots / numShotDomains, rem = numshots % numShotDomains;
+            const IndexType lb = dom * base + std::min(dom, rem), ub = lb + base + (dom < rem ? 1 : 0);
+            if (numShotDomains == 1)
+                runShotDomain(config, dom, dom, lb, ub, sourceSettings, uniqueShotNos, model, modelCoordinates, globalStart_t, &errors[dom]);
+            else
+                threads.emplace_back(runShotDomain, std::cref(config), dom, dom, lb, ub, std::cref(sourceSettings), std::cref(uniqueShotNos), model, std::cref(modelCoordinates),
+                                     globalStart_t, &errors[dom]);
+        }
+        for (auto &t : threads)
+            t.join();
+        for (auto const &e : errors)
+            if (!e.empty())
+                COMMON_THROWEXCEPTION(e)
+        HOST_PRINT("\nTotal runtime of WAVE-Simulation: " << now() - globalStart_t << " sec.\nWAVE-Simulation finished!\n\n")
+    } catch (std::exception const &e) {
+        std::cerr << "\nERROR: " << e.what() << std::endl;
+        return 1;
+    }
+    return 0;
+}

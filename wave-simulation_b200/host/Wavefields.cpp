@@ -1,0 +1,114 @@
+#include "Wavefields.hpp"
+#include "../../include/wavesim.h"
+#include "IO.hpp"
+#include <algorithm>
+
+using namespace KITGPI;
+
+template <typename ValueType> Wavefields::Wavefields<ValueType>::Wavefields(std::string const &dimension, std::string const &type) : equationType(type)
+{
+    SCAI_ASSERT_ERROR(dimension == "2d" || dimension == "3d", "Unkown dimension")
+    numDimension = dimension == "3d" ? 3 : 2;
+    const bool d3 = numDimension == 3;
+    if (type == "acoustic") {
+        first = d3 ? std::vector<std::string>{"VX", "VY", "VZ"} : std::vector<std::string>{"VX", "VY"};
+        second = {"P"};
+    } else if (type == "elastic" || type == "viscoelastic") {
+        first = d3 ? std::vector<std::string>{"VX", "VY", "VZ"} : std::vector<std::string>{"VX", "VY"};
+        second = d3 ? std::vector<std::string>{"Sxx", "Syy", "Szz", "Sxy", "Sxz", "Syz"} : std::vector<std::string>{"Sxx", "Syy", "Sxy"};
+    } else if (type == "sh" || type == "viscosh") {
+        SCAI_ASSERT_ERROR(!d3, "Unkown type") // WavefieldsFactory.cpp: SH exists in 2D only
+        first = {"VZ"};
+        second = {"Sxz", "Syz"};
+    } else if (type == "tmem" || type == "viscotmem") {
+        SCAI_ASSERT_ERROR(!d3, "Unkown type")
+        first = {"HX", "HY"};
+        second = {"EZ"};
+    } else if (type == "emem" || type == "viscoemem") {
+        first = d3 ? std::vector<std::string>{"HX", "HY", "HZ"} : std::vector<std::string>{"HZ"};
+        second = d3 ? std::vector<std::string>{"EX", "EY", "EZ"} : std::vector<std::string>{"EX", "EY"};
+    } else
+        COMMON_THROWEXCEPTION("Unkown type")
+    init(0);
+}
+
+template <typename ValueType> void Wavefields::Wavefields<ValueType>::init(IndexType L)
+{
+    memory.clear();
+    const bool d3 = numDimension == 3;
+    for (IndexType l = 1; l <= L; l++) {
+        std::vector<std::string> base;
+        if (equationType == "viscoelastic")
+            base = d3 ? std::vector<std::string>{"Rxx", "Ryy", "Rzz", "Rxy", "Rxz", "Ryz"} : std::vector<std::string>{"Rxx", "Ryy", "Rxy"};
+        else if (equationType == "viscosh")
+            base = {"Rxz", "Ryz"};
+        else if (equationType == "viscotmem")
+            base = {"RZ"};
+        else if (equationType == "viscoemem")
+            base = d3 ? std::vector<std::string>{"RX", "RY", "RZ"} : std::vector<std::string>{"RX", "RY"};
+        for (auto const &b : base)
+            memory.push_back(b + std::to_string(l));
+    }
+    all = first;
+    all.insert(all.end(), second.begin(), second.end());
+    all.insert(all.end(), memory.begin(), memory.end());
+}
+
+template <typename ValueType> void Wavefields::Wavefields<ValueType>::resetWavefields()
+{
+    SCAI_ASSERT_ERROR(h, "The wavefields are not bound to a forward solver yet (initForwardSolver)")
+    if (ws_reset(h) != WS_OK)
+        COMMON_THROWEXCEPTION(ws_last_error())
+}
+
+template <typename ValueType> bool Wavefields::Wavefields<ValueType>::isFinite() const
+{
+    SCAI_ASSERT_ERROR(h, "The wavefields are not bound to a forward solver yet (initForwardSolver)")
+    int32_t flag = 0;
+    if (ws_is_finite(h, &flag) != WS_OK)
+        COMMON_THROWEXCEPTION(ws_last_error())
+    return flag != 0;
+}
+
+template <typename ValueType> std::vector<ValueType> Wavefields::Wavefields<ValueType>::get(std::string const &component) const
+{
+    SCAI_ASSERT_ERROR(h, "The wavefields are not bound to a forward solver yet (initForwardSolver)")
+    std::vector<ValueType> out(n);
+    if (ws_get_wavefield(h, component.c_str(), out.data(), out.size()) != WS_OK)
+        COMMON_THROWEXCEPTION(ws_last_error())
+    return out;
+}
+
+template <typename ValueType> void Wavefields::Wavefields<ValueType>::set(std::string const &component, std::vector<ValueType> const &values)
+{
+    SCAI_ASSERT_ERROR(h, "The wavefields are not bound to a forward solver yet (initForwardSolver)")
+    if (ws_set_wavefield(h, component.c_str(), values.data(), values.size()) != WS_OK)
+        COMMON_THROWEXCEPTION(ws_last_error())
+}
+
+template <typename ValueType> void Wavefields::Wavefields<ValueType>::write(IndexType snapType, std::string baseName, IndexType t, IndexType fileFormat) const
+{
+    const std::string timeStep = std::to_string(static_cast<long long>(t));
+    switch (snapType) {
+    case 1:
+        for (auto const &c : first)
+            IO::writeVector(get(c), baseName + "." + c + "." + timeStep, fileFormat);
+        break;
+    case 2:
+        for (auto const &c : second)
+            IO::writeVector(get(c), baseName + "." + c + "." + timeStep, fileFormat);
+        break;
+    case 3: COMMON_THROWEXCEPTION("snapType 3 (div / curl) is not available in the B200 host layer")
+    default: COMMON_THROWEXCEPTION("Invalid snapType.")
+    }
+}
+
+template <typename ValueType> typename Wavefields::Wavefields<ValueType>::WavefieldPtr Wavefields::Factory<ValueType>::Create(std::string dimension, std::string type)
+{
+    std::transform(dimension.begin(), dimension.end(), dimension.begin(), ::tolower);
+    std::transform(type.begin(), type.end(), type.begin(), ::tolower);
+    return std::make_shared<Wavefields<ValueType>>(dimension, type);
+}
+
+template class Wavefields::Wavefields<float>;
+template class Wavefields::Factory<float>;

@@ -1,0 +1,51 @@
+// Wavefields.hpp — wavefield state (mirror of src/Wavefields/Wavefields.hpp:25-215 and src/WavefieldsEM for the forward path).
+// The state itself lives in HBM inside the solver handle (padded arenas); this class keeps the reference's
+// component names (VX..Sxy, P, Rxx1.., HX..EZ, RX1..), resetWavefields, getRef*-style access (copies through
+// ws_get_wavefield / ws_set_wavefield) and the snapshot writer `<base>.<COMP>.<tStep>.<mtx|lmf>`
+// (Wavefields3Delastic.cpp:62-96; snapType 1 = particle velocities / H, 2 = stresses / pressure / E).
+#pragma once
+#include "Common.hpp"
+#include <memory>
+
+struct ws_solver;
+
+namespace KITGPI
+{
+    namespace Wavefields
+    {
+        template <typename ValueType> class Wavefields
+        {
+          public:
+            typedef std::shared_ptr<Wavefields<ValueType>> WavefieldPtr;
+            Wavefields(std::string const &dimension, std::string const &type);
+
+            //! number of relaxation mechanisms fixes the memory-variable components (Wavefields3Dviscoelastic.cpp init)
+            void init(IndexType numRelaxationMechanisms);
+            void resetWavefields();
+            bool isFinite() const;
+            std::vector<std::string> const &getComponents() const { return all; }
+            std::vector<ValueType> get(std::string const &component) const;       // e.g. "VX", "Sxy", "P", "EZ", "Rxx1"
+            void set(std::string const &component, std::vector<ValueType> const &values);
+            //! snapType 1 or 2 (3 = div/curl belongs to the inversion tool chain and is not available here)
+            void write(IndexType snapType, std::string baseName, IndexType t, IndexType fileFormat) const;
+            std::string getEquationType() const { return equationType; }
+            IndexType getNumDimension() const { return numDimension; }
+
+            void bind(ws_solver *handle, size_t nLocal) { h = handle; n = nLocal; }
+
+          private:
+            std::string equationType;
+            IndexType numDimension;
+            std::vector<std::string> first, second, memory, all; // first half-step fields, second half-step fields, memory variables
+            ws_solver *h = nullptr;
+            size_t n = 0;
+        };
+
+        template <typename ValueType> class Factory
+        {
+          public:
+            //! (2D|3D) x (acoustic, elastic, viscoelastic, sh, viscosh, tmem, emem, viscotmem, viscoemem): WavefieldsFactory.cpp:6
+            static typename Wavefields<ValueType>::WavefieldPtr Create(std::string dimension, std::string type);
+        };
+    }
+}
