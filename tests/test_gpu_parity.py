@@ -166,3 +166,77 @@ def test_fast_kernels_3d_elastic_golden():
     o, s = run_pair(case, 250)
     assert s.uses_fast_kernels()
     assert rel_l2(s.seismogram(), o.seismogram()) <= TOL
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# BASELINE.json configs at (or near) their full sizes: size-independent properties (the oracle would not finish)
+# ---------------------------------------------------------------------------------------------------------------------
+def _layered_2d(nx, ny):
+    k = np.minimum(np.arange(ny) * 8 // ny, 7).astype(np.float32)[:, None]
+    vp = np.broadcast_to(1500.0 + 250.0 * k, (ny, nx)).astype(np.float32)
+    return dict(velocityP=vp.ravel(), velocityS=(vp / np.float32(np.sqrt(3.0))).ravel().astype(np.float32),
+                density=np.broadcast_to(1800.0 + 100.0 * k, (ny, nx)).astype(np.float32).ravel())
+
+
+BIG = [
+    # name, eq, dim, nx, ny, nz, fs, L, dh, dt, fc, vmax, relax
+    ("cfg2-2D-elastic-4096", "elastic", 2, 4096, 4096, 1, 1, 0, 5.0, 5e-4, 10.0, 3500.0, ()),
+    ("cfg3-3D-acoustic-512", "acoustic", 3, 512, 512, 512, 0, 0, 10.0, 1e-3, 10.0, 3500.0, ()),
+    ("cfg4-3D-visco-L2-256", "viscoelastic", 3, 256, 256, 256, 1, 2, 10.0, 8e-4, 10.0, 4550.0, (5.0, 50.0)),
+    ("cfg5-2D-viscotmem-8192x2048", "viscotmem", 2, 8192, 2048, 1, 0, 1, 0.01, 1.5e-11, 1e8, 3e8, (1e8,)),
+]
+
+
+@pytest.mark.parametrize("cfg", BIG, ids=[c[0] for c in BIG])
+def test_baseline_configs_linearity_reset_finite(cfg):
+    """FD order 8 + CPML(20) on the BASELINE.json grids: doubling the source doubles every trace exactly, a reset
+    reproduces the run bit for bit, the wavefields stay finite and the direct wave arrives (non-zero traces)."""
+    from wsharness import make_desc, idx1d, ricker_np
+    from cases import EPS0, MU0
+    name, eq, dim, nx, ny, nz, fs, L, dh, dt, fc, vmax, relax = cfg
+    nt = 48
+    d = make_desc(dim, eq, nx, ny, nz, dh=dh, dt=dt, nt=nt, fd_order=8, edge_policy=0, free_surface=fs, damping=2, boundary_width=20,
+                  vmax_cpml=vmax, fc_cpml=fc, npower=4.0, relax_freq=relax)
+    s = Solver(d)
+    n = nx * ny * nz
+    if eq == "viscotmem":
+        s.set_material("dielectricPermittivity", np.full(n, 4 * EPS0, np.float32))
+        s.set_material("electricConductivity", np.full(n, 1e-3, np.float32))
+        s.set_material("magneticPermeability", np.full(n, MU0, np.float32))
+        s.set_material("tauDielectricPermittivity", np.full(n, 0.05, np.float32))
+        s.set_material("tauElectricConductivity", np.zeros(n, np.float32))
+        stype, rtype, amp = 1, 1, 1.0
+    else:
+        if dim == 2:
+            m = _layered_2d(nx, ny)
+        else:
+            y = (np.arange(ny, dtype=np.float32) / ny)[:, None, None]
+            vp = np.broadcast_to(2000.0 + 1500.0 * y, (ny, nz, nx)).astype(np.float32).ravel()
+            m = dict(velocityP=vp, velocityS=(vp / np.float32(np.sqrt(3.0))).astype(np.float32), density=np.full(n, 2000.0, np.float32))
+        for k in (["velocityP", "density"] if eq == "acoustic" else ["velocityP", "velocityS", "density"]):
+            s.set_material(k, m[k])
+        if eq == "viscoelastic":
+            s.set_material("tauP", np.full(n, 0.1, np.float32))
+            s.set_material("tauS", np.full(n, 0.1, np.float32))
+        stype, rtype, amp = (1, 1, 1e6) if eq == "acoustic" else (3, 3, 1e6)
+    s.prepare()
+    ys = 24
+    sig = ricker_np(nt, dt, fc * 4, amp)[None, :]  # short wavelet: the direct wave reaches the receivers within nt steps
+    s.set_sources([stype], [idx1d(nx // 2, ys, nz // 2, nx, nz)], sig)
+    rec = [idx1d(nx // 2 + 2 + 2 * i, ys, nz // 2, nx, nz) for i in range(8)]
+    s.set_receivers([rtype] * 8, rec)
+    s.reset()
+    s.run(0, nt)
+    a = s.seismogram()
+    assert s.is_finite()
+    assert np.abs(a).max() > 0
+    s.reset()
+    s.run(0, nt)
+    assert np.array_equal(a, s.seismogram())
+    s.set_sources([stype], [idx1d(nx // 2, ys, nz // 2, nx, nz)], 2.0 * sig)
+    s.reset()
+    s.run(0, nt)
+    b = s.seismogram()
+    big = np.abs(a) > 1e-18 * np.abs(a).max()
+    assert np.array_equal((2.0 * a)[big], b[big])
+    s.close()
