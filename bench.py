@@ -32,6 +32,20 @@ def measured_peak():
         return 6650.0, "fallback"
 
 
+def measured_traffic(kernel, nx, ny, nz, damping, free_surface):
+    """DRAM bytes per half-step (dram__bytes_read.sum + dram__bytes_write.sum over the launches of that half-step) from the
+    committed ncu capture of this very configuration (profiles/traffic_1024.json, written by scripts/exp.sh); None for
+    any other configuration."""
+    if (nx, ny, nz, damping, free_surface) != (1024, 1024, 1024, 2, 1):
+        return None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic_1024.json")) as f:
+            t = json.load(f)["per_half_step"]["str" if kernel == 1 else "vel"]
+        return float(t["dram_read_bytes"] + t["dram_write_bytes"])
+    except Exception:
+        return None
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks + throttle reasons during the timed region."""
 
@@ -243,7 +257,8 @@ def main():
                        "l2": "inputs (%.0f GB/GPU of wavefields+model) far exceed the 126 MB L2" % (20 * npts_local * 4 / 1e9),
                        "kernels": "fast-tiled" if s.uses_fast_kernels() else "general", "finite": bool(finite)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "stress half-step" if dom else "velocity half-step", "peak_source": which,
+                         "traffic": measured_traffic(dom, nx, nyl, nz, args.damping, args.free_surface),
+                         "kernel": "stress half-step" if dom else "velocity half-step", "peak_source": which,
                          "ms_velocity": msA, "ms_stress": msB,
                          "whole_step_frac": B_PER_UPDATE["elastic3d"] * npts_local / (ms / K * 1e-3) / 1e9 / peak},
             "cpu_baseline": cpu,

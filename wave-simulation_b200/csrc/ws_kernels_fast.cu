@@ -19,17 +19,7 @@
 //   * CPML memory variables live in compact boundary slabs; their loads are issued before the stage wait.
 // The arithmetic sequence is the one of the general kernels (ws_kernels_general.cuh) in FMA mode, so both produce
 // bit-identical results.
-#include "../../include/wavesim.h"
-#include "ws_launch.hpp"
-
-#include <cuda.h>
-#include <cstdio>
-#include <cstdlib>
-#include <algorithm>
-#include <cmath>
-#include <stdexcept>
-#include <string>
-#include <vector>
+#include "ws_fast_common.cuh"
 
 namespace {
 
@@ -39,33 +29,7 @@ namespace {
 #ifndef WS_NSTS
 #define WS_NSTS 4
 #endif
-constexpr int TX = 64, TZ = 8;
-constexpr int WS_TRACE_MAX = 1 << 16; // thread blocks per half-step covered by the developer trace
-constexpr int NSTV = WS_NSTV, NSTS = WS_NSTS, NSTMAX = NSTV > NSTS ? NSTV : NSTS; // ring depth of the velocity / stress kernel
-constexpr int NGROUPS = 3;
-// planes per trip of the unrolled march: the y queue holds Q + UNR - 1 planes and is shifted by UNR once per trip
-// (full rotation, UNR = Q, needs no moves but its code overflows the instruction cache: measured)
-#ifndef WS_UNR
-#define WS_UNR 1
-#endif
-constexpr int UNR = WS_UNR;
-
-template <int Q> struct Cfg {
-    static constexpr int H = Q / 2;
-    static constexpr int HX = (H <= 4) ? 4 : 8; // x halo rounded to a float4
-    static constexpr int TXH = TX + 2 * HX;
-    static constexpr int TZH = TZ + 2 * H;
-    static constexpr int LXN = TX / 4;
-    static constexpr int NTG = LXN * TZ; // threads per consumer group
-    static constexpr int WPG = NTG / 32; // warps per group
-    // tile sizes (floats); all are multiples of 32 floats = 128 bytes
-    static constexpr int N_P = TX * TZ, N_X = TXH * TZ, N_Z = TX * TZH, N_XZ = TXH * TZH;
-    static_assert(NTG % 32 == 0, "consumer groups must be whole warps");
-    static_assert(N_P % 32 == 0 && N_X % 32 == 0 && N_Z % 32 == 0 && N_XZ % 32 == 0, "TMA destinations must stay 128-byte aligned");
-    static constexpr int QL = Q + UNR - 1; // physical length of the y queue
-    static_assert(Q % UNR == 0 && NSTV % UNR == 0 && NSTS % UNR == 0, "trips must tile the queue prologue and the stage ring");
-};
-
+constexpr int NSTV = WS_NSTV, NSTS = WS_NSTS; // ring depth of the velocity / stress kernel
 // tensor-map slots.  Arena order of the wavefields: vx vy vz sxx sxy syy syz szz sxz; of the model parameters:
 // rix riy riz pi mu muxy muxz muyz (ws_api.cu) — arrays that one box fetches together are neighbours.
 enum {
@@ -88,238 +52,6 @@ enum { AM_RIX = 0, AM_RIY, AM_RIZ, AM_PW, AM_MU, AM_MUXY, AM_MUXZ, AM_MUYZ, AM_C
 // memory-variable arenas (ws_api.cu): x terms {sxx_x, sxy_x, sxz_x | vxx, vyx, vzx}, z terms {sxz_z, syz_z, szz_z | vzz, vxz, vyz};
 // the first three of each belong to the velocity half-step (role order), the last three to the stress half-step
 enum { APS_COUNT = 6 };
-
-__device__ __forceinline__ uint32_t smemU32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbarInit(uint32_t bar, int count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbarExpectTx(uint32_t bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbarArrive(uint32_t bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbarWait(uint32_t bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "LAB_WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE_%=;\n"
-        "bra LAB_WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(bar),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void tmaLoad4D(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2, int c3)
-{
-    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
-                 "l"((unsigned long long)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-                 : "memory");
-}
-
-// same with an L2 eviction-priority hint: operands that no thread block reads again before the grid has been swept
-// (own-point wavefields and model parameters) are fetched evict-first, so that L2 keeps the halo rows shared with the
-// neighbouring tiles and the planes that re-enter as stencil tiles
-__device__ __forceinline__ void tmaLoad4DHint(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2, int c3, uint64_t policy)
-{
-    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6}], [%2], %7;" ::"r"(dst),
-                 "l"((unsigned long long)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(policy)
-                 : "memory");
-}
-__device__ __forceinline__ uint64_t policyEvictFirst()
-{
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-__device__ __forceinline__ uint64_t policyEvictLast()
-{
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-
-struct F4 {
-    float v[4];
-};
-__device__ __forceinline__ F4 ld4(const float *p)
-{
-    const float4 t = *reinterpret_cast<const float4 *>(p);
-    F4 r;
-    r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
-    return r;
-}
-__device__ __forceinline__ F4 ldg4(const float *p)
-{
-    const float4 t = __ldg(reinterpret_cast<const float4 *>(p));
-    F4 r;
-    r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
-    return r;
-}
-__device__ __forceinline__ void st4(float *p, const F4 &a) { *reinterpret_cast<float4 *>(p) = make_float4(a.v[0], a.v[1], a.v[2], a.v[3]); }
-// streaming store: the written plane is not read again before the whole grid has been swept
-__device__ __forceinline__ void st4cs(float *p, const F4 &a) { __stcs(reinterpret_cast<float4 *>(p), make_float4(a.v[0], a.v[1], a.v[2], a.v[3])); }
-__device__ __forceinline__ F4 zero4()
-{
-    F4 r;
-    r.v[0] = r.v[1] = r.v[2] = r.v[3] = 0.0f;
-    return r;
-}
-
-using A = Ar<false>;
-
-// x derivative of 4 consecutive points from a shared-memory row; `row` points at the tile column of x0 - HX
-template <int Q, bool FWD> __device__ __forceinline__ F4 dX(const float *row, const float *__restrict__ c)
-{
-    constexpr int H = Q / 2, HX = Cfg<Q>::HX, NV = (2 * HX + 4) / 4;
-    float w[NV * 4];
-#pragma unroll
-    for (int k = 0; k < NV; k++) {
-        const F4 t = ld4(row + 4 * k);
-        w[4 * k] = t.v[0]; w[4 * k + 1] = t.v[1]; w[4 * k + 2] = t.v[2]; w[4 * k + 3] = t.v[3];
-    }
-    F4 r;
-#pragma unroll
-    for (int p = 0; p < 4; p++) {
-        float acc = 0.0f;
-#pragma unroll
-        for (int j = 0; j < Q; j++)
-            acc = A::madd(c[j], w[HX + p + (FWD ? j - H + 1 : j - H)], acc);
-        r.v[p] = acc;
-    }
-    return r;
-}
-// z derivative: `col` points at (row of z - H, column of x0) of a tile with z halo; rows are LD floats apart
-template <int Q, bool FWD, int LD> __device__ __forceinline__ F4 dZ(const float *col, const float *__restrict__ c)
-{
-    F4 r = zero4();
-#pragma unroll
-    for (int j = 0; j < Q; j++) {
-        const F4 t = ld4(col + (FWD ? j + 1 : j) * LD);
-#pragma unroll
-        for (int p = 0; p < 4; p++)
-            r.v[p] = A::madd(c[j], t.v[p], r.v[p]);
-    }
-    return r;
-}
-// y derivative from the register queue; tap k of the R-th plane of a trip lives in q[k + R]
-template <int Q, int R> __device__ __forceinline__ F4 dY(const F4 (&q)[Cfg<Q>::QL], const float *__restrict__ w)
-{
-    F4 r = zero4();
-#pragma unroll
-    for (int j = 0; j < Q; j++)
-#pragma unroll
-        for (int p = 0; p < 4; p++)
-            r.v[p] = A::madd(w[j], q[j + R].v[p], r.v[p]);
-    return r;
-}
-
-// ---------------------------------------------------------------------------------------------------------------------
-// CPML (CPML.cpp:84-95 applyCPML): psi = b psi + a d ; d = d + psi.  The memory variables live in compact slabs
-// (x: [ly][z][PX], y: [2W][z][x], z: [ly][2W][x]).
-// Row layout of the x slabs (wsPsiXIndex, ws_common.cuh): the low-side entries sit at k' = x, the high-side entries at
-// k' = x - D with D a multiple of 4, and the entries between the two sides are padding.  A thread's 4 points therefore
-// map to ONE aligned float4 of the row, whose entries are either its own layer points or padding nobody else touches:
-// the x term is a branch-free vector update with coefficient rows that are zero on the padding (a = b = 0 leaves the
-// derivative unchanged and stores psi = 0).
-// ---------------------------------------------------------------------------------------------------------------------
-constexpr int PXMAX = 80; // floats per x-slab row the coefficient table in shared memory can hold (W <= 36)
-struct CpT { // per thread, constant over the march
-    int kxv;  // k' of the thread's first point, or -1 if none of its 4 points lies in an x layer
-    int oXA;  // offset of this role's a' row in the shared coefficient table (b' row follows PX later)
-    int kz;
-    float za, zb;
-};
-template <bool CPML> __device__ __forceinline__ void cpSetup(const WsParams &P, CpT &t, bool active, int x0, int z, bool halfX, bool halfZ)
-{
-    t.kxv = -1;
-    t.oXA = 0;
-    t.kz = -1;
-    t.za = t.zb = 0.0f;
-    if (!CPML || !active)
-        return;
-    const int W = P.W;
-    if (x0 < W || x0 + 3 >= P.nx - W)
-        t.kxv = x0 < W ? x0 : x0 - P.psiDX;
-    t.oXA = (halfX ? 2 : 0) * P.psiPitchX;
-    t.kz = wsCpmlIndex(z, P.nz, W);
-    if (t.kz >= 0) {
-        t.za = __ldg((halfZ ? P.cazh : P.caz) + t.kz);
-        t.zb = __ldg((halfZ ? P.cbzh : P.cbz) + t.kz);
-    }
-}
-// one x term: sps = staged slab row of this thread's (ly, z) in shared memory, gps = the same row in the slab, tab = shared
-// coefficient table {a', b', a'half, b'half}[PX]
-__device__ __forceinline__ void cpApplyXv(const CpT &t, const float *sps, float *gps, const float *tab, int PX, F4 &d)
-{
-    const F4 old = ld4(sps + t.kxv), a = ld4(tab + t.oXA + t.kxv), b = ld4(tab + t.oXA + PX + t.kxv);
-    F4 nw;
-#pragma unroll
-    for (int p = 0; p < 4; p++) {
-        float v = A::mul(old.v[p], b.v[p]);
-        v = A::add(v, A::mul(a.v[p], d.v[p]));
-        nw.v[p] = v;
-        d.v[p] = A::add(d.v[p], v);
-    }
-    st4(gps + t.kxv, nw);
-}
-__device__ __forceinline__ void cpApply4(float *ps, const F4 &old, float a, float b, F4 &d)
-{
-    F4 nw;
-#pragma unroll
-    for (int p = 0; p < 4; p++) {
-        float v = A::mul(old.v[p], b);
-        v = A::add(v, A::mul(a, d.v[p]));
-        nw.v[p] = v;
-        d.v[p] = A::add(d.v[p], v);
-    }
-    st4(ps, nw);
-}
-
-// per-plane (run-time) y quantities of the generic step
-template <int Q> struct YDyn {
-    float w[Q]; // y weights of this plane
-    int ky;     // y-CPML slab index or -1
-    float ya, yb;
-};
-// y weights of the first half-step for global plane gy: with a free surface every row comes from the image-method
-// operators (their interior rows are scaled (c/DH)*DT, not c*(DT/DH): Derivatives.cpp:407-425 vs FDTD3D.cpp:211-216)
-template <int Q, bool FWD> __device__ __forceinline__ void loadYWeightsVel(const WsParams &P, int gy, float (&w)[Q])
-{
-    constexpr int H = Q / 2;
-    const int op = P.free_surface == 1 ? (FWD ? OP_YF_FS : OP_YB_FS) : (FWD ? OP_YF : OP_YB);
-    const int row = (P.free_surface == 1 && gy < H) ? max(gy, 0) : H;
-    const float *t = P.tab + ((size_t)op * (2 * H + 1) + row) * (Q + 1) + (FWD ? 1 : 0);
-#pragma unroll
-    for (int j = 0; j < Q; j++)
-        w[j] = __ldg(t + j);
-}
-__device__ __forceinline__ int yCpmlIndex(const WsParams &P, int gy)
-{
-    int ky = wsCpmlIndex(gy, P.gny, P.W);
-    if (P.free_surface != 0 && gy < P.W)
-        ky = -1; // no CPML in the top layer below a free surface (CPML3D.cpp:320-328)
-    return ky;
-}
-// true if planes [gy0, gy1] need the generic step (image-method rows or a y-CPML layer)
-template <bool CPML> __device__ __forceinline__ bool needsGeneric(const WsParams &P, int gy0, int gy1, int H, bool velocity)
-{
-    if (velocity && P.free_surface == 1 && gy0 < H)
-        return true;
-    if (CPML) {
-        if (P.free_surface == 0 && gy0 < P.W)
-            return true;
-        if (gy1 >= P.gny - P.W)
-            return true;
-    }
-    return false;
-}
 
 // ---------------------------------------------------------------------------------------------------------------------
 // shared-memory stage layouts (offsets in floats); the order inside a multi-field box is the arena order
@@ -347,60 +79,10 @@ template <int Q> struct StageS { // stress half-step
     static constexpr uint32_t BYTES_FULL = (uint32_t)SIZE * 4u;
 };
 
-struct Bars {
-    uint64_t full[NSTMAX], empty[NSTMAX];
-    uint64_t xfull, xfree; // stress half-step: derivative exchange between the roles
-};
-
-// consumer bookkeeping shared by both half-steps
-struct Thr {
-    int lx, lz, x0, z, lane;
-    bool active;
-    uint32_t barFull, barEmpty; // shared addresses of full[0] / empty[0]
-    uint32_t barXFull, barXFree;
-    int stride;                 // floats per stage (operands + staged CPML memory variables)
-    const float *cxTab;         // shared coefficient table of the x layers
-    int oPX, oPZ, oPZ2;         // offsets inside a stage of this thread's staged memory variables (x row, z term, 2nd z term)
-};
 // floats of the staged memory variables per stage: 3 x-term slab rows sets (TZ rows of 2W) + 3 z-term tiles
 // (PX = row length of the x-term slabs, 2W rounded up to a 16-byte multiple)
 __host__ __device__ __forceinline__ int psxFloats(int PX) { return (3 * TZ * PX + 31) / 32 * 32; }
 __host__ __device__ __forceinline__ int psiStageFloats(int PX) { return psxFloats(PX) + 3 * TX * TZ; }
-// developer trace (env WS_FAST_TRACE=file): per thread block {start ns, end ns, SM id} of the last launch of each half-step
-__device__ __forceinline__ unsigned long long globalTimer()
-{
-    unsigned long long v;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
-    return v;
-}
-__device__ __forceinline__ void traceStart(const WsParams &P, int pass)
-{
-    if (P.fastTrace && threadIdx.x == 0) {
-        const size_t b = (size_t)pass * WS_TRACE_MAX + (P.fastTileBase + blockIdx.x + (size_t)P.fastNTiles * blockIdx.z);
-        if (b < (size_t)(pass + 1) * WS_TRACE_MAX) {
-            unsigned smid;
-            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-            P.fastTrace[3 * b] = globalTimer();
-            P.fastTrace[3 * b + 1] = 0;
-            P.fastTrace[3 * b + 2] = smid;
-        }
-    }
-}
-__device__ __forceinline__ void traceEnd(const WsParams &P, int pass, int lane)
-{
-    if (P.fastTrace && lane == 0) {
-        const size_t b = (size_t)pass * WS_TRACE_MAX + (P.fastTileBase + blockIdx.x + (size_t)P.fastNTiles * blockIdx.z);
-        if (b < (size_t)(pass + 1) * WS_TRACE_MAX)
-            atomicMax(P.fastTrace + 3 * b + 1, globalTimer());
-    }
-}
-__device__ __forceinline__ void consumerRelease(const Thr &t, int stage)
-{
-    __syncwarp();
-    if (t.lane == 0)
-        mbarArrive(t.barEmpty + 8u * stage);
-}
-
 // ---------------------------------------------------------------------------------------------------------------------
 // velocity half-step (ForwardSolver3Delastic.cpp:181-277)
 //   role 0: vx += rix * (Dxf Sxx + Dyb* Sxy + Dzb Sxz)      role 1: vy += riy * (Dxb Sxy + Dyf* Syy + Dzb Syz)
@@ -419,28 +101,6 @@ struct VRole {
     int opY;                // OP_YF or OP_YB (+ image-method variant) for the generic step
     bool yFwd, halfY;
 };
-
-// x derivative with 9-tap weights (see above); `row` points at the tile column of x0 - HX
-template <int Q> __device__ __forceinline__ F4 dX9(const float *row, const float *__restrict__ c)
-{
-    constexpr int H = Q / 2, HX = Cfg<Q>::HX, NV = (2 * HX + 4) / 4;
-    float w[NV * 4];
-#pragma unroll
-    for (int k = 0; k < NV; k++) {
-        const F4 t = ld4(row + 4 * k);
-        w[4 * k] = t.v[0]; w[4 * k + 1] = t.v[1]; w[4 * k + 2] = t.v[2]; w[4 * k + 3] = t.v[3];
-    }
-    F4 r;
-#pragma unroll
-    for (int p = 0; p < 4; p++) {
-        float acc = 0.0f;
-#pragma unroll
-        for (int j = 0; j <= Q; j++)
-            acc = A::madd(c[j], w[HX + p + j - H], acc);
-        r.v[p] = acc;
-    }
-    return r;
-}
 
 // one plane of one velocity component.  R = position inside a trip; GENERIC = run-time y weights / y-CPML; XZ = this
 // warp may sit in an x or z CPML layer.
@@ -1085,61 +745,12 @@ template <int Q, bool CPML, bool EDGE> __global__ void __launch_bounds__(NGROUPS
 // ---------------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn encodeFn()
-{
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void *p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
-        if (e != cudaSuccess || !p)
-            throw std::runtime_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
-        fn = reinterpret_cast<EncodeTiledFn>(p);
-    }
-    return fn;
-}
-
-// 4-D map over an arena: (x, z, y, array); box = boxX x boxZ x 1 plane x boxF arrays
-CUtensorMap makeMap(const float *arena, int pitch, int nzp, int nyp, long long arrayStride, int nArrays, int boxX, int boxZ, int boxF)
-{
-    CUtensorMap m;
-    const cuuint64_t dims[4] = {(cuuint64_t)pitch, (cuuint64_t)nzp, (cuuint64_t)nyp, (cuuint64_t)nArrays};
-    const cuuint64_t strides[3] = {(cuuint64_t)pitch * 4, (cuuint64_t)pitch * nzp * 4, (cuuint64_t)arrayStride * 4};
-    const cuuint32_t box[4] = {(cuuint32_t)boxX, (cuuint32_t)boxZ, 1, (cuuint32_t)boxF};
-    const cuuint32_t es[4] = {1, 1, 1, 1};
-    CUresult r = encodeFn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(arena), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS)
-        throw std::runtime_error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
-    return m;
-}
-
-constexpr int kMaxDynSmem = 227 * 1024 - 2048; // 227 KB per block minus the static barriers and coefficient table
 // cpmlEdge: the launch covers tiles in x / z CPML layers (staged memory variables); the stress half-step appends the
 // derivative exchange buffer (6 plain tiles)
 template <int Q> size_t smemBytes(int pass, bool cpmlEdge, int PX)
 {
     const size_t stage = (pass == 0 ? StageV<Q>::SIZE : StageS<Q>::SIZE) + (cpmlEdge ? psiStageFloats(PX) : 0);
     return ((size_t)(pass == 0 ? NSTV : NSTS) * stage + (pass == 1 ? 6 * Cfg<Q>::N_P : 0)) * 4;
-}
-
-// dense 4-D map (d0 fastest, arrays outermost); box = b0 x b1 x 1 x bA
-CUtensorMap makeMapG(const float *arena, int d0, int d1, int d2, int nArrays, int b0, int b1, int bA)
-{
-    CUtensorMap m;
-    const cuuint64_t dims[4] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2, (cuuint64_t)nArrays};
-    const cuuint64_t strides[3] = {(cuuint64_t)d0 * 4, (cuuint64_t)d0 * d1 * 4, (cuuint64_t)d0 * d1 * d2 * 4};
-    const cuuint32_t box[4] = {(cuuint32_t)b0, (cuuint32_t)b1, 1, (cuuint32_t)bA};
-    const cuuint32_t es[4] = {1, 1, 1, 1};
-    CUresult r = encodeFn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(arena), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS)
-        throw std::runtime_error("cuTensorMapEncodeTiled (memory variables) failed with code " + std::to_string((int)r));
-    return m;
 }
 
 template <int Q> void setAttrs()
@@ -1288,26 +899,8 @@ void *wsFastPrepare(WsParams &P, int nyp)
         cudaMemset(g_trace, 0, sizeof(unsigned long long) * 3 * 2 * WS_TRACE_MAX);
         P.fastTrace = g_trace;
     }
-    // planes per block: the march is cut into chunks so that the last round of thread blocks on the 148 SMs is short;
-    // every chunk pays Q-1 feed-only planes plus the pipeline fill
-    auto pickChunk = [&](int nTiles) {
-        int best = P.nyl;
-        double bestCost = 1e30;
-        for (int k = 1; k <= 8; k++) {
-            const int len = (P.nyl + k - 1) / k;
-            if (k > 1 && len < 64)
-                break;
-            const double rounds = std::ceil((double)nTiles * k / 148.0);
-            const double cost = rounds * (len + P.q + 3);
-            if (cost < bestCost * 0.995) {
-                bestCost = cost;
-                best = len;
-            }
-        }
-        return best;
-    };
-    P.fastChunk = pickChunk(P.fastNTiles - P.fastNEdge);
-    P.fastChunkEdge = P.fastNEdge > 0 ? pickChunk(P.fastNEdge) : P.fastChunk;
+    P.fastChunk = wsPickChunk(P.fastNTiles - P.fastNEdge, P.nyl, P.q);
+    P.fastChunkEdge = P.fastNEdge > 0 ? wsPickChunk(P.fastNEdge, P.nyl, P.q) : P.fastChunk;
     if (getenv("WS_FAST_CHUNK"))
         P.fastChunk = P.fastChunkEdge = atoi(getenv("WS_FAST_CHUNK"));
     return dev;
