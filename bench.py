@@ -20,8 +20,82 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-B_PER_UPDATE = {"elastic3d": 140.0}  # 60 B velocity pass + 80 B stress pass
-B_PASS = {"elastic3d": (60.0, 80.0)}
+EPS0, MU0 = 8.8541878176e-12, 1.2566370614e-6
+# Workloads = SURVEY.md §8(d) "concrete synthetic inputs".  `bytes` = ALGORITHMIC bytes per grid-point update of the first /
+# second half-step (§8(d) table).  The default (north-star) is the configuration BASELINE.json's metric is quoted on; the
+# others are BASELINE.json's configs[1..4], selectable with --workload for the numbers in DESIGN.md.
+WORKLOADS = {
+    "northstar": dict(dim=3, eq="elastic", n=(1024, 1024, 1024), dh=10.0, dt=8e-4, fs=1, damp=2, L=0, relax=(), bytes=(60.0, 80.0),
+                      vmax=5000.0, fc=10.0, src_type=3, rec_type=3, name="3D elastic FD8"),
+    "cfg2": dict(dim=2, eq="elastic", n=(4096, 4096, 1), dh=5.0, dt=5e-4, fs=1, damp=2, L=0, relax=(), bytes=(36.0, 44.0),
+                 vmax=3500.0, fc=10.0, src_type=3, rec_type=3, name="2D elastic FD8"),
+    "cfg3": dict(dim=3, eq="acoustic", n=(1024, 1024, 1024), dh=10.0, dt=1e-3, fs=0, damp=2, L=0, relax=(), bytes=(40.0, 24.0),
+                 vmax=3500.0, fc=10.0, src_type=1, rec_type=1, name="3D acoustic FD8"),
+    "cfg4": dict(dim=3, eq="viscoelastic", n=(768, 768, 768), dh=10.0, dt=8e-4, fs=1, damp=2, L=2, relax=(5.0, 50.0), bytes=(60.0, 196.0),
+                 vmax=3500.0, fc=10.0, src_type=3, rec_type=3, name="3D viscoelastic L=2 FD8"),
+    "cfg5": dict(dim=2, eq="viscotmem", n=(8192, 2048, 1), dh=0.01, dt=1.5e-11, fs=0, damp=2, L=1, relax=(1.0e8,), bytes=(28.0, 36.0),
+                 vmax=3.0e8, fc=1.0e8, src_type=1, rec_type=1, name="2D viscoTMEz L=1 FD8"),
+}
+
+
+def set_model_device(s, torch, wl, gny, nx, nz):
+    """Synthetic models of SURVEY.md §8(d), generated on the device slab by slab (global depth index = s.y0 + local y)."""
+    shape = (s.nyl, nz, nx)
+    yi = torch.arange(s.y0, s.y0 + s.nyl, device="cuda", dtype=torch.float32).view(-1, 1, 1)
+
+    def put(name, t):
+        t = t.expand(*shape).contiguous()
+        torch.cuda.synchronize()
+        s.set_material_device(name, t.data_ptr(), t.numel())
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        if wl == "northstar":  # vp 2000..5000 m/s linear in depth, vs = vp/sqrt(3), rho = 2000 + 0.2 (vp-2000)
+            vp = 2000.0 + 3000.0 * (yi / gny)
+            put("velocityP", vp)
+            put("velocityS", vp / float(np.sqrt(3.0)))
+            put("density", 2000.0 + 0.2 * (vp - 2000.0))
+        elif wl == "cfg2":  # 8 horizontal layers: vp = 1500 + 250 k, vs = vp/sqrt(3), rho = 1800 + 100 k
+            k = torch.clamp(torch.floor(yi * 8.0 / gny), 0, 7)
+            vp = 1500.0 + 250.0 * k
+            put("velocityP", vp)
+            put("velocityS", vp / float(np.sqrt(3.0)))
+            put("density", 1800.0 + 100.0 * k)
+        elif wl == "cfg3":  # vp = 2000 + 1500 y/NY, rho 2000
+            put("velocityP", 2000.0 + 1500.0 * (yi / gny))
+            put("density", torch.full((1, 1, 1), 2000.0, device="cuda"))
+        elif wl == "cfg4":  # two layers, interface at 0.4 NY; tauP = tauS = 0.1
+            top = (yi < 0.4 * gny).float()
+            put("velocityP", 3500.0 - 1000.0 * top)
+            put("velocityS", 2000.0 - 600.0 * top)
+            put("density", 2300.0 - 300.0 * top)
+            put("tauP", torch.full((1, 1, 1), 0.1, device="cuda"))
+            put("tauS", torch.full((1, 1, 1), 0.1, device="cuda"))
+        elif wl == "cfg5":  # eps_r = 4 +- 10 % in 64-cell blocks (seed 20260101), sigma 1e-3, mu_r 1, tau_eps 0.05, tau_sigma 0
+            g = torch.Generator(device="cpu").manual_seed(20260101)
+            blocks = torch.rand((gny + 63) // 64, (nx + 63) // 64, generator=g)
+            er = 4.0 * (0.9 + 0.2 * blocks).repeat_interleave(64, 0).repeat_interleave(64, 1)[s.y0:s.y0 + s.nyl, :nx]
+            put("dielectricPermittivity", (EPS0 * er).to("cuda").view(s.nyl, 1, nx))
+            put("electricConductivity", torch.full((1, 1, 1), 1.0e-3, device="cuda"))
+            put("magneticPermeability", torch.full((1, 1, 1), MU0, device="cuda"))
+            put("tauDielectricPermittivity", torch.full((1, 1, 1), 0.05, device="cuda"))
+            put("tauElectricConductivity", torch.full((1, 1, 1), 0.0, device="cuda"))
+        torch.cuda.empty_cache()
+
+
+def acquisition(wl, nx, gny, nz):
+    """(source index, receiver indices) as 64-bit global linear indices x + z NX + y NX NZ"""
+    pl = nx * nz
+    if wl == "cfg2":
+        return [nx // 2 + 1 * pl], [(nx // 4 + 4 * i) + 1 * pl for i in range(min(512, nx // 8))]
+    if wl == "cfg3":
+        ry = min(32, gny - 1)
+        return [nx // 2 + (nz // 2) * nx + (gny // 2) * pl], [i + (nz // 2) * nx + ry * pl for i in range(min(1024, nx))]
+    if wl == "cfg5":
+        xs = min(512, nx // 4)
+        return [xs + 21 * pl], [min(xs + 8 * i, nx - 1) + 21 * pl for i in range(128)]
+    nrec = min(1024, nx)
+    return [(nx // 2) + (nz // 2) * nx + 1 * pl], [(nx // 2 - nrec // 2 + i) + (nz // 2) * nx + 1 * pl for i in range(nrec)]
 
 
 def measured_peak():
@@ -128,16 +202,21 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--nx", type=int, default=1024)
-    ap.add_argument("--ny", type=int, default=1024, help="planes PER GPU")
-    ap.add_argument("--nz", type=int, default=1024)
+    ap.add_argument("--workload", default="northstar", choices=sorted(WORKLOADS))
+    ap.add_argument("--nx", type=int, default=0)
+    ap.add_argument("--ny", type=int, default=0, help="planes PER GPU")
+    ap.add_argument("--nz", type=int, default=0)
     ap.add_argument("--ref-n", type=int, default=192)
     ap.add_argument("--cpu-n", type=int, default=160)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--variant", type=int, default=0, help="0 auto (fast kernels), 1 force general kernels")
-    ap.add_argument("--damping", type=int, default=2, help="developer switch: 2 = CPML (the benchmark configuration), 0 = none")
-    ap.add_argument("--free-surface", type=int, default=1, help="developer switch: 1 = image method (the benchmark configuration)")
+    ap.add_argument("--variant", type=int, default=0, help="0 auto (TMA kernels, else marching kernels), 1 per-point kernels, 2 marching kernels")
+    ap.add_argument("--damping", type=int, default=-1, help="developer switch: 2 = CPML (the benchmark configuration), 0 = none")
+    ap.add_argument("--free-surface", type=int, default=-1, help="developer switch: 1 = image method")
     args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    args.nx, args.ny, args.nz = args.nx or wl["n"][0], args.ny or wl["n"][1], (args.nz or wl["n"][2]) if wl["dim"] == 3 else 1
+    args.damping = wl["damp"] if args.damping < 0 else args.damping
+    args.free_surface = wl["fs"] if args.free_surface < 0 else args.free_surface
     if args.impl == "reference":
         return run_reference(args)
 
@@ -155,36 +234,23 @@ def main():
     nx, nyl, nz = args.nx, args.ny, args.nz
     gny = nyl * world
     nt = 2 * (W + K) + 8
-    dt_, dh = 8e-4, 10.0
-    d = make_desc(3, "elastic", nx, gny, nz, dh=dh, dt=dt_, nt=nt, fd_order=8, edge_policy=0, free_surface=args.free_surface, damping=args.damping,
-                  boundary_width=20, vmax_cpml=5000.0, fc_cpml=10.0, npower=4.0, exact_arith=0, kernel_variant=args.variant,
-                  rank=rank, nranks=world, device=local)
+    dt_, dh = wl["dt"], wl["dh"]
+    d = make_desc(wl["dim"], wl["eq"], nx, gny, nz, dh=dh, dt=dt_, nt=nt, fd_order=8, edge_policy=0, free_surface=args.free_surface, damping=args.damping,
+                  boundary_width=20, vmax_cpml=wl["vmax"], fc_cpml=wl["fc"], npower=4.0, relax_freq=wl["relax"], exact_arith=0,
+                  kernel_variant=args.variant, rank=rank, nranks=world, device=local)
     s = Solver(d)
     if world > 1:
         ids = [Solver.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         s.comm_init(ids[0])
-    # synthetic model generated on the device: vp 2000..5000 m/s linear in depth, vs = vp/sqrt(3), rho = 2000 + 0.2 (vp-2000)
-    with torch.no_grad():
-        y = (torch.arange(s.y0, s.y0 + s.nyl, device="cuda", dtype=torch.float32) / gny).view(-1, 1, 1)
-        vp = (2000.0 + 3000.0 * y).expand(s.nyl, nz, nx).contiguous()
-        torch.cuda.synchronize()
-        s.set_material_device("velocityP", vp.data_ptr(), vp.numel())
-        vs = vp / float(np.sqrt(3.0))
-        torch.cuda.synchronize()
-        s.set_material_device("velocityS", vs.data_ptr(), vs.numel())
-        rho = 2000.0 + 0.2 * (vp - 2000.0)
-        torch.cuda.synchronize()
-        s.set_material_device("density", rho.data_ptr(), rho.numel())
-        del vp, vs, rho, y
-        torch.cuda.empty_cache()
+    set_model_device(s, torch, args.workload, gny, nx, nz)
     s.prepare()
-    pl = nx * nz
-    nrec = min(1024, nx)
-    src_idx = np.array([(nx // 2) + (nz // 2) * nx + 1 * pl], dtype=np.int64)
-    rec_idx = np.array([(nx // 2 - nrec // 2 + i) + (nz // 2) * nx + 1 * pl for i in range(nrec)], dtype=np.int64)
-    s.set_sources64([3], src_idx, ricker_np(nt, dt_, 10.0, 1.0e6)[None, :])
-    s.set_receivers64([3] * nrec, rec_idx)
+    src, recs = acquisition(args.workload, nx, gny, nz)
+    nrec = len(recs)
+    amp = 1.0e6 if not wl["eq"].endswith("mem") else 1.0
+    sig = ricker_np(nt, dt_, wl["fc"], amp)
+    s.set_sources64([wl["src_type"]], np.array(src, dtype=np.int64), sig[None, :])
+    s.set_receivers64([wl["rec_type"]] * nrec, np.array(recs, dtype=np.int64))
     s.reset()
 
     stream = torch.cuda.ExternalStream(s.stream_ptr())
@@ -213,7 +279,6 @@ def main():
     msA, msB, msStep = s.last_timing(0), s.last_timing(1), s.last_timing(2)
     # ---- end-to-end run through host buffers: per step H2D of the source samples, D2H of the receiver samples --------
     s.set_timing(False)
-    sig = ricker_np(nt, dt_, 10.0, 1.0e6)
     rec = np.zeros(nrec, np.float32)
     t_base = W + K
     for t in range(t_base, t_base + 3):
@@ -236,16 +301,17 @@ def main():
         launches = int(lt.item())
     ms, e2e_ms, msA, msB = (float(v) for v in t_ms.tolist())
     npts_local = float(nx) * nyl * nz
+    ws_bytes = s.estimate_memory()
     npts = npts_local * world
     value = npts * K / (ms * 1e-3) / 1e9
     e2e = npts * K / (e2e_ms * 1e-3) / 1e9
     if rank == 0:
         peak, which = measured_peak()
-        bA, bB = B_PASS["elastic3d"]
+        bA, bB = wl["bytes"]
         dom = 1 if msB >= msA else 0
         achieved = (bB if dom else bA) * npts_local / ((msB if dom else msA) * 1e-3) / 1e9
         cpu = None
-        if not args.no_cpu and world == 1:
+        if not args.no_cpu and world == 1 and args.workload == "northstar":
             g, sec, cores = cpu_oracle_throughput(args.cpu_n, 3, 1)
             cpu = {"value": g, "unit": "Gpt/s", "cores": cores, "kind": "port",
                    "sample": "%d^3 grid, 3 steps, oracle CSR formulation (restatement of the LAMA sparse path)" % args.cpu_n}
@@ -253,14 +319,15 @@ def main():
             "metric": "Gpt-updates/s", "value": value, "unit": "Gpt/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": "3D elastic FD8 %dx%dx%d per GPU (global NY %d), free surface + CPML(20), y-slab decomposition" % (nx, nyl, nz, gny),
-                       "l2": "inputs (%.0f GB/GPU of wavefields+model) far exceed the 126 MB L2" % (20 * npts_local * 4 / 1e9),
-                       "kernels": "fast-tiled" if s.uses_fast_kernels() else "general", "finite": bool(finite)},
+            "config": {"workload": "%s %dx%dx%d per GPU (global NY %d), %sCPML(20), y-slab decomposition"
+                                   % (wl["name"], nx, nyl, nz, gny, "free surface + " if args.free_surface else ""),
+                       "l2": "inputs (%.1f GB/GPU of wavefields+model) exceed the 126 MB L2" % (ws_bytes / 1e9),
+                       "kernels": ["per-point", "marching", "tma-tiled"][s.kernel_path()], "finite": bool(finite)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": measured_traffic(dom, nx, nyl, nz, args.damping, args.free_surface),
-                         "kernel": "stress half-step" if dom else "velocity half-step", "peak_source": which,
-                         "ms_velocity": msA, "ms_stress": msB,
-                         "whole_step_frac": B_PER_UPDATE["elastic3d"] * npts_local / (ms / K * 1e-3) / 1e9 / peak},
+                         "traffic": measured_traffic(dom, nx, nyl, nz, args.damping, args.free_surface) if args.workload == "northstar" else None,
+                         "kernel": "second half-step (stress / E)" if dom else "first half-step (velocity / H)", "peak_source": which,
+                         "ms_first": msA, "ms_second": msB,
+                         "whole_step_frac": (bA + bB) * npts_local / (ms / K * 1e-3) / 1e9 / peak},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e, "unit": "Gpt/s", "h2d_bytes_per_step": 4 * world, "d2h_bytes_per_step": 4 * nrec},
             "gpu_launches": launches,

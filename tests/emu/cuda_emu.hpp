@@ -3,8 +3,9 @@
 // Minimal host-side stand-in for the CUDA runtime API and the device intrinsics used by wave-simulation_b200/csrc,
 // so that the CPU-only test suite (`pytest -m "not gpu"`, no GPU in the build container) can compile the general
 // kernels, the model-preparation kernels and the whole C ABI with -DWS_EMULATE into tests/emu/libwavesim_emu.so and
-// check their LOGIC against the oracle before GPU time is spent.  Kernels run as sequential loops over the launch grid
-// (valid for kernels without shared memory / __syncthreads).  This library is never loaded by the product, by
+// check their LOGIC against the oracle before GPU time is spent.  Kernels without shared memory run as sequential loops
+// over the launch grid (launch); kernels that use shared memory and __syncthreads run one thread block at a time with
+// one OS thread per CUDA thread and a barrier (launchCoop).  This library is never loaded by the product, by
 // bench.py or by the `-m gpu` tests: the product has no CPU path and fails loudly without its CUDA library.
 #pragma once
 #include <algorithm>
@@ -12,6 +13,10 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <barrier>
+#include <memory>
+#include <thread>
+#include <vector>
 
 #define __global__
 #define __device__
@@ -47,7 +52,40 @@ void launch(K kern, dim3 grid, dim3 block, Args... args)
                         }
             }
 }
+// cooperative kernels: the threads of a block are real threads, __syncthreads is a barrier, shared memory is g_smem
+inline void *g_smem = nullptr;
+inline std::barrier<> *g_barrier = nullptr;
+template <typename K, typename... Args>
+void launchCoop(K kern, dim3 grid, dim3 block, size_t smemBytes, Args... args)
+{
+    const unsigned nthr = block.x * block.y * block.z;
+    std::vector<unsigned char> smem(smemBytes + 16);
+    std::barrier<> bar(nthr), blockBar(nthr);
+    g_smem = smem.data();
+    g_barrier = &bar;
+    // one OS thread per CUDA thread, reused for every block of the grid (blocks run one after the other)
+    std::vector<std::thread> pool;
+    pool.reserve(nthr);
+    for (unsigned t = 0; t < nthr; t++)
+        pool.emplace_back([=, &blockBar]() {
+            g_gridDim = grid;
+            g_blockDim = block;
+            g_threadIdx = {t % block.x, (t / block.x) % block.y, t / (block.x * block.y)};
+            for (unsigned bz = 0; bz < grid.z; bz++)
+                for (unsigned by = 0; by < grid.y; by++)
+                    for (unsigned bx = 0; bx < grid.x; bx++) {
+                        g_blockIdx = {bx, by, bz};
+                        kern(args...);
+                        blockBar.arrive_and_wait(); // shared memory is reused by the next block
+                    }
+        });
+    for (auto &th : pool)
+        th.join();
+    g_smem = nullptr;
+    g_barrier = nullptr;
+}
 } // namespace wsemu
+inline void __syncthreads() { wsemu::g_barrier->arrive_and_wait(); }
 #define blockIdx wsemu::g_blockIdx
 #define threadIdx wsemu::g_threadIdx
 #define blockDim wsemu::g_blockDim

@@ -35,6 +35,41 @@ def test_emulated_kernels_fma_mode(cfg):
     assert rel_l2(e.seismogram(), o.seismogram()) <= 1.0e-5
 
 
+@pytest.mark.parametrize("cfg", SWEEP, ids=[sweep_id(c) for c in SWEEP])
+def test_emulated_marching_kernels_equal_per_point_kernels(cfg):
+    """The marching kernels (register queues + staged planes, ws_kernels_march.cuh) run the statement sequence of the
+    per-point kernels with the weights applied in the same order: bit-identical wavefields in FMA mode."""
+    eq, dim, nx, ny, nz, q, pol, fs, damp, W, L = cfg
+    res = []
+    for variant in (1, 2):
+        case = make_case(eq, dim, nx, ny, nz, q, pol, fs, damp, W, L, nt=12, exact=0, kernel_variant=variant)
+        e = case.setup(EmuSolver(case.desc))
+        assert e.kernel_path() == (0 if variant == 1 else 1)
+        e.run(0, 12)
+        res.append((e.seismogram(), {f: e.wavefield(f) for f in fields_of(eq, dim, L)}))
+        e.close()
+    assert np.abs(res[0][0]).max() > 0
+    assert np.array_equal(res[0][0], res[1][0])
+    for f in res[0][1]:
+        assert np.array_equal(res[0][1][f], res[1][1][f]), f
+
+
+def test_emulated_marching_kernels_partial_tiles_and_chunks(monkeypatch):
+    """grid sizes that are not multiples of the tile, several y chunks per column (WS_MARCH_CHUNK)"""
+    monkeypatch.setenv("WS_MARCH_CHUNK", "7")
+    for cfg in (("elastic", 3, 37, 23, 11, 8, 0, 1, 2, 5, 0), ("viscoelastic", 2, 150, 31, 1, 8, 0, 1, 2, 6, 2), ("acoustic", 3, 34, 20, 19, 8, 0, 0, 2, 5, 0)):
+        eq, dim, nx, ny, nz, q, pol, fs, damp, W, L = cfg
+        res = []
+        for variant in (1, 2):
+            case = make_case(eq, dim, nx, ny, nz, q, pol, fs, damp, W, L, nt=8, exact=0, kernel_variant=variant)
+            e = case.setup(EmuSolver(case.desc))
+            e.run(0, 8)
+            res.append({f: e.wavefield(f) for f in fields_of(eq, dim, L)})
+            e.close()
+        for f in res[0]:
+            assert np.array_equal(res[0][f], res[1][f]), (cfg, f)
+
+
 def test_emulated_ci_case_2d_elastic_full_trace():
     case = ci_case("2D.elastic")
     for exact, tol in ((1, 0.0), (0, 1.0e-5)):

@@ -151,6 +151,50 @@ def test_fast_kernels_equal_general_kernels(shape):
         assert np.array_equal(res[0][1][f], res[1][1][f]), f
 
 
+@pytest.mark.parametrize("cfg", SWEEP, ids=[sweep_id(c) for c in SWEEP])
+def test_marching_kernels_equal_per_point_kernels(cfg):
+    """ws_kernels_march.cuh (register queues along y, cp.async-staged planes for x / z) against the per-point kernels:
+    same statement sequence, same accumulation order => bit-identical in FMA mode, for every equation type."""
+    eq, dim, nx, ny, nz, q, pol, fs, damp, W, L = cfg
+    res = []
+    for variant in (1, 2):
+        case = make_case(eq, dim, nx, ny, nz, q, pol, fs, damp, W, L, nt=40, exact=0, kernel_variant=variant)
+        s = case.setup(Solver(case.desc))
+        assert s.kernel_path() == (0 if variant == 1 else 1)
+        s.run(0, 40)
+        s.sync()
+        res.append((s.seismogram(), {f: s.wavefield(f) for f in fields_of(eq, dim, L)}))
+        assert s.is_finite()
+        s.close()
+    assert np.abs(res[0][0]).max() > 0
+    assert np.array_equal(res[0][0], res[1][0])
+    for f in res[0][1]:
+        assert np.array_equal(res[0][1][f], res[1][1][f]), f
+
+
+MARCH_SHAPES = [
+    # eq, dim, nx, ny, nz, q, pol, fs, damp, W, L : ragged tiles, several tiles per axis, several y chunks
+    ("acoustic", 3, 100, 150, 70, 8, 0, 0, 2, 10, 0), ("elastic", 3, 70, 90, 50, 8, 0, 1, 2, 8, 0), ("viscoelastic", 3, 67, 75, 35, 8, 0, 1, 2, 8, 2),
+    ("elastic", 2, 1000, 700, 1, 8, 0, 1, 2, 20, 0), ("viscotmem", 2, 900, 300, 1, 8, 0, 0, 2, 20, 1), ("viscoemem", 3, 40, 90, 37, 4, 1, 0, 2, 6, 1),
+    ("acoustic", 2, 515, 260, 1, 12, 1, 1, 1, 12, 0), ("viscosh", 2, 300, 200, 1, 6, 0, 1, 2, 10, 2),
+]
+
+
+@pytest.mark.parametrize("cfg", MARCH_SHAPES, ids=[sweep_id(c) + "-%dx%dx%d" % c[2:5] for c in MARCH_SHAPES])
+def test_marching_kernels_ragged_shapes(cfg):
+    eq, dim, nx, ny, nz, q, pol, fs, damp, W, L = cfg
+    res = []
+    for variant in (1, 2):
+        case = make_case(eq, dim, nx, ny, nz, q, pol, fs, damp, W, L, nt=25, exact=0, kernel_variant=variant)
+        s = case.setup(Solver(case.desc))
+        s.run(0, 25)
+        s.sync()
+        res.append({f: s.wavefield(f) for f in fields_of(eq, dim, L)})
+        s.close()
+    for f in res[0]:
+        assert np.array_equal(res[0][f], res[1][f]), f
+
+
 def test_fast_kernels_vs_oracle():
     case = make_case("elastic", 3, 64, 48, 40, 8, 0, 1, 2, 8, 0, nt=60, exact=0, kernel_variant=0)
     o, s = run_pair(case, 60)

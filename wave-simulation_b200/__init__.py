@@ -146,6 +146,7 @@ def _load_ws_lib(path):
     lib.ws_stream.restype = C.c_void_p
     lib.ws_stream.argtypes = [C.c_void_p]
     lib.ws_uses_fast_kernels.argtypes = [C.c_void_p]
+    lib.ws_kernel_path.argtypes = [C.c_void_p]
     return lib
 
 
@@ -204,8 +205,16 @@ class Solver(SolverBase):
     def uses_fast_kernels(self):
         return bool(self.lib.ws_uses_fast_kernels(self.h))
 
+    def kernel_path(self):
+        """0 per-point kernels, 1 marching kernels, 2 warp-specialised TMA kernels"""
+        return int(self.lib.ws_kernel_path(self.h))
+
     def launch_count(self):
         return int(self.lib.ws_launch_count(self.h))
+
+    def estimate_memory(self):
+        """bytes of HBM this rank allocates (ForwardSolver::estimateMemory)"""
+        return int(self.lib.ws_estimate_memory(C.byref(self.desc)))
 
     def last_timing(self, which):
         ms = C.c_float()

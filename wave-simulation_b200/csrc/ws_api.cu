@@ -308,6 +308,7 @@ struct ws_solver {
     std::vector<cudaEvent_t> evPool;
     float msA = 0, msB = 0, msStep = 0;
     bool useFast = false;
+    bool useMarch = false; // marching kernels (ws_kernels_march.cu) serve this configuration
     void *fastMaps = nullptr;
     // CUDA graph of one time step
     cudaGraphExec_t graphExec = nullptr;
@@ -974,6 +975,13 @@ void launchPass(ws_solver *s, int pass, int ylo, int yhi)
             return;
         }
     }
+    if (s->useMarch) {
+        const int n = wsLaunchMarch(P, pass, s->stream);
+        if (n > 0) {
+            s->launches += n;
+            return;
+        }
+    }
     wsLaunchGeneral(P, s->exact, pass, s->stream);
     s->launches++;
 }
@@ -1301,6 +1309,10 @@ int ws_prepare(ws_solver *s)
         }
         if (s->useFast)
             s->fastMaps = wsFastPrepare(s->P, s->nyl + 2 * WS_HALO);
+        // kernel_variant: 0 = best available (TMA kernels, else marching kernels), 1 = per-point kernels, 2 = marching kernels
+        s->useMarch = !s->useFast && (s->d.kernel_variant == 0 || s->d.kernel_variant == 2) && wsMarchSupported(s->P, s->exact);
+        if (s->useMarch)
+            wsMarchPrepare(s->P);
         WS_CUDA_CHECK(cudaStreamSynchronize(s->stream));
         WS_CUDA_CHECK(cudaGetLastError());
         s->prepared = true;
@@ -1696,5 +1708,6 @@ int ws_last_timing(ws_solver *s, int which, float *ms)
 void *ws_stream(ws_solver *s) { return s ? (void *)s->stream : nullptr; }
 
 int ws_uses_fast_kernels(const ws_solver *s) { return s && s->useFast ? 1 : 0; }
+int ws_kernel_path(const ws_solver *s) { return !s ? -1 : (s->useFast ? 2 : (s->useMarch ? 1 : 0)); }
 
 } // extern "C"

@@ -73,6 +73,8 @@ struct WsParams {
     int ylo, yhi;     // local y range [ylo, yhi) processed by this launch (interior/boundary split for overlap)
     int edge_policy;  // 0 truncate | 1 order-reduce
     int fastChunk, fastChunkEdge; // planes per thread block of the tiled kernels (interior / CPML-layer launch)
+    int marchChunk;   // planes per thread block of the marching kernels (ws_kernels_march.cuh)
+    int marchStages;  // developer switch (env WS_MARCH_STAGES): depth of the stage ring, 0 = chosen from the stage size
     int fastDebug;    // developer switch (env WS_FAST_DEBUG): 1 = consumers skip the arithmetic and the stores (memory-side ceiling of the tiling)
     int fastFlags;    // developer switch (env WS_FAST_FLAGS): bit 0 = L2 eviction-priority hints on the TMA loads, bit 1 = CPML-layer tiles in a launch of their own (default 3)
     const int *fastTiles; // tile list of the tiled kernels ((z tile << 16) | x tile), layer tiles first

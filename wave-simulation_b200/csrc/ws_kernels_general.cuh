@@ -9,8 +9,15 @@
 
 namespace wsgen {
 
+template <int N> struct IC { // compile-time integer tag (array slots as arguments of generic lambdas)
+    static constexpr int value = N;
+};
+
+// Per-point bookkeeping shared by the per-point kernels below and the marching kernels (ws_kernels_march.cuh): indices,
+// row classes of the derivative tables, CPML slab positions, ABS factor.  The derivative itself (D<F, OP>) is supplied
+// by the derived point type, so both kernel families run the SAME statement sequence (passA / passB).
 template <bool EXACT>
-struct Pt {
+struct PtBase {
     using A = Ar<EXACT>;
     const WsParams &P;
     int x, ly, z, gy;
@@ -19,44 +26,38 @@ struct Pt {
     int kx, ky, kz; // CPML slab indices (-1 outside)
     long long px, py, pz; // psi offsets
 
-    __device__ __forceinline__ Pt(const WsParams &P_, int x_, int ly_, int z_) : P(P_), x(x_), ly(ly_), z(z_)
+    __device__ __forceinline__ PtBase(const WsParams &P_, int x_, int ly_, int z_) : P(P_), x(x_), z(z_)
     {
+        rx = wsRowClass(x, P.nx, P.h);
+        rz = wsRowClass(z, P.nz, P.h);
+        kx = kz = -1;
+        if (P.damping == 2) {
+            kx = wsCpmlIndex(x, P.nx, P.W);
+            if (P.dim == 3)
+                kz = wsCpmlIndex(z, P.nz, P.W);
+        }
+        setY(ly_);
+    }
+    // everything that depends on the plane (the marching kernels advance a point along y)
+    __device__ __forceinline__ void setY(int ly_)
+    {
+        ly = ly_;
         gy = P.gy0 + ly;
         i = P.base + x + (long long)z * P.pitch + (long long)ly * P.plane;
-        rx = wsRowClass(x, P.nx, P.h);
         ry = wsRowClass(gy, P.gny, P.h);
-        rz = wsRowClass(z, P.nz, P.h);
-        kx = ky = kz = -1;
+        ky = -1;
         px = py = pz = 0;
         if (P.damping == 2) {
             const int W = P.W;
-            kx = wsCpmlIndex(x, P.nx, W);
             ky = wsCpmlIndex(gy, P.gny, W);
             if (P.free_surface != 0 && gy < W)
                 ky = -1; // no CPML in the top layer with a free surface (CPML3D.cpp:320-328)
-            if (P.dim == 3)
-                kz = wsCpmlIndex(z, P.nz, W);
             px = ((long long)ly * P.nz + z) * P.psiPitchX + wsPsiXIndex(x, W, P.psiDX);
             py = ((long long)ky * P.nz + z) * P.nx + x;
             pz = ((long long)ly * (2 * W) + kz) * P.nx + x;
         }
     }
 
-    // row of matrix `op` applied to field f: ascending-column accumulation like a CSR SpMV
-    __device__ __forceinline__ float D(const float *__restrict__ f, int op) const
-    {
-        const int axis = (op < 6) ? (op >> 1) : 1;
-        const int r = axis == 0 ? rx : (axis == 1 ? ry : rz);
-        const long long s = axis == 0 ? 1 : (axis == 1 ? P.plane : (long long)P.pitch);
-        const float *__restrict__ w = P.tab + ((size_t)op * (2 * P.h + 1) + r) * (P.q + 1);
-        const float *__restrict__ p = f + i - (long long)P.h * s;
-        float acc = 0.0f;
-        for (int j = 0; j <= P.q; j++) {
-            acc = A::madd(__ldg(w + j), p[0], acc);
-            p += s;
-        }
-        return acc;
-    }
     // CPML.cpp:84-95 applyCPML
     __device__ __forceinline__ float cp(float d, int slot, int k, long long off, const float *__restrict__ ca, const float *__restrict__ cb) const
     {
@@ -102,137 +103,159 @@ struct Pt {
     __device__ __forceinline__ int surfaceIndex() const { return z * P.nx + x; }
 };
 
+// one thread per grid point, every tap read from global memory
 template <bool EXACT>
-__device__ __forceinline__ float &FL(const WsParams &P, int slot, long long i) { return P.fld[slot][i]; }
+struct Pt : PtBase<EXACT> {
+    using A = Ar<EXACT>;
+    using PtBase<EXACT>::P;
+    __device__ __forceinline__ Pt(const WsParams &P_, int x_, int ly_, int z_) : PtBase<EXACT>(P_, x_, ly_, z_) {}
+    // row of matrix `op` applied to field f: ascending-column accumulation like a CSR SpMV
+    __device__ __forceinline__ float D(const float *__restrict__ f, int op) const
+    {
+        const int axis = (op < 6) ? (op >> 1) : 1;
+        const int r = axis == 0 ? this->rx : (axis == 1 ? this->ry : this->rz);
+        const long long s = axis == 0 ? 1 : (axis == 1 ? P.plane : (long long)P.pitch);
+        const float *__restrict__ w = P.tab + ((size_t)op * (2 * P.h + 1) + r) * (P.q + 1);
+        const float *__restrict__ p = f + this->i - (long long)P.h * s;
+        float acc = 0.0f;
+        for (int j = 0; j <= P.q; j++) {
+            acc = A::madd(__ldg(w + j), p[0], acc);
+            p += s;
+        }
+        return acc;
+    }
+    template <int F, int OP> __device__ __forceinline__ float D() const { return D(P.fld[F], OP); }
+    // own-point operands: wavefield F, model parameter M, memory variable C of relaxation mechanism l, EM coefficient Cd
+    template <int F> __device__ __forceinline__ float fld() const { return P.fld[F][this->i]; }
+    template <int F> __device__ __forceinline__ void put(float v) const { P.fld[F][this->i] = v; }
+    template <int M> __device__ __forceinline__ float mat() const { return P.mat[M][this->i]; }
+    template <int C> __device__ __forceinline__ float rget(int l) const { return P.fld[F_R0 + 6 * l + C][this->i]; }
+    template <int C> __device__ __forceinline__ void rput(int l, float v) const { P.fld[F_R0 + 6 * l + C][this->i] = v; }
+    template <int AXIS> __device__ __forceinline__ float cd(int l) const { return P.mat[M_CD0 + 3 * l + AXIS][this->i]; }
+};
 
 // --------------------------------------------------------------------------------------------------------------------
 // first half-step: particle velocities / magnetic field
 // --------------------------------------------------------------------------------------------------------------------
-template <int EQ, int DIM, bool EXACT>
-__device__ __forceinline__ void passA(const WsParams &P, const Pt<EXACT> &t)
+template <int EQ, int DIM, bool EXACT, typename PT>
+__device__ __forceinline__ void passA(const WsParams &P, const PT &t)
 {
     using A = Ar<EXACT>;
     const long long i = t.i;
     const bool fs = P.free_surface == 1;
     if (EQ == WS_EQ_ACOUSTIC) {
         // ForwardSolver3Dacoustic.cpp:131-187, ForwardSolver2Dacoustic.cpp:121-160
-        const float *p = P.fld[F_P];
-        float u = t.D(p, OP_XF);
+        float u = t.template D<F_P, OP_XF>();
         u = t.cpx(u, PSI_P_X, true);
-        u = A::mul(u, P.mat[M_RIX][i]);
-        P.fld[F_VX][i] = A::add(P.fld[F_VX][i], u);
-        u = t.D(p, fs ? OP_YF_FS : OP_YF);
+        u = A::mul(u, t.template mat<M_RIX>());
+        t.template put<F_VX>(A::add(t.template fld<F_VX>(), u));
+        u = (fs ? t.template D<F_P, OP_YF_FS>() : t.template D<F_P, OP_YF>());
         u = t.cpy(u, PSI_P_Y, true);
-        u = A::mul(u, P.mat[M_RIY][i]);
-        P.fld[F_VY][i] = A::add(P.fld[F_VY][i], u);
+        u = A::mul(u, t.template mat<M_RIY>());
+        t.template put<F_VY>(A::add(t.template fld<F_VY>(), u));
         if (DIM == 3) {
-            u = t.D(p, OP_ZF);
+            u = t.template D<F_P, OP_ZF>();
             u = t.cpz(u, PSI_P_Z, true);
-            u = A::mul(u, P.mat[M_RIZ][i]);
-            P.fld[F_VZ][i] = A::add(P.fld[F_VZ][i], u);
+            u = A::mul(u, t.template mat<M_RIZ>());
+            t.template put<F_VZ>(A::add(t.template fld<F_VZ>(), u));
         }
     } else if (EQ == WS_EQ_ELASTIC || EQ == WS_EQ_VISCOELASTIC) {
         // ForwardSolver3Delastic.cpp:181-277, ForwardSolver2Delastic.cpp:163-208, ForwardSolver3Dviscoelastic.cpp:188-262
-        const float *sxx = P.fld[F_SXX], *syy = P.fld[F_SYY], *sxy = P.fld[F_SXY];
-        const float *szz = P.fld[F_SZZ], *sxz = P.fld[F_SXZ], *syz = P.fld[F_SYZ];
-        float u = t.D(sxx, OP_XF);
+        float u = t.template D<F_SXX, OP_XF>();
         u = t.cpx(u, PSI_SXX_X, true);
-        float w = t.D(sxy, fs ? OP_YB_FS : OP_YB);
+        float w = (fs ? t.template D<F_SXY, OP_YB_FS>() : t.template D<F_SXY, OP_YB>());
         w = t.cpy(w, PSI_SXY_Y, false);
         u = A::add(u, w);
         if (DIM == 3) {
-            w = t.D(sxz, OP_ZB);
+            w = t.template D<F_SXZ, OP_ZB>();
             w = t.cpz(w, PSI_SXZ_Z, false);
             u = A::add(u, w);
         }
-        u = A::mul(u, P.mat[M_RIX][i]);
-        P.fld[F_VX][i] = A::add(P.fld[F_VX][i], u);
+        u = A::mul(u, t.template mat<M_RIX>());
+        t.template put<F_VX>(A::add(t.template fld<F_VX>(), u));
 
-        u = t.D(sxy, OP_XB);
+        u = t.template D<F_SXY, OP_XB>();
         u = t.cpx(u, PSI_SXY_X, false);
-        w = t.D(syy, fs ? OP_YF_FS : OP_YF);
+        w = (fs ? t.template D<F_SYY, OP_YF_FS>() : t.template D<F_SYY, OP_YF>());
         w = t.cpy(w, PSI_SYY_Y, true);
         u = A::add(u, w);
         if (DIM == 3) {
-            w = t.D(syz, OP_ZB);
+            w = t.template D<F_SYZ, OP_ZB>();
             w = t.cpz(w, PSI_SYZ_Z, false);
             u = A::add(u, w);
         }
-        u = A::mul(u, P.mat[M_RIY][i]);
-        P.fld[F_VY][i] = A::add(P.fld[F_VY][i], u);
+        u = A::mul(u, t.template mat<M_RIY>());
+        t.template put<F_VY>(A::add(t.template fld<F_VY>(), u));
 
         if (DIM == 3) {
-            u = t.D(sxz, OP_XB);
+            u = t.template D<F_SXZ, OP_XB>();
             u = t.cpx(u, PSI_SXZ_X, false);
-            w = t.D(syz, fs ? OP_YB_FS : OP_YB);
+            w = (fs ? t.template D<F_SYZ, OP_YB_FS>() : t.template D<F_SYZ, OP_YB>());
             w = t.cpy(w, PSI_SYZ_Y, false);
             u = A::add(u, w);
-            w = t.D(szz, OP_ZF);
+            w = t.template D<F_SZZ, OP_ZF>();
             w = t.cpz(w, PSI_SZZ_Z, true);
             u = A::add(u, w);
-            u = A::mul(u, P.mat[M_RIZ][i]);
-            P.fld[F_VZ][i] = A::add(P.fld[F_VZ][i], u);
+            u = A::mul(u, t.template mat<M_RIZ>());
+            t.template put<F_VZ>(A::add(t.template fld<F_VZ>(), u));
         }
     } else if (EQ == WS_EQ_SH || EQ == WS_EQ_VISCOSH) {
         // ForwardSolver2Dsh.cpp:140-158
-        float u = t.D(P.fld[F_SXZ], OP_XB);
-        float w = t.D(P.fld[F_SYZ], fs ? OP_YB_FS : OP_YB);
+        float u = t.template D<F_SXZ, OP_XB>();
+        float w = (fs ? t.template D<F_SYZ, OP_YB_FS>() : t.template D<F_SYZ, OP_YB>());
         u = t.cpx(u, PSI_SXZ_X, false);
         w = t.cpy(w, PSI_SYZ_Y, false);
         u = A::add(u, w);
-        u = A::mul(u, P.mat[M_INVRHO][i]);
-        P.fld[F_VZ][i] = A::add(P.fld[F_VZ][i], u);
+        u = A::mul(u, t.template mat<M_INVRHO>());
+        t.template put<F_VZ>(A::add(t.template fld<F_VZ>(), u));
     } else if (EQ == WS_EQ_TMEM || EQ == WS_EQ_VISCOTMEM) {
         // ForwardSolver2Dtmem.cpp:131-146
-        const float *ez = P.fld[F_EZ];
-        float u = t.D(ez, OP_YF);
+        float u = t.template D<F_EZ, OP_YF>();
         u = t.cpy(u, PSI_EZY, true);
-        u = A::mul(u, P.mat[M_MIYZ][i]);
-        P.fld[F_HX][i] = A::sub(P.fld[F_HX][i], u);
-        float w = t.D(ez, OP_XF);
+        u = A::mul(u, t.template mat<M_MIYZ>());
+        t.template put<F_HX>(A::sub(t.template fld<F_HX>(), u));
+        float w = t.template D<F_EZ, OP_XF>();
         w = t.cpx(w, PSI_EZX, true);
         u = A::mul(-1.0f, w);
-        u = A::mul(u, P.mat[M_MIXZ][i]);
-        P.fld[F_HY][i] = A::sub(P.fld[F_HY][i], u);
+        u = A::mul(u, t.template mat<M_MIXZ>());
+        t.template put<F_HY>(A::sub(t.template fld<F_HY>(), u));
     } else if (EQ == WS_EQ_EMEM || EQ == WS_EQ_VISCOEMEM) {
-        const float *ex = P.fld[F_EX], *ey = P.fld[F_EY], *ez = P.fld[F_EZ];
         if (DIM == 3) {
             // ForwardSolver3Demem.cpp:154-187
-            float u = t.D(ez, OP_YF);
-            float w = t.D(ey, OP_ZF);
+            float u = t.template D<F_EZ, OP_YF>();
+            float w = t.template D<F_EY, OP_ZF>();
             u = t.cpy(u, PSI_EZY, true);
             w = t.cpz(w, PSI_EYZ, true);
             u = A::sub(u, w);
-            u = A::mul(u, P.mat[M_MIYZ][i]);
-            P.fld[F_HX][i] = A::sub(P.fld[F_HX][i], u);
-            u = t.D(ex, OP_ZF);
-            w = t.D(ez, OP_XF);
+            u = A::mul(u, t.template mat<M_MIYZ>());
+            t.template put<F_HX>(A::sub(t.template fld<F_HX>(), u));
+            u = t.template D<F_EX, OP_ZF>();
+            w = t.template D<F_EZ, OP_XF>();
             u = t.cpz(u, PSI_EXZ, true);
             w = t.cpx(w, PSI_EZX, true);
             u = A::sub(u, w);
-            u = A::mul(u, P.mat[M_MIXZ][i]);
-            P.fld[F_HY][i] = A::sub(P.fld[F_HY][i], u);
+            u = A::mul(u, t.template mat<M_MIXZ>());
+            t.template put<F_HY>(A::sub(t.template fld<F_HY>(), u));
         }
         // ForwardSolver2Demem.cpp:136-146
-        float u = t.D(ey, OP_XF);
-        float w = t.D(ex, OP_YF);
+        float u = t.template D<F_EY, OP_XF>();
+        float w = t.template D<F_EX, OP_YF>();
         u = t.cpx(u, PSI_EYX, true);
         w = t.cpy(w, PSI_EXY, true);
         u = A::sub(u, w);
-        u = A::mul(u, P.mat[M_MIXY][i]);
-        P.fld[F_HZ][i] = A::sub(P.fld[F_HZ][i], u);
+        u = A::mul(u, t.template mat<M_MIXY>());
+        t.template put<F_HZ>(A::sub(t.template fld<F_HZ>(), u));
     }
 }
 
 // viscoelastic helpers (ForwardSolver3Dviscoelastic.cpp:284-416) -------------------------------------------------------
-template <bool EXACT>
-__device__ __forceinline__ float viscoShear(const WsParams &P, long long i, float S, int rc, float u, float muAvg, float tauAvg, float onePlusLtauS)
+template <bool EXACT, int RC, typename PT>
+__device__ __forceinline__ float viscoShear(const WsParams &P, const PT &t, float S, float u, float muAvg, float tauAvg, float onePlusLtauS)
 {
     using A = Ar<EXACT>;
     u = A::mul(u, muAvg);
     for (int l = 0; l < P.L; l++) {
-        float *Rp = P.fld[F_R0 + 6 * l + rc] + i;
-        float R = *Rp;
+        float R = t.template rget<RC>(l);
         S = A::madd(P.DThalf, R, S);
         R = A::mul(R, P.viscoCoeff1[l]);
         float u2 = A::mul(P.invRelaxTime[l], u);
@@ -240,7 +263,7 @@ __device__ __forceinline__ float viscoShear(const WsParams &P, long long i, floa
         R = A::sub(R, u2);
         R = A::mul(R, P.viscoCoeff2[l]);
         S = A::madd(P.DThalf, R, S);
-        *Rp = R;
+        t.template rput<RC>(l, R);
     }
     u = A::mul(u, onePlusLtauS);
     return A::add(S, u);
@@ -249,8 +272,8 @@ __device__ __forceinline__ float viscoShear(const WsParams &P, long long i, floa
 // --------------------------------------------------------------------------------------------------------------------
 // second half-step: stresses / pressure / electric field, free surface, ABS on the fields written here
 // --------------------------------------------------------------------------------------------------------------------
-template <int EQ, int DIM, bool EXACT>
-__device__ __forceinline__ void passB(const WsParams &P, const Pt<EXACT> &t)
+template <int EQ, int DIM, bool EXACT, typename PT>
+__device__ __forceinline__ void passB(const WsParams &P, const PT &t)
 {
     using A = Ar<EXACT>;
     const long long i = t.i;
@@ -259,37 +282,36 @@ __device__ __forceinline__ void passB(const WsParams &P, const Pt<EXACT> &t)
     const bool surf = fs && t.gy == 0;
     if (EQ == WS_EQ_ACOUSTIC) {
         // ForwardSolver3Dacoustic.cpp:192-225
-        float u = t.D(P.fld[F_VX], OP_XB);
+        float u = t.template D<F_VX, OP_XB>();
         u = t.cpx(u, PSI_VXX, false);
-        float w = t.D(P.fld[F_VY], OP_YB);
+        float w = t.template D<F_VY, OP_YB>();
         w = t.cpy(w, PSI_VYY, false);
         u = A::add(u, w);
         if (DIM == 3) {
-            w = t.D(P.fld[F_VZ], OP_ZB);
+            w = t.template D<F_VZ, OP_ZB>();
             w = t.cpz(w, PSI_VZZ, false);
             u = A::add(u, w);
         }
-        u = A::mul(u, P.mat[M_PW][i]);
-        float p = A::add(P.fld[F_P][i], u);
+        u = A::mul(u, t.template mat<M_PW>());
+        float p = A::add(t.template fld<F_P>(), u);
         p = A::mul(p, damp);
         if (surf)
             p = A::mul(p, 0.0f);
-        P.fld[F_P][i] = p;
+        t.template put<F_P>(p);
     } else if (EQ == WS_EQ_ELASTIC || EQ == WS_EQ_VISCOELASTIC) {
-        const float *vx = P.fld[F_VX], *vy = P.fld[F_VY], *vz = P.fld[F_VZ];
-        float vxx = t.D(vx, OP_XB);
-        float vyy = t.D(vy, OP_YB); // plain Dyb even with a free surface (ForwardSolver3Delastic.cpp:289)
+        float vxx = t.template D<F_VX, OP_XB>();
+        float vyy = t.template D<F_VY, OP_YB>(); // plain Dyb even with a free surface (ForwardSolver3Delastic.cpp:289)
         float vzz = 0.0f;
         if (DIM == 3)
-            vzz = t.D(vz, OP_ZB);
+            vzz = t.template D<F_VZ, OP_ZB>();
         vxx = t.cpx(vxx, PSI_VXX, false);
         vyy = t.cpy(vyy, PSI_VYY, false);
         if (DIM == 3)
             vzz = t.cpz(vzz, PSI_VZZ, false);
-        float sxx = P.fld[F_SXX][i], syy = P.fld[F_SYY][i], szz = 0.0f;
+        float sxx = t.template fld<F_SXX>(), syy = t.template fld<F_SYY>(), szz = 0.0f;
         if (DIM == 3)
-            szz = P.fld[F_SZZ][i];
-        const float pi = P.mat[M_PW][i], mu = P.mat[M_MU][i];
+            szz = t.template fld<F_SZZ>();
+        const float pi = t.template mat<M_PW>(), mu = t.template mat<M_MU>();
         float optp = 0.f, opts = 0.f, tauP = 0.f, tauS = 0.f;
         if (EQ == WS_EQ_ELASTIC) {
             // ForwardSolver3Delastic.cpp:297-314, ForwardSolver2Delastic.cpp:224-241
@@ -316,8 +338,8 @@ __device__ __forceinline__ void passB(const WsParams &P, const Pt<EXACT> &t)
             }
         } else {
             // ForwardSolver3Dviscoelastic.cpp:279-352, ForwardSolver2Dviscoelastic.cpp:220-262
-            tauP = P.mat[M_TAUP][i];
-            tauS = P.mat[M_TAUS][i];
+            tauP = t.template mat<M_TAUP>();
+            tauS = t.template mat<M_TAUS>();
             optp = A::add(1.0f, A::mul(P.fL, tauP)); // onePlusLtauP = 1 + L*tauP (:109-112)
             opts = A::add(1.0f, A::mul(P.fL, tauS));
             float u = A::add(vxx, vyy);
@@ -327,16 +349,16 @@ __device__ __forceinline__ void passB(const WsParams &P, const Pt<EXACT> &t)
             for (int l = 0; l < P.L; l++) {
                 float u2 = A::mul(P.invRelaxTime[l], u);
                 u2 = A::mul(u2, tauP);
-                float *r = P.fld[F_R0 + 6 * l + RC_XX] + i;
-                sxx = A::madd(P.DThalf, *r, sxx);
-                *r = A::sub(A::mul(*r, P.viscoCoeff1[l]), u2);
-                r = P.fld[F_R0 + 6 * l + RC_YY] + i;
-                syy = A::madd(P.DThalf, *r, syy);
-                *r = A::sub(A::mul(*r, P.viscoCoeff1[l]), u2);
+                float r = t.template rget<RC_XX>(l);
+                sxx = A::madd(P.DThalf, r, sxx);
+                t.template rput<RC_XX>(l, A::sub(A::mul(r, P.viscoCoeff1[l]), u2));
+                r = t.template rget<RC_YY>(l);
+                syy = A::madd(P.DThalf, r, syy);
+                t.template rput<RC_YY>(l, A::sub(A::mul(r, P.viscoCoeff1[l]), u2));
                 if (DIM == 3) {
-                    r = P.fld[F_R0 + 6 * l + RC_ZZ] + i;
-                    szz = A::madd(P.DThalf, *r, szz);
-                    *r = A::sub(A::mul(*r, P.viscoCoeff1[l]), u2);
+                    r = t.template rget<RC_ZZ>(l);
+                    szz = A::madd(P.DThalf, r, szz);
+                    t.template rput<RC_ZZ>(l, A::sub(A::mul(r, P.viscoCoeff1[l]), u2));
                 }
             }
             u = A::mul(u, optp);
@@ -344,68 +366,68 @@ __device__ __forceinline__ void passB(const WsParams &P, const Pt<EXACT> &t)
             syy = A::add(syy, u);
             if (DIM == 3)
                 szz = A::add(szz, u);
-            auto normalPart = [&](float S, int rc, float e) {
+            auto normalPart = [&](float S, auto rc, float e) {
+                constexpr int RC = decltype(rc)::value;
                 float uu = A::mul(e, mu);
                 uu = A::mul(uu, 2.0f);
                 for (int l = 0; l < P.L; l++) {
                     float u2 = A::mul(P.invRelaxTime[l], uu);
                     u2 = A::mul(u2, tauS);
-                    float *r = P.fld[F_R0 + 6 * l + rc] + i;
-                    float R = A::add(*r, u2);
+                    float R = A::add(t.template rget<RC>(l), u2);
                     R = A::mul(R, P.viscoCoeff2[l]);
                     S = A::madd(P.DThalf, R, S);
-                    *r = R;
+                    t.template rput<RC>(l, R);
                 }
                 uu = A::mul(uu, opts);
                 return A::sub(S, uu);
             };
             if (DIM == 3) {
-                sxx = normalPart(sxx, RC_XX, A::add(vyy, vzz));
-                syy = normalPart(syy, RC_YY, A::add(vxx, vzz));
-                szz = normalPart(szz, RC_ZZ, A::add(vxx, vyy));
+                sxx = normalPart(sxx, IC<RC_XX>{}, A::add(vyy, vzz));
+                syy = normalPart(syy, IC<RC_YY>{}, A::add(vxx, vzz));
+                szz = normalPart(szz, IC<RC_ZZ>{}, A::add(vxx, vyy));
             } else {
-                sxx = normalPart(sxx, RC_XX, vyy);
-                syy = normalPart(syy, RC_YY, vxx);
+                sxx = normalPart(sxx, IC<RC_XX>{}, vyy);
+                syy = normalPart(syy, IC<RC_YY>{}, vxx);
             }
         }
         // shear stresses: ForwardSolver3Delastic.cpp:331-382, ForwardSolver3Dviscoelastic.cpp:355-416
         {
-            float u = t.D(vx, OP_YF);
+            float u = t.template D<F_VX, OP_YF>();
             u = t.cpy(u, PSI_VXY, true);
-            float w = t.D(vy, OP_XF);
+            float w = t.template D<F_VY, OP_XF>();
             w = t.cpx(w, PSI_VYX, true);
             u = A::add(u, w);
-            float s = P.fld[F_SXY][i];
+            float s = t.template fld<F_SXY>();
             if (EQ == WS_EQ_ELASTIC)
-                s = A::add(s, A::mul(u, P.mat[M_MUXY][i]));
+                s = A::add(s, A::mul(u, t.template mat<M_MUXY>()));
             else
-                s = viscoShear<EXACT>(P, i, s, RC_XY, u, P.mat[M_MUXY][i], P.mat[M_TSXY][i], opts);
-            P.fld[F_SXY][i] = A::mul(s, damp);
+                s = viscoShear<EXACT, RC_XY>(P, t, s, u, t.template mat<M_MUXY>(), t.template mat<M_TSXY>(), opts);
+            t.template put<F_SXY>(A::mul(s, damp));
         }
         if (DIM == 3) {
-            float u = t.D(vx, OP_ZF);
+            float u = t.template D<F_VX, OP_ZF>();
             u = t.cpz(u, PSI_VXZ, true);
-            float w = t.D(vz, OP_XF);
+            float w = t.template D<F_VZ, OP_XF>();
             w = t.cpx(w, PSI_VZX, true);
             u = A::add(u, w);
-            float s = P.fld[F_SXZ][i];
+            float s = t.template fld<F_SXZ>();
             if (EQ == WS_EQ_ELASTIC)
-                s = A::add(s, A::mul(u, P.mat[M_MUXZ][i]));
+                s = A::add(s, A::mul(u, t.template mat<M_MUXZ>()));
             else
-                s = viscoShear<EXACT>(P, i, s, RC_XZ, u, P.mat[M_MUXZ][i], P.mat[M_TSXZ][i], opts);
-            P.fld[F_SXZ][i] = A::mul(s, damp);
+                s = viscoShear<EXACT, RC_XZ>(P, t, s, u, t.template mat<M_MUXZ>(), t.template mat<M_TSXZ>(), opts);
+            t.template put<F_SXZ>(A::mul(s, damp));
 
-            u = t.D(vy, OP_ZF);
+            u = t.template D<F_VY, OP_ZF>();
             u = t.cpz(u, PSI_VYZ, true);
-            w = t.D(vz, OP_YF);
+            w = t.template D<F_VZ, OP_YF>();
             w = t.cpy(w, PSI_VZY, true);
             u = A::add(u, w);
-            s = P.fld[F_SYZ][i];
+            s = t.template fld<F_SYZ>();
             if (EQ == WS_EQ_ELASTIC)
-                s = A::add(s, A::mul(u, P.mat[M_MUYZ][i]));
+                s = A::add(s, A::mul(u, t.template mat<M_MUYZ>()));
             else
-                s = viscoShear<EXACT>(P, i, s, RC_YZ, u, P.mat[M_MUYZ][i], P.mat[M_TSYZ][i], opts);
-            P.fld[F_SYZ][i] = A::mul(s, damp);
+                s = viscoShear<EXACT, RC_YZ>(P, t, s, u, t.template mat<M_MUYZ>(), t.template mat<M_TSYZ>(), opts);
+            t.template put<F_SYZ>(A::mul(s, damp));
         }
         if (surf) {
             const int k = t.surfaceIndex();
@@ -424,9 +446,9 @@ __device__ __forceinline__ void passB(const WsParams &P, const Pt<EXACT> &t)
             } else {
                 // FreeSurface3Dviscoelastic.cpp:17-75, FreeSurface2Dviscoelastic.cpp:15-63
                 for (int l = 0; l < P.L; l++) {
-                    sxx = A::msub(P.DThalf, A::mul(1.0f, P.fld[F_R0 + 6 * l + RC_XX][i]), sxx);
+                    sxx = A::msub(P.DThalf, A::mul(1.0f, t.template rget<RC_XX>(l)), sxx);
                     if (DIM == 3)
-                        szz = A::msub(P.DThalf, A::mul(1.0f, P.fld[F_R0 + 6 * l + RC_ZZ][i]), szz);
+                        szz = A::msub(P.DThalf, A::mul(1.0f, t.template rget<RC_ZZ>(l)), szz);
                 }
                 float tmp = A::mul(P.sH[k], hor);
                 sxx = A::add(sxx, tmp);
@@ -439,104 +461,99 @@ __device__ __forceinline__ void passB(const WsParams &P, const Pt<EXACT> &t)
                 for (int l = 0; l < P.L; l++) {
                     const float th = A::mul(P.sRH[l][k], hor);
                     const float tv = A::mul(P.sRV[l][k], vyy);
-                    float *r = P.fld[F_R0 + 6 * l + RC_XX] + i;
-                    float R = A::sub(A::add(*r, th), tv);
-                    *r = R;
+                    float R = A::sub(A::add(t.template rget<RC_XX>(l), th), tv);
+                    t.template rput<RC_XX>(l, R);
                     sxx = A::madd(P.DThalf, A::mul(1.0f, R), sxx);
                     if (DIM == 3) {
-                        r = P.fld[F_R0 + 6 * l + RC_ZZ] + i;
-                        R = A::sub(A::add(*r, th), tv);
-                        *r = R;
+                        R = A::sub(A::add(t.template rget<RC_ZZ>(l), th), tv);
+                        t.template rput<RC_ZZ>(l, R);
                         szz = A::madd(P.DThalf, A::mul(1.0f, R), szz);
                     }
-                    r = P.fld[F_R0 + 6 * l + RC_YY] + i;
-                    *r = A::mul(*r, 0.0f);
+                    t.template rput<RC_YY>(l, A::mul(t.template rget<RC_YY>(l), 0.0f));
                 }
                 syy = A::mul(syy, 0.0f);
             }
         }
-        P.fld[F_SXX][i] = A::mul(sxx, damp);
-        P.fld[F_SYY][i] = A::mul(syy, damp);
+        t.template put<F_SXX>(A::mul(sxx, damp));
+        t.template put<F_SYY>(A::mul(syy, damp));
         if (DIM == 3)
-            P.fld[F_SZZ][i] = A::mul(szz, damp);
+            t.template put<F_SZZ>(A::mul(szz, damp));
     } else if (EQ == WS_EQ_SH || EQ == WS_EQ_VISCOSH) {
         // ForwardSolver2Dsh.cpp:162-192, ForwardSolver2Dviscosh.cpp:190-236
-        const float *vz = P.fld[F_VZ];
         float opts = 0.f;
         if (EQ == WS_EQ_VISCOSH)
-            opts = A::add(1.0f, A::mul(P.fL, P.mat[M_TAUS][i]));
-        float u = t.D(vz, OP_XF);
+            opts = A::add(1.0f, A::mul(P.fL, t.template mat<M_TAUS>()));
+        float u = t.template D<F_VZ, OP_XF>();
         u = t.cpx(u, PSI_VZX, true);
-        float s = P.fld[F_SXZ][i];
+        float s = t.template fld<F_SXZ>();
         if (EQ == WS_EQ_SH)
-            s = A::add(s, A::mul(u, P.mat[M_MUXZ][i]));
+            s = A::add(s, A::mul(u, t.template mat<M_MUXZ>()));
         else
-            s = viscoShear<EXACT>(P, i, s, RC_XZ, u, P.mat[M_MUXZ][i], P.mat[M_TSXZ][i], opts);
-        P.fld[F_SXZ][i] = A::mul(s, damp);
-        u = t.D(vz, OP_YF);
+            s = viscoShear<EXACT, RC_XZ>(P, t, s, u, t.template mat<M_MUXZ>(), t.template mat<M_TSXZ>(), opts);
+        t.template put<F_SXZ>(A::mul(s, damp));
+        u = t.template D<F_VZ, OP_YF>();
         u = t.cpy(u, PSI_VZY, true);
-        s = P.fld[F_SYZ][i];
+        s = t.template fld<F_SYZ>();
         if (EQ == WS_EQ_SH)
-            s = A::add(s, A::mul(u, P.mat[M_MUYZ][i]));
+            s = A::add(s, A::mul(u, t.template mat<M_MUYZ>()));
         else
-            s = viscoShear<EXACT>(P, i, s, RC_YZ, u, P.mat[M_MUYZ][i], P.mat[M_TSYZ][i], opts);
-        P.fld[F_SYZ][i] = A::mul(s, damp);
+            s = viscoShear<EXACT, RC_YZ>(P, t, s, u, t.template mat<M_MUYZ>(), t.template mat<M_TSYZ>(), opts);
+        t.template put<F_SYZ>(A::mul(s, damp));
     } else {
         // EM: r_l = Cc_l r_l + Cd_l e ;  e = Ca e + Cb (curl - DT sum r_l)
-        auto updateE = [&](int fslot, int axis, float curl) {
-            float e = P.fld[fslot][i];
+        auto updateE = [&](auto fslot, auto axisTag, float curl) {
+            constexpr int FS = decltype(fslot)::value, AXIS = decltype(axisTag)::value;
+            float e = t.template fld<FS>();
             for (int l = 0; l < P.L; l++) {
-                float *r = P.fld[F_R0 + 6 * l + axis] + i;
-                const float a = A::mul(P.Cc[l], *r);
-                const float b = A::mul(P.mat[M_CD0 + 3 * l + axis][i], e);
-                *r = A::add(b, a);
+                const float a = A::mul(P.Cc[l], t.template rget<AXIS>(l));
+                const float b = A::mul(t.template cd<AXIS>(l), e);
+                t.template rput<AXIS>(l, A::add(b, a));
             }
             for (int l = 0; l < P.L; l++)
-                curl = A::msub(P.DT, P.fld[F_R0 + 6 * l + axis][i], curl);
-            curl = A::mul(curl, P.mat[M_CBX + axis][i]);
-            const float ca = A::mul(P.mat[M_CAX + axis][i], e);
+                curl = A::msub(P.DT, t.template rget<AXIS>(l), curl);
+            curl = A::mul(curl, t.template mat<M_CBX + AXIS>());
+            const float ca = A::mul(t.template mat<M_CAX + AXIS>(), e);
             e = A::add(ca, curl);
-            P.fld[fslot][i] = A::mul(e, damp);
+            t.template put<FS>(A::mul(e, damp));
         };
         if (EQ == WS_EQ_TMEM || EQ == WS_EQ_VISCOTMEM) {
             // ForwardSolver2Dtmem.cpp:148-163, ForwardSolver2Dviscotmem.cpp:176-197
-            float u = t.D(P.fld[F_HY], OP_XB);
-            float w = t.D(P.fld[F_HX], OP_YB);
+            float u = t.template D<F_HY, OP_XB>();
+            float w = t.template D<F_HX, OP_YB>();
             u = t.cpx(u, PSI_HYX, false);
             w = t.cpy(w, PSI_HXY, false);
             u = A::sub(u, w);
-            updateE(F_EZ, RC_Z, u);
+            updateE(IC<F_EZ>{}, IC<RC_Z>{}, u);
         } else {
-            const float *hx = P.fld[F_HX], *hy = P.fld[F_HY], *hz = P.fld[F_HZ];
             if (DIM == 3) {
                 // ForwardSolver3Demem.cpp:189-232
-                float u = t.D(hz, OP_YB);
-                float w = t.D(hy, OP_ZB);
+                float u = t.template D<F_HZ, OP_YB>();
+                float w = t.template D<F_HY, OP_ZB>();
                 u = t.cpy(u, PSI_HZY, false);
                 w = t.cpz(w, PSI_HYZ, false);
                 u = A::sub(u, w);
-                updateE(F_EX, RC_X, u);
-                u = t.D(hx, OP_ZB);
-                w = t.D(hz, OP_XB);
+                updateE(IC<F_EX>{}, IC<RC_X>{}, u);
+                u = t.template D<F_HX, OP_ZB>();
+                w = t.template D<F_HZ, OP_XB>();
                 u = t.cpz(u, PSI_HXZ, false);
                 w = t.cpx(w, PSI_HZX, false);
                 u = A::sub(u, w);
-                updateE(F_EY, RC_Y, u);
-                u = t.D(hy, OP_XB);
-                w = t.D(hx, OP_YB);
+                updateE(IC<F_EY>{}, IC<RC_Y>{}, u);
+                u = t.template D<F_HY, OP_XB>();
+                w = t.template D<F_HX, OP_YB>();
                 u = t.cpx(u, PSI_HYX, true); // half profile: CPMLEM3D.cpp:69
                 w = t.cpy(w, PSI_HXY, false);
                 u = A::sub(u, w);
-                updateE(F_EZ, RC_Z, u);
+                updateE(IC<F_EZ>{}, IC<RC_Z>{}, u);
             } else {
                 // ForwardSolver2Demem.cpp:148-169, ForwardSolver2Dviscoemem.cpp:195-222
-                float u = t.D(hz, OP_YB);
+                float u = t.template D<F_HZ, OP_YB>();
                 u = t.cpy(u, PSI_HZY, false);
-                updateE(F_EX, RC_X, u);
-                float w = t.D(hz, OP_XB);
+                updateE(IC<F_EX>{}, IC<RC_X>{}, u);
+                float w = t.template D<F_HZ, OP_XB>();
                 w = t.cpx(w, PSI_HZX, false);
                 u = A::mul(-1.0f, w);
-                updateE(F_EY, RC_Y, u);
+                updateE(IC<F_EY>{}, IC<RC_Y>{}, u);
             }
         }
     }

@@ -1,0 +1,148 @@
+// ws_kernels_march.cu — instantiation + launch dispatch of the marching kernels (ws_kernels_march.cuh).
+// Built once per FD order (-DWS_MARCH_Q=<q>: the kernels of that order) and once without (the dispatcher), so that the
+// orders compile in parallel; the host emulation build of the test suite (-DWS_MARCH_ALL) takes everything in one unit.
+#include "../../include/wavesim.h"
+#include "ws_kernels_march.cuh"
+#include "ws_launch.hpp"
+
+#include <cstdlib>
+
+#ifdef WS_EMULATE
+#define WS_LAUNCH_COOP(kern, grid, block, smem, stream, ...) wsemu::launchCoop(kern, dim3(grid), dim3(block), smem, __VA_ARGS__)
+#else
+#define WS_LAUNCH_COOP(kern, grid, block, smem, stream, ...) kern<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#endif
+
+namespace {
+
+template <int EQ, int DIM, int Q, int PASS, int NST> void launchK(const WsParams &P, dim3 grid, size_t smem, cudaStream_t st)
+{
+    auto k = wsmarch::kMarch<EQ, DIM, Q, PASS, NST>;
+#ifndef WS_EMULATE
+    static bool attr = false; // per instantiation
+    if (!attr) {
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
+        attr = true;
+    }
+#endif
+    const int nthr = wsmarch::Geo<DIM, Q>::NTHR;
+    WS_LAUNCH_COOP(k, grid, nthr, smem, st, P);
+}
+
+template <int EQ, int DIM, int Q> void launchT(const WsParams &P, int pass, cudaStream_t st)
+{
+    using G = wsmarch::Geo<DIM, Q>;
+    const int ny = P.yhi - P.ylo;
+    const dim3 grid((P.nx + G::TX - 1) / G::TX, (P.nz + G::TZ - 1) / G::TZ, (ny + P.marchChunk - 1) / P.marchChunk);
+    const size_t stage = sizeof(float) * (pass == 0 ? wsmarch::stageFloats<EQ, DIM, Q, 0>(P.L) : wsmarch::stageFloats<EQ, DIM, Q, 1>(P.L));
+    // ring depth: 4 stages when two thread blocks of that size fit an SM, else 2 (P.marchStages overrides: developer switch)
+    int nst = 4 * stage * 2 <= 220 * 1024 ? 4 : 2;
+    if (P.marchStages == 2 || P.marchStages == 4)
+        nst = P.marchStages;
+    if (pass == 0) {
+        if (nst == 4)
+            launchK<EQ, DIM, Q, 0, 4>(P, grid, 4 * stage, st);
+        else
+            launchK<EQ, DIM, Q, 0, 2>(P, grid, 2 * stage, st);
+    } else {
+        if (nst == 4)
+            launchK<EQ, DIM, Q, 1, 4>(P, grid, 4 * stage, st);
+        else
+            launchK<EQ, DIM, Q, 1, 2>(P, grid, 2 * stage, st);
+    }
+}
+
+template <int EQ, int Q> void launchD(const WsParams &P, int pass, cudaStream_t st)
+{
+    if (P.dim == 3)
+        launchT<EQ, 3, Q>(P, pass, st);
+    else
+        launchT<EQ, 2, Q>(P, pass, st);
+}
+
+template <int Q> void launchQ(const WsParams &P, int pass, cudaStream_t st)
+{
+    switch (P.eq) {
+    case WS_EQ_ACOUSTIC: launchD<WS_EQ_ACOUSTIC, Q>(P, pass, st); break;
+    case WS_EQ_ELASTIC: launchD<WS_EQ_ELASTIC, Q>(P, pass, st); break;
+    case WS_EQ_VISCOELASTIC: launchD<WS_EQ_VISCOELASTIC, Q>(P, pass, st); break;
+    case WS_EQ_SH: launchT<WS_EQ_SH, 2, Q>(P, pass, st); break;
+    case WS_EQ_VISCOSH: launchT<WS_EQ_VISCOSH, 2, Q>(P, pass, st); break;
+    case WS_EQ_TMEM: launchT<WS_EQ_TMEM, 2, Q>(P, pass, st); break;
+    case WS_EQ_VISCOTMEM: launchT<WS_EQ_VISCOTMEM, 2, Q>(P, pass, st); break;
+    case WS_EQ_EMEM: launchD<WS_EQ_EMEM, Q>(P, pass, st); break;
+    case WS_EQ_VISCOEMEM: launchD<WS_EQ_VISCOEMEM, Q>(P, pass, st); break;
+    default: break;
+    }
+}
+
+} // namespace
+
+#define WS_MARCH_NAME2(q) wsLaunchMarchQ##q
+#define WS_MARCH_NAME(q) WS_MARCH_NAME2(q)
+
+#ifdef WS_MARCH_Q
+void WS_MARCH_NAME(WS_MARCH_Q)(const WsParams &P, int pass, cudaStream_t st) { launchQ<WS_MARCH_Q>(P, pass, st); }
+#else
+
+#ifdef WS_MARCH_ALL
+void wsLaunchMarchQ2(const WsParams &P, int pass, cudaStream_t st) { launchQ<2>(P, pass, st); }
+void wsLaunchMarchQ4(const WsParams &P, int pass, cudaStream_t st) { launchQ<4>(P, pass, st); }
+void wsLaunchMarchQ6(const WsParams &P, int pass, cudaStream_t st) { launchQ<6>(P, pass, st); }
+void wsLaunchMarchQ8(const WsParams &P, int pass, cudaStream_t st) { launchQ<8>(P, pass, st); }
+void wsLaunchMarchQ10(const WsParams &P, int pass, cudaStream_t st) { launchQ<10>(P, pass, st); }
+void wsLaunchMarchQ12(const WsParams &P, int pass, cudaStream_t st) { launchQ<12>(P, pass, st); }
+#else
+void wsLaunchMarchQ2(const WsParams &P, int pass, cudaStream_t st);
+void wsLaunchMarchQ4(const WsParams &P, int pass, cudaStream_t st);
+void wsLaunchMarchQ6(const WsParams &P, int pass, cudaStream_t st);
+void wsLaunchMarchQ8(const WsParams &P, int pass, cudaStream_t st);
+void wsLaunchMarchQ10(const WsParams &P, int pass, cudaStream_t st);
+void wsLaunchMarchQ12(const WsParams &P, int pass, cudaStream_t st);
+#endif
+
+// every equation type and order; FMA arithmetic only (the exact-arithmetic parity mode stays on the per-point kernels)
+bool wsMarchSupported(const WsParams &P, bool exact)
+{
+    if (exact)
+        return false;
+    if (P.q < 2 || P.q > 12 || (P.q & 1))
+        return false;
+    return P.dim == 2 || P.dim == 3;
+}
+
+// planes per thread block: enough thread blocks to fill the 148 SMs several times over, but chunks long enough that
+// the q feed-only planes at the start of a chunk stay a small fraction
+void wsMarchPrepare(WsParams &P)
+{
+    const int TX = P.dim == 3 ? 32 : 128, TZ = P.dim == 3 ? 8 : 1;
+    const long long tiles = (long long)((P.nx + TX - 1) / TX) * ((P.nz + TZ - 1) / TZ);
+    const long long want = 148LL * 8;
+    long long nchunks = (want + tiles - 1) / tiles;
+    if (nchunks < 1)
+        nchunks = 1;
+    int chunk = (int)((P.nyl + nchunks - 1) / nchunks);
+    if (chunk < 32)
+        chunk = 32;
+    if (const char *e = getenv("WS_MARCH_CHUNK"))
+        chunk = atoi(e) > 0 ? atoi(e) : chunk;
+    P.marchChunk = chunk;
+    P.marchStages = getenv("WS_MARCH_STAGES") ? atoi(getenv("WS_MARCH_STAGES")) : 0;
+}
+
+int wsLaunchMarch(const WsParams &P, int pass, cudaStream_t st)
+{
+    if (P.yhi <= P.ylo || P.marchChunk <= 0)
+        return 0;
+    switch (P.q) {
+    case 2: wsLaunchMarchQ2(P, pass, st); break;
+    case 4: wsLaunchMarchQ4(P, pass, st); break;
+    case 6: wsLaunchMarchQ6(P, pass, st); break;
+    case 8: wsLaunchMarchQ8(P, pass, st); break;
+    case 10: wsLaunchMarchQ10(P, pass, st); break;
+    case 12: wsLaunchMarchQ12(P, pass, st); break;
+    default: return 0;
+    }
+    return 1;
+}
+#endif

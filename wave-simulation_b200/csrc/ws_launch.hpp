@@ -14,3 +14,8 @@ bool wsFastSupported(const WsParams &P, bool exact);
 void *wsFastPrepare(WsParams &P, int nyp);
 void wsFastRelease(void *maps);
 int wsLaunchFast(const WsParams &P, int pass, cudaStream_t st); // number of kernels launched (0 = not served)
+
+// marching kernels (ws_kernels_march.cu): every equation type, compile-time FD order, FMA arithmetic
+bool wsMarchSupported(const WsParams &P, bool exact);
+void wsMarchPrepare(WsParams &P); // fills P.marchChunk
+int wsLaunchMarch(const WsParams &P, int pass, cudaStream_t st); // number of kernels launched (0 = not served)
