@@ -32,6 +32,9 @@ struct dim3 {
 struct uint3 {
     unsigned x, y, z;
 };
+struct alignas(16) float4 {
+    float x, y, z, w;
+};
 namespace wsemu {
 inline thread_local uint3 g_blockIdx, g_threadIdx;
 inline thread_local dim3 g_blockDim, g_gridDim;

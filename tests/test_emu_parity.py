@@ -57,7 +57,9 @@ def test_emulated_marching_kernels_equal_per_point_kernels(cfg):
 def test_emulated_marching_kernels_partial_tiles_and_chunks(monkeypatch):
     """grid sizes that are not multiples of the tile, several y chunks per column (WS_MARCH_CHUNK)"""
     monkeypatch.setenv("WS_MARCH_CHUNK", "7")
-    for cfg in (("elastic", 3, 37, 23, 11, 8, 0, 1, 2, 5, 0), ("viscoelastic", 2, 150, 31, 1, 8, 0, 1, 2, 6, 2), ("acoustic", 3, 34, 20, 19, 8, 0, 0, 2, 5, 0)):
+    # the last three contain interior tiles (the thread-block-uniform fast path without edge rows / CPML / ABS)
+    for cfg in (("elastic", 3, 37, 23, 11, 8, 0, 1, 2, 5, 0), ("viscoelastic", 2, 150, 31, 1, 8, 0, 1, 2, 6, 2), ("acoustic", 3, 34, 20, 19, 8, 0, 0, 2, 5, 0),
+                ("acoustic", 3, 100, 24, 30, 4, 0, 0, 2, 5, 0), ("viscoelastic", 2, 300, 40, 1, 8, 0, 1, 2, 6, 2), ("viscoelastic", 3, 72, 20, 26, 4, 1, 1, 1, 4, 1)):
         eq, dim, nx, ny, nz, q, pol, fs, damp, W, L = cfg
         res = []
         for variant in (1, 2):

@@ -9,6 +9,7 @@
 // y-slab domain decomposition.
 #pragma once
 #include <cstdint>
+#include <type_traits>
 #ifdef WS_EMULATE
 // tests/emu/cuda_emu.hpp: host-side stand-in for the CUDA runtime and the device intrinsics used here, so that the
 // kernels and the whole C ABI can be exercised by the CPU-only test suite.  Never defined in the product build.
@@ -74,6 +75,9 @@ struct WsParams {
     int edge_policy;  // 0 truncate | 1 order-reduce
     int fastChunk, fastChunkEdge; // planes per thread block of the tiled kernels (interior / CPML-layer launch)
     int marchChunk;   // planes per thread block of the marching kernels (ws_kernels_march.cuh)
+    int marchDebug;   // developer switch (env WS_MARCH_DEBUG): 1 = stage the planes but skip the arithmetic and the stores
+    int marchStageR;  // 1 = the memory variables and EM Cd coefficients go through the stage ring too (0: read from global memory)
+    int marchLanes;   // developer switch (env WS_MARCH_LANES): x points per thread where both variants exist, 0 = chosen per half-step
     int marchStages;  // developer switch (env WS_MARCH_STAGES): depth of the stage ring, 0 = chosen from the stage size
     int fastDebug;    // developer switch (env WS_FAST_DEBUG): 1 = consumers skip the arithmetic and the stores (memory-side ceiling of the tiling)
     int fastFlags;    // developer switch (env WS_FAST_FLAGS): bit 0 = L2 eviction-priority hints on the TMA loads, bit 1 = CPML-layer tiles in a launch of their own (default 3)
@@ -112,9 +116,83 @@ struct WsParams {
     float fL;    // (float) L
 };
 
+// N consecutive x points handled by one thread (marching kernels: N = 4, or 1 where shared memory limits the number of
+// resident threads); every operation is applied lane by lane, so a lane sees exactly the operation sequence of the
+// one-point-per-thread kernels
+template <int N> struct alignas(4 * N) FV {
+    float v[N];
+    FV() = default;
+    __host__ __device__ __forceinline__ FV(float a)
+    {
+        for (int l = 0; l < N; l++)
+            v[l] = a;
+    }
+};
+using F4v = FV<4>;
+template <class T> struct WsVecN { static constexpr int n = 0; };
+template <int N> struct WsVecN<FV<N>> { static constexpr int n = N; };
+template <class X, class Y, class Z = float> struct WsVecOf {
+    static constexpr int n = WsVecN<X>::n > 0 ? WsVecN<X>::n : (WsVecN<Y>::n > 0 ? WsVecN<Y>::n : WsVecN<Z>::n);
+    using type = FV<(n > 0 ? n : 1)>;
+};
+__host__ __device__ __forceinline__ float wsLane(float a, int) { return a; }
+template <int N> __host__ __device__ __forceinline__ float wsLane(const FV<N> &a, int p) { return a.v[p]; }
+#define WS_IF_VEC2(X, Y) typename std::enable_if<(WsVecOf<X, Y>::n > 0), int>::type = 0
+#define WS_IF_VEC3(X, Y, Z) typename std::enable_if<(WsVecOf<X, Y, Z>::n > 0), int>::type = 0
+
+// lane-wise forms of a scalar policy, for any mix of float (broadcast) and FV<N> arguments
+template <class S> struct ArVec : S {
+    using S::add;
+    using S::madd;
+    using S::msub;
+    using S::mul;
+    using S::sub;
+    template <class X, class Y, WS_IF_VEC2(X, Y)> static __device__ __forceinline__ typename WsVecOf<X, Y>::type mul(const X &a, const Y &b)
+    {
+        typename WsVecOf<X, Y>::type r;
+#pragma unroll
+        for (int p = 0; p < WsVecOf<X, Y>::n; p++)
+            r.v[p] = S::mul(wsLane(a, p), wsLane(b, p));
+        return r;
+    }
+    template <class X, class Y, WS_IF_VEC2(X, Y)> static __device__ __forceinline__ typename WsVecOf<X, Y>::type add(const X &a, const Y &b)
+    {
+        typename WsVecOf<X, Y>::type r;
+#pragma unroll
+        for (int p = 0; p < WsVecOf<X, Y>::n; p++)
+            r.v[p] = S::add(wsLane(a, p), wsLane(b, p));
+        return r;
+    }
+    template <class X, class Y, WS_IF_VEC2(X, Y)> static __device__ __forceinline__ typename WsVecOf<X, Y>::type sub(const X &a, const Y &b)
+    {
+        typename WsVecOf<X, Y>::type r;
+#pragma unroll
+        for (int p = 0; p < WsVecOf<X, Y>::n; p++)
+            r.v[p] = S::sub(wsLane(a, p), wsLane(b, p));
+        return r;
+    }
+    template <class X, class Y, class Z, WS_IF_VEC3(X, Y, Z)>
+    static __device__ __forceinline__ typename WsVecOf<X, Y, Z>::type madd(const X &a, const Y &b, const Z &c)
+    {
+        typename WsVecOf<X, Y, Z>::type r;
+#pragma unroll
+        for (int p = 0; p < WsVecOf<X, Y, Z>::n; p++)
+            r.v[p] = S::madd(wsLane(a, p), wsLane(b, p), wsLane(c, p));
+        return r;
+    }
+    template <class X, class Y, class Z, WS_IF_VEC3(X, Y, Z)>
+    static __device__ __forceinline__ typename WsVecOf<X, Y, Z>::type msub(const X &a, const Y &b, const Z &c)
+    {
+        typename WsVecOf<X, Y, Z>::type r;
+#pragma unroll
+        for (int p = 0; p < WsVecOf<X, Y, Z>::n; p++)
+            r.v[p] = S::msub(wsLane(a, p), wsLane(b, p), wsLane(c, p));
+        return r;
+    }
+};
+
 // arithmetic policy: EXACT keeps every rounding of the reference statement sequence (no FMA contraction)
-template <bool EXACT> struct Ar;
-template <> struct Ar<true> {
+struct ArExact {
     static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
     static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
     static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
@@ -122,7 +200,7 @@ template <> struct Ar<true> {
     static __device__ __forceinline__ float msub(float a, float b, float c) { return __fsub_rn(c, __fmul_rn(a, b)); } // c - a*b
     static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
 };
-template <> struct Ar<false> {
+struct ArFma {
     // only the explicit multiply-adds fuse; everything else keeps its own rounding, so the result does not depend on
     // the compiler's contraction choices (general kernels, tiled kernels and the host emulation agree bit for bit)
     static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
@@ -132,6 +210,9 @@ template <> struct Ar<false> {
     static __device__ __forceinline__ float msub(float a, float b, float c) { return fmaf(-a, b, c); }
     static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
 };
+template <bool EXACT> struct Ar;
+template <> struct Ar<true> : ArVec<ArExact> {};
+template <> struct Ar<false> : ArVec<ArFma> {};
 
 // row class of coordinate `pos` on an axis of length n: 0..h-1 low edge rows, h interior, h+1..2h high edge rows
 __host__ __device__ __forceinline__ int wsRowClass(int pos, int n, int h)

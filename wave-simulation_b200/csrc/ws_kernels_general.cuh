@@ -13,6 +13,33 @@ template <int N> struct IC { // compile-time integer tag (array slots as argumen
     static constexpr int value = N;
 };
 
+// ABS3D.cpp:182-213 / ABS2D.cpp:141-172: damping factor of a point (1 outside the frame)
+__device__ __forceinline__ float wsAbsFactor(const WsParams &P, int x, int gy, int z)
+{
+    if (P.damping != 1)
+        return 1.0f;
+    const int W = P.W;
+    const int dx = min(x, P.nx - 1 - x), dy = min(gy, P.gny - 1 - gy);
+    int m;
+    if (P.dim == 3) {
+        const int dz = min(z, P.nz - 1 - z);
+        if (P.free_surface == 0) {
+            m = min(min(dx, dy), dz);
+        } else if (gy < W) {
+            m = (dz < W || dx < W) ? min(dx, dz) : W;
+        } else
+            m = min(min(dx, dy), dz);
+    } else {
+        if (P.free_surface == 0)
+            m = min(dx, dy);
+        else if (gy < W)
+            m = dx;
+        else
+            m = min(dx, dy);
+    }
+    return m < W ? __ldg(P.absCoeff + m) : 1.0f;
+}
+
 // Per-point bookkeeping shared by the per-point kernels below and the marching kernels (ws_kernels_march.cuh): indices,
 // row classes of the derivative tables, CPML slab positions, ABS factor.  The derivative itself (D<F, OP>) is supplied
 // by the derived point type, so both kernel families run the SAME statement sequence (passA / passB).
@@ -74,32 +101,7 @@ struct PtBase {
     __device__ __forceinline__ float cpy(float d, int slot, bool half) const { return cp(d, slot, ky, py, half ? P.cayh : P.cay, half ? P.cbyh : P.cby); }
     __device__ __forceinline__ float cpz(float d, int slot, bool half) const { return cp(d, slot, kz, pz, half ? P.cazh : P.caz, half ? P.cbzh : P.cbz); }
 
-    // ABS3D.cpp:182-213 / ABS2D.cpp:141-172: damping factor of this point (1 outside the frame)
-    __device__ __forceinline__ float absFactor() const
-    {
-        if (P.damping != 1)
-            return 1.0f;
-        const int W = P.W;
-        const int dx = min(x, P.nx - 1 - x), dy = min(gy, P.gny - 1 - gy);
-        int m;
-        if (P.dim == 3) {
-            const int dz = min(z, P.nz - 1 - z);
-            if (P.free_surface == 0) {
-                m = min(min(dx, dy), dz);
-            } else if (gy < W) {
-                m = (dz < W || dx < W) ? min(dx, dz) : W;
-            } else
-                m = min(min(dx, dy), dz);
-        } else {
-            if (P.free_surface == 0)
-                m = min(dx, dy);
-            else if (gy < W)
-                m = dx;
-            else
-                m = min(dx, dy);
-        }
-        return m < W ? __ldg(P.absCoeff + m) : 1.0f;
-    }
+    __device__ __forceinline__ float absFactor() const { return wsAbsFactor(P, x, gy, z); }
     __device__ __forceinline__ int surfaceIndex() const { return z * P.nx + x; }
 };
 
@@ -107,6 +109,7 @@ struct PtBase {
 template <bool EXACT>
 struct Pt : PtBase<EXACT> {
     using A = Ar<EXACT>;
+    using V = float;
     using PtBase<EXACT>::P;
     __device__ __forceinline__ Pt(const WsParams &P_, int x_, int ly_, int z_) : PtBase<EXACT>(P_, x_, ly_, z_) {}
     // row of matrix `op` applied to field f: ascending-column accumulation like a CSR SpMV
@@ -132,6 +135,11 @@ struct Pt : PtBase<EXACT> {
     template <int C> __device__ __forceinline__ float rget(int l) const { return P.fld[F_R0 + 6 * l + C][this->i]; }
     template <int C> __device__ __forceinline__ void rput(int l, float v) const { P.fld[F_R0 + 6 * l + C][this->i] = v; }
     template <int AXIS> __device__ __forceinline__ float cd(int l) const { return P.mat[M_CD0 + 3 * l + AXIS][this->i]; }
+    // free-surface scalings of this column (FreeSurfaceElastic.cpp:35-46, FreeSurfaceViscoelastic.cpp:38-95)
+    __device__ __forceinline__ float sH() const { return P.sH[this->surfaceIndex()]; }
+    __device__ __forceinline__ float sV() const { return P.sV[this->surfaceIndex()]; }
+    __device__ __forceinline__ float sRH(int l) const { return P.sRH[l][this->surfaceIndex()]; }
+    __device__ __forceinline__ float sRV(int l) const { return P.sRV[l][this->surfaceIndex()]; }
 };
 
 // --------------------------------------------------------------------------------------------------------------------
@@ -141,11 +149,11 @@ template <int EQ, int DIM, bool EXACT, typename PT>
 __device__ __forceinline__ void passA(const WsParams &P, const PT &t)
 {
     using A = Ar<EXACT>;
-    const long long i = t.i;
+    using V = typename PT::V; // float, or 4 consecutive x points (marching kernels)
     const bool fs = P.free_surface == 1;
     if (EQ == WS_EQ_ACOUSTIC) {
         // ForwardSolver3Dacoustic.cpp:131-187, ForwardSolver2Dacoustic.cpp:121-160
-        float u = t.template D<F_P, OP_XF>();
+        V u = t.template D<F_P, OP_XF>();
         u = t.cpx(u, PSI_P_X, true);
         u = A::mul(u, t.template mat<M_RIX>());
         t.template put<F_VX>(A::add(t.template fld<F_VX>(), u));
@@ -161,9 +169,9 @@ __device__ __forceinline__ void passA(const WsParams &P, const PT &t)
         }
     } else if (EQ == WS_EQ_ELASTIC || EQ == WS_EQ_VISCOELASTIC) {
         // ForwardSolver3Delastic.cpp:181-277, ForwardSolver2Delastic.cpp:163-208, ForwardSolver3Dviscoelastic.cpp:188-262
-        float u = t.template D<F_SXX, OP_XF>();
+        V u = t.template D<F_SXX, OP_XF>();
         u = t.cpx(u, PSI_SXX_X, true);
-        float w = (fs ? t.template D<F_SXY, OP_YB_FS>() : t.template D<F_SXY, OP_YB>());
+        V w = (fs ? t.template D<F_SXY, OP_YB_FS>() : t.template D<F_SXY, OP_YB>());
         w = t.cpy(w, PSI_SXY_Y, false);
         u = A::add(u, w);
         if (DIM == 3) {
@@ -201,8 +209,8 @@ __device__ __forceinline__ void passA(const WsParams &P, const PT &t)
         }
     } else if (EQ == WS_EQ_SH || EQ == WS_EQ_VISCOSH) {
         // ForwardSolver2Dsh.cpp:140-158
-        float u = t.template D<F_SXZ, OP_XB>();
-        float w = (fs ? t.template D<F_SYZ, OP_YB_FS>() : t.template D<F_SYZ, OP_YB>());
+        V u = t.template D<F_SXZ, OP_XB>();
+        V w = (fs ? t.template D<F_SYZ, OP_YB_FS>() : t.template D<F_SYZ, OP_YB>());
         u = t.cpx(u, PSI_SXZ_X, false);
         w = t.cpy(w, PSI_SYZ_Y, false);
         u = A::add(u, w);
@@ -210,11 +218,11 @@ __device__ __forceinline__ void passA(const WsParams &P, const PT &t)
         t.template put<F_VZ>(A::add(t.template fld<F_VZ>(), u));
     } else if (EQ == WS_EQ_TMEM || EQ == WS_EQ_VISCOTMEM) {
         // ForwardSolver2Dtmem.cpp:131-146
-        float u = t.template D<F_EZ, OP_YF>();
+        V u = t.template D<F_EZ, OP_YF>();
         u = t.cpy(u, PSI_EZY, true);
         u = A::mul(u, t.template mat<M_MIYZ>());
         t.template put<F_HX>(A::sub(t.template fld<F_HX>(), u));
-        float w = t.template D<F_EZ, OP_XF>();
+        V w = t.template D<F_EZ, OP_XF>();
         w = t.cpx(w, PSI_EZX, true);
         u = A::mul(-1.0f, w);
         u = A::mul(u, t.template mat<M_MIXZ>());
@@ -222,8 +230,8 @@ __device__ __forceinline__ void passA(const WsParams &P, const PT &t)
     } else if (EQ == WS_EQ_EMEM || EQ == WS_EQ_VISCOEMEM) {
         if (DIM == 3) {
             // ForwardSolver3Demem.cpp:154-187
-            float u = t.template D<F_EZ, OP_YF>();
-            float w = t.template D<F_EY, OP_ZF>();
+            V u = t.template D<F_EZ, OP_YF>();
+            V w = t.template D<F_EY, OP_ZF>();
             u = t.cpy(u, PSI_EZY, true);
             w = t.cpz(w, PSI_EYZ, true);
             u = A::sub(u, w);
@@ -238,8 +246,8 @@ __device__ __forceinline__ void passA(const WsParams &P, const PT &t)
             t.template put<F_HY>(A::sub(t.template fld<F_HY>(), u));
         }
         // ForwardSolver2Demem.cpp:136-146
-        float u = t.template D<F_EY, OP_XF>();
-        float w = t.template D<F_EX, OP_YF>();
+        V u = t.template D<F_EY, OP_XF>();
+        V w = t.template D<F_EX, OP_YF>();
         u = t.cpx(u, PSI_EYX, true);
         w = t.cpy(w, PSI_EXY, true);
         u = A::sub(u, w);
@@ -250,15 +258,17 @@ __device__ __forceinline__ void passA(const WsParams &P, const PT &t)
 
 // viscoelastic helpers (ForwardSolver3Dviscoelastic.cpp:284-416) -------------------------------------------------------
 template <bool EXACT, int RC, typename PT>
-__device__ __forceinline__ float viscoShear(const WsParams &P, const PT &t, float S, float u, float muAvg, float tauAvg, float onePlusLtauS)
+__device__ __forceinline__ typename PT::V viscoShear(const WsParams &P, const PT &t, typename PT::V S, typename PT::V u, typename PT::V muAvg, typename PT::V tauAvg,
+                                                     typename PT::V onePlusLtauS)
 {
     using A = Ar<EXACT>;
+    using V = typename PT::V;
     u = A::mul(u, muAvg);
     for (int l = 0; l < P.L; l++) {
-        float R = t.template rget<RC>(l);
+        V R = t.template rget<RC>(l);
         S = A::madd(P.DThalf, R, S);
         R = A::mul(R, P.viscoCoeff1[l]);
-        float u2 = A::mul(P.invRelaxTime[l], u);
+        V u2 = A::mul(P.invRelaxTime[l], u);
         u2 = A::mul(u2, tauAvg);
         R = A::sub(R, u2);
         R = A::mul(R, P.viscoCoeff2[l]);
@@ -276,15 +286,15 @@ template <int EQ, int DIM, bool EXACT, typename PT>
 __device__ __forceinline__ void passB(const WsParams &P, const PT &t)
 {
     using A = Ar<EXACT>;
-    const long long i = t.i;
+    using V = typename PT::V;
     const bool fs = P.free_surface == 1;
-    const float damp = t.absFactor();
+    const V damp = t.absFactor();
     const bool surf = fs && t.gy == 0;
     if (EQ == WS_EQ_ACOUSTIC) {
         // ForwardSolver3Dacoustic.cpp:192-225
-        float u = t.template D<F_VX, OP_XB>();
+        V u = t.template D<F_VX, OP_XB>();
         u = t.cpx(u, PSI_VXX, false);
-        float w = t.template D<F_VY, OP_YB>();
+        V w = t.template D<F_VY, OP_YB>();
         w = t.cpy(w, PSI_VYY, false);
         u = A::add(u, w);
         if (DIM == 3) {
@@ -293,29 +303,29 @@ __device__ __forceinline__ void passB(const WsParams &P, const PT &t)
             u = A::add(u, w);
         }
         u = A::mul(u, t.template mat<M_PW>());
-        float p = A::add(t.template fld<F_P>(), u);
+        V p = A::add(t.template fld<F_P>(), u);
         p = A::mul(p, damp);
         if (surf)
             p = A::mul(p, 0.0f);
         t.template put<F_P>(p);
     } else if (EQ == WS_EQ_ELASTIC || EQ == WS_EQ_VISCOELASTIC) {
-        float vxx = t.template D<F_VX, OP_XB>();
-        float vyy = t.template D<F_VY, OP_YB>(); // plain Dyb even with a free surface (ForwardSolver3Delastic.cpp:289)
-        float vzz = 0.0f;
+        V vxx = t.template D<F_VX, OP_XB>();
+        V vyy = t.template D<F_VY, OP_YB>(); // plain Dyb even with a free surface (ForwardSolver3Delastic.cpp:289)
+        V vzz = 0.0f;
         if (DIM == 3)
             vzz = t.template D<F_VZ, OP_ZB>();
         vxx = t.cpx(vxx, PSI_VXX, false);
         vyy = t.cpy(vyy, PSI_VYY, false);
         if (DIM == 3)
             vzz = t.cpz(vzz, PSI_VZZ, false);
-        float sxx = t.template fld<F_SXX>(), syy = t.template fld<F_SYY>(), szz = 0.0f;
+        V sxx = t.template fld<F_SXX>(), syy = t.template fld<F_SYY>(), szz = 0.0f;
         if (DIM == 3)
             szz = t.template fld<F_SZZ>();
-        const float pi = t.template mat<M_PW>(), mu = t.template mat<M_MU>();
-        float optp = 0.f, opts = 0.f, tauP = 0.f, tauS = 0.f;
+        const V pi = t.template mat<M_PW>(), mu = t.template mat<M_MU>();
+        V optp = 0.f, opts = 0.f, tauP = 0.f, tauS = 0.f;
         if (EQ == WS_EQ_ELASTIC) {
             // ForwardSolver3Delastic.cpp:297-314, ForwardSolver2Delastic.cpp:224-241
-            float u = A::add(vxx, vyy);
+            V u = A::add(vxx, vyy);
             if (DIM == 3)
                 u = A::add(u, vzz);
             u = A::mul(u, pi);
@@ -342,14 +352,14 @@ __device__ __forceinline__ void passB(const WsParams &P, const PT &t)
             tauS = t.template mat<M_TAUS>();
             optp = A::add(1.0f, A::mul(P.fL, tauP)); // onePlusLtauP = 1 + L*tauP (:109-112)
             opts = A::add(1.0f, A::mul(P.fL, tauS));
-            float u = A::add(vxx, vyy);
+            V u = A::add(vxx, vyy);
             if (DIM == 3)
                 u = A::add(u, vzz);
             u = A::mul(u, pi);
             for (int l = 0; l < P.L; l++) {
-                float u2 = A::mul(P.invRelaxTime[l], u);
+                V u2 = A::mul(P.invRelaxTime[l], u);
                 u2 = A::mul(u2, tauP);
-                float r = t.template rget<RC_XX>(l);
+                V r = t.template rget<RC_XX>(l);
                 sxx = A::madd(P.DThalf, r, sxx);
                 t.template rput<RC_XX>(l, A::sub(A::mul(r, P.viscoCoeff1[l]), u2));
                 r = t.template rget<RC_YY>(l);
@@ -366,14 +376,14 @@ __device__ __forceinline__ void passB(const WsParams &P, const PT &t)
             syy = A::add(syy, u);
             if (DIM == 3)
                 szz = A::add(szz, u);
-            auto normalPart = [&](float S, auto rc, float e) {
+            auto normalPart = [&](V S, auto rc, V e) {
                 constexpr int RC = decltype(rc)::value;
-                float uu = A::mul(e, mu);
+                V uu = A::mul(e, mu);
                 uu = A::mul(uu, 2.0f);
                 for (int l = 0; l < P.L; l++) {
-                    float u2 = A::mul(P.invRelaxTime[l], uu);
+                    V u2 = A::mul(P.invRelaxTime[l], uu);
                     u2 = A::mul(u2, tauS);
-                    float R = A::add(t.template rget<RC>(l), u2);
+                    V R = A::add(t.template rget<RC>(l), u2);
                     R = A::mul(R, P.viscoCoeff2[l]);
                     S = A::madd(P.DThalf, R, S);
                     t.template rput<RC>(l, R);
@@ -392,12 +402,12 @@ __device__ __forceinline__ void passB(const WsParams &P, const PT &t)
         }
         // shear stresses: ForwardSolver3Delastic.cpp:331-382, ForwardSolver3Dviscoelastic.cpp:355-416
         {
-            float u = t.template D<F_VX, OP_YF>();
+            V u = t.template D<F_VX, OP_YF>();
             u = t.cpy(u, PSI_VXY, true);
-            float w = t.template D<F_VY, OP_XF>();
+            V w = t.template D<F_VY, OP_XF>();
             w = t.cpx(w, PSI_VYX, true);
             u = A::add(u, w);
-            float s = t.template fld<F_SXY>();
+            V s = t.template fld<F_SXY>();
             if (EQ == WS_EQ_ELASTIC)
                 s = A::add(s, A::mul(u, t.template mat<M_MUXY>()));
             else
@@ -405,12 +415,12 @@ __device__ __forceinline__ void passB(const WsParams &P, const PT &t)
             t.template put<F_SXY>(A::mul(s, damp));
         }
         if (DIM == 3) {
-            float u = t.template D<F_VX, OP_ZF>();
+            V u = t.template D<F_VX, OP_ZF>();
             u = t.cpz(u, PSI_VXZ, true);
-            float w = t.template D<F_VZ, OP_XF>();
+            V w = t.template D<F_VZ, OP_XF>();
             w = t.cpx(w, PSI_VZX, true);
             u = A::add(u, w);
-            float s = t.template fld<F_SXZ>();
+            V s = t.template fld<F_SXZ>();
             if (EQ == WS_EQ_ELASTIC)
                 s = A::add(s, A::mul(u, t.template mat<M_MUXZ>()));
             else
@@ -430,15 +440,14 @@ __device__ __forceinline__ void passB(const WsParams &P, const PT &t)
             t.template put<F_SYZ>(A::mul(s, damp));
         }
         if (surf) {
-            const int k = t.surfaceIndex();
-            const float hor = DIM == 3 ? A::add(vxx, vzz) : vxx;
+            const V hor = DIM == 3 ? A::add(vxx, vzz) : vxx;
             if (EQ == WS_EQ_ELASTIC) {
                 // FreeSurface3Delastic.cpp:15-47, FreeSurface2Delastic.cpp:14-46, FreeSurface.cpp:13-20
-                float tmp = A::mul(P.sH[k], hor);
+                V tmp = A::mul(t.sH(), hor);
                 sxx = A::add(sxx, tmp);
                 if (DIM == 3)
                     szz = A::add(szz, tmp);
-                tmp = A::mul(P.sV[k], vyy);
+                tmp = A::mul(t.sV(), vyy);
                 sxx = A::sub(sxx, tmp);
                 if (DIM == 3)
                     szz = A::sub(szz, tmp);
@@ -450,18 +459,18 @@ __device__ __forceinline__ void passB(const WsParams &P, const PT &t)
                     if (DIM == 3)
                         szz = A::msub(P.DThalf, A::mul(1.0f, t.template rget<RC_ZZ>(l)), szz);
                 }
-                float tmp = A::mul(P.sH[k], hor);
+                V tmp = A::mul(t.sH(), hor);
                 sxx = A::add(sxx, tmp);
                 if (DIM == 3)
                     szz = A::add(szz, tmp);
-                tmp = A::mul(P.sV[k], vyy);
+                tmp = A::mul(t.sV(), vyy);
                 sxx = A::sub(sxx, tmp);
                 if (DIM == 3)
                     szz = A::sub(szz, tmp);
                 for (int l = 0; l < P.L; l++) {
-                    const float th = A::mul(P.sRH[l][k], hor);
-                    const float tv = A::mul(P.sRV[l][k], vyy);
-                    float R = A::sub(A::add(t.template rget<RC_XX>(l), th), tv);
+                    const V th = A::mul(t.sRH(l), hor);
+                    const V tv = A::mul(t.sRV(l), vyy);
+                    V R = A::sub(A::add(t.template rget<RC_XX>(l), th), tv);
                     t.template rput<RC_XX>(l, R);
                     sxx = A::madd(P.DThalf, A::mul(1.0f, R), sxx);
                     if (DIM == 3) {
@@ -480,12 +489,12 @@ __device__ __forceinline__ void passB(const WsParams &P, const PT &t)
             t.template put<F_SZZ>(A::mul(szz, damp));
     } else if (EQ == WS_EQ_SH || EQ == WS_EQ_VISCOSH) {
         // ForwardSolver2Dsh.cpp:162-192, ForwardSolver2Dviscosh.cpp:190-236
-        float opts = 0.f;
+        V opts = 0.f;
         if (EQ == WS_EQ_VISCOSH)
             opts = A::add(1.0f, A::mul(P.fL, t.template mat<M_TAUS>()));
-        float u = t.template D<F_VZ, OP_XF>();
+        V u = t.template D<F_VZ, OP_XF>();
         u = t.cpx(u, PSI_VZX, true);
-        float s = t.template fld<F_SXZ>();
+        V s = t.template fld<F_SXZ>();
         if (EQ == WS_EQ_SH)
             s = A::add(s, A::mul(u, t.template mat<M_MUXZ>()));
         else
@@ -501,25 +510,25 @@ __device__ __forceinline__ void passB(const WsParams &P, const PT &t)
         t.template put<F_SYZ>(A::mul(s, damp));
     } else {
         // EM: r_l = Cc_l r_l + Cd_l e ;  e = Ca e + Cb (curl - DT sum r_l)
-        auto updateE = [&](auto fslot, auto axisTag, float curl) {
+        auto updateE = [&](auto fslot, auto axisTag, V curl) {
             constexpr int FS = decltype(fslot)::value, AXIS = decltype(axisTag)::value;
-            float e = t.template fld<FS>();
+            V e = t.template fld<FS>();
             for (int l = 0; l < P.L; l++) {
-                const float a = A::mul(P.Cc[l], t.template rget<AXIS>(l));
-                const float b = A::mul(t.template cd<AXIS>(l), e);
+                const V a = A::mul(P.Cc[l], t.template rget<AXIS>(l));
+                const V b = A::mul(t.template cd<AXIS>(l), e);
                 t.template rput<AXIS>(l, A::add(b, a));
             }
             for (int l = 0; l < P.L; l++)
                 curl = A::msub(P.DT, t.template rget<AXIS>(l), curl);
             curl = A::mul(curl, t.template mat<M_CBX + AXIS>());
-            const float ca = A::mul(t.template mat<M_CAX + AXIS>(), e);
+            const V ca = A::mul(t.template mat<M_CAX + AXIS>(), e);
             e = A::add(ca, curl);
             t.template put<FS>(A::mul(e, damp));
         };
         if (EQ == WS_EQ_TMEM || EQ == WS_EQ_VISCOTMEM) {
             // ForwardSolver2Dtmem.cpp:148-163, ForwardSolver2Dviscotmem.cpp:176-197
-            float u = t.template D<F_HY, OP_XB>();
-            float w = t.template D<F_HX, OP_YB>();
+            V u = t.template D<F_HY, OP_XB>();
+            V w = t.template D<F_HX, OP_YB>();
             u = t.cpx(u, PSI_HYX, false);
             w = t.cpy(w, PSI_HXY, false);
             u = A::sub(u, w);
@@ -527,8 +536,8 @@ __device__ __forceinline__ void passB(const WsParams &P, const PT &t)
         } else {
             if (DIM == 3) {
                 // ForwardSolver3Demem.cpp:189-232
-                float u = t.template D<F_HZ, OP_YB>();
-                float w = t.template D<F_HY, OP_ZB>();
+                V u = t.template D<F_HZ, OP_YB>();
+                V w = t.template D<F_HY, OP_ZB>();
                 u = t.cpy(u, PSI_HZY, false);
                 w = t.cpz(w, PSI_HYZ, false);
                 u = A::sub(u, w);
@@ -547,10 +556,10 @@ __device__ __forceinline__ void passB(const WsParams &P, const PT &t)
                 updateE(IC<F_EZ>{}, IC<RC_Z>{}, u);
             } else {
                 // ForwardSolver2Demem.cpp:148-169, ForwardSolver2Dviscoemem.cpp:195-222
-                float u = t.template D<F_HZ, OP_YB>();
+                V u = t.template D<F_HZ, OP_YB>();
                 u = t.cpy(u, PSI_HZY, false);
                 updateE(IC<F_EX>{}, IC<RC_X>{}, u);
-                float w = t.template D<F_HZ, OP_XB>();
+                V w = t.template D<F_HZ, OP_XB>();
                 w = t.cpx(w, PSI_HZX, false);
                 u = A::mul(-1.0f, w);
                 updateE(IC<F_EY>{}, IC<RC_Y>{}, u);

@@ -15,9 +15,10 @@
 
 namespace {
 
-template <int EQ, int DIM, int Q, int PASS, int NST> void launchK(const WsParams &P, dim3 grid, size_t smem, cudaStream_t st)
+template <int EQ, int DIM, int Q, int PASS, int NST, int NL> void launchK(const WsParams &P, size_t smem, cudaStream_t st)
 {
-    auto k = wsmarch::kMarch<EQ, DIM, Q, PASS, NST>;
+    using G = wsmarch::Geo<DIM, Q, NL>;
+    auto k = wsmarch::kMarch<EQ, DIM, Q, PASS, NST, NL>;
 #ifndef WS_EMULATE
     static bool attr = false; // per instantiation
     if (!attr) {
@@ -25,31 +26,46 @@ template <int EQ, int DIM, int Q, int PASS, int NST> void launchK(const WsParams
         attr = true;
     }
 #endif
-    const int nthr = wsmarch::Geo<DIM, Q>::NTHR;
+    const int ny = P.yhi - P.ylo;
+    const dim3 grid((P.nx + G::TX - 1) / G::TX, (P.nz + G::TZ - 1) / G::TZ, (ny + P.marchChunk - 1) / P.marchChunk);
+    const int nthr = G::NTHR;
     WS_LAUNCH_COOP(k, grid, nthr, smem, st, P);
 }
 
+template <int EQ, int DIM, int Q, int PASS, int NL> void launchP(const WsParams &P, cudaStream_t st)
+{
+    const int Ls = P.marchStageR ? P.L : 0;
+    const size_t stage = sizeof(float) * wsmarch::stageFloats<EQ, DIM, Q, PASS, NL>(Ls);
+    // ring depth 2 (the plane after the one being computed is in flight): more resident thread blocks hide the latencies
+    // of the compute phase better than a deeper ring does (measured on all BASELINE configs; 3 is a developer switch)
+    int nst = 2;
+    if (P.marchStages == 2 || P.marchStages == 3)
+        nst = P.marchStages;
+    if (nst == 3)
+        launchK<EQ, DIM, Q, PASS, 3, NL>(P, 3 * stage, st);
+    else
+        launchK<EQ, DIM, Q, PASS, 2, NL>(P, 2 * stage, st);
+}
+
+// one x point per thread where the operands of a plane are so many that 4 points per thread would leave one thread
+// block of 4 warps per SM (3-D half-steps with memory variables); 4 points per thread otherwise
 template <int EQ, int DIM, int Q> void launchT(const WsParams &P, int pass, cudaStream_t st)
 {
-    using G = wsmarch::Geo<DIM, Q>;
-    const int ny = P.yhi - P.ylo;
-    const dim3 grid((P.nx + G::TX - 1) / G::TX, (P.nz + G::TZ - 1) / G::TZ, (ny + P.marchChunk - 1) / P.marchChunk);
-    const size_t stage = sizeof(float) * (pass == 0 ? wsmarch::stageFloats<EQ, DIM, Q, 0>(P.L) : wsmarch::stageFloats<EQ, DIM, Q, 1>(P.L));
-    // ring depth: 4 stages when two thread blocks of that size fit an SM, else 2 (P.marchStages overrides: developer switch)
-    int nst = 4 * stage * 2 <= 220 * 1024 ? 4 : 2;
-    if (P.marchStages == 2 || P.marchStages == 4)
-        nst = P.marchStages;
-    if (pass == 0) {
-        if (nst == 4)
-            launchK<EQ, DIM, Q, 0, 4>(P, grid, 4 * stage, st);
-        else
-            launchK<EQ, DIM, Q, 0, 2>(P, grid, 2 * stage, st);
-    } else {
-        if (nst == 4)
-            launchK<EQ, DIM, Q, 1, 4>(P, grid, 4 * stage, st);
-        else
-            launchK<EQ, DIM, Q, 1, 2>(P, grid, 2 * stage, st);
+    constexpr bool heavy = DIM == 3 && (EQ == WS_EQ_VISCOELASTIC || EQ == WS_EQ_VISCOEMEM);
+    if constexpr (heavy) {
+        const bool one = P.marchLanes == 1 || (P.marchLanes == 0 && pass == 1 && P.L > 0 && P.marchStageR);
+        if (one) {
+            if (pass == 0)
+                launchP<EQ, DIM, Q, 0, 1>(P, st);
+            else
+                launchP<EQ, DIM, Q, 1, 1>(P, st);
+            return;
+        }
     }
+    if (pass == 0)
+        launchP<EQ, DIM, Q, 0, 4>(P, st);
+    else
+        launchP<EQ, DIM, Q, 1, 4>(P, st);
 }
 
 template <int EQ, int Q> void launchD(const WsParams &P, int pass, cudaStream_t st)
@@ -115,7 +131,8 @@ bool wsMarchSupported(const WsParams &P, bool exact)
 // the q feed-only planes at the start of a chunk stay a small fraction
 void wsMarchPrepare(WsParams &P)
 {
-    const int TX = P.dim == 3 ? 32 : 128, TZ = P.dim == 3 ? 8 : 1;
+    const int TX = P.dim == 3 ? 64 : 256, TZ = P.dim == 3 ? 8 : 1;
+    P.marchLanes = getenv("WS_MARCH_LANES") ? atoi(getenv("WS_MARCH_LANES")) : 0;
     const long long tiles = (long long)((P.nx + TX - 1) / TX) * ((P.nz + TZ - 1) / TZ);
     const long long want = 148LL * 8;
     long long nchunks = (want + tiles - 1) / tiles;
@@ -128,6 +145,8 @@ void wsMarchPrepare(WsParams &P)
         chunk = atoi(e) > 0 ? atoi(e) : chunk;
     P.marchChunk = chunk;
     P.marchStages = getenv("WS_MARCH_STAGES") ? atoi(getenv("WS_MARCH_STAGES")) : 0;
+    P.marchDebug = getenv("WS_MARCH_DEBUG") ? atoi(getenv("WS_MARCH_DEBUG")) : 0;
+    P.marchStageR = getenv("WS_MARCH_STAGE_R") ? atoi(getenv("WS_MARCH_STAGE_R")) : 1;
 }
 
 int wsLaunchMarch(const WsParams &P, int pass, cudaStream_t st)

@@ -2,16 +2,19 @@
 // the warp-specialised TMA kernels (ws_kernels_fast.cu, 3-D elastic only) do not cover.
 //
 // 2.5-D blocking.  A thread block owns a TX x TZ tile of the x-z plane (a TX-wide strip of the row in 2-D) and marches
-// along y, the slowest axis; a thread owns one grid column (x, z).
-//   * y derivatives: every field that is differentiated along y lives in a REGISTER QUEUE of q+1 planes per thread;
-//     one global load per field and plane feeds it (prefetched one plane ahead), so each value is read from memory once
-//     per thread block instead of q times;
-//   * x / z derivatives: the plane of every field differentiated along x or z is staged, with its halo, in shared memory
-//     by 16-byte cp.async copies into a double buffer (plane y+1 is in flight while plane y is computed);
-//   * everything else (own-point operands, CPML memory variables, ABS factors, free surface) and the statement sequence
-//     itself are the ones of the per-point kernels: the point type below only replaces the derivative D<F, OP>() of
-//     wsgen::passA / passB, and the weights are applied in the same ascending-column order, so the results are
-//     bit-identical to the general kernels in FMA mode (checked by the tests).
+// along y, the slowest axis; a thread owns FOUR consecutive x points of one row (128-bit shared-memory loads, 128-bit
+// global stores, index arithmetic shared by the four points).
+//   * every operand of a plane is staged in shared memory by 16-byte cp.async copies into a ring of NST stages, so
+//     NST-1 planes are in flight while one is computed: the halo tiles of the fields differentiated along x or z, the
+//     plane that enters each y window, and the own-point operands (updated fields, model parameters, memory variables);
+//   * y derivatives: every field differentiated along y lives in a REGISTER QUEUE of q+1 planes per thread, fed from the
+//     staged plane y + q/2: each value is read from memory once per thread block instead of q times;
+//   * the statement sequence is the one of the per-point kernels: the point type below only supplies the operands of
+//     wsgen::passA / passB (derivatives D<F, OP>(), own-point values, CPML / ABS / free-surface terms) as 4-lane
+//     values, every lane sees the scalar operation order, and the weights are applied in the same ascending-column
+//     order, so the results are bit-identical to the per-point kernels in FMA mode (checked by the tests);
+//   * tiles and planes that lie inside the grid on every axis (no edge rows, no CPML / ABS layer) run an instantiation
+//     without any of the boundary code (a thread-block-uniform choice).
 // Which fields are staged / queued per (equation, dimension, half-step) is the table `spec` below; it restates which
 // operator the reference applies to which field (ForwardSolver/ForwardSolver{2D,3D}*.cpp, ForwardSolverEM/*.cpp run()).
 #pragma once
@@ -81,22 +84,25 @@ __host__ __device__ constexpr int findIn(const int *a, int n, int v)
     return -1;
 }
 
-template <int DIM, int Q> struct Geo {
+// NL = consecutive x points per thread: 4 (128-bit accesses, index arithmetic shared by the points) or 1 (more resident
+// threads per staged byte: the half-steps whose operands fill the shared memory, e.g. 3-D viscoelastic)
+template <int DIM, int Q, int NL> struct Geo {
     static constexpr int H = Q / 2;
     static constexpr int HX = H <= 4 ? 4 : 8; // x halo rounded to whole 16-byte copies
-    static constexpr int TX = DIM == 3 ? 32 : 128, TZ = DIM == 3 ? 8 : 1;
+    static constexpr int TX = DIM == 3 ? (NL == 4 ? 64 : 32) : (NL == 4 ? 256 : 128), TZ = DIM == 3 ? 8 : 1;
     static constexpr int HZ = DIM == 3 ? H : 0;
     static constexpr int LDX = TX + 2 * HX, NROW = TZ + 2 * HZ, TILE = LDX * NROW; // staged tile with halo
     static constexpr int NP = TX * TZ;                                            // plain tile (own points)
-    static constexpr int NTHR = TX * TZ;
+    static constexpr int LXN = TX / NL;                                           // threads per tile row
+    static constexpr int NTHR = LXN * TZ;
 };
 constexpr int MAXPLAIN = 3 + 6 + 10 + 4 * (6 + 3); // plain tiles per stage: feeds, own fields, model parameters, L x (R + Cd)
 
 // floats per stage
-template <int EQ, int DIM, int Q, int PASS> __host__ __device__ constexpr int stageFloats(int L)
+template <int EQ, int DIM, int Q, int PASS, int NL> __host__ __device__ constexpr int stageFloats(int L)
 {
     constexpr Lists S = spec(EQ, DIM, PASS);
-    using G = Geo<DIM, Q>;
+    using G = Geo<DIM, Q, NL>;
     return S.nt * G::TILE + (S.nq + S.nf + S.nm + L * (S.nr + S.nc)) * G::NP;
 }
 
@@ -112,37 +118,80 @@ __device__ __forceinline__ void cpAsync16(float *dst, const float *src)
 __device__ __forceinline__ void cpCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cpWait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 #endif
+template <int N> __device__ __forceinline__ FV<N> ldv(const float *p) { return *reinterpret_cast<const FV<N> *>(p); }
+template <int N> __device__ __forceinline__ void stv(float *p, const FV<N> &a) { *reinterpret_cast<FV<N> *>(p) = a; }
 
-// point of the marching kernels: derivatives from the staged plane (x, z) and the register queues (y), own-point
-// operands from the staged plain tiles
-template <int EQ, int DIM, int Q, int PASS>
-struct MPt : wsgen::PtBase<false> {
+// NL consecutive x points (x0 .. x0+NL-1) of row z on the plane being computed.
+// INTR = the points are known to be interior points of every axis (no edge rows, no CPML / ABS layer, not on the free
+// surface): a thread-block-uniform property of (tile, plane), so the boundary code disappears from that instantiation.
+template <int EQ, int DIM, int Q, int PASS, int NL, bool INTR>
+struct MPt {
     using A = Ar<false>;
-    using G = Geo<DIM, Q>;
+    using V = FV<NL>;
+    using G = Geo<DIM, Q, NL>;
+    static constexpr int H = Q / 2;
     static constexpr int NQ = spec(EQ, DIM, PASS).nq;
     static constexpr int O_Q = spec(EQ, DIM, PASS).nt * G::TILE, O_F = O_Q + NQ * G::NP, O_M = O_F + spec(EQ, DIM, PASS).nf * G::NP,
                          O_R = O_M + spec(EQ, DIM, PASS).nm * G::NP;
-    float *st;  // current stage: halo tiles [nt][TILE], then plain tiles [feeds | fields | model | R[l][nr] | Cd[l][nc]][NP]
-    int so, op; // own point inside a halo tile / a plain tile
-    int oC;     // offset of the Cd tiles (after the L * nr memory-variable tiles)
-    float (&q)[NQ][Q + 1];
+    const WsParams &P;
+    int x0, z, nAct; // nAct = lanes inside the grid (NL except in a ragged last column or an inactive row)
+    int ly, gy;
+    long long i;     // padded linear index of lane 0
+    int ry, rz;      // derivative row classes of the plane / the row
+    bool xEdge;      // some lane is an edge row of the x operators
+    int ky, kz;      // CPML slab indices of the plane / the row (-1 outside)
+    bool xLayer;     // some lane lies in an x CPML layer
+    float *st;       // current stage: halo tiles [nt][TILE], then plain tiles [feeds | fields | model | R[l][nr] | Cd[l][nc]][NP]
+    int so, op;      // lane 0 inside a halo tile / a plain tile
+    int oC;          // offset of the Cd tiles (after the L * nr memory-variable tiles)
+    bool stR;        // the memory variables and Cd coefficients are staged (else they are read from global memory)
+    V (&q)[NQ][Q + 1];
 
-    __device__ __forceinline__ MPt(const WsParams &P_, int x_, int ly_, int z_, int so_, int op_, float (&q_)[NQ][Q + 1])
-        : wsgen::PtBase<false>(P_, x_, ly_, z_), st(nullptr), so(so_), op(op_), oC(O_R + P_.L * spec(EQ, DIM, PASS).nr * G::NP), q(q_)
+    __device__ __forceinline__ MPt(const WsParams &P_, int x0_, int z_, int nAct_, int so_, int op_, V (&q_)[NQ][Q + 1])
+        : P(P_), x0(x0_), z(z_), nAct(nAct_), st(nullptr), so(so_), op(op_), oC(O_R + P_.L * spec(EQ, DIM, PASS).nr * G::NP), stR(P_.marchStageR != 0), q(q_)
     {
+        ly = gy = 0;
+        i = 0;
+        ry = rz = H;
+        ky = kz = -1;
+        xEdge = xLayer = false;
+        if (!INTR) {
+            rz = wsRowClass(z, P.nz, H);
+            xEdge = x0 < H || x0 + NL - 1 >= P.nx - H;
+            if (P.damping == 2) {
+                xLayer = x0 < P.W || x0 + NL - 1 >= P.nx - P.W;
+                if (DIM == 3)
+                    kz = wsCpmlIndex(z, P.nz, P.W);
+            }
+        }
+    }
+    // plane ly, whose lane-0 point has the padded linear index i_
+    __device__ __forceinline__ void setPlane(int ly_, long long i_)
+    {
+        ly = ly_;
+        gy = P.gy0 + ly_;
+        i = i_;
+        if (!INTR) {
+            ry = wsRowClass(gy, P.gny, H);
+            ky = -1;
+            if (P.damping == 2) {
+                ky = wsCpmlIndex(gy, P.gny, P.W);
+                if (P.free_surface != 0 && gy < P.W)
+                    ky = -1; // no CPML in the top layer with a free surface (CPML3D.cpp:320-328)
+            }
+        }
     }
 
-    template <int F, int OP> __device__ __forceinline__ float D() const
+    template <int F, int OP> __device__ __forceinline__ V D() const
     {
         constexpr int axis = OP < 6 ? (OP >> 1) : 1;
         constexpr int fw = (OP & 1) == 0 ? 1 : 0; // forward operators: taps -H+1..H, backward: -H..H-1
-        constexpr int H = Q / 2;
         constexpr Lists S = spec(EQ, DIM, PASS);
-        float acc = 0.0f;
+        V acc(0.0f);
         if constexpr (axis == 1) {
             constexpr int qi = findIn(S.qf, S.nq, F);
             if constexpr (qi >= 0) {
-                if (ry == H) { // interior row: weights from the constant bank, the zero tap of the table row skipped
+                if (INTR || ry == H) { // interior row: weights from the constant bank, the zero tap of the table row skipped
 #pragma unroll
                     for (int j = 0; j < Q; j++)
                         acc = A::madd(OP >= 6 ? P.cwy[j] : P.cw[j], q[qi][j + fw], acc);
@@ -153,81 +202,232 @@ struct MPt : wsgen::PtBase<false> {
                         acc = A::madd(__ldg(w + j), q[qi][j], acc);
                 }
             }
+        } else if constexpr (axis == 2) {
+            constexpr int ti = findIn(S.t, S.nt, F);
+            if constexpr (ti >= 0) {
+                const float *p = st + ti * G::TILE + so - H * G::LDX;
+                if (INTR || rz == H) {
+#pragma unroll
+                    for (int j = 0; j < Q; j++)
+                        acc = A::madd(P.cw[j], ldv<NL>(p + (j + fw) * G::LDX), acc);
+                } else {
+                    const float *__restrict__ w = P.tab + ((size_t)OP * (2 * H + 1) + rz) * (Q + 1);
+#pragma unroll
+                    for (int j = 0; j <= Q; j++)
+                        acc = A::madd(__ldg(w + j), ldv<NL>(p + j * G::LDX), acc);
+                }
+            }
         } else {
             constexpr int ti = findIn(S.t, S.nt, F);
             if constexpr (ti >= 0) {
-                constexpr int sd = axis == 0 ? 1 : G::LDX;
-                const float *p = st + ti * G::TILE + so - H * sd;
-                const int r = axis == 0 ? rx : rz;
-                if (r == H) {
+                // the row around the points: offsets -H .. H+NL-1 (NL = 4: aligned 16-byte loads from -HX on)
+                constexpr int HX = G::HX;
+                constexpr int W0 = NL == 4 ? HX : H; // w[W0 + o] = value at offset o from lane 0
+                float w[NL == 4 ? 2 * HX + 4 : 2 * H + 1];
+                if constexpr (NL == 4) {
+                    const float *p = st + ti * G::TILE + so - HX;
 #pragma unroll
-                    for (int j = 0; j < Q; j++)
-                        acc = A::madd(P.cw[j], p[(j + fw) * sd], acc);
+                    for (int k = 0; k < (2 * HX + 4) / 4; k++) {
+                        if (4 * k + 3 >= HX - H && 4 * k <= HX + H + 3) { // vectors that hold a tap of some lane
+                            const FV<4> t = ldv<4>(p + 4 * k);
+                            w[4 * k] = t.v[0]; w[4 * k + 1] = t.v[1]; w[4 * k + 2] = t.v[2]; w[4 * k + 3] = t.v[3];
+                        } else
+                            w[4 * k] = w[4 * k + 1] = w[4 * k + 2] = w[4 * k + 3] = 0.0f;
+                    }
                 } else {
-                    const float *__restrict__ w = P.tab + ((size_t)OP * (2 * H + 1) + r) * (Q + 1);
+                    const float *p = st + ti * G::TILE + so - H;
 #pragma unroll
-                    for (int j = 0; j <= Q; j++)
-                        acc = A::madd(__ldg(w + j), p[j * sd], acc);
+                    for (int k = 0; k <= 2 * H + NL - 1; k++)
+                        w[k] = p[k];
+                }
+                if (INTR || !xEdge) {
+#pragma unroll
+                    for (int l = 0; l < NL; l++) {
+                        float a = 0.0f;
+#pragma unroll
+                        for (int j = 0; j < Q; j++)
+                            a = A::madd(P.cw[j], w[W0 - H + j + fw + l], a);
+                        acc.v[l] = a;
+                    }
+                } else {
+#pragma unroll
+                    for (int l = 0; l < NL; l++) {
+                        const float *__restrict__ c = P.tab + ((size_t)OP * (2 * H + 1) + wsRowClass(x0 + l, P.nx, H)) * (Q + 1);
+                        float a = 0.0f;
+#pragma unroll
+                        for (int j = 0; j <= Q; j++)
+                            a = A::madd(__ldg(c + j), w[W0 - H + j + l], a);
+                        acc.v[l] = a;
+                    }
                 }
             }
         }
         return acc;
     }
+
+    // CPML.cpp:84-95 applyCPML on the lanes inside a layer: psi = b psi + a d ; d = d + psi (all memory variables are read
+    // before the first one is written)
+    __device__ __forceinline__ V cpx(V d, int slot, bool half) const
+    {
+        if (INTR || !xLayer)
+            return d;
+        const float *__restrict__ ca = half ? P.caxh : P.cax, *__restrict__ cb = half ? P.cbxh : P.cbx;
+        float *ps = P.psi[slot] + ((long long)ly * P.nz + z) * P.psiPitchX;
+        int k[NL], o[NL];
+        float old[NL];
+#pragma unroll
+        for (int l = 0; l < NL; l++) {
+            k[l] = l < nAct ? wsCpmlIndex(x0 + l, P.nx, P.W) : -1;
+            o[l] = wsPsiXIndex(x0 + l, P.W, P.psiDX);
+            old[l] = k[l] >= 0 ? __ldg(ps + o[l]) : 0.0f;
+        }
+#pragma unroll
+        for (int l = 0; l < NL; l++)
+            if (k[l] >= 0) {
+                float v = A::mul(old[l], __ldg(cb + k[l]));
+                const float t = A::mul(__ldg(ca + k[l]), d.v[l]);
+                v = A::add(v, t);
+                ps[o[l]] = v;
+                d.v[l] = A::add(d.v[l], v);
+            }
+        return d;
+    }
+    // a memory variable is read once (before it is written) and by this thread only, so the read may take the
+    // read-only path: the loads of all terms of a half-step can then be issued ahead of the stores of the earlier terms
+    __device__ __forceinline__ V cpRow(V d, float *ps, float a, float b) const
+    {
+        if (NL == 4 && nAct == 4 && (P.nx & 3) == 0) {
+            const float4 o4 = __ldg(reinterpret_cast<const float4 *>(ps));
+            const float old[4] = {o4.x, o4.y, o4.z, o4.w};
+            V nw;
+#pragma unroll
+            for (int l = 0; l < NL; l++) {
+                float v = A::mul(old[l], b);
+                const float t = A::mul(a, d.v[l]);
+                v = A::add(v, t);
+                nw.v[l] = v;
+                d.v[l] = A::add(d.v[l], v);
+            }
+            stv<NL>(ps, nw);
+            return d;
+        }
+        float old[NL];
+#pragma unroll
+        for (int l = 0; l < NL; l++)
+            old[l] = l < nAct ? __ldg(ps + l) : 0.0f;
+#pragma unroll
+        for (int l = 0; l < NL; l++)
+            if (l < nAct) {
+                float v = A::mul(old[l], b);
+                const float t = A::mul(a, d.v[l]);
+                v = A::add(v, t);
+                ps[l] = v;
+                d.v[l] = A::add(d.v[l], v);
+            }
+        return d;
+    }
+    __device__ __forceinline__ V cpy(V d, int slot, bool half) const
+    {
+        if (INTR || ky < 0)
+            return d;
+        return cpRow(d, P.psi[slot] + ((long long)ky * P.nz + z) * P.nx + x0, __ldg((half ? P.cayh : P.cay) + ky), __ldg((half ? P.cbyh : P.cby) + ky));
+    }
+    __device__ __forceinline__ V cpz(V d, int slot, bool half) const
+    {
+        if (INTR || kz < 0)
+            return d;
+        return cpRow(d, P.psi[slot] + ((long long)ly * (2 * P.W) + kz) * P.nx + x0, __ldg((half ? P.cazh : P.caz) + kz), __ldg((half ? P.cbzh : P.cbz) + kz));
+    }
+    __device__ __forceinline__ V absFactor() const
+    {
+        V r(1.0f);
+        if (!INTR && P.damping == 1) {
+#pragma unroll
+            for (int l = 0; l < NL; l++)
+                r.v[l] = wsgen::wsAbsFactor(P, x0 + l, gy, z);
+        }
+        return r;
+    }
     // own-point operands: from the stage when the half-step's lists name them, else from global memory
-    template <int F> __device__ __forceinline__ float fld() const
+    __device__ __forceinline__ V ldGlobal(const float *g) const
+    {
+        V r(0.0f);
+#pragma unroll
+        for (int l = 0; l < NL; l++)
+            if (l < nAct)
+                r.v[l] = g[l];
+        return r;
+    }
+    __device__ __forceinline__ void stGlobal(float *g, const V &v) const
+    {
+        if (nAct == NL)
+            stv<NL>(g, v);
+        else {
+#pragma unroll
+            for (int l = 0; l < NL; l++)
+                if (l < nAct)
+                    g[l] = v.v[l];
+        }
+    }
+    template <int F> __device__ __forceinline__ V fld() const
     {
         constexpr Lists S = spec(EQ, DIM, PASS);
         constexpr int k = findIn(S.f, S.nf, F);
         if constexpr (k >= 0)
-            return st[O_F + k * G::NP + op];
+            return ldv<NL>(st + O_F + k * G::NP + op);
         else
-            return P.fld[F][i];
+            return ldGlobal(P.fld[F] + i);
     }
-    template <int F> __device__ __forceinline__ void put(float v) const { P.fld[F][i] = v; }
-    template <int M> __device__ __forceinline__ float mat() const
+    template <int F> __device__ __forceinline__ void put(const V &v) const { stGlobal(P.fld[F] + i, v); }
+    template <int M> __device__ __forceinline__ V mat() const
     {
         constexpr Lists S = spec(EQ, DIM, PASS);
         constexpr int k = findIn(S.m, S.nm, M);
         if constexpr (k >= 0)
-            return st[O_M + k * G::NP + op];
+            return ldv<NL>(st + O_M + k * G::NP + op);
         else
-            return P.mat[M][i];
+            return ldGlobal(P.mat[M] + i);
     }
-    template <int C> __device__ __forceinline__ float rget(int l) const
+    template <int C> __device__ __forceinline__ V rget(int l) const
     {
         constexpr Lists S = spec(EQ, DIM, PASS);
         constexpr int k = findIn(S.r, S.nr, C);
-        if constexpr (k >= 0)
-            return st[O_R + (l * S.nr + k) * G::NP + op];
-        else
-            return P.fld[F_R0 + 6 * l + C][i];
+        if (k >= 0 && stR)
+            return ldv<NL>(st + O_R + (l * S.nr + k) * G::NP + op);
+        return ldGlobal(P.fld[F_R0 + 6 * l + C] + i);
     }
     // write-through: later statements of the same half-step read the updated memory variable again
-    template <int C> __device__ __forceinline__ void rput(int l, float v) const
+    template <int C> __device__ __forceinline__ void rput(int l, const V &v) const
     {
         constexpr Lists S = spec(EQ, DIM, PASS);
         constexpr int k = findIn(S.r, S.nr, C);
-        P.fld[F_R0 + 6 * l + C][i] = v;
-        if constexpr (k >= 0)
-            st[O_R + (l * S.nr + k) * G::NP + op] = v;
+        stGlobal(P.fld[F_R0 + 6 * l + C] + i, v);
+        if (k >= 0 && stR)
+            stv<NL>(st + O_R + (l * S.nr + k) * G::NP + op, v);
     }
-    template <int AXIS> __device__ __forceinline__ float cd(int l) const
+    template <int AXIS> __device__ __forceinline__ V cd(int l) const
     {
         constexpr Lists S = spec(EQ, DIM, PASS);
         constexpr int k = findIn(S.c, S.nc, AXIS);
-        if constexpr (k >= 0)
-            return st[oC + (l * S.nc + k) * G::NP + op];
-        else
-            return P.mat[M_CD0 + 3 * l + AXIS][i];
+        if (k >= 0 && stR)
+            return ldv<NL>(st + oC + (l * S.nc + k) * G::NP + op);
+        return ldGlobal(P.mat[M_CD0 + 3 * l + AXIS] + i);
     }
+    // free-surface scalings of these columns (only read on the plane y = 0)
+    __device__ __forceinline__ V sH() const { return ldGlobal(P.sH + (long long)z * P.nx + x0); }
+    __device__ __forceinline__ V sV() const { return ldGlobal(P.sV + (long long)z * P.nx + x0); }
+    __device__ __forceinline__ V sRH(int l) const { return ldGlobal(P.sRH[l] + (long long)z * P.nx + x0); }
+    __device__ __forceinline__ V sRV(int l) const { return ldGlobal(P.sRV[l] + (long long)z * P.nx + x0); }
 };
 
 // NST = depth of the stage ring (planes y .. y+NST-2 are in flight while plane y is computed)
-template <int EQ, int DIM, int Q, int PASS, int NST>
-__global__ void __launch_bounds__(Geo<DIM, Q>::NTHR) kMarch(const __grid_constant__ WsParams P)
+template <int EQ, int DIM, int Q, int PASS, int NST, int NL>
+__global__ void __launch_bounds__(Geo<DIM, Q, NL>::NTHR) kMarch(const __grid_constant__ WsParams P)
 {
-    using G = Geo<DIM, Q>;
-    using MP = MPt<EQ, DIM, Q, PASS>;
+    using G = Geo<DIM, Q, NL>;
+    using MPG = MPt<EQ, DIM, Q, PASS, NL, false>;
+    using MPI = MPt<EQ, DIM, Q, PASS, NL, true>;
+    using V = FV<NL>;
     constexpr Lists S = spec(EQ, DIM, PASS);
     constexpr int H = G::H, NQ = S.nq, NT = S.nt, NP = G::NP;
 #ifdef WS_EMULATE
@@ -239,17 +439,21 @@ __global__ void __launch_bounds__(Geo<DIM, Q>::NTHR) kMarch(const __grid_constan
     __shared__ const float *srcTab[MAXPLAIN];
 #endif
     const int tid = threadIdx.x;
-    const int lx = tid % G::TX, lz = tid / G::TX;
+    const int lx = tid % G::LXN, lz = tid / G::LXN;
     const int tx0 = blockIdx.x * G::TX, tz0 = blockIdx.y * G::TZ;
     const int yc0 = P.ylo + blockIdx.z * P.marchChunk;
     const int yc1 = min(P.yhi, yc0 + P.marchChunk);
     if (yc0 >= yc1)
         return;
-    const int x = tx0 + lx, z = tz0 + lz;
-    const bool active = x < P.nx && z < P.nz;
-    const int L = P.L;
+    const int x0 = tx0 + NL * lx, z = tz0 + lz;
+    const int nAct = z < P.nz ? max(0, min(NL, P.nx - x0)) : 0;
+    const bool active = nAct > 0;
+    const int L = P.marchStageR ? P.L : 0; // relaxation mechanisms whose memory variables / Cd coefficients are staged
     const int nPlain = NQ + S.nf + S.nm + L * (S.nr + S.nc);
     const int stride = NT * G::TILE + nPlain * NP;
+    // interior tile: every point is at least `lo` points away from the x and z faces (no edge rows, no CPML / ABS layer)
+    const int lo = max(H, P.damping != 0 ? P.W : 0);
+    const bool tileIn = tx0 >= lo && tx0 + G::TX <= P.nx - lo && (DIM == 2 || (tz0 >= lo && tz0 + G::TZ <= P.nz - lo));
 
     // plain tiles of a stage, in stage order: source = array origin of this tile (feeds: q/2 planes ahead)
     const long long ownOrg = P.base + tx0 + (long long)tz0 * P.pitch;
@@ -276,60 +480,73 @@ __global__ void __launch_bounds__(Geo<DIM, Q>::NTHR) kMarch(const __grid_constan
     }
     __syncthreads();
 
-    // stage the operands of plane ly: halo tiles of the x / z differentiated fields, then the plain tiles
+    // stage the operands of a plane: halo tiles of the x / z differentiated fields, then the plain tiles (NL = 4: a thread
+    // copies exactly the 16 bytes of each plain tile it reads itself).  Chunk offsets are the same for every plane.
+    constexpr int TCH = G::TILE / 4, NCT = (TCH + G::NTHR - 1) / G::NTHR; // 16-byte chunks per halo tile / per thread
+    int tSrc[NCT], tDst[NCT];
+#pragma unroll
+    for (int n = 0; n < NCT; n++) {
+        const int c = tid + n * G::NTHR;
+        const int row = c / (G::LDX / 4), col = c - row * (G::LDX / 4);
+        tSrc[n] = c < TCH ? row * P.pitch + 4 * col : -1;
+        tDst[n] = row * G::LDX + 4 * col;
+    }
+    const int op = lz * G::TX + NL * lx, so = (lz + G::HZ) * G::LDX + NL * lx + G::HX;
+    constexpr int CH = NP / 4, APR = G::NTHR / CH; // 16-byte chunks per plain tile / plain tiles per round of the block
+    const int pc = tid % CH, pa0 = tid / CH;
+    const int pSrc = (pc / (G::TX / 4)) * P.pitch + 4 * (pc % (G::TX / 4));
     const long long tileOrg = P.base + (tx0 - G::HX) + (long long)(tz0 - G::HZ) * P.pitch;
-    auto stage = [&](int ly, int slot) {
+    auto stage = [&](long long yo, int slot) {
         float *dst = sm + slot * stride;
-        const long long yo = (long long)ly * P.plane;
 #pragma unroll
         for (int k = 0; k < NT; k++) {
             const float *src = P.fld[S.t[k]] + tileOrg + yo;
-            for (int c = tid; c < G::TILE / 4; c += G::NTHR) {
-                const int row = c / (G::LDX / 4), col = c - row * (G::LDX / 4);
-                cpAsync16(dst + k * G::TILE + row * G::LDX + 4 * col, src + (long long)row * P.pitch + 4 * col);
-            }
+#pragma unroll
+            for (int n = 0; n < NCT; n++)
+                if (tSrc[n] >= 0)
+                    cpAsync16(dst + k * G::TILE + tDst[n], src + tSrc[n]);
         }
-        constexpr int CH = NP / 4, CPR = G::TX / 4; // 16-byte chunks per plain tile / per tile row
-        float *dp = dst + NT * G::TILE;
-        for (int g = tid; g < nPlain * CH; g += G::NTHR) {
-            const int a = g / CH, c = g - a * CH;
-            const int row = c / CPR, col = c - row * CPR;
-            cpAsync16(dp + a * NP + row * G::TX + 4 * col, srcTab[a] + yo + (long long)row * P.pitch + 4 * col);
-        }
+        float *dp = dst + NT * G::TILE + 4 * pc;
+        for (int a = pa0; a < nPlain; a += APR)
+            cpAsync16(dp + a * NP, srcTab[a] + yo + pSrc);
         cpCommit();
     };
 
     // register queues: q[f][j] = plane ly - H + j of queued field f while plane ly is computed
-    float q[NQ][Q + 1];
-    const long long own0 = P.base + x + (long long)z * P.pitch;
+    V q[NQ][Q + 1];
+    const long long own0 = P.base + x0 + (long long)z * P.pitch;
 #pragma unroll
     for (int f = 0; f < NQ; f++) {
         const float *src = P.fld[S.qf[f]] + own0;
-        q[f][0] = 0.0f;
+        q[f][0] = V(0.0f);
 #pragma unroll
         for (int j = 1; j <= Q; j++)
-            q[f][j] = active ? __ldg(src + (long long)(yc0 - 1 - H + j) * P.plane) : 0.0f;
+            q[f][j] = active ? ldv<NL>(src + (long long)(yc0 - 1 - H + j) * P.plane) : V(0.0f);
     }
 
-    const int op = lz * G::TX + lx;
-    MP t(P, x, yc0, z, (lz + G::HZ) * G::LDX + lx + G::HX, op, q);
+    MPG tg(P, x0, z, nAct, so, op, q);
+    MPI ti(P, x0, z, nAct, so, op, q);
+    long long yo = (long long)yc0 * P.plane; // plane offset of the next plane to stage
 #pragma unroll
     for (int s = 0; s < NST - 1; s++) {
         if (yc0 + s < yc1)
-            stage(yc0 + s, s);
+            stage(yo, s);
         else
             cpCommit(); // empty group: the group count stays uniform
+        yo += P.plane;
     }
     int slot = 0;
+    long long iCur = own0 + (long long)yc0 * P.plane;
     for (int ly = yc0; ly < yc1; ly++) {
         cpWait<NST - 2>(); // this thread's copies of plane ly have landed
         __syncthreads();   // ... and everybody else's; everybody has finished plane ly - 1
         {
             const int refill = slot == 0 ? NST - 1 : slot - 1; // the stage of plane ly - 1
             if (ly + NST - 1 < yc1)
-                stage(ly + NST - 1, refill);
+                stage(yo, refill);
             else
                 cpCommit();
+            yo += P.plane;
         }
         float *st = sm + slot * stride;
 #pragma unroll
@@ -337,16 +554,26 @@ __global__ void __launch_bounds__(Geo<DIM, Q>::NTHR) kMarch(const __grid_constan
 #pragma unroll
             for (int j = 0; j < Q; j++)
                 q[f][j] = q[f][j + 1];
-            q[f][Q] = st[MP::O_Q + f * NP + op];
+            q[f][Q] = ldv<NL>(st + MPG::O_Q + f * NP + op);
         }
-        if (active) {
-            t.setY(ly);
-            t.st = st;
+        const int gy = P.gy0 + ly;
+        if (P.marchDebug == 1) { // developer switch: staging only (memory-side ceiling of the skeleton)
+        } else if (tileIn && gy >= lo && gy < P.gny - lo) { // uniform over the thread block
+            ti.setPlane(ly, iCur);
+            ti.st = st;
             if (PASS == 0)
-                wsgen::passA<EQ, DIM, false>(P, t);
+                wsgen::passA<EQ, DIM, false>(P, ti);
             else
-                wsgen::passB<EQ, DIM, false>(P, t);
+                wsgen::passB<EQ, DIM, false>(P, ti);
+        } else if (active) {
+            tg.setPlane(ly, iCur);
+            tg.st = st;
+            if (PASS == 0)
+                wsgen::passA<EQ, DIM, false>(P, tg);
+            else
+                wsgen::passB<EQ, DIM, false>(P, tg);
         }
+        iCur += P.plane;
         slot = slot + 1 == NST ? 0 : slot + 1;
     }
     cpWait<0>();
