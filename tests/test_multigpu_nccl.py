@@ -30,6 +30,9 @@ CASES = [
     (("elastic", 3, 64, 40, 24, 8, 1, 1, 2, 6, 0), 1),     # general kernels, order-reducing edges
     (("viscoelastic", 2, 96, 120, 1, 6, 1, 1, 2, 8, 2), 0),
     (("acoustic", 3, 48, 64, 40, 4, 0, 0, 1, 8, 0), 0),
+    (("elastic", 3, 128, 96, 48, 8, 0, 1, 2, 10, 0), 2),   # marching kernels forced (4 x points per thread)
+    (("viscoelastic", 3, 72, 64, 24, 8, 0, 1, 2, 8, 2), 0),  # marching kernels, one x point per thread in the stress half-step
+    (("viscoemem", 3, 40, 64, 24, 4, 1, 0, 2, 6, 1), 0),
 ]
 
 

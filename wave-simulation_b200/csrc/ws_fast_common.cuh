@@ -400,24 +400,19 @@ CUtensorMap makeMapG(const float *arena, int d0, int d1, int d2, int nArrays, in
     return m;
 }
 
-// planes per thread block: the march is cut into chunks so that the last round of thread blocks on the 148 SMs is
-// short; every chunk pays q-1 feed-only planes plus the pipeline fill
+// planes per thread block.  Chunks of ~64 planes are fastest (measured at 1024^3: 36.7 Gpt/s against 35.5 with 3 chunks
+// per column, profiles/r01_march_chunk_sweep.txt): the thread blocks of one y range march in step, so the halo rows
+// they share are still in L2 when the neighbouring tile asks for them; shorter chunks pay too many of the q-1
+// feed-only planes and pipeline fills every chunk starts with.  With thousands of thread blocks per launch the length
+// of the last wave no longer matters.
 inline int wsPickChunk(int nTiles, int nyl, int q)
 {
-    int best = nyl;
-    double bestCost = 1e30;
-    for (int k = 1; k <= 8; k++) {
-        const int len = (nyl + k - 1) / k;
-        if (k > 1 && len < 64)
-            break;
-        const double rounds = std::ceil((double)nTiles * k / 148.0);
-        const double cost = rounds * (len + q + 3);
-        if (cost < bestCost * 0.995) {
-            bestCost = cost;
-            best = len;
-        }
-    }
-    return best;
+    (void)nTiles;
+    (void)q;
+    if (nyl < 96)
+        return nyl;
+    const int k = (nyl + 63) / 64;
+    return (nyl + k - 1) / k;
 }
 
 } // namespace

@@ -127,20 +127,22 @@ bool wsMarchSupported(const WsParams &P, bool exact)
     return P.dim == 2 || P.dim == 3;
 }
 
-// planes per thread block: enough thread blocks to fill the 148 SMs several times over, but chunks long enough that
-// the q feed-only planes at the start of a chunk stay a small fraction
+// planes per thread block.  Short chunks win (measured, profiles/r01_march_chunk_sweep.txt): the thread blocks of one
+// y range march in step, so the halo rows they share are still in L2 when the neighbour asks for them (with one chunk
+// per column the marches drift apart and the halos come from HBM again: 3-D acoustic 1024^3 58.7 -> 77.1 Gpt/s at 64
+// planes), and small 2-D grids only fill the 148 SMs when they are cut into ~3000 thread blocks.  The price, q feed-only
+// planes at the start of every chunk, bounds the chunk from below.
 void wsMarchPrepare(WsParams &P)
 {
     const int TX = P.dim == 3 ? 64 : 256, TZ = P.dim == 3 ? 8 : 1;
     P.marchLanes = getenv("WS_MARCH_LANES") ? atoi(getenv("WS_MARCH_LANES")) : 0;
     const long long tiles = (long long)((P.nx + TX - 1) / TX) * ((P.nz + TZ - 1) / TZ);
-    const long long want = 148LL * 8;
+    const long long want = 148LL * 20;
     long long nchunks = (want + tiles - 1) / tiles;
     if (nchunks < 1)
         nchunks = 1;
     int chunk = (int)((P.nyl + nchunks - 1) / nchunks);
-    if (chunk < 32)
-        chunk = 32;
+    chunk = chunk < 16 ? 16 : (chunk > 64 ? 64 : chunk);
     if (const char *e = getenv("WS_MARCH_CHUNK"))
         chunk = atoi(e) > 0 ? atoi(e) : chunk;
     P.marchChunk = chunk;
