@@ -146,9 +146,14 @@ def test_fast_kernels_equal_general_kernels(shape):
         res.append((s.seismogram(), {f: s.wavefield(f) for f in fields_of("elastic", 3, 0)}))
         assert s.is_finite()
     assert np.abs(res[0][0]).max() > 0
-    assert np.array_equal(res[0][0], res[1][0])
     for f in res[0][1]:
-        assert np.array_equal(res[0][1][f], res[1][1][f]), f
+        a, b = res[0][1][f].reshape(ny, nz, nx), res[1][1][f].reshape(ny, nz, nx)
+        if not np.array_equal(a, b):
+            bad = np.argwhere(a != b)
+            raise AssertionError("%s differs at %d points, first (y,z,x) %s, y range %d..%d z %d..%d x %d..%d, max |d| %.3e of %.3e"
+                                 % (f, len(bad), bad[0], bad[:, 0].min(), bad[:, 0].max(), bad[:, 1].min(), bad[:, 1].max(),
+                                    bad[:, 2].min(), bad[:, 2].max(), np.abs(a - b).max(), np.abs(a).max()))
+    assert np.array_equal(res[0][0], res[1][0])
 
 
 @pytest.mark.parametrize("cfg", SWEEP, ids=[sweep_id(c) for c in SWEEP])

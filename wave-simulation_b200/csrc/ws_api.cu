@@ -221,10 +221,15 @@ struct DevBuf {
     void upload(const std::vector<T> &h)
     {
         alloc(h.size());
-        if (!h.empty())
+        if (!h.empty()) {
             WS_CUDA_CHECK(cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+            // a pageable host-to-device copy may return before its DMA has landed; the solver's kernels run on a
+            // non-blocking stream that is not ordered with the legacy default stream
+            WS_CUDA_CHECK(cudaStreamSynchronize(0));
+        }
     }
-    void zero(cudaStream_t st = 0)
+    // always on the solver's own stream: it is a non-blocking stream, so work on the legacy default stream is not ordered with it
+    void zero(cudaStream_t st)
     {
         if (p)
             WS_CUDA_CHECK(cudaMemsetAsync(p, 0, n * sizeof(T), st));
@@ -513,7 +518,7 @@ float *matBuf(ws_solver *s, int slot)
 {
     if (!s->mat[slot].p) {
         s->mat[slot].alloc((size_t)s->total);
-        s->mat[slot].zero();
+        s->mat[slot].zero(s->stream);
     }
     return s->mat[slot].p;
 }
@@ -876,9 +881,9 @@ void prepareBoundaries(ws_solver *s)
             static const int oz[6] = {PSI_SXZ_Z, PSI_SYZ_Z, PSI_SZZ_Z, PSI_VXZ, PSI_VYZ, PSI_VZZ};
             const size_t nxs = psiSize(s, 0), nzs = psiSize(s, 2);
             s->psiXArena.alloc(6 * nxs);
-            s->psiXArena.zero();
+            s->psiXArena.zero(s->stream);
             s->psiZArena.alloc(6 * nzs);
-            s->psiZArena.zero();
+            s->psiZArena.zero(s->stream);
             for (int k = 0; k < 6; k++) {
                 s->psi[ox[k]].borrow(s->psiXArena.p + k * nxs, nxs);
                 s->psi[oz[k]].borrow(s->psiZArena.p + k * nzs, nzs);
@@ -887,7 +892,7 @@ void prepareBoundaries(ws_solver *s)
         for (auto &pa : psiFor(d)) {
             if (!s->psi[pa.first].p)
                 s->psi[pa.first].alloc(psiSize(s, pa.second));
-            s->psi[pa.first].zero();
+            s->psi[pa.first].zero(s->stream);
         }
     }
     if (d.damping == 1)
@@ -896,10 +901,10 @@ void prepareBoundaries(ws_solver *s)
     if (s->seismic && d.free_surface == 1 && (d.eq == WS_EQ_ELASTIC || d.eq == WS_EQ_VISCOELASTIC)) {
         const size_t ns = (size_t)s->nx * s->nz;
         s->sH.alloc(ns); s->sV.alloc(ns);
-        s->sH.zero(); s->sV.zero();
+        s->sH.zero(s->stream); s->sV.zero(s->stream);
         for (int l = 0; l < s->L; l++) {
             s->sRH[l].alloc(ns); s->sRV[l].alloc(ns);
-            s->sRH[l].zero(); s->sRV[l].zero();
+            s->sRH[l].zero(s->stream); s->sRV[l].zero(s->stream);
         }
         if (s->y0 == 0) {
             dim3 block = s->nz > 1 ? dim3(64, 4, 1) : dim3(128, 1, 1);
@@ -1175,11 +1180,11 @@ int ws_create(const ws_desc *desc, ws_solver **out)
                 static const int fo[9] = {F_VX, F_VY, F_VZ, F_SXX, F_SXY, F_SYY, F_SYZ, F_SZZ, F_SXZ};
                 static const int mo[8] = {M_RIX, M_RIY, M_RIZ, M_PW, M_MU, M_MUXY, M_MUXZ, M_MUYZ};
                 s->fldArena.alloc((size_t)s->total * 9);
-                s->fldArena.zero();
+                s->fldArena.zero(s->stream);
                 for (int k = 0; k < 9; k++)
                     s->fld[fo[k]].borrow(s->fldArena.p + (size_t)k * s->total, (size_t)s->total);
                 s->matArena.alloc((size_t)s->total * 8);
-                s->matArena.zero();
+                s->matArena.zero(s->stream);
                 for (int k = 0; k < 8; k++)
                     s->mat[mo[k]].borrow(s->matArena.p + (size_t)k * s->total, (size_t)s->total);
                 for (auto &kv : fieldsFor(s->d).f)
@@ -1187,7 +1192,7 @@ int ws_create(const ws_desc *desc, ws_solver **out)
             } else {
                 for (auto &kv : fieldsFor(s->d).f) {
                     s->fld[kv.second].alloc((size_t)s->total);
-                    s->fld[kv.second].zero();
+                    s->fld[kv.second].zero(s->stream);
                     s->fldSlot[kv.first] = kv.second;
                 }
             }
@@ -1196,7 +1201,7 @@ int ws_create(const ws_desc *desc, ws_solver **out)
             for (auto &pa : psiFor(s->d))
                 s->psiAxis[pa.first] = pa.second;
             s->tdev.alloc(1);
-            s->tdev.zero();
+            s->tdev.zero(s->stream);
             s->flag.alloc(1);
             // ghost exchange lists: the fields differentiated along y by the NEXT half-step
             const bool d3 = s->d.dim == 3;
@@ -1396,9 +1401,9 @@ static int setReceiversImpl(ws_solver *s, int32_t n, const int32_t *type, const 
         s->recType.upload(types);
         s->recOff.upload(off);
         s->seis.alloc(std::max<size_t>(1, (size_t)n * s->d.nt));
-        s->seis.zero();
+        s->seis.zero(s->stream);
         s->recStep.alloc(std::max(1, n));
-        s->recStep.zero();
+        s->recStep.zero(s->stream);
         if (s->pinRec)
             cudaFreeHost(s->pinRec);
         WS_CUDA_CHECK(cudaMallocHost(&s->pinRec, std::max(1, n) * sizeof(float)));
