@@ -72,6 +72,38 @@ def test_emulated_marching_kernels_partial_tiles_and_chunks(monkeypatch):
             assert np.array_equal(res[0][f], res[1][f]), (cfg, f)
 
 
+@pytest.mark.parametrize("dim", [2, 3])
+def test_div_curl_snapshot(dim):
+    """snapType 3 (Wavefields3Delastic.cpp:197-245, Wavefields2Delastic.cpp:217-248): for velocity fields that are linear
+    in the coordinates the interior values are known in closed form (FD weights sum to DT/DH per unit slope)."""
+    nx, ny, nz = 24, 22, (20 if dim == 3 else 1)
+    case = make_case("elastic", dim, nx, ny, nz, 4, 0, 0, 0, 6, 0, nt=4, exact=1)
+    e = case.setup(EmuSolver(case.desc))
+    y, z, x = np.meshgrid(np.arange(ny), np.arange(nz), np.arange(nx), indexing="ij")
+    a, b, c = 3.0, -2.0, 0.5
+    e.set_wavefield("VX", (a * y + 2 * x).astype(np.float32))
+    e.set_wavefield("VY", (b * x + c * z + 1.5 * y).astype(np.float32))
+    if dim == 3:
+        e.set_wavefield("VZ", (0.25 * y - 1.0 * z).astype(np.float32))
+    s = np.float32(case.desc.dt / case.desc.dh)
+    pi, mu = e.get_material("pWaveModulus").reshape(ny, nz, nx), e.get_material("sWaveModulus").reshape(ny, nz, nx)
+    div, curl = e.wavefield("DIV").reshape(ny, nz, nx), e.wavefield("CURL").reshape(ny, nz, nx)
+    inner = (slice(3, ny - 3), slice(3, nz - 3) if dim == 3 else slice(None), slice(3, nx - 3))
+    if dim == 3:
+        d = (2 + 1.5 - 1.0) * s  # Dxb vx + Dyb vy + Dzb vz
+        want_div = np.sqrt(d * d * pi)
+        cx, cy, cz = (0.25 - c) * s, (0.0 - 0.0) * s, (b - a) * s  # (Dyf vz - Dzf vy), (Dzf vx - Dxf vz), (Dxf vy - Dyf vx)
+        want_curl = np.sqrt((cx * cx + cy * cy + cz * cz) * mu)
+    else:
+        want_div = (2 + 1.5) * s * np.sqrt(pi)
+        want_curl = (a - b) * s * np.sqrt(mu)  # Dyf vx - Dxf vy
+    assert np.allclose(div[inner], want_div[inner], rtol=2e-5)
+    assert np.allclose(curl[inner], want_curl[inner], rtol=2e-5)
+    with pytest.raises(RuntimeError):
+        a_case = make_case("acoustic", 2, 20, 20, 1, 2, 0, 0, 0, 6, 0, nt=2)
+        a_case.setup(EmuSolver(a_case.desc)).wavefield("DIV")
+
+
 def test_emulated_ci_case_2d_elastic_full_trace():
     case = ci_case("2D.elastic")
     for exact, tol in ((1, 0.0), (0, 1.0e-5)):

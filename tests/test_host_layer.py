@@ -184,6 +184,49 @@ def test_driver_multishot_receivers_per_shot_resampling_normalisation_snapshots(
     assert "wavefield.shot_1.VX.0.mtx" in snaps and "wavefield.shot_1.VX.150.mtx" in snaps and len(snaps) == 4
 
 
+def read_su(path):
+    """Seismic Unix traces: 240-byte SEG-Y trace header (native endian) + ns float32 samples per trace."""
+    raw = open(path, "rb").read()
+    ns = struct.unpack_from("<H", raw, 114)[0]
+    rec = 240 + 4 * ns
+    assert len(raw) % rec == 0
+    ntr = len(raw) // rec
+    hdr = [raw[k * rec:k * rec + 240] for k in range(ntr)]
+    data = np.stack([np.frombuffer(raw, "<f4", ns, k * rec + 240) for k in range(ntr)])
+    return hdr, data
+
+
+def test_driver_su_seismograms(driver, tmp_path):
+    """SeismogramFormat=4: trace headers as the reference fills them (src/IO/SUIO.hpp:196-246: coordinates in mm with
+    scalco = -3, offset from the source, dt in microseconds), samples identical to the .mtx output of the same run."""
+    tmp = str(tmp_path)
+    rec = "30 0 0 3\n44 7 0 3\n"
+    cfg = setup_case(tmp, receivers=rec, sfmt=4, T=0.3, sdt="4.0e-03")
+    run(driver, cfg, tmp)
+    hdr, su = read_su(os.path.join(tmp, "seismograms", "seismogram.shot_1.vy.su"))
+    cfg = setup_case(tmp, receivers=rec, sfmt=1, T=0.3, sdt="4.0e-03", snap=3)  # + snapType 3: curl / div energy snapshots
+    run(driver, cfg, tmp)
+    mtx = read_mtx(os.path.join(tmp, "seismograms", "seismogram.shot_1.vy.mtx"))
+    snaps = sorted(os.listdir(os.path.join(tmp, "wavefields")))
+    assert snaps == ["wavefield.shot_1.%s.%d.mtx" % (c, t) for c in ("CURL", "DIV") for t in (0, 100, 50)]
+    div = read_mtx(os.path.join(tmp, "wavefields", "wavefield.shot_1.DIV.100.mtx"))
+    assert div.shape == (10000, 1) and np.isfinite(div).all() and np.abs(div).max() > 0  # signed in 2-D (Wavefields2Delastic.cpp:234-248)
+    assert su.shape == (2, 75) and np.abs(su).max() > 0
+    assert np.allclose(su, mtx, rtol=2e-6, atol=0)  # the mtx file carries 6-7 digits
+
+    def word(h, off, fmt):
+        return struct.unpack_from("<" + fmt, h, off)[0]
+    for k, (xr, yr) in enumerate(((30, 0), (44, 7))):
+        h = hdr[k]
+        assert word(h, 0, "i") == k + 1 and word(h, 204, "i") == 2 and word(h, 28, "h") == 1       # tracl, ntr, trid
+        assert word(h, 114, "H") == 75 and word(h, 116, "H") == 4000                              # ns, dt [us]
+        assert abs(word(h, 180, "f") - 4.0e-3) < 1e-9                                            # d1
+        assert word(h, 70, "h") == -3 and word(h, 68, "h") == -3 and word(h, 88, "h") == 1       # scalco, scalel, counit
+        assert word(h, 72, "i") == 20 * 50 * 1000 and word(h, 48, "i") == 0                      # sx, sdepth (source at (20, 0))
+        assert word(h, 80, "i") == xr * 50 * 1000 and word(h, 40, "i") == yr * 50 * 1000          # gx, gelev
+        assert word(h, 36, "i") == int(round(np.hypot((xr - 20) * 50.0, yr * 50.0) * 1000.0))     # offset
+
+
 def test_driver_error_behaviour(driver, tmp_path):
     tmp = str(tmp_path)
     cfg = setup_case(tmp)

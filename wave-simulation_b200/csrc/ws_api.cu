@@ -1607,6 +1607,24 @@ int ws_get_wavefield(ws_solver *s, const char *comp, float *host, size_t n)
     return guarded([&] {
         WS_REQUIRE(s && comp && host, WS_EINVAL, "null argument");
         setDevice(s);
+        const std::string name(comp);
+        if (name == "CURL" || name == "DIV") {
+            // snapType 3 (Wavefields3Delastic.cpp:86-91): derived from the particle velocities with the plain operators
+            WS_REQUIRE(s->d.eq == WS_EQ_ELASTIC || s->d.eq == WS_EQ_VISCOELASTIC, WS_EINVAL, "There is no curl or div of wavefield in this modelling");
+            WS_REQUIRE(s->prepared, WS_ESTATE, "ws_prepare must precede the curl / div snapshot");
+            WS_REQUIRE(n == (size_t)s->nx * s->nyl * s->nz, WS_EINVAL, "size mismatch");
+            DevBuf<float> tmp;
+            tmp.alloc((size_t)s->total);
+            tmp.zero(s->stream);
+            WsParams P = s->P;
+            P.ylo = 0;
+            P.yhi = s->nyl;
+            wsLaunchDivCurl(P, tmp.p, name == "DIV" ? 1 : 0, s->stream);
+            s->launches++;
+            downloadLocal(s, tmp.p, host);
+            WS_CUDA_CHECK(cudaStreamSynchronize(s->stream));
+            return;
+        }
         auto it = s->fldSlot.find(comp);
         WS_REQUIRE(it != s->fldSlot.end(), WS_EINVAL, std::string("wavefield '") + comp + "' does not exist in this modelling");
         WS_REQUIRE(n == (size_t)s->nx * s->nyl * s->nz, WS_EINVAL, "size mismatch");

@@ -83,3 +83,17 @@ void wsLaunchAbsFirstHalf(const WsParams &P, bool exact, int f0, int f1, int f2,
     else
         WS_LAUNCH(kf, grid, block, 0, st, P, f0, f1, f2);
 }
+
+void wsLaunchDivCurl(const WsParams &P, float *out, int which, cudaStream_t st)
+{
+    if (P.yhi <= P.ylo)
+        return;
+    dim3 grid, block;
+    wsGeneralGrid(P, grid, block);
+    auto k2 = wsgen::kDivCurl<2>;
+    auto k3 = wsgen::kDivCurl<3>;
+    if (P.dim == 3)
+        WS_LAUNCH(k3, grid, block, 0, st, P, out, which);
+    else
+        WS_LAUNCH(k2, grid, block, 0, st, P, out, which);
+}

@@ -604,4 +604,48 @@ __global__ void __launch_bounds__(256) kAbsFirstHalf(const __grid_constant__ WsP
             P.fld[fs[k]][t.i] = Ar<EXACT>::mul(P.fld[fs[k]][t.i], d);
 }
 
+// snapType 3 of the elastic / viscoelastic wavefields: P- and S-wave energy measures after Dougherty and Stephen (1988)
+// (Wavefields3Delastic.cpp:197-245 getCurl / getDiv, Wavefields2Delastic.cpp:217-248), reference statement order.
+// which = 0: curl, 1: div.  `out` is a padded array like the wavefields.
+template <int DIM>
+__global__ void __launch_bounds__(256) kDivCurl(const __grid_constant__ WsParams P, float *out, int which)
+{
+    using A = Ar<true>;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int z = blockIdx.y * blockDim.y + threadIdx.y;
+    const int ly = P.ylo + blockIdx.z;
+    if (x >= P.nx || z >= P.nz || ly >= P.yhi)
+        return;
+    Pt<true> t(P, x, ly, z);
+    float r;
+    if (which == 1) {
+        r = t.template D<F_VX, OP_XB>();
+        r = A::add(r, t.template D<F_VY, OP_YB>());
+        if (DIM == 3) {
+            r = A::add(r, t.template D<F_VZ, OP_ZB>());
+            r = A::mul(r, r);
+            r = A::mul(r, t.template mat<M_PW>());
+            r = sqrtf(r);
+        } else
+            r = A::mul(r, sqrtf(t.template mat<M_PW>()));
+    } else if (DIM == 3) {
+        float u = t.template D<F_VZ, OP_YF>();
+        u = A::sub(u, t.template D<F_VY, OP_ZF>());
+        r = A::mul(u, u);
+        u = t.template D<F_VX, OP_ZF>();
+        u = A::sub(u, t.template D<F_VZ, OP_XF>());
+        r = A::add(r, A::mul(u, u));
+        u = t.template D<F_VY, OP_XF>();
+        u = A::sub(u, t.template D<F_VX, OP_YF>());
+        r = A::add(r, A::mul(u, u));
+        r = A::mul(r, t.template mat<M_MU>());
+        r = sqrtf(r);
+    } else {
+        r = t.template D<F_VX, OP_YF>();
+        r = A::sub(r, t.template D<F_VY, OP_XF>());
+        r = A::mul(r, sqrtf(t.template mat<M_MU>()));
+    }
+    out[t.i] = r;
+}
+
 } // namespace wsgen

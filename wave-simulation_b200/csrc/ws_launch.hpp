@@ -6,6 +6,8 @@
 void wsGeneralGrid(const WsParams &P, dim3 &grid, dim3 &block);
 void wsLaunchGeneral(const WsParams &P, bool exact, int pass, cudaStream_t st);
 void wsLaunchAbsFirstHalf(const WsParams &P, bool exact, int f0, int f1, int f2, cudaStream_t st);
+// snapType 3: curl (which = 0) / div (which = 1) energy measure of the velocity field into the padded array `out`
+void wsLaunchDivCurl(const WsParams &P, float *out, int which, cudaStream_t st);
 
 // tiled fast kernels (ws_kernels_fast.cu); return false when the configuration is not covered
 bool wsFastSupported(const WsParams &P, bool exact);

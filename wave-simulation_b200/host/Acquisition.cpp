@@ -310,24 +310,33 @@ template <typename ValueType> bool Acquisition::Seismogram<ValueType>::isFinite(
     return true;
 }
 
-template <typename ValueType> void Acquisition::Seismogram<ValueType>::write(IndexType seismogramFormat, std::string const &filename) const
+template <typename ValueType>
+void Acquisition::Seismogram<ValueType>::write(IndexType seismogramFormat, std::string const &filename, Coordinates<ValueType> const *modelCoordinates) const
 {
     if (data.empty())
         return;
-    SCAI_ASSERT_ERROR(seismogramFormat == 1 || seismogramFormat == 2, "SeismogramFormat " << seismogramFormat << " (frv / SU) is not available in the B200 host layer")
+    SCAI_ASSERT_ERROR(seismogramFormat == 1 || seismogramFormat == 2 || seismogramFormat == 4,
+                      "SeismogramFormat " << seismogramFormat << " (3 = frv, 5 = inverse AGC of the inversion workflow) is not available in the B200 host layer")
     const std::string name = filename + "." + (isSeismic ? SeismogramTypeString[type] : SeismogramTypeStringEM[type]);
     std::vector<ValueType> out(data);
     IndexType ns = numSamples;
     if (outputDT > 0 && DT > 0)
         Common::resampleRows(out, getNumTraces(), numSamples, outputDT / DT, ns); // Seismogram.cpp:610-618 setSeismoDT
-    IO::writeMatrix(out, getNumTraces(), ns, name, seismogramFormat);
+    if (seismogramFormat == 4) { // Seismogram.cpp:119-121
+        SCAI_ASSERT_ERROR(modelCoordinates, "SeismogramFormat 4 (SU) needs the model coordinates for the trace headers")
+        SUIO::writeSU(name, out, getNumTraces(), ns, coordinates1D, outputDT > 0 ? outputDT : DT, sourceCoordinate1D, *modelCoordinates);
+    } else
+        IO::writeMatrix(out, getNumTraces(), ns, name, seismogramFormat);
 }
 
 template <typename ValueType> void Acquisition::Seismogram<ValueType>::read(IndexType seismogramFormat, std::string const &filename)
 {
     const std::string name = filename + "." + (isSeismic ? SeismogramTypeString[type] : SeismogramTypeStringEM[type]);
     IndexType r, c;
-    IO::readMatrix(data, r, c, name, seismogramFormat);
+    if (seismogramFormat == 4)
+        SUIO::readDataSU(name, data, r, c); // Seismogram.cpp:180-193
+    else
+        IO::readMatrix(data, r, c, name, seismogramFormat);
     numSamples = c;
 }
 
@@ -365,10 +374,16 @@ template <typename ValueType> bool Acquisition::SeismogramHandler<ValueType>::is
             return false;
     return true;
 }
-template <typename ValueType> void Acquisition::SeismogramHandler<ValueType>::write(IndexType seismogramFormat, std::string const &filename) const
+template <typename ValueType>
+void Acquisition::SeismogramHandler<ValueType>::write(IndexType seismogramFormat, std::string const &filename, Coordinates<ValueType> const *modelCoordinates) const
 {
     for (auto const &s : seismo)
-        s.write(seismogramFormat, filename);
+        s.write(seismogramFormat, filename, modelCoordinates);
+}
+template <typename ValueType> void Acquisition::SeismogramHandler<ValueType>::setSourceCoordinate(IndexType sourceCoord)
+{
+    for (auto &s : seismo)
+        s.setSourceCoordinate(sourceCoord);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

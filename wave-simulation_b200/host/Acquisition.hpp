@@ -69,12 +69,16 @@ namespace KITGPI
             IndexType getTraceType() const { return type; }
             void normalizeTrace(IndexType normalizeTraces);
             bool isFinite() const;
-            void write(IndexType seismogramFormat, std::string const &filename) const;
+            //! SeismogramFormat 1 = mtx, 2 = lmf, 4 = SU (needs the model coordinates for the trace headers, Seismogram.cpp:82-147)
+            void write(IndexType seismogramFormat, std::string const &filename, Coordinates<ValueType> const *modelCoordinates = nullptr) const;
             void read(IndexType seismogramFormat, std::string const &filename);
+            void setSourceCoordinate(IndexType sourceCoord) { sourceCoordinate1D = sourceCoord; } // Seismogram.cpp:561
+            IndexType getSourceCoordinate() const { return sourceCoordinate1D; }
 
           private:
             std::vector<ValueType> data;
             std::vector<IndexType> coordinates1D;
+            IndexType sourceCoordinate1D = 0;
             IndexType numSamples = 0, type = 0;
             bool isSeismic = true;
             ValueType DT = 0, outputDT = 0;
@@ -94,7 +98,8 @@ namespace KITGPI
             void resetData();
             void normalize(IndexType normalizeTraces);
             bool isFinite() const;
-            void write(IndexType seismogramFormat, std::string const &filename) const;
+            void write(IndexType seismogramFormat, std::string const &filename, Coordinates<ValueType> const *modelCoordinates = nullptr) const;
+            void setSourceCoordinate(IndexType sourceCoord); // SeismogramHandler.cpp:340
 
           private:
             std::array<Seismogram<ValueType>, NUM_ELEMENTS_SEISMOGRAMTYPE> seismo;

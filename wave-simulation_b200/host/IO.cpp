@@ -147,3 +147,131 @@ void IO::readMatrix(std::vector<ValueType> &matrix, IndexType &numRows, IndexTyp
         numCols = s[1];
     }
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Seismic Unix traces (src/IO/SUIO.hpp).  The 240-byte trace header is written field by field at the byte offsets of the
+// CWP/SU `segy` struct (src/Acquisition/segy.hpp): i = int32, h = int16, u = uint16, f = float32.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace
+{
+    struct SuKey {
+        const char *name;
+        int offset;
+        char type;
+    };
+    const SuKey kSuKeys[] = {{"tracl", 0, 'i'},   {"tracr", 4, 'i'},   {"fldr", 8, 'i'},     {"tracf", 12, 'i'},  {"ep", 16, 'i'},      {"cdp", 20, 'i'},
+                             {"cdpt", 24, 'i'},   {"trid", 28, 'h'},   {"nvs", 30, 'h'},     {"nhs", 32, 'h'},    {"duse", 34, 'h'},    {"offset", 36, 'i'},
+                             {"gelev", 40, 'i'},  {"selev", 44, 'i'},  {"sdepth", 48, 'i'},  {"gdel", 52, 'i'},   {"sdel", 56, 'i'},    {"swdep", 60, 'i'},
+                             {"gwdep", 64, 'i'},  {"scalel", 68, 'h'}, {"scalco", 70, 'h'},  {"sx", 72, 'i'},     {"sy", 76, 'i'},      {"gx", 80, 'i'},
+                             {"gy", 84, 'i'},     {"counit", 88, 'h'}, {"ns", 114, 'u'},     {"dt", 116, 'u'},    {"d1", 180, 'f'},     {"ntr", 204, 'i'}};
+    const SuKey &suKey(std::string const &name)
+    {
+        for (auto const &k : kSuKeys)
+            if (name == k.name)
+                return k;
+        COMMON_THROWEXCEPTION("unknown SU header word " << name)
+    }
+    void suPut(unsigned char *hdr, const char *name, double v)
+    {
+        const SuKey &k = suKey(name);
+        switch (k.type) {
+        case 'i': { int32_t w = (int32_t)v; std::memcpy(hdr + k.offset, &w, 4); break; }
+        case 'h': { int16_t w = (int16_t)v; std::memcpy(hdr + k.offset, &w, 2); break; }
+        case 'u': { uint16_t w = (uint16_t)v; std::memcpy(hdr + k.offset, &w, 2); break; }
+        default: { float w = (float)v; std::memcpy(hdr + k.offset, &w, 4); break; }
+        }
+    }
+    double suGet(const unsigned char *hdr, const SuKey &k)
+    {
+        switch (k.type) {
+        case 'i': { int32_t w; std::memcpy(&w, hdr + k.offset, 4); return w; }
+        case 'h': { int16_t w; std::memcpy(&w, hdr + k.offset, 2); return w; }
+        case 'u': { uint16_t w; std::memcpy(&w, hdr + k.offset, 2); return w; }
+        default: { float w; std::memcpy(&w, hdr + k.offset, 4); return w; }
+        }
+    }
+}
+
+void KITGPI::SUIO::writeSU(std::string const &filename, std::vector<ValueType> const &data, IndexType ntr, IndexType ns, std::vector<IndexType> const &coordinates1D,
+                           ValueType DT, IndexType sourceCoordinate1D, Acquisition::Coordinates<ValueType> const &modelCoordinates)
+{
+    SCAI_ASSERT_ERROR((IndexType)coordinates1D.size() == ntr && (IndexType)data.size() == ntr * ns, "writeSU: " << ntr << " traces of " << ns << " samples expected")
+    SCAI_ASSERT_ERROR(ns <= 65535, "writeSU: the SU header holds at most 65535 samples per trace")
+    const std::string name = filename + ".su";
+    std::ofstream out(name, std::ios::binary);
+    SCAI_ASSERT_ERROR(out.good(), "Could not open " << name)
+    const ValueType DH = modelCoordinates.getDH();
+    const Acquisition::coordinate3D src = modelCoordinates.index2coordinate(sourceCoordinate1D);
+    const ValueType XS = src.x * DH, YS = src.y * DH, ZS = src.z * DH;
+    const ValueType xshift = 800.0, yshift = 800.0; // SUIO.hpp:203
+    const ValueType dtms = (ValueType)(DT * 1000000);
+    for (IndexType tr = 0; tr < ntr; tr++) {
+        unsigned char hdr[240];
+        std::memset(hdr, 0, sizeof(hdr));
+        const Acquisition::coordinate3D rec = modelCoordinates.index2coordinate(coordinates1D[tr]);
+        const ValueType xr = rec.x * DH, yr = rec.y * DH, zr = rec.z * DH;
+        const ValueType x = xr - XS, y = yr - YS, z = zr - ZS; // source position as reference point
+        suPut(hdr, "counit", 1);
+        suPut(hdr, "ntr", ntr);
+        suPut(hdr, "tracl", tr + 1);
+        suPut(hdr, "tracr", 1);
+        suPut(hdr, "ep", 1);
+        suPut(hdr, "cdp", ntr);
+        suPut(hdr, "trid", 1);
+        suPut(hdr, "offset", std::round(std::sqrt((XS - xr) * (XS - xr) + (YS - yr) * (YS - yr) + (ZS - zr) * (ZS - zr)) * 1000.0));
+        suPut(hdr, "gelev", std::round(yr * 1000.0));
+        suPut(hdr, "sdepth", std::round(YS * 1000.0));
+        suPut(hdr, "gdel", std::round(std::atan2(-y, z) * 180 * 1000.0 / 3.1415926));
+        suPut(hdr, "gwdep", std::round(std::sqrt(z * z + y * y) * 1000.0));
+        suPut(hdr, "swdep", std::round(((360.0 / (2.0 * 3.1415926)) * std::atan2(x - xshift, y - yshift)) * 1000.0));
+        suPut(hdr, "scalel", -3);
+        suPut(hdr, "scalco", -3);
+        suPut(hdr, "sx", std::round(XS * 1000.0));
+        suPut(hdr, "sy", std::round(ZS * 1000.0));
+        suPut(hdr, "gx", std::round(xr * 1000.0));
+        suPut(hdr, "gy", std::round(zr * 1000.0));
+        suPut(hdr, "ns", ns);
+        suPut(hdr, "dt", std::round(dtms));
+        suPut(hdr, "d1", (float)(uint16_t)std::round(dtms) * 1.0e-6);
+        out.write(reinterpret_cast<const char *>(hdr), 240);
+        out.write(reinterpret_cast<const char *>(data.data() + (size_t)tr * ns), sizeof(float) * ns);
+    }
+    SCAI_ASSERT_ERROR(out.good(), "Could not write " << name)
+}
+
+void KITGPI::SUIO::readDataSU(std::string const &filename, std::vector<ValueType> &data, IndexType &ntr, IndexType &ns)
+{
+    const std::string name = filename + ".su";
+    std::ifstream in(name, std::ios::binary | std::ios::ate);
+    SCAI_ASSERT_ERROR(in.good(), "Could not open " << name)
+    const std::streamoff size = in.tellg();
+    in.seekg(0);
+    unsigned char hdr[240];
+    in.read(reinterpret_cast<char *>(hdr), 240);
+    SCAI_ASSERT_ERROR(in.good(), name << " holds no SU trace")
+    ns = (IndexType)suGet(hdr, suKey("ns"));
+    const std::streamoff rec = 240 + (std::streamoff)sizeof(float) * ns;
+    SCAI_ASSERT_ERROR(ns > 0 && size % rec == 0, name << " is not a sequence of SU traces with " << ns << " samples")
+    ntr = (IndexType)(size / rec);
+    data.resize((size_t)ntr * ns);
+    for (IndexType tr = 0; tr < ntr; tr++) {
+        in.seekg((std::streamoff)tr * rec + 240);
+        in.read(reinterpret_cast<char *>(data.data() + (size_t)tr * ns), sizeof(float) * ns);
+    }
+    SCAI_ASSERT_ERROR(in.good(), "Could not read " << name)
+}
+
+double KITGPI::SUIO::readHeaderWordSU(std::string const &filename, IndexType trace, std::string const &key)
+{
+    const std::string name = filename + ".su";
+    std::ifstream in(name, std::ios::binary);
+    SCAI_ASSERT_ERROR(in.good(), "Could not open " << name)
+    unsigned char hdr[240];
+    in.read(reinterpret_cast<char *>(hdr), 240);
+    SCAI_ASSERT_ERROR(in.good(), name << " holds no SU trace")
+    const IndexType ns = (IndexType)suGet(hdr, suKey("ns"));
+    in.seekg((std::streamoff)trace * (240 + (std::streamoff)sizeof(float) * ns));
+    in.read(reinterpret_cast<char *>(hdr), 240);
+    SCAI_ASSERT_ERROR(in.good(), name << " has no trace " << trace)
+    return suGet(hdr, suKey(key));
+}

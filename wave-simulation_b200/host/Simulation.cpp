@@ -68,7 +68,7 @@ static void runShotDomain(Configuration::Configuration const &config, IndexType 
             sources.init(sourceSettingsShot, config, modelCoordinates);
             CheckParameter::checkNumericalArtefactsAndInstabilities<ValueType>(config, sourceSettingsShot, modelLocal, modelCoordinates, shotNumber);
             if (config.getAndCatch("writeSource", false))
-                sources.getSeismogramHandler().write(config.get<IndexType>("SeismogramFormat"), config.get<std::string>("writeSourceFilename") + ".shot_" + std::to_string(shotNumber));
+                sources.getSeismogramHandler().write(config.get<IndexType>("SeismogramFormat"), config.get<std::string>("writeSourceFilename") + ".shot_" + std::to_string(shotNumber), &modelCoordinates);
             if (config.get<IndexType>("useReceiversPerShot") != 0)
                 receivers.init(config, modelCoordinates, shotNumber);
             receivers.getSeismogramHandler().resetData();
@@ -109,7 +109,10 @@ static void runShotDomain(Configuration::Configuration const &config, IndexType 
                 HOST_PRINT("Finished time stepping for shot number: " << shotNumber << " in " << now() - start_t << " sec.\n")
             }
             receivers.getSeismogramHandler().normalize(config.get<IndexType>("normalizeTraces"));
-            receivers.getSeismogramHandler().write(config.get<IndexType>("SeismogramFormat"), config.get<std::string>("SeismogramFilename") + ".shot_" + std::to_string(shotNumber));
+            // the SU trace headers refer to the source position when the shot has a single source (Simulation.cpp, Seismogram.cpp:939)
+            receivers.getSeismogramHandler().setSourceCoordinate(sources.get1DCoordinates().size() == 1 ? sources.get1DCoordinates()[0] : 0);
+            receivers.getSeismogramHandler().write(config.get<IndexType>("SeismogramFormat"), config.get<std::string>("SeismogramFilename") + ".shot_" + std::to_string(shotNumber),
+                                                   &modelCoordinates);
         }
     } catch (std::exception const &e) {
         *error = e.what();

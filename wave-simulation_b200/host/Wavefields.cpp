@@ -98,7 +98,11 @@ template <typename ValueType> void Wavefields::Wavefields<ValueType>::write(Inde
         for (auto const &c : second)
             IO::writeVector(get(c), baseName + "." + c + "." + timeStep, fileFormat);
         break;
-    case 3: COMMON_THROWEXCEPTION("snapType 3 (div / curl) is not available in the B200 host layer")
+    case 3: // Wavefields3Delastic.cpp:82-92, Wavefields2Delastic.cpp:75-85: energy of the S- and P-wave parts
+        SCAI_ASSERT_ERROR(equationType == "elastic" || equationType == "viscoelastic", "There is no curl or div of wavefield in the " << numDimension << "D " << equationType << " case.")
+        IO::writeVector(get("CURL"), baseName + ".CURL." + timeStep, fileFormat);
+        IO::writeVector(get("DIV"), baseName + ".DIV." + timeStep, fileFormat);
+        break;
     default: COMMON_THROWEXCEPTION("Invalid snapType.")
     }
 }

@@ -26,7 +26,7 @@ namespace KITGPI
             std::vector<std::string> const &getComponents() const { return all; }
             std::vector<ValueType> get(std::string const &component) const;       // e.g. "VX", "Sxy", "P", "EZ", "Rxx1"
             void set(std::string const &component, std::vector<ValueType> const &values);
-            //! snapType 1 or 2 (3 = div/curl belongs to the inversion tool chain and is not available here)
+            //! snapType 1 = first half-step fields, 2 = second half-step fields, 3 = curl / div energy measures (elastic, viscoelastic)
             void write(IndexType snapType, std::string baseName, IndexType t, IndexType fileFormat) const;
             std::string getEquationType() const { return equationType; }
             IndexType getNumDimension() const { return numDimension; }
