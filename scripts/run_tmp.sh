@@ -1,1 +1,6 @@
-for c in 32 48 64 80 96; do echo "fast chunk $c"; WS_FAST_CHUNK=$c python bench.py --steps 10 --warmup 3 --no-cpu 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); r=d['roofline']; print(round(d['value'],2), round(r['ms_first'],3), round(r['ms_second'],3), round(r['frac'],3))"; done
+cp wave-simulation_b200/csrc/libwavesim_cuda.so /tmp/new.so
+echo "== new"; WS_MARCH_LANES=1 WS_MARCH_SINGLE=0 WORKLOADS="northstar cfg4" STAGES="0" scripts/march_sweep.sh
+cp alt_old.so wave-simulation_b200/csrc/libwavesim_cuda.so
+echo "== old"; WS_MARCH_LANES=1 WORKLOADS="northstar cfg4" STAGES="0" scripts/march_sweep.sh
+cp /tmp/new.so wave-simulation_b200/csrc/libwavesim_cuda.so
+echo "== new again"; WS_MARCH_LANES=1 WS_MARCH_SINGLE=0 WORKLOADS="northstar" STAGES="0" scripts/march_sweep.sh

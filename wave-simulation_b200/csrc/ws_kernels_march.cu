@@ -47,13 +47,15 @@ template <int EQ, int DIM, int Q, int PASS, int NL> void launchP(const WsParams 
         launchK<EQ, DIM, Q, PASS, 2, NL>(P, 2 * stage, st);
 }
 
-// one x point per thread where the operands of a plane are so many that 4 points per thread would leave one thread
-// block of 4 warps per SM (3-D half-steps with memory variables); 4 points per thread otherwise
+// one x point per thread where the operands of a plane are so many that 4 points per thread would leave one or two
+// thread blocks of 4 warps per SM (the 3-D elastic / viscoelastic half-steps); 4 points per thread otherwise
 template <int EQ, int DIM, int Q> void launchT(const WsParams &P, int pass, cudaStream_t st)
 {
-    constexpr bool heavy = DIM == 3 && (EQ == WS_EQ_VISCOELASTIC || EQ == WS_EQ_VISCOEMEM);
+    // (measured: 3-D viscoelastic 768^3 velocity half-step 7.9 ms with 1 point against 9.1 ms with 4, stress half-step
+    // 23.8 against 40.3 ms; 3-D elastic 1024^3 17.7 / 21.0 against 19.8 / 22.1 ms)
+    constexpr bool heavy = DIM == 3 && (EQ == WS_EQ_ELASTIC || EQ == WS_EQ_VISCOELASTIC || EQ == WS_EQ_VISCOEMEM);
     if constexpr (heavy) {
-        const bool one = P.marchLanes == 1 || (P.marchLanes == 0 && pass == 1 && P.L > 0 && P.marchStageR);
+        const bool one = P.marchLanes == 1 || (P.marchLanes == 0 && (EQ != WS_EQ_VISCOEMEM || (pass == 1 && P.L > 0 && P.marchStageR)));
         if (one) {
             if (pass == 0)
                 launchP<EQ, DIM, Q, 0, 1>(P, st);
