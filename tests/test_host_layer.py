@@ -225,6 +225,15 @@ def test_driver_su_seismograms(driver, tmp_path):
         assert word(h, 72, "i") == 20 * 50 * 1000 and word(h, 48, "i") == 0                      # sx, sdepth (source at (20, 0))
         assert word(h, 80, "i") == xr * 50 * 1000 and word(h, 40, "i") == yr * 50 * 1000          # gx, gelev
         assert word(h, 36, "i") == int(round(np.hypot((xr - 20) * 50.0, yr * 50.0) * 1000.0))     # offset
+    # initReceiverFromSU=1: the receiver geometry comes from the trace headers of <ReceiverFilename>.<comp>.su (suHandler.cpp)
+    os.makedirs(os.path.join(tmp, "acq_su"), exist_ok=True)
+    os.rename(os.path.join(tmp, "seismograms", "seismogram.shot_1.vy.su"), os.path.join(tmp, "acq_su", "rec.vy.su"))
+    open(os.path.join(tmp, "acq", "receiver.txt"), "w").write("# unused\n1 1 0 1\n")
+    text = open(cfg).read().replace("initReceiverFromSU=0", "initReceiverFromSU=1").replace("ReceiverFilename=acq/receiver", "ReceiverFilename=acq_su/rec")
+    open(cfg, "w").write(text.replace("snapType=3", "snapType=0"))
+    run(driver, cfg, tmp)
+    again = read_mtx(os.path.join(tmp, "seismograms", "seismogram.shot_1.vy.mtx"))
+    assert np.array_equal(again, mtx)
 
 
 def test_driver_error_behaviour(driver, tmp_path):

@@ -419,7 +419,7 @@ void Acquisition::AcquisitionGeometry<ValueType>::setAcquisition(std::vector<Set
 
 template <typename ValueType> void Acquisition::Sources<ValueType>::getAcquisitionSettings(Configuration::Configuration const &config)
 {
-    SCAI_ASSERT_ERROR(!config.getAndCatch("initSourcesFromSU", false), "initSourcesFromSU=1 (SU input) is not available in the B200 host layer")
+    SCAI_ASSERT_ERROR(!config.getAndCatch("initSourcesFromSU", false), "initSourcesFromSU=1 (source positions and signals from SU files) is not available in the B200 host layer")
     readAllSettings(allSourceSettings, config.get<std::string>("SourceFilename") + ".txt");
 }
 
@@ -468,9 +468,40 @@ void Acquisition::Receivers<ValueType>::init(std::vector<receiverSettings> const
     this->seismograms.setSeismoDT(config.get<ValueType>("seismoDT"));
 }
 
+// receiver geometry from the trace headers of <filename>.<component>.su (suHandler.cpp:33-52,88-107): grid coordinates
+// x = gx 10^scalco / DH, y = gelev 10^scalel / DH, z = gy 10^scalco / DH (truncated), type = component of the file name
+template <typename ValueType> static void readReceiverSettingsFromSU(std::vector<Acquisition::receiverSettings> &all, std::string const &filename, ValueType DH)
+{
+    all.clear();
+    IndexType missing = 0;
+    for (IndexType comp = 0; comp < Acquisition::NUM_ELEMENTS_SEISMOGRAMTYPE; comp++) {
+        const std::string name = filename + "." + Acquisition::SeismogramTypeString[comp];
+        const IndexType ntr = SUIO::numTracesSU(name);
+        if (ntr == 0) {
+            missing++;
+            continue;
+        }
+        for (IndexType tr = 0; tr < ntr; tr++) {
+            const double sco = std::pow(10.0, SUIO::readHeaderWordSU(name, tr, "scalco")), sel = std::pow(10.0, SUIO::readHeaderWordSU(name, tr, "scalel"));
+            Acquisition::receiverSettings r;
+            r.receiverCoords.x = static_cast<IndexType>((ValueType)(SUIO::readHeaderWordSU(name, tr, "gx") * sco) / DH);
+            r.receiverCoords.y = static_cast<IndexType>((ValueType)(SUIO::readHeaderWordSU(name, tr, "gelev") * sel) / DH);
+            r.receiverCoords.z = static_cast<IndexType>((ValueType)(SUIO::readHeaderWordSU(name, tr, "gy") * sco) / DH);
+            r.receiverType = comp + 1;
+            all.push_back(r);
+        }
+    }
+    SCAI_ASSERT_ERROR(missing < Acquisition::NUM_ELEMENTS_SEISMOGRAMTYPE, "No file with name: " << filename << ".'comp'.su could be read")
+}
+
 template <typename ValueType> void Acquisition::Receivers<ValueType>::init(Configuration::Configuration const &config, Coordinates<ValueType> const &modelCoordinates)
 {
-    SCAI_ASSERT_ERROR(!config.getAndCatch("initReceiverFromSU", false), "initReceiverFromSU=1 (SU input) is not available in the B200 host layer")
+    if (config.getAndCatch("initReceiverFromSU", false)) { // Receivers.cpp: acquisition from the SU trace headers
+        std::vector<receiverSettings> all;
+        readReceiverSettingsFromSU<ValueType>(all, config.get<std::string>("ReceiverFilename"), modelCoordinates.getDH());
+        init(all, config, modelCoordinates);
+        return;
+    }
     std::vector<receiverSettings> all;
     readAllSettings(all, config.get<std::string>("ReceiverFilename") + ".txt");
     init(all, config, modelCoordinates);

@@ -275,3 +275,21 @@ double KITGPI::SUIO::readHeaderWordSU(std::string const &filename, IndexType tra
     SCAI_ASSERT_ERROR(in.good(), name << " has no trace " << trace)
     return suGet(hdr, suKey(key));
 }
+
+IndexType KITGPI::SUIO::numTracesSU(std::string const &filename)
+{
+    const std::string name = filename + ".su";
+    std::ifstream in(name, std::ios::binary | std::ios::ate);
+    if (!in.good())
+        return 0;
+    const std::streamoff size = in.tellg();
+    if (size < 240)
+        return 0;
+    in.seekg(0);
+    unsigned char hdr[240];
+    in.read(reinterpret_cast<char *>(hdr), 240);
+    const IndexType ns = (IndexType)suGet(hdr, suKey("ns"));
+    const std::streamoff rec = 240 + (std::streamoff)sizeof(float) * ns;
+    SCAI_ASSERT_ERROR(size % rec == 0, name << " is not a sequence of SU traces with " << ns << " samples")
+    return (IndexType)(size / rec);
+}

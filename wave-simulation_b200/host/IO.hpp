@@ -30,5 +30,7 @@ namespace KITGPI
         void readDataSU(std::string const &filename, std::vector<ValueType> &data, IndexType &ntr, IndexType &ns);
         //! one header word of trace `trace` by its SU keyword: tracl offset gelev sdepth sx sy gx gy ns dt scalco ntr ... (for tests / suHandler)
         double readHeaderWordSU(std::string const &filename, IndexType trace, std::string const &key);
+        //! number of traces of <filename>.su (0 if the file does not exist)
+        IndexType numTracesSU(std::string const &filename);
     }
 }
