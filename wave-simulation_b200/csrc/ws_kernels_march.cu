@@ -136,7 +136,7 @@ bool wsMarchSupported(const WsParams &P, bool exact)
 // planes at the start of every chunk, bounds the chunk from below.
 void wsMarchPrepare(WsParams &P)
 {
-    const int TX = P.dim == 3 ? 64 : 256, TZ = P.dim == 3 ? 8 : 1;
+    const int TX = P.dim == 3 ? 64 : WS_MARCH_TX2D, TZ = P.dim == 3 ? 8 : 1;
     P.marchLanes = getenv("WS_MARCH_LANES") ? atoi(getenv("WS_MARCH_LANES")) : 0;
     const long long tiles = (long long)((P.nx + TX - 1) / TX) * ((P.nz + TZ - 1) / TZ);
     const long long want = 148LL * 20;

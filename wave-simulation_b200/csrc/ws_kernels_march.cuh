@@ -89,7 +89,10 @@ __host__ __device__ constexpr int findIn(const int *a, int n, int v)
 template <int DIM, int Q, int NL> struct Geo {
     static constexpr int H = Q / 2;
     static constexpr int HX = H <= 4 ? 4 : 8; // x halo rounded to whole 16-byte copies
-    static constexpr int TX = DIM == 3 ? (NL == 4 ? 64 : 32) : (NL == 4 ? 256 : 128), TZ = DIM == 3 ? 8 : 1;
+#ifndef WS_MARCH_TX2D
+#define WS_MARCH_TX2D 256 /* developer switch: width of the 2-D strips */
+#endif
+    static constexpr int TX = DIM == 3 ? (NL == 4 ? 64 : 32) : (NL == 4 ? WS_MARCH_TX2D : 128), TZ = DIM == 3 ? 8 : 1;
     static constexpr int HZ = DIM == 3 ? H : 0;
     static constexpr int LDX = TX + 2 * HX, NROW = TZ + 2 * HZ, TILE = LDX * NROW; // staged tile with halo
     static constexpr int NP = TX * TZ;                                            // plain tile (own points)
