@@ -867,7 +867,9 @@ void *wsFastPrepare(WsParams &P, int nyp)
         maps[TM_PX] = makeMapG(P.psiXArena, P.psiPitchX, P.nz, P.nyl, APS_COUNT, P.psiBoxX, TZ, 3);
         maps[TM_PZ] = makeMapG(P.psiZArena, P.nx, W2, P.nyl, APS_COUNT, TX, TZ, 3);
     }
-    P.fastFlags = getenv("WS_FAST_FLAGS") ? atoi(getenv("WS_FAST_FLAGS")) : 3;
+    // bit 0 = L2 eviction-priority hints on the TMA loads, bit 1 = layer tiles in a launch of their own.  With 64-plane chunks
+    // the hints no longer pay (36.7 Gpt/s with, 37.1 without at 1024^3), the separate launch still does (32.0 without)
+    P.fastFlags = getenv("WS_FAST_FLAGS") ? atoi(getenv("WS_FAST_FLAGS")) : 2;
     // tile list: layer tiles first (z layers and corners, then x layers: longest first; neighbours adjacent), then interior
     const int ntx = (P.nx + TX - 1) / TX, ntz = (P.nz + TZ - 1) / TZ;
     std::vector<int> tilesCorner, tilesZ, tilesX, tilesIn;
