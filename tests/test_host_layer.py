@@ -236,6 +236,31 @@ def test_driver_su_seismograms(driver, tmp_path):
     assert np.array_equal(again, mtx)
 
 
+def test_two_layer_tool_feeds_the_driver(driver, tmp_path):
+    """host/Tools/TwoLayer (src/Tools/CreateModel/TwoLayer.cpp): the model it writes equals the fixture the other tests
+    build in numpy, in both file formats, and the tool refuses to run without a configuration."""
+    subprocess.check_call(["make", "-s", "-C", HOST, "Tools/TwoLayer"])
+    tool = os.path.join(HOST, "Tools", "TwoLayer")
+    tmp = str(tmp_path)
+    m = two_layer(100, 100, 1)
+    for fmt, ext in ((1, ".mtx"), (2, ".lmf")):
+        cfg = setup_case(tmp, fmt=fmt)
+        for suffix in ("vp", "vs", "density"):
+            os.remove(os.path.join(tmp, "model", "model." + suffix + ext))
+        subprocess.run([tool, cfg], cwd=tmp, check=True)
+        assert sorted(os.listdir(os.path.join(tmp, "model"))) == sorted("model." + sfx + e for sfx in ("vp", "vs", "density") for e in ((".mtx", ".lmf") if fmt == 2 else (".mtx",)))
+        for key, suffix in (("velocityP", "vp"), ("velocityS", "vs"), ("density", "density")):
+            path = os.path.join(tmp, "model", "model." + suffix + ext)
+            if fmt == 1:
+                v = read_mtx(path).ravel()
+            else:
+                raw = open(path, "rb").read()
+                v = np.frombuffer(raw[20:], "<f4")
+            assert np.array_equal(v.astype(np.float32), m[key]), (fmt, key)
+    p = subprocess.run([tool], capture_output=True, text=True)
+    assert p.returncode == 2 and "No configuration file given" in p.stdout
+
+
 def test_driver_error_behaviour(driver, tmp_path):
     tmp = str(tmp_path)
     cfg = setup_case(tmp)
