@@ -35,7 +35,11 @@ def test_emulated_kernels_fma_mode(cfg):
     assert rel_l2(e.seismogram(), o.seismogram()) <= 1.0e-5
 
 
-@pytest.mark.parametrize("cfg", SWEEP, ids=[sweep_id(c) for c in SWEEP])
+# every equation type once (the GPU suite runs the whole sweep)
+MARCH_EMU = [c for k, c in enumerate(SWEEP) if k in (0, 2, 3, 6, 8, 9, 11, 12, 14, 15, 17, 18, 19, 20)]
+
+
+@pytest.mark.parametrize("cfg", MARCH_EMU, ids=[sweep_id(c) for c in MARCH_EMU])
 def test_emulated_marching_kernels_equal_per_point_kernels(cfg):
     """The marching kernels (register queues + staged planes, ws_kernels_march.cuh) run the statement sequence of the
     per-point kernels with the weights applied in the same order: bit-identical wavefields in FMA mode."""

@@ -101,7 +101,7 @@ def build_emu(force=False):
     newest = max(newest, os.path.getmtime(os.path.join(ROOT, "tests", "emu", "cuda_emu.hpp")),
                  os.path.getmtime(os.path.join(ROOT, "include", "wavesim.h")))
     if force or not os.path.exists(EMU_SO) or os.path.getmtime(EMU_SO) < newest:
-        subprocess.check_call(["make", "-s", "-B", "-C", os.path.join(ROOT, "tests", "emu")])
+        subprocess.check_call(["make", "-s", "-j", str(min(8, os.cpu_count() or 2)), "-C", os.path.join(ROOT, "tests", "emu")])
     return EMU_SO
 
 

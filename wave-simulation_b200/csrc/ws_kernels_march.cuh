@@ -2,15 +2,18 @@
 // the warp-specialised TMA kernels (ws_kernels_fast.cu, 3-D elastic only) do not cover.
 //
 // 2.5-D blocking.  A thread block owns a TX x TZ tile of the x-z plane (a TX-wide strip of the row in 2-D) and marches
-// along y, the slowest axis; a thread owns FOUR consecutive x points of one row (128-bit shared-memory loads, 128-bit
-// global stores, index arithmetic shared by the four points).
-//   * every operand of a plane is staged in shared memory by 16-byte cp.async copies into a ring of NST stages, so
-//     NST-1 planes are in flight while one is computed: the halo tiles of the fields differentiated along x or z, the
-//     plane that enters each y window, and the own-point operands (updated fields, model parameters, memory variables);
+// along y, the slowest axis, in chunks of <= 64 planes (thread blocks of one y range march in step and share their halo
+// rows in L2: ws_kernels_march.cu); a thread owns FOUR consecutive x points of one row (128-bit shared-memory loads,
+// 128-bit global stores, index arithmetic shared by the four points) — ONE point in the 3-D elastic / viscoelastic
+// half-steps, whose operands are so many that shared memory would otherwise leave 4-8 warps per SM.
+//   * every operand of a plane is staged in shared memory by 16-byte cp.async copies into a ring of NST stages (2: the
+//     next plane is in flight while one is computed; deeper rings cost resident thread blocks and lose, measured): the
+//     halo tiles of the fields differentiated along x or z, the plane that enters each y window, and the own-point
+//     operands (updated fields, model parameters, memory variables);
 //   * y derivatives: every field differentiated along y lives in a REGISTER QUEUE of q+1 planes per thread, fed from the
 //     staged plane y + q/2: each value is read from memory once per thread block instead of q times;
 //   * the statement sequence is the one of the per-point kernels: the point type below only supplies the operands of
-//     wsgen::passA / passB (derivatives D<F, OP>(), own-point values, CPML / ABS / free-surface terms) as 4-lane
+//     wsgen::passA / passB (derivatives D<F, OP>(), own-point values, CPML / ABS / free-surface terms) as NL-lane
 //     values, every lane sees the scalar operation order, and the weights are applied in the same ascending-column
 //     order, so the results are bit-identical to the per-point kernels in FMA mode (checked by the tests);
 //   * tiles and planes that lie inside the grid on every axis (no edge rows, no CPML / ABS layer) run an instantiation
