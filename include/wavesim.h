@@ -124,8 +124,8 @@ int ws_step_host(ws_solver *s, int32_t t, const float *src_samples, float *rec_s
 int ws_get_seismogram(ws_solver *s, float *host);
 /* wavefield component by reference name: "VX" "VY" "VZ" "Sxx" "Syy" "Szz" "Sxy" "Sxz" "Syz" "P" "Rxx1".. /
  * "HX" "HY" "HZ" "EX" "EY" "EZ" "RX1"..  (Wavefields/Wavefields.hpp:83-141). Local slab, n = nyl*nz*nx.
- * Elastic / viscoelastic only: "CURL" and "DIV", the snapType 3 energy measures computed from the particle
- * velocities (Wavefields3Delastic.cpp:197-245 getCurl / getDiv).                                                */
+ * "CURL" and "DIV": the snapType 3 energy measures computed from the particle velocities (elastic / viscoelastic,
+ * Wavefields3Delastic.cpp:197-245 getCurl / getDiv) or the magnetic field (2-D TMEz, 3-D EM: WavefieldsEM/).    */
 int ws_get_wavefield(ws_solver *s, const char *comp, float *host, size_t n);
 int ws_set_wavefield(ws_solver *s, const char *comp, const float *host, size_t n);
 int ws_is_finite(ws_solver *s, int32_t *flag); /* Wavefields::isFinite + SeismogramHandler::isFinite, Simulation.cpp:519 */

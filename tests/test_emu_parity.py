@@ -108,6 +108,37 @@ def test_div_curl_snapshot(dim):
         a_case.setup(EmuSolver(a_case.desc)).wavefield("DIV")
 
 
+@pytest.mark.parametrize("eq,dim", [("tmem", 2), ("viscoemem", 3)])
+def test_div_curl_snapshot_em(eq, dim):
+    """EM variants (WavefieldsEM/Wavefields2Dtmem.cpp, Wavefields3Dviscoemem.cpp): magnetic field, curl scaled by the
+    permittivity, div by the EM velocity 1/sqrt(eps mu) (3-D visco: by the conductivity)."""
+    nx, ny, nz = 24, 22, (20 if dim == 3 else 1)
+    case = make_case(eq, dim, nx, ny, nz, 4, 0, 0, 0, 6, 1 if eq.startswith("visco") else 0, nt=4, exact=1)
+    e = case.setup(EmuSolver(case.desc))
+    y, z, x = np.meshgrid(np.arange(ny), np.arange(nz), np.arange(nx), indexing="ij")
+    a, b, c = 3.0, -2.0, 0.5
+    e.set_wavefield("HX", (a * y + 2 * x).astype(np.float32))
+    e.set_wavefield("HY", (b * x + c * z + 1.5 * y).astype(np.float32))
+    if dim == 3:
+        e.set_wavefield("HZ", (0.25 * y - 1.0 * z).astype(np.float32))
+    s = np.float32(case.desc.dt / case.desc.dh)
+    eps = case.materials["dielectricPermittivity"].reshape(ny, nz, nx).astype(np.float64)
+    mu = case.materials["magneticPermeability"].reshape(ny, nz, nx).astype(np.float64)
+    sig = case.materials["electricConductivity"].reshape(ny, nz, nx).astype(np.float64)
+    div, curl = e.wavefield("DIV").reshape(ny, nz, nx), e.wavefield("CURL").reshape(ny, nz, nx)
+    inner = (slice(3, ny - 3), slice(3, nz - 3) if dim == 3 else slice(None), slice(3, nx - 3))
+    if dim == 3:
+        d = (2 + 1.5 - 1.0) * s
+        want_div = np.sqrt(d * d * sig)  # Wavefields3Dviscoemem.cpp:99: the conductivity
+        cx, cz = (0.25 - c) * s, (b - a) * s
+        want_curl = np.sqrt((cx * cx + cz * cz) * eps)
+    else:
+        want_div = (2 + 1.5) * s * np.sqrt(1.0 / np.sqrt(eps * mu))
+        want_curl = (a - b) * s * np.sqrt(eps)
+    assert np.allclose(div[inner], want_div[inner], rtol=3e-5)
+    assert np.allclose(curl[inner], want_curl[inner], rtol=3e-5)
+
+
 def test_emulated_ci_case_2d_elastic_full_trace():
     case = ci_case("2D.elastic")
     for exact, tol in ((1, 0.0), (0, 1.0e-5)):

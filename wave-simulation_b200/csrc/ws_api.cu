@@ -1610,7 +1610,12 @@ int ws_get_wavefield(ws_solver *s, const char *comp, float *host, size_t n)
         const std::string name(comp);
         if (name == "CURL" || name == "DIV") {
             // snapType 3 (Wavefields3Delastic.cpp:86-91): derived from the particle velocities with the plain operators
-            WS_REQUIRE(s->d.eq == WS_EQ_ELASTIC || s->d.eq == WS_EQ_VISCOELASTIC, WS_EINVAL, "There is no curl or div of wavefield in this modelling");
+            // elastic / viscoelastic, 2-D TMEz / viscoTMEz, 3-D EM / viscoEM (the wavefield classes that implement getCurl / getDiv)
+            const int eq = s->d.eq;
+            const bool ok = eq == WS_EQ_ELASTIC || eq == WS_EQ_VISCOELASTIC || ((eq == WS_EQ_TMEM || eq == WS_EQ_VISCOTMEM) && s->d.dim == 2) ||
+                            ((eq == WS_EQ_EMEM || eq == WS_EQ_VISCOEMEM) && s->d.dim == 3);
+            WS_REQUIRE(ok, WS_EINVAL, "There is no curl or div of wavefield in this modelling");
+            WS_REQUIRE(s->seismic || (s->mat[M_EPS].p && s->mat[M_MUM].p && s->mat[M_SIG].p), WS_ESTATE, "the EM model parameters must be set before the curl / div snapshot");
             WS_REQUIRE(s->prepared, WS_ESTATE, "ws_prepare must precede the curl / div snapshot");
             WS_REQUIRE(n == (size_t)s->nx * s->nyl * s->nz, WS_EINVAL, "size mismatch");
             DevBuf<float> tmp;

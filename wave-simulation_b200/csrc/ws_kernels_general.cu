@@ -90,10 +90,21 @@ void wsLaunchDivCurl(const WsParams &P, float *out, int which, cudaStream_t st)
         return;
     dim3 grid, block;
     wsGeneralGrid(P, grid, block);
-    auto k2 = wsgen::kDivCurl<2>;
-    auto k3 = wsgen::kDivCurl<3>;
-    if (P.dim == 3)
-        WS_LAUNCH(k3, grid, block, 0, st, P, out, which);
-    else
-        WS_LAUNCH(k2, grid, block, 0, st, P, out, which);
+    const bool em = P.eq == WS_EQ_TMEM || P.eq == WS_EQ_VISCOTMEM || P.eq == WS_EQ_EMEM || P.eq == WS_EQ_VISCOEMEM;
+    const int divCoef = P.eq == WS_EQ_VISCOEMEM ? 1 : 0; // Wavefields3Dviscoemem.cpp:99 passes the conductivity
+    auto s2 = wsgen::kDivCurl<2, false>;
+    auto s3 = wsgen::kDivCurl<3, false>;
+    auto e2 = wsgen::kDivCurl<2, true>;
+    auto e3 = wsgen::kDivCurl<3, true>;
+    if (em) {
+        if (P.dim == 3)
+            WS_LAUNCH(e3, grid, block, 0, st, P, out, which, divCoef);
+        else
+            WS_LAUNCH(e2, grid, block, 0, st, P, out, which, divCoef);
+    } else {
+        if (P.dim == 3)
+            WS_LAUNCH(s3, grid, block, 0, st, P, out, which, divCoef);
+        else
+            WS_LAUNCH(s2, grid, block, 0, st, P, out, which, divCoef);
+    }
 }

@@ -604,46 +604,64 @@ __global__ void __launch_bounds__(256) kAbsFirstHalf(const __grid_constant__ WsP
             P.fld[fs[k]][t.i] = Ar<EXACT>::mul(P.fld[fs[k]][t.i], d);
 }
 
-// snapType 3 of the elastic / viscoelastic wavefields: P- and S-wave energy measures after Dougherty and Stephen (1988)
-// (Wavefields3Delastic.cpp:197-245 getCurl / getDiv, Wavefields2Delastic.cpp:217-248), reference statement order.
-// which = 0: curl, 1: div.  `out` is a padded array like the wavefields.
-template <int DIM>
-__global__ void __launch_bounds__(256) kDivCurl(const __grid_constant__ WsParams P, float *out, int which)
+// snapType 3: energy measures of the rotational and the divergent part of the first-half-step fields after Dougherty
+// and Stephen (1988), reference statement order.  Seismic (Wavefields3Delastic.cpp:197-245, Wavefields2Delastic.cpp:217-248):
+// particle velocities, curl scaled by the S-wave modulus, div by the P-wave modulus.  EM (WavefieldsEM/Wavefields2Dtmem.cpp,
+// Wavefields3Demem.cpp, Wavefields3Dviscoemem.cpp getCurl / getDiv and the arguments of their write()): magnetic field,
+// curl scaled by the dielectric permittivity, div by the EM velocity 1/sqrt(eps mu) (divCoef = 0) or, in the 3-D visco
+// case, by the conductivity (divCoef = 1).  which = 0: curl, 1: div.  `out` is a padded array like the wavefields.
+template <int DIM, bool EM>
+__global__ void __launch_bounds__(256) kDivCurl(const __grid_constant__ WsParams P, float *out, int which, int divCoef)
 {
     using A = Ar<true>;
+    constexpr int FX = EM ? F_HX : F_VX, FY = EM ? F_HY : F_VY, FZ = EM ? F_HZ : F_VZ;
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int z = blockIdx.y * blockDim.y + threadIdx.y;
     const int ly = P.ylo + blockIdx.z;
     if (x >= P.nx || z >= P.nz || ly >= P.yhi)
         return;
     Pt<true> t(P, x, ly, z);
+    float cDiv, cCurl;
+    if (EM) {
+        cCurl = t.template mat<M_EPS>();
+        if (divCoef == 1)
+            cDiv = t.template mat<M_SIG>();
+        else { // ModelparameterEM.cpp:319-328 calcVelocityFromModulus (Inf / NaN -> 0)
+            cDiv = A::div(1.0f, sqrtf(A::mul(t.template mat<M_EPS>(), t.template mat<M_MUM>())));
+            if (isnan(cDiv) || isinf(cDiv))
+                cDiv = 0.0f;
+        }
+    } else {
+        cCurl = t.template mat<M_MU>();
+        cDiv = t.template mat<M_PW>();
+    }
     float r;
     if (which == 1) {
-        r = t.template D<F_VX, OP_XB>();
-        r = A::add(r, t.template D<F_VY, OP_YB>());
+        r = t.template D<FX, OP_XB>();
+        r = A::add(r, t.template D<FY, OP_YB>());
         if (DIM == 3) {
-            r = A::add(r, t.template D<F_VZ, OP_ZB>());
+            r = A::add(r, t.template D<FZ, OP_ZB>());
             r = A::mul(r, r);
-            r = A::mul(r, t.template mat<M_PW>());
+            r = A::mul(r, cDiv);
             r = sqrtf(r);
         } else
-            r = A::mul(r, sqrtf(t.template mat<M_PW>()));
+            r = A::mul(r, sqrtf(cDiv));
     } else if (DIM == 3) {
-        float u = t.template D<F_VZ, OP_YF>();
-        u = A::sub(u, t.template D<F_VY, OP_ZF>());
+        float u = t.template D<FZ, OP_YF>();
+        u = A::sub(u, t.template D<FY, OP_ZF>());
         r = A::mul(u, u);
-        u = t.template D<F_VX, OP_ZF>();
-        u = A::sub(u, t.template D<F_VZ, OP_XF>());
+        u = t.template D<FX, OP_ZF>();
+        u = A::sub(u, t.template D<FZ, OP_XF>());
         r = A::add(r, A::mul(u, u));
-        u = t.template D<F_VY, OP_XF>();
-        u = A::sub(u, t.template D<F_VX, OP_YF>());
+        u = t.template D<FY, OP_XF>();
+        u = A::sub(u, t.template D<FX, OP_YF>());
         r = A::add(r, A::mul(u, u));
-        r = A::mul(r, t.template mat<M_MU>());
+        r = A::mul(r, cCurl);
         r = sqrtf(r);
     } else {
-        r = t.template D<F_VX, OP_YF>();
-        r = A::sub(r, t.template D<F_VY, OP_XF>());
-        r = A::mul(r, sqrtf(t.template mat<M_MU>()));
+        r = t.template D<FX, OP_YF>();
+        r = A::sub(r, t.template D<FY, OP_XF>());
+        r = A::mul(r, sqrtf(cCurl));
     }
     out[t.i] = r;
 }

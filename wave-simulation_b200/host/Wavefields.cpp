@@ -99,9 +99,15 @@ template <typename ValueType> void Wavefields::Wavefields<ValueType>::write(Inde
             IO::writeVector(get(c), baseName + "." + c + "." + timeStep, fileFormat);
         break;
     case 3: // Wavefields3Delastic.cpp:82-92, Wavefields2Delastic.cpp:75-85: energy of the S- and P-wave parts
-        SCAI_ASSERT_ERROR(equationType == "elastic" || equationType == "viscoelastic", "There is no curl or div of wavefield in the " << numDimension << "D " << equationType << " case.")
-        IO::writeVector(get("CURL"), baseName + ".CURL." + timeStep, fileFormat);
-        IO::writeVector(get("DIV"), baseName + ".DIV." + timeStep, fileFormat);
+        if (equationType == "elastic" || equationType == "viscoelastic") {
+            IO::writeVector(get("CURL"), baseName + ".CURL." + timeStep, fileFormat);
+            IO::writeVector(get("DIV"), baseName + ".DIV." + timeStep, fileFormat);
+        } else if (((equationType == "tmem" || equationType == "viscotmem") && numDimension == 2) || ((equationType == "emem" || equationType == "viscoemem") && numDimension == 3)) {
+            // WavefieldsEM/Wavefields2Dtmem.cpp:75-87, Wavefields3Demem.cpp:70-85: lower-case component names
+            IO::writeVector(get("CURL"), baseName + ".curl." + timeStep, fileFormat);
+            IO::writeVector(get("DIV"), baseName + ".div." + timeStep, fileFormat);
+        } else
+            COMMON_THROWEXCEPTION("There is no curl or div of wavefield in the " << numDimension << "D " << equationType << " case.")
         break;
     default: COMMON_THROWEXCEPTION("Invalid snapType.")
     }
