@@ -150,10 +150,31 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons}
 
 
-def cpu_oracle_throughput(n, steps, warmup=1):
-    """Reference CPU formulation on a bounded sample: 3D elastic FD8, free surface + CPML, n^3 grid."""
+def host_cores():
+    """Physical cores this process may use (affinity mask and hyper-threading taken into account)."""
+    try:
+        aff = len(os.sched_getaffinity(0))
+    except Exception:
+        aff = os.cpu_count() or 1
+    try:
+        import psutil
+        phys = psutil.cpu_count(logical=False) or aff
+    except Exception:
+        phys = aff
+    return max(1, min(aff, phys))
+
+
+def cpu_worker(spec):
+    """Child process of cpu_reference_sample: the reference CPU formulation (oracle CSR restatement of the LAMA path) on a
+    bounded sample of the north-star workload — 3D elastic FD8, free surface + CPML, n^3 grid.  `repeats` timed blocks of
+    `steps` steps after `warm` warm-up steps; the best block counts (pinned threads, best of 3)."""
     from wsharness import Oracle, make_desc, idx1d, ricker_np
-    nt = steps + warmup
+    n, steps, warm, repeats = (int(v) for v in spec.split(","))
+    cores = int(os.environ.get("OMP_NUM_THREADS", "1"))
+    Oracle.num_threads()  # loads the library
+    Oracle.lib.wso_set_threads(cores)
+    Oracle.lib.wso_set_flush_denormals(1)
+    nt = warm + repeats * steps
     d = make_desc(3, "elastic", n, n, n, dh=10.0, dt=8e-4, nt=nt, fd_order=8, edge_policy=0, free_surface=1, damping=2,
                   boundary_width=min(20, n // 4), vmax_cpml=5000.0, fc_cpml=10.0, npower=4.0)
     o = Oracle(d)
@@ -166,30 +187,55 @@ def cpu_oracle_throughput(n, steps, warmup=1):
     o.set_sources([3], [idx1d(n // 2, 1, n // 2, n, n)], ricker_np(nt, d.dt, 10.0, 1.0)[None, :])
     o.set_receivers([3] * 8, [idx1d(n // 4 + 4 * i, 1, n // 2, n, n) for i in range(8)])
     o.reset()
-    o.run(0, warmup)
-    t0 = time.perf_counter()
-    o.run(warmup, nt)
-    dt = time.perf_counter() - t0
-    return float(n) ** 3 * steps / dt / 1e9, dt / steps, Oracle.num_threads()
+    o.run(0, warm)
+    best = None
+    for r in range(repeats):
+        t0 = time.perf_counter()
+        o.run(warm + r * steps, warm + (r + 1) * steps)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    print(json.dumps({"gpts": float(n) ** 3 * steps / best / 1e9, "sec_step": best / steps, "cores": Oracle.num_threads(), "n": n,
+                      "steps": steps, "repeats": repeats}), flush=True)
+
+
+def cpu_reference_sample(n, steps, warm=1, repeats=3):
+    """The CPU arm, in a fresh process whose OpenMP environment is set HERE: all physical cores the process may use, one
+    pinned thread per core — whatever OMP_NUM_THREADS the launcher exported (torchrun sets it to 1).  The same sample
+    serves `cpu_baseline` of the GPU line and the `--impl reference` line."""
+    env = {k: v for k, v in os.environ.items() if not k.startswith(("OMP_", "GOMP_", "KMP_", "MKL_"))}
+    cores = host_cores()
+    env.update(OMP_NUM_THREADS=str(cores), OMP_PROC_BIND="close", OMP_PLACES="cores", OMP_DYNAMIC="false")
+    out = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-worker", "%d,%d,%d,%d" % (n, steps, warm, repeats)], env=env, capture_output=True,
+                         text=True, timeout=1700)
+    if out.returncode != 0:
+        raise RuntimeError("CPU reference sample failed: " + out.stderr[-2000:])
+    r = json.loads(out.stdout.strip().splitlines()[-1])
+    r["sample"] = ("%d^3 grid of the 1024^3 workload, best of %d blocks of %d steps, %d pinned threads (one per physical core), FTZ/DAZ; oracle CSR "
+                   "formulation (restatement of the LAMA sparse path, not the LAMA binary)" % (r["n"], r["repeats"], r["steps"], r["cores"]))
+    return r
+
+
+def cpu_sample_size(n, steps, warm, repeats=3):
+    """bound the run: the CSR formulation moves ~2 kB per grid point and step (about 8e6 point-steps per second and core pair)"""
+    while n > 64 and (repeats * steps + warm) * (n ** 3) / 8.0e6 > 240.0:
+        n -= 32
+    return n
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n = args.ref_n
-    steps, warm = max(1, args.steps), max(0, args.warmup)
-    # bound the run: the CSR formulation moves ~2 kB per grid point and step
-    while n > 64 and (steps + warm) * (n ** 3) / 8.0e6 > 240.0:
-        n -= 32
-    gpts, sec_step, cores = cpu_oracle_throughput(n, steps, max(1, warm))
+    steps, warm = max(1, min(args.steps, 20)), max(1, args.warmup)
+    n = cpu_sample_size(args.ref_n, steps, warm)
+    r = cpu_reference_sample(n, steps, warm)
+    gpts = r["gpts"]
     line = {
         "impl": "reference", "metric": "Gpt-updates/s", "value": gpts, "unit": "Gpt/s", "n_gpus": args.gpus, "steps": steps,
-        "warmup": warm, "ms_per_step": sec_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": warm, "ms_per_step": r["sec_step"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "3D elastic FD8, free surface + CPML(20), synthetic gradient model; CPU sample %d^3 of the 1024^3 workload" % n},
-        "cpu_baseline": {"value": gpts, "unit": "Gpt/s", "cores": cores, "kind": "port",
-                         "sample": "%d^3 grid, %d steps, oracle CSR formulation (restatement of the LAMA sparse path, not the LAMA binary)" % (n, steps)},
+        "cpu_baseline": {"value": gpts, "unit": "Gpt/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
         "e2e": {"value": gpts, "unit": "Gpt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -207,9 +253,10 @@ def main():
     ap.add_argument("--ny", type=int, default=0, help="planes PER GPU")
     ap.add_argument("--nz", type=int, default=0)
     ap.add_argument("--ref-n", type=int, default=192)
-    ap.add_argument("--cpu-n", type=int, default=160)
-    ap.add_argument("--cpu-steps", type=int, default=60, help="time steps of the bounded CPU sample (cpu_baseline)")
+    ap.add_argument("--cpu-worker", default="", help="internal: child process of the CPU arm (n,steps,warm,repeats)")
+    ap.add_argument("--no-others", action="store_true", help="skip the short runs of BASELINE configs 2-5 appended to the default line")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--strong", action="store_true", help="strong scaling: --ny is the GLOBAL number of planes, cut into y-slabs over the GPUs")
     ap.add_argument("--variant", type=int, default=0, help="0 auto (TMA kernels, else marching kernels), 1 per-point kernels, 2 marching kernels")
     ap.add_argument("--damping", type=int, default=-1, help="developer switch: 2 = CPML (the benchmark configuration), 0 = none")
     ap.add_argument("--free-surface", type=int, default=-1, help="developer switch: 1 = image method")
@@ -218,12 +265,13 @@ def main():
     args.nx, args.ny, args.nz = args.nx or wl["n"][0], args.ny or wl["n"][1], (args.nz or wl["n"][2]) if wl["dim"] == 3 else 1
     args.damping = wl["damp"] if args.damping < 0 else args.damping
     args.free_surface = wl["fs"] if args.free_surface < 0 else args.free_surface
+    if args.cpu_worker:
+        return cpu_worker(args.cpu_worker)
     if args.impl == "reference":
         return run_reference(args)
 
     import torch
     import torch.distributed as dist
-    from wsharness import Solver, make_desc, ricker_np
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -232,21 +280,68 @@ def main():
     if world > 1:
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
     W, K = max(3, args.warmup), max(1, args.steps)
-    nx, nyl, nz = args.nx, args.ny, args.nz
-    gny = nyl * world
+    sampler = ClockSampler(local)
+    sampler.start()
+    m = measure(args.workload, args.nx, args.ny, args.nz, K, W, args.variant, args.damping, args.free_surface, world, rank, local, e2e=True, strong=args.strong)
+    sampler.stop_flag = True
+    sampler.join()
+    # BASELINE configs 2-5 (short runs after the headline's timed region: driver-run numbers for the other solvers)
+    others = None
+    if world == 1 and args.workload == "northstar" and not args.no_others and (args.nx, args.ny, args.nz) == WORKLOADS["northstar"]["n"]:
+        others = {}
+        for name in ("cfg2", "cfg3", "cfg4", "cfg5"):
+            o = WORKLOADS[name]
+            try:
+                r = measure(name, o["n"][0], o["n"][1], o["n"][2], 10, 3, args.variant, o["damp"], o["fs"], 1, 0, local, e2e=False)
+                others[name] = {"workload": r["workload"], "value": r["value"], "unit": "Gpt/s", "steps": 10, "warmup": 3, "ms_per_step": r["ms_per_step"],
+                                "kernels": r["kernels"], "frac": r["roofline"]["frac"], "whole_step_frac": r["roofline"]["whole_step_frac"],
+                                "ms_first": r["roofline"]["ms_first"], "ms_second": r["roofline"]["ms_second"], "finite": r["finite"]}
+            except Exception as exc:  # the headline must survive
+                others[name] = {"error": str(exc)[:300]}
+    parity = parity_multi(world, rank, local) if world > 1 else None
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu and world == 1 and args.workload == "northstar":
+            ck, cw = max(1, min(K, 20)), max(1, args.warmup)
+            r = cpu_reference_sample(cpu_sample_size(args.ref_n, ck, cw), ck, cw)
+            cpu = {"value": r["gpts"], "unit": "Gpt/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+        cfg = {"workload": m["workload"], "l2": m["l2"], "kernels": m["kernels"], "finite": m["finite"]}
+        if others is not None:
+            cfg["others"] = others
+        line = {
+            "metric": "Gpt-updates/s", "value": m["value"], "unit": "Gpt/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": cfg, "roofline": m["roofline"], "cpu_baseline": cpu, "e2e": m["e2e"],
+            "gpu_launches": m["launches"], "clocks": sampler.summary(),
+        }
+        if parity is not None:
+            line["parity_multi"] = parity
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def measure(wlname, nx, nyl, nz, K, W, variant, damping, free_surface, world, rank, local, e2e=True, strong=False):
+    """W warm-up steps, exactly K timed steps of workload `wlname` on this rank's slab (nyl planes per GPU); max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from wsharness import Solver, make_desc, ricker_np
+    wl = WORKLOADS[wlname]
+    nz = nz if wl["dim"] == 3 else 1
+    gny = nyl if strong else nyl * world
     nt = 2 * (W + K) + 8
     dt_, dh = wl["dt"], wl["dh"]
-    d = make_desc(wl["dim"], wl["eq"], nx, gny, nz, dh=dh, dt=dt_, nt=nt, fd_order=8, edge_policy=0, free_surface=args.free_surface, damping=args.damping,
+    d = make_desc(wl["dim"], wl["eq"], nx, gny, nz, dh=dh, dt=dt_, nt=nt, fd_order=8, edge_policy=0, free_surface=free_surface, damping=damping,
                   boundary_width=20, vmax_cpml=wl["vmax"], fc_cpml=wl["fc"], npower=4.0, relax_freq=wl["relax"], exact_arith=0,
-                  kernel_variant=args.variant, rank=rank, nranks=world, device=local)
+                  kernel_variant=variant, rank=rank, nranks=world, device=local)
     s = Solver(d)
     if world > 1:
         ids = [Solver.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         s.comm_init(ids[0])
-    set_model_device(s, torch, args.workload, gny, nx, nz)
+    set_model_device(s, torch, wlname, gny, nx, nz)
     s.prepare()
-    src, recs = acquisition(args.workload, nx, gny, nz)
+    src, recs = acquisition(wlname, nx, gny, nz)
     nrec = len(recs)
     amp = 1.0e6 if not wl["eq"].endswith("mem") else 1.0
     sig = ricker_np(nt, dt_, wl["fc"], amp)
@@ -267,8 +362,6 @@ def main():
     s.run(0, W)
     barrier()
     l0 = s.launch_count()
-    sampler = ClockSampler(local)
-    sampler.start()
     s.set_timing(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -277,21 +370,21 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1)
     launches = s.launch_count() - l0
-    msA, msB, msStep = s.last_timing(0), s.last_timing(1), s.last_timing(2)
+    msA, msB = s.last_timing(0), s.last_timing(1)
     # ---- end-to-end run through host buffers: per step H2D of the source samples, D2H of the receiver samples --------
     s.set_timing(False)
-    rec = np.zeros(nrec, np.float32)
-    t_base = W + K
-    for t in range(t_base, t_base + 3):
-        s.step_host(t, sig[t:t + 1], rec)
-    barrier()
-    t0 = time.perf_counter()
-    for t in range(t_base + 3, t_base + 3 + K):
-        s.step_host(t, sig[t:t + 1], rec)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    sampler.stop_flag = True
-    sampler.join()
+    e2e_s = 0.0
+    if e2e:
+        rec = np.zeros(nrec, np.float32)
+        t_base = W + K
+        for t in range(t_base, t_base + 3):
+            s.step_host(t, sig[t:t + 1], rec)
+        barrier()
+        t0 = time.perf_counter()
+        for t in range(t_base + 3, t_base + 3 + K):
+            s.step_host(t, sig[t:t + 1], rec)
+        barrier()
+        e2e_s = time.perf_counter() - t0
     finite = s.is_finite()
 
     t_ms = torch.tensor([ms, e2e_s * 1e3, msA, msB], device="cuda", dtype=torch.float64)
@@ -301,43 +394,73 @@ def main():
         dist.all_reduce(lt)
         launches = int(lt.item())
     ms, e2e_ms, msA, msB = (float(v) for v in t_ms.tolist())
-    npts_local = float(nx) * nyl * nz
+    npts_local = float(nx) * s.nyl * nz  # (strong scaling: the first ranks hold the remainder planes, i.e. the largest slab)
     ws_bytes = s.estimate_memory()
-    npts = npts_local * world
-    value = npts * K / (ms * 1e-3) / 1e9
-    e2e = npts * K / (e2e_ms * 1e-3) / 1e9
-    if rank == 0:
-        peak, which = measured_peak()
-        bA, bB = wl["bytes"]
-        dom = 1 if msB >= msA else 0
-        achieved = (bB if dom else bA) * npts_local / ((msB if dom else msA) * 1e-3) / 1e9
-        cpu = None
-        if not args.no_cpu and world == 1 and args.workload == "northstar":
-            g, sec, cores = cpu_oracle_throughput(args.cpu_n, args.cpu_steps, 1)
-            cpu = {"value": g, "unit": "Gpt/s", "cores": cores, "kind": "port",
-                   "sample": "%d^3 grid, %d steps (%.1f s), oracle CSR formulation (restatement of the LAMA sparse path)" % (args.cpu_n, args.cpu_steps, sec * args.cpu_steps)}
-        line = {
-            "metric": "Gpt-updates/s", "value": value, "unit": "Gpt/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
-            "config": {"workload": "%s %dx%dx%d per GPU (global NY %d), %sCPML(20), y-slab decomposition"
-                                   % (wl["name"], nx, nyl, nz, gny, "free surface + " if args.free_surface else ""),
-                       "l2": "inputs (%.1f GB/GPU of wavefields+model) exceed the 126 MB L2" % (ws_bytes / 1e9),
-                       "kernels": ["per-point", "marching", "tma-tiled"][s.kernel_path()], "finite": bool(finite)},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": measured_traffic(dom, nx, nyl, nz, args.damping, args.free_surface) if args.workload == "northstar" else None,
-                         "kernel": "second half-step (stress / E)" if dom else "first half-step (velocity / H)", "peak_source": which,
-                         "ms_first": msA, "ms_second": msB,
-                         "whole_step_frac": (bA + bB) * npts_local / (ms / K * 1e-3) / 1e9 / peak},
-            "cpu_baseline": cpu,
-            "e2e": {"value": e2e, "unit": "Gpt/s", "h2d_bytes_per_step": 4 * world, "d2h_bytes_per_step": 4 * nrec},
-            "gpu_launches": launches,
-            "clocks": sampler.summary(),
-        }
-        print(json.dumps(line), flush=True)
+    npts = float(nx) * gny * nz
+    nyl = s.nyl
+    peak, which = measured_peak()
+    bA, bB = wl["bytes"]
+    dom = 1 if msB >= msA else 0
+    achieved = (bB if dom else bA) * npts_local / ((msB if dom else msA) * 1e-3) / 1e9
+    traffic = measured_traffic(dom, nx, nyl, nz, damping, free_surface) if wlname == "northstar" else None
+    out = {
+        "workload": "%s %dx%dx%d per GPU (global NY %d), %sCPML(20), y-slab decomposition" % (wl["name"], nx, nyl, nz, gny, "free surface + " if free_surface else ""),
+        "l2": "inputs (%.1f GB/GPU of wavefields+model) exceed the 126 MB L2" % (ws_bytes / 1e9),
+        "kernels": ["per-point", "marching", "tma-tiled", "tma-marching"][s.kernel_path()], "finite": bool(finite),
+        "value": npts * K / (ms * 1e-3) / 1e9, "ms_per_step": ms / K, "launches": launches,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "traffic_source": "committed ncu capture of this configuration (profiles/traffic_1024.json), not measured in this run" if traffic else None,
+                     "kernel": "second half-step (stress / E)" if dom else "first half-step (velocity / H)", "peak_source": which,
+                     "ms_first": msA, "ms_second": msB, "whole_step_frac": (bA + bB) * npts_local / (ms / K * 1e-3) / 1e9 / peak},
+        "e2e": {"value": npts * K / (e2e_ms * 1e-3) / 1e9, "unit": "Gpt/s", "h2d_bytes_per_step": 4 * world, "d2h_bytes_per_step": 4 * nrec} if e2e else None,
+    }
     s.close()
-    if world > 1:
-        dist.destroy_process_group()
+    torch.cuda.empty_cache()
+    return out
+
+
+def parity_multi(world, rank, local):
+    """Driver-visible multi-GPU correctness: a small 3D elastic case (free surface + CPML, TMA kernels) on the `world` ranks
+    of this run against the same case on rank 0 alone; "bit-identical" or the worst relative L2 difference."""
+    import torch.distributed as dist
+    from cases import make_case
+    from wsharness import Solver, rel_l2
+    nx, ny, nz, nt = 128, 48 * world, 48, 24
+    fields = ["VX", "VY", "VZ", "Sxx", "Syy", "Szz", "Sxy", "Sxz", "Syz"]
+    case = make_case("elastic", 3, nx, ny, nz, 8, 0, 1, 2, W=10, L=0, nt=nt, exact=0, kernel_variant=0)
+    case.desc.rank, case.desc.nranks, case.desc.device = rank, world, local
+    s = Solver(case.desc)
+    ids = [Solver.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    s.comm_init(ids[0])
+    case.setup(s)
+    s.run(0, nt)
+    s.sync()
+    mine = (s.y0, s.nyl, s.seismogram(), {f: s.wavefield(f) for f in fields}, s.kernel_path())
+    s.close()
+    parts = [None] * world if rank == 0 else None
+    dist.gather_object(mine, parts, dst=0)
+    if rank != 0:
+        return None
+    case.desc.rank, case.desc.nranks = 0, 1
+    ref = case.setup(Solver(case.desc))
+    ref.run(0, nt)
+    ref.sync()
+    worst, same = 0.0, True
+    seis = np.zeros_like(ref.seismogram())
+    plane = nx * nz
+    for y0, nyl, sg, fl, path in parts:
+        seis += sg
+        for f in fields:
+            a, b = fl[f], ref.wavefield(f)[y0 * plane:(y0 + nyl) * plane]
+            if not np.array_equal(a, b):
+                same = False
+                worst = max(worst, rel_l2(a, b))
+    if not np.array_equal(seis, ref.seismogram()):
+        same = False
+        worst = max(worst, rel_l2(seis, ref.seismogram()))
+    ref.close()
+    return "bit-identical" if same else worst
 
 
 if __name__ == "__main__":

@@ -1986,4 +1986,35 @@ int wso_num_threads(void)
 #endif
     return n;
 }
+
+// bench.py only: number of OpenMP threads of the following runs (the launcher's OMP_NUM_THREADS must not decide it)
+void wso_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0)
+        omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
+// bench.py only: flush-to-zero / denormals-are-zero in every OpenMP thread.  The timed sample runs on a wavefield whose
+// front is a shell of fp32 denormals; x86 handles those in microcode, which would make the CPU baseline depend on how far
+// the front has travelled.  Never set by the parity tests (it changes roundings near zero).
+void wso_set_flush_denormals(int on)
+{
+#if defined(__x86_64__) || defined(__i386__)
+#pragma omp parallel
+    {
+        unsigned csr = __builtin_ia32_stmxcsr();
+        if (on)
+            csr |= 0x8040u; // FTZ | DAZ
+        else
+            csr &= ~0x8040u;
+        __builtin_ia32_ldmxcsr(csr);
+    }
+#else
+    (void)on;
+#endif
+}
 }

@@ -69,3 +69,79 @@ def test_nccl_slabs_equal_single_gpu(cfg, variant, world):
             assert np.array_equal(a, ref_fields[f][y0 * plane:(y0 + nyl) * plane]), (rank, f)
     assert np.abs(ref_seis).max() > 0
     assert np.array_equal(seis, ref_seis)
+
+
+def test_two_handles_on_two_devices_in_one_process():
+    """One process, two solver handles on two GPUs (what host/Simulation does for NumShotDomains > 1): the dynamic
+    shared-memory opt-in of the TMA / marching kernels is a per-device attribute and must reach both devices."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from wsharness import Solver
+    for cfg, variant in ((("elastic", 3, 128, 40, 48, 8, 0, 1, 2, 10, 0), 0), (("viscoelastic", 3, 72, 40, 24, 8, 0, 1, 2, 8, 2), 0), (("acoustic", 2, 300, 80, 1, 8, 1, 0, 2, 8, 0), 0)):
+        eq, dim, nx, ny, nz, q, pol, fs, damp, W, L = cfg
+        nt = 20
+        res = []
+        solvers = []
+        for dev in (0, 1):
+            case = make_case(eq, dim, nx, ny, nz, q, pol, fs, damp, W, L, nt=nt, exact=0, kernel_variant=variant)
+            case.desc.device = dev
+            solvers.append(case.setup(Solver(case.desc)))
+        for s in solvers:  # both GPUs work concurrently
+            s.run(0, nt)
+        for s in solvers:
+            s.sync()
+            assert s.is_finite()
+            res.append((s.seismogram(), {f: s.wavefield(f) for f in fields_of(eq, dim, L)}, s.kernel_path()))
+            s.close()
+        assert res[0][2] == res[1][2] and res[0][2] >= 1
+        assert np.abs(res[0][0]).max() > 0 and np.array_equal(res[0][0], res[1][0])
+        for f in res[0][1]:
+            assert np.array_equal(res[0][1][f], res[1][1][f]), f
+
+
+def _worker_reset(rank, world, uid, cfg, nt, out):
+    from wsharness import Solver
+    eq, dim, nx, ny, nz, q, pol, fs, damp, W, L = cfg
+    case = make_case(eq, dim, nx, ny, nz, q, pol, fs, damp, W, L, nt=nt, exact=0, kernel_variant=0)
+    case.desc.rank, case.desc.nranks, case.desc.device = rank, world, rank
+    s = Solver(case.desc)
+    s.comm_init(uid)
+    case.setup(s)
+    s.run(0, nt)
+    s.reset()  # the last halo exchange of the first shot must not land in the freshly zeroed ghost planes
+    s.run(0, nt)
+    s.sync()
+    out.put((rank, s.y0, s.nyl, s.seismogram(), {f: s.wavefield(f) for f in fields_of(eq, dim, L)}))
+    s.close()
+
+
+def test_run_reset_run_on_two_ranks_equals_single_gpu():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from wsharness import Solver
+    cfg = ("elastic", 3, 128, 96, 48, 8, 0, 1, 2, 10, 0)
+    eq, dim, nx, ny, nz, q, pol, fs, damp, W, L = cfg
+    nt = 30
+    case = make_case(eq, dim, nx, ny, nz, q, pol, fs, damp, W, L, nt=nt, exact=0, kernel_variant=0)
+    ref = case.setup(Solver(case.desc))
+    ref.run(0, nt)
+    ref.sync()
+    ref_seis, ref_fields = ref.seismogram(), {f: ref.wavefield(f) for f in fields_of(eq, dim, L)}
+    ref.close()
+    uid = Solver.comm_unique_id()
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    procs = [ctx.Process(target=_worker_reset, args=(r, 2, uid, cfg, nt, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = sorted((out.get(timeout=300) for _ in range(2)), key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    plane = nx * nz
+    seis = np.zeros_like(ref_seis)
+    for rank, y0, nyl, sg, fields in results:
+        seis += sg
+        for f, a in fields.items():
+            assert np.array_equal(a, ref_fields[f][y0 * plane:(y0 + nyl) * plane]), (rank, f)
+    assert np.array_equal(seis, ref_seis)

@@ -281,6 +281,8 @@ struct ws_solver {
     bool seismic = true, visco = false, exact = false;
     cudaStream_t stream = nullptr, commStream = nullptr;
     cudaEvent_t evCompute = nullptr, evComm = nullptr;
+    cudaEvent_t evComputeG = nullptr, evCommG = nullptr; // the same roles inside a stream capture (a captured event cannot be waited on outside)
+    bool capturing = false;
     DevBuf<float> fldArena, matArena, psiXArena, psiZArena; // declared first: the slots below borrow from them
     DevBuf<float> fld[F_COUNT], mat[M_COUNT], psi[PSI_COUNT];
     bool matGiven[M_COUNT] = {};
@@ -332,6 +334,10 @@ struct ws_solver {
             cudaEventDestroy(evCompute);
         if (evComm)
             cudaEventDestroy(evComm);
+        if (evComputeG)
+            cudaEventDestroy(evComputeG);
+        if (evCommG)
+            cudaEventDestroy(evCommG);
         if (ncclComm && g_nccl.CommDestroy)
             g_nccl.CommDestroy(ncclComm);
         if (pinSrc)
@@ -353,8 +359,7 @@ struct ws_solver {
     }
     void gridFor(int ylo, int yhi, dim3 &grid, dim3 &block) const
     {
-        block = nz > 1 ? dim3(64, 4, 1) : dim3(128, 1, 1);
-        grid = dim3((nx + block.x - 1) / block.x, (nz + block.y - 1) / block.y, std::max(0, yhi - ylo));
+        wsPointGrid(nx, nz, std::max(0, yhi - ylo), grid, block);
     }
     long long offsetOf(int x, int ly, int z) const { return base + x + (long long)z * pitch + (long long)ly * plane; }
 };
@@ -389,6 +394,8 @@ void validateDesc(const ws_desc &d)
     const int nz = d.dim == 2 ? 1 : d.nz;
     (void)nz; // grids beyond 2^31 points are accepted; they need the 64-bit acquisition entry points
     WS_REQUIRE(d.ny / d.nranks >= std::max(d.fd_order / 2, 1) * 2 || d.nranks == 1, WS_EINVAL, "y-slabs thinner than the stencil");
+    // the raw model parameters exchange WS_HALO ghost planes (ws_set_material_device): a thinner slab would send its own ghosts
+    WS_REQUIRE(d.ny / d.nranks >= WS_HALO || d.nranks == 1, WS_EINVAL, "y-slabs thinner than " + std::to_string(WS_HALO) + " planes are not supported");
 }
 
 void slabRange(const ws_desc &d, int rank, int &y0, int &nyl)
@@ -537,6 +544,7 @@ void packPlanes(ws_solver *s, const float *denseDev, float *padded, int ylo, int
     if (grid.z == 0)
         return;
     WS_LAUNCH(wsprep::kPack, grid, block, 0, s->stream, s->geo(ylo, yhi), denseDev, padded, ylo);
+    WS_CUDA_CHECK(cudaGetLastError()); // set-up path: a failed launch must not pass for a copied array
     s->launches++;
 }
 
@@ -566,6 +574,7 @@ void downloadLocal(ws_solver *s, const float *padded, float *hostLocal)
         dim3 grid, block;
         s->gridFor(l0, l1, grid, block);
         WS_LAUNCH(wsprep::kUnpack, grid, block, 0, s->stream, s->geo(l0, l1), padded, s->scratch.p);
+        WS_CUDA_CHECK(cudaGetLastError());
         s->launches++;
         WS_CUDA_CHECK(cudaMemcpyAsync(hostLocal + (size_t)l0 * planeDense, s->scratch.p, (size_t)(l1 - l0) * planeDense * sizeof(float),
                                       cudaMemcpyDeviceToHost, s->stream));
@@ -1012,10 +1021,13 @@ void launchAcquisition(ws_solver *s, const float *srcStepDev, float *recStepDev)
 }
 
 // one reference time step = ForwardSolver::run(...), enqueued asynchronously
-void enqueueStep(ws_solver *s, const float *srcStepDev, float *recStepDev, cudaEvent_t *ev /* 4 events or null */)
+// haloLanded: the halo exchange of the previous step is known to have completed (first step of a captured graph: the
+// wait happened on the stream before the graph was launched)
+void enqueueStep(ws_solver *s, const float *srcStepDev, float *recStepDev, cudaEvent_t *ev /* 4 events or null */, bool haloLanded = false)
 {
     const bool multi = s->d.nranks > 1;
     const int h = s->h, n = s->nyl;
+    const cudaEvent_t evCompute = s->capturing ? s->evComputeG : s->evCompute, evComm = s->capturing ? s->evCommG : s->evComm;
     int fA[3];
     firstHalfFields(s, fA);
     auto gather = [&](const std::vector<int> &slots) {
@@ -1031,13 +1043,14 @@ void enqueueStep(ws_solver *s, const float *srcStepDev, float *recStepDev, cudaE
     } else {
         // interior first (needs no ghost planes), then the edge slabs once the previous exchange has landed
         launchPass(s, 0, h, n - h);
-        WS_CUDA_CHECK(cudaStreamWaitEvent(s->stream, s->evComm, 0));
+        if (!haloLanded)
+            WS_CUDA_CHECK(cudaStreamWaitEvent(s->stream, evComm, 0));
         launchPass(s, 0, 0, std::min(h, n));
         launchPass(s, 0, std::max(n - h, h), n);
-        WS_CUDA_CHECK(cudaEventRecord(s->evCompute, s->stream));
-        WS_CUDA_CHECK(cudaStreamWaitEvent(s->commStream, s->evCompute, 0));
+        WS_CUDA_CHECK(cudaEventRecord(evCompute, s->stream));
+        WS_CUDA_CHECK(cudaStreamWaitEvent(s->commStream, evCompute, 0));
         exchangeHalos(s, gather(s->exchA), h, s->commStream);
-        WS_CUDA_CHECK(cudaEventRecord(s->evComm, s->commStream));
+        WS_CUDA_CHECK(cudaEventRecord(evComm, s->commStream));
     }
     if (ev) {
         WS_CUDA_CHECK(cudaEventRecord(ev[1], s->stream));
@@ -1047,7 +1060,7 @@ void enqueueStep(ws_solver *s, const float *srcStepDev, float *recStepDev, cudaE
         launchPass(s, 1, 0, n);
     } else {
         launchPass(s, 1, h, n - h);
-        WS_CUDA_CHECK(cudaStreamWaitEvent(s->stream, s->evComm, 0));
+        WS_CUDA_CHECK(cudaStreamWaitEvent(s->stream, evComm, 0));
         launchPass(s, 1, 0, std::min(h, n));
         launchPass(s, 1, std::max(n - h, h), n);
     }
@@ -1060,10 +1073,10 @@ void enqueueStep(ws_solver *s, const float *srcStepDev, float *recStepDev, cudaE
     }
     launchAcquisition(s, srcStepDev, recStepDev);
     if (multi) {
-        WS_CUDA_CHECK(cudaEventRecord(s->evCompute, s->stream));
-        WS_CUDA_CHECK(cudaStreamWaitEvent(s->commStream, s->evCompute, 0));
+        WS_CUDA_CHECK(cudaEventRecord(evCompute, s->stream));
+        WS_CUDA_CHECK(cudaStreamWaitEvent(s->commStream, evCompute, 0));
         exchangeHalos(s, gather(s->exchB), h, s->commStream);
-        WS_CUDA_CHECK(cudaEventRecord(s->evComm, s->commStream));
+        WS_CUDA_CHECK(cudaEventRecord(evComm, s->commStream));
     }
 }
 
@@ -1174,6 +1187,8 @@ int ws_create(const ws_desc *desc, ws_solver **out)
             WS_CUDA_CHECK(cudaStreamCreateWithFlags(&s->commStream, cudaStreamNonBlocking));
             WS_CUDA_CHECK(cudaEventCreateWithFlags(&s->evCompute, cudaEventDisableTiming));
             WS_CUDA_CHECK(cudaEventCreateWithFlags(&s->evComm, cudaEventDisableTiming));
+            WS_CUDA_CHECK(cudaEventCreateWithFlags(&s->evComputeG, cudaEventDisableTiming));
+            WS_CUDA_CHECK(cudaEventCreateWithFlags(&s->evCommG, cudaEventDisableTiming));
             WS_CUDA_CHECK(cudaEventRecord(s->evComm, s->commStream));
             if (s->d.eq == WS_EQ_ELASTIC && s->d.dim == 3) {
                 // arena order of the tiled kernels (ws_kernels_fast.cu): neighbours are fetched by one TMA box
@@ -1443,6 +1458,10 @@ int ws_reset(ws_solver *s)
     return guarded([&] {
         WS_REQUIRE(s, WS_EINVAL, "null argument");
         setDevice(s);
+        // the last halo exchange of the previous shot may still be landing in the ghost planes (its ncclRecv completes when
+        // the neighbour sends): the memsets below must come after it
+        WS_CUDA_CHECK(cudaStreamSynchronize(s->commStream));
+        WS_CUDA_CHECK(cudaStreamSynchronize(s->stream));
         for (int k = 0; k < F_COUNT; k++)
             s->fld[k].zero(s->stream); // Wavefields::resetWavefields (Wavefields3Delastic.cpp:111-122)
         for (int k = 0; k < PSI_COUNT; k++)
@@ -1536,10 +1555,14 @@ int ws_run(ws_solver *s, int32_t t0, int32_t t1)
             s->msStep = tot / nsteps;
             return;
         }
+        const bool multi = s->d.nranks > 1;
 #ifdef WS_EMULATE
         const bool canGraph = false;
 #else
-        const bool canGraph = s->d.nranks == 1;
+        // multi-rank: the NCCL send / recv of the halo exchange are captured too (fork to the communication stream and
+        // join at the end of the graph); not with a bring-your-own transport, which is host-synchronous
+        static const bool multiGraph = !(getenv("WS_MULTI_GRAPH") && atoi(getenv("WS_MULTI_GRAPH")) == 0);
+        const bool canGraph = !multi || (multiGraph && s->ncclComm && !s->extFn);
 #endif
         if (!canGraph || nsteps < 4) {
             for (int k = 0; k < nsteps; k++)
@@ -1551,10 +1574,22 @@ int ws_run(ws_solver *s, int32_t t0, int32_t t1)
         const int G = 8;
         if (!s->graphExec) {
             cudaGraph_t graph;
+            if (multi) // nothing of an earlier exchange may be pending when the capture forks the communication stream
+                WS_CUDA_CHECK(cudaStreamSynchronize(s->commStream));
             WS_CUDA_CHECK(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
             const uint64_t before = s->launches;
-            for (int k = 0; k < G; k++)
-                enqueueStep(s, nullptr, nullptr, nullptr);
+            s->capturing = true;
+            try {
+                for (int k = 0; k < G; k++)
+                    enqueueStep(s, nullptr, nullptr, nullptr, multi && k == 0);
+                if (multi) // join: the last exchange of the graph belongs to it
+                    WS_CUDA_CHECK(cudaStreamWaitEvent(s->stream, s->evCommG, 0));
+            } catch (...) {
+                s->capturing = false;
+                cudaStreamEndCapture(s->stream, &graph);
+                throw;
+            }
+            s->capturing = false;
             s->graphLaunchesPerStep = (s->launches - before) / G;
             s->launches = before;
             WS_CUDA_CHECK(cudaStreamEndCapture(s->stream, &graph));
@@ -1565,6 +1600,8 @@ int ws_run(ws_solver *s, int32_t t0, int32_t t1)
         int done = 0;
         const uint64_t perStep = s->graphLaunchesPerStep;
         while (nsteps - done >= G) {
+            if (multi) // the exchange of the step before the graph (the graph's first step does not wait inside)
+                WS_CUDA_CHECK(cudaStreamWaitEvent(s->stream, s->evComm, 0));
             WS_CUDA_CHECK(cudaGraphLaunch(s->graphExec, s->stream));
             s->launches += perStep * G;
             done += G;
@@ -1624,6 +1661,19 @@ int ws_get_wavefield(ws_solver *s, const char *comp, float *host, size_t n)
             WsParams P = s->P;
             P.ylo = 0;
             P.yhi = s->nyl;
+            if (s->d.nranks > 1) {
+                // the y derivatives read ghost planes: those of the last exchange predate the ABS damping and the source
+                // injection of the step, so they are refreshed (collective: every rank takes the snapshot)
+                int fA[3];
+                firstHalfFields(s, fA);
+                std::vector<float *> v;
+                for (int k = 0; k < 3; k++)
+                    if (fA[k] >= 0)
+                        v.push_back(s->fld[fA[k]].p);
+                WS_CUDA_CHECK(cudaStreamSynchronize(s->commStream));
+                exchangeHalos(s, v, s->h, s->stream);
+                WS_CUDA_CHECK(cudaStreamSynchronize(s->stream));
+            }
             wsLaunchDivCurl(P, tmp.p, name == "DIV" ? 1 : 0, s->stream);
             s->launches++;
             downloadLocal(s, tmp.p, host);
@@ -1680,6 +1730,28 @@ int ws_is_finite(ws_solver *s, int32_t *flag)
                     bad = 1;
                     break;
                 }
+        }
+        if (s->d.nranks > 1 && !s->ncclComm) {
+            // bring-your-own transport: the flag travels along the chain of slabs, nranks - 1 sweeps make it global
+            WS_REQUIRE(s->extFn, WS_ESTATE, "multi-rank solver used before ws_comm_init");
+            DevBuf<float> fl;
+            fl.alloc(2);
+            float mine = bad ? 1.0f : 0.0f;
+            const int up = s->d.rank - 1, down = s->d.rank + 1;
+            for (int sweep = 0; sweep < s->d.nranks - 1; sweep++) {
+                float got[2] = {0.0f, 0.0f};
+                WS_CUDA_CHECK(cudaMemcpy(fl.p, &mine, sizeof(float), cudaMemcpyHostToDevice));
+                if (up >= 0) {
+                    WS_REQUIRE(s->extFn(s->extUser, fl.p, fl.p + 1, 1, up) == 0, WS_ECOMM, "external transport failed");
+                    WS_CUDA_CHECK(cudaMemcpy(&got[0], fl.p + 1, sizeof(float), cudaMemcpyDeviceToHost));
+                }
+                if (down < s->d.nranks) {
+                    WS_REQUIRE(s->extFn(s->extUser, fl.p, fl.p + 1, 1, down) == 0, WS_ECOMM, "external transport failed");
+                    WS_CUDA_CHECK(cudaMemcpy(&got[1], fl.p + 1, sizeof(float), cudaMemcpyDeviceToHost));
+                }
+                mine = std::max(mine, std::max(got[0], got[1]));
+            }
+            bad = mine != 0.0f;
         }
         if (s->d.nranks > 1 && s->ncclComm) { // commShot->all(...)
             WS_CUDA_CHECK(cudaMemcpyAsync(s->flag.p, &bad, sizeof(int), cudaMemcpyHostToDevice, s->stream));

@@ -21,6 +21,11 @@
 #endif
 #include "../../include/wavesim.h"
 
+// Launch geometry of the per-point kernels: CUDA caps gridDim.z at 65535, so a plane range longer than that is cut into
+// chunks of WS_ZCHUNK planes that ride on gridDim.y next to the z blocks (gridDim.y = z blocks x chunks).
+#define WS_ZCHUNK 65535
+#define WS_POINT_Z(nz) ((int)((blockIdx.y % (((nz) + blockDim.y - 1) / blockDim.y)) * blockDim.y + threadIdx.y))
+#define WS_POINT_PLANE(nz) ((int)((blockIdx.y / (((nz) + blockDim.y - 1) / blockDim.y)) * WS_ZCHUNK + blockIdx.z))
 #define WS_HALO 6  /* max spatialFDorder / 2 (orders 2..12, Derivatives.cpp:2001-2042) */
 #define WS_PADX 32 /* floats left of x = 0: one 128-byte line */
 #define WS_MAXQ 12
@@ -231,6 +236,14 @@ __host__ __device__ __forceinline__ int wsCpmlIndex(int pos, int n, int W)
     if (pos >= n - W)
         return W + (pos - (n - W));
     return -1;
+}
+
+// grid of a per-point launch over planes [ylo, yhi) (see WS_POINT_Z / WS_POINT_PLANE)
+inline void wsPointGrid(int nx, int nz, int planes, dim3 &grid, dim3 &block)
+{
+    block = nz > 1 ? dim3(64, 4, 1) : dim3(128, 1, 1);
+    const unsigned nbz = (nz + block.y - 1) / block.y, nch = planes > 0 ? (planes + WS_ZCHUNK - 1) / WS_ZCHUNK : 0;
+    grid = dim3((nx + block.x - 1) / block.x, nbz * (nch ? nch : 1), planes > WS_ZCHUNK ? WS_ZCHUNK : (planes > 0 ? planes : 0));
 }
 
 // entry of grid column x (inside an x layer) in a row of the x-term slabs

@@ -753,23 +753,21 @@ template <int Q> size_t smemBytes(int pass, bool cpmlEdge, int PX)
     return ((size_t)(pass == 0 ? NSTV : NSTS) * stage + (pass == 1 ? 6 * Cfg<Q>::N_P : 0)) * 4;
 }
 
-template <int Q> void setAttrs()
+template <int Q> bool setAttrs()
 {
-    static bool done = false;
-    if (done)
-        return;
-    cudaFuncSetAttribute(kFastVel<Q, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
-    cudaFuncSetAttribute(kFastVel<Q, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
-    cudaFuncSetAttribute(kFastVel<Q, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
-    cudaFuncSetAttribute(kFastStress<Q, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
-    cudaFuncSetAttribute(kFastStress<Q, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
-    cudaFuncSetAttribute(kFastStress<Q, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
-    done = true;
+    const void *ks[6] = {reinterpret_cast<const void *>(kFastVel<Q, true, true>),     reinterpret_cast<const void *>(kFastVel<Q, true, false>),
+                         reinterpret_cast<const void *>(kFastVel<Q, false, false>),   reinterpret_cast<const void *>(kFastStress<Q, true, true>),
+                         reinterpret_cast<const void *>(kFastStress<Q, true, false>), reinterpret_cast<const void *>(kFastStress<Q, false, false>)};
+    for (const void *k : ks)
+        if (wsOptInSmem(k, kMaxDynSmem) != cudaSuccess)
+            return false;
+    return true;
 }
 
 template <int Q> int launchQ(const WsParams &P, int pass, cudaStream_t st)
 {
-    setAttrs<Q>();
+    if (!setAttrs<Q>())
+        return 0;
     int launched = 0;
     const int ny = P.yhi - P.ylo;
     const bool cpml = P.damping == 2;

@@ -43,11 +43,7 @@ void launch2(const WsParams &P, bool exact, int pass, dim3 grid, dim3 block, cud
 
 void wsGeneralGrid(const WsParams &P, dim3 &grid, dim3 &block)
 {
-    if (P.nz > 1)
-        block = dim3(64, 4, 1);
-    else
-        block = dim3(128, 1, 1);
-    grid = dim3((P.nx + block.x - 1) / block.x, (P.nz + block.y - 1) / block.y, P.yhi - P.ylo);
+    wsPointGrid(P.nx, P.nz, P.yhi - P.ylo, grid, block);
 }
 
 void wsLaunchGeneral(const WsParams &P, bool exact, int pass, cudaStream_t st)

@@ -572,8 +572,8 @@ template <int EQ, int DIM, bool EXACT, int PASS>
 __global__ void __launch_bounds__(256) kGeneral(const __grid_constant__ WsParams P)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int z = blockIdx.y * blockDim.y + threadIdx.y;
-    const int ly = P.ylo + blockIdx.z;
+    const int z = WS_POINT_Z(P.nz);
+    const int ly = P.ylo + WS_POINT_PLANE(P.nz);
     if (x >= P.nx || z >= P.nz || ly >= P.yhi)
         return;
     Pt<EXACT> t(P, x, ly, z);
@@ -589,8 +589,8 @@ template <bool EXACT>
 __global__ void __launch_bounds__(256) kAbsFirstHalf(const __grid_constant__ WsParams P, int f0, int f1, int f2)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int z = blockIdx.y * blockDim.y + threadIdx.y;
-    const int ly = P.ylo + blockIdx.z;
+    const int z = WS_POINT_Z(P.nz);
+    const int ly = P.ylo + WS_POINT_PLANE(P.nz);
     if (x >= P.nx || z >= P.nz || ly >= P.yhi)
         return;
     Pt<EXACT> t(P, x, ly, z);
@@ -616,8 +616,8 @@ __global__ void __launch_bounds__(256) kDivCurl(const __grid_constant__ WsParams
     using A = Ar<true>;
     constexpr int FX = EM ? F_HX : F_VX, FY = EM ? F_HY : F_VY, FZ = EM ? F_HZ : F_VZ;
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int z = blockIdx.y * blockDim.y + threadIdx.y;
-    const int ly = P.ylo + blockIdx.z;
+    const int z = WS_POINT_Z(P.nz);
+    const int ly = P.ylo + WS_POINT_PLANE(P.nz);
     if (x >= P.nx || z >= P.nz || ly >= P.yhi)
         return;
     Pt<true> t(P, x, ly, z);

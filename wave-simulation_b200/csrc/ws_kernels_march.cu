@@ -20,11 +20,8 @@ template <int EQ, int DIM, int Q, int PASS, int NST, int NL> void launchK(const 
     using G = wsmarch::Geo<DIM, Q, NL>;
     auto k = wsmarch::kMarch<EQ, DIM, Q, PASS, NST, NL>;
 #ifndef WS_EMULATE
-    static bool attr = false; // per instantiation
-    if (!attr) {
-        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
-        attr = true;
-    }
+    if (wsOptInSmem(reinterpret_cast<const void *>(k), 227 * 1024 - 1024) != cudaSuccess)
+        return; // the error stays pending: ws_step / ws_run report it through cudaGetLastError
 #endif
     const int ny = P.yhi - P.ylo;
     const dim3 grid((P.nx + G::TX - 1) / G::TX, (P.nz + G::TZ - 1) / G::TZ, (ny + P.marchChunk - 1) / P.marchChunk);

@@ -21,3 +21,27 @@ int wsLaunchFast(const WsParams &P, int pass, cudaStream_t st); // number of ker
 bool wsMarchSupported(const WsParams &P, bool exact);
 void wsMarchPrepare(WsParams &P); // fills P.marchChunk
 int wsLaunchMarch(const WsParams &P, int pass, cudaStream_t st); // number of kernels launched (0 = not served)
+
+#ifndef WS_EMULATE
+#include <mutex>
+#include <set>
+#include <utility>
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a property of (kernel, device): one process may drive several GPUs
+// (host/Simulation.cpp runs one thread per shot domain), so the opt-in is remembered per device, under a lock.
+inline cudaError_t wsOptInSmem(const void *kernel, int bytes)
+{
+    static std::mutex m;
+    static std::set<std::pair<const void *, int>> done;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess)
+        return e;
+    std::lock_guard<std::mutex> lock(m);
+    if (done.count({kernel, dev}))
+        return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess)
+        done.insert({kernel, dev});
+    return e;
+}
+#endif

@@ -17,8 +17,8 @@ struct Geo {
 
 #define WSPREP_POINT                                                                                                   \
     const int x = blockIdx.x * blockDim.x + threadIdx.x;                                                               \
-    const int z = blockIdx.y * blockDim.y + threadIdx.y;                                                               \
-    const int ly = g.ylo + blockIdx.z;                                                                                 \
+    const int z = WS_POINT_Z(g.nz);                                                                                    \
+    const int ly = g.ylo + WS_POINT_PLANE(g.nz);                                                                       \
     if (x >= g.nx || z >= g.nz || ly >= g.yhi)                                                                         \
         return;                                                                                                        \
     const int gy = g.gy0 + ly;                                                                                         \
@@ -231,8 +231,8 @@ __global__ void kEmCoefficients(Geo g, const float *__restrict__ eps, const floa
 __global__ void kPack(Geo g, const float *__restrict__ dense, float *__restrict__ padded, int denseY0 /* local y of dense plane 0 */)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int z = blockIdx.y * blockDim.y + threadIdx.y;
-    const int ly = g.ylo + blockIdx.z;
+    const int z = WS_POINT_Z(g.nz);
+    const int ly = g.ylo + WS_POINT_PLANE(g.nz);
     if (x >= g.nx || z >= g.nz || ly >= g.yhi)
         return;
     padded[g.idx(x, ly, z)] = dense[((long long)(ly - denseY0) * g.nz + z) * g.nx + x];
@@ -240,8 +240,8 @@ __global__ void kPack(Geo g, const float *__restrict__ dense, float *__restrict_
 __global__ void kUnpack(Geo g, const float *__restrict__ padded, float *__restrict__ dense)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int z = blockIdx.y * blockDim.y + threadIdx.y;
-    const int ly = g.ylo + blockIdx.z;
+    const int z = WS_POINT_Z(g.nz);
+    const int ly = g.ylo + WS_POINT_PLANE(g.nz);
     if (x >= g.nx || z >= g.nz || ly >= g.yhi)
         return;
     dense[((long long)(ly - g.ylo) * g.nz + z) * g.nx + x] = padded[g.idx(x, ly, z)];

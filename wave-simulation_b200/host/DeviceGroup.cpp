@@ -1,0 +1,165 @@
+#include "DeviceGroup.hpp"
+#include <cstring>
+
+using namespace KITGPI;
+
+namespace
+{
+    void check(int rc)
+    {
+        if (rc != WS_OK)
+            COMMON_THROWEXCEPTION(ws_last_error())
+    }
+}
+
+ForwardSolver::DeviceGroup::DeviceGroup(std::vector<IndexType> const &devs) : devices(devs)
+{
+    SCAI_ASSERT_ERROR(!devices.empty(), "a shot domain needs at least one GPU")
+    handles.assign(devices.size(), nullptr);
+    y0.assign(devices.size(), 0);
+    nyl.assign(devices.size(), 0);
+    errors.assign(devices.size(), "");
+    if (devices.size() > 1)
+        for (IndexType r = 0; r < size(); r++)
+            workers.emplace_back(&DeviceGroup::workerLoop, this, r);
+}
+
+ForwardSolver::DeviceGroup::~DeviceGroup()
+{
+    destroy();
+    {
+        std::lock_guard<std::mutex> lock(m);
+        stop = true;
+    }
+    cvStart.notify_all();
+    for (auto &t : workers)
+        t.join();
+}
+
+void ForwardSolver::DeviceGroup::workerLoop(IndexType rank)
+{
+    unsigned long seen = 0;
+    for (;;) {
+        std::function<void(IndexType)> const *fn = nullptr;
+        {
+            std::unique_lock<std::mutex> lock(m);
+            cvStart.wait(lock, [&] { return stop || generation != seen; });
+            if (stop)
+                return;
+            seen = generation;
+            fn = task;
+        }
+        std::string err;
+        try {
+            (*fn)(rank);
+        } catch (std::exception const &e) {
+            err = e.what();
+            if (err.empty())
+                err = "unknown error";
+        }
+        {
+            std::lock_guard<std::mutex> lock(m);
+            errors[rank] = err;
+            if (--pending == 0)
+                cvDone.notify_all();
+        }
+    }
+}
+
+void ForwardSolver::DeviceGroup::forEach(std::function<void(IndexType)> const &fn)
+{
+    if (devices.size() == 1) {
+        fn(0);
+        return;
+    }
+    {
+        std::unique_lock<std::mutex> lock(m);
+        task = &fn;
+        pending = size();
+        generation++;
+        cvStart.notify_all();
+        cvDone.wait(lock, [&] { return pending == 0; });
+        task = nullptr;
+    }
+    for (IndexType r = 0; r < size(); r++)
+        if (!errors[r].empty())
+            COMMON_THROWEXCEPTION("GPU " << devices[r] << " (slab " << r << " of " << size() << "): " << errors[r])
+}
+
+void ForwardSolver::DeviceGroup::create(ws_desc desc)
+{
+    destroy();
+    unsigned char id[128];
+    std::memset(id, 0, sizeof(id));
+    if (size() > 1)
+        check(ws_comm_unique_id(id));
+    const IndexType nz = desc.dim == 3 ? desc.nz : 1;
+    planeSize = (size_t)desc.nx * nz;
+    nGlobal = planeSize * desc.ny;
+    forEach([&](IndexType r) {
+        ws_desc d = desc;
+        d.rank = r;
+        d.nranks = size();
+        d.device = devices[r];
+        check(ws_create(&d, &handles[r]));
+        if (size() > 1)
+            check(ws_comm_init(handles[r], id));
+        int32_t a = 0, b = 0;
+        check(ws_local_range(handles[r], &a, &b));
+        y0[r] = a;
+        nyl[r] = b;
+    });
+}
+
+void ForwardSolver::DeviceGroup::destroy()
+{
+    bool any = false;
+    for (auto h : handles)
+        any = any || h != nullptr;
+    if (!any)
+        return;
+    forEach([&](IndexType r) {
+        if (handles[r])
+            ws_destroy(handles[r]);
+        handles[r] = nullptr;
+    });
+}
+
+std::vector<float> ForwardSolver::DeviceGroup::getWavefield(std::string const &component)
+{
+    std::vector<float> out(nGlobal);
+    // "CURL" / "DIV" refresh ghost planes over the communicator: a collective call
+    forEach([&](IndexType r) { check(ws_get_wavefield(handles[r], component.c_str(), out.data() + (size_t)y0[r] * planeSize, (size_t)nyl[r] * planeSize)); });
+    return out;
+}
+
+void ForwardSolver::DeviceGroup::setWavefield(std::string const &component, std::vector<float> const &values)
+{
+    SCAI_ASSERT_ERROR(values.size() == nGlobal, "wavefield vector must hold NX*NY*NZ values")
+    forEach([&](IndexType r) { check(ws_set_wavefield(handles[r], component.c_str(), values.data() + (size_t)y0[r] * planeSize, (size_t)nyl[r] * planeSize)); });
+}
+
+std::vector<float> ForwardSolver::DeviceGroup::getMaterial(std::string const &name)
+{
+    std::vector<float> out(nGlobal);
+    forEach([&](IndexType r) { check(ws_get_material(handles[r], name.c_str(), out.data() + (size_t)y0[r] * planeSize, (size_t)nyl[r] * planeSize)); });
+    return out;
+}
+
+void ForwardSolver::DeviceGroup::getSeismogram(std::vector<float> &all)
+{
+    // rows of receivers that live on another slab are left untouched by ws_get_seismogram, so the ranks fill one buffer in turn
+    std::fill(all.begin(), all.end(), 0.0f);
+    for (IndexType r = 0; r < size(); r++)
+        check(ws_get_seismogram(handles[r], all.data()));
+}
+
+bool ForwardSolver::DeviceGroup::isFinite()
+{
+    std::vector<int32_t> flags(size(), 0);
+    forEach([&](IndexType r) { check(ws_is_finite(handles[r], &flags[r])); }); // all-reduced inside the library
+    bool ok = true;
+    for (auto f : flags)
+        ok = ok && f != 0;
+    return ok;
+}

@@ -1,0 +1,62 @@
+// DeviceGroup.hpp — the GPUs of one shot domain.  Replaces the role of the reference's commShot / dist pair
+// (src/Simulation.cpp:116-149, src/Partitioning/Partitioning.hpp:43-81): the grid of a shot domain is cut into y-slabs, one
+// per GPU (ws_desc.rank / nranks), and the slabs exchange halo planes over NCCL inside the CUDA library.  Every rank is
+// driven by its own persistent host thread (NCCL needs the ranks of a communicator to call concurrently); forEach()
+// is the fork-join the host classes use for every collective call.  With one GPU the calls run inline on the caller's
+// thread.  Vectors that cross this interface are GLOBAL vectors in the reference's linear-index order (y slowest), so
+// a rank's slab is the contiguous range [y0, y0 + nyl) * NX * NZ.
+#pragma once
+#include "Common.hpp"
+#include "../../include/wavesim.h"
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
+
+namespace KITGPI
+{
+    namespace ForwardSolver
+    {
+        class DeviceGroup
+        {
+          public:
+            explicit DeviceGroup(std::vector<IndexType> const &devices);
+            ~DeviceGroup();
+            DeviceGroup(DeviceGroup const &) = delete;
+            DeviceGroup &operator=(DeviceGroup const &) = delete;
+
+            IndexType size() const { return (IndexType)devices.size(); }
+            ws_solver *handle(IndexType rank = 0) const { return handles[rank]; }
+            //! runs fn(rank) for every rank concurrently and rethrows the first failure as KITGPI::Exception
+            void forEach(std::function<void(IndexType)> const &fn);
+            //! ws_create for every rank of the group (desc.rank / nranks / device are filled in) + NCCL communicator
+            void create(ws_desc desc);
+            void destroy();
+
+            size_t getNGlobal() const { return nGlobal; }
+            //! wavefield component / derived model parameter as a global vector (every rank contributes its slab)
+            std::vector<float> getWavefield(std::string const &component);
+            void setWavefield(std::string const &component, std::vector<float> const &values);
+            std::vector<float> getMaterial(std::string const &name);
+            //! seismogram rows of all receivers (n_rec x NT): every receiver is recorded by the rank that owns its grid point
+            void getSeismogram(std::vector<float> &all);
+            bool isFinite();
+
+          private:
+            void workerLoop(IndexType rank);
+            std::vector<IndexType> devices;
+            std::vector<ws_solver *> handles;
+            std::vector<IndexType> y0, nyl;
+            size_t nGlobal = 0, planeSize = 0;
+            // fork-join over the rank threads
+            std::vector<std::thread> workers;
+            std::mutex m;
+            std::condition_variable cvStart, cvDone;
+            std::function<void(IndexType)> const *task = nullptr;
+            unsigned long generation = 0;
+            IndexType pending = 0;
+            bool stop = false;
+            std::vector<std::string> errors;
+        };
+    }
+}

@@ -64,16 +64,13 @@ template <typename ValueType> ForwardSolver::ForwardSolver<ValueType>::ForwardSo
         COMMON_THROWEXCEPTION("Unkown type")
 }
 
-template <typename ValueType> ForwardSolver::ForwardSolver<ValueType>::~ForwardSolver()
-{
-    if (h)
-        ws_destroy(h);
-}
+template <typename ValueType> ForwardSolver::ForwardSolver<ValueType>::~ForwardSolver() {}
 
 template <typename ValueType>
 ValueType ForwardSolver::ForwardSolver<ValueType>::estimateMemory(Configuration::Configuration const &config, Acquisition::Coordinates<ValueType> const &)
 {
-    ws_desc d = makeDesc(config, dimension, equationType, deviceId);
+    ws_desc d = makeDesc(config, dimension, equationType, deviceIds[0]);
+    d.nranks = (int32_t)deviceIds.size(); // memory of the first slab (the largest one)
     return (ValueType)(ws_estimate_memory(&d) / 1024.0 / 1024.0);
 }
 
@@ -84,33 +81,31 @@ void ForwardSolver::ForwardSolver<ValueType>::initForwardSolver(Configuration::C
 {
     SCAI_ASSERT_ERROR(derivatives.getSpatialFDorder() == config.get<IndexType>("spatialFDorder"), "Derivatives::init must be called with the same configuration")
     SCAI_ASSERT_ERROR(model.getEquationType() == equationType && wavefield.getEquationType() == equationType, "model / wavefield type differs from the solver type")
-    if (h) {
-        ws_destroy(h);
-        h = nullptr;
-    }
-    ws_desc d = makeDesc(config, dimension, equationType, deviceId);
+    group.reset(new DeviceGroup(deviceIds));
+    ws_desc d = makeDesc(config, dimension, equationType, deviceIds[0]);
     d.dt = DT;
-    check(ws_create(&d, &h));
+    group->create(d);
     NT = d.nt;
-    nLocal = (size_t)modelCoordinates.getNGridpoints();
+    SCAI_ASSERT_ERROR(group->getNGlobal() == (size_t)modelCoordinates.getNGridpoints(), "grid of the configuration and of the coordinates differ")
+    // every rank receives the GLOBAL vectors and keeps its slab plus the ghost planes the averaging needs
     for (auto const &kv : model.getRawParameters())
-        check(ws_set_material(h, kv.first.c_str(), kv.second.data(), kv.second.size()));
+        group->forEach([&](IndexType r) { check(ws_set_material(group->handle(r), kv.first.c_str(), kv.second.data(), kv.second.size())); });
     wavefield.init(d.n_relax);
-    wavefield.bind(h, nLocal);
-    model.bind(h, nLocal);
+    wavefield.bind(group.get());
+    model.bind(group.get());
     srcVersion = recVersion = ~0ul;
 }
 
 template <typename ValueType> void ForwardSolver::ForwardSolver<ValueType>::prepareForModelling(Modelparameter::Modelparameter<ValueType> const &, ValueType)
 {
-    SCAI_ASSERT_ERROR(h, "initForwardSolver must be called before prepareForModelling")
-    check(ws_prepare(h));
+    SCAI_ASSERT_ERROR(group, "initForwardSolver must be called before prepareForModelling")
+    group->forEach([&](IndexType r) { check(ws_prepare(group->handle(r))); });
 }
 
 template <typename ValueType> void ForwardSolver::ForwardSolver<ValueType>::resetCPML()
 {
-    SCAI_ASSERT_ERROR(h, "initForwardSolver must be called first")
-    check(ws_reset(h)); // memory variables (and wavefields, traces: both are re-initialised per shot anyway)
+    SCAI_ASSERT_ERROR(group, "initForwardSolver must be called first")
+    group->forEach([&](IndexType r) { check(ws_reset(group->handle(r))); }); // memory variables (and wavefields, traces: both are re-initialised per shot anyway)
 }
 
 template <typename ValueType>
@@ -125,12 +120,14 @@ void ForwardSolver::ForwardSolver<ValueType>::bindAcquisition(Acquisition::Recei
             SCAI_ASSERT_ERROR(sg.getNumSamples() == NT, "source signals must hold NT samples")
             std::memcpy(&signals[k * NT], &sg.getData()[(size_t)sources.getRowOfEntry((IndexType)k) * NT], sizeof(ValueType) * NT);
         }
-        check(ws_set_sources(h, (int32_t)types.size(), types.data(), idx.data(), signals.data()));
+        group->forEach([&](IndexType r) { check(ws_set_sources(group->handle(r), (int32_t)types.size(), types.data(), idx.data(), signals.data())); });
         srcObj = &sources;
         srcVersion = sources.getVersion();
     }
     if (recObj != &receiver || recVersion != receiver.getVersion()) {
-        check(ws_set_receivers(h, (int32_t)receiver.getSeismogramTypes().size(), receiver.getSeismogramTypes().data(), receiver.get1DCoordinates().data()));
+        group->forEach([&](IndexType r) {
+            check(ws_set_receivers(group->handle(r), (int32_t)receiver.getSeismogramTypes().size(), receiver.getSeismogramTypes().data(), receiver.get1DCoordinates().data()));
+        });
         recObj = &receiver;
         recVersion = receiver.getVersion();
     }
@@ -140,7 +137,7 @@ template <typename ValueType> void ForwardSolver::ForwardSolver<ValueType>::fetc
 {
     auto const &types = receiver.getSeismogramTypes();
     std::vector<ValueType> all((size_t)types.size() * NT);
-    check(ws_get_seismogram(h, all.data()));
+    group->getSeismogram(all);
     for (size_t k = 0; k < types.size(); k++) {
         auto &sg = receiver.getSeismogramHandler().getSeismogram(types[k] - 1);
         std::memcpy(&sg.getData()[(size_t)receiver.getRowOfEntry((IndexType)k) * NT], &all[k * NT], sizeof(ValueType) * NT);
@@ -152,9 +149,9 @@ void ForwardSolver::ForwardSolver<ValueType>::run(Acquisition::Receivers<ValueTy
                                                   Modelparameter::Modelparameter<ValueType> const &, Wavefields::Wavefields<ValueType> &,
                                                   Derivatives::Derivatives<ValueType> const &, IndexType t)
 {
-    SCAI_ASSERT_ERROR(h, "initForwardSolver must be called before run")
+    SCAI_ASSERT_ERROR(group, "initForwardSolver must be called before run")
     bindAcquisition(receiver, sources);
-    check(ws_step(h, t));
+    group->forEach([&](IndexType r) { check(ws_step(group->handle(r), t)); });
     if (t == NT - 1)
         fetchSeismograms(receiver);
 }
@@ -162,17 +159,17 @@ void ForwardSolver::ForwardSolver<ValueType>::run(Acquisition::Receivers<ValueTy
 template <typename ValueType>
 void ForwardSolver::ForwardSolver<ValueType>::run(Acquisition::Receivers<ValueType> &receiver, Acquisition::Sources<ValueType> const &sources, IndexType t0, IndexType t1)
 {
-    SCAI_ASSERT_ERROR(h, "initForwardSolver must be called before run")
+    SCAI_ASSERT_ERROR(group, "initForwardSolver must be called before run")
     bindAcquisition(receiver, sources);
-    check(ws_run(h, t0, t1));
+    group->forEach([&](IndexType r) { check(ws_run(group->handle(r), t0, t1)); });
     if (t1 == NT)
         fetchSeismograms(receiver);
 }
 
 template <typename ValueType> void ForwardSolver::ForwardSolver<ValueType>::sync()
 {
-    if (h)
-        check(ws_sync(h));
+    if (group)
+        group->forEach([&](IndexType r) { check(ws_sync(group->handle(r))); });
 }
 
 template <typename ValueType> typename ForwardSolver::ForwardSolver<ValueType>::ForwardSolverPtr ForwardSolver::Factory<ValueType>::Create(std::string dimension, std::string type)

@@ -9,6 +9,7 @@
 #include "Configuration.hpp"
 #include "Coordinates.hpp"
 #include "Derivatives.hpp"
+#include "DeviceGroup.hpp"
 #include "Modelparameter.hpp"
 #include "Wavefields.hpp"
 
@@ -27,8 +28,12 @@ namespace KITGPI
             ForwardSolver(ForwardSolver const &) = delete;
             ForwardSolver &operator=(ForwardSolver const &) = delete;
 
-            //! CUDA device used by this solver (one solver per shot domain / GPU); call before initForwardSolver
-            void setDevice(IndexType device) { deviceId = device; }
+            //! CUDA device used by this solver (one solver per shot domain); call before initForwardSolver
+            void setDevice(IndexType device) { deviceIds.assign(1, device); }
+            //! several GPUs for one shot domain: the grid is cut into y-slabs, one per device (replaces the reference's
+            //! spatial Partitioning over the processes of commShot, Simulation.cpp:126-149)
+            void setDevices(std::vector<IndexType> const &devices) { deviceIds = devices; }
+            std::vector<IndexType> const &getDevices() const { return deviceIds; }
 
             //! memory in MB the solver will allocate in HBM (wavefields, model, CPML slabs): estimateMemory of the reference
             ValueType estimateMemory(Configuration::Configuration const &config, Acquisition::Coordinates<ValueType> const &modelCoordinates);
@@ -50,16 +55,17 @@ namespace KITGPI
             void run(Acquisition::Receivers<ValueType> &receiver, Acquisition::Sources<ValueType> const &sources, IndexType t0, IndexType t1);
             void sync();
 
-            ws_solver *handle() const { return h; }
+            ws_solver *handle() const { return group ? group->handle(0) : nullptr; }
+            DeviceGroup *getGroup() const { return group.get(); }
             IndexType getNT() const { return NT; }
 
           private:
             void bindAcquisition(Acquisition::Receivers<ValueType> &receiver, Acquisition::Sources<ValueType> const &sources);
             void fetchSeismograms(Acquisition::Receivers<ValueType> &receiver);
             std::string dimension, equationType;
-            ws_solver *h = nullptr;
-            IndexType deviceId = 0, NT = 0;
-            size_t nLocal = 0;
+            std::unique_ptr<DeviceGroup> group;
+            std::vector<IndexType> deviceIds{0};
+            IndexType NT = 0;
             unsigned long srcVersion = ~0ul, recVersion = ~0ul;
             const void *srcObj = nullptr, *recObj = nullptr;
         };

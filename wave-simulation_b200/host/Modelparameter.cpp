@@ -1,5 +1,5 @@
 #include "Modelparameter.hpp"
-#include "../../include/wavesim.h"
+#include "DeviceGroup.hpp"
 #include "IO.hpp"
 #include <algorithm>
 
@@ -97,10 +97,7 @@ template <typename ValueType> std::vector<ValueType> const &Modelparameter::Mode
 template <typename ValueType> std::vector<ValueType> Modelparameter::Modelparameter<ValueType>::getParameter(std::string const &name) const
 {
     SCAI_ASSERT_ERROR(h, "The model is not bound to a forward solver yet (initForwardSolver)")
-    std::vector<ValueType> out(n);
-    if (ws_get_material(h, name.c_str(), out.data(), out.size()) != WS_OK)
-        COMMON_THROWEXCEPTION(ws_last_error())
-    return out;
+    return h->getMaterial(name);
 }
 
 template <typename ValueType> ValueType Modelparameter::Modelparameter<ValueType>::getMaxVelocity() const

@@ -11,7 +11,7 @@
 #include <map>
 #include <memory>
 
-struct ws_solver;
+namespace KITGPI { namespace ForwardSolver { class DeviceGroup; } }
 
 namespace KITGPI
 {
@@ -50,7 +50,7 @@ namespace KITGPI
             ValueType getMaxVelocity() const;
             ValueType getMinVelocity() const;
 
-            void bind(ws_solver *handle, size_t nLocal) { h = handle; n = nLocal; }
+            void bind(ForwardSolver::DeviceGroup *group) { h = group; }
 
             static constexpr ValueType MagneticPermeabilityVacuum = 1.2566370614e-6f;    // Modelparameter.hpp:359
             static constexpr ValueType DielectricPermittivityVacuum = 8.8541878176e-12f; // Modelparameter.hpp:360
@@ -62,8 +62,7 @@ namespace KITGPI
             bool dirtyFlag = true;
             std::map<std::string, std::vector<ValueType>> raw;
             std::vector<ValueType> relaxationFrequency;
-            ws_solver *h = nullptr;
-            size_t n = 0;
+            ForwardSolver::DeviceGroup *h = nullptr;
         };
 
         template <typename ValueType> class Factory

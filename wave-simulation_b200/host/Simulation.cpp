@@ -1,7 +1,9 @@
 // Simulation.cpp — forward-modelling driver with the flow of the reference's src/Simulation.cpp:36-574:
 // configuration -> factories -> acquisition -> model -> forward solver -> loop over shots -> loop over time steps ->
-// seismograms.  Runs the `par/` configurations unchanged on the CUDA library (include/wavesim.h); NumShotDomains maps
-// to GPUs: every shot domain is one GPU working on its block of the shots (Simulation.cpp:116-121, 369).
+// seismograms.  Runs the `par/` configurations unchanged on the CUDA library (include/wavesim.h).  The GPUs of the box
+// take the place of the reference's MPI processes: they are split into NumShotDomains groups (Simulation.cpp:116-121),
+// every group works on its block of the shots (:369) and cuts the grid into y-slabs over its GPUs (the reference's
+// spatial partitioning over commShot, :126-149; the `partitioning` key is accepted and always means y-slabs here).
 #include "Acquisition.hpp"
 #include "CheckParameter.hpp"
 #include "Configuration.hpp"
@@ -27,7 +29,7 @@ namespace
 }
 
 // one shot domain = one GPU: shots [lb, ub) of the unique shot list (dmemo::blockDistribution(numshots, commInterShot))
-static void runShotDomain(Configuration::Configuration const &config, IndexType shotDomain, IndexType device, IndexType lb, IndexType ub,
+static void runShotDomain(Configuration::Configuration const &config, IndexType shotDomain, std::vector<IndexType> devices, IndexType lb, IndexType ub,
                           std::vector<Acquisition::sourceSettings<ValueType>> const &sourceSettings, std::vector<IndexType> const &uniqueShotNos,
                           Modelparameter::Modelparameter<ValueType>::ModelparameterPtr model, Acquisition::Coordinates<ValueType> const &modelCoordinates, double globalStart_t,
                           std::string *error)
@@ -43,7 +45,7 @@ static void runShotDomain(Configuration::Configuration const &config, IndexType 
         auto derivatives = ForwardSolver::Derivatives::Factory<ValueType>::Create(dimension);
         auto wavefields = Wavefields::Factory<ValueType>::Create(dimension, equationType);
         auto solver = ForwardSolver::Factory<ValueType>::Create(dimension, equationType);
-        solver->setDevice(device);
+        solver->setDevices(devices);
         derivatives->init(config);
 
         // every domain works on its own copy of the model object (binding to its solver); the raw vectors are shared data
@@ -138,8 +140,10 @@ int main(int argc, const char *argv[])
         if (verbose)
             config.print();
 
-        const IndexType nDevices = ws_device_count();
+        IndexType nDevices = ws_device_count();
         SCAI_ASSERT_ERROR(nDevices > 0, "no CUDA device available (there is no CPU fallback)")
+        if (const char *e = std::getenv("WS_NUM_GPUS"))
+            nDevices = std::max<IndexType>(1, std::min<IndexType>(nDevices, std::atoi(e)));
 
         Acquisition::Coordinates<ValueType> modelCoordinates(config);
         const IndexType numRelaxationMechanisms = config.getAndCatch("numRelaxationMechanisms", 0);
@@ -168,18 +172,33 @@ int main(int argc, const char *argv[])
         model->init(config, modelCoordinates);
         HOST_PRINT("", "Finished initializing model in " << now() - start_t << " sec.\n\n")
 
-        /* shot domains: block distribution of the shots over min(NumShotDomains, GPUs) domains */
+        /* shot domains: block distribution of the shots over min(NumShotDomains, GPUs) domains; the GPUs of a domain share
+           one shot as y-slabs.  A slab should keep enough planes to hide the halo exchange behind its interior, so by
+           default a domain uses at most NY / 64 GPUs (key GPUsPerShotDomain overrides, WS_NUM_GPUS limits the box). */
         IndexType numShotDomains = std::max<IndexType>(1, config.getAndCatch("NumShotDomains", 1));
         numShotDomains = std::min(numShotDomains, std::min(numshots, nDevices));
+        IndexType gpusPerDomain = std::max<IndexType>(1, nDevices / numShotDomains);
+        {
+            const IndexType NY = config.get<IndexType>("NY");
+            const IndexType wanted = config.getAndCatch("GPUsPerShotDomain", 0);
+            if (wanted > 0)
+                gpusPerDomain = std::min(gpusPerDomain, wanted);
+            else
+                gpusPerDomain = std::min(gpusPerDomain, std::max<IndexType>(1, NY / 64));
+        }
+        HOST_PRINT(" " << numShotDomains << " shot domain(s) x " << gpusPerDomain << " GPU(s) per domain (y-slabs), " << nDevices << " GPU(s) visible\n\n")
         std::vector<std::thread> threads;
         std::vector<std::string> errors(numShotDomains);
         for (IndexType dom = 0; dom < numShotDomains; dom++) {
             const IndexType base = numshots / numShotDomains, rem = numshots % numShotDomains;
             const IndexType lb = dom * base + std::min(dom, rem), ub = lb + base + (dom < rem ? 1 : 0);
+            std::vector<IndexType> devices;
+            for (IndexType r = 0; r < gpusPerDomain; r++)
+                devices.push_back(dom * gpusPerDomain + r);
             if (numShotDomains == 1)
-                runShotDomain(config, dom, dom, lb, ub, sourceSettings, uniqueShotNos, model, modelCoordinates, globalStart_t, &errors[dom]);
+                runShotDomain(config, dom, devices, lb, ub, sourceSettings, uniqueShotNos, model, modelCoordinates, globalStart_t, &errors[dom]);
             else
-                threads.emplace_back(runShotDomain, std::cref(config), dom, dom, lb, ub, std::cref(sourceSettings), std::cref(uniqueShotNos), model, std::cref(modelCoordinates),
+                threads.emplace_back(runShotDomain, std::cref(config), dom, devices, lb, ub, std::cref(sourceSettings), std::cref(uniqueShotNos), model, std::cref(modelCoordinates),
                                      globalStart_t, &errors[dom]);
         }
         for (auto &t : threads)

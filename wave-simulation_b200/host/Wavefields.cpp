@@ -1,5 +1,5 @@
 #include "Wavefields.hpp"
-#include "../../include/wavesim.h"
+#include "DeviceGroup.hpp"
 #include "IO.hpp"
 #include <algorithm>
 
@@ -57,33 +57,28 @@ template <typename ValueType> void Wavefields::Wavefields<ValueType>::init(Index
 template <typename ValueType> void Wavefields::Wavefields<ValueType>::resetWavefields()
 {
     SCAI_ASSERT_ERROR(h, "The wavefields are not bound to a forward solver yet (initForwardSolver)")
-    if (ws_reset(h) != WS_OK)
-        COMMON_THROWEXCEPTION(ws_last_error())
+    h->forEach([&](IndexType r) {
+        if (ws_reset(h->handle(r)) != WS_OK)
+            COMMON_THROWEXCEPTION(ws_last_error())
+    });
 }
 
 template <typename ValueType> bool Wavefields::Wavefields<ValueType>::isFinite() const
 {
     SCAI_ASSERT_ERROR(h, "The wavefields are not bound to a forward solver yet (initForwardSolver)")
-    int32_t flag = 0;
-    if (ws_is_finite(h, &flag) != WS_OK)
-        COMMON_THROWEXCEPTION(ws_last_error())
-    return flag != 0;
+    return h->isFinite();
 }
 
 template <typename ValueType> std::vector<ValueType> Wavefields::Wavefields<ValueType>::get(std::string const &component) const
 {
     SCAI_ASSERT_ERROR(h, "The wavefields are not bound to a forward solver yet (initForwardSolver)")
-    std::vector<ValueType> out(n);
-    if (ws_get_wavefield(h, component.c_str(), out.data(), out.size()) != WS_OK)
-        COMMON_THROWEXCEPTION(ws_last_error())
-    return out;
+    return h->getWavefield(component);
 }
 
 template <typename ValueType> void Wavefields::Wavefields<ValueType>::set(std::string const &component, std::vector<ValueType> const &values)
 {
     SCAI_ASSERT_ERROR(h, "The wavefields are not bound to a forward solver yet (initForwardSolver)")
-    if (ws_set_wavefield(h, component.c_str(), values.data(), values.size()) != WS_OK)
-        COMMON_THROWEXCEPTION(ws_last_error())
+    h->setWavefield(component, values);
 }
 
 template <typename ValueType> void Wavefields::Wavefields<ValueType>::write(IndexType snapType, std::string baseName, IndexType t, IndexType fileFormat) const

@@ -7,7 +7,7 @@
 #include "Common.hpp"
 #include <memory>
 
-struct ws_solver;
+namespace KITGPI { namespace ForwardSolver { class DeviceGroup; } }
 
 namespace KITGPI
 {
@@ -31,14 +31,14 @@ namespace KITGPI
             std::string getEquationType() const { return equationType; }
             IndexType getNumDimension() const { return numDimension; }
 
-            void bind(ws_solver *handle, size_t nLocal) { h = handle; n = nLocal; }
+            //! the GPUs that hold the state (set by ForwardSolver::initForwardSolver)
+            void bind(ForwardSolver::DeviceGroup *group) { h = group; }
 
           private:
             std::string equationType;
             IndexType numDimension;
             std::vector<std::string> first, second, memory, all; // first half-step fields, second half-step fields, memory variables
-            ws_solver *h = nullptr;
-            size_t n = 0;
+            ForwardSolver::DeviceGroup *h = nullptr;
         };
 
         template <typename ValueType> class Factory
