@@ -66,7 +66,7 @@ typedef struct ws_desc {
     int32_t n_relax;        /* L                                      key: numRelaxationMechanisms             */
     float relax_freq[WS_MAX_RELAX]; /*                                keys: relaxationFrequency[2..4]          */
     int32_t exact_arith;    /* 1 = reference operation order, no FMA contraction (bit-parity mode); 0 = FMA    */
-    int32_t kernel_variant; /* 0 = auto (TMA kernels, else marching kernels), 1 = per-point kernels, 2 = marching kernels */
+    int32_t kernel_variant; /* 0 = auto (TMA kernels), 1 = per-point kernels, 2 = cp.async marching kernels, 3 = TMA marching kernels */
     int32_t rank, nranks;   /* y-slab decomposition of the global grid over `nranks` processes (one GPU each)  */
     int32_t device;         /* CUDA device ordinal used by this handle                                         */
 } ws_desc;
@@ -154,8 +154,8 @@ void *ws_stream(ws_solver *s); /* cudaStream_t the kernels are launched on */
 int ws_set_timing(ws_solver *s, int enable);
 /* 1 if the tiled TMA kernels (not the general per-point kernels) serve this configuration */
 int ws_uses_fast_kernels(const ws_solver *s);
-/* which kernel family serves this configuration: 0 per-point (general), 1 marching (register queue + staged planes),
- * 2 warp-specialised TMA kernels */
+/* which kernel family serves this configuration: 0 per-point (general), 1 marching (register queue + cp.async-staged
+ * planes), 2 warp-specialised TMA kernels of the 3-D elastic case, 3 warp-specialised TMA marching kernels (all solvers) */
 int ws_kernel_path(const ws_solver *s);
 
 #ifdef __cplusplus

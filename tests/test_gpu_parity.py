@@ -156,16 +156,51 @@ def test_fast_kernels_equal_general_kernels(shape):
     assert np.array_equal(res[0][0], res[1][0])
 
 
+@pytest.mark.parametrize("family", [2, 3], ids=["cpasync", "tma"])
 @pytest.mark.parametrize("cfg", SWEEP, ids=[sweep_id(c) for c in SWEEP])
-def test_marching_kernels_equal_per_point_kernels(cfg):
-    """ws_kernels_march.cuh (register queues along y, cp.async-staged planes for x / z) against the per-point kernels:
-    same statement sequence, same accumulation order => bit-identical in FMA mode, for every equation type."""
+def test_marching_kernels_equal_per_point_kernels(cfg, family):
+    """ws_kernels_march.cuh (register queues along y, cp.async-staged planes for x / z) and ws_kernels_tma.cuh (the same
+    march fed by a TMA producer through an mbarrier ring) against the per-point kernels: same statement sequence, same
+    accumulation order => bit-identical in FMA mode, for every equation type."""
     eq, dim, nx, ny, nz, q, pol, fs, damp, W, L = cfg
     res = []
-    for variant in (1, 2):
+    for variant in (1, family):
         case = make_case(eq, dim, nx, ny, nz, q, pol, fs, damp, W, L, nt=40, exact=0, kernel_variant=variant)
         s = case.setup(Solver(case.desc))
-        assert s.kernel_path() == (0 if variant == 1 else 1)
+        assert s.kernel_path() == (0 if variant == 1 else (1 if variant == 2 else 3))
+        s.run(0, 40)
+        s.sync()
+        res.append((s.seismogram(), {f: s.wavefield(f) for f in fields_of(eq, dim, L)}))
+        assert s.is_finite()
+        s.close()
+    assert np.abs(res[0][0]).max() > 0
+    assert np.array_equal(res[0][0], res[1][0])
+    for f in res[0][1]:
+        assert np.array_equal(res[0][1][f], res[1][1][f]), f
+
+
+DEFAULT_PATHS = [
+    # (cfg, expected ws_kernel_path with kernel_variant = 0)
+    (("elastic", 3, 72, 64, 24, 8, 0, 1, 2, 8, 0), 2),       # 3-D elastic TMA kernels
+    (("viscoelastic", 3, 72, 64, 24, 8, 0, 1, 2, 8, 2), 3),  # velocity half-step: 3-D elastic TMA kernel, stress half-step: TMA marching kernel
+    (("viscoelastic", 3, 70, 64, 24, 6, 1, 1, 2, 8, 1), 3),  # both half-steps on the TMA marching kernels
+    (("acoustic", 3, 100, 80, 40, 8, 0, 0, 2, 10, 0), 3),
+    (("elastic", 3, 64, 48, 40, 8, 1, 1, 2, 8, 0), 3),       # order-reducing edges (the par/ default): TMA marching kernels
+    (("viscotmem", 2, 900, 300, 1, 8, 0, 0, 2, 20, 1), None),
+    (("elastic", 2, 1000, 300, 1, 8, 0, 1, 2, 20, 0), None),
+]
+
+
+@pytest.mark.parametrize("cfg,path", DEFAULT_PATHS, ids=[sweep_id(c[0]) for c in DEFAULT_PATHS])
+def test_default_kernels_equal_per_point_kernels(cfg, path):
+    """kernel_variant = 0 (what a par/ configuration gets) against the per-point kernels: bit-identical in FMA mode."""
+    eq, dim, nx, ny, nz, q, pol, fs, damp, W, L = cfg
+    res = []
+    for variant in (1, 0):
+        case = make_case(eq, dim, nx, ny, nz, q, pol, fs, damp, W, L, nt=40, exact=0, kernel_variant=variant)
+        s = case.setup(Solver(case.desc))
+        if variant == 0:
+            assert s.kernel_path() >= 1 and (path is None or s.kernel_path() == path)
         s.run(0, 40)
         s.sync()
         res.append((s.seismogram(), {f: s.wavefield(f) for f in fields_of(eq, dim, L)}))
@@ -185,11 +220,12 @@ MARCH_SHAPES = [
 ]
 
 
+@pytest.mark.parametrize("family", [2, 3], ids=["cpasync", "tma"])
 @pytest.mark.parametrize("cfg", MARCH_SHAPES, ids=[sweep_id(c) + "-%dx%dx%d" % c[2:5] for c in MARCH_SHAPES])
-def test_marching_kernels_ragged_shapes(cfg):
+def test_marching_kernels_ragged_shapes(cfg, family):
     eq, dim, nx, ny, nz, q, pol, fs, damp, W, L = cfg
     res = []
-    for variant in (1, 2):
+    for variant in (1, family):
         case = make_case(eq, dim, nx, ny, nz, q, pol, fs, damp, W, L, nt=25, exact=0, kernel_variant=variant)
         s = case.setup(Solver(case.desc))
         s.run(0, 25)

@@ -375,7 +375,8 @@ def test_product_driver_shot_domains_on_several_gpus(tmp_path, domains):
     os.makedirs(one), os.makedirs(many)
     _run_product(_multishot_case(one, sfmt=4), one, {"WS_NUM_GPUS": "1"})
     cfg = _multishot_case(many, sfmt=4)
-    open(cfg, "w").write(open(cfg).read().replace("NumShotDomains=1", "NumShotDomains=%d" % domains))
+    text = open(cfg).read()
+    open(cfg, "w").write(text.replace("NumShotDomains=1", "NumShotDomains=%d" % domains))
     log = _run_product(cfg, many)
     assert "%d shot domain(s) x 1 GPU(s)" % domains in log
     a, b = _outputs(one), _outputs(many)
@@ -396,7 +397,8 @@ def test_product_driver_spatial_slabs_on_two_gpus(tmp_path):
     os.makedirs(one), os.makedirs(two)
     _run_product(_multishot_case(one, snap=3), one, {"WS_NUM_GPUS": "1"})
     cfg = _multishot_case(two, snap=3)
-    open(cfg, "w").write(open(cfg).read() + "GPUsPerShotDomain=2\npartitioning=0\n")
+    text = open(cfg).read()
+    open(cfg, "w").write(text + "GPUsPerShotDomain=2\npartitioning=0\n")
     log = _run_product(cfg, two)
     assert "1 shot domain(s) x 2 GPU(s)" in log
     a, b = _outputs(one), _outputs(two)

@@ -28,6 +28,7 @@ struct WsError : public std::exception {
 #include "ws_launch.hpp"
 #include "ws_prepare.cuh"
 #include "ws_tables.hpp"
+#include "ws_kernels_tma.cuh" // operand table (wsmarch::spec) and the TMA program type
 
 namespace {
 
@@ -284,6 +285,12 @@ struct ws_solver {
     cudaEvent_t evComputeG = nullptr, evCommG = nullptr; // the same roles inside a stream capture (a captured event cannot be waited on outside)
     bool capturing = false;
     DevBuf<float> fldArena, matArena, psiXArena, psiZArena; // declared first: the slots below borrow from them
+    DevBuf<float> arena; // every other solver: wavefields, then the model parameters the kernels read (TMA marching kernels)
+    WsArenaInfo ainfo;
+    wstma::TmaProg tmaProg[2];
+    int tmaNL[2] = {4, 4};
+    void *tmaMaps = nullptr;
+    bool useTma = false; // TMA marching kernels (ws_kernels_tma.cu) serve this configuration
     DevBuf<float> fld[F_COUNT], mat[M_COUNT], psi[PSI_COUNT];
     bool matGiven[M_COUNT] = {};
     int psiAxis[PSI_COUNT];
@@ -315,6 +322,7 @@ struct ws_solver {
     std::vector<cudaEvent_t> evPool;
     float msA = 0, msB = 0, msStep = 0;
     bool useFast = false;
+    bool useFastA = false; // 3-D viscoelastic: the velocity half-step runs the tiled elastic kernel (same statements)
     bool useMarch = false; // marching kernels (ws_kernels_march.cu) serve this configuration
     void *fastMaps = nullptr;
     // CUDA graph of one time step
@@ -328,6 +336,10 @@ struct ws_solver {
             cudaGraphExecDestroy(graphExec);
         if (fastMaps)
             wsFastRelease(fastMaps);
+#ifndef WS_EMULATE
+        if (tmaMaps)
+            wsTmaRelease(tmaMaps);
+#endif
         for (auto e : evPool)
             cudaEventDestroy(e);
         if (evCompute)
@@ -982,13 +994,22 @@ void launchPass(ws_solver *s, int pass, int ylo, int yhi)
     WsParams P = s->P;
     P.ylo = ylo;
     P.yhi = yhi;
-    if (s->useFast) {
+    if (s->useFast || (s->useFastA && pass == 0)) {
         const int n = wsLaunchFast(P, pass, s->stream);
         if (n > 0) {
             s->launches += n;
             return;
         }
     }
+#ifndef WS_EMULATE
+    if (s->useTma) {
+        const int n = wsLaunchTma(P, pass, s->tmaProg[pass], s->tmaNL[pass], s->stream);
+        if (n > 0) {
+            s->launches += n;
+            return;
+        }
+    }
+#endif
     if (s->useMarch) {
         const int n = wsLaunchMarch(P, pass, s->stream);
         if (n > 0) {
@@ -1190,26 +1211,72 @@ int ws_create(const ws_desc *desc, ws_solver **out)
             WS_CUDA_CHECK(cudaEventCreateWithFlags(&s->evComputeG, cudaEventDisableTiming));
             WS_CUDA_CHECK(cudaEventCreateWithFlags(&s->evCommG, cudaEventDisableTiming));
             WS_CUDA_CHECK(cudaEventRecord(s->evComm, s->commStream));
-            if (s->d.eq == WS_EQ_ELASTIC && s->d.dim == 3) {
-                // arena order of the tiled kernels (ws_kernels_fast.cu): neighbours are fetched by one TMA box
+            if ((s->d.eq == WS_EQ_ELASTIC || s->d.eq == WS_EQ_VISCOELASTIC) && s->d.dim == 3) {
+                // arena order of the tiled kernels (ws_kernels_fast.cu): neighbours are fetched by one TMA box.  The
+                // viscoelastic solver shares the velocity half-step with the elastic one, so its arrays start the same way
+                // and the memory variables / relaxation parameters follow.
                 static const int fo[9] = {F_VX, F_VY, F_VZ, F_SXX, F_SXY, F_SYY, F_SYZ, F_SZZ, F_SXZ};
-                static const int mo[8] = {M_RIX, M_RIY, M_RIZ, M_PW, M_MU, M_MUXY, M_MUXZ, M_MUYZ};
-                s->fldArena.alloc((size_t)s->total * 9);
+                static const int mo[13] = {M_RIX, M_RIY, M_RIZ, M_PW, M_MU, M_MUXY, M_MUXZ, M_MUYZ, M_TAUP, M_TAUS, M_TSXY, M_TSXZ, M_TSYZ};
+                const int nf = 9 + 6 * s->L, nm = s->visco ? 13 : 8;
+                s->fldArena.alloc((size_t)s->total * nf);
                 s->fldArena.zero(s->stream);
-                for (int k = 0; k < 9; k++)
-                    s->fld[fo[k]].borrow(s->fldArena.p + (size_t)k * s->total, (size_t)s->total);
-                s->matArena.alloc((size_t)s->total * 8);
+                s->matArena.alloc((size_t)s->total * nm);
                 s->matArena.zero(s->stream);
-                for (int k = 0; k < 8; k++)
+                for (int k = 0; k < F_COUNT; k++) { s->ainfo.fldPos[k] = -1; s->ainfo.fldArena[k] = 0; }
+                for (int k = 0; k < M_COUNT; k++) { s->ainfo.matPos[k] = -1; s->ainfo.matArena[k] = 1; }
+                for (int k = 0; k < nf; k++) {
+                    const int slot = k < 9 ? fo[k] : F_R0 + (k - 9); // memory variables: [mechanism][xx yy zz xy xz yz]
+                    s->fld[slot].borrow(s->fldArena.p + (size_t)k * s->total, (size_t)s->total);
+                    s->ainfo.fldPos[slot] = (short)k;
+                }
+                for (int k = 0; k < nm; k++) {
                     s->mat[mo[k]].borrow(s->matArena.p + (size_t)k * s->total, (size_t)s->total);
+                    s->ainfo.matPos[mo[k]] = (short)k;
+                }
                 for (auto &kv : fieldsFor(s->d).f)
                     s->fldSlot[kv.first] = kv.second;
+                s->ainfo.base[0] = s->fldArena.p; s->ainfo.base[1] = s->matArena.p;
+                s->ainfo.count[0] = nf; s->ainfo.count[1] = nm;
+                s->ainfo.stride = s->total;
             } else {
-                for (auto &kv : fieldsFor(s->d).f) {
-                    s->fld[kv.second].alloc((size_t)s->total);
-                    s->fld[kv.second].zero(s->stream);
-                    s->fldSlot[kv.first] = kv.second;
+                // one arena: the wavefields and the model parameters the half-steps read, in the order of the operand table
+                // (ws_kernels_march.cuh spec), second half-step first: arrays that one TMA box can fetch together are neighbours
+                std::vector<int> fo, mo;
+                auto addU = [](std::vector<int> &v, int x) { if (std::find(v.begin(), v.end(), x) == v.end()) v.push_back(x); };
+                for (int pass = 1; pass >= 0; pass--) {
+                    const wsmarch::Lists S = wsmarch::spec(s->d.eq, s->d.dim, pass);
+                    for (int k = 0; k < S.nf; k++) addU(fo, S.f[k]);
+                    for (int k = 0; k < S.nt; k++) addU(fo, S.t[k]);
+                    for (int k = 0; k < S.nq; k++) addU(fo, S.qf[k]);
+                    for (int k = 0; k < S.nm; k++) addU(mo, S.m[k]);
                 }
+                {
+                    const wsmarch::Lists S = wsmarch::spec(s->d.eq, s->d.dim, 1);
+                    for (int l = 0; l < s->L; l++)
+                        for (int k = 0; k < S.nr; k++) addU(fo, F_R0 + 6 * l + S.r[k]);
+                    for (int l = 0; l < s->L; l++)
+                        for (int k = 0; k < S.nc; k++) addU(mo, M_CD0 + 3 * l + S.c[k]);
+                }
+                for (auto &kv : fieldsFor(s->d).f)
+                    addU(fo, kv.second);
+                const size_t nf = fo.size(), nm = mo.size();
+                s->arena.alloc((size_t)s->total * (nf + nm));
+                s->arena.zero(s->stream);
+                for (int k = 0; k < F_COUNT; k++) { s->ainfo.fldPos[k] = -1; s->ainfo.fldArena[k] = 0; }
+                for (int k = 0; k < M_COUNT; k++) { s->ainfo.matPos[k] = -1; s->ainfo.matArena[k] = 0; }
+                for (size_t k = 0; k < nf; k++) {
+                    s->fld[fo[k]].borrow(s->arena.p + k * (size_t)s->total, (size_t)s->total);
+                    s->ainfo.fldPos[fo[k]] = (short)k;
+                }
+                for (size_t k = 0; k < nm; k++) {
+                    s->mat[mo[k]].borrow(s->arena.p + (nf + k) * (size_t)s->total, (size_t)s->total);
+                    s->ainfo.matPos[mo[k]] = (short)(nf + k);
+                }
+                s->ainfo.base[0] = s->arena.p;
+                s->ainfo.count[0] = (int)(nf + nm);
+                s->ainfo.stride = s->total;
+                for (auto &kv : fieldsFor(s->d).f)
+                    s->fldSlot[kv.first] = kv.second;
             }
             for (int k = 0; k < PSI_COUNT; k++)
                 s->psiAxis[k] = -1;
@@ -1323,14 +1390,31 @@ int ws_prepare(ws_solver *s)
         prepareBoundaries(s);
         refreshParams(s);
         s->useFast = s->d.kernel_variant == 0 && wsFastSupported(s->P, s->exact);
+        s->useFastA = !s->useFast && s->d.kernel_variant == 0 && wsFastSupported(s->P, s->exact, 0) && !(getenv("WS_NO_FAST_A") && atoi(getenv("WS_NO_FAST_A")));
         if (s->fastMaps) {
             wsFastRelease(s->fastMaps);
             s->fastMaps = nullptr;
         }
-        if (s->useFast)
+        if (s->useFast || s->useFastA)
             s->fastMaps = wsFastPrepare(s->P, s->nyl + 2 * WS_HALO);
-        // kernel_variant: 0 = best available (TMA kernels, else marching kernels), 1 = per-point kernels, 2 = marching kernels
-        s->useMarch = !s->useFast && (s->d.kernel_variant == 0 || s->d.kernel_variant == 2) && wsMarchSupported(s->P, s->exact);
+        // kernel_variant: 0 = best available (3-D elastic TMA kernels, else TMA marching kernels, else cp.async marching kernels),
+        // 1 = per-point kernels, 2 = cp.async marching kernels, 3 = TMA marching kernels
+#ifndef WS_EMULATE
+        if (s->tmaMaps) {
+            wsTmaRelease(s->tmaMaps);
+            s->tmaMaps = nullptr;
+        }
+        s->P.tmaMaps = nullptr;
+        // (2-D grids stay on the cp.async marching kernels by default: their strips stage 512 bytes per array and plane, and the
+        // TMA ring then holds fewer resident warps per SM than the cp.async kernels do; measured 30 against 41 Gpt/s on 2-D elastic
+        // 4096^2, profiles/r02_tma_sweep.txt)
+        s->useTma = ((!s->useFast && s->d.kernel_variant == 0 && s->d.dim == 3) || s->d.kernel_variant == 3) && wsTmaSupported(s->P, s->ainfo, s->exact);
+        if (s->useTma) {
+            s->useFast = false;
+            s->tmaMaps = wsTmaPrepare(s->P, s->ainfo, s->nyl + 2 * WS_HALO, s->tmaProg, s->tmaNL);
+        }
+#endif
+        s->useMarch = !s->useFast && !s->useTma && (s->d.kernel_variant == 0 || s->d.kernel_variant == 2 || s->d.kernel_variant == 3) && wsMarchSupported(s->P, s->exact);
         if (s->useMarch)
             wsMarchPrepare(s->P);
         WS_CUDA_CHECK(cudaStreamSynchronize(s->stream));
@@ -1808,6 +1892,6 @@ int ws_last_timing(ws_solver *s, int which, float *ms)
 void *ws_stream(ws_solver *s) { return s ? (void *)s->stream : nullptr; }
 
 int ws_uses_fast_kernels(const ws_solver *s) { return s && s->useFast ? 1 : 0; }
-int ws_kernel_path(const ws_solver *s) { return !s ? -1 : (s->useFast ? 2 : (s->useMarch ? 1 : 0)); }
+int ws_kernel_path(const ws_solver *s) { return !s ? -1 : (s->useFast ? 2 : (s->useTma ? 3 : (s->useMarch ? 1 : 0))); }
 
 } // extern "C"

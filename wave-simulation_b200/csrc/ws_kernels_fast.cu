@@ -812,9 +812,11 @@ template <int Q> int launchQ(const WsParams &P, int pass, cudaStream_t st)
 
 static unsigned long long *g_trace = nullptr;
 
-bool wsFastSupported(const WsParams &P, bool exact)
+// pass: 0 = velocity half-step only (the same statements in the elastic and the viscoelastic solver:
+// ForwardSolver3Delastic.cpp:181-277 = ForwardSolver3Dviscoelastic.cpp:188-262), -1 = both half-steps (elastic)
+bool wsFastSupported(const WsParams &P, bool exact, int pass)
 {
-    if (exact || P.eq != WS_EQ_ELASTIC || P.dim != 3)
+    if (exact || P.dim != 3 || !(P.eq == WS_EQ_ELASTIC || (P.eq == WS_EQ_VISCOELASTIC && pass == 0)))
         return false;
     if (P.edge_policy != 0 || P.damping == 1)
         return false;

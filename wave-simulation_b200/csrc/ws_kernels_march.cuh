@@ -49,7 +49,8 @@ __host__ __device__ constexpr Lists spec(int EQ, int DIM, int PASS)
             return d3 ? Lists{5, {F_SXX, F_SXY, F_SXZ, F_SYZ, F_SZZ}, 3, {F_SXY, F_SYY, F_SYZ}, 3, {F_VX, F_VY, F_VZ}, 3, {M_RIX, M_RIY, M_RIZ}, 0, {}, 0, {}}
                       : Lists{2, {F_SXX, F_SXY}, 2, {F_SXY, F_SYY}, 2, {F_VX, F_VY}, 2, {M_RIX, M_RIY}, 0, {}, 0, {}};
         if (d3)
-            return Lists{3, {F_VX, F_VY, F_VZ}, 3, {F_VX, F_VY, F_VZ}, 6, {F_SXX, F_SYY, F_SZZ, F_SXY, F_SXZ, F_SYZ},
+            // (own-point stresses in the order of the 3-D elastic arena, ws_api.cu: one TMA box fetches them together)
+            return Lists{3, {F_VX, F_VY, F_VZ}, 3, {F_VX, F_VY, F_VZ}, 6, {F_SXX, F_SXY, F_SYY, F_SYZ, F_SZZ, F_SXZ},
                          v ? 10 : 5, {M_PW, M_MU, M_MUXY, M_MUXZ, M_MUYZ, M_TAUP, M_TAUS, M_TSXY, M_TSXZ, M_TSYZ},
                          v ? 6 : 0, {RC_XX, RC_YY, RC_ZZ, RC_XY, RC_XZ, RC_YZ}, 0, {}};
         return Lists{2, {F_VX, F_VY}, 2, {F_VX, F_VY}, 3, {F_SXX, F_SYY, F_SXY}, v ? 6 : 3, {M_PW, M_MU, M_MUXY, M_TAUP, M_TAUS, M_TSXY},
@@ -98,6 +99,7 @@ template <int DIM, int Q, int NL> struct Geo {
     static constexpr int TX = DIM == 3 ? (NL == 4 ? 64 : 32) : (NL == 4 ? WS_MARCH_TX2D : 128), TZ = DIM == 3 ? 8 : 1;
     static constexpr int HZ = DIM == 3 ? H : 0;
     static constexpr int LDX = TX + 2 * HX, NROW = TZ + 2 * HZ, TILE = LDX * NROW; // staged tile with halo
+    static constexpr int TS = TILE;                                               // floats between two halo tiles of a stage
     static constexpr int NP = TX * TZ;                                            // plain tile (own points)
     static constexpr int LXN = TX / NL;                                           // threads per tile row
     static constexpr int NTHR = LXN * TZ;
@@ -130,15 +132,17 @@ template <int N> __device__ __forceinline__ void stv(float *p, const FV<N> &a) {
 // NL consecutive x points (x0 .. x0+NL-1) of row z on the plane being computed.
 // INTR = the points are known to be interior points of every axis (no edge rows, no CPML / ABS layer, not on the free
 // surface): a thread-block-uniform property of (tile, plane), so the boundary code disappears from that instantiation.
-template <int EQ, int DIM, int Q, int PASS, int NL, bool INTR>
+// G = tile geometry; PB = planes per stage (the TMA kernels of ws_kernels_tma.cuh stage groups of PB planes in 2-D: every
+// entry of a stage then holds PB tiles, one per plane, and `st` points at the tile of the plane being computed).
+template <int EQ, int DIM, int Q, int PASS, int NL, bool INTR, class G_ = Geo<DIM, Q, NL>, int PB = 1>
 struct MPt {
     using A = Ar<false>;
     using V = FV<NL>;
-    using G = Geo<DIM, Q, NL>;
+    using G = G_;
     static constexpr int H = Q / 2;
     static constexpr int NQ = spec(EQ, DIM, PASS).nq;
-    static constexpr int O_Q = spec(EQ, DIM, PASS).nt * G::TILE, O_F = O_Q + NQ * G::NP, O_M = O_F + spec(EQ, DIM, PASS).nf * G::NP,
-                         O_R = O_M + spec(EQ, DIM, PASS).nm * G::NP;
+    static constexpr int TS = G::TS, PS = PB * G::NP; // floats between two halo-tile entries / two plain-tile entries
+    static constexpr int O_Q = 0, O_F = O_Q + NQ * PS, O_M = O_F + spec(EQ, DIM, PASS).nf * PS, O_R = O_M + spec(EQ, DIM, PASS).nm * PS;
     const WsParams &P;
     int x0, z, nAct; // nAct = lanes inside the grid (NL except in a ragged last column or an inactive row)
     int ly, gy;
@@ -147,14 +151,15 @@ struct MPt {
     bool xEdge;      // some lane is an edge row of the x operators
     int ky, kz;      // CPML slab indices of the plane / the row (-1 outside)
     bool xLayer;     // some lane lies in an x CPML layer
-    float *st;       // current stage: halo tiles [nt][TILE], then plain tiles [feeds | fields | model | R[l][nr] | Cd[l][nc]][NP]
+    float *st;       // current stage, halo tiles [nt][PB][TILE] (at the tile of the current plane)
+    float *sp;       // current stage, plain tiles [feeds | fields | model | R[l][nr] | Cd[l][nc]][PB][NP] (same)
     int so, op;      // lane 0 inside a halo tile / a plain tile
     int oC;          // offset of the Cd tiles (after the L * nr memory-variable tiles)
     bool stR;        // the memory variables and Cd coefficients are staged (else they are read from global memory)
     V (&q)[NQ][Q + 1];
 
     __device__ __forceinline__ MPt(const WsParams &P_, int x0_, int z_, int nAct_, int so_, int op_, V (&q_)[NQ][Q + 1])
-        : P(P_), x0(x0_), z(z_), nAct(nAct_), st(nullptr), so(so_), op(op_), oC(O_R + P_.L * spec(EQ, DIM, PASS).nr * G::NP), stR(P_.marchStageR != 0), q(q_)
+        : P(P_), x0(x0_), z(z_), nAct(nAct_), st(nullptr), sp(nullptr), so(so_), op(op_), oC(O_R + P_.L * spec(EQ, DIM, PASS).nr * PS), stR(P_.marchStageR != 0), q(q_)
     {
         ly = gy = 0;
         i = 0;
@@ -211,7 +216,7 @@ struct MPt {
         } else if constexpr (axis == 2) {
             constexpr int ti = findIn(S.t, S.nt, F);
             if constexpr (ti >= 0) {
-                const float *p = st + ti * G::TILE + so - H * G::LDX;
+                const float *p = st + ti * TS + so - H * G::LDX;
                 if (INTR || rz == H) {
 #pragma unroll
                     for (int j = 0; j < Q; j++)
@@ -231,7 +236,7 @@ struct MPt {
                 constexpr int W0 = NL == 4 ? HX : H; // w[W0 + o] = value at offset o from lane 0
                 float w[NL == 4 ? 2 * HX + 4 : 2 * H + 1];
                 if constexpr (NL == 4) {
-                    const float *p = st + ti * G::TILE + so - HX;
+                    const float *p = st + ti * TS + so - HX;
 #pragma unroll
                     for (int k = 0; k < (2 * HX + 4) / 4; k++) {
                         if (4 * k + 3 >= HX - H && 4 * k <= HX + H + 3) { // vectors that hold a tap of some lane
@@ -241,7 +246,7 @@ struct MPt {
                             w[4 * k] = w[4 * k + 1] = w[4 * k + 2] = w[4 * k + 3] = 0.0f;
                     }
                 } else {
-                    const float *p = st + ti * G::TILE + so - H;
+                    const float *p = st + ti * TS + so - H;
 #pragma unroll
                     for (int k = 0; k <= 2 * H + NL - 1; k++)
                         w[k] = p[k];
@@ -380,7 +385,7 @@ struct MPt {
         constexpr Lists S = spec(EQ, DIM, PASS);
         constexpr int k = findIn(S.f, S.nf, F);
         if constexpr (k >= 0)
-            return ldv<NL>(st + O_F + k * G::NP + op);
+            return ldv<NL>(sp + O_F + k * PS + op);
         else
             return ldGlobal(P.fld[F] + i);
     }
@@ -390,7 +395,7 @@ struct MPt {
         constexpr Lists S = spec(EQ, DIM, PASS);
         constexpr int k = findIn(S.m, S.nm, M);
         if constexpr (k >= 0)
-            return ldv<NL>(st + O_M + k * G::NP + op);
+            return ldv<NL>(sp + O_M + k * PS + op);
         else
             return ldGlobal(P.mat[M] + i);
     }
@@ -399,7 +404,7 @@ struct MPt {
         constexpr Lists S = spec(EQ, DIM, PASS);
         constexpr int k = findIn(S.r, S.nr, C);
         if (k >= 0 && stR)
-            return ldv<NL>(st + O_R + (l * S.nr + k) * G::NP + op);
+            return ldv<NL>(sp + O_R + (l * S.nr + k) * PS + op);
         return ldGlobal(P.fld[F_R0 + 6 * l + C] + i);
     }
     // write-through: later statements of the same half-step read the updated memory variable again
@@ -409,14 +414,14 @@ struct MPt {
         constexpr int k = findIn(S.r, S.nr, C);
         stGlobal(P.fld[F_R0 + 6 * l + C] + i, v);
         if (k >= 0 && stR)
-            stv<NL>(st + O_R + (l * S.nr + k) * G::NP + op, v);
+            stv<NL>(sp + O_R + (l * S.nr + k) * PS + op, v);
     }
     template <int AXIS> __device__ __forceinline__ V cd(int l) const
     {
         constexpr Lists S = spec(EQ, DIM, PASS);
         constexpr int k = findIn(S.c, S.nc, AXIS);
         if (k >= 0 && stR)
-            return ldv<NL>(st + oC + (l * S.nc + k) * G::NP + op);
+            return ldv<NL>(sp + oC + (l * S.nc + k) * PS + op);
         return ldGlobal(P.mat[M_CD0 + 3 * l + AXIS] + i);
     }
     // free-surface scalings of these columns (only read on the plane y = 0)
@@ -560,13 +565,14 @@ __global__ void __launch_bounds__(Geo<DIM, Q, NL>::NTHR) kMarch(const __grid_con
 #pragma unroll
             for (int j = 0; j < Q; j++)
                 q[f][j] = q[f][j + 1];
-            q[f][Q] = ldv<NL>(st + MPG::O_Q + f * NP + op);
+            q[f][Q] = ldv<NL>(st + NT * G::TILE + f * NP + op);
         }
         const int gy = P.gy0 + ly;
         if (P.marchDebug == 1) { // developer switch: staging only (memory-side ceiling of the skeleton)
         } else if (tileIn && gy >= lo && gy < P.gny - lo) { // uniform over the thread block
             ti.setPlane(ly, iCur);
             ti.st = st;
+            ti.sp = st + NT * G::TILE;
             if (PASS == 0)
                 wsgen::passA<EQ, DIM, false>(P, ti);
             else
@@ -574,6 +580,7 @@ __global__ void __launch_bounds__(Geo<DIM, Q, NL>::NTHR) kMarch(const __grid_con
         } else if (active) {
             tg.setPlane(ly, iCur);
             tg.st = st;
+            tg.sp = st + NT * G::TILE;
             if (PASS == 0)
                 wsgen::passA<EQ, DIM, false>(P, tg);
             else

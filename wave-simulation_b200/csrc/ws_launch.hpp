@@ -10,7 +10,7 @@ void wsLaunchAbsFirstHalf(const WsParams &P, bool exact, int f0, int f1, int f2,
 void wsLaunchDivCurl(const WsParams &P, float *out, int which, cudaStream_t st);
 
 // tiled fast kernels (ws_kernels_fast.cu); return false when the configuration is not covered
-bool wsFastSupported(const WsParams &P, bool exact);
+bool wsFastSupported(const WsParams &P, bool exact, int pass = -1);
 // builds the TMA tensor maps for this solver's arrays into a device buffer (returned, owned by the caller; freed with
 // wsFastRelease) and fills P.fastMaps / P.fastChunk
 void *wsFastPrepare(WsParams &P, int nyp);
@@ -21,6 +21,21 @@ int wsLaunchFast(const WsParams &P, int pass, cudaStream_t st); // number of ker
 bool wsMarchSupported(const WsParams &P, bool exact);
 void wsMarchPrepare(WsParams &P); // fills P.marchChunk
 int wsLaunchMarch(const WsParams &P, int pass, cudaStream_t st); // number of kernels launched (0 = not served)
+
+// TMA marching kernels (ws_kernels_tma.cu): every equation type, compile-time FD order, FMA arithmetic; the operands are
+// fetched by tensor maps over the solver's arenas (allocations that hold several padded arrays at a constant stride)
+struct WsArenaInfo {
+    const float *base[2] = {nullptr, nullptr}; // arena origins
+    int count[2] = {0, 0};                     // arrays per arena
+    long long stride = 0;                      // floats between two arrays of an arena
+    signed char fldArena[F_COUNT], matArena[M_COUNT]; // arena of a wavefield / model slot
+    short fldPos[F_COUNT], matPos[M_COUNT];           // position inside it, -1 = not in an arena
+};
+namespace wstma { struct TmaProg; }
+bool wsTmaSupported(const WsParams &P, const WsArenaInfo &A, bool exact);
+void *wsTmaPrepare(WsParams &P, const WsArenaInfo &A, int nyp, wstma::TmaProg prog[2], int nl[2]);
+void wsTmaRelease(void *maps);
+int wsLaunchTma(const WsParams &P, int pass, const wstma::TmaProg &prog, int nl, cudaStream_t st);
 
 #ifndef WS_EMULATE
 #include <mutex>
