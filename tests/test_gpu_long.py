@@ -1,0 +1,69 @@
+"""Long runs on the GPU (`-m gpu`): what no reference fixture pins — stability over 10 000 steps and the drift of the FMA mode
+against the reference operation order over thousands of steps."""
+import numpy as np
+import pytest
+
+from cases import make_case
+from wsharness import Solver, idx1d, make_desc, rel_l2, ricker_np
+
+pytestmark = pytest.mark.gpu
+
+
+def _energy(s, fields):
+    return float(sum(np.sum(s.wavefield(f).astype(np.float64) ** 2) for f in fields))
+
+
+def test_config3_10k_steps_stay_finite_and_energy_decays():
+    """BASELINE config 3 (3D acoustic FD8, CPML 20, vp 2000..3500 m/s) over 10 000 time steps on a 256^3 grid (the 1024^3
+    run is recorded in profiles/r02_stability_cfg3_1024.txt): after the wavelet has ended the CPML must drain the
+    wavefield — the sum of squares of the pressure keeps falling and nothing grows back."""
+    n, nt = 256, 10000
+    d = make_desc(3, "acoustic", n, n, n, dh=10.0, dt=1e-3, nt=nt, fd_order=8, edge_policy=0, free_surface=0, damping=2, boundary_width=20,
+                  vmax_cpml=3500.0, fc_cpml=10.0, npower=4.0)
+    s = Solver(d)
+    y = (np.arange(n, dtype=np.float32) / n)[:, None, None]
+    s.set_material("velocityP", np.broadcast_to(2000.0 + 1500.0 * y, (n, n, n)).astype(np.float32).ravel())
+    s.set_material("density", np.full(n ** 3, 2000.0, np.float32))
+    s.prepare()
+    sig = np.zeros((1, nt), np.float32)
+    sig[0, :400] = ricker_np(400, 1e-3, 10.0, 1.0e6)  # 0.4 s wavelet, then silence
+    s.set_sources([1], [idx1d(n // 2, n // 2, n // 2, n, n)], sig)
+    s.set_receivers([1] * 4, [idx1d(n // 2 + 20 * (i + 1), n // 2, n // 2, n, n) for i in range(4)])
+    s.reset()
+    energies = []
+    for t0 in range(0, nt, 1000):
+        s.run(t0, t0 + 1000)
+        s.sync()
+        assert s.is_finite(), t0
+        energies.append(_energy(s, ["P"]))
+    seis = s.seismogram()
+    s.close()
+    assert np.isfinite(seis).all() and np.abs(seis[:, :1000]).max() > 0
+    # the direct wave leaves the 2.56 km cube within ~1.5 s; from then on the energy must fall monotonically towards zero
+    assert energies[0] > 0
+    for a, b in zip(energies[1:], energies[2:]):
+        assert b <= a * 1.0001, energies
+    assert energies[-1] < 1e-6 * energies[0], energies
+    assert np.abs(seis[:, -1000:]).max() < 1e-4 * np.abs(seis).max()
+
+
+@pytest.mark.parametrize("eq,dim,shape", [("elastic", 3, (128, 96, 64)), ("acoustic", 3, (96, 96, 96)), ("viscoelastic", 2, (256, 256, 1))])
+def test_fma_mode_drift_over_5000_steps(eq, dim, shape):
+    """default arithmetic (FMA contraction of the explicit multiply-adds, tiled / marching kernels) against the reference
+    operation order (exact mode, per-point kernels; bit-identical to the oracle) over 5000 steps: the seismograms must
+    stay within the 1e-5 relative L2 the north-star allows, i.e. the rounding differences do not accumulate."""
+    nx, ny, nz = shape
+    nt = 5000
+    res = []
+    for exact, variant in ((1, 1), (0, 0)):
+        case = make_case(eq, dim, nx, ny, nz, 8, 0, 1, 2, W=12, L=2 if eq == "viscoelastic" else 0, nt=nt, exact=exact, kernel_variant=variant)
+        s = case.setup(Solver(case.desc))
+        s.run(0, nt)
+        s.sync()
+        assert s.is_finite()
+        res.append(s.seismogram())
+        s.close()
+    assert np.abs(res[0]).max() > 0
+    for r in range(res[0].shape[0]):
+        if np.abs(res[0][r]).max() > 1e-12 * np.abs(res[0]).max():
+            assert rel_l2(res[1][r], res[0][r]) <= 1.0e-5, (r, rel_l2(res[1][r], res[0][r]))
