@@ -405,3 +405,29 @@ def test_product_driver_spatial_slabs_on_two_gpus(tmp_path):
     assert sorted(a) == sorted(b)
     for k in a:
         assert a[k] == b[k], k
+
+
+def test_driver_sources_from_su(driver, tmp_path):
+    """initSourcesFromSU=1 (Sources.cpp:235, 511; suHandler.cpp:14-27, 65-86): source position and type from the trace headers of
+    <SourceFilename>.<component>.su, the signal from the traces of the SU file SourceSignalFilename.  Both files are produced by
+    a first run of the driver itself (seismogram headers carry the source position, writeSource=1 writes the wavelet), and the
+    second run must reproduce the first run's seismogram."""
+    tmp = str(tmp_path)
+    os.makedirs(os.path.join(tmp, "SourceSignal"), exist_ok=True)
+    cfg = setup_case(tmp, receivers="30 0 0 3\n", sfmt=4, T=0.3)
+    text = open(cfg).read().replace("writeSource=0", "writeSource=1\nwriteSourceFilename=SourceSignal/Source")
+    open(cfg, "w").write(text)
+    run(driver, cfg, tmp)
+    _, first = read_su(os.path.join(tmp, "seismograms", "seismogram.shot_1.vy.su"))
+    _, wavelet = read_su(os.path.join(tmp, "SourceSignal", "Source.shot_1.vx.su"))
+    assert first.shape == (1, 150) and wavelet.shape == (1, 150) and np.abs(first).max() > 0
+    os.makedirs(os.path.join(tmp, "acq_su"), exist_ok=True)
+    # the seismogram file of a VY receiver becomes the geometry file of a VX source: only its headers (sx, sdepth) are read
+    os.rename(os.path.join(tmp, "seismograms", "seismogram.shot_1.vy.su"), os.path.join(tmp, "acq_su", "src.vx.su"))
+    text = text.replace("initSourcesFromSU=0", "initSourcesFromSU=1").replace("SourceFilename=acq/sources", "SourceFilename=acq_su/src")
+    text = text.replace("writeSource=1", "writeSource=0") + "SourceSignalFilename=SourceSignal/Source.shot_1.vx.su\n"
+    open(cfg, "w").write(text)
+    run(driver, cfg, tmp)
+    # the SU sources carry shot number 0 (the reference value-initialises the settings it does not read from the headers)
+    _, again = read_su(os.path.join(tmp, "seismograms", "seismogram.shot_0.vy.su"))
+    assert np.array_equal(again, first)

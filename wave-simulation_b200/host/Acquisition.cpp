@@ -417,10 +417,37 @@ void Acquisition::AcquisitionGeometry<ValueType>::setAcquisition(std::vector<Set
     version++;
 }
 
+// source geometry from the trace headers of <SourceFilename>.<component>.su (suHandler.cpp:14-27, 65-86): grid coordinates
+// x = sx 10^scalco / DH + 0.5, y = sdepth 10^scalel / DH + 0.5, z = sy 10^scalco / DH + 0.5 (truncated), type = component of the
+// file name, wavelet type 3 (signal from file).  The reference value-initialises the other fields (sourceSettingsVec.resize):
+// shot number 0 and signal row 0 for every trace, i.e. all SU sources fire together as one shot with the first trace of
+// SourceSignalFilename; components without a file are skipped here (the reference requires all four files).
+template <typename ValueType> static void readSourceSettingsFromSU(std::vector<Acquisition::sourceSettings<ValueType>> &all, std::string const &filename, ValueType DH)
+{
+    all.clear();
+    for (IndexType comp = 0; comp < Acquisition::NUM_ELEMENTS_SEISMOGRAMTYPE; comp++) {
+        const std::string name = filename + "." + Acquisition::SeismogramTypeString[comp];
+        const IndexType ntr = SUIO::numTracesSU(name);
+        for (IndexType tr = 0; tr < ntr; tr++) {
+            const double sco = std::pow(10.0, SUIO::readHeaderWordSU(name, tr, "scalco")), sel = std::pow(10.0, SUIO::readHeaderWordSU(name, tr, "scalel"));
+            Acquisition::sourceSettings<ValueType> s{};
+            s.sourceCoords.x = static_cast<IndexType>((ValueType)(SUIO::readHeaderWordSU(name, tr, "sx") * sco) / DH + 0.5);
+            s.sourceCoords.y = static_cast<IndexType>((ValueType)(SUIO::readHeaderWordSU(name, tr, "sdepth") * sel) / DH + 0.5);
+            s.sourceCoords.z = static_cast<IndexType>((ValueType)(SUIO::readHeaderWordSU(name, tr, "sy") * sco) / DH + 0.5);
+            s.sourceType = comp + 1;
+            s.waveletType = 3;
+            all.push_back(s);
+        }
+    }
+    SCAI_ASSERT_ERROR(!all.empty(), "No file with name: " << filename << ".'comp'.su could be read")
+}
+
 template <typename ValueType> void Acquisition::Sources<ValueType>::getAcquisitionSettings(Configuration::Configuration const &config)
 {
-    SCAI_ASSERT_ERROR(!config.getAndCatch("initSourcesFromSU", false), "initSourcesFromSU=1 (source positions and signals from SU files) is not available in the B200 host layer")
-    readAllSettings(allSourceSettings, config.get<std::string>("SourceFilename") + ".txt");
+    if (config.getAndCatch("initSourcesFromSU", false)) // Sources.cpp:511-512
+        readSourceSettingsFromSU<ValueType>(allSourceSettings, config.get<std::string>("SourceFilename"), config.get<ValueType>("DH"));
+    else
+        readAllSettings(allSourceSettings, config.get<std::string>("SourceFilename") + ".txt");
 }
 
 template <typename ValueType>
@@ -448,8 +475,15 @@ void Acquisition::Sources<ValueType>::init(std::vector<sourceSettings<ValueType>
         } else if (s.waveletType == 2 || s.waveletType == 3) {
             (s.waveletType == 2 ? flag2 : flag3) = true;
             SCAI_ASSERT_ERROR(!(flag2 && flag3), "Combination of wavelet type 2 and 3 not supported")
-            if (fileSignals.empty())
-                IO::readMatrix(fileSignals, fileRows, fileCols, config.get<std::string>("SourceSignalFilename"), config.get<IndexType>("SeismogramFormat"));
+            if (fileSignals.empty()) {
+                if (config.getAndCatch("initSourcesFromSU", false)) { // Sources.cpp:235-245: traces of the SU file SourceSignalFilename
+                    std::string name = config.get<std::string>("SourceSignalFilename");
+                    if (name.size() > 3 && name.compare(name.size() - 3, 3, ".su") == 0)
+                        name.erase(name.size() - 3);
+                    SUIO::readDataSU(name, fileSignals, fileRows, fileCols);
+                } else
+                    IO::readMatrix(fileSignals, fileRows, fileCols, config.get<std::string>("SourceSignalFilename"), config.get<IndexType>("SeismogramFormat"));
+            }
             const IndexType r = s.waveletType == 2 ? 0 : s.row;
             SCAI_ASSERT_ERROR(r < fileRows && fileCols == NT, "source signal file must hold one row of " << NT << " samples per source")
             std::copy(fileSignals.begin() + (size_t)r * fileCols, fileSignals.begin() + (size_t)(r + 1) * fileCols, row);

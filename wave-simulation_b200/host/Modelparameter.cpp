@@ -51,7 +51,7 @@ void Modelparameter::Modelparameter<ValueType>::init(Configuration::Configuratio
             relaxationFrequency.push_back(config.get<ValueType>(keys[l]));
     }
     const size_t N = (size_t)modelCoordinates.getNGridpoints();
-    raw.clear();
+    raw = std::make_shared<std::map<std::string, std::vector<ValueType>>>();
     for (auto const &p : parsOf(equationType)) {
         std::vector<ValueType> v(N);
         if (modelRead == 1) {
@@ -67,14 +67,16 @@ void Modelparameter::Modelparameter<ValueType>::init(Configuration::Configuratio
         if (scale != 1)
             for (auto &x : v)
                 x *= scale;
-        raw[p.name] = std::move(v);
+        (*raw)[p.name] = std::move(v);
     }
     dirtyFlag = true;
 }
 
 template <typename ValueType> void Modelparameter::Modelparameter<ValueType>::init(std::string const &name, std::vector<ValueType> const &values)
 {
-    raw[name] = values;
+    if (raw.use_count() > 1)
+        raw = std::make_shared<std::map<std::string, std::vector<ValueType>>>(*raw);
+    (*raw)[name] = values;
     dirtyFlag = true;
 }
 
@@ -88,8 +90,8 @@ template <typename ValueType> void Modelparameter::Modelparameter<ValueType>::wr
 
 template <typename ValueType> std::vector<ValueType> const &Modelparameter::Modelparameter<ValueType>::at(std::string const &name) const
 {
-    auto it = raw.find(name);
-    if (it == raw.end())
+    auto it = raw->find(name);
+    if (it == raw->end())
         COMMON_THROWEXCEPTION("There is no " << name << " parameter in an " << equationType << " modelling")
     return it->second;
 }

@@ -35,7 +35,7 @@ namespace KITGPI
             std::vector<ValueType> const &getRelaxationFrequency() const { return relaxationFrequency; }
 
             //! raw parameters by their C-ABI / reference getter names ("velocityP", "density", "magneticPermeability", ...)
-            std::map<std::string, std::vector<ValueType>> const &getRawParameters() const { return raw; }
+            std::map<std::string, std::vector<ValueType>> const &getRawParameters() const { return *raw; }
             std::vector<ValueType> const &getVelocityP() const { return at("velocityP"); }
             std::vector<ValueType> const &getVelocityS() const { return at("velocityS"); }
             std::vector<ValueType> const &getDensity() const { return at("density"); }
@@ -60,7 +60,9 @@ namespace KITGPI
             std::string equationType;
             bool seismic = true;
             bool dirtyFlag = true;
-            std::map<std::string, std::vector<ValueType>> raw;
+            //! shared between the copies the shot domains work on (one copy of a 768^3 model is 9 GB of host memory); a copy that
+            //! changes a parameter gets its own map (init)
+            std::shared_ptr<std::map<std::string, std::vector<ValueType>>> raw = std::make_shared<std::map<std::string, std::vector<ValueType>>>();
             std::vector<ValueType> relaxationFrequency;
             ForwardSolver::DeviceGroup *h = nullptr;
         };
