@@ -35,6 +35,7 @@
 namespace {
 
 using Idx = int32_t;
+constexpr int WS_MAXQ_ORACLE = 12; // Derivatives.cpp:2001-2042: orders 2..12
 using std::vector;
 
 thread_local std::string g_err;
@@ -204,6 +205,176 @@ struct Profile { // pattern + (a,b) full-grid and half-grid coefficient values o
     vector<T> a, b, ah, bh;
 };
 
+// ------------------------------------------------------------------------------------------------------------------
+// Variable grid (Acquisition/Coordinates.cpp:115-247, 383-407, 464-536, 623-694): horizontal layers whose grid spacing is
+// dhFactor = 3^n times the finest one; an interface plane is stored with the spacing of its FINER neighbour.  Coordinates
+// are always fine-grid coordinates; the model vector is the concatenation of the layers' own regular grids.
+// ------------------------------------------------------------------------------------------------------------------
+struct VarGrid {
+    bool active = false;
+    int numLayers = 1;
+    Idx NX = 0, NY = 0, NZ = 0, n = 0;
+    vector<int> iface;      // interface[0] = -1 ... interface[numLayers] = NY - 1
+    vector<int> dhFactor, transition, layerStart, layerEnd, varNX, varNY, varNZ, fdOrder;
+    vector<Idx> nPerLayer;
+
+    // Coordinates.cpp:115-247 (init(dhFactors, interfaces)); interfaces = the file column without its leading 0
+    void init(Idx nx, Idx ny, Idx nz, const vector<int> &dhf, vector<int> interfaces)
+    {
+        NX = nx; NY = ny; NZ = nz;
+        dhFactor = dhf;
+        numLayers = (int)dhFactor.size();
+        ORACLE_REQUIRE(numLayers > 0 && (int)interfaces.size() == numLayers - 1, "number of interfaces doesn't match to the number of different grid spacings");
+        iface = interfaces;
+        iface.push_back((int)NY - 1);
+        iface.insert(iface.begin(), -1);
+        int dhMax = 0;
+        for (int l = 0; l < numLayers; l++) {
+            int f = dhFactor[l];
+            ORACLE_REQUIRE(f >= 1, "incompatible dhFactor, dhFactor must be 3^n");
+            while (f % 3 == 0)
+                f /= 3;
+            ORACLE_REQUIRE(f == 1, "incompatible dhFactor, dhFactor must be 3^n");
+            dhMax = std::max(dhMax, dhFactor[l]);
+        }
+        Idx NXmax = NX, NZmax = NZ;
+        if (dhMax != 1) {
+            while (NXmax != (NXmax / dhMax) * dhMax + 1 + dhMax / 2)
+                NXmax--;
+            while (NZ != 1 && NZmax != (NZmax / dhMax) * dhMax + 1 + dhMax / 2)
+                NZmax--;
+            NX = NXmax;
+            NZ = NZmax;
+            // the layer thicknesses must be multiples of the layer's spacing (:178-197): interfaces move up until they are
+            int layer = 0;
+            while (layer < 1) {
+                layer++;
+                if ((iface[layer] - iface[layer - 1] - 1) % dhFactor[layer - 1] != 0) {
+                    iface[layer]--;
+                    layer--;
+                }
+            }
+            layer = 1;
+            while (layer < numLayers) {
+                layer++;
+                if ((iface[layer] - iface[layer - 1]) % dhFactor[layer - 1] != 0) {
+                    iface[layer]--;
+                    layer--;
+                }
+            }
+        }
+        NY = iface[numLayers] + 1;
+        transition.assign(numLayers, 0);
+        layerStart.assign(numLayers, 0);
+        layerEnd.assign(numLayers, 0);
+        for (int l = 0; l < numLayers - 1; l++) {
+            if (dhFactor[l] < dhFactor[l + 1]) {
+                transition[l] = 1;
+                layerEnd[l] = iface[l + 1];
+                layerStart[l + 1] = iface[l + 1] + dhFactor[l + 1];
+            } else if (dhFactor[l] > dhFactor[l + 1]) {
+                transition[l] = -1;
+                layerEnd[l] = iface[l + 1] - dhFactor[l];
+                layerStart[l + 1] = iface[l + 1];
+            } else {
+                transition[l] = 0;
+                layerEnd[l] = iface[l + 1] - dhFactor[l];
+                layerStart[l + 1] = iface[l + 1];
+            }
+        }
+        transition[numLayers - 1] = 0;
+        layerEnd[numLayers - 1] = iface[numLayers];
+        varNX.assign(numLayers, 0); varNY.assign(numLayers, 0); varNZ.assign(numLayers, 0);
+        nPerLayer.assign(numLayers, 0);
+        n = 0;
+        for (int l = 0; l < numLayers; l++) {
+            varNY[l] = (layerEnd[l] - layerStart[l]) / dhFactor[l] + 1;
+            varNX[l] = (int)(NXmax / dhFactor[l]);
+            varNZ[l] = (int)(NZmax / dhFactor[l]);
+            if (dhFactor[l] > 1) {
+                varNX[l]++;
+                varNZ[l]++;
+            }
+            nPerLayer[l] = (Idx)varNX[l] * varNY[l] * varNZ[l];
+            n += nPerLayer[l];
+        }
+        active = true;
+    }
+    // Coordinates.cpp:383-398: the coarse grids own the interface of a fine -> coarse transition
+    int getLayer(Idx y) const
+    {
+        int layer = 0;
+        for (layer = 0; layer < numLayers; layer++) {
+            if ((int)y < iface[layer + 1] && (int)y > iface[layer])
+                break;
+            else if ((int)y == iface[layer + 1]) {
+                if (transition.at(layer) > 0)
+                    layer += 1;
+                break;
+            }
+        }
+        return layer;
+    }
+    bool onInterface(Idx y) const // :474-483 (interface[numLayers] = NY - 1 is not tested, interface[0] = -1 never matches)
+    {
+        for (int l = 0; l < numLayers; l++)
+            if ((int)y == iface[l])
+                return true;
+        return false;
+    }
+    Idx distToInterface(Idx y) const // :490-499
+    {
+        Idx dist = NY;
+        for (int k = 1; k < numLayers; k++)
+            dist = std::min<Idx>(dist, std::abs((int)y - iface[k]));
+        return dist;
+    }
+    int getTransition(Idx y) const // :517-530
+    {
+        ORACLE_REQUIRE(onInterface(y), "Y Coordinate is not located on an variable grid interface");
+        int t = 0;
+        for (int l = 0; l < numLayers; l++)
+            if ((int)y == iface[l + 1])
+                t = transition[l];
+        return t;
+    }
+    int factorAt(Idx y) const { return dhFactor[getLayer(y)]; }
+    void index2coord(Idx index, Idx &x, Idx &y, Idx &z) const // :623-651
+    {
+        int layer;
+        for (layer = 0; layer < numLayers; layer++) {
+            if (index >= nPerLayer[layer])
+                index -= nPerLayer[layer];
+            else
+                break;
+        }
+        y = index / ((Idx)varNX[layer] * varNZ[layer]);
+        index -= y * ((Idx)varNX[layer] * varNZ[layer]);
+        z = index / varNX[layer];
+        index -= z * varNX[layer];
+        x = index;
+        x *= dhFactor[layer];
+        y *= dhFactor[layer];
+        z *= dhFactor[layer];
+        y += layerStart[layer];
+    }
+    Idx coord2index(Idx X, Idx Y, Idx Z) const // :668-694
+    {
+        ORACLE_REQUIRE(X >= 0 && X < NX && Y >= 0 && Y < NY && Z >= 0 && Z < NZ, "Could not map from coordinate to index!");
+        int layer;
+        for (layer = 0; layer < numLayers; layer++)
+            if (Y <= layerEnd[layer] && Y >= layerStart[layer]) {
+                Y -= layerStart[layer];
+                break;
+            }
+        ORACLE_REQUIRE(layer < numLayers, "Could not map from coordinate to index!");
+        Idx index = (X / dhFactor[layer]) + (Z / dhFactor[layer]) * varNX[layer] + (Y / dhFactor[layer]) * (Idx)varNX[layer] * varNZ[layer];
+        for (int l = 1; l <= layer; l++)
+            index += nPerLayer[l - 1];
+        return index;
+    }
+};
+
 template <typename T>
 struct Oracle {
     ws_desc d{};
@@ -216,6 +387,8 @@ struct Oracle {
     std::map<std::string, vector<T>> fld; // wavefields by reference component name
 
     Csr<T> Dxf, Dxb, Dyf, Dyb, Dzf, Dzb, DyfFS, DybFS;
+    VarGrid vg;                                   // variable grid (inactive on a regular grid)
+    Csr<T> InterFull, InterStagX, InterStagZ;     // interpolation on the interface planes (Derivatives.cpp:1252-1566)
 
     // boundaries
     vector<T> damping;                 // ABS (dense, default 1.0)
@@ -240,9 +413,13 @@ struct Oracle {
     // temporaries
     vector<T> update, update_temp, update2, vxx, vyy, vzz;
 
-    Idx index(Idx x, Idx y, Idx z) const { return x + z * NX + y * NX * NZ; } // Coordinates.cpp:687
+    Idx index(Idx x, Idx y, Idx z) const { return vg.active ? vg.coord2index(x, y, z) : x + z * NX + y * NX * NZ; } // Coordinates.cpp:687
     void coord(Idx i, Idx &x, Idx &y, Idx &z) const
     { // Coordinates.cpp:615-645
+        if (vg.active) {
+            vg.index2coord(i, x, y, z);
+            return;
+        }
         y = i / (NX * NZ);
         i -= y * (NX * NZ);
         z = i / NX;
@@ -394,8 +571,283 @@ struct Oracle {
         return A;
     }
 
+    // ------------------------------------------------------------------------------------------------------------
+    // Variable grid / variable FD order: the same assembly loops with the layer's spacing and order
+    // ------------------------------------------------------------------------------------------------------------
+    int orderOfLayer(int layer) const { return vg.fdOrder.empty() ? d.fd_order : vg.fdOrder[layer]; }
+    T dhOfLayer(int layer) const { return DH * (T)vg.dhFactor[layer]; } // Coordinates.cpp:240 varDH
+    std::map<int, vector<T>> allFdCoef() const
+    {
+        std::map<int, vector<T>> m;
+        for (int o = 2; o <= WS_MAXQ_ORACLE; o += 2)
+            m[o] = fdCoef<T>(o);
+        return m;
+    }
+
+    // x / z derivatives: Derivatives.cpp:129-186 (calcDxf), :706-763 (calcDxb), :304-359 (calcDzf), :1177-1243 (calcDzb).
+    // On an interface plane (stored with the fine spacing, operated with the coarse one) the taps are shifted by a third
+    // of the coarse spacing towards the staggered position.
+    Csr<T> derivVarXZ(int axis, bool forward)
+    {
+        const auto fdmap = allFdCoef();
+        const Idx n = axis == 0 ? NX : NZ;
+        Csr<T> A = assemble<T>(N, [&](Idx row, Idx *cols, T *vals) {
+            Idx x, y, z;
+            coord(row, x, y, z);
+            const int layer = vg.getLayer(y);
+            const int f = vg.dhFactor[layer];
+            int order = orderOfLayer(layer);
+            Idx c = axis == 0 ? x : z;
+            const Idx shift = vg.onInterface(y) ? (forward ? -(f / 3) : (f / 3)) : 0;
+            int k = 0;
+            for (int j = 0; j < order; j++) {
+                Idx X, Xmin, Xmax;
+                if (forward) {
+                    X = c + shift + f * (j - order / 2 + 1);
+                    Xmin = c + shift + f * (-order / 2 + 1);
+                    Xmax = c + shift + f * order / 2;
+                } else {
+                    X = c + shift + f * (j - order / 2);
+                    Xmin = c + shift + f * (-order / 2);
+                    Xmax = c + shift + f * (order / 2 - 1);
+                }
+                static const int H1 = getenv("VG_H1") ? atoi(getenv("VG_H1")) : 0;
+                if (H1 == 2) { // truncation: full order, off-grid taps dropped
+                    if (X >= 0 && X < n) {
+                        cols[k] = axis == 0 ? vg.coord2index(X, y, z) : vg.coord2index(x, y, X);
+                        vals[k] = fdmap.at(order)[j] / dhOfLayer(layer);
+                        k++;
+                    }
+                    continue;
+                }
+                if (Xmin < 0) {
+                    order += H1 ? 2 * (int)((Xmin - f + 1) / f) : 2 * (int)Xmin;
+                    if (!forward && order == 0) {
+                        order = 2;
+                        c += H1 ? f : 1;
+                    }
+                    j--;
+                } else if (Xmax >= n) {
+                    order -= H1 ? 2 * (int)((Xmax - n + f) / f) : 2 * (int)(Xmax - n + 1);
+                    if (forward && order == 0) {
+                        order = 2;
+                        c -= H1 ? f : 1;
+                    }
+                    j--;
+                } else {
+                    cols[k] = axis == 0 ? vg.coord2index(X, y, z) : vg.coord2index(x, y, X);
+                    vals[k] = fdmap.at(order)[j] / dhOfLayer(layer);
+                    k++;
+                }
+            }
+            return k;
+        });
+        scaleCsr(A, DT);
+        return A;
+    }
+
+    // order at a point of the y operators: reduced towards the interfaces (Derivatives.cpp:237-244, 803-811)
+    int orderNearInterface(int layer, Idx y) const
+    {
+        int order = orderOfLayer(layer);
+        static const int H6 = getenv("VG_H6") ? atoi(getenv("VG_H6")) : 0;
+        Idx distance = vg.distToInterface(y) / vg.dhFactor[layer];
+        if (H6 == 1 && vg.distToInterface(y) % vg.dhFactor[layer] != 0)
+            distance += 1;
+        if (distance == 0)
+            order = 2;
+        else if (order > distance * 2)
+            order = (int)distance * 2;
+        return order;
+    }
+
+    // y derivatives: Derivatives.cpp:210-280 (calcDyf), :771-843 (calcDyb), :367-440 (calcDyfFreeSurface; image = true)
+    Csr<T> derivVarY(bool forward, bool image)
+    {
+        const auto fdmap = allFdCoef();
+        Csr<T> A = assemble<T>(N, [&](Idx row, Idx *cols, T *vals) {
+            Idx x, y, z;
+            coord(row, x, y, z);
+            const int layer = vg.getLayer(y);
+            int order = orderNearInterface(layer, y);
+            const bool onI = vg.onInterface(y);
+            const int trans = onI ? vg.getTransition(y) : 0;
+            int f = vg.dhFactor[layer];
+            T dh = dhOfLayer(layer);
+            static const int H3 = getenv("VG_H3") ? atoi(getenv("VG_H3")) : 0;
+            if (forward && onI && trans == -1 && !(H3 == 1 && image)) { // coarse -> fine: the forward operator of the interface uses the fine grid below
+                f = vg.dhFactor[layer + 1];
+                dh = dhOfLayer(layer + 1);
+            }
+            int k = 0;
+            if (image) {
+                for (int j = 0; j < order; j++) {
+                    const Idx Y = y + f * (j - order / 2 + 1);
+                    const T fdCoeff = fdmap.at(order)[j];
+                    T diffCoeff = 0;
+                    if (order >= (2 + (int)(2 * y / f) + j)) // C++ precedence: 2 * y / dhFactor = (2 * y) / dhFactor
+                        diffCoeff = fdmap.at(order)[order - 2 - (int)(2 * y / f) - j];
+                    if (Y >= 0 && Y < NY) {
+                        cols[k] = vg.coord2index(x, Y, z);
+                        vals[k] = (fdCoeff - diffCoeff) / dh;
+                        k++;
+                    }
+                }
+                return k;
+            }
+            Idx yc = y;
+            for (int j = 0; j < order; j++) {
+                Idx Y, Ymin, Ymax;
+                if (forward) {
+                    Y = yc + f * (j - order / 2 + 1);
+                    Ymin = yc + f * (-order / 2 + 1);
+                    Ymax = yc + f * order / 2;
+                } else {
+                    Y = yc + f * (j - order / 2);
+                    Ymin = yc + f * (-order / 2);
+                    Ymax = yc + f * (order / 2 - 1);
+                    // coordinate correction in the fine staggered grid (:823-830)
+                    if (onI) {
+                        if (j == 0 && trans == 1)
+                            Y += vg.dhFactor[layer - 1];
+                        static const int H4 = getenv("VG_H4") ? atoi(getenv("VG_H4")) : 0;
+                        if (j == 1 && trans == -1 && H4 != 1)
+                            Y += vg.dhFactor[layer + 1];
+                    }
+                }
+                static const int H1 = getenv("VG_H1") ? atoi(getenv("VG_H1")) : 0;
+                if (H1 == 2) {
+                    if (Y >= 0 && Y < NY) {
+                        cols[k] = vg.coord2index(x, Y, z);
+                        vals[k] = fdmap.at(order)[j] / (forward ? dh : dhOfLayer(layer));
+                        k++;
+                    }
+                    continue;
+                }
+                if (Ymin < 0) {
+                    order += 2 * (int)Ymin;
+                    if (!forward && order == 0) {
+                        order = 2;
+                        yc += 1;
+                    }
+                    j--;
+                } else if (Ymax >= NY) {
+                    order -= 2 * (int)(Ymax - NY + 1);
+                    if (forward && order == 0) {
+                        order = 2;
+                        yc -= 1;
+                    }
+                    j--;
+                } else {
+                    cols[k] = vg.coord2index(x, Y, z);
+                    vals[k] = fdmap.at(order)[j] / (forward ? dh : dhOfLayer(layer));
+                    k++;
+                }
+            }
+            return k;
+        });
+        scaleCsr(A, DT);
+        return A;
+    }
+
+    // bilinear interpolation of the points of an interface plane that are not points of the coarse grid
+    // (Derivatives.cpp:1252-1354 full grid, :1356-1460 staggered in x, :1462-1566 staggered in z); identity elsewhere
+    Csr<T> interpolationVar(int mode)
+    {
+        return assemble<T>(N, [&](Idx row, Idx *cols, T *vals) {
+            Idx x, y, z;
+            coord(row, x, y, z);
+            if (!vg.onInterface(y)) {
+                cols[0] = row;
+                vals[0] = (T)1;
+                return 1;
+            }
+            const int layer = vg.getLayer(y);
+            const int f = vg.dhFactor[layer];
+            int fFine = f;
+            const int trans = vg.getTransition(y);
+            if (trans == 1)
+                fFine = vg.dhFactor[layer - 1];
+            else if (trans == -1)
+                fFine = vg.dhFactor[layer + 1];
+            const T denom = (T)1 / (T)(f * f);
+            const int modx = mode == 1 ? (int)((x - f / 2) % f) : (int)(x % f);
+            const int modz = mode == 2 ? (int)((z - f / 2) % f) : (int)(z % f);
+            const int kx = mode == 1 ? 1 : 2, kz = mode == 2 ? 1 : 2; // reach towards the upper end of the axis
+            const bool lowX = mode != 1 || x >= modx, lowZ = mode != 2 || z >= modz;
+            int k = 0;
+            auto push = [&](Idx X, Idx Z, T v) {
+                cols[k] = vg.coord2index(X, y, Z);
+                vals[k] = v;
+                k++;
+            };
+            if (lowX && lowZ)
+                push(x - modx, z - modz, (T)((f - modx) * (f - modz)) * denom);
+            if (lowZ && x + kx * fFine < NX)
+                push(x + f - modx, z - modz, (T)(modx * (f - modz)) * denom);
+            if (lowX && z + kz * fFine < NZ)
+                push(x - modx, z + f - modz, (T)((f - modx) * modz) * denom);
+            if (x + kx * fFine < NX && z + kz * fFine < NZ)
+                push(x + f - modx, z + f - modz, (T)(modx * modz) * denom);
+            return k;
+        });
+    }
+
+    // 2-point averaging matrices on the variable grid, Modelparameter.cpp:336-437
+    Csr<T> avg2Var(int axis)
+    {
+        return assemble<T>(N, [&](Idx row, Idx *cols, T *vals) {
+            Idx x, y, z;
+            coord(row, x, y, z);
+            const int layer = vg.getLayer(y);
+            Idx X = x, Y = y, Z = z;
+            bool inside;
+            if (axis == 0) {
+                X += vg.dhFactor[layer];
+                inside = X < NX;
+            } else if (axis == 2) {
+                Z += vg.dhFactor[layer];
+                inside = Z < NZ;
+            } else {
+                if (vg.onInterface(y) && vg.getTransition(y) == 0)
+                    Y += vg.dhFactor[layer + 1];
+                else
+                    Y += vg.dhFactor[layer];
+                inside = Y < NY;
+            }
+            if (!inside) {
+                cols[0] = row;
+                vals[0] = (T)1.0;
+                return 1;
+            }
+            cols[0] = row;
+            vals[0] = (T)(1.0 / 2.0);
+            cols[1] = vg.coord2index(X, Y, Z);
+            vals[1] = (T)(1.0 / 2.0);
+            return 2;
+        });
+    }
+
     void buildDerivatives()
     {
+        if (vg.active) {
+            ORACLE_REQUIRE(d.eq == WS_EQ_ACOUSTIC, "variable grid: this oracle restates the acoustic solvers only");
+            Dxf = derivVarXZ(0, true);
+            Dxb = derivVarXZ(0, false);
+            Dyf = derivVarY(true, false);
+            Dyb = derivVarY(false, false);
+            if (d.dim == 3) {
+                Dzf = derivVarXZ(2, true);
+                Dzb = derivVarXZ(2, false);
+            }
+            if (d.free_surface == 1)
+                DyfFS = derivVarY(true, true);
+            InterFull = interpolationVar(0);
+            InterStagX = interpolationVar(1);
+            if (d.dim == 3)
+                InterStagZ = interpolationVar(2);
+            return;
+        }
         auto mk = [&](int axis, bool fwd) { return d.edge_policy == 0 ? derivStencil(axis, fwd) : derivSparse(axis, fwd); };
         Dxf = mk(0, true);
         Dxb = mk(0, false);
@@ -417,6 +869,8 @@ struct Oracle {
     // 2-point averaging matrices, Modelparameter.cpp:336-447
     Csr<T> avg2(int axis)
     {
+        if (vg.active)
+            return avg2Var(axis);
         const Idx n = axisN(axis), st = axisStride(axis);
         return assemble<T>(N, [&](Idx row, Idx *cols, T *vals) {
             Idx c = axisCoord(row, axis);
@@ -789,6 +1243,7 @@ struct Oracle {
     // ABS3D.cpp:154-218, ABS2D.cpp:115-178
     void initABS()
     {
+        ORACLE_REQUIRE(!vg.active, "variable grid: the ABS frame is not restated (the reference's CI uses CPML there)");
         const int W = d.boundary_width;
         damping.assign(N, (T)1.0);
         vector<T> coeff(W);
@@ -833,7 +1288,8 @@ struct Oracle {
     }
 
     // CPML.cpp:39-68
-    void calcCoeffCPML(vector<T> &a, vector<T> &b, bool shiftGrid)
+    void calcCoeffCPML(vector<T> &a, vector<T> &b, bool shiftGrid) { calcCoeffCPML(a, b, shiftGrid, DH); }
+    void calcCoeffCPML(vector<T> &a, vector<T> &b, bool shiftGrid, T DH)
     {
         const int W = (int)a.size();
         T shift = shiftGrid ? (T)0.5 : (T)0;
@@ -854,8 +1310,54 @@ struct Oracle {
     }
 
     // CPML3D.cpp:222-368, CPML2D.cpp:170-285 (same rules; 2D has no z)
+    // CPML2DAcoustic.cpp:99-200, CPML3DAcoustic.cpp init: per layer a profile of ceil(BoundaryWidth / dhFactor) points with the layer's DH
+    void initCPMLVar()
+    {
+        const int fs = d.free_surface;
+        vector<vector<T>> a, b, ah, bh;
+        for (int l = 0; l < vg.numLayers; l++) {
+            const int width = (int)std::ceil((float)d.boundary_width / vg.dhFactor[l]);
+            vector<T> al(width), bl(width), ahl(width), bhl(width);
+            calcCoeffCPML(al, bl, false, dhOfLayer(l));
+            calcCoeffCPML(ahl, bhl, true, dhOfLayer(l));
+            a.push_back(al); b.push_back(bl); ah.push_back(ahl); bh.push_back(bhl);
+        }
+        px = Profile<T>();
+        py = Profile<T>();
+        pz = Profile<T>();
+        for (Idx i = 0; i < N; i++) {
+            Idx x, y, z;
+            coord(i, x, y, z);
+            const int l = vg.getLayer(y), f = vg.dhFactor[l];
+            const int width = (int)std::ceil((float)d.boundary_width / f);
+            const Idx xDist = edgeDist(x, NX) / f, yDist = edgeDist(y, NY) / f, zDist = edgeDist(z, NZ) / f;
+            auto push = [&](Profile<T> &p, Idx dist, bool low) {
+                p.idx.push_back(i);
+                if (low) {
+                    p.a.push_back(a[l][dist]); p.b.push_back(b[l][dist]); p.ah.push_back(ah[l][dist]); p.bh.push_back(bh[l][dist]);
+                } else {
+                    p.a.push_back(ah[l][dist]); p.b.push_back(bh[l][dist]); p.ah.push_back(a[l][dist]); p.bh.push_back(b[l][dist]);
+                }
+            };
+            if (xDist < width)
+                push(px, xDist, x / f < width);
+            if (yDist < width) {
+                if (y / f < width) {
+                    if (fs == 0)
+                        push(py, yDist, true);
+                } else
+                    push(py, yDist, false);
+            }
+            if (d.dim == 3 && zDist < width)
+                push(pz, zDist, z / f < width);
+        }
+    }
     void initCPML()
     {
+        if (vg.active) {
+            initCPMLVar();
+            return;
+        }
         const int W = d.boundary_width;
         vector<T> a(W), b(W), ah(W), bh(W);
         calcCoeffCPML(a, b, false);
@@ -1017,6 +1519,10 @@ struct Oracle {
         ORACLE_REQUIRE(NX > 0 && NY > 0 && NZ > 0, "invalid grid");
         ORACLE_REQUIRE((int64_t)NX * NY * NZ < (int64_t)1 << 31, "grid too large for int32 indices");
         N = NX * NY * NZ;
+        if (vg.active) { // the grid may have been trimmed to fit the coarsest spacing (Coordinates.cpp:153-200)
+            NX = vg.NX; NY = vg.NY; NZ = vg.NZ;
+            N = vg.n;
+        }
         DT = d.dt;
         DH = d.dh;
         L = visco() ? d.n_relax : 0;
@@ -1216,19 +1722,30 @@ struct Oracle {
     {
         const bool fs = d.free_surface == 1, d3 = d.dim == 3;
         vector<T> &p = F("P"), &vX = F("VX"), &vY = F("VY");
+        // variable grid: the points of the interface planes that are not coarse-grid points are interpolated after every
+        // update (ForwardSolver2Dacoustic.cpp:127-157,179-183; ForwardSolver3Dacoustic.cpp:141-190,218-222)
+        auto interpolate = [&](const Csr<T> &I, vector<T> &v) {
+            if (!vg.active)
+                return;
+            update_temp.swap(v);
+            spmv(I, update_temp, v);
+        };
         spmv(Dxf, p, update);
         applyCPML(update, "p_x", px, true);
         vmul(update, M("inverseDensityAverageX"));
         vadd(vX, update);
+        interpolate(InterStagX, vX);
         spmv(fs ? DyfFS : Dyf, p, update);
         applyCPML(update, "p_y", py, true);
         vmul(update, M("inverseDensityAverageY"));
         vadd(vY, update);
+        interpolate(InterFull, vY);
         if (d3) {
             spmv(Dzf, p, update);
             applyCPML(update, "p_z", pz, true);
             vmul(update, M("inverseDensityAverageZ"));
             vadd(F("VZ"), update);
+            interpolate(InterStagZ, F("VZ"));
         }
         spmv(Dxb, vX, update);
         applyCPML(update, "vxx", px, false);
@@ -1246,6 +1763,7 @@ struct Oracle {
             absApply({"P", "VX", "VY", "VZ"});
         else
             absApply({"P", "VX", "VY"});
+        interpolate(InterFull, p);
         if (fs)
             setSurfaceZero(p);
         applySource(t);
@@ -1840,6 +2358,50 @@ int wso_create(const ws_desc *desc, int precision, wso_solver **out)
         }
         *out = reinterpret_cast<wso_solver *>(h.release());
     });
+}
+// Variable grid / variable FD order (Coordinates.cpp:44-72: gridConfig columns interface, dhFactor, FDorder; the first interface must
+// be 0).  desc->nx/ny/nz is the fine regular grid; the model vectors then hold wso_grid_size() values in the layered order and
+// acquisition indices come from wso_coordinate2index().  fd_orders may be null (desc->fd_order everywhere).
+int wso_create_vargrid(const ws_desc *desc, int precision, int32_t nlayers, const int32_t *interfaces, const int32_t *dh_factors, const int32_t *fd_orders, wso_solver **out)
+{
+    return guard([&] {
+        ORACLE_REQUIRE(desc && out && nlayers >= 1 && interfaces && dh_factors, "null argument");
+        ORACLE_REQUIRE(precision == 32 || precision == 64, "precision must be 32 or 64");
+        ORACLE_REQUIRE(interfaces[0] == 0, "First interface must by at y=0 ");
+        for (int l = 1; l < nlayers; l++) {
+            ORACLE_REQUIRE(l == 1 || interfaces[l] > interfaces[l - 1], "interface coordinates must increase.");
+            ORACLE_REQUIRE(dh_factors[l] == dh_factors[l - 1] * 3 || dh_factors[l] * 3 == dh_factors[l - 1] || dh_factors[l] == dh_factors[l - 1],
+                           "Only gridspacing changes with factor 3 eg: 1<->3 or 9<->3 are alowed");
+        }
+        VarGrid vg;
+        vg.init(desc->nx, desc->ny, desc->dim == 2 ? 1 : desc->nz, vector<int>(dh_factors, dh_factors + nlayers), vector<int>(interfaces + 1, interfaces + nlayers));
+        if (fd_orders)
+            vg.fdOrder.assign(fd_orders, fd_orders + nlayers);
+        for (int o : vg.fdOrder)
+            ORACLE_REQUIRE(o >= 2 && o <= WS_MAXQ_ORACLE && o % 2 == 0, "Unsupported spatialFDorder value.");
+        auto h = std::make_unique<Handle>();
+        h->precision = precision;
+        if (precision == 64) {
+            h->dd = std::make_unique<Oracle<double>>();
+            h->dd->vg = vg;
+            h->dd->create(*desc);
+        } else {
+            h->f = std::make_unique<Oracle<float>>();
+            h->f->vg = vg;
+            h->f->create(*desc);
+        }
+        *out = reinterpret_cast<wso_solver *>(h.release());
+    });
+}
+int wso_grid_size(wso_solver *s, int32_t *nx, int32_t *ny, int32_t *nz, int32_t *n)
+{
+    Handle *h = reinterpret_cast<Handle *>(s);
+    return guard([&] { DISPATCH(h, { *nx = o.NX; *ny = o.NY; *nz = o.NZ; *n = o.N; }); });
+}
+int wso_coordinate2index(wso_solver *s, int32_t x, int32_t y, int32_t z, int32_t *index)
+{
+    Handle *h = reinterpret_cast<Handle *>(s);
+    return guard([&] { DISPATCH(h, *index = o.index(x, y, z)); });
 }
 void wso_destroy(wso_solver *s) { delete reinterpret_cast<Handle *>(s); }
 

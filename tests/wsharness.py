@@ -83,6 +83,28 @@ class Oracle(SolverBase):
         return Oracle.lib.wso_num_threads()
 
 
+class OracleVarGrid(Oracle):
+    """Oracle on a variable grid / with variable FD orders (gridConfig columns: interface, dhFactor, FDorder)."""
+
+    def __init__(self, desc, interfaces, dh_factors, fd_orders=None, precision=32):
+        Oracle.num_threads()  # loads the library
+        self.desc = desc
+        self.h = C.c_void_p()
+        self.n_rec = 0
+        n = len(interfaces)
+        ii, dd = _i32(interfaces), _i32(dh_factors)
+        oo = _i32(fd_orders) if fd_orders is not None else None
+        self._check(self.lib.wso_create_vargrid(C.byref(desc), precision, n, _ip(ii), _ip(dd), _ip(oo) if oo is not None else None, C.byref(self.h)), "create_vargrid")
+        v = [C.c_int32() for _ in range(4)]
+        self._check(self.lib.wso_grid_size(self.h, *[C.byref(x) for x in v]), "grid_size")
+        self.nx, self.ny, self.nz, self.n_local = (x.value for x in v)
+
+    def index(self, x, y, z=0):
+        out = C.c_int32()
+        self._check(self.lib.wso_coordinate2index(self.h, int(x), int(y), int(z), C.byref(out)), "coordinate2index")
+        return out.value
+
+
 def ricker(nt, dt, fc, amp, tshift=0.0):
     """Acquisition/SourceSignal/Ricker.cpp:29-53 evaluated by the oracle library in float."""
     build_oracle()
