@@ -31,6 +31,84 @@ def test_oracle_reproduces_reference_golden(name, nt):
     assert reference_gate(s, g) <= 5.0e-7
 
 
+VARGRID = dict(interfaces=[0, 30, 150, 200], dh_factors=[1, 3, 1, 3], fd_orders=[2, 6, 2, 6])  # par/ci/gridConfig.txt
+
+
+def vargrid_ci_case(dim, nt, edge_policy=0):
+    """par/ci/configuration_ci.{2D,3D}.acoustic.varGrid.txt: variable grid (dhFactor 1/3/1/3) with variable FD order (2/6/2/6),
+    free surface + CPML(30), DH 17, homogeneous vp 3500 / rho 2000, P source and four P receivers at increasing depth."""
+    from wsharness import OracleVarGrid, make_desc, ricker
+    common = dict(dh=17.0, dt=2e-3, nt=nt, fd_order=2, edge_policy=edge_policy, free_surface=1, damping=2, boundary_width=30, vmax_cpml=3500.0, fc_cpml=5.0, npower=4.0)
+    if dim == 2:
+        d = make_desc(2, "acoustic", 305, 303, 1, **common)
+        src, recs, g = (150, 20, 0), [(150, 20, 0), (150, 90, 0), (150, 170, 0), (150, 239, 0)], "seismogram.2D.acoustic.varGrid.ref.p.mtx"
+    else:
+        d = make_desc(3, "acoustic", 104, 303, 104, **common)
+        src, recs, g = (50, 20, 50), [(50, 20, 50), (51, 90, 51), (50, 170, 50), (51, 239, 51)], "seismogram.3D.acoustic.varGrid.ref.p.mtx"
+    o = OracleVarGrid(d, VARGRID["interfaces"], VARGRID["dh_factors"], VARGRID["fd_orders"])
+    o.set_material("velocityP", np.full(o.n_local, 3500.0, np.float32))
+    o.set_material("density", np.full(o.n_local, 2000.0, np.float32))
+    o.prepare()
+    o.set_sources([1], [o.index(*src)], ricker(1000, 2e-3, 5.0, 5.0, 0.0)[None, :nt])
+    o.set_receivers([1] * 4, [o.index(*r) for r in recs])
+    o.reset()
+    return o, g
+
+
+@pytest.mark.parametrize("dim,nt", [(2, 1000), (3, 1000)], ids=["2D", "3D"])
+def test_oracle_reproduces_variable_grid_goldens(dim, nt):
+    """The two variable-grid goldens are the only reference fixtures that exercise CPML (and the acoustic free surface).  With
+    the truncating edge policy the oracle passes the reference's own CI gate (Test_CompareSeismogram.cpp:84) on both and
+    reproduces the 2-D traces to 3e-5 .. 6e-4 relative L2 each (the source-depth trace of the 3-D case to 6e-5).  What is
+    NOT reproduced to the goldens' 6 digits: the transmission through the coarse -> fine interface (3-5e-4) and, in the
+    3-D case, the deep traces of the 44-cell-wide tube between the CPML layers (3-6 %, within the gate because they are 200x
+    weaker than the shallow trace): like the regular-grid goldens these files predate details of the current assembly
+    (the literal order reduction of the calc* loops misses them by 7e-3, test below)."""
+    nt = 1000 if FULL else nt
+    o, gname = vargrid_ci_case(dim, nt)
+    assert (o.nx, o.ny, o.nz) == ((305, 303, 1) if dim == 2 else (104, 303, 104))
+    o.run(0, nt)
+    s = o.seismogram()
+    g = golden(gname)[:, :nt]
+    assert reference_gate(s, g) <= 5.0e-7, reference_gate(s, g)
+    per_trace = [rel_l2(s[k], g[k]) for k in range(4)]
+    print("variable grid %dD: gate %.2e total rel L2 %.2e per trace %s" % (dim, reference_gate(s, g), rel_l2(s, g), ["%.1e" % v for v in per_trace]))
+    assert per_trace[0] <= 1.0e-4
+    if dim == 2:
+        assert rel_l2(s, g) <= 1.0e-4 and max(per_trace) <= 8.0e-4
+        # up to the arrival of the wave transmitted through the coarse -> fine interface the traces agree to the goldens' digits
+        assert rel_l2(s[1][:450], g[1][:450]) <= 1.0e-5 and rel_l2(s[0][:700], g[0][:700]) <= 1.0e-5
+    else:
+        assert rel_l2(s, g) <= 5.0e-4 and max(per_trace) <= 8.0e-2
+
+
+def test_variable_grid_literal_order_reduction_differs_from_golden():
+    o, gname = vargrid_ci_case(2, 1000, edge_policy=1)
+    o.run(0, 1000)
+    assert rel_l2(o.seismogram(), golden(gname)) > 3.0e-3
+
+
+def test_variable_grid_code_equals_regular_code_on_one_layer():
+    """dhFactor 1 and one FD order everywhere: the layered assembly must give the regular sparse assembly bit for bit."""
+    from wsharness import OracleVarGrid, idx1d, make_desc, ricker
+    nt = 200
+    res = []
+    for var in (False, True):
+        d = make_desc(2, "acoustic", 80, 70, 1, dh=17.0, dt=2e-3, nt=nt, fd_order=4, edge_policy=1, free_surface=1, damping=2, boundary_width=10, vmax_cpml=3500.0,
+                      fc_cpml=5.0, npower=4.0)
+        o = OracleVarGrid(d, [0, 20, 40], [1, 1, 1], [4, 4, 4]) if var else Oracle(d)
+        n = 80 * 70
+        o.set_material("velocityP", np.full(n, 3500.0, np.float32))
+        o.set_material("density", np.full(n, 2000.0, np.float32))
+        o.prepare()
+        o.set_sources([1], [idx1d(40, 10, 0, 80, 1)], ricker(nt, 2e-3, 5.0, 5.0, 0.0)[None, :])
+        o.set_receivers([1, 1], [idx1d(40, 30, 0, 80, 1), idx1d(10, 60, 0, 80, 1)])
+        o.reset()
+        o.run(0, nt)
+        res.append(o.seismogram())
+    assert np.abs(res[0]).max() > 0 and np.array_equal(res[0], res[1])
+
+
 def test_order_reducing_policy_differs_from_golden():
     """Documents that the literal restatement of the sparse assembly (order reduction) is NOT what produced the goldens."""
     case = ci_case("2D.elastic", nt=600)
