@@ -143,6 +143,29 @@ int ws_comm_init(ws_solver *s, const void *id128);
 typedef int (*ws_sendrecv_fn)(void *user, const float *send, float *recv, size_t count, int peer);
 int ws_comm_init_external(ws_solver *s, ws_sendrecv_fn fn, void *user);
 
+/* --- operator-given mode: irregular grids ------------------------------------------------------------- *
+ * On a variable grid (layers of spacing 3^n DH, Acquisition/Coordinates.cpp:115-247) or with a variable FD order the reference's
+ * derivative matrices are no stencils: it assembles them point by point (ForwardSolver/Derivatives/Derivatives.cpp:129-1243) together
+ * with interpolation matrices for the interface planes (:1252-1566), and its boundary profiles are per-point sparse vectors
+ * (BoundaryCondition/CPML2DAcoustic.cpp:99-200).  The host layer (wave-simulation_b200/host/) assembles the same rows and hands
+ * them over here; the library then runs the reference's statement sequence (ForwardSolver{2D,3D}acoustic.cpp run()) with one
+ * fused gather kernel per half-step.  Acoustic solvers; one GPU per shot.  All vectors hold n_points values in the model's own
+ * order (Coordinates::index2coordinate), source / receiver indices are model-vector indices.
+ * ws_create_sparse replaces ws_create; the model parameters the kernels read ("pWaveModulus", "inverseDensityAverageX|Y|Z") are
+ * given with ws_set_material; ws_prepare only checks that everything is there.                                                   */
+int ws_create_sparse(const ws_desc *desc, int64_t n_points, ws_solver **out);
+/* operator rows in ELL form: cols / vals are n_points x max_taps row-major, columns ascending, unused entries cols = -1.
+ * name: "Dxf" "Dxb" "Dyf" "Dyb" "Dzf" "Dzb"; values already carry DT (FDTD2D.cpp:213-216).  With FreeSurface = 1 the acoustic
+ * solvers use DyfFreeSurface in place of Dyf (ForwardSolver2Dacoustic.cpp:141-146): pass that matrix as "Dyf".                    */
+int ws_set_operator(ws_solver *s, const char *name, int32_t max_taps, const int32_t *cols, const float *vals);
+/* interpolation matrices "InterpolationFull" "InterpolationStaggeredX" "InterpolationStaggeredZ": only the n_rows rows that are not
+ * identity rows (the points of the interface planes), rows[] = their model-vector indices.                                        */
+int ws_set_interpolation(ws_solver *s, const char *name, int64_t n_rows, const int32_t *rows, int32_t max_taps, const int32_t *cols, const float *vals);
+/* CPML coefficients of one axis (0 x, 1 y, 2 z) as the reference's sparse vectors a, b, a_half, b_half on the points idx[]        */
+int ws_set_cpml_profile(ws_solver *s, int32_t axis, int64_t n, const int32_t *idx, const float *a, const float *b, const float *a_half, const float *b_half);
+/* points of the free surface (FreeSurface::setSurfaceZero, FreeSurface.cpp:13-20)                                                 */
+int ws_set_surface(ws_solver *s, int64_t n, const int32_t *idx);
+
 /* --- instrumentation --------------------------------------------------------------------------------------------- */
 /* number of kernel launches issued by this handle since creation */
 uint64_t ws_launch_count(const ws_solver *s);

@@ -780,7 +780,7 @@ struct Oracle {
             };
             if (lowX && lowZ)
                 push(x - modx, z - modz, (T)((f - modx) * (f - modz)) * denom);
-            if (lowZ && x + kx * fFine < NX)
+            if (x + kx * fFine < NX)
                 push(x + f - modx, z - modz, (T)(modx * (f - modz)) * denom);
             if (lowX && z + kz * fFine < NZ)
                 push(x - modx, z + f - modz, (T)((f - modx) * modz) * denom);

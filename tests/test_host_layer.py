@@ -431,3 +431,123 @@ def test_driver_sources_from_su(driver, tmp_path):
     # the SU sources carry shot number 0 (the reference value-initialises the settings it does not read from the headers)
     _, again = read_su(os.path.join(tmp, "seismograms", "seismogram.shot_0.vy.su"))
     assert np.array_equal(again, first)
+
+
+CONFIG_VARGRID = """# par/ci/configuration_ci.{dim}.acoustic.varGrid.txt of the reference, transcribed (+ edgePolicy / exactArithmetic, B200 extensions)
+dimension={dim}
+equationType=acoustic
+useVariableGrid=1
+partitioning=2
+useVariableFDoperators=1
+gridConfigurationFilename=gridConfig.txt
+NX={nx}
+NY=303
+NZ={nz}
+NumShotDomains=1
+DH=17
+DT=2.0e-03
+T={T}
+spatialFDorder=2
+ModelRead=0
+ModelFilename=model/model
+FileFormat=1
+FreeSurface=1
+DampingBoundary=2
+BoundaryWidth=30
+DampingCoeff=8.0
+VMaxCPML=3500.0
+CenterFrequencyCPML=5.0
+NPower=4.0
+numRelaxationMechanisms=0
+relaxationFrequency=0
+velocityP=3500
+velocityS=2000
+rho=2000
+tauP=0.0
+tauS=0.0
+SourceFilename=acq/sources
+ReceiverFilename=acq/receiver
+SeismogramFilename=seismograms/seismogram
+SeismogramFormat=2
+initSourcesFromSU=0
+initReceiverFromSU=0
+seismoDT=2.0e-03
+normalizeTraces=0
+useReceiversPerShot=0
+writeSource=0
+snapType=0
+WavefieldFileName=wavefields/wavefield
+tFirstSnapshot=0
+tLastSnapshot=2
+tIncSnapshot=0.05
+verbose=0
+edgePolicy={pol}
+exactArithmetic={exact}
+"""
+
+
+def setup_vargrid_case(tmp, dim, T, pol=0, exact=1):
+    for d in ("acq", "seismograms"):
+        os.makedirs(os.path.join(tmp, d), exist_ok=True)
+    open(os.path.join(tmp, "gridConfig.txt"), "w").write("#interface\tdhfactor\tFDOrder\n0\t\t1\t\t2\n30\t\t3\t\t6\n150\t\t1\t\t2\n200\t\t3\t\t6\t\n")
+    if dim == 2:
+        src, rec, nx, nz = "0 150 20 0 1 1 1 5.0 5.0 0.0\n", "150 20  0 1\n150 90  0 1\n150 170 0 1\n150 239 0 1\n", 305, 1
+    else:
+        src, rec, nx, nz = "0 50 20 50 1 1 1 5.0 5.0 0.0\n", "50 20  50 1\n51 90  51 1\n50 170 50 1\n51 239 51 1\n", 104, 104
+    open(os.path.join(tmp, "acq", "sources.txt"), "w").write(src)
+    open(os.path.join(tmp, "acq", "receiver.txt"), "w").write(rec)
+    cfg = os.path.join(tmp, "configuration.txt")
+    open(cfg, "w").write(CONFIG_VARGRID.format(dim="%dD" % dim, nx=nx, nz=nz, T=T, pol=pol, exact=exact))
+    return cfg
+
+
+def _oracle_vargrid(dim, nt, pol=0):
+    from test_oracle_golden import vargrid_ci_case
+    o, gname = vargrid_ci_case(dim, nt, edge_policy=pol)
+    o.run(0, nt)
+    s = o.seismogram()
+    o.close()
+    return s, gname
+
+
+def test_driver_variable_grid_2d_reproduces_oracle_and_golden(driver, tmp_path):
+    """useVariableGrid=1 + useVariableFDoperators=1: the host layer assembles the operators of the layered
+    grid (IrregularGrid.cpp), the library runs them in operator-given mode.  In exact-arithmetic mode the seismogram is
+    bit-identical to the oracle's, and with the truncating edge policy it passes the reference's CI gate against
+    par/ci/seismogram.2D.acoustic.varGrid.ref.p.mtx (emulated library here; test_product_driver_variable_grid_on_gpu runs the CUDA one)."""
+    from wsharness import reference_gate
+    tmp = str(tmp_path)
+    cfg = setup_vargrid_case(tmp, 2, 2)
+    run(driver, cfg, tmp)
+    s = read_lmf_matrix(os.path.join(tmp, "seismograms", "seismogram.shot_0.p.lmf"))
+    ref, gname = _oracle_vargrid(2, 1000)
+    assert s.shape == (4, 1000) and np.abs(s).max() > 0
+    assert np.array_equal(s, ref)
+    assert reference_gate(s, golden(gname)) <= 5.0e-7
+    # the literal order reduction of the reference's current assembly (edgePolicy follows useStencilMatrix = 0 by default)
+    cfg = setup_vargrid_case(tmp, 2, 0.6, pol=1)
+    run(driver, cfg, tmp)
+    s = read_lmf_matrix(os.path.join(tmp, "seismograms", "seismogram.shot_0.p.lmf"))
+    ref, _ = _oracle_vargrid(2, 300, pol=1)
+    assert np.array_equal(s, ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dim,T", [(2, 2), (3, 2)])
+def test_product_driver_variable_grid_on_gpu(tmp_path, dim, T):
+    """The product binary on the reference's two variable-grid CI cases: bit-identical to the oracle in exact-arithmetic mode,
+    within the reference's CI gate of the goldens; the default (FMA) arithmetic stays within 1e-5 of the exact one."""
+    from wsharness import reference_gate
+    subprocess.check_call(["make", "-s", "-C", HOST])
+    tmp = str(tmp_path)
+    nt = 1000
+    cfg = setup_vargrid_case(tmp, dim, T)
+    _run_product(cfg, tmp, {"WS_NUM_GPUS": "1"})
+    s = read_lmf_matrix(os.path.join(tmp, "seismograms", "seismogram.shot_0.p.lmf"))
+    ref, gname = _oracle_vargrid(dim, nt)
+    assert np.array_equal(s, ref)
+    assert reference_gate(s, golden(gname)) <= 5.0e-7
+    cfg = setup_vargrid_case(tmp, dim, T, exact=0)
+    _run_product(cfg, tmp, {"WS_NUM_GPUS": "1"})
+    f = read_lmf_matrix(os.path.join(tmp, "seismograms", "seismogram.shot_0.p.lmf"))
+    assert rel_l2(f, s) <= 1.0e-5

@@ -29,6 +29,7 @@ struct WsError : public std::exception {
 #include "ws_prepare.cuh"
 #include "ws_tables.hpp"
 #include "ws_kernels_tma.cuh" // operand table (wsmarch::spec) and the TMA program type
+#include "ws_kernels_sparse.cuh"
 
 namespace {
 
@@ -325,6 +326,19 @@ struct ws_solver {
     bool useFastA = false; // 3-D viscoelastic: the velocity half-step runs the tiled elastic kernel (same statements)
     bool useMarch = false; // marching kernels (ws_kernels_march.cu) serve this configuration
     void *fastMaps = nullptr;
+    // operator-given mode (ws_create_sparse): irregular grids, the operators come from the caller in ELL form
+    bool sparse = false;
+    struct Interp {
+        long long nrows = 0;
+        int taps = 0;
+        DevBuf<int> rows, cols;
+        DevBuf<float> vals;
+    };
+    DevBuf<int> spCol[wssparse::SP_NOPS], spCpK[3], spSurf;
+    DevBuf<float> spVal[wssparse::SP_NOPS], spCa[3], spCb[3], spCah[3], spCbh[3], spPsi[wssparse::SPSI_COUNT], spTmp;
+    int spTaps[wssparse::SP_NOPS] = {};
+    long long spSurfN = 0;
+    Interp spInterp[3]; // full grid, staggered in x, staggered in z
     // CUDA graph of one time step
     cudaGraphExec_t graphExec = nullptr;
     int graphSteps = 0;
@@ -1042,10 +1056,88 @@ void launchAcquisition(ws_solver *s, const float *srcStepDev, float *recStepDev)
 }
 
 // one reference time step = ForwardSolver::run(...), enqueued asynchronously
+// ---------------------------------------------------------------------------------------------------------------------
+// operator-given mode (ws_kernels_sparse.cuh)
+// ---------------------------------------------------------------------------------------------------------------------
+wssparse::Params sparseParams(ws_solver *s)
+{
+    wssparse::Params Q{};
+    Q.n = s->nx;
+    Q.dim = s->d.dim;
+    for (int k = 0; k < wssparse::SP_NOPS; k++) {
+        Q.col[k] = s->spCol[k].p;
+        Q.val[k] = s->spVal[k].p;
+        Q.taps[k] = s->spTaps[k];
+    }
+    for (int a = 0; a < 3; a++) {
+        Q.cpK[a] = s->spCpK[a].p;
+        Q.ca[a] = s->spCa[a].p; Q.cb[a] = s->spCb[a].p; Q.cah[a] = s->spCah[a].p; Q.cbh[a] = s->spCbh[a].p;
+    }
+    for (int k = 0; k < wssparse::SPSI_COUNT; k++)
+        Q.psi[k] = s->spPsi[k].p;
+    Q.vx = s->fld[F_VX].p; Q.vy = s->fld[F_VY].p; Q.vz = s->fld[F_VZ].p; Q.p = s->fld[F_P].p;
+    Q.rix = s->mat[M_RIX].p; Q.riy = s->mat[M_RIY].p; Q.riz = s->mat[M_RIZ].p; Q.pw = s->mat[M_PW].p;
+    return Q;
+}
+
+void sparseInterpolate(ws_solver *s, int which, float *field)
+{
+    ws_solver::Interp &I = s->spInterp[which];
+    if (I.nrows == 0)
+        return;
+    const unsigned nb = (unsigned)((I.nrows + 255) / 256);
+    if (s->exact)
+        WS_LAUNCH(wssparse::kInterpGather<true>, nb, 256, 0, s->stream, I.nrows, I.taps, I.cols.p, I.vals.p, field, s->spTmp.p);
+    else
+        WS_LAUNCH(wssparse::kInterpGather<false>, nb, 256, 0, s->stream, I.nrows, I.taps, I.cols.p, I.vals.p, field, s->spTmp.p);
+    WS_LAUNCH(wssparse::kInterpScatter, nb, 256, 0, s->stream, I.nrows, I.rows.p, s->spTmp.p, field);
+    s->launches += 2;
+}
+
+// one time step on an irregular grid: ForwardSolver2Dacoustic.cpp:121-190 / ForwardSolver3Dacoustic.cpp:131-229 incl. the
+// interpolation of the interface planes after every update
+void enqueueSparseStep(ws_solver *s, const float *srcStepDev, float *recStepDev, cudaEvent_t *ev)
+{
+    const wssparse::Params Q = sparseParams(s);
+    const unsigned nb = (unsigned)((Q.n + 255) / 256);
+    if (ev)
+        WS_CUDA_CHECK(cudaEventRecord(ev[0], s->stream));
+    if (s->exact)
+        WS_LAUNCH(wssparse::kVelAcoustic<true>, nb, 256, 0, s->stream, Q);
+    else
+        WS_LAUNCH(wssparse::kVelAcoustic<false>, nb, 256, 0, s->stream, Q);
+    s->launches++;
+    sparseInterpolate(s, 1, Q.vx);
+    sparseInterpolate(s, 0, Q.vy);
+    if (Q.dim == 3)
+        sparseInterpolate(s, 2, Q.vz);
+    if (ev) {
+        WS_CUDA_CHECK(cudaEventRecord(ev[1], s->stream));
+        WS_CUDA_CHECK(cudaEventRecord(ev[2], s->stream));
+    }
+    if (s->exact)
+        WS_LAUNCH(wssparse::kPressure<true>, nb, 256, 0, s->stream, Q);
+    else
+        WS_LAUNCH(wssparse::kPressure<false>, nb, 256, 0, s->stream, Q);
+    s->launches++;
+    sparseInterpolate(s, 0, Q.p);
+    if (s->spSurfN > 0) {
+        WS_LAUNCH(wssparse::kSurfaceZero, (unsigned)((s->spSurfN + 255) / 256), 256, 0, s->stream, s->spSurfN, s->spSurf.p, Q.p);
+        s->launches++;
+    }
+    if (ev)
+        WS_CUDA_CHECK(cudaEventRecord(ev[3], s->stream));
+    launchAcquisition(s, srcStepDev, recStepDev);
+}
+
 // haloLanded: the halo exchange of the previous step is known to have completed (first step of a captured graph: the
 // wait happened on the stream before the graph was launched)
 void enqueueStep(ws_solver *s, const float *srcStepDev, float *recStepDev, cudaEvent_t *ev /* 4 events or null */, bool haloLanded = false)
 {
+    if (s->sparse) {
+        enqueueSparseStep(s, srcStepDev, recStepDev, ev);
+        return;
+    }
     const bool multi = s->d.nranks > 1;
     const int h = s->h, n = s->nyl;
     const cudaEvent_t evCompute = s->capturing ? s->evComputeG : s->evCompute, evComm = s->capturing ? s->evCommG : s->evComm;
@@ -1175,11 +1267,30 @@ size_t ws_estimate_memory(const ws_desc *desc)
     return bytes;
 }
 
-int ws_create(const ws_desc *desc, ws_solver **out)
+static int createImpl(const ws_desc *desc, long long sparseN, ws_solver **out)
 {
     return guarded([&] {
         WS_REQUIRE(desc && out, WS_EINVAL, "null argument");
-        validateDesc(*desc);
+        ws_desc local = *desc;
+        if (sparseN > 0) {
+            // operator-given mode: the model vector is one row of n_points values; geometry-dependent keys are the caller's business
+            WS_REQUIRE(sparseN < (1LL << 31), WS_EINVAL, "n_points exceeds int32 indices (scai::IndexType)");
+            WS_REQUIRE(local.eq == WS_EQ_ACOUSTIC, WS_EINVAL, "operator-given mode (variable grid) is available for the acoustic solvers");
+            WS_REQUIRE(local.nranks <= 1, WS_EINVAL, "operator-given mode runs on one GPU per shot");
+            WS_REQUIRE(local.damping == 0 || local.damping == 2, WS_EINVAL, "operator-given mode: DampingBoundary must be 0 or 2 (CPML)");
+            local.nx = (int32_t)sparseN;
+            local.ny = 1;
+            local.nz = 1;
+            local.boundary_width = 0;
+            if (local.fd_order < 2 || local.fd_order > WS_MAXQ || local.fd_order % 2)
+                local.fd_order = 2; // per-layer orders live in the operators
+            const int keepDamping = local.damping;
+            local.damping = 0;
+            validateDesc(local);
+            local.damping = keepDamping;
+        } else
+            validateDesc(local);
+        desc = &local;
         int ndev = 0;
         cudaError_t e = cudaGetDeviceCount(&ndev);
         WS_REQUIRE(e == cudaSuccess && ndev > 0, WS_ECUDA,
@@ -1204,6 +1315,13 @@ int ws_create(const ws_desc *desc, ws_solver **out)
             s->plane = (long long)s->pitch * s->nzp;
             s->total = s->plane * (s->nyl + 2 * WS_HALO);
             s->base = WS_PADX + (long long)(s->nzp > 1 ? WS_HALO : 0) * s->pitch + (long long)WS_HALO * s->plane;
+            if (sparseN > 0) { // no pads: the arrays ARE the model vectors
+                s->sparse = true;
+                s->pitch = s->nx;
+                s->plane = s->nx;
+                s->total = s->nx;
+                s->base = 0;
+            }
             WS_CUDA_CHECK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
             WS_CUDA_CHECK(cudaStreamCreateWithFlags(&s->commStream, cudaStreamNonBlocking));
             WS_CUDA_CHECK(cudaEventCreateWithFlags(&s->evCompute, cudaEventDisableTiming));
@@ -1313,6 +1431,16 @@ int ws_create(const ws_desc *desc, ws_solver **out)
     });
 }
 
+int ws_create(const ws_desc *desc, ws_solver **out) { return createImpl(desc, 0, out); }
+int ws_create_sparse(const ws_desc *desc, int64_t n_points, ws_solver **out)
+{
+    if (n_points <= 0) {
+        g_lastError = "n_points must be positive";
+        return WS_EINVAL;
+    }
+    return createImpl(desc, n_points, out);
+}
+
 void ws_destroy(ws_solver *s)
 {
     if (!s)
@@ -1382,6 +1510,25 @@ int ws_prepare(ws_solver *s)
         WS_REQUIRE(s, WS_EINVAL, "null argument");
         setDevice(s);
         invalidateGraph(s);
+        if (s->sparse) {
+            // the caller supplies the operators and the prepareForModelling products of its irregular grid
+            const int nop = s->d.dim == 3 ? 6 : 4;
+            static const int need2[4] = {wssparse::SP_XF, wssparse::SP_XB, wssparse::SP_YF, wssparse::SP_YB};
+            for (int k = 0; k < 4; k++)
+                WS_REQUIRE(s->spCol[need2[k]].p, WS_ESTATE, "operator-given mode: Dxf, Dxb, Dyf and Dyb must be set (ws_set_operator)");
+            if (nop == 6)
+                WS_REQUIRE(s->spCol[wssparse::SP_ZF].p && s->spCol[wssparse::SP_ZB].p, WS_ESTATE, "operator-given mode: Dzf and Dzb must be set (ws_set_operator)");
+            requireMat(s, M_PW, "pWaveModulus");
+            requireMat(s, M_RIX, "inverseDensityAverageX");
+            requireMat(s, M_RIY, "inverseDensityAverageY");
+            if (s->d.dim == 3)
+                requireMat(s, M_RIZ, "inverseDensityAverageZ");
+            refreshParams(s);
+            s->useFast = s->useFastA = s->useTma = s->useMarch = false;
+            WS_CUDA_CHECK(cudaStreamSynchronize(s->stream));
+            s->prepared = true;
+            return;
+        }
         if (s->seismic)
             prepareSeismic(s);
         else
@@ -1550,6 +1697,8 @@ int ws_reset(ws_solver *s)
             s->fld[k].zero(s->stream); // Wavefields::resetWavefields (Wavefields3Delastic.cpp:111-122)
         for (int k = 0; k < PSI_COUNT; k++)
             s->psi[k].zero(s->stream); // ForwardSolver::resetCPML (CPML3D.cpp:6-26)
+        for (int k = 0; k < wssparse::SPSI_COUNT; k++)
+            s->spPsi[k].zero(s->stream);
         s->seis.zero(s->stream);
         s->tdev.zero(s->stream);
         WS_CUDA_CHECK(cudaStreamSynchronize(s->stream));
@@ -1844,6 +1993,118 @@ int ws_is_finite(ws_solver *s, int32_t *flag)
             WS_CUDA_CHECK(cudaStreamSynchronize(s->stream));
         }
         *flag = bad ? 0 : 1;
+    });
+}
+
+// --- operator-given mode ---------------------------------------------------------------------------------------------
+namespace {
+// row-major host ELL (n x taps) -> column-major device arrays
+void uploadEll(long long n, int taps, const int32_t *cols, const float *vals, DevBuf<int> &dc, DevBuf<float> &dv)
+{
+    std::vector<int> c((size_t)n * taps);
+    std::vector<float> v((size_t)n * taps);
+    for (long long i = 0; i < n; i++)
+        for (int k = 0; k < taps; k++) {
+            c[(size_t)k * n + i] = cols[(size_t)i * taps + k];
+            v[(size_t)k * n + i] = vals[(size_t)i * taps + k];
+        }
+    dc.upload(c);
+    dv.upload(v);
+}
+} // namespace
+
+int ws_set_operator(ws_solver *s, const char *name, int32_t max_taps, const int32_t *cols, const float *vals)
+{
+    return guarded([&] {
+        WS_REQUIRE(s && name && cols && vals, WS_EINVAL, "null argument");
+        WS_REQUIRE(s->sparse, WS_ESTATE, "ws_set_operator needs a solver created with ws_create_sparse");
+        WS_REQUIRE(max_taps >= 1 && max_taps <= 64, WS_EINVAL, "max_taps out of range");
+        setDevice(s);
+        invalidateGraph(s);
+        static const char *names[wssparse::SP_NOPS] = {"Dxf", "Dxb", "Dyf", "Dyb", "Dzf", "Dzb"};
+        int op = -1;
+        for (int k = 0; k < wssparse::SP_NOPS; k++)
+            if (std::strcmp(name, names[k]) == 0)
+                op = k;
+        WS_REQUIRE(op >= 0, WS_EINVAL, std::string("unknown operator '") + name + "' (Dxf Dxb Dyf Dyb Dzf Dzb)");
+        const long long n = s->nx;
+        for (long long i = 0; i < n * max_taps; i++)
+            WS_REQUIRE(cols[i] >= -1 && cols[i] < n, WS_EINVAL, std::string("operator '") + name + "': column index out of range");
+        uploadEll(n, max_taps, cols, vals, s->spCol[op], s->spVal[op]);
+        s->spTaps[op] = max_taps;
+        s->prepared = false;
+    });
+}
+
+int ws_set_interpolation(ws_solver *s, const char *name, int64_t n_rows, const int32_t *rows, int32_t max_taps, const int32_t *cols, const float *vals)
+{
+    return guarded([&] {
+        WS_REQUIRE(s && name && (n_rows == 0 || (rows && cols && vals)), WS_EINVAL, "null argument");
+        WS_REQUIRE(s->sparse, WS_ESTATE, "ws_set_interpolation needs a solver created with ws_create_sparse");
+        WS_REQUIRE(n_rows >= 0 && max_taps >= 1 && max_taps <= 64, WS_EINVAL, "invalid interpolation size");
+        setDevice(s);
+        invalidateGraph(s);
+        static const char *names[3] = {"InterpolationFull", "InterpolationStaggeredX", "InterpolationStaggeredZ"};
+        int w = -1;
+        for (int k = 0; k < 3; k++)
+            if (std::strcmp(name, names[k]) == 0)
+                w = k;
+        WS_REQUIRE(w >= 0, WS_EINVAL, std::string("unknown interpolation '") + name + "'");
+        ws_solver::Interp &I = s->spInterp[w];
+        I.nrows = n_rows;
+        I.taps = max_taps;
+        if (n_rows == 0)
+            return;
+        for (int64_t r = 0; r < n_rows; r++)
+            WS_REQUIRE(rows[r] >= 0 && rows[r] < s->nx, WS_EINVAL, "interpolation row out of range");
+        for (int64_t i = 0; i < n_rows * max_taps; i++)
+            WS_REQUIRE(cols[i] >= -1 && cols[i] < s->nx, WS_EINVAL, "interpolation column out of range");
+        I.rows.upload(std::vector<int>(rows, rows + n_rows));
+        uploadEll(n_rows, max_taps, cols, vals, I.cols, I.vals);
+        if ((long long)s->spTmp.n < n_rows)
+            s->spTmp.alloc((size_t)n_rows);
+    });
+}
+
+int ws_set_cpml_profile(ws_solver *s, int32_t axis, int64_t n, const int32_t *idx, const float *a, const float *b, const float *a_half, const float *b_half)
+{
+    return guarded([&] {
+        WS_REQUIRE(s && (n == 0 || (idx && a && b && a_half && b_half)), WS_EINVAL, "null argument");
+        WS_REQUIRE(s->sparse, WS_ESTATE, "ws_set_cpml_profile needs a solver created with ws_create_sparse");
+        WS_REQUIRE(axis >= 0 && axis < 3 && n >= 0, WS_EINVAL, "invalid axis");
+        setDevice(s);
+        invalidateGraph(s);
+        std::vector<int> k((size_t)s->nx, -1);
+        for (int64_t e = 0; e < n; e++) {
+            WS_REQUIRE(idx[e] >= 0 && idx[e] < s->nx && k[idx[e]] < 0, WS_EINVAL, "CPML profile: index out of range or listed twice");
+            k[idx[e]] = (int)e;
+        }
+        s->spCpK[axis].upload(k);
+        s->spCa[axis].upload(std::vector<float>(a, a + n));
+        s->spCb[axis].upload(std::vector<float>(b, b + n));
+        s->spCah[axis].upload(std::vector<float>(a_half, a_half + n));
+        s->spCbh[axis].upload(std::vector<float>(b_half, b_half + n));
+        // memory variables of the two terms of this axis: d/d(axis) of p, and of the velocity component along the axis
+        for (int slot : {wssparse::SPSI_P_X + axis, wssparse::SPSI_VXX + axis}) {
+            s->spPsi[slot].alloc((size_t)std::max<int64_t>(1, n));
+            s->spPsi[slot].zero(s->stream);
+        }
+        WS_CUDA_CHECK(cudaStreamSynchronize(s->stream));
+    });
+}
+
+int ws_set_surface(ws_solver *s, int64_t n, const int32_t *idx)
+{
+    return guarded([&] {
+        WS_REQUIRE(s && (n == 0 || idx), WS_EINVAL, "null argument");
+        WS_REQUIRE(s->sparse, WS_ESTATE, "ws_set_surface needs a solver created with ws_create_sparse");
+        setDevice(s);
+        invalidateGraph(s);
+        for (int64_t e = 0; e < n; e++)
+            WS_REQUIRE(idx[e] >= 0 && idx[e] < s->nx, WS_EINVAL, "surface index out of range");
+        s->spSurfN = n;
+        if (n > 0)
+            s->spSurf.upload(std::vector<int>(idx, idx + n));
     });
 }
 

@@ -23,13 +23,25 @@ namespace KITGPI
 
             void init(Configuration::Configuration const &config);
             void init(IndexType nx, IndexType ny, IndexType nz, ValueType dh);
+            //! variable grid / variable FD order: layers of spacing dhFactor * DH below the interfaces (Coordinates.cpp:115-247);
+            //! `interfaces` without the leading 0 of the gridConfig file
+            void init(IndexType nx, IndexType ny, IndexType nz, ValueType dh, std::vector<IndexType> const &dhFactors, std::vector<IndexType> const &interfaces);
 
             IndexType getNX() const { return NX; }
             IndexType getNY() const { return NY; }
             IndexType getNZ() const { return NZ; }
             ValueType getDH() const { return DH; }
-            IndexType getNGridpoints() const { return NX * NY * NZ; }
-            bool isVariable() const { return false; }
+            IndexType getNGridpoints() const { return layered ? nGridpoints : NX * NY * NZ; }
+            //! true when the model vector is layered (useVariableGrid or useVariableFDoperators): the operators are assembled point by point
+            bool isVariable() const { return layered; }
+            bool hasVariableSpacing() const { return variableSpacing; }
+            IndexType getNumLayers() const { return layered ? (IndexType)dhFactor.size() : 1; }
+            IndexType getLayer(IndexType y) const;                    // Coordinates.cpp:383-398
+            IndexType getDHFactor(IndexType layer) const { return layered ? dhFactor[layer] : 1; }
+            ValueType getDH(IndexType layer) const { return DH * getDHFactor(layer); }
+            bool locatedOnInterface(IndexType y) const;               // :474-483
+            IndexType distToInterface(IndexType y) const;             // :490-499
+            int getTransition(IndexType y) const;                     // :517-530
 
             coordinate3D index2coordinate(IndexType index) const;
             IndexType coordinate2index(coordinate3D coordinate) const { return coordinate2index(coordinate.x, coordinate.y, coordinate.z); }
@@ -41,6 +53,11 @@ namespace KITGPI
             void check(IndexType X, IndexType Y, IndexType Z) const;
             IndexType NX, NY, NZ;
             ValueType DH;
+            bool layered = false, variableSpacing = false;
+            IndexType nGridpoints = 0;
+            std::vector<IndexType> dhFactor, interface, transition, layerStart, layerEnd, varNX, varNY, varNZ, nGridpointsPerLayer;
         };
+        //! one column of a whitespace-separated text file, '#' comments skipped (Common::readColumnFromFile)
+        std::vector<IndexType> readColumnFromFile(std::string const &filename, unsigned column);
     }
 }

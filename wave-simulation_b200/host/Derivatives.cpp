@@ -1,4 +1,5 @@
 #include "Derivatives.hpp"
+#include "Coordinates.hpp"
 #include <algorithm>
 
 using namespace KITGPI;
@@ -28,11 +29,20 @@ template <typename ValueType> std::vector<ValueType> Derivatives<ValueType>::cal
 
 template <typename ValueType> void Derivatives<ValueType>::init(Configuration::Configuration const &config)
 {
-    SCAI_ASSERT_ERROR(config.getAndCatch("useVariableGrid", 0) == 0, "useVariableGrid=1 is not available in the B200 path")
-    SCAI_ASSERT_ERROR(config.getAndCatch("useVariableFDoperators", 0) == 0, "useVariableFDoperators=1 is not available in the B200 path")
     spatialFDorder = config.get<IndexType>("spatialFDorder");
     FDCoef = calcFDCoef(spatialFDorder);
     useStencilMatrix = config.getAndCatch("useStencilMatrix", 0) != 0;
+    spatialFDorderVec.clear();
+    if (config.getAndCatch("useVariableFDoperators", 0) != 0) { // Derivatives.cpp:47-53
+        SCAI_ASSERT_ERROR(!useStencilMatrix, "Variable FD operators are not available for stencil matrices")
+        spatialFDorderVec = Acquisition::readColumnFromFile(config.get<std::string>("gridConfigurationFilename"), 2);
+        for (IndexType o : spatialFDorderVec)
+            calcFDCoef(o); // throws "Unsupported spatialFDorder value."
+    }
+    if (config.getAndCatch("useVariableGrid", 0) != 0)
+        SCAI_ASSERT_ERROR(!useStencilMatrix, "It is not possible to use the stencil matrix on a variable grid")
+    edgePolicy = config.getAndCatch("edgePolicy", useStencilMatrix ? 0 : 1);
+    SCAI_ASSERT_ERROR(edgePolicy == 0 || edgePolicy == 1, "edgePolicy must be 0 or 1")
     useFreeSurface = config.get<IndexType>("FreeSurface");
     SCAI_ASSERT_ERROR(useFreeSurface == 0 || useFreeSurface == 1, "FreeSurface=" << useFreeSurface << " (improved vacuum formulation) is not available in the B200 path")
 }

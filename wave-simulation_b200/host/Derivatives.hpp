@@ -23,10 +23,16 @@ namespace KITGPI
                 //! = setup(config) + init(dist, ctx, modelCoordinates, comm) of the reference (FDTD3D.cpp:51-61)
                 void init(Configuration::Configuration const &config);
                 IndexType getSpatialFDorder() const { return spatialFDorder; }
+                //! FD order of a layer of the grid (useVariableFDoperators: third column of gridConfigurationFilename, Derivatives.cpp:1663-1673)
+                IndexType getSpatialFDorder(IndexType layer) const { return spatialFDorderVec.empty() ? spatialFDorder : spatialFDorderVec.at(layer); }
+                bool getUseVarFDorder() const { return !spatialFDorderVec.empty(); }
                 bool getUseStencilMatrix() const { return useStencilMatrix; }
                 bool getUseFreeSurface() const { return useFreeSurface == 1; }
                 //! 0 = off-grid taps dropped (StencilMatrix), 1 = order reduced towards the edges (sparse assembly)
-                IndexType getEdgePolicy() const { return useStencilMatrix ? 0 : 1; }
+                //! 0: off-grid taps dropped (StencilMatrix), 1: order reduced towards the grid edges (sparse assembly, Derivatives.cpp:159-175).
+                //! Follows useStencilMatrix; the key edgePolicy (B200 extension) overrides it, e.g. to run a variable grid — where the
+                //! reference has sparse matrices only — with the dropped taps its golden seismograms were produced with.
+                IndexType getEdgePolicy() const { return edgePolicy; }
                 IndexType getNumDimension() const { return numDimension; }
                 //! Taylor coefficients of the staggered first derivative, spatialFDorder entries (setFDCoef)
                 std::vector<ValueType> const &getFDCoef() const { return FDCoef; }
@@ -36,7 +42,8 @@ namespace KITGPI
 
               private:
                 IndexType numDimension;
-                IndexType spatialFDorder = 0, useFreeSurface = 0;
+                IndexType spatialFDorder = 0, useFreeSurface = 0, edgePolicy = 1;
+                std::vector<IndexType> spatialFDorderVec;
                 bool useStencilMatrix = false;
                 std::vector<ValueType> FDCoef;
             };

@@ -111,6 +111,21 @@ void ForwardSolver::DeviceGroup::create(ws_desc desc)
     });
 }
 
+void ForwardSolver::DeviceGroup::createSparse(ws_desc desc, size_t nPoints)
+{
+    destroy();
+    // the reference partitions irregular grids with a graph partitioner; here a shot on an irregular grid runs on one GPU
+    SCAI_ASSERT_ERROR(size() == 1, "variable grids run on one GPU per shot domain (set GPUsPerShotDomain=1)")
+    desc.rank = 0;
+    desc.nranks = 1;
+    desc.device = devices[0];
+    check(ws_create_sparse(&desc, (int64_t)nPoints, &handles[0]));
+    planeSize = nPoints;
+    nGlobal = nPoints;
+    y0[0] = 0;
+    nyl[0] = 1;
+}
+
 void ForwardSolver::DeviceGroup::destroy()
 {
     bool any = false;

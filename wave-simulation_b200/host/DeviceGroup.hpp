@@ -31,6 +31,8 @@ namespace KITGPI
             void forEach(std::function<void(IndexType)> const &fn);
             //! ws_create for every rank of the group (desc.rank / nranks / device are filled in) + NCCL communicator
             void create(ws_desc desc);
+            //! operator-given mode (irregular grids): one GPU, model vectors of nPoints values (ws_create_sparse)
+            void createSparse(ws_desc desc, size_t nPoints);
             void destroy();
 
             size_t getNGlobal() const { return nGlobal; }

@@ -1,4 +1,5 @@
 #include "ForwardSolver.hpp"
+#include "IrregularGrid.hpp"
 #include "../../include/wavesim.h"
 #include <algorithm>
 #include <cstring>
@@ -33,7 +34,7 @@ namespace
         d.dt = config.get<ValueType>("DT");
         d.nt = Common::time2index(config.get<ValueType>("T"), d.dt); // Simulation.cpp:304
         d.fd_order = config.get<IndexType>("spatialFDorder");
-        d.edge_policy = config.getAndCatch("useStencilMatrix", 0) ? 0 : 1;
+        d.edge_policy = config.getAndCatch("edgePolicy", config.getAndCatch("useStencilMatrix", 0) ? 0 : 1);
         d.free_surface = config.get<IndexType>("FreeSurface") == 1 ? 1 : 0;
         d.damping = config.get<IndexType>("DampingBoundary");
         d.boundary_width = config.getAndCatch("BoundaryWidth", 0);
@@ -84,12 +85,79 @@ void ForwardSolver::ForwardSolver<ValueType>::initForwardSolver(Configuration::C
     group.reset(new DeviceGroup(deviceIds));
     ws_desc d = makeDesc(config, dimension, equationType, deviceIds[0]);
     d.dt = DT;
+    if (modelCoordinates.isVariable()) {
+        initIrregular(config, d, derivatives, wavefield, model, modelCoordinates);
+        return;
+    }
     group->create(d);
     NT = d.nt;
     SCAI_ASSERT_ERROR(group->getNGlobal() == (size_t)modelCoordinates.getNGridpoints(), "grid of the configuration and of the coordinates differ")
     // every rank receives the GLOBAL vectors and keeps its slab plus the ghost planes the averaging needs
     for (auto const &kv : model.getRawParameters())
         group->forEach([&](IndexType r) { check(ws_set_material(group->handle(r), kv.first.c_str(), kv.second.data(), kv.second.size())); });
+    wavefield.init(d.n_relax);
+    wavefield.bind(group.get());
+    model.bind(group.get());
+    srcVersion = recVersion = ~0ul;
+}
+
+// Variable grid / variable FD order: the operators are assembled here by the reference's rules (IrregularGrid.cpp) and handed to
+// the library (operator-given mode); replaces Derivatives::init + prepareBoundaryConditions + Modelparameter::prepareForModelling
+// of FDTD2D.cpp:186-232, CPML2DAcoustic.cpp:99-200, Acoustic.cpp prepareForModelling for this case.
+template <typename ValueType>
+void ForwardSolver::ForwardSolver<ValueType>::initIrregular(Configuration::Configuration const &config, ws_desc d, Derivatives::Derivatives<ValueType> &derivatives,
+                                                            Wavefields::Wavefields<ValueType> &wavefield, Modelparameter::Modelparameter<ValueType> &model,
+                                                            Acquisition::Coordinates<ValueType> const &mc)
+{
+    SCAI_ASSERT_ERROR(equationType == "acoustic", "variable grids / variable FD orders are available for the acoustic solvers (equationType=" << equationType << ")")
+    SCAI_ASSERT_ERROR(d.damping == 0 || d.damping == 2, "variable grid: DampingBoundary must be 0 or 2 (CPML)")
+    const size_t N = (size_t)mc.getNGridpoints();
+    group->createSparse(d, N);
+    NT = d.nt;
+    ws_solver *h = group->handle(0);
+    const bool d3 = dimension == "3d", fs = d.free_surface == 1;
+    IrregularOperators<ValueType> ops(mc, derivatives, d.dt);
+    auto setOp = [&](const char *name, EllRows const &m) { check(ws_set_operator(h, name, (int32_t)m.taps, m.cols.data(), m.vals.data())); };
+    setOp("Dxf", ops.derivative(0, true));
+    setOp("Dxb", ops.derivative(0, false));
+    setOp("Dyf", ops.derivative(1, true, fs)); // DyfFreeSurface takes the place of Dyf (ForwardSolver2Dacoustic.cpp:141-146)
+    setOp("Dyb", ops.derivative(1, false));
+    if (d3) {
+        setOp("Dzf", ops.derivative(2, true));
+        setOp("Dzb", ops.derivative(2, false));
+    }
+    if (mc.hasVariableSpacing()) {
+        const char *names[3] = {"InterpolationFull", "InterpolationStaggeredX", "InterpolationStaggeredZ"};
+        for (IndexType mode = 0; mode < (d3 ? 3 : 2); mode++) {
+            const EllRows m = ops.interpolation(mode);
+            check(ws_set_interpolation(h, names[mode], (int64_t)m.rows.size(), m.rows.data(), (int32_t)m.taps, m.cols.data(), m.vals.data()));
+        }
+    }
+    if (d.damping == 2)
+        for (IndexType axis = 0; axis < (d3 ? 3 : 2); axis++) {
+            const IndexType ax = (!d3 && axis == 1) ? 1 : axis; // 2-D: axes x, y
+            const CpmlProfile p = ops.cpml(ax, d.boundary_width, d.npower, d.fc_cpml, d.vmax_cpml, fs);
+            check(ws_set_cpml_profile(h, (int32_t)ax, (int64_t)p.idx.size(), p.idx.data(), p.a.data(), p.b.data(), p.aHalf.data(), p.bHalf.data()));
+        }
+    if (fs) {
+        const std::vector<int32_t> surf = ops.surfacePoints();
+        check(ws_set_surface(h, (int64_t)surf.size(), surf.data()));
+    }
+    // prepareForModelling products on the host: P-wave modulus rho vp^2 (ModelparameterSeismic.cpp:131-136), staggered inverse densities
+    auto const &vp = model.getVelocityP();
+    auto const &rho = model.getDensity();
+    SCAI_ASSERT_ERROR(vp.size() == N && rho.size() == N, "the model must hold one value per point of the variable grid")
+    std::vector<ValueType> pw(N);
+    for (size_t i = 0; i < N; i++)
+        pw[i] = (rho[i] * vp[i]) * vp[i];
+    check(ws_set_material(h, "pWaveModulus", pw.data(), N));
+    const char *avgNames[3] = {"inverseDensityAverageX", "inverseDensityAverageY", "inverseDensityAverageZ"};
+    for (IndexType axis = 0; axis < (d3 ? 3 : 2); axis++) {
+        const std::vector<ValueType> r = ops.inverseAverage(rho, axis);
+        check(ws_set_material(h, avgNames[axis], r.data(), N));
+    }
+    for (auto const &kv : model.getRawParameters())
+        check(ws_set_material(h, kv.first.c_str(), kv.second.data(), kv.second.size()));
     wavefield.init(d.n_relax);
     wavefield.bind(group.get());
     model.bind(group.get());

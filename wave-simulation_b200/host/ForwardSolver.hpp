@@ -14,6 +14,7 @@
 #include "Wavefields.hpp"
 
 struct ws_solver;
+struct ws_desc;
 
 namespace KITGPI
 {
@@ -60,6 +61,8 @@ namespace KITGPI
             IndexType getNT() const { return NT; }
 
           private:
+            void initIrregular(Configuration::Configuration const &config, ws_desc d, Derivatives::Derivatives<ValueType> &derivatives, Wavefields::Wavefields<ValueType> &wavefield,
+                               Modelparameter::Modelparameter<ValueType> &model, Acquisition::Coordinates<ValueType> const &modelCoordinates);
             void bindAcquisition(Acquisition::Receivers<ValueType> &receiver, Acquisition::Sources<ValueType> const &sources);
             void fetchSeismograms(Acquisition::Receivers<ValueType> &receiver);
             std::string dimension, equationType;
