@@ -260,6 +260,7 @@ def main():
     ap.add_argument("--variant", type=int, default=0, help="0 auto (TMA kernels, else marching kernels), 1 per-point kernels, 2 marching kernels")
     ap.add_argument("--damping", type=int, default=-1, help="developer switch: 2 = CPML (the benchmark configuration), 0 = none")
     ap.add_argument("--free-surface", type=int, default=-1, help="developer switch: 1 = image method")
+    ap.add_argument("--edge-policy", type=int, default=0, help="developer switch: 1 = order-reducing edges (useStencilMatrix=0, the par/ default)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     args.nx, args.ny, args.nz = args.nx or wl["n"][0], args.ny or wl["n"][1], (args.nz or wl["n"][2]) if wl["dim"] == 3 else 1
@@ -282,7 +283,7 @@ def main():
     W, K = max(3, args.warmup), max(1, args.steps)
     sampler = ClockSampler(local)
     sampler.start()
-    m = measure(args.workload, args.nx, args.ny, args.nz, K, W, args.variant, args.damping, args.free_surface, world, rank, local, e2e=True, strong=args.strong)
+    m = measure(args.workload, args.nx, args.ny, args.nz, K, W, args.variant, args.damping, args.free_surface, world, rank, local, e2e=True, strong=args.strong, edge_policy=args.edge_policy)
     sampler.stop_flag = True
     sampler.join()
     # BASELINE configs 2-5 (short runs after the headline's timed region: driver-run numbers for the other solvers)
@@ -321,7 +322,7 @@ def main():
         dist.destroy_process_group()
 
 
-def measure(wlname, nx, nyl, nz, K, W, variant, damping, free_surface, world, rank, local, e2e=True, strong=False):
+def measure(wlname, nx, nyl, nz, K, W, variant, damping, free_surface, world, rank, local, e2e=True, strong=False, edge_policy=0):
     """W warm-up steps, exactly K timed steps of workload `wlname` on this rank's slab (nyl planes per GPU); max over ranks."""
     import torch
     import torch.distributed as dist
@@ -331,7 +332,7 @@ def measure(wlname, nx, nyl, nz, K, W, variant, damping, free_surface, world, ra
     gny = nyl if strong else nyl * world
     nt = 2 * (W + K) + 8
     dt_, dh = wl["dt"], wl["dh"]
-    d = make_desc(wl["dim"], wl["eq"], nx, gny, nz, dh=dh, dt=dt_, nt=nt, fd_order=8, edge_policy=0, free_surface=free_surface, damping=damping,
+    d = make_desc(wl["dim"], wl["eq"], nx, gny, nz, dh=dh, dt=dt_, nt=nt, fd_order=8, edge_policy=edge_policy, free_surface=free_surface, damping=damping,
                   boundary_width=20, vmax_cpml=wl["vmax"], fc_cpml=wl["fc"], npower=4.0, relax_freq=wl["relax"], exact_arith=0,
                   kernel_variant=variant, rank=rank, nranks=world, device=local)
     s = Solver(d)

@@ -135,22 +135,21 @@ struct Entry {
     int arena, pos, dy;
 };
 
-// x points per thread of a half-step: one where the operands of a plane are so many that four would leave too few
-// resident threads per staged byte (the 3-D elastic / viscoelastic half-steps, the 3-D viscoEM E half-step)
+// x points per thread of a half-step: four (128-bit accesses, index arithmetic shared by the points) except where the operands
+// of a plane are so many that a four-point tile would not fit the stage ring twice: the 3-D viscoelastic stress half-step and
+// the 3-D viscoEM E half-step (196+ bytes per point).  Measured on the north-star grid with order-reducing edges
+// (3-D elastic 1024^3, profiles/r02_tma_sweep.txt): 31.5 Gpt/s with four points per thread against 22.2 with one.
 int lanesFor(const WsParams &P, int pass)
 {
     if (P.dim != 3)
         return (P.marchLanes == 1 || P.marchLanes == 2 || P.marchLanes == 4) ? P.marchLanes : 4;
-    const bool heavy = P.eq == WS_EQ_ELASTIC || P.eq == WS_EQ_VISCOELASTIC || P.eq == WS_EQ_VISCOEMEM;
-    if (P.marchLanes == 4 || (P.marchLanes == 1 && heavy))
+    const bool heavyKernels = P.eq == WS_EQ_ELASTIC || P.eq == WS_EQ_VISCOELASTIC || P.eq == WS_EQ_VISCOEMEM; // instantiated with 1 and 4
+    if (P.marchLanes == 4 || (P.marchLanes == 1 && heavyKernels))
         return P.marchLanes;
-    if (P.eq == WS_EQ_ELASTIC || P.eq == WS_EQ_VISCOELASTIC)
-        return 1;
-    if (P.eq == WS_EQ_VISCOEMEM && pass == 1 && P.L > 0)
+    if (pass == 1 && P.L > 0 && (P.eq == WS_EQ_VISCOELASTIC || P.eq == WS_EQ_VISCOEMEM))
         return 1;
     return 4;
 }
-
 
 } // namespace
 
