@@ -127,18 +127,20 @@ def test_linearity_and_reset_large():
 # tiled TMA kernels (3D elastic): same arithmetic sequence as the general kernels -> bit-identical in FMA mode
 # ---------------------------------------------------------------------------------------------------------------------
 FAST_SHAPES = [
-    # nx, ny, nz, q, fs, damp, W
-    (64, 40, 32, 8, 1, 2, 8), (68, 37, 21, 8, 1, 2, 6), (132, 50, 40, 8, 0, 2, 10), (64, 33, 16, 8, 0, 0, 6),
-    (96, 44, 36, 4, 1, 2, 8), (72, 70, 50, 8, 1, 0, 6),
+    # nx, ny, nz, q, fs, damp, W, edge policy
+    (64, 40, 32, 8, 1, 2, 8, 0), (68, 37, 21, 8, 1, 2, 6, 0), (132, 50, 40, 8, 0, 2, 10, 0), (64, 33, 16, 8, 0, 0, 6, 0),
+    (96, 44, 36, 4, 1, 2, 8, 0), (72, 70, 50, 8, 1, 0, 6, 0),
+    # order-reducing edges (useStencilMatrix=0, the par/ default): own weights within q/2 of every grid face
+    (64, 40, 32, 8, 1, 2, 8, 1), (132, 50, 40, 8, 0, 2, 10, 1), (196, 37, 29, 8, 1, 2, 6, 1), (96, 44, 36, 4, 0, 2, 8, 1), (72, 38, 24, 4, 1, 2, 4, 1),
 ]
 
 
-@pytest.mark.parametrize("shape", FAST_SHAPES, ids=["%dx%dx%d-q%d-fs%d-damp%d" % s[:6] for s in FAST_SHAPES])
+@pytest.mark.parametrize("shape", FAST_SHAPES, ids=["%dx%dx%d-q%d-fs%d-damp%d-w%d-pol%d" % s for s in FAST_SHAPES])
 def test_fast_kernels_equal_general_kernels(shape):
-    nx, ny, nz, q, fs, damp, W = shape
+    nx, ny, nz, q, fs, damp, W, pol = shape
     res = []
     for variant in (0, 1):
-        case = make_case("elastic", 3, nx, ny, nz, q, 0, fs, damp, W, 0, nt=40, exact=0, kernel_variant=variant)
+        case = make_case("elastic", 3, nx, ny, nz, q, pol, fs, damp, W, 0, nt=40, exact=0, kernel_variant=variant)
         s = case.setup(Solver(case.desc))
         assert s.uses_fast_kernels() == (variant == 0)
         s.run(0, 40)
@@ -185,7 +187,8 @@ DEFAULT_PATHS = [
     (("viscoelastic", 3, 72, 64, 24, 8, 0, 1, 2, 8, 2), 3),  # velocity half-step: 3-D elastic TMA kernel, stress half-step: TMA marching kernel
     (("viscoelastic", 3, 70, 64, 24, 6, 1, 1, 2, 8, 1), 3),  # both half-steps on the TMA marching kernels
     (("acoustic", 3, 100, 80, 40, 8, 0, 0, 2, 10, 0), 3),
-    (("elastic", 3, 64, 48, 40, 8, 1, 1, 2, 8, 0), 3),       # order-reducing edges (the par/ default): TMA marching kernels
+    (("elastic", 3, 64, 48, 40, 8, 1, 1, 2, 8, 0), 2),       # order-reducing edges (the par/ default) + CPML: 3-D elastic TMA kernels
+    (("elastic", 3, 64, 48, 40, 8, 1, 1, 1, 8, 0), 3),       # ... + ABS frame: TMA marching kernels
     (("viscotmem", 2, 900, 300, 1, 8, 0, 0, 2, 20, 1), None),
     (("elastic", 2, 1000, 300, 1, 8, 0, 1, 2, 20, 0), None),
 ]

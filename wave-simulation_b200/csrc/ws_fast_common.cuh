@@ -267,6 +267,8 @@ template <bool CPML> __device__ __forceinline__ bool needsGeneric(const WsParams
 {
     if (velocity && P.free_surface == 1 && gy0 < H)
         return true;
+    if (P.edge_policy == 1 && (gy0 < H || gy1 >= P.gny - H)) // order-reducing edges: the rows next to the grid edge have their own weights
+        return true;
     if (CPML) {
         if (P.free_surface == 0 && gy0 < P.W)
             return true;
@@ -344,6 +346,45 @@ template <int Q> __device__ __forceinline__ F4 dX9(const float *row, const float
         for (int j = 0; j <= Q; j++)
             acc = A::madd(c[j], w[HX + p + j - H], acc);
         r.v[p] = acc;
+    }
+    return r;
+}
+
+// Order-reducing edges (edge_policy 1, Derivatives.cpp:159-175): the columns / rows within q/2 of a grid face have their own
+// weights (table rows, ws_tables.hpp).  They lie inside the x / z CPML layers, i.e. in layer tiles only; a thread that owns
+// such a column or row takes these forms, with the accumulation order of the per-point kernels (all q + 1 window entries).
+template <int Q> __device__ __forceinline__ F4 dX9t(const float *row, const float *__restrict__ tab, int op, int x0, int nx)
+{
+    constexpr int H = Q / 2, HX = Cfg<Q>::HX, NV = (2 * HX + 4) / 4;
+    float w[NV * 4];
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+        const F4 t = ld4(row + 4 * k);
+        w[4 * k] = t.v[0]; w[4 * k + 1] = t.v[1]; w[4 * k + 2] = t.v[2]; w[4 * k + 3] = t.v[3];
+    }
+    F4 r;
+#pragma unroll
+    for (int p = 0; p < 4; p++) {
+        const float *__restrict__ c = tab + ((size_t)op * (2 * H + 1) + wsRowClass(x0 + p, nx, H)) * (Q + 1);
+        float acc = 0.0f;
+#pragma unroll
+        for (int j = 0; j <= Q; j++)
+            acc = A::madd(__ldg(c + j), w[HX + p + j - H], acc);
+        r.v[p] = acc;
+    }
+    return r;
+}
+// `col` points at (row of z - H, column of x0); c = the q + 1 weights of the row's class
+template <int Q, int LD> __device__ __forceinline__ F4 dZ9t(const float *col, const float *__restrict__ c)
+{
+    F4 r = zero4();
+#pragma unroll
+    for (int j = 0; j <= Q; j++) {
+        const F4 t = ld4(col + j * LD);
+        const float wj = __ldg(c + j);
+#pragma unroll
+        for (int p = 0; p < 4; p++)
+            r.v[p] = A::madd(wj, t.v[p], r.v[p]);
     }
     return r;
 }

@@ -95,6 +95,10 @@ __host__ __device__ __forceinline__ int psiStageFloats(int PX) { return psxFloat
 // ---------------------------------------------------------------------------------------------------------------------
 struct VRole {
     int oX, oZ, oF, oV, oR; // shared-memory offsets inside a stage
+    int oZ9;                // z stencil from row z - H whatever the operator (order-reducing edge rows)
+    int opX;                // x operator of this role (table rows of the edge columns)
+    bool xEdge;             // order-reducing edges: some of the thread's 4 columns lie within q/2 of an x face
+    const float *wz;        // ... the thread's row lies within q/2 of a z face: its weights (null otherwise)
     float cx[WS_MAXQ + 1];  // x weights over offsets -H..+H
     float *out;             // own row of the output field at plane 0
     float *psx, *psy, *psz; // memory-variable slabs of the x / y / z term
@@ -104,7 +108,8 @@ struct VRole {
 
 // one plane of one velocity component.  R = position inside a trip; GENERIC = run-time y weights / y-CPML; XZ = this
 // warp may sit in an x or z CPML layer.
-template <int Q, int R, bool GENERIC, bool XZ>
+// POL1 = order-reducing edges (edge_policy 1): own instantiations, so that the code of the default policy is not touched
+template <int Q, int R, bool GENERIC, bool XZ, bool POL1>
 __device__ __forceinline__ void velPlane(const WsParams &P, const Thr &t, const CpT &cpt, const VRole &ro, F4 (&q)[Cfg<Q>::QL], const float *st, float *gout, float *psx,
                                          float *psz, const YDyn<Q> &yd, float *psy)
 {
@@ -115,7 +120,7 @@ __device__ __forceinline__ void velPlane(const WsParams &P, const Thr &t, const 
         pz = ld4(st + t.oPZ);
     if (ycp)
         py = ld4(psy);
-    F4 u = dX9<Q>(st + ro.oX, ro.cx);
+    F4 u = (POL1 && XZ && ro.xEdge) ? dX9t<Q>(st + ro.oX, P.tab, ro.opX, t.x0, P.nx) : dX9<Q>(st + ro.oX, ro.cx);
     if (XZ && cpt.kxv >= 0)
         cpApplyXv(cpt, st + t.oPX, psx, t.cxTab, P.psiPitchX, u);
     F4 w = dY<Q, R>(q, GENERIC ? yd.w : P.cwy);
@@ -124,7 +129,7 @@ __device__ __forceinline__ void velPlane(const WsParams &P, const Thr &t, const 
 #pragma unroll
     for (int p = 0; p < 4; p++)
         u.v[p] = A::add(u.v[p], w.v[p]);
-    w = dZ<Q, false, C::TXH>(st + ro.oZ, P.cw);
+    w = (POL1 && XZ && ro.wz) ? dZ9t<Q, C::TXH>(st + ro.oZ9, ro.wz) : dZ<Q, false, C::TXH>(st + ro.oZ, P.cw);
     if (XZ && cpt.kz >= 0)
         cpApply4(psz, pz, cpt.za, cpt.zb, w);
     F4 v = ld4(st + ro.oV);
@@ -146,7 +151,7 @@ __device__ __forceinline__ void velPlane(const WsParams &P, const Thr &t, const 
 }
 
 // UNR consecutive planes of a trip (template recursion keeps the queue offset R a compile-time constant)
-template <int Q, bool XZ, int R> struct VelUnroll {
+template <int Q, bool XZ, bool POL1, int R> struct VelUnroll {
     static __device__ __forceinline__ void run(const WsParams &P, const Thr &t, const CpT &cpt, const VRole &ro, F4 (&q)[Cfg<Q>::QL], const float *sm, int stage0,
                                                uint32_t parity, float *gout, float *psx, float *psz, long long sxStride, long long szStride)
     {
@@ -161,19 +166,19 @@ template <int Q, bool XZ, int R> struct VelUnroll {
             if (t.active)
                 st4cs(gout, ld4(st + ro.oV));
         } else if (P.fastDebug != 1)
-            velPlane<Q, R, false, XZ>(P, t, cpt, ro, q, st, gout, psx, psz, yd, nullptr);
+            velPlane<Q, R, false, XZ, POL1>(P, t, cpt, ro, q, st, gout, psx, psz, yd, nullptr);
         consumerRelease(t, stage);
-        VelUnroll<Q, XZ, R + 1>::run(P, t, cpt, ro, q, sm, stage0, parity, gout + P.plane, XZ ? psx + sxStride : psx, XZ ? psz + szStride : psz, sxStride, szStride);
+        VelUnroll<Q, XZ, POL1, R + 1>::run(P, t, cpt, ro, q, sm, stage0, parity, gout + P.plane, XZ ? psx + sxStride : psx, XZ ? psz + szStride : psz, sxStride, szStride);
     }
 };
-template <int Q, bool XZ> struct VelUnroll<Q, XZ, UNR> {
+template <int Q, bool XZ, bool POL1> struct VelUnroll<Q, XZ, POL1, UNR> {
     static __device__ __forceinline__ void run(const WsParams &, const Thr &, const CpT &, const VRole &, F4 (&)[Cfg<Q>::QL], const float *, int, uint32_t, float *,
                                                float *, float *, long long, long long)
     {
     }
 };
 
-template <int Q, bool CPML, bool EDGE>
+template <int Q, bool CPML, bool EDGE, bool POL1>
 __device__ __forceinline__ void velConsumer(const WsParams &P, const float *sm, Thr t, int G, int yc0, int yc1)
 {
     using S = StageV<Q>;
@@ -190,6 +195,13 @@ __device__ __forceinline__ void velConsumer(const WsParams &P, const float *sm, 
     ro.oF = S::FEED + G * C::N_P + oP;
     ro.oV = S::OWNV + G * C::N_P + oP;
     ro.oR = S::OWNR + G * C::N_P + oP;
+    // order-reducing edges: operators Dxf | Dxb | Dxb and Dzb | Dzb | Dzf of the three roles
+    ro.oZ9 = G == 2 ? ro.oZ - TXH : ro.oZ;
+    ro.opX = G == 0 ? OP_XF : OP_XB;
+    ro.xEdge = POL1 && XZC && t.active && (t.x0 < H || t.x0 + 3 >= P.nx - H);
+    ro.wz = (POL1 && XZC && t.active && (t.z < H || t.z >= P.nz - H))
+                ? P.tab + ((size_t)(G == 2 ? OP_ZF : OP_ZB) * (2 * H + 1) + wsRowClass(t.z, P.nz, H)) * (Q + 1)
+                : nullptr;
 #pragma unroll
     for (int j = 0; j <= Q; j++) // forward (role 0): offsets -H+1..H; backward: -H..H-1
         ro.cx[j] = G == 0 ? (j >= 1 ? P.cw[j - 1] : 0.0f) : (j < Q ? P.cw[j] : 0.0f);
@@ -231,7 +243,8 @@ __device__ __forceinline__ void velConsumer(const WsParams &P, const float *sm, 
         if (comp) {
             // y weights of this plane: with a free surface every row comes from the image-method operators (their
             // interior rows are scaled (c/DH)*DT, not c*(DT/DH): Derivatives.cpp:407-425 vs FDTD3D.cpp:211-216)
-            const int row = (P.free_surface == 1 && gy < H) ? max(gy, 0) : H;
+            // (order-reducing edges: the plain operators have their own rows next to both y faces as well)
+            const int row = (P.free_surface == 1 && gy < H) ? max(gy, 0) : (POL1 ? wsRowClass(min(max(gy, 0), P.gny - 1), P.gny, H) : H);
             const float *tw = P.tab + ((size_t)ro.opY * (2 * H + 1) + row) * (Q + 1) + (ro.yFwd ? 1 : 0);
 #pragma unroll
             for (int j = 0; j < Q; j++)
@@ -248,7 +261,7 @@ __device__ __forceinline__ void velConsumer(const WsParams &P, const float *sm, 
         const float *st = sm + stage * t.stride;
         q[Q - 1] = ld4(st + ro.oF);
         if (comp)
-            velPlane<Q, 0, true, XZC>(P, t, cpt, ro, q, st, ro.out + (long long)ly * P.plane, XZC ? ro.psx + (long long)ly * sxStride : nullptr,
+            velPlane<Q, 0, true, XZC, POL1>(P, t, cpt, ro, q, st, ro.out + (long long)ly * P.plane, XZC ? ro.psx + (long long)ly * sxStride : nullptr,
                                       XZC ? ro.psz + (long long)ly * szStride : nullptr, yd, CPML ? ro.psy + (long long)yd.ky * P.nz * P.nx : nullptr);
         consumerRelease(t, stage);
 #pragma unroll
@@ -265,10 +278,10 @@ __device__ __forceinline__ void velConsumer(const WsParams &P, const float *sm, 
             const int stage0 = it % NSTV;
             const uint32_t parity = (it / NSTV) & 1;
             if (warpXZ)
-                VelUnroll<Q, XZC, 0>::run(P, t, cpt, ro, q, sm, stage0, parity, gout, ro.psx + (long long)ly0 * sxStride, ro.psz + (long long)ly0 * szStride, sxStride,
+                VelUnroll<Q, XZC, POL1, 0>::run(P, t, cpt, ro, q, sm, stage0, parity, gout, ro.psx + (long long)ly0 * sxStride, ro.psz + (long long)ly0 * szStride, sxStride,
                                            szStride);
             else
-                VelUnroll<Q, false, 0>::run(P, t, cpt, ro, q, sm, stage0, parity, gout, nullptr, nullptr, 0, 0);
+                VelUnroll<Q, false, POL1, 0>::run(P, t, cpt, ro, q, sm, stage0, parity, gout, nullptr, nullptr, 0, 0);
 #pragma unroll
             for (int k = 0; k < Q - 1; k++)
                 q[k] = q[k + UNR];
@@ -280,7 +293,7 @@ __device__ __forceinline__ void velConsumer(const WsParams &P, const float *sm, 
     }
 }
 
-template <int Q, bool CPML, bool EDGE> __global__ void __launch_bounds__(NGROUPS *Cfg<Q>::NTG + 32, 1) kFastVel(const __grid_constant__ WsParams P)
+template <int Q, bool CPML, bool EDGE, bool POL1 = false> __global__ void __launch_bounds__(NGROUPS *Cfg<Q>::NTG + 32, 1) kFastVel(const __grid_constant__ WsParams P)
 {
     using C = Cfg<Q>;
     using S = StageV<Q>;
@@ -330,7 +343,7 @@ template <int Q, bool CPML, bool EDGE> __global__ void __launch_bounds__(NGROUPS
         t.stride = S::SIZE + (XZC ? psiStageFloats(P.psiBoxX) : 0);
         t.cxTab = cxTab;
         t.oPX = t.oPZ = t.oPZ2 = 0;
-        velConsumer<Q, CPML, EDGE>(P, sm, t, grp, yc0, yc1);
+        velConsumer<Q, CPML, EDGE, POL1>(P, sm, t, grp, yc0, yc1);
         traceEnd(P, 0, t.lane);
     } else if (tid == NGROUPS * C::NTG) {
         // ---- producer: one elected thread streams the planes ----
@@ -405,6 +418,9 @@ template <int Q, bool CPML, bool EDGE> __global__ void __launch_bounds__(NGROUPS
 // the free-surface plane need the generic step.
 // ---------------------------------------------------------------------------------------------------------------------
 struct SRole {
+    int oZ9, opX, opY;  // order-reducing edges: z stencil from row z - H, x / y operator of this role
+    bool xEdge, yFwd;
+    const float *wz;
     int r;
     int oP;             // own point inside a plain tile
     int oX, oZ, oF;     // stage offsets: x stencil row, z stencil start, feed tile
@@ -416,7 +432,7 @@ struct SRole {
     bool halfY;
 };
 
-template <int Q, int R, bool GENERIC, bool XZ>
+template <int Q, int R, bool GENERIC, bool XZ, bool POL1>
 __device__ __forceinline__ void strPlane(const WsParams &P, const Thr &t, const CpT &cpt, const SRole &ro, F4 (&q)[Cfg<Q>::QL], const float *st, float *xch, int n,
                                          long long o, float *psx, float *psz, const YDyn<Q> &yd, float *psy, int gy)
 {
@@ -429,13 +445,13 @@ __device__ __forceinline__ void strPlane(const WsParams &P, const Thr &t, const 
         pz = ld4(st + t.oPZ);
     if (ycp)
         py = ld4(psy);
-    F4 a = dX9<Q>(st + ro.oX, ro.cx);
+    F4 a = (POL1 && XZ && ro.xEdge) ? dX9t<Q>(st + ro.oX, P.tab, ro.opX, t.x0, P.nx) : dX9<Q>(st + ro.oX, ro.cx);
     if (XZ && cpt.kxv >= 0)
         cpApplyXv(cpt, st + t.oPX, psx, t.cxTab, P.psiPitchX, a);
-    F4 b = dY<Q, R>(q, P.cw);
+    F4 b = dY<Q, R>(q, (GENERIC && POL1) ? yd.w : P.cw);
     if (ycp)
         cpApply4(psy, py, yd.ya, yd.yb, b);
-    F4 c = dZ<Q, false, C::TXH>(st + ro.oZ, P.cw);
+    F4 c = (POL1 && XZ && ro.wz) ? dZ9t<Q, C::TXH>(st + ro.oZ9, ro.wz) : dZ<Q, false, C::TXH>(st + ro.oZ, P.cw);
     if (XZ && cpt.kz >= 0)
         cpApply4(psz, pz, cpt.za, cpt.zb, c);
     // publish the normal strain rate and the shear term another role needs; keep the shear term of the own shear stress
@@ -506,7 +522,7 @@ __device__ __forceinline__ void strPlane(const WsParams &P, const Thr &t, const 
     }
 }
 
-template <int Q, bool XZ, int R> struct StrUnroll {
+template <int Q, bool XZ, bool POL1, int R> struct StrUnroll {
     static __device__ __forceinline__ void run(const WsParams &P, const Thr &t, const CpT &cpt, const SRole &ro, F4 (&q)[Cfg<Q>::QL], const float *sm, float *xch, int n,
                                                int stage0, uint32_t parity, long long o, float *psx, float *psz, long long sxStride, long long szStride)
     {
@@ -516,20 +532,20 @@ template <int Q, bool XZ, int R> struct StrUnroll {
         q[Q - 1 + R] = ld4(st + ro.oF);
         YDyn<Q> yd;
         yd.ky = -1;
-        strPlane<Q, R, false, XZ>(P, t, cpt, ro, q, st, xch, n, o, psx, psz, yd, nullptr, 1);
+        strPlane<Q, R, false, XZ, POL1>(P, t, cpt, ro, q, st, xch, n, o, psx, psz, yd, nullptr, 1);
         consumerRelease(t, stage);
-        StrUnroll<Q, XZ, R + 1>::run(P, t, cpt, ro, q, sm, xch, n + 1, stage0, parity, o + P.plane, XZ ? psx + sxStride : psx, XZ ? psz + szStride : psz, sxStride,
+        StrUnroll<Q, XZ, POL1, R + 1>::run(P, t, cpt, ro, q, sm, xch, n + 1, stage0, parity, o + P.plane, XZ ? psx + sxStride : psx, XZ ? psz + szStride : psz, sxStride,
                                      szStride);
     }
 };
-template <int Q, bool XZ> struct StrUnroll<Q, XZ, UNR> {
+template <int Q, bool XZ, bool POL1> struct StrUnroll<Q, XZ, POL1, UNR> {
     static __device__ __forceinline__ void run(const WsParams &, const Thr &, const CpT &, const SRole &, F4 (&)[Cfg<Q>::QL], const float *, float *, int, int, uint32_t,
                                                long long, float *, float *, long long, long long)
     {
     }
 };
 
-template <int Q, bool CPML, bool EDGE>
+template <int Q, bool CPML, bool EDGE, bool POL1>
 __device__ __forceinline__ void strConsumer(const WsParams &P, const float *sm, float *xch, Thr t, int G, int yc0, int yc1)
 {
     using S = StageS<Q>;
@@ -544,6 +560,15 @@ __device__ __forceinline__ void strConsumer(const WsParams &P, const float *sm, 
     ro.oX = tv + (t.lz + H) * TXH + 4 * t.lx;                    // x stencil: own row, column of x0 - HX
     ro.oZ = tv + (t.lz + (G == 2 ? 0 : 1)) * TXH + 4 * t.lx + HX; // z stencil: row z - H (backward, role 2) or z - H + 1 (forward)
     ro.oF = S::FEED + G * NP + oP;
+    // order-reducing edges: operators Dxb | Dxf | Dxf, Dyf | Dyb | Dyf and Dzf | Dzf | Dzb of the three roles
+    ro.oZ9 = G == 2 ? ro.oZ : ro.oZ - TXH;
+    ro.opX = G == 0 ? OP_XB : OP_XF;
+    ro.yFwd = G != 1;
+    ro.opY = ro.yFwd ? OP_YF : OP_YB;
+    ro.xEdge = POL1 && XZC && t.active && (t.x0 < H || t.x0 + 3 >= P.nx - H);
+    ro.wz = (POL1 && XZC && t.active && (t.z < H || t.z >= P.nz - H))
+                ? P.tab + ((size_t)(G == 2 ? OP_ZB : OP_ZF) * (2 * H + 1) + wsRowClass(t.z, P.nz, H)) * (Q + 1)
+                : nullptr;
 #pragma unroll
     for (int j = 0; j <= Q; j++) // offsets -H..H: backward (role 0) -H..H-1, forward -H+1..H
         ro.cx[j] = G == 0 ? (j < Q ? P.cw[j] : 0.0f) : (j >= 1 ? P.cw[j - 1] : 0.0f);
@@ -587,6 +612,15 @@ __device__ __forceinline__ void strConsumer(const WsParams &P, const float *sm, 
         const int stage = it % NSTS;
         YDyn<Q> yd;
         yd.ky = -1;
+        if (POL1) {
+            // y weights of this plane: the plain operators (ForwardSolver3Delastic.cpp:289); with order-reducing edges the rows next
+            // to the y faces have their own
+            const int row = wsRowClass(min(max(gy, 0), P.gny - 1), P.gny, H);
+            const float *tw = P.tab + ((size_t)ro.opY * (2 * H + 1) + row) * (Q + 1) + (ro.yFwd ? 1 : 0);
+#pragma unroll
+            for (int j = 0; j < Q; j++)
+                yd.w[j] = __ldg(tw + j);
+        }
         if (comp && CPML) {
             yd.ky = yCpmlIndex(P, gy);
             if (yd.ky >= 0) {
@@ -598,7 +632,7 @@ __device__ __forceinline__ void strConsumer(const WsParams &P, const float *sm, 
         const float *st = sm + stage * t.stride;
         q[Q - 1] = ld4(st + ro.oF);
         if (comp) {
-            strPlane<Q, 0, true, XZC>(P, t, cpt, ro, q, st, xch, n, rowOff + (long long)ly * P.plane, XZC ? ro.psx + (long long)ly * sxStride : nullptr,
+            strPlane<Q, 0, true, XZC, POL1>(P, t, cpt, ro, q, st, xch, n, rowOff + (long long)ly * P.plane, XZC ? ro.psx + (long long)ly * sxStride : nullptr,
                                       XZC ? ro.psz + (long long)ly * szStride : nullptr, yd, CPML ? ro.psy + (long long)yd.ky * P.nz * P.nx : nullptr, gy);
             n++;
         }
@@ -617,10 +651,10 @@ __device__ __forceinline__ void strConsumer(const WsParams &P, const float *sm, 
             const int stage0 = it % NSTS;
             const uint32_t parity = (it / NSTS) & 1;
             if (warpXZ)
-                StrUnroll<Q, XZC, 0>::run(P, t, cpt, ro, q, sm, xch, n, stage0, parity, o, ro.psx + (long long)ly0 * sxStride, ro.psz + (long long)ly0 * szStride, sxStride,
+                StrUnroll<Q, XZC, POL1, 0>::run(P, t, cpt, ro, q, sm, xch, n, stage0, parity, o, ro.psx + (long long)ly0 * sxStride, ro.psz + (long long)ly0 * szStride, sxStride,
                                           szStride);
             else
-                StrUnroll<Q, false, 0>::run(P, t, cpt, ro, q, sm, xch, n, stage0, parity, o, nullptr, nullptr, 0, 0);
+                StrUnroll<Q, false, POL1, 0>::run(P, t, cpt, ro, q, sm, xch, n, stage0, parity, o, nullptr, nullptr, 0, 0);
             n += UNR;
 #pragma unroll
             for (int k = 0; k < Q - 1; k++)
@@ -633,7 +667,7 @@ __device__ __forceinline__ void strConsumer(const WsParams &P, const float *sm, 
     }
 }
 
-template <int Q, bool CPML, bool EDGE> __global__ void __launch_bounds__(NGROUPS *Cfg<Q>::NTG + 32, 1) kFastStress(const __grid_constant__ WsParams P)
+template <int Q, bool CPML, bool EDGE, bool POL1 = false> __global__ void __launch_bounds__(NGROUPS *Cfg<Q>::NTG + 32, 1) kFastStress(const __grid_constant__ WsParams P)
 {
     using C = Cfg<Q>;
     using S = StageS<Q>;
@@ -687,7 +721,7 @@ template <int Q, bool CPML, bool EDGE> __global__ void __launch_bounds__(NGROUPS
         t.stride = stride;
         t.cxTab = cxTab;
         t.oPX = t.oPZ = t.oPZ2 = 0;
-        strConsumer<Q, CPML, EDGE>(P, sm, sm + NSTS * stride, t, grp, yc0, yc1);
+        strConsumer<Q, CPML, EDGE, POL1>(P, sm, sm + NSTS * stride, t, grp, yc0, yc1);
         traceEnd(P, 1, t.lane);
     } else if (tid == NGROUPS * C::NTG) {
         const int HZP = (P.nzp > 1) ? WS_HALO : 0;
@@ -755,9 +789,11 @@ template <int Q> size_t smemBytes(int pass, bool cpmlEdge, int PX)
 
 template <int Q> bool setAttrs()
 {
-    const void *ks[6] = {reinterpret_cast<const void *>(kFastVel<Q, true, true>),     reinterpret_cast<const void *>(kFastVel<Q, true, false>),
-                         reinterpret_cast<const void *>(kFastVel<Q, false, false>),   reinterpret_cast<const void *>(kFastStress<Q, true, true>),
-                         reinterpret_cast<const void *>(kFastStress<Q, true, false>), reinterpret_cast<const void *>(kFastStress<Q, false, false>)};
+    const void *ks[10] = {reinterpret_cast<const void *>(kFastVel<Q, true, true>),           reinterpret_cast<const void *>(kFastVel<Q, true, false>),
+                          reinterpret_cast<const void *>(kFastVel<Q, false, false>),         reinterpret_cast<const void *>(kFastStress<Q, true, true>),
+                          reinterpret_cast<const void *>(kFastStress<Q, true, false>),       reinterpret_cast<const void *>(kFastStress<Q, false, false>),
+                          reinterpret_cast<const void *>(kFastVel<Q, true, true, true>),     reinterpret_cast<const void *>(kFastVel<Q, true, false, true>),
+                          reinterpret_cast<const void *>(kFastStress<Q, true, true, true>), reinterpret_cast<const void *>(kFastStress<Q, true, false, true>)};
     for (const void *k : ks)
         if (wsOptInSmem(k, kMaxDynSmem) != cudaSuccess)
             return false;
@@ -789,7 +825,19 @@ template <int Q> int launchQ(const WsParams &P, int pass, cudaStream_t st)
         const bool edge = cpml && (part == 0 || P.fastNEdge == 0);
         const size_t sm = smemBytes<Q>(pass, edge, P.psiBoxX);
         Q2.fastChunk = chunk;
-        if (pass == 0) {
+        if (P.edge_policy == 1) { // order-reducing edges: CPML variants only (wsFastSupported)
+            if (pass == 0) {
+                if (edge)
+                    kFastVel<Q, true, true, true><<<grid, nt, sm, st>>>(Q2);
+                else
+                    kFastVel<Q, true, false, true><<<grid, nt, sm, st>>>(Q2);
+            } else {
+                if (edge)
+                    kFastStress<Q, true, true, true><<<grid, nt, sm, st>>>(Q2);
+                else
+                    kFastStress<Q, true, false, true><<<grid, nt, sm, st>>>(Q2);
+            }
+        } else if (pass == 0) {
             if (edge)
                 kFastVel<Q, true, true><<<grid, nt, sm, st>>>(Q2);
             else if (cpml)
@@ -818,7 +866,10 @@ bool wsFastSupported(const WsParams &P, bool exact, int pass)
 {
     if (exact || P.dim != 3 || !(P.eq == WS_EQ_ELASTIC || (P.eq == WS_EQ_VISCOELASTIC && pass == 0)))
         return false;
-    if (P.edge_policy != 0 || P.damping == 1)
+    if (P.damping == 1)
+        return false;
+    // order-reducing edges: the edge columns / rows must lie in the layer tiles (x / z CPML layers at least q/2 wide)
+    if (P.edge_policy != 0 && !(P.damping == 2 && P.W >= P.h))
         return false;
     if (P.q != 8 && P.q != 4)
         return false;
