@@ -407,7 +407,7 @@ def measure(wlname, nx, nyl, nz, K, W, variant, damping, free_surface, world, ra
     out = {
         "workload": "%s %dx%dx%d per GPU (global NY %d), %sCPML(20), y-slab decomposition" % (wl["name"], nx, nyl, nz, gny, "free surface + " if free_surface else ""),
         "l2": "inputs (%.1f GB/GPU of wavefields+model) exceed the 126 MB L2" % (ws_bytes / 1e9),
-        "kernels": ["per-point", "marching", "tma-tiled", "tma-marching"][s.kernel_path()], "finite": bool(finite),
+        "kernels": ["per-point", "marching", "tma-tiled", "tma-marching", "tma-tile2d"][s.kernel_path()], "finite": bool(finite),
         "value": npts * K / (ms * 1e-3) / 1e9, "ms_per_step": ms / K, "launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "traffic_source": "committed ncu capture of this configuration (profiles/traffic_1024.json), not measured in this run" if traffic else None,

@@ -66,7 +66,7 @@ typedef struct ws_desc {
     int32_t n_relax;        /* L                                      key: numRelaxationMechanisms             */
     float relax_freq[WS_MAX_RELAX]; /*                                keys: relaxationFrequency[2..4]          */
     int32_t exact_arith;    /* 1 = reference operation order, no FMA contraction (bit-parity mode); 0 = FMA    */
-    int32_t kernel_variant; /* 0 = auto (TMA kernels), 1 = per-point kernels, 2 = cp.async marching kernels, 3 = TMA marching kernels */
+    int32_t kernel_variant; /* 0 = auto (TMA kernels; 2-D: tile kernels), 1 = per-point kernels, 2 = cp.async marching kernels, 3 = TMA marching kernels, 4 = 2-D tile kernels */
     int32_t rank, nranks;   /* y-slab decomposition of the global grid over `nranks` processes (one GPU each)  */
     int32_t device;         /* CUDA device ordinal used by this handle                                         */
 } ws_desc;

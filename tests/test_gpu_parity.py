@@ -189,8 +189,8 @@ DEFAULT_PATHS = [
     (("acoustic", 3, 100, 80, 40, 8, 0, 0, 2, 10, 0), 3),
     (("elastic", 3, 64, 48, 40, 8, 1, 1, 2, 8, 0), 2),       # order-reducing edges (the par/ default) + CPML: 3-D elastic TMA kernels
     (("elastic", 3, 64, 48, 40, 8, 1, 1, 1, 8, 0), 3),       # ... + ABS frame: TMA marching kernels
-    (("viscotmem", 2, 900, 300, 1, 8, 0, 0, 2, 20, 1), None),
-    (("elastic", 2, 1000, 300, 1, 8, 0, 1, 2, 20, 0), None),
+    (("viscotmem", 2, 900, 300, 1, 8, 0, 0, 2, 20, 1), 4),   # 2-D: tile kernels
+    (("elastic", 2, 1000, 300, 1, 8, 0, 1, 2, 20, 0), 4),
 ]
 
 
@@ -237,6 +237,53 @@ def test_marching_kernels_ragged_shapes(cfg, family):
         s.close()
     for f in res[0]:
         assert np.array_equal(res[0][f], res[1][f]), f
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# 2-D tile kernels (ws_kernels_tile2d.cuh): one thread block per 128 x 8 / 16 tile, x AND y stencils from TMA-fetched halo tiles
+# ---------------------------------------------------------------------------------------------------------------------
+TILE_SHAPES = [
+    # eq, dim, nx, ny, nz, q, pol, fs, damp, W, L : ragged tiles on both axes, several tiles per axis, every 2-D equation type
+    ("elastic", 2, 1000, 700, 1, 8, 0, 1, 2, 20, 0), ("elastic", 2, 515, 260, 1, 12, 1, 1, 1, 12, 0), ("elastic", 2, 130, 45, 1, 2, 1, 0, 0, 6, 0),
+    ("acoustic", 2, 515, 260, 1, 12, 1, 1, 1, 12, 0), ("acoustic", 2, 300, 129, 1, 8, 0, 1, 2, 10, 0), ("acoustic", 2, 257, 100, 1, 6, 0, 0, 2, 8, 0),
+    ("viscoelastic", 2, 400, 150, 1, 8, 0, 1, 2, 12, 2), ("viscoelastic", 2, 260, 97, 1, 4, 1, 0, 1, 8, 4), ("viscoelastic", 2, 300, 120, 1, 10, 1, 1, 2, 10, 1),
+    ("sh", 2, 300, 200, 1, 8, 1, 1, 2, 10, 0), ("viscosh", 2, 300, 200, 1, 6, 0, 1, 2, 10, 2), ("viscosh", 2, 140, 77, 1, 4, 1, 0, 1, 8, 3),
+    ("tmem", 2, 270, 130, 1, 8, 0, 0, 2, 10, 0), ("viscotmem", 2, 900, 300, 1, 8, 0, 0, 2, 20, 1), ("viscotmem", 2, 200, 90, 1, 4, 1, 0, 1, 8, 3),
+    ("emem", 2, 270, 130, 1, 8, 0, 0, 2, 10, 0), ("viscoemem", 2, 333, 111, 1, 6, 1, 0, 2, 9, 2), ("viscoemem", 2, 200, 64, 1, 12, 0, 0, 0, 6, 4),
+]
+
+
+@pytest.mark.parametrize("ty", [8, 16])
+@pytest.mark.parametrize("cfg", TILE_SHAPES, ids=[sweep_id(c) + "-%dx%d" % c[2:4] for c in TILE_SHAPES])
+def test_tile2d_kernels_equal_per_point_kernels(cfg, ty, monkeypatch):
+    """Same statement sequence, same accumulation order as the per-point kernels => bit-identical in FMA mode, for both tile
+    heights (WS_TILE_TY is a developer switch read at ws_prepare)."""
+    eq, dim, nx, ny, nz, q, pol, fs, damp, W, L = cfg
+    monkeypatch.setenv("WS_TILE_TY", str(ty))
+    res = []
+    for variant in (1, 4):
+        case = make_case(eq, dim, nx, ny, nz, q, pol, fs, damp, W, L, nt=30, exact=0, kernel_variant=variant)
+        s = case.setup(Solver(case.desc))
+        assert s.kernel_path() == (0 if variant == 1 else 4)
+        s.run(0, 30)
+        s.sync()
+        res.append((s.seismogram(), {f: s.wavefield(f) for f in fields_of(eq, dim, L)}))
+        assert s.is_finite()
+        s.close()
+    assert np.abs(res[0][0]).max() > 0
+    assert np.array_equal(res[0][0], res[1][0])
+    for f in res[0][1]:
+        assert np.array_equal(res[0][1][f], res[1][1][f]), f
+
+
+@pytest.mark.parametrize("cfg", [c for c in SWEEP if c[1] == 2], ids=[sweep_id(c) for c in SWEEP if c[1] == 2])
+def test_tile2d_kernels_vs_oracle(cfg):
+    """The 2-D default path (kernel_variant 0 -> tile kernels) against the CPU oracle on the sweep cases."""
+    eq, dim, nx, ny, nz, q, pol, fs, damp, W, L = cfg
+    case = make_case(eq, dim, nx, ny, nz, q, pol, fs, damp, W, L, nt=40, exact=0, kernel_variant=0)
+    o, s = run_pair(case, 40)
+    assert s.kernel_path() == 4
+    assert rel_l2(s.seismogram(), o.seismogram()) <= TOL
 
 
 def test_fast_kernels_vs_oracle():

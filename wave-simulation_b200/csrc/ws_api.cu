@@ -29,6 +29,7 @@ struct WsError : public std::exception {
 #include "ws_prepare.cuh"
 #include "ws_tables.hpp"
 #include "ws_kernels_tma.cuh" // operand table (wsmarch::spec) and the TMA program type
+#include "ws_kernels_tile2d.cuh" // program type of the 2-D tile kernels
 #include "ws_kernels_sparse.cuh"
 
 namespace {
@@ -136,32 +137,36 @@ __device__ __forceinline__ void wsInject(const WsParams &P, int type, long long 
 
 // sequential = 1: one thread applies all sources in reference order (types P,VX,VY,VZ; ascending trace) so that
 // coincident sources accumulate deterministically; sequential = 0: all (target,index) pairs are distinct -> parallel.
+__device__ __forceinline__ void wsSourcesSequential(const WsParams &P, const WsAcq &a, int t)
+{
+    for (int type = 1; type <= 4; type++)
+        for (int s = 0; s < a.nsrc; s++) {
+            if (a.srcType[s] != type || a.srcOff[s] < 0)
+                continue;
+            const float v = a.srcStep ? a.srcStep[s] : a.srcSig[(size_t)s * a.nt + t];
+            wsInject(P, type, a.srcOff[s], v);
+        }
+}
+__device__ __forceinline__ void wsSourceOne(const WsParams &P, const WsAcq &a, int t, int s)
+{
+    if (s >= a.nsrc || a.srcOff[s] < 0)
+        return;
+    const float v = a.srcStep ? a.srcStep[s] : a.srcSig[(size_t)s * a.nt + t];
+    wsInject(P, a.srcType[s], a.srcOff[s], v);
+}
 __global__ void kSources(const __grid_constant__ WsParams P, WsAcq a, int sequential)
 {
     const int t = *a.tdev;
     if (sequential) {
         if (blockIdx.x != 0 || threadIdx.x != 0)
             return;
-        for (int type = 1; type <= 4; type++)
-            for (int s = 0; s < a.nsrc; s++) {
-                if (a.srcType[s] != type || a.srcOff[s] < 0)
-                    continue;
-                const float v = a.srcStep ? a.srcStep[s] : a.srcSig[(size_t)s * a.nt + t];
-                wsInject(P, type, a.srcOff[s], v);
-            }
-    } else {
-        const int s = blockIdx.x * blockDim.x + threadIdx.x;
-        if (s >= a.nsrc || a.srcOff[s] < 0)
-            return;
-        const float v = a.srcStep ? a.srcStep[s] : a.srcSig[(size_t)s * a.nt + t];
-        wsInject(P, a.srcType[s], a.srcOff[s], v);
-    }
+        wsSourcesSequential(P, a, t);
+    } else
+        wsSourceOne(P, a, t, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
-__global__ void kReceivers(const __grid_constant__ WsParams P, WsAcq a)
+__device__ __forceinline__ void wsReceiverOne(const WsParams &P, const WsAcq &a, int t, int r)
 {
-    const int t = *a.tdev;
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= a.nrec || a.recOff[r] < 0)
         return;
     const long long off = a.recOff[r];
@@ -193,8 +198,32 @@ __global__ void kReceivers(const __grid_constant__ WsParams P, WsAcq a)
     if (a.recStep)
         a.recStep[r] = v;
 }
+__global__ void kReceivers(const __grid_constant__ WsParams P, WsAcq a) { wsReceiverOne(P, a, *a.tdev, blockIdx.x * blockDim.x + threadIdx.x); }
 // the time index lives in device memory so that a captured CUDA graph is step-invariant
 __global__ void kAdvance(int *tdev) { *tdev = *tdev + 1; }
+// Sources, receivers and the time index of a step in ONE launch of one thread block (small acquisition geometries: three
+// launches of 2-5 us each weigh 3 % of a 2-D step of 0.25 ms).  Same order as the three kernels: all sources (block barrier
+// + fence), then the receivers, then the time index.
+constexpr int WS_ACQ_THREADS = 512, WS_ACQ_MAX_SRC = 2048, WS_ACQ_MAX_REC = 8192;
+__global__ void __launch_bounds__(WS_ACQ_THREADS) kAcquisition(const __grid_constant__ WsParams P, WsAcq a, int sequential)
+{
+    const int t = *a.tdev;
+    if (a.nsrc > 0) {
+        if (sequential) {
+            if (threadIdx.x == 0)
+                wsSourcesSequential(P, a, t);
+        } else {
+            for (int s = threadIdx.x; s < a.nsrc; s += blockDim.x)
+                wsSourceOne(P, a, t, s);
+        }
+        __threadfence();
+    }
+    __syncthreads();
+    for (int r = threadIdx.x; r < a.nrec; r += blockDim.x)
+        wsReceiverOne(P, a, t, r);
+    if (threadIdx.x == 0)
+        *a.tdev = t + 1;
+}
 
 template <typename T>
 struct DevBuf {
@@ -291,6 +320,9 @@ struct ws_solver {
     wstma::TmaProg tmaProg[2];
     int tmaNL[2] = {4, 4};
     void *tmaMaps = nullptr;
+    bool useTile = false; // 2-D tile kernels (ws_kernels_tile2d.cu) serve this configuration
+    wstile::TileProg tileProg[2];
+    void *tileMaps = nullptr;
     bool useTma = false; // TMA marching kernels (ws_kernels_tma.cu) serve this configuration
     DevBuf<float> fld[F_COUNT], mat[M_COUNT], psi[PSI_COUNT];
     bool matGiven[M_COUNT] = {};
@@ -353,6 +385,8 @@ struct ws_solver {
 #ifndef WS_EMULATE
         if (tmaMaps)
             wsTmaRelease(tmaMaps);
+        if (tileMaps)
+            wsTileRelease(tileMaps);
 #endif
         for (auto e : evPool)
             cudaEventDestroy(e);
@@ -1016,6 +1050,13 @@ void launchPass(ws_solver *s, int pass, int ylo, int yhi)
         }
     }
 #ifndef WS_EMULATE
+    if (s->useTile) {
+        const int n = wsLaunchTile(P, pass, s->tileProg[pass], s->stream);
+        if (n > 0) {
+            s->launches += n;
+            return;
+        }
+    }
     if (s->useTma) {
         const int n = wsLaunchTma(P, pass, s->tmaProg[pass], s->tmaNL[pass], s->stream);
         if (n > 0) {
@@ -1040,6 +1081,13 @@ void launchAcquisition(ws_solver *s, const float *srcStepDev, float *recStepDev)
     WsAcq a = s->acq;
     a.srcStep = srcStepDev;
     a.recStep = recStepDev;
+#ifndef WS_EMULATE /* (the host emulation runs the threads of a block one after the other: no block barriers) */
+    if (s->nsrc <= WS_ACQ_MAX_SRC && s->nrec <= WS_ACQ_MAX_REC && !(s->srcSequential && s->nsrc > 64)) {
+        WS_LAUNCH(kAcquisition, 1, WS_ACQ_THREADS, 0, s->stream, s->P, a, s->srcSequential ? 1 : 0);
+        s->launches++;
+        return;
+    }
+#endif
     if (s->nsrc > 0) {
         if (s->srcSequential)
             WS_LAUNCH(kSources, 1, 32, 0, s->stream, s->P, a, 1);
@@ -1524,7 +1572,7 @@ int ws_prepare(ws_solver *s)
             if (s->d.dim == 3)
                 requireMat(s, M_RIZ, "inverseDensityAverageZ");
             refreshParams(s);
-            s->useFast = s->useFastA = s->useTma = s->useMarch = false;
+            s->useFast = s->useFastA = s->useTma = s->useMarch = s->useTile = false;
             WS_CUDA_CHECK(cudaStreamSynchronize(s->stream));
             s->prepared = true;
             return;
@@ -1544,7 +1592,8 @@ int ws_prepare(ws_solver *s)
         }
         if (s->useFast || s->useFastA)
             s->fastMaps = wsFastPrepare(s->P, s->nyl + 2 * WS_HALO);
-        // kernel_variant: 0 = best available (3-D elastic TMA kernels, else TMA marching kernels, else cp.async marching kernels),
+        // kernel_variant: 0 = best available (3-D elastic TMA kernels, else TMA marching kernels in 3-D and the tile kernels in 2-D),
+        // 4 = 2-D tile kernels,
         // 1 = per-point kernels, 2 = cp.async marching kernels, 3 = TMA marching kernels
 #ifndef WS_EMULATE
         if (s->tmaMaps) {
@@ -1561,7 +1610,17 @@ int ws_prepare(ws_solver *s)
             s->tmaMaps = wsTmaPrepare(s->P, s->ainfo, s->nyl + 2 * WS_HALO, s->tmaProg, s->tmaNL);
         }
 #endif
-        s->useMarch = !s->useFast && !s->useTma && (s->d.kernel_variant == 0 || s->d.kernel_variant == 2 || s->d.kernel_variant == 3) && wsMarchSupported(s->P, s->exact);
+#ifndef WS_EMULATE
+        if (s->tileMaps) {
+            wsTileRelease(s->tileMaps);
+            s->tileMaps = nullptr;
+        }
+        s->P.tileMaps = nullptr;
+        s->useTile = !s->useFast && !s->useTma && s->d.dim == 2 && (s->d.kernel_variant == 0 || s->d.kernel_variant == 4) && wsTileSupported(s->P, s->ainfo, s->exact);
+        if (s->useTile)
+            s->tileMaps = wsTilePrepare(s->P, s->ainfo, s->nyl + 2 * WS_HALO, s->tileProg);
+#endif
+        s->useMarch = !s->useFast && !s->useTma && !s->useTile && (s->d.kernel_variant == 0 || s->d.kernel_variant >= 2) && wsMarchSupported(s->P, s->exact);
         if (s->useMarch)
             wsMarchPrepare(s->P);
         WS_CUDA_CHECK(cudaStreamSynchronize(s->stream));
@@ -2153,6 +2212,6 @@ int ws_last_timing(ws_solver *s, int which, float *ms)
 void *ws_stream(ws_solver *s) { return s ? (void *)s->stream : nullptr; }
 
 int ws_uses_fast_kernels(const ws_solver *s) { return s && s->useFast ? 1 : 0; }
-int ws_kernel_path(const ws_solver *s) { return !s ? -1 : (s->useFast ? 2 : (s->useTma ? 3 : (s->useMarch ? 1 : 0))); }
+int ws_kernel_path(const ws_solver *s) { return !s ? -1 : (s->useFast ? 2 : (s->useTma ? 3 : (s->useTile ? 4 : (s->useMarch ? 1 : 0)))); }
 
 } // extern "C"

@@ -86,6 +86,8 @@ struct WsParams {
     int marchStages;  // developer switch (env WS_MARCH_STAGES): depth of the stage ring, 0 = chosen from the stage size
     int tmaChunk;     // planes per thread block of the TMA marching kernels (ws_kernels_tma.cuh)
     const void *tmaMaps; // device array of CUtensorMap (TMA marching kernels)
+    const void *tileMaps; // device array of CUtensorMap (2-D tile kernels, ws_kernels_tile2d.cuh)
+    int tileTY;           // rows per tile of the 2-D tile kernels
     int fastDebug;    // developer switch (env WS_FAST_DEBUG): 1 = consumers skip the arithmetic and the stores (memory-side ceiling of the tiling)
     int fastFlags;    // developer switch (env WS_FAST_FLAGS): bit 0 = L2 eviction-priority hints on the TMA loads, bit 1 = CPML-layer tiles in a launch of their own (default 2)
     const int *fastTiles; // tile list of the tiled kernels ((z tile << 16) | x tile), layer tiles first

@@ -87,6 +87,21 @@ __host__ __device__ constexpr int findIn(const int *a, int n, int v)
             return k;
     return -1;
 }
+// every field a half-step differentiates (along x / z: `t`, along y: `qf`), each once: the halo tiles of the kernels that
+// take the y stencils from shared memory too (2-D tile kernels, ws_kernels_tile2d.cuh)
+struct HaloSet {
+    int n; int f[8];
+};
+__host__ __device__ constexpr HaloSet haloSet(const Lists &S)
+{
+    HaloSet U{0, {}};
+    for (int k = 0; k < S.nt; k++)
+        U.f[U.n++] = S.t[k];
+    for (int k = 0; k < S.nq; k++)
+        if (findIn(S.t, S.nt, S.qf[k]) < 0)
+            U.f[U.n++] = S.qf[k];
+    return U;
+}
 
 // NL = consecutive x points per thread: 4 (128-bit accesses, index arithmetic shared by the points) or 1 (more resident
 // threads per staged byte: the half-steps whose operands fill the shared memory, e.g. 3-D viscoelastic)
@@ -134,7 +149,9 @@ template <int N> __device__ __forceinline__ void stv(float *p, const FV<N> &a) {
 // surface): a thread-block-uniform property of (tile, plane), so the boundary code disappears from that instantiation.
 // G = tile geometry; PB = planes per stage (the TMA kernels of ws_kernels_tma.cuh stage groups of PB planes in 2-D: every
 // entry of a stage then holds PB tiles, one per plane, and `st` points at the tile of the plane being computed).
-template <int EQ, int DIM, int Q, int PASS, int NL, bool INTR, class G_ = Geo<DIM, Q, NL>, int PB = 1>
+// YSM = the y stencils are read from the halo tiles as well (2-D tile kernels: a halo tile holds the rows y - H .. y + H of
+// every differentiated field, LDX floats apart; no register queues, no feed tiles).
+template <int EQ, int DIM, int Q, int PASS, int NL, bool INTR, class G_ = Geo<DIM, Q, NL>, int PB = 1, bool YSM = false>
 struct MPt {
     using A = Ar<false>;
     using V = FV<NL>;
@@ -142,7 +159,7 @@ struct MPt {
     static constexpr int H = Q / 2;
     static constexpr int NQ = spec(EQ, DIM, PASS).nq;
     static constexpr int TS = G::TS, PS = PB * G::NP; // floats between two halo-tile entries / two plain-tile entries
-    static constexpr int O_Q = 0, O_F = O_Q + NQ * PS, O_M = O_F + spec(EQ, DIM, PASS).nf * PS, O_R = O_M + spec(EQ, DIM, PASS).nm * PS;
+    static constexpr int O_Q = 0, O_F = O_Q + (YSM ? 0 : NQ) * PS, O_M = O_F + spec(EQ, DIM, PASS).nf * PS, O_R = O_M + spec(EQ, DIM, PASS).nm * PS;
     const WsParams &P;
     int x0, z, nAct; // nAct = lanes inside the grid (NL except in a ragged last column or an inactive row)
     int ly, gy;
@@ -199,7 +216,23 @@ struct MPt {
         constexpr int fw = (OP & 1) == 0 ? 1 : 0; // forward operators: taps -H+1..H, backward: -H..H-1
         constexpr Lists S = spec(EQ, DIM, PASS);
         V acc(0.0f);
-        if constexpr (axis == 1) {
+        if constexpr (axis == 1 && YSM) {
+            constexpr HaloSet U = haloSet(S);
+            constexpr int ti = findIn(U.f, U.n, F);
+            if constexpr (ti >= 0) {
+                const float *p = st + ti * TS + so - H * G::LDX;
+                if (INTR || ry == H) {
+#pragma unroll
+                    for (int j = 0; j < Q; j++)
+                        acc = A::madd(OP >= 6 ? P.cwy[j] : P.cw[j], ldv<NL>(p + (j + fw) * G::LDX), acc);
+                } else {
+                    const float *__restrict__ w = P.tab + ((size_t)OP * (2 * H + 1) + ry) * (Q + 1);
+#pragma unroll
+                    for (int j = 0; j <= Q; j++)
+                        acc = A::madd(__ldg(w + j), ldv<NL>(p + j * G::LDX), acc);
+                }
+            }
+        } else if constexpr (axis == 1) {
             constexpr int qi = findIn(S.qf, S.nq, F);
             if constexpr (qi >= 0) {
                 if (INTR || ry == H) { // interior row: weights from the constant bank, the zero tap of the table row skipped
@@ -214,7 +247,7 @@ struct MPt {
                 }
             }
         } else if constexpr (axis == 2) {
-            constexpr int ti = findIn(S.t, S.nt, F);
+            constexpr int ti = YSM ? findIn(haloSet(S).f, haloSet(S).n, F) : findIn(S.t, S.nt, F);
             if constexpr (ti >= 0) {
                 const float *p = st + ti * TS + so - H * G::LDX;
                 if (INTR || rz == H) {
@@ -229,7 +262,7 @@ struct MPt {
                 }
             }
         } else {
-            constexpr int ti = findIn(S.t, S.nt, F);
+            constexpr int ti = YSM ? findIn(haloSet(S).f, haloSet(S).n, F) : findIn(S.t, S.nt, F);
             if constexpr (ti >= 0) {
                 // the row around the points: offsets -H .. H+NL-1 (NL = 4: aligned 16-byte loads from -HX on)
                 constexpr int HX = G::HX;

@@ -37,6 +37,14 @@ void *wsTmaPrepare(WsParams &P, const WsArenaInfo &A, int nyp, wstma::TmaProg pr
 void wsTmaRelease(void *maps);
 int wsLaunchTma(const WsParams &P, int pass, const wstma::TmaProg &prog, int nl, cudaStream_t st);
 
+// 2-D tile kernels (ws_kernels_tile2d.cu): every 2-D equation type, compile-time FD order, FMA arithmetic; one thread block per
+// 128 x 8 / 16 tile, all operands of the tile fetched by a handful of TMA boxes
+namespace wstile { struct TileProg; }
+bool wsTileSupported(const WsParams &P, const WsArenaInfo &A, bool exact);
+void *wsTilePrepare(WsParams &P, const WsArenaInfo &A, int nyp, wstile::TileProg prog[2]);
+void wsTileRelease(void *maps);
+int wsLaunchTile(const WsParams &P, int pass, const wstile::TileProg &prog, cudaStream_t st);
+
 #ifndef WS_EMULATE
 #include <mutex>
 #include <set>
