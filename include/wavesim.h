@@ -130,6 +130,27 @@ int ws_get_wavefield(ws_solver *s, const char *comp, float *host, size_t n);
 int ws_set_wavefield(ws_solver *s, const char *comp, const float *host, size_t n);
 int ws_is_finite(ws_solver *s, int32_t *flag); /* Wavefields::isFinite + SeismogramHandler::isFinite, Simulation.cpp:519 */
 
+/* --- wavefield objects and their operators (hooks of WAVE-Inversion) ------------------------------------- *
+ * The reference's time loop and the inversion code that links libSimulation work on whole Wavefields objects: a copy taken
+ * before a step (`*wavefieldsTemp = *wavefields`, Simulation.cpp:450), `-=`, `+=`, `*= scalar`, `*= vector`
+ * (Wavefields/Wavefields.hpp:62-80; every concrete class applies the operator to all of its components incl. the memory
+ * variables, e.g. Wavefields3Dviscoelastic.cpp:305-330).  A ws_wavefields is such a second set of components, resident in HBM in
+ * the layout of the handle it was created from; NULL stands for the solver's own (live) wavefields.  Element-wise fp32
+ * operations, one rounding each, asynchronous on the handle's stream.                                                          */
+typedef struct ws_wavefields ws_wavefields;
+int ws_wavefields_create(ws_solver *s, ws_wavefields **out);  /* all components zero (Wavefields::init)                        */
+void ws_wavefields_destroy(ws_wavefields *w);
+int ws_wavefields_assign(ws_solver *s, ws_wavefields *dst, const ws_wavefields *src);        /* operator=                       */
+int ws_wavefields_plus_assign(ws_solver *s, ws_wavefields *dst, const ws_wavefields *src);   /* operator+=                      */
+int ws_wavefields_minus_assign(ws_solver *s, ws_wavefields *dst, const ws_wavefields *src);  /* operator-=                      */
+int ws_wavefields_times_assign(ws_solver *s, ws_wavefields *dst, float rhs);                 /* operator*=(ValueType)           */
+/* operator*=(DenseVector): `host` holds this rank's slab of the vector (n = nyl*nz*nx values, like ws_set_wavefield)           */
+int ws_wavefields_times_assign_vector(ws_solver *s, ws_wavefields *dst, const float *host, size_t n);
+int ws_wavefields_get(ws_solver *s, const ws_wavefields *w, const char *comp, float *host, size_t n); /* like ws_get_wavefield */
+/* `*wavefields *= compensation` after every time step (Simulation.cpp:455-456; Modelparameter::getCompensation, EM only): the
+ * vector stays in HBM and the multiplication rides in the captured step graph.  host = NULL switches it off.                    */
+int ws_set_step_scaling(ws_solver *s, const float *host, size_t n);
+
 /* --- multi-GPU (replaces src/Partitioning; y-slab decomposition) --------------------------------- *
  * One process per GPU.  Rank 0 creates an id with ws_comm_unique_id, the launcher broadcasts the 128 bytes, every
  * rank calls ws_comm_init.  Halo planes are exchanged with ncclSend/ncclRecv on a communication stream overlapped

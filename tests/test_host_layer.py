@@ -551,3 +551,145 @@ def test_product_driver_variable_grid_on_gpu(tmp_path, dim, T):
     _run_product(cfg, tmp, {"WS_NUM_GPUS": "1"})
     f = read_lmf_matrix(os.path.join(tmp, "seismograms", "seismogram.shot_0.p.lmf"))
     assert rel_l2(f, s) <= 1.0e-5
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# hooks of the inversion workflow: wavefield operators, compensation
+# ---------------------------------------------------------------------------------------------------------------------
+CONFIG_2D_TMEM = """# 2-D TMEz modelling, homogeneous lossy medium (ModelRead=0)
+dimension=2D
+equationType=tmem
+NX=60
+NY=50
+NZ=1
+UseVariableGrid=0
+useVariableFDoperators=0
+useStencilMatrix=1
+NumShotDomains=1
+DH=0.02
+DT=2.0e-11
+T={T}
+spatialFDorder=4
+ModelRead=0
+ModelFilename=model/model
+fileFormat=1
+mur=1
+sigma=0.02
+epsilonr=4
+numRelaxationMechanisms=0;
+FreeSurface=0
+DampingBoundary=2
+BoundaryWidth=8
+DampingCoeff=8.0
+VMaxCPML=3.0e8
+CenterFrequencyCPML=1.0e8
+NPower=4
+KMaxCPML=1
+SourceFilename=acq/sources
+ReceiverFilename=acq/receiver
+SeismogramFilename=seismograms/seismogram
+initSourcesFromSU=0
+initReceiverFromSU=0
+SeismogramFormat=1
+normalizeTraces=0
+useReceiversPerShot=0
+writeSource=0
+seismoDT=2.0e-11
+snapType=0
+WavefieldFileName=wavefields/wavefield
+tFirstSnapshot=0
+tLastSnapshot=2
+tIncSnapshot=0.1
+verbose=0
+kernelVariant={kvar}
+compensation={comp}
+"""
+
+
+def setup_tmem_case(tmp, T="8.0e-10", comp=1, kvar=1):
+    for d in ("model", "acq", "seismograms", "wavefields"):
+        os.makedirs(os.path.join(tmp, d), exist_ok=True)
+    open(os.path.join(tmp, "acq", "sources.txt"), "w").write("# sourceNo X Y Z type wType wShape fc amp tShift\n1 30 25 0 1 1 1 1.0e8 1.0 0.0\n")
+    open(os.path.join(tmp, "acq", "receiver.txt"), "w").write("# X Y Z type\n40 30 0 1\n22 20 0 1\n")
+    cfg = os.path.join(tmp, "configuration.txt")
+    open(cfg, "w").write(CONFIG_2D_TMEM.format(T=T, comp=comp, kvar=kvar))
+    return cfg
+
+
+def tmem_oracle_with_compensation(nt, comp_on):
+    from wsharness import TYPE, idx1d, make_desc, ricker
+    nx, ny = 60, 50
+    eps0, mu0 = np.float32(8.8541878176e-12), np.float32(1.2566370614e-6)
+    d = make_desc(2, "tmem", nx, ny, 1, dh=0.02, dt=2e-11, nt=nt, fd_order=4, edge_policy=0, free_surface=0, damping=2, boundary_width=8,
+                  vmax_cpml=3e8, fc_cpml=1e8, exact_arith=0)
+    n = nx * ny
+    m = dict(magneticPermeability=np.full(n, mu0, np.float32), electricConductivity=np.full(n, 0.02, np.float32),
+             dielectricPermittivity=np.full(n, np.float32(4) * eps0, np.float32))
+    o = Oracle(d)
+    for k, v in m.items():
+        o.set_material(k, v)
+    o.prepare()
+    o.set_sources([TYPE["P"]], [idx1d(30, 25, 0, nx, 1)], ricker(nt, 2e-11, 1e8, 1.0, 0.0)[None, :])
+    o.set_receivers([TYPE["P"], TYPE["P"]], [idx1d(40, 30, 0, nx, 1), idx1d(22, 20, 0, nx, 1)])
+    o.reset()
+    v = (m["electricConductivity"] / m["dielectricPermittivity"]) * np.float32(1 * 2e-11)  # Modelparameter.cpp:135-138
+    comp = np.exp(v.astype(np.float32)).astype(np.float32)
+    for t in range(nt):
+        o.run(t, t + 1)
+        if comp_on:
+            for f in ("HX", "HY", "EZ"):
+                o.set_wavefield(f, o.wavefield(f) * comp)
+    return o.seismogram()
+
+
+def test_driver_compensation_in_the_time_loop(driver, tmp_path):
+    """`compensation=1` (Simulation.cpp:441-456): the wavefields are multiplied by exp(sigma/eps DT) after every step; checked
+    against the oracle stepped one step at a time with the multiplication in numpy, and against the uncompensated run."""
+    tmp = str(tmp_path)
+    run(driver, setup_tmem_case(tmp, comp=1), tmp)
+    s = read_mtx(os.path.join(tmp, "seismograms", "seismogram.shot_1.ez.mtx"))
+    want, plain = tmem_oracle_with_compensation(40, True), tmem_oracle_with_compensation(40, False)
+    assert s.shape == want.shape == (2, 40)
+    assert rel_l2(s, want) <= 1.0e-5
+    assert rel_l2(plain, want) > 1.0e-2  # the factor matters in this medium
+    run(driver, setup_tmem_case(tmp, comp=0), tmp)
+    assert rel_l2(read_mtx(os.path.join(tmp, "seismograms", "seismogram.shot_1.ez.mtx")), plain) <= 1.0e-5
+
+
+def build_wavefield_ops(tmp, emu):
+    subprocess.check_call(["make", "-s", "-C", HOST, "libSimulation_host.a"])
+    exe = os.path.join(tmp, "test_wavefield_ops")
+    src = os.path.join(ROOT, "tests", "host", "test_wavefield_ops.cpp")
+    lib = ["-L" + EMU_DIR, "-lwavesim_emu", "-Wl,-rpath," + EMU_DIR, "-fopenmp"] if emu else \
+        ["-L" + os.path.join(ROOT, "wave-simulation_b200", "csrc"), "-lwavesim_cuda", "-Wl,-rpath," + os.path.join(ROOT, "wave-simulation_b200", "csrc")]
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-pthread", "-I" + HOST, src, os.path.join(HOST, "libSimulation_host.a")] + lib + ["-o", exe])
+    return exe
+
+
+@pytest.mark.parametrize("which", ["elastic", "tmem"])
+def test_host_wavefield_operators(driver, tmp_path, which):
+    """Wavefields operator=, -=, +=, *= scalar, *= vector on whole objects and Modelparameter::getCompensation through the host
+    classes (tests/host/test_wavefield_ops.cpp), on the emulation build of the library."""
+    tmp = str(tmp_path)
+    cfg = setup_case(tmp, T=0.1) if which == "elastic" else setup_tmem_case(tmp)
+    p = subprocess.run([build_wavefield_ops(tmp, True), cfg], cwd=tmp, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0 and "wavefield operator tests OK" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("which", ["elastic", "tmem"])
+def test_host_wavefield_operators_on_gpu(tmp_path, which):
+    subprocess.check_call(["make", "-s", "-C", HOST])
+    tmp = str(tmp_path)
+    cfg = setup_case(tmp, T=0.1, kvar=0) if which == "elastic" else setup_tmem_case(tmp, kvar=0)
+    p = subprocess.run([build_wavefield_ops(tmp, False), cfg], cwd=tmp, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0 and "wavefield operator tests OK" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
+
+
+@pytest.mark.gpu
+def test_product_driver_compensation_on_gpu(tmp_path):
+    subprocess.check_call(["make", "-s", "-C", HOST])
+    tmp = str(tmp_path)
+    run(os.path.join(HOST, "Simulation"), setup_tmem_case(tmp, comp=1, kvar=0), tmp)
+    s = read_mtx(os.path.join(tmp, "seismograms", "seismogram.shot_1.ez.mtx"))
+    assert rel_l2(s, tmem_oracle_with_compensation(40, True)) <= 1.0e-5

@@ -147,6 +147,15 @@ def _load_ws_lib(path):
     lib.ws_stream.argtypes = [C.c_void_p]
     lib.ws_uses_fast_kernels.argtypes = [C.c_void_p]
     lib.ws_kernel_path.argtypes = [C.c_void_p]
+    if hasattr(lib, "ws_wavefields_create"):
+        lib.ws_wavefields_destroy.argtypes = [C.c_void_p]
+        lib.ws_wavefields_destroy.restype = None
+        for name in ("assign", "plus_assign", "minus_assign"):
+            getattr(lib, "ws_wavefields_" + name).argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.ws_wavefields_times_assign.argtypes = [C.c_void_p, C.c_void_p, C.c_float]
+        lib.ws_wavefields_times_assign_vector.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.c_size_t]
+        lib.ws_wavefields_get.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.POINTER(C.c_float), C.c_size_t]
+        lib.ws_set_step_scaling.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_size_t]
     return lib
 
 
@@ -220,6 +229,43 @@ class Solver(SolverBase):
         ms = C.c_float()
         self._check(self.lib.ws_last_timing(self.h, which, C.byref(ms)), "last_timing")
         return ms.value
+
+    # wavefield objects (Wavefields/Wavefields.hpp:62-80); None = the solver's own wavefields
+    def wavefields_create(self):
+        w = C.c_void_p()
+        self._check(self.lib.ws_wavefields_create(self.h, C.byref(w)), "wavefields_create")
+        return w
+
+    def wavefields_destroy(self, w):
+        self.lib.ws_wavefields_destroy(w)
+
+    def wavefields_assign(self, dst, src):
+        self._check(self.lib.ws_wavefields_assign(self.h, dst, src), "wavefields_assign")
+
+    def wavefields_plus_assign(self, dst, src):
+        self._check(self.lib.ws_wavefields_plus_assign(self.h, dst, src), "wavefields_plus_assign")
+
+    def wavefields_minus_assign(self, dst, src):
+        self._check(self.lib.ws_wavefields_minus_assign(self.h, dst, src), "wavefields_minus_assign")
+
+    def wavefields_times_assign(self, dst, rhs):
+        if np.ndim(rhs) == 0:
+            self._check(self.lib.ws_wavefields_times_assign(self.h, dst, C.c_float(float(rhs))), "wavefields_times_assign")
+        else:
+            a = _f32(rhs).ravel()
+            self._check(self.lib.ws_wavefields_times_assign_vector(self.h, dst, _fp(a), C.c_size_t(a.size)), "wavefields_times_assign_vector")
+
+    def wavefields_get(self, w, comp):
+        out = np.empty(self.n_local, dtype=np.float32)
+        self._check(self.lib.ws_wavefields_get(self.h, w, comp.encode(), _fp(out), C.c_size_t(out.size)), "wavefields_get")
+        return out
+
+    def set_step_scaling(self, vec):
+        if vec is None:
+            self._check(self.lib.ws_set_step_scaling(self.h, None, C.c_size_t(0)), "set_step_scaling")
+        else:
+            a = _f32(vec).ravel()
+            self._check(self.lib.ws_set_step_scaling(self.h, _fp(a), C.c_size_t(a.size)), "set_step_scaling")
 
     def is_finite(self):
         f = C.c_int32()

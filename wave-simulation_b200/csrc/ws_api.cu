@@ -14,6 +14,7 @@
 #include <dlfcn.h>
 #include <exception>
 #include <map>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -204,6 +205,7 @@ __global__ void kAdvance(int *tdev) { *tdev = *tdev + 1; }
 // Sources, receivers and the time index of a step in ONE launch of one thread block (small acquisition geometries: three
 // launches of 2-5 us each weigh 3 % of a 2-D step of 0.25 ms).  Same order as the three kernels: all sources (block barrier
 // + fence), then the receivers, then the time index.
+#ifndef WS_EMULATE
 constexpr int WS_ACQ_THREADS = 512, WS_ACQ_MAX_SRC = 2048, WS_ACQ_MAX_REC = 8192;
 __global__ void __launch_bounds__(WS_ACQ_THREADS) kAcquisition(const __grid_constant__ WsParams P, WsAcq a, int sequential)
 {
@@ -223,6 +225,43 @@ __global__ void __launch_bounds__(WS_ACQ_THREADS) kAcquisition(const __grid_cons
         wsReceiverOne(P, a, t, r);
     if (threadIdx.x == 0)
         *a.tdev = t + 1;
+}
+#endif
+
+// element-wise operators of the wavefield objects (Wavefields.hpp:62-80): op 0 dst = src, 1 dst += src, 2 dst -= src
+__global__ void kWfBinary(float *__restrict__ dst, const float *__restrict__ src, size_t n, int op)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const float b = src[i];
+    dst[i] = op == 0 ? b : (op == 1 ? __fadd_rn(dst[i], b) : __fsub_rn(dst[i], b));
+}
+__global__ void kWfScale(float *__restrict__ dst, size_t n, float a)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+        dst[i] = __fmul_rn(dst[i], a);
+}
+__global__ void kWfScaleVec(float *__restrict__ dst, const float *__restrict__ vec, size_t n)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+        dst[i] = __fmul_rn(dst[i], vec[i]);
+}
+// every component of the live wavefields times a grid vector, own planes only (the ghost planes belong to the neighbours)
+struct WsFieldTable {
+    float *p[F_COUNT];
+    int n;
+};
+__global__ void kWfScaleVecAll(WsFieldTable t, const float *__restrict__ vec, size_t first, size_t n)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const float v = vec[first + i];
+    for (int k = 0; k < t.n; k++)
+        t.p[k][first + i] = __fmul_rn(t.p[k][first + i], v);
 }
 
 template <typename T>
@@ -332,6 +371,7 @@ struct ws_solver {
     DevBuf<float> tab, cax, cbx, caxh, cbxh, cay, cby, cayh, cbyh, caz, cbz, cazh, cbzh, absCoeff;
     DevBuf<float> sH, sV, sRH[4], sRV[4];
     DevBuf<float> scratch; // dense staging buffer for pack/unpack
+    DevBuf<float> stepScale; // `*wavefields *= compensation` after every step (ws_set_step_scaling), padded like a wavefield; null = off
     DevBuf<int> flag;
     WsParams P{};
     bool prepared = false;
@@ -1103,6 +1143,20 @@ void launchAcquisition(ws_solver *s, const float *srcStepDev, float *recStepDev)
     s->launches++;
 }
 
+// Simulation.cpp:455-456 `*wavefields *= compensation` (all components, after the step incl. source injection and recording)
+void launchStepScaling(ws_solver *s)
+{
+    if (!s->stepScale.p)
+        return;
+    WsFieldTable t{};
+    for (int k = 0; k < F_COUNT; k++)
+        if (s->fld[k].p)
+            t.p[t.n++] = s->fld[k].p;
+    const size_t first = s->sparse ? 0 : (size_t)WS_HALO * (size_t)s->plane, n = s->sparse ? (size_t)s->total : (size_t)s->nyl * (size_t)s->plane;
+    WS_LAUNCH(kWfScaleVecAll, (unsigned)((n + 255) / 256), 256, 0, s->stream, t, s->stepScale.p, first, n);
+    s->launches++;
+}
+
 // one reference time step = ForwardSolver::run(...), enqueued asynchronously
 // ---------------------------------------------------------------------------------------------------------------------
 // operator-given mode (ws_kernels_sparse.cuh)
@@ -1176,6 +1230,7 @@ void enqueueSparseStep(ws_solver *s, const float *srcStepDev, float *recStepDev,
     if (ev)
         WS_CUDA_CHECK(cudaEventRecord(ev[3], s->stream));
     launchAcquisition(s, srcStepDev, recStepDev);
+    launchStepScaling(s);
 }
 
 // haloLanded: the halo exchange of the previous step is known to have completed (first step of a captured graph: the
@@ -1233,6 +1288,7 @@ void enqueueStep(ws_solver *s, const float *srcStepDev, float *recStepDev, cudaE
         s->launches++;
     }
     launchAcquisition(s, srcStepDev, recStepDev);
+    launchStepScaling(s);
     if (multi) {
         WS_CUDA_CHECK(cudaEventRecord(evCompute, s->stream));
         WS_CUDA_CHECK(cudaStreamWaitEvent(s->commStream, evCompute, 0));
@@ -2166,6 +2222,156 @@ int ws_set_surface(ws_solver *s, int64_t n, const int32_t *idx)
             s->spSurf.upload(std::vector<int>(idx, idx + n));
     });
 }
+
+
+} // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------------
+// wavefield objects and their operators (Wavefields/Wavefields.hpp:62-80)
+// ---------------------------------------------------------------------------------------------------------------------
+struct ws_wavefields {
+    ws_solver *owner = nullptr;
+    DevBuf<float> f[F_COUNT]; // the slots the owner has, each `total` floats in the owner's layout
+};
+
+namespace {
+// this rank's slab of a grid vector (dense, nyl*nz*nx values) -> a zero-padded array in the layout of the wavefields
+void uploadLocalPadded(ws_solver *s, const float *host, size_t n, DevBuf<float> &out)
+{
+    out.alloc((size_t)s->total);
+    out.zero(s->stream);
+    if (s->sparse) {
+        WS_CUDA_CHECK(cudaMemcpyAsync(out.p, host, n * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+        return;
+    }
+    ensureScratch(s, n);
+    WS_CUDA_CHECK(cudaMemcpyAsync(s->scratch.p, host, n * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    packPlanes(s, s->scratch.p, out.p, 0, s->nyl);
+}
+float *wfSlot(ws_solver *s, ws_wavefields *w, int k) { return w ? w->f[k].p : s->fld[k].p; }
+const float *wfSlot(ws_solver *s, const ws_wavefields *w, int k) { return w ? w->f[k].p : s->fld[k].p; }
+void wfCheck(ws_solver *s, const ws_wavefields *a, const ws_wavefields *b)
+{
+    WS_REQUIRE(s, WS_EINVAL, "null argument");
+    WS_REQUIRE((!a || a->owner == s) && (!b || b->owner == s), WS_EINVAL, "the wavefield object belongs to another solver");
+}
+int wfBinary(ws_solver *s, ws_wavefields *dst, const ws_wavefields *src, int op)
+{
+    return guarded([&] {
+        wfCheck(s, dst, src);
+        WS_REQUIRE(dst != src, WS_EINVAL, "source and destination are the same wavefield object");
+        setDevice(s);
+        const size_t n = (size_t)s->total;
+        for (int k = 0; k < F_COUNT; k++)
+            if (s->fld[k].p) {
+                WS_LAUNCH(kWfBinary, (unsigned)((n + 255) / 256), 256, 0, s->stream, wfSlot(s, dst, k), wfSlot(s, src, k), n, op);
+                s->launches++;
+            }
+        WS_CUDA_CHECK(cudaGetLastError());
+    });
+}
+} // namespace
+
+extern "C" {
+
+int ws_wavefields_create(ws_solver *s, ws_wavefields **out)
+{
+    return guarded([&] {
+        WS_REQUIRE(s && out, WS_EINVAL, "null argument");
+        setDevice(s);
+        std::unique_ptr<ws_wavefields> w(new ws_wavefields);
+        w->owner = s;
+        for (int k = 0; k < F_COUNT; k++)
+            if (s->fld[k].p) {
+                w->f[k].alloc((size_t)s->total);
+                w->f[k].zero(s->stream);
+            }
+        WS_CUDA_CHECK(cudaStreamSynchronize(s->stream));
+        *out = w.release();
+    });
+}
+void ws_wavefields_destroy(ws_wavefields *w)
+{
+    if (!w)
+        return;
+    if (w->owner) {
+        setDevice(w->owner);
+        cudaStreamSynchronize(w->owner->stream);
+    }
+    delete w;
+}
+int ws_wavefields_assign(ws_solver *s, ws_wavefields *dst, const ws_wavefields *src) { return wfBinary(s, dst, src, 0); }
+int ws_wavefields_plus_assign(ws_solver *s, ws_wavefields *dst, const ws_wavefields *src) { return wfBinary(s, dst, src, 1); }
+int ws_wavefields_minus_assign(ws_solver *s, ws_wavefields *dst, const ws_wavefields *src) { return wfBinary(s, dst, src, 2); }
+int ws_wavefields_times_assign(ws_solver *s, ws_wavefields *dst, float rhs)
+{
+    return guarded([&] {
+        wfCheck(s, dst, nullptr);
+        setDevice(s);
+        const size_t n = (size_t)s->total;
+        for (int k = 0; k < F_COUNT; k++)
+            if (s->fld[k].p) {
+                WS_LAUNCH(kWfScale, (unsigned)((n + 255) / 256), 256, 0, s->stream, wfSlot(s, dst, k), n, rhs);
+                s->launches++;
+            }
+        WS_CUDA_CHECK(cudaGetLastError());
+    });
+}
+int ws_wavefields_times_assign_vector(ws_solver *s, ws_wavefields *dst, const float *host, size_t n)
+{
+    return guarded([&] {
+        wfCheck(s, dst, nullptr);
+        WS_REQUIRE(host, WS_EINVAL, "null argument");
+        WS_REQUIRE(n == (size_t)s->nx * s->nyl * s->nz, WS_EINVAL, "size mismatch");
+        setDevice(s);
+        DevBuf<float> vec;
+        uploadLocalPadded(s, host, n, vec);
+        // own planes only: the pads of the vector are zero, and the ghost planes of live wavefields belong to the neighbours
+        const size_t first = s->sparse ? 0 : (size_t)WS_HALO * (size_t)s->plane, cnt = s->sparse ? (size_t)s->total : (size_t)s->nyl * (size_t)s->plane;
+        for (int k = 0; k < F_COUNT; k++)
+            if (s->fld[k].p) {
+                WS_LAUNCH(kWfScaleVec, (unsigned)((cnt + 255) / 256), 256, 0, s->stream, wfSlot(s, dst, k) + first, vec.p + first, cnt);
+                s->launches++;
+            }
+        WS_CUDA_CHECK(cudaGetLastError());
+        WS_CUDA_CHECK(cudaStreamSynchronize(s->stream)); // `vec` is released on return
+    });
+}
+int ws_wavefields_get(ws_solver *s, const ws_wavefields *w, const char *comp, float *host, size_t n)
+{
+    if (!w)
+        return ws_get_wavefield(s, comp, host, n);
+    return guarded([&] {
+        wfCheck(s, w, nullptr);
+        WS_REQUIRE(comp && host, WS_EINVAL, "null argument");
+        setDevice(s);
+        auto it = s->fldSlot.find(comp);
+        WS_REQUIRE(it != s->fldSlot.end(), WS_EINVAL, std::string("wavefield '") + comp + "' does not exist in this modelling");
+        WS_REQUIRE(n == (size_t)s->nx * s->nyl * s->nz, WS_EINVAL, "size mismatch");
+        downloadLocal(s, w->f[it->second].p, host);
+    });
+}
+int ws_set_step_scaling(ws_solver *s, const float *host, size_t n)
+{
+    return guarded([&] {
+        WS_REQUIRE(s, WS_EINVAL, "null argument");
+        setDevice(s);
+        invalidateGraph(s);
+        WS_CUDA_CHECK(cudaStreamSynchronize(s->stream));
+        if (!host) {
+            s->stepScale.release();
+            return;
+        }
+        WS_REQUIRE(n == (size_t)s->nx * s->nyl * s->nz, WS_EINVAL, "size mismatch");
+        uploadLocalPadded(s, host, n, s->stepScale);
+        WS_CUDA_CHECK(cudaStreamSynchronize(s->stream));
+    });
+}
+
+} // extern "C"
+
+
+extern "C" {
 
 int ws_comm_unique_id(void *id128)
 {

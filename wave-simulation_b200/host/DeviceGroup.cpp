@@ -169,6 +169,53 @@ void ForwardSolver::DeviceGroup::getSeismogram(std::vector<float> &all)
         check(ws_get_seismogram(handles[r], all.data()));
 }
 
+ForwardSolver::DeviceGroup::FieldSet ForwardSolver::DeviceGroup::createFieldSet()
+{
+    FieldSet set(size(), nullptr);
+    forEach([&](IndexType r) { check(ws_wavefields_create(handles[r], &set[r])); });
+    return set;
+}
+
+void ForwardSolver::DeviceGroup::destroyFieldSet(FieldSet &set)
+{
+    for (auto *w : set)
+        ws_wavefields_destroy(w);
+    set.clear();
+}
+
+void ForwardSolver::DeviceGroup::fieldSetBinary(FieldSet const *dst, FieldSet const *src, int op)
+{
+    forEach([&](IndexType r) {
+        ws_wavefields *d = dst ? (*dst)[r] : nullptr;
+        const ws_wavefields *s = src ? (*src)[r] : nullptr;
+        check(op == 0 ? ws_wavefields_assign(handles[r], d, s) : (op == 1 ? ws_wavefields_plus_assign(handles[r], d, s) : ws_wavefields_minus_assign(handles[r], d, s)));
+    });
+}
+
+void ForwardSolver::DeviceGroup::fieldSetScale(FieldSet const *dst, float rhs)
+{
+    forEach([&](IndexType r) { check(ws_wavefields_times_assign(handles[r], dst ? (*dst)[r] : nullptr, rhs)); });
+}
+
+void ForwardSolver::DeviceGroup::fieldSetScale(FieldSet const *dst, std::vector<float> const &rhs)
+{
+    SCAI_ASSERT_ERROR(rhs.size() == nGlobal, "the vector must hold NX*NY*NZ values")
+    forEach([&](IndexType r) { check(ws_wavefields_times_assign_vector(handles[r], dst ? (*dst)[r] : nullptr, rhs.data() + (size_t)y0[r] * planeSize, (size_t)nyl[r] * planeSize)); });
+}
+
+std::vector<float> ForwardSolver::DeviceGroup::getWavefield(FieldSet const &set, std::string const &component)
+{
+    std::vector<float> out(nGlobal);
+    forEach([&](IndexType r) { check(ws_wavefields_get(handles[r], set[r], component.c_str(), out.data() + (size_t)y0[r] * planeSize, (size_t)nyl[r] * planeSize)); });
+    return out;
+}
+
+void ForwardSolver::DeviceGroup::setStepScaling(std::vector<float> const &vec)
+{
+    SCAI_ASSERT_ERROR(vec.empty() || vec.size() == nGlobal, "the vector must hold NX*NY*NZ values")
+    forEach([&](IndexType r) { check(ws_set_step_scaling(handles[r], vec.empty() ? nullptr : vec.data() + (size_t)y0[r] * planeSize, (size_t)nyl[r] * planeSize)); });
+}
+
 bool ForwardSolver::DeviceGroup::isFinite()
 {
     std::vector<int32_t> flags(size(), 0);

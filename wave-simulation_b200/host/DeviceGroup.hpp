@@ -44,6 +44,19 @@ namespace KITGPI
             void getSeismogram(std::vector<float> &all);
             bool isFinite();
 
+            //! a second set of wavefield components on the GPUs of the group (ws_wavefields, one per rank); the operators below take
+            //! nullptr for the solvers' own wavefields (Wavefields/Wavefields.hpp:62-80)
+            typedef std::vector<ws_wavefields *> FieldSet;
+            FieldSet createFieldSet();
+            void destroyFieldSet(FieldSet &set);
+            //! op 0: dst = src, 1: dst += src, 2: dst -= src
+            void fieldSetBinary(FieldSet const *dst, FieldSet const *src, int op);
+            void fieldSetScale(FieldSet const *dst, float rhs);
+            void fieldSetScale(FieldSet const *dst, std::vector<float> const &rhs); // global vector, NX*NY*NZ values
+            std::vector<float> getWavefield(FieldSet const &set, std::string const &component);
+            //! `*wavefields *= vector` after every time step inside the library (Simulation.cpp:455-456); empty vector = off
+            void setStepScaling(std::vector<float> const &vec);
+
           private:
             void workerLoop(IndexType rank);
             std::vector<IndexType> devices;

@@ -1,4 +1,5 @@
 #include "Modelparameter.hpp"
+#include <cmath>
 #include "DeviceGroup.hpp"
 #include "IO.hpp"
 #include <algorithm>
@@ -136,6 +137,21 @@ template <typename ValueType> typename Modelparameter::Modelparameter<ValueType>
 {
     std::transform(type.begin(), type.end(), type.begin(), ::tolower);
     return std::make_shared<Modelparameter<ValueType>>(type); // throws "Unkown type" for anything else
+}
+
+template <typename ValueType> std::vector<ValueType> Modelparameter::Modelparameter<ValueType>::getCompensation(ValueType DT, IndexType tStep) const
+{
+    if (seismic)
+        COMMON_THROWEXCEPTION("There is no compensation in an Seismic modelling")
+    std::vector<ValueType> c = getElectricConductivity();
+    std::vector<ValueType> const &eps = getDielectricPermittivity();
+    const ValueType f = tStep * DT;
+    for (size_t i = 0; i < c.size(); i++) {
+        ValueType v = c[i] / eps[i];
+        v *= f;
+        c[i] = std::exp(v);
+    }
+    return c;
 }
 
 template class Modelparameter::Modelparameter<float>;

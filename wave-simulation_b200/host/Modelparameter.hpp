@@ -49,6 +49,8 @@ namespace KITGPI
             //! largest propagation velocity (vp, vs for SH, c0/sqrt(eps_r mu_r) for EM): CheckParameter.hpp:183-200
             ValueType getMaxVelocity() const;
             ValueType getMinVelocity() const;
+            //! exp(sigma / eps * tStep * DT), the amplitude compensation of an EM modelling (Modelparameter.cpp:127-143)
+            std::vector<ValueType> getCompensation(ValueType DT, IndexType tStep) const;
 
             void bind(ForwardSolver::DeviceGroup *group) { h = group; }
 

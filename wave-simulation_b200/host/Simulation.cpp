@@ -82,6 +82,10 @@ static void runShotDomain(Configuration::Configuration const &config, IndexType 
             }
             start_t = now();
             wavefields->resetWavefields();
+            // Simulation.cpp:441-456: `*wavefields *= compensation` after every step; the vector goes to the GPUs once and the
+            // multiplication rides in the captured step graph
+            if (config.getAndCatch("compensation", 0))
+                solver->getGroup()->setStepScaling(modelLocal.getCompensation(DT, 1));
             double start_t2 = start_t;
             for (IndexType tStep = 0; tStep < tStepEnd; tStep++) {
                 if ((tStep - 1) % 100 == 0)

@@ -54,9 +54,70 @@ template <typename ValueType> void Wavefields::Wavefields<ValueType>::init(Index
     all.insert(all.end(), memory.begin(), memory.end());
 }
 
+template <typename ValueType> void Wavefields::Wavefields<ValueType>::init(Wavefields<ValueType> const &like)
+{
+    SCAI_ASSERT_ERROR(like.h, "The wavefields are not bound to a forward solver yet (initForwardSolver)")
+    SCAI_ASSERT_ERROR(like.equationType == equationType && like.numDimension == numDimension, "wavefield objects of different type")
+    if (stored && h)
+        h->destroyFieldSet(own);
+    h = like.h;
+    memory = like.memory;
+    all = like.all;
+    own = h->createFieldSet();
+    stored = true;
+}
+
+template <typename ValueType> Wavefields::Wavefields<ValueType>::~Wavefields()
+{
+    if (stored && h)
+        h->destroyFieldSet(own);
+}
+
+namespace
+{
+    typedef KITGPI::ForwardSolver::DeviceGroup::FieldSet FieldSet;
+}
+#define WS_WF_CHECK(rhs)                                                                                                                  \
+    SCAI_ASSERT_ERROR(h && (rhs).h == h, "wavefield operators need two objects on the same forward solver (Wavefields::init(like))")
+
+template <typename ValueType> Wavefields::Wavefields<ValueType> &Wavefields::Wavefields<ValueType>::operator=(Wavefields<ValueType> &rhs)
+{
+    WS_WF_CHECK(rhs)
+    h->fieldSetBinary(stored ? &own : nullptr, rhs.stored ? &rhs.own : nullptr, 0);
+    return *this;
+}
+template <typename ValueType> Wavefields::Wavefields<ValueType> &Wavefields::Wavefields<ValueType>::operator+=(Wavefields<ValueType> &rhs)
+{
+    WS_WF_CHECK(rhs)
+    h->fieldSetBinary(stored ? &own : nullptr, rhs.stored ? &rhs.own : nullptr, 1);
+    return *this;
+}
+template <typename ValueType> Wavefields::Wavefields<ValueType> &Wavefields::Wavefields<ValueType>::operator-=(Wavefields<ValueType> &rhs)
+{
+    WS_WF_CHECK(rhs)
+    h->fieldSetBinary(stored ? &own : nullptr, rhs.stored ? &rhs.own : nullptr, 2);
+    return *this;
+}
+template <typename ValueType> Wavefields::Wavefields<ValueType> &Wavefields::Wavefields<ValueType>::operator*=(ValueType rhs)
+{
+    SCAI_ASSERT_ERROR(h, "The wavefields are not bound to a forward solver yet (initForwardSolver)")
+    h->fieldSetScale(stored ? &own : nullptr, rhs);
+    return *this;
+}
+template <typename ValueType> Wavefields::Wavefields<ValueType> &Wavefields::Wavefields<ValueType>::operator*=(std::vector<ValueType> const &rhs)
+{
+    SCAI_ASSERT_ERROR(h, "The wavefields are not bound to a forward solver yet (initForwardSolver)")
+    h->fieldSetScale(stored ? &own : nullptr, rhs);
+    return *this;
+}
+
 template <typename ValueType> void Wavefields::Wavefields<ValueType>::resetWavefields()
 {
     SCAI_ASSERT_ERROR(h, "The wavefields are not bound to a forward solver yet (initForwardSolver)")
+    if (stored) { // a stored object: all components back to zero
+        h->fieldSetScale(&own, ValueType(0));
+        return;
+    }
     h->forEach([&](IndexType r) {
         if (ws_reset(h->handle(r)) != WS_OK)
             COMMON_THROWEXCEPTION(ws_last_error())
@@ -72,12 +133,15 @@ template <typename ValueType> bool Wavefields::Wavefields<ValueType>::isFinite()
 template <typename ValueType> std::vector<ValueType> Wavefields::Wavefields<ValueType>::get(std::string const &component) const
 {
     SCAI_ASSERT_ERROR(h, "The wavefields are not bound to a forward solver yet (initForwardSolver)")
+    if (stored)
+        return h->getWavefield(own, component);
     return h->getWavefield(component);
 }
 
 template <typename ValueType> void Wavefields::Wavefields<ValueType>::set(std::string const &component, std::vector<ValueType> const &values)
 {
     SCAI_ASSERT_ERROR(h, "The wavefields are not bound to a forward solver yet (initForwardSolver)")
+    SCAI_ASSERT_ERROR(!stored, "set() addresses the solver's own wavefields")
     h->setWavefield(component, values);
 }
 

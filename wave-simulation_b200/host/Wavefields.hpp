@@ -5,6 +5,7 @@
 // (Wavefields3Delastic.cpp:62-96; snapType 1 = particle velocities / H, 2 = stresses / pressure / E).
 #pragma once
 #include "Common.hpp"
+#include "../../include/wavesim.h"
 #include <memory>
 
 namespace KITGPI { namespace ForwardSolver { class DeviceGroup; } }
@@ -34,11 +35,27 @@ namespace KITGPI
             //! the GPUs that hold the state (set by ForwardSolver::initForwardSolver)
             void bind(ForwardSolver::DeviceGroup *group) { h = group; }
 
+            //! a second wavefield object next to the solver's own (e.g. `wavefieldsTemp`, Simulation.cpp:327): same components, zero,
+            //! resident on the GPUs of `like` (takes the place of Wavefields::init(ctx, dist, numRelaxationMechanisms))
+            void init(Wavefields<ValueType> const &like);
+            ~Wavefields();
+            Wavefields(Wavefields const &) = delete;
+
+            //! Operator overloading (Wavefields.hpp:62-80): applied to every component incl. the memory variables, on the GPUs
+            Wavefields<ValueType> &operator=(Wavefields<ValueType> &rhs);
+            Wavefields<ValueType> &operator-=(Wavefields<ValueType> &rhs);
+            Wavefields<ValueType> &operator+=(Wavefields<ValueType> &rhs);
+            Wavefields<ValueType> &operator*=(ValueType rhs);
+            Wavefields<ValueType> &operator*=(std::vector<ValueType> const &rhs);
+
           private:
             std::string equationType;
             IndexType numDimension;
             std::vector<std::string> first, second, memory, all; // first half-step fields, second half-step fields, memory variables
             ForwardSolver::DeviceGroup *h = nullptr;
+            //! empty: this object IS the solver's wavefields; else its own component set per GPU of the group
+            std::vector<ws_wavefields *> own;
+            bool stored = false;
         };
 
         template <typename ValueType> class Factory
