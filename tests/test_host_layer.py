@@ -693,3 +693,117 @@ def test_product_driver_compensation_on_gpu(tmp_path):
     run(os.path.join(HOST, "Simulation"), setup_tmem_case(tmp, comp=1, kvar=0), tmp)
     s = read_mtx(os.path.join(tmp, "seismograms", "seismogram.shot_1.ez.mtx"))
     assert rel_l2(s, tmem_oracle_with_compensation(40, True)) <= 1.0e-5
+
+
+# source encoding, random shots, shot increment, per-shot model cut-outs (Sources.cpp:500-714, AcquisitionSettings.hpp:136-483,
+# Simulation.cpp:233-282, 339-398)
+FOUR_SHOTS = "".join("%d %d 0 0 2 1 1 5.0 %.1f 0.0\n" % (k + 1, 20 + 12 * k, 5.0 + k) for k in range(4))
+
+
+def seismograms_of(tmp, comp="vy"):
+    out = {}
+    for f in os.listdir(os.path.join(tmp, "seismograms")):
+        if f.endswith("." + comp + ".mtx"):
+            out[int(f.split("shot_")[1].split(".")[0])] = read_mtx(os.path.join(tmp, "seismograms", f))
+    return out
+
+
+def with_keys(cfg, **kw):
+    text = open(cfg).read()
+    for k, v in kw.items():
+        text = "\n".join(ln for ln in text.split("\n") if not ln.startswith(k + "=")) + "\n%s=%s\n" % (k, v)
+    open(cfg, "w").write(text)
+    return cfg
+
+
+def test_driver_source_encoding(driver, tmp_path):
+    """useSourceEncode: the shots fire together in NumShotDomains supershots (numbers NumShotDomains*1e4+1+k).  The equations are
+    linear, so a supershot's seismogram is the (signed) sum of the seismograms of its shots."""
+    plain = str(tmp_path / "plain")
+    run(driver, setup_case(plain, sources=FOUR_SHOTS, receivers="30 2 0 3\n70 3 0 3\n", T=0.5), plain)
+    single = seismograms_of(plain)
+    assert sorted(single) == [1, 2, 3, 4]
+    for mode, groups in ((2, {20001: [1, 3], 20002: [2, 4]}), (3, {20001: [1, 2], 20002: [3, 4]})):
+        tmp = str(tmp_path / ("mode%d" % mode))
+        cfg = with_keys(setup_case(tmp, sources=FOUR_SHOTS, receivers="30 2 0 3\n70 3 0 3\n", T=0.5), useSourceEncode=mode, NumShotDomains=2, seedtime=7)
+        run(driver, cfg, tmp)
+        enc = seismograms_of(tmp)
+        assert sorted(enc) == sorted(groups)
+        for no, members in groups.items():
+            assert rel_l2(enc[no], sum(single[m] for m in members)) <= 2.0e-5, (mode, no)
+        lines = [ln.split() for ln in open(os.path.join(tmp, "acq", "sources.encode.txt")) if not ln.startswith("#")]
+        assert {int(ln[0]): [int(x) for x in ln[1:]] for ln in lines} == groups
+    # mode 1: random assignment (every supershot holds numshots / NumShotDomains shots) with random polarity; a given seed repeats
+    res = []
+    for rep in range(2):
+        tmp = str(tmp_path / ("mode1_%d" % rep))
+        cfg = with_keys(setup_case(tmp, sources=FOUR_SHOTS, receivers="30 2 0 3\n70 3 0 3\n", T=0.5), useSourceEncode=1, NumShotDomains=2, seedtime=11)
+        run(driver, cfg, tmp)
+        enc = seismograms_of(tmp)
+        lines = [ln.split() for ln in open(os.path.join(tmp, "acq", "sources.encode.txt")) if not ln.startswith("#")]
+        groups = {int(ln[0]): [int(x) for x in ln[1:]] for ln in lines}
+        assert sorted(groups) == [20001, 20002] and sorted(sum(groups.values(), [])) == [1, 2, 3, 4] and all(len(g) == 2 for g in groups.values())
+        for no, members in groups.items():
+            basis = np.stack([single[m].ravel() for m in members], axis=1)
+            coef = np.linalg.lstsq(basis, enc[no].ravel(), rcond=None)[0]
+            assert np.allclose(np.abs(coef), 1.0, atol=1e-3), coef  # +-1: the random polarity
+        res.append((groups, {k: v.copy() for k, v in enc.items()}))
+    assert res[0][0] == res[1][0] and all(np.array_equal(res[0][1][k], res[1][1][k]) for k in res[0][1])
+
+
+def test_driver_random_shots_and_shot_increment(driver, tmp_path):
+    plain = str(tmp_path / "plain")
+    run(driver, setup_case(plain, sources=FOUR_SHOTS, T=0.3), plain)
+    single = seismograms_of(plain)
+    for mode in (1, 2, 3):  # two passes of two shots each: every shot exactly once (maxcount = 1)
+        tmp = str(tmp_path / ("rand%d" % mode))
+        run(driver, with_keys(setup_case(tmp, sources=FOUR_SHOTS, T=0.3), useRandomSource=mode, NumShotDomains=2, seedtime=3), tmp)
+        got = seismograms_of(tmp)
+        assert sorted(got) == [1, 2, 3, 4]
+        assert all(np.array_equal(got[k], single[k]) for k in got)
+    # shotIncr = 200 m on a line of shots 2 grid points (100 m) apart: every second shot (Sources.cpp:516-553)
+    tmp = str(tmp_path / "incr")
+    six = "".join("%d %d 0 0 2 1 1 5.0 5.0 0.0\n" % (k + 1, 20 + 2 * k) for k in range(6))
+    run(driver, with_keys(setup_case(tmp, sources=six, T=0.1), shotIncr=200), tmp)
+    assert sorted(seismograms_of(tmp)) == [1, 3, 5]
+    lines = [ln.split() for ln in open(os.path.join(tmp, "acq", "sources.shotIncr.txt")) if not ln.startswith("#")]
+    assert lines == [["1", "1"], ["3", "3"], ["5", "5"]]
+
+
+def test_driver_stream_config_model_per_shot(driver, tmp_path):
+    """useStreamConfig: every shot works on its own NX-wide cut-out of a big model (cut where the shot lies relative to the first
+    one), its sources / receivers are given in the big model; compared with the oracle run on the cut-outs themselves."""
+    tmp = str(tmp_path)
+    nxb, nx, ny, nt = 160, 100, 100, 200
+    cfg = setup_case(tmp, sources="1 40 15 0 2 1 1 5.0 5.0 0.0\n2 90 15 0 2 1 1 5.0 5.0 0.0\n", rps=1, T=0.4)  # (a cut-out keeps its acquisition out of the boundary frame)
+    big = two_layer(nxb, ny, 1)
+    lateral = (1.0 + 0.15 * np.arange(nxb, dtype=np.float32) / nxb)[None, :]
+    for key in big:
+        big[key] = (big[key].reshape(ny, nxb) * lateral).astype(np.float32).ravel()
+    for key, suffix in (("velocityP", "vp"), ("velocityS", "vs"), ("density", "density")):
+        write_mtx_vector(os.path.join(tmp, "model", "big." + suffix + ".mtx"), big[key])
+    text = open(cfg).read()
+    open(os.path.join(tmp, "configBig.txt"), "w").write(text.replace("NX=100", "NX=%d" % nxb).replace("ModelFilename=model/model", "ModelFilename=model/big"))
+    with_keys(cfg, useStreamConfig=1, streamConfigFilename="configBig.txt")
+    open(os.path.join(tmp, "acq", "receiver.shot_1.txt"), "w").write("50 12 0 3\n")
+    open(os.path.join(tmp, "acq", "receiver.shot_2.txt"), "w").write("100 12 0 3\n")
+    run(driver, cfg, tmp)
+    got = seismograms_of(tmp)
+    assert sorted(got) == [1, 2]
+    cut = [ln.split() for ln in open(os.path.join(tmp, "acq", "sources.cut.txt")) if not ln.startswith("#")]
+    assert cut == [[str(nx * ny), str(nx), str(ny), "1"], ["1", "0", "0", "0"], ["2", "50", "0", "0"]]
+    for shot, x0 in ((1, 0), (2, 50)):
+        case = ci_case("2D.elastic", nt=nt)
+        case.desc.edge_policy = 0
+        case.materials = {k: v.reshape(ny, nxb)[:, x0:x0 + nx].ravel().copy() for k, v in big.items()}
+        o = case.setup(Oracle(case.desc))
+        from wsharness import TYPE, idx1d, ricker
+        o.set_sources([TYPE["VX"]], [idx1d(40, 15, 0, nx, 1)], ricker(nt, 2e-3, 5.0, 5.0, 0.0)[None, :])  # both shots sit at x = 40 of their cut-out
+        o.set_receivers([TYPE["VY"]], [idx1d(50, 12, 0, nx, 1)])
+        o.reset()
+        o.run(0, nt)
+        assert rel_l2(got[shot], o.seismogram()) <= 1.0e-5, shot
+        # the model of the shot was written next to the big one (Simulation.cpp:393)
+        vp = read_mtx(os.path.join(tmp, "model", "model.shot_%d.vp.mtx" % shot)).ravel()
+        assert np.array_equal(vp.astype(np.float32), case.materials["velocityP"])
+    assert not np.allclose(got[1], got[2], rtol=1e-3)  # the lateral gradient makes the two cut-outs differ

@@ -2,6 +2,7 @@
 #include "IO.hpp"
 #include <algorithm>
 #include <fstream>
+#include <iomanip>
 
 using namespace KITGPI;
 
@@ -442,12 +443,293 @@ template <typename ValueType> static void readSourceSettingsFromSU(std::vector<A
     SCAI_ASSERT_ERROR(!all.empty(), "No file with name: " << filename << ".'comp'.su could be read")
 }
 
-template <typename ValueType> void Acquisition::Sources<ValueType>::getAcquisitionSettings(Configuration::Configuration const &config)
+template <typename ValueType> void Acquisition::Sources<ValueType>::getAcquisitionSettings(Configuration::Configuration const &config, ValueType shotIncr)
 {
+    // Sources.cpp:502-514: with useStreamConfig the sources are those of the big model
+    std::string filename = config.get<std::string>("SourceFilename");
+    if (config.getAndCatch("useStreamConfig", false)) {
+        Configuration::Configuration configBig(config.get<std::string>("streamConfigFilename"));
+        filename = configBig.get<std::string>("SourceFilename");
+    }
+    std::vector<sourceSettings<ValueType>> allSettings;
     if (config.getAndCatch("initSourcesFromSU", false)) // Sources.cpp:511-512
-        readSourceSettingsFromSU<ValueType>(allSourceSettings, config.get<std::string>("SourceFilename"), config.get<ValueType>("DH"));
+        readSourceSettingsFromSU<ValueType>(allSettings, filename, config.get<ValueType>("DH"));
     else
-        readAllSettings(allSourceSettings, config.get<std::string>("SourceFilename") + ".txt");
+        readAllSettings(allSettings, filename + ".txt");
+    // Sources.cpp:516-559: one shot every shotIncr metres along the axis the shot line runs on
+    const IndexType numshots = (IndexType)allSettings.size();
+    const ValueType DH = config.get<ValueType>("DH");
+    shotIndsIncr.clear();
+    allSourceSettings.clear();
+    if (numshots > 1 && shotIncr > DH) {
+        std::vector<IndexType> sourceLength;
+        const IndexType dx = std::abs(allSettings[0].sourceCoords.x - allSettings[1].sourceCoords.x), dy = std::abs(allSettings[0].sourceCoords.y - allSettings[1].sourceCoords.y);
+        SCAI_ASSERT_ERROR(dx != dy, "shotIncr: the first two sources do not tell the direction of the shot line")
+        for (IndexType k = 0; k < numshots; k++)
+            sourceLength.push_back(dx > dy ? allSettings[k].sourceCoords.x : allSettings[k].sourceCoords.y);
+        IndexType numshotsIncr = 0, shotIncrInd = sourceLength[0], shotIncrStep;
+        allSourceSettings.push_back(allSettings[0]);
+        shotIndsIncr.push_back(0);
+        for (IndexType shotInd = 0; shotInd < numshots - 1; shotInd++) {
+            if (shotIncrInd >= sourceLength[shotInd] && shotIncrInd <= sourceLength[shotInd + 1]) {
+                if (shotIndsIncr[numshotsIncr] != shotInd && std::abs(shotIncrInd - sourceLength[shotInd]) < std::abs(shotIncrInd - sourceLength[shotInd + 1])) {
+                    allSourceSettings.push_back(allSettings[shotInd]);
+                    shotIndsIncr.push_back(shotInd);
+                    numshotsIncr++;
+                } else if (shotIndsIncr[numshotsIncr] != shotInd + 1 && std::abs(shotIncrInd - sourceLength[shotInd]) >= std::abs(shotIncrInd - sourceLength[shotInd + 1])) {
+                    allSourceSettings.push_back(allSettings[shotInd + 1]);
+                    shotIndsIncr.push_back(shotInd + 1);
+                    numshotsIncr++;
+                }
+                shotIncrStep = (IndexType)std::round(shotIncr * (numshotsIncr + 1) / DH);
+                shotIncrInd = sourceLength[0] + shotIncrStep;
+                shotInd--; // the same interval may hold the next position too
+            } else if (shotInd == numshots - 2 && shotIndsIncr[numshotsIncr] != shotInd + 1 &&
+                       std::abs(sourceLength[shotInd + 1] - sourceLength[shotInd]) > std::abs(shotIncrInd - sourceLength[shotInd + 1])) {
+                allSourceSettings.push_back(allSettings[shotInd + 1]);
+                shotIndsIncr.push_back(shotInd + 1);
+            }
+        }
+    } else {
+        allSourceSettings = allSettings;
+        for (IndexType k = 0; k < numshots; k++)
+            shotIndsIncr.push_back(k);
+    }
+}
+
+template <typename ValueType> void Acquisition::Sources<ValueType>::calcSourceSettingsEncode(Configuration::Configuration const &config, IndexType &seedtime)
+{
+    const IndexType numshotsIncr = (IndexType)shotIndsIncr.size();
+    const IndexType useSourceEncode = config.getAndCatch("useSourceEncode", 0), useRandomSource = config.getAndCatch("useRandomSource", 0);
+    SCAI_ASSERT_ERROR(useSourceEncode * useRandomSource == 0, "useSourceEncode and useRandomSource are not compatible!")
+    SCAI_ASSERT_ERROR(useSourceEncode * config.getAndCatch("useSourceSignalTaper", 0) == 0, "useSourceEncode and useSourceSignalTaper are not compatible!")
+    if (config.getAndCatch("useStreamConfig", 0) != 0)
+        SCAI_ASSERT_ERROR(useSourceEncode == 0 || useSourceEncode == 3, "useSourceEncode must be 0 or 3 when useStreamConfig != 0!")
+    SCAI_ASSERT_ERROR(config.getAndCatch("gradientDomain", 0) == 0, "gradientDomain != 0 (frequency selection of the inversion) is not available in the forward driver")
+    sourceSettingsEncode.clear();
+    if (useSourceEncode == 0)
+        return;
+    sourceSettingsEncode = allSourceSettings;
+    const IndexType numShotDomains = config.get<IndexType>("NumShotDomains"); // the number of supershots
+    const IndexType numShotPerSuperShot = (IndexType)std::ceil(ValueType(numshotsIncr) / numShotDomains);
+    std::srand(seedtime);
+    seedtime++;
+    std::vector<IndexType> shotHistory(numShotDomains, 0);
+    const IndexType base = (IndexType)(numShotDomains * 1e4) + 1;
+    if (useSourceEncode == 1) { // randomly, with random polarity
+        for (IndexType shotInd = 0; shotInd < numshotsIncr; shotInd++) {
+            if (shotInd < numShotDomains) { // every supershot gets one shot first
+                sourceSettingsEncode[shotInd].sourceNo = base + shotInd;
+                shotHistory[shotInd]++;
+            } else {
+                IndexType sourceInd = std::rand() % numShotDomains;
+                while (shotHistory[sourceInd] >= numShotPerSuperShot)
+                    sourceInd = std::rand() % numShotDomains;
+                shotHistory[sourceInd]++;
+                sourceSettingsEncode[shotInd].sourceNo = base + sourceInd;
+            }
+        }
+        for (IndexType shotInd = 0; shotInd < numshotsIncr; shotInd++) {
+            const IndexType signAmp = (std::rand() % 2) > 0 ? 1 : -1;
+            sourceSettingsEncode[shotInd].amp *= signAmp;
+        }
+    } else if (useSourceEncode == 2) { // sequentially to cover the global area
+        for (IndexType shotInd = 0; shotInd < numshotsIncr; shotInd++)
+            sourceSettingsEncode[shotInd].sourceNo = base + shotInd % numShotDomains;
+    } else if (useSourceEncode == 3) { // sequentially to cover a local area
+        for (IndexType shotInd = 0; shotInd < numshotsIncr; shotInd++)
+            sourceSettingsEncode[shotInd].sourceNo = base + shotInd / numShotPerSuperShot;
+    } else
+        COMMON_THROWEXCEPTION("useSourceEncode must be 0, 1, 2 or 3")
+}
+
+void Acquisition::getRandomShotInds(std::vector<IndexType> &uniqueShotInds, std::vector<IndexType> &shotHistory, IndexType numshots, IndexType maxcount, IndexType useRandomSource,
+                                    IndexType &seedtime)
+{
+    const IndexType numShotDomains = (IndexType)uniqueShotInds.size();
+    if (useRandomSource == 1) {
+        std::vector<IndexType> randomShotIndHistory(numShotDomains, 0);
+        std::srand(seedtime);
+        seedtime++;
+        for (IndexType shotDomainInd = 0; shotDomainInd < numShotDomains; shotDomainInd++) {
+            bool repeat = false;
+            const IndexType randomShotInd = std::rand() % numshots;
+            randomShotIndHistory[shotDomainInd] = randomShotInd;
+            for (IndexType i = 0; i < shotDomainInd; i++)
+                if (randomShotIndHistory[i] == randomShotInd) {
+                    repeat = true;
+                    break;
+                }
+            if (shotHistory[randomShotInd] >= maxcount || repeat)
+                shotDomainInd--;
+            else {
+                uniqueShotInds[shotDomainInd] = randomShotInd;
+                shotHistory[randomShotInd]++;
+            }
+        }
+    } else if (useRandomSource == 2 || useRandomSource == 3) {
+        IndexType sum = 0;
+        for (auto c : shotHistory)
+            sum += c;
+        sum /= numShotDomains; // passes done so far
+        const IndexType step = (IndexType)std::ceil(ValueType(numshots) / numShotDomains);
+        for (IndexType shotDomainInd = 0; shotDomainInd < numShotDomains; shotDomainInd++) {
+            IndexType ind = useRandomSource == 2 ? sum + shotDomainInd * step : sum * numShotDomains + shotDomainInd;
+            ind %= numshots;
+            uniqueShotInds[shotDomainInd] = ind;
+            shotHistory[ind]++;
+        }
+    }
+}
+
+template <typename ValueType>
+void Acquisition::Sources<ValueType>::calcUniqueShotInds(Configuration::Configuration const &config, std::vector<IndexType> &shotHistory, IndexType maxcount, IndexType &seedtime)
+{
+    const IndexType numshotsIncr = (IndexType)shotIndsIncr.size();
+    const IndexType useSourceEncode = config.getAndCatch("useSourceEncode", 0), useRandomSource = config.getAndCatch("useRandomSource", 0);
+    const IndexType numShotDomains = config.get<IndexType>("NumShotDomains");
+    SCAI_ASSERT_ERROR(useSourceEncode * useRandomSource == 0, "useSourceEncode and useRandomSource are not compatible!")
+    uniqueShotInds.clear();
+    if (useRandomSource != 0) {
+        uniqueShotInds.assign(numShotDomains, 0);
+        getRandomShotInds(uniqueShotInds, shotHistory, numshotsIncr, maxcount, useRandomSource, seedtime);
+    } else if (useSourceEncode != 0) {
+        for (IndexType k = 0; k < numShotDomains; k++)
+            uniqueShotInds.push_back(k);
+    } else {
+        for (IndexType k = 0; k < numshotsIncr; k++)
+            uniqueShotInds.push_back(k);
+    }
+}
+
+template <typename ValueType> void Acquisition::Sources<ValueType>::writeShotIndsIncr(Configuration::Configuration const &config, std::vector<IndexType> const &uniqueShotNos) const
+{
+    const ValueType shotIncr = config.getAndCatch("shotIncr", ValueType(0));
+    if (!(shotIncr > config.get<ValueType>("DH")))
+        return;
+    SCAI_ASSERT_ERROR(shotIndsIncr.size() == uniqueShotNos.size(), "shotIndsIncr.size() != uniqueShotNos.size()")
+    std::string filename = config.get<std::string>("SourceFilename");
+    if (config.getAndCatch("useStreamConfig", false))
+        filename = Configuration::Configuration(config.get<std::string>("streamConfigFilename")).get<std::string>("SourceFilename");
+    std::ofstream out(filename + ".shotIncr.txt");
+    out << "# Shot indices (shotIncr = " << shotIncr << " m, numshots = " << shotIndsIncr.size() << ")\n# Shot index | shot number\n";
+    for (size_t k = 0; k < shotIndsIncr.size(); k++)
+        out << std::setw(12) << shotIndsIncr[k] + 1 << std::setw(12) << uniqueShotNos[k] << "\n";
+}
+
+template <typename ValueType> void Acquisition::Sources<ValueType>::writeSourceEncode(Configuration::Configuration const &config) const
+{
+    const IndexType useSourceEncode = config.getAndCatch("useSourceEncode", 0);
+    if (useSourceEncode == 0)
+        return;
+    std::vector<IndexType> uniqueShotNosEncode;
+    calcuniqueShotNo(uniqueShotNosEncode, sourceSettingsEncode);
+    SCAI_ASSERT_ERROR(sourceSettingsEncode.size() == shotIndsIncr.size(), "sourceSettingsEncode.size() != shotIndsIncr.size()")
+    std::string filename = config.get<std::string>("SourceFilename");
+    if (config.getAndCatch("useStreamConfig", false))
+        filename = Configuration::Configuration(config.get<std::string>("streamConfigFilename")).get<std::string>("SourceFilename");
+    std::ofstream out(filename + ".encode.txt");
+    out << "# Shot indices used in source encode (useSourceEncode = " << useSourceEncode << ", numShotDomains = " << config.get<IndexType>("NumShotDomains")
+        << ", numshots = " << shotIndsIncr.size() << ")\n# Shot number | shot index (selected)\n";
+    for (auto no : uniqueShotNosEncode) {
+        out << std::setw(13) << no;
+        for (size_t k = 0; k < sourceSettingsEncode.size(); k++)
+            if (std::abs(sourceSettingsEncode[k].sourceNo) == no)
+                out << std::setw(5) << k + 1;
+        out << "\n";
+    }
+}
+
+void Acquisition::getuniqueShotInd(IndexType &shotInd, std::vector<IndexType> const &uniqueShotNos, IndexType shotNumber)
+{
+    for (size_t i = 0; i < uniqueShotNos.size(); i++)
+        if (uniqueShotNos[i] == shotNumber) {
+            shotInd = (IndexType)i;
+            break;
+        }
+}
+template <typename ValueType> void Acquisition::getuniqueShotInd(IndexType &shotInd, std::vector<sourceSettings<ValueType>> const &enc, IndexType shotNumber)
+{
+    for (size_t i = 0; i < enc.size(); i++)
+        if (std::abs(enc[i].sourceNo) == shotNumber) {
+            shotInd = (IndexType)i;
+            break;
+        }
+}
+
+template <typename ValueType>
+void Acquisition::getCutCoord(Configuration::Configuration const &config, std::vector<coordinate3D> &cutCoordinates, std::vector<sourceSettings<ValueType>> const &big,
+                              Coordinates<ValueType> const &modelCoordinates, Coordinates<ValueType> const &modelCoordinatesBig)
+{
+    cutCoordinates.clear();
+    std::vector<IndexType> uniqueShotNos;
+    calcuniqueShotNo(uniqueShotNos, big);
+    SCAI_ASSERT_ERROR(big.size() == uniqueShotNos.size(), "sourceSettingsBig.size() != uniqueShotNos.size()")
+    const IndexType numshotsIncr = (IndexType)big.size();
+    SCAI_ASSERT_ERROR(modelCoordinates.getDH() == modelCoordinatesBig.getDH(), "DH != DHBig")
+    const IndexType useSourceEncode = config.getAndCatch("useSourceEncode", 0);
+    const IndexType numShotDomains = config.get<IndexType>("NumShotDomains");
+    const IndexType numShotPerSuperShot = (IndexType)std::ceil(ValueType(numshotsIncr) / numShotDomains);
+    IndexType minX = big[0].sourceCoords.x;
+    for (auto const &s : big)
+        minX = std::min(minX, s.sourceCoords.x);
+    minX -= (IndexType)std::round((modelCoordinates.getX0() - modelCoordinatesBig.getX0()) / modelCoordinates.getDH());
+    IndexType sourceCoordX = 0;
+    for (IndexType i = 0; i < numshotsIncr; i++) {
+        if (big[i].sourceNo >= 0 && (useSourceEncode == 0 || (useSourceEncode == 3 && i % numShotPerSuperShot == 0)))
+            sourceCoordX = big[i].sourceCoords.x; // a negative sourceNo keeps the cut of the shot before it
+        SCAI_ASSERT_ERROR(sourceCoordX != 0, "sourceCoordX cannot be 0 when sourceSettingsBig[i].sourceNo < 0")
+        coordinate3D c;
+        c.x = sourceCoordX - minX > 0 ? sourceCoordX - minX : 0;
+        c.y = 0;
+        c.z = 0;
+        cutCoordinates.push_back(c);
+    }
+}
+
+namespace
+{
+    template <typename ValueType> void moveIntoSubModel(Acquisition::coordinate3D &c, Acquisition::coordinate3D const &cut, Acquisition::Coordinates<ValueType> const &mc, IndexType W, const char *what, size_t i)
+    {
+        c.x -= cut.x;
+        SCAI_ASSERT_ERROR(c.x >= W && c.x < mc.getNX() - W, "settings[" << i << "]." << what << ".x = " << c.x)
+        c.y -= cut.y;
+        SCAI_ASSERT_ERROR(c.y >= W && c.y < mc.getNY() - W, "settings[" << i << "]." << what << ".y = " << c.y)
+        c.z -= cut.z;
+        if (mc.getNZ() > W * 2)
+            SCAI_ASSERT_ERROR(c.z >= W && c.z < mc.getNZ() - W, "settings[" << i << "]." << what << ".z = " << c.z)
+    }
+}
+
+template <typename ValueType>
+void Acquisition::getSettingsPerShot(std::vector<sourceSettings<ValueType>> &settings, std::vector<sourceSettings<ValueType>> const &allSettings, std::vector<coordinate3D> const &cutCoordinates,
+                                     Coordinates<ValueType> const &modelCoordinates, IndexType BoundaryWidth)
+{
+    settings = allSettings;
+    for (size_t i = 0; i < settings.size(); i++)
+        moveIntoSubModel(settings[i].sourceCoords, cutCoordinates[i], modelCoordinates, BoundaryWidth, "sourceCoords", i);
+}
+
+template <typename ValueType>
+void Acquisition::getSettingsPerShot(std::vector<receiverSettings> &settings, std::vector<receiverSettings> const &allSettings, coordinate3D const &cutCoordinate,
+                                     Coordinates<ValueType> const &modelCoordinates, IndexType BoundaryWidth)
+{
+    settings = allSettings;
+    for (size_t i = 0; i < settings.size(); i++)
+        moveIntoSubModel(settings[i].receiverCoords, cutCoordinate, modelCoordinates, BoundaryWidth, "receiverCoords", i);
+}
+
+void Acquisition::writeCutCoordToFile(Configuration::Configuration const &config, std::string const &sourceFilename, std::vector<coordinate3D> const &cutCoordinates,
+                                      std::vector<IndexType> const &uniqueShotNos, IndexType NXPerShot)
+{
+    if (!config.getAndCatch("useStreamConfig", false))
+        return;
+    std::ofstream out(sourceFilename + ".cut.txt");
+    out << "# Coordinate for cutting model per shot (the first row is the size of modelPerShot)\n# ShotNumber | index_x | index_y | index_z\n";
+    out << std::setw(12) << (long long)NXPerShot * config.get<IndexType>("NY") * config.get<IndexType>("NZ") << std::setw(10) << NXPerShot << std::setw(10) << config.get<IndexType>("NY")
+        << std::setw(10) << config.get<IndexType>("NZ") << "\n";
+    for (size_t i = 0; i < uniqueShotNos.size(); i++)
+        out << std::setw(12) << uniqueShotNos[i] << std::setw(10) << cutCoordinates[i].x << std::setw(10) << cutCoordinates[i].y << std::setw(10) << cutCoordinates[i].z << "\n";
 }
 
 template <typename ValueType>
@@ -551,6 +833,12 @@ void Acquisition::Receivers<ValueType>::init(Configuration::Configuration const 
 
 template void Acquisition::readAllSettings<float>(std::vector<sourceSettings<float>> &, std::string);
 template void Acquisition::calcuniqueShotNo<float>(std::vector<IndexType> &, std::vector<sourceSettings<float>> const &);
+template void Acquisition::getuniqueShotInd<float>(IndexType &, std::vector<sourceSettings<float>> const &, IndexType);
+template void Acquisition::getCutCoord<float>(Configuration::Configuration const &, std::vector<coordinate3D> &, std::vector<sourceSettings<float>> const &, Coordinates<float> const &,
+                                              Coordinates<float> const &);
+template void Acquisition::getSettingsPerShot<float>(std::vector<sourceSettings<float>> &, std::vector<sourceSettings<float>> const &, std::vector<coordinate3D> const &, Coordinates<float> const &,
+                                                     IndexType);
+template void Acquisition::getSettingsPerShot<float>(std::vector<receiverSettings> &, std::vector<receiverSettings> const &, coordinate3D const &, Coordinates<float> const &, IndexType);
 template void Acquisition::createSettingsForShot<float>(std::vector<sourceSettings<float>> &, std::vector<sourceSettings<float>> const &, IndexType);
 template class Acquisition::Seismogram<float>;
 template class Acquisition::SeismogramHandler<float>;

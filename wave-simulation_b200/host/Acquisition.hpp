@@ -45,6 +45,27 @@ namespace KITGPI
         template <typename ValueType>
         void createSettingsForShot(std::vector<sourceSettings<ValueType>> &settings, std::vector<sourceSettings<ValueType>> const &allSettings, IndexType shotNumber);
 
+        //! index of shotNumber in the list of unique shot numbers / of the first encoded source with that number (AcquisitionSettings.hpp:208-232)
+        void getuniqueShotInd(IndexType &shotInd, std::vector<IndexType> const &uniqueShotNos, IndexType shotNumber);
+        template <typename ValueType> void getuniqueShotInd(IndexType &shotInd, std::vector<sourceSettings<ValueType>> const &sourceSettingsEncode, IndexType shotNumber);
+        //! per-shot model cut-outs (useStreamConfig, AcquisitionSettings.hpp:136-187, 364-430): where the sub-model of a shot starts in
+        //! the big model, and the acquisition settings of the big model moved into the sub-model
+        template <typename ValueType>
+        void getCutCoord(Configuration::Configuration const &config, std::vector<coordinate3D> &cutCoordinates, std::vector<sourceSettings<ValueType>> const &sourceSettingsBig,
+                         Coordinates<ValueType> const &modelCoordinates, Coordinates<ValueType> const &modelCoordinatesBig);
+        template <typename ValueType>
+        void getSettingsPerShot(std::vector<sourceSettings<ValueType>> &settings, std::vector<sourceSettings<ValueType>> const &allSettings, std::vector<coordinate3D> const &cutCoordinates,
+                                Coordinates<ValueType> const &modelCoordinates, IndexType BoundaryWidth);
+        template <typename ValueType>
+        void getSettingsPerShot(std::vector<receiverSettings> &settings, std::vector<receiverSettings> const &allSettings, coordinate3D const &cutCoordinate,
+                                Coordinates<ValueType> const &modelCoordinates, IndexType BoundaryWidth);
+        void writeCutCoordToFile(Configuration::Configuration const &config, std::string const &sourceFilename, std::vector<coordinate3D> const &cutCoordinates,
+                                 std::vector<IndexType> const &uniqueShotNos, IndexType NXPerShot);
+        //! shot sequence of one pass over the shot domains (useRandomSource 1 random without repetition, 2 / 3 sequential covering the
+        //! global / local area; AcquisitionSettings.hpp:437-483)
+        void getRandomShotInds(std::vector<IndexType> &uniqueShotInds, std::vector<IndexType> &shotHistory, IndexType numshots, IndexType maxcount, IndexType useRandomSource,
+                               IndexType &seedtime);
+
         namespace SourceSignal
         {
             //! waveletShape 1 Ricker, 2 SinW, 3 SinThree, 4 FGaussian, 5 Spike, 6 IntgSinThree, 7 Ricker_GprMax, 8 Berlage, 9 Sin
@@ -128,14 +149,28 @@ namespace KITGPI
         template <typename ValueType> class Sources : public AcquisitionGeometry<ValueType>
         {
           public:
-            void getAcquisitionSettings(Configuration::Configuration const &config);
+            //! reads <SourceFilename>.txt (or the SU files); shotIncr > DH keeps one shot every shotIncr metres (Sources.cpp:500-560)
+            void getAcquisitionSettings(Configuration::Configuration const &config, ValueType shotIncr = 0);
             std::vector<sourceSettings<ValueType>> const &getSourceSettings() const { return allSourceSettings; }
+            void setSourceSettings(std::vector<sourceSettings<ValueType>> const &settings) { allSourceSettings = settings; }
+            std::vector<IndexType> const &getShotIndsIncr() const { return shotIndsIncr; }
+            //! useSourceEncode 1 / 2 / 3: the shots are merged into NumShotDomains supershots (random with random polarity / interleaved
+            //! / blockwise; Sources.cpp:568-646, time-domain part)
+            void calcSourceSettingsEncode(Configuration::Configuration const &config, IndexType &seedtime);
+            std::vector<sourceSettings<ValueType>> const &getSourceSettingsEncode() const { return sourceSettingsEncode; }
+            //! the shot indices one pass over the shot domains works on (Sources.cpp:687-714)
+            void calcUniqueShotInds(Configuration::Configuration const &config, std::vector<IndexType> &shotHistory, IndexType maxcount, IndexType &seedtime);
+            std::vector<IndexType> const &getUniqueShotInds() const { return uniqueShotInds; }
+            void writeShotIndsIncr(Configuration::Configuration const &config, std::vector<IndexType> const &uniqueShotNos) const; // <SourceFilename>.shotIncr.txt
+            void writeSourceEncode(Configuration::Configuration const &config) const;                                              // <SourceFilename>.encode.txt
             //! sources of one shot: geometry + signals (Sources.cpp:16-46, 99-145)
             void init(std::vector<sourceSettings<ValueType>> const &shotSettings, Configuration::Configuration const &config, Coordinates<ValueType> const &modelCoordinates);
             IndexType getRowOfEntry(IndexType k) const { return this->traceOfEntry[k]; }
 
           private:
-            std::vector<sourceSettings<ValueType>> allSourceSettings;
+            std::vector<sourceSettings<ValueType>> allSourceSettings; // after the shotIncr selection (sourceSettingsShotIncr of the reference)
+            std::vector<sourceSettings<ValueType>> sourceSettingsEncode;
+            std::vector<IndexType> shotIndsIncr, uniqueShotInds;
         };
 
         template <typename ValueType> class Receivers : public AcquisitionGeometry<ValueType>

@@ -29,6 +29,7 @@ template <typename ValueType> void Acquisition::Coordinates<ValueType>::init(Con
 {
     const IndexType nx = config.get<IndexType>("NX"), ny = config.get<IndexType>("NY"), nz = config.get<IndexType>("NZ");
     const ValueType dh = config.get<ValueType>("DH");
+    x0 = config.getAndCatch("x0", ValueType(0));
     const bool varGrid = config.getAndCatch("useVariableGrid", 0) != 0, varFD = config.getAndCatch("useVariableFDoperators", 0) != 0;
     if (!varGrid && !varFD) {
         init(nx, ny, nz, dh);

@@ -31,6 +31,7 @@ namespace KITGPI
             IndexType getNY() const { return NY; }
             IndexType getNZ() const { return NZ; }
             ValueType getDH() const { return DH; }
+            ValueType getX0() const { return x0; } // origin of the model in metres (key x0, Coordinates.cpp:40): places a sub-model in the big one
             IndexType getNGridpoints() const { return layered ? nGridpoints : NX * NY * NZ; }
             //! true when the model vector is layered (useVariableGrid or useVariableFDoperators): the operators are assembled point by point
             bool isVariable() const { return layered; }
@@ -53,6 +54,7 @@ namespace KITGPI
             void check(IndexType X, IndexType Y, IndexType Z) const;
             IndexType NX, NY, NZ;
             ValueType DH;
+            ValueType x0 = 0;
             bool layered = false, variableSpacing = false;
             IndexType nGridpoints = 0;
             std::vector<IndexType> dhFactor, interface, transition, layerStart, layerEnd, varNX, varNY, varNZ, nGridpointsPerLayer;

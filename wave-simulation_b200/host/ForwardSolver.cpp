@@ -101,6 +101,17 @@ void ForwardSolver::ForwardSolver<ValueType>::initForwardSolver(Configuration::C
     srcVersion = recVersion = ~0ul;
 }
 
+template <typename ValueType> void ForwardSolver::ForwardSolver<ValueType>::updateModel(Modelparameter::Modelparameter<ValueType> &model)
+{
+    SCAI_ASSERT_ERROR(group, "initForwardSolver must be called before updateModel")
+    SCAI_ASSERT_ERROR(model.getEquationType() == equationType, "model type differs from the solver type")
+    for (auto const &kv : model.getRawParameters()) {
+        SCAI_ASSERT_ERROR(kv.second.size() == group->getNGlobal(), "the model does not fit the grid of the solver")
+        group->forEach([&](IndexType r) { check(ws_set_material(group->handle(r), kv.first.c_str(), kv.second.data(), kv.second.size())); });
+    }
+    model.bind(group.get());
+}
+
 // Variable grid / variable FD order: the operators are assembled here by the reference's rules (IrregularGrid.cpp) and handed to
 // the library (operator-given mode); replaces Derivatives::init + prepareBoundaryConditions + Modelparameter::prepareForModelling
 // of FDTD2D.cpp:186-232, CPML2DAcoustic.cpp:99-200, Acoustic.cpp prepareForModelling for this case.

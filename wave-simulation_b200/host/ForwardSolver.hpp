@@ -43,6 +43,9 @@ namespace KITGPI
             //! binds `wavefield` / `model` to it
             void initForwardSolver(Configuration::Configuration const &config, Derivatives::Derivatives<ValueType> &derivatives, Wavefields::Wavefields<ValueType> &wavefield,
                                    Modelparameter::Modelparameter<ValueType> &model, Acquisition::Coordinates<ValueType> const &modelCoordinates, ValueType DT);
+            //! another model on the same grid (the cut-out of the next shot, useStreamConfig): re-uploads the raw parameters into the
+            //! existing device solver; prepareForModelling must follow
+            void updateModel(Modelparameter::Modelparameter<ValueType> &model);
             //! Modelparameter::prepareForModelling products + boundary coefficients (CPML / ABS / free surface) on the GPU
             void prepareForModelling(Modelparameter::Modelparameter<ValueType> const &model, ValueType DT);
             void prepareBoundaryConditions(Configuration::Configuration const &, Acquisition::Coordinates<ValueType> const &, Derivatives::Derivatives<ValueType> &) {}

@@ -139,6 +139,29 @@ template <typename ValueType> typename Modelparameter::Modelparameter<ValueType>
     return std::make_shared<Modelparameter<ValueType>>(type); // throws "Unkown type" for anything else
 }
 
+template <typename ValueType>
+void Modelparameter::Modelparameter<ValueType>::getModelPerShot(Modelparameter<ValueType> &modelPerShot, Acquisition::Coordinates<ValueType> const &mc,
+                                                                Acquisition::Coordinates<ValueType> const &mcBig, Acquisition::coordinate3D const &cut) const
+{
+    SCAI_ASSERT_ERROR(modelPerShot.equationType == equationType, "model per shot of another equation type")
+    SCAI_ASSERT_ERROR(cut.x >= 0 && cut.x + mc.getNX() <= mcBig.getNX() && cut.y + mc.getNY() <= mcBig.getNY() && cut.z + mc.getNZ() <= mcBig.getNZ(),
+                      "the model per shot (cut at x = " << cut.x << ") does not lie inside the big model")
+    const IndexType nx = mc.getNX(), ny = mc.getNY(), nz = mc.getNZ();
+    auto out = std::make_shared<std::map<std::string, std::vector<ValueType>>>();
+    for (auto const &kv : *raw) {
+        std::vector<ValueType> v((size_t)nx * ny * nz);
+        for (IndexType y = 0; y < ny; y++)
+            for (IndexType z = 0; z < nz; z++) {
+                const ValueType *src = &kv.second[(size_t)mcBig.coordinate2index(cut.x, y + cut.y, z + cut.z)];
+                std::copy(src, src + nx, &v[(size_t)mc.coordinate2index(0, y, z)]);
+            }
+        (*out)[kv.first] = std::move(v);
+    }
+    modelPerShot.raw = out;
+    modelPerShot.relaxationFrequency = relaxationFrequency;
+    modelPerShot.dirtyFlag = true;
+}
+
 template <typename ValueType> std::vector<ValueType> Modelparameter::Modelparameter<ValueType>::getCompensation(ValueType DT, IndexType tStep) const
 {
     if (seismic)

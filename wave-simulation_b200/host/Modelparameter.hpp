@@ -49,6 +49,10 @@ namespace KITGPI
             //! largest propagation velocity (vp, vs for SH, c0/sqrt(eps_r mu_r) for EM): CheckParameter.hpp:183-200
             ValueType getMaxVelocity() const;
             ValueType getMinVelocity() const;
+            //! the part of this (big) model a shot works on: the box of `modelCoordinates` starting at cutCoordinate (useStreamConfig;
+            //! Elastic.cpp:104-140 getModelPerShot: shrink matrix = one 1 per row)
+            void getModelPerShot(Modelparameter<ValueType> &modelPerShot, Acquisition::Coordinates<ValueType> const &modelCoordinates,
+                                 Acquisition::Coordinates<ValueType> const &modelCoordinatesBig, Acquisition::coordinate3D const &cutCoordinate) const;
             //! exp(sigma / eps * tStep * DT), the amplitude compensation of an EM modelling (Modelparameter.cpp:127-143)
             std::vector<ValueType> getCompensation(ValueType DT, IndexType tStep) const;
 

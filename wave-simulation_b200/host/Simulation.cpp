@@ -14,6 +14,7 @@
 #include "Wavefields.hpp"
 #include "../../include/wavesim.h"
 #include <chrono>
+#include <ctime>
 #include <mutex>
 #include <thread>
 
@@ -28,12 +29,25 @@ namespace
     std::mutex printMutex;
 }
 
-// one shot domain = one GPU: shots [lb, ub) of the unique shot list (dmemo::blockDistribution(numshots, commInterShot))
-static void runShotDomain(Configuration::Configuration const &config, IndexType shotDomain, std::vector<IndexType> devices, IndexType lb, IndexType ub,
-                          std::vector<Acquisition::sourceSettings<ValueType>> const &sourceSettings, std::vector<IndexType> const &uniqueShotNos,
+// what the shot domains share: the acquisition of the survey as the main thread has set it up (Simulation.cpp:233-282)
+struct Survey {
+    std::vector<Acquisition::sourceSettings<ValueType>> sourceSettings; // plain or encoded (useSourceEncode): the list the shots are taken from
+    std::vector<IndexType> uniqueShotNos;                               // ... and its shot numbers
+    std::vector<Acquisition::sourceSettings<ValueType>> sourceSettingsEncode; // encoded list (empty without useSourceEncode)
+    bool useStreamConfig = false;                                       // per-shot model cut-outs of a big model
+    std::vector<Acquisition::coordinate3D> cutCoordinates;
+    Acquisition::Coordinates<ValueType> modelCoordinatesBig;
+    IndexType useSourceEncode = 0;
+};
+
+// one shot domain = one group of GPUs: the shots `shotInds` (indices into the unique shot list; block distribution of the shots or,
+// with useRandomSource, one shot of every pass: dmemo::blockDistribution(..., commInterShot), Simulation.cpp:339-344, 362-369)
+static void runShotDomain(Configuration::Configuration const &config, IndexType shotDomain, std::vector<IndexType> devices, std::vector<IndexType> shotInds, Survey const &survey,
                           Modelparameter::Modelparameter<ValueType>::ModelparameterPtr model, Acquisition::Coordinates<ValueType> const &modelCoordinates, double globalStart_t,
                           std::string *error)
 {
+    auto const &sourceSettings = survey.sourceSettings;
+    auto const &uniqueShotNos = survey.uniqueShotNos;
     try {
         std::string dimension = config.get<std::string>("dimension"), equationType = config.get<std::string>("equationType");
         std::transform(dimension.begin(), dimension.end(), dimension.begin(), ::tolower);
@@ -48,9 +62,16 @@ static void runShotDomain(Configuration::Configuration const &config, IndexType 
         solver->setDevices(devices);
         derivatives->init(config);
 
-        // every domain works on its own copy of the model object (binding to its solver); the raw vectors are shared data
+        // every domain works on its own copy of the model object (binding to its solver); the raw vectors are shared data.  With
+        // useStreamConfig the model of the domain is the cut-out of the current shot (Simulation.cpp:387-398).
         Modelparameter::Modelparameter<ValueType> modelLocal(*model);
         double start_t = now();
+        if (survey.useStreamConfig && !shotInds.empty()) {
+            IndexType first = shotInds[0];
+            if (survey.useSourceEncode == 3)
+                Acquisition::getuniqueShotInd(first, survey.sourceSettingsEncode, uniqueShotNos[shotInds[0]]);
+            model->getModelPerShot(modelLocal, modelCoordinates, survey.modelCoordinatesBig, survey.cutCoordinates.at(first));
+        }
         solver->initForwardSolver(config, *derivatives, *wavefields, modelLocal, modelCoordinates, DT);
         modelLocal.prepareForModelling();
         solver->prepareForModelling(modelLocal, DT);
@@ -63,15 +84,37 @@ static void runShotDomain(Configuration::Configuration const &config, IndexType 
 
         const IndexType snapType = config.get<IndexType>("snapType");
         const double tInit = now() - globalStart_t;
-        for (IndexType shotInd = lb; shotInd < ub; shotInd++) {
+        bool firstShot = true;
+        for (IndexType shotInd : shotInds) {
             const IndexType shotNumber = uniqueShotNos[shotInd];
             std::vector<Acquisition::sourceSettings<ValueType>> sourceSettingsShot;
             Acquisition::createSettingsForShot(sourceSettingsShot, sourceSettings, shotNumber);
             sources.init(sourceSettingsShot, config, modelCoordinates);
+            IndexType shotIndPerShot = shotInd;
+            if (survey.useStreamConfig) {
+                // Simulation.cpp:387-398: switch to the model subset of this shot
+                if (survey.useSourceEncode == 3)
+                    Acquisition::getuniqueShotInd(shotIndPerShot, survey.sourceSettingsEncode, shotNumber);
+                if (!firstShot) {
+                    model->getModelPerShot(modelLocal, modelCoordinates, survey.modelCoordinatesBig, survey.cutCoordinates.at(shotIndPerShot));
+                    solver->updateModel(modelLocal);
+                    modelLocal.prepareForModelling();
+                    solver->prepareForModelling(modelLocal, DT);
+                }
+                if (modelLocal.isSeismic())
+                    modelLocal.write(config.get<std::string>("ModelFilename") + ".shot_" + std::to_string(shotNumber), config.get<IndexType>("FileFormat"));
+            }
+            firstShot = false;
             CheckParameter::checkNumericalArtefactsAndInstabilities<ValueType>(config, sourceSettingsShot, modelLocal, modelCoordinates, shotNumber);
             if (config.getAndCatch("writeSource", false))
                 sources.getSeismogramHandler().write(config.get<IndexType>("SeismogramFormat"), config.get<std::string>("writeSourceFilename") + ".shot_" + std::to_string(shotNumber), &modelCoordinates);
-            if (config.get<IndexType>("useReceiversPerShot") != 0)
+            if (survey.useStreamConfig) {
+                // Receivers.cpp:86-121: the receivers of the shot are given in the big model and moved into its cut-out
+                std::vector<Acquisition::receiverSettings> bigSettings, shotSettings;
+                Acquisition::readAllSettings(bigSettings, config.get<std::string>("ReceiverFilename") + ".shot_" + std::to_string(shotNumber) + ".txt");
+                Acquisition::getSettingsPerShot<ValueType>(shotSettings, bigSettings, survey.cutCoordinates.at(shotIndPerShot), modelCoordinates, config.get<IndexType>("BoundaryWidth"));
+                receivers.init(shotSettings, config, modelCoordinates);
+            } else if (config.get<IndexType>("useReceiversPerShot") != 0)
                 receivers.init(config, modelCoordinates, shotNumber);
             receivers.getSeismogramHandler().resetData();
 
@@ -138,7 +181,14 @@ int main(int argc, const char *argv[])
         std::string dimension = config.get<std::string>("dimension"), equationType = config.get<std::string>("equationType");
         std::transform(dimension.begin(), dimension.end(), dimension.begin(), ::tolower);
         std::transform(equationType.begin(), equationType.end(), equationType.begin(), ::tolower);
-        SCAI_ASSERT_ERROR(config.getAndCatch("useStreamConfig", 0) == 0, "useStreamConfig=1 (model cut-outs per shot) is not available in the B200 host layer")
+        Survey survey;
+        survey.useStreamConfig = config.getAndCatch("useStreamConfig", false);
+        Configuration::Configuration configBig;
+        if (survey.useStreamConfig) { // Simulation.cpp:60-65: the big model the shots cut their sub-models from
+            configBig.readFromFile(config.get<std::string>("streamConfigFilename"));
+            survey.modelCoordinatesBig.init(configBig);
+            SCAI_ASSERT_ERROR(config.get<IndexType>("useReceiversPerShot") == 1, "useStreamConfig needs useReceiversPerShot = 1 here (Receivers.cpp:104-111; mode 2 is not available)")
+        }
 
         HOST_PRINT("\nWAVE-Simulation " << dimension << " " << equationType << " - LAMA-free host layer on " << ws_version() << "\n\n")
         if (verbose)
@@ -160,27 +210,58 @@ int main(int argc, const char *argv[])
             HOST_PRINT(" Wavefields, model and boundary slabs in HBM: " << solver->estimateMemory(config, modelCoordinates) << " MB per shot domain (derivatives are matrix-free: 0 MB)\n\n")
         }
 
-        /* acquisition geometry (Simulation.cpp:233-282) */
+        /* acquisition geometry (Simulation.cpp:233-282): shot selection (shotIncr), per-shot cut-outs (useStreamConfig), source encoding */
+        IndexType seedtime = config.getAndCatch("seedtime", (IndexType)time(nullptr)); // Simulation.cpp:46 takes the clock; the key makes a run repeatable
         Acquisition::Sources<ValueType> sources;
-        sources.getAcquisitionSettings(config);
-        std::vector<Acquisition::sourceSettings<ValueType>> sourceSettings = sources.getSourceSettings();
+        sources.getAcquisitionSettings(config, config.getAndCatch("shotIncr", ValueType(0)));
+        std::vector<Acquisition::sourceSettings<ValueType>> sourceSettings;
+        if (survey.useStreamConfig) {
+            std::vector<Acquisition::sourceSettings<ValueType>> sourceSettingsBig = sources.getSourceSettings();
+            Acquisition::getCutCoord(config, survey.cutCoordinates, sourceSettingsBig, modelCoordinates, survey.modelCoordinatesBig);
+            Acquisition::getSettingsPerShot(sourceSettings, sourceSettingsBig, survey.cutCoordinates, modelCoordinates, config.get<IndexType>("BoundaryWidth"));
+            sources.setSourceSettings(sourceSettings); // for useSourceEncode
+        } else
+            sourceSettings = sources.getSourceSettings();
         CheckParameter::checkAcquisition<ValueType>(sourceSettings, modelCoordinates, "source");
         std::vector<IndexType> uniqueShotNos;
         Acquisition::calcuniqueShotNo(uniqueShotNos, sourceSettings);
-        const IndexType numshots = (IndexType)uniqueShotNos.size();
-        SCAI_ASSERT_ERROR(config.getAndCatch("useSourceEncode", 0) == 0 && config.getAndCatch("useRandomSource", 0) == 0, "source encoding / random shots belong to the inversion workflow")
+        survey.useSourceEncode = config.getAndCatch("useSourceEncode", 0);
+        const IndexType useRandomSource = config.getAndCatch("useRandomSource", 0);
+        IndexType wantedDomains = std::max<IndexType>(1, config.getAndCatch("NumShotDomains", 1));
+        sources.calcSourceSettingsEncode(config, seedtime);
+        IndexType numshots;
+        if (survey.useSourceEncode == 0) {
+            numshots = (IndexType)uniqueShotNos.size();
+            survey.sourceSettings = sourceSettings;
+            survey.uniqueShotNos = uniqueShotNos;
+        } else { // the supershots take the place of the shots (Simulation.cpp:260-266)
+            survey.sourceSettingsEncode = sources.getSourceSettingsEncode();
+            survey.sourceSettings = survey.sourceSettingsEncode;
+            Acquisition::calcuniqueShotNo(survey.uniqueShotNos, survey.sourceSettingsEncode);
+            numshots = (IndexType)survey.uniqueShotNos.size();
+            SCAI_ASSERT_ERROR(numshots <= wantedDomains, "more supershots than NumShotDomains")
+        }
+        SCAI_ASSERT_ERROR(numshots >= wantedDomains || survey.useSourceEncode != 0, "numshots = " << numshots << ", numShotDomains = " << wantedDomains)
+        if (survey.useSourceEncode == 0 && useRandomSource == 0 && wantedDomains <= nDevices)
+            SCAI_ASSERT_ERROR(numshots % wantedDomains == 0, "numshots = " << numshots << ", numShotDomains = " << wantedDomains)
+        sources.writeShotIndsIncr(config, uniqueShotNos);
+        sources.writeSourceEncode(config);
+        if (survey.useStreamConfig)
+            Acquisition::writeCutCoordToFile(config, configBig.get<std::string>("SourceFilename"), survey.cutCoordinates, uniqueShotNos, config.get<IndexType>("NX"));
 
-        /* model (Simulation.cpp:284-295) */
+        /* model (Simulation.cpp:284-295): with useStreamConfig the big model */
         double start_t = now();
         auto model = Modelparameter::Factory<ValueType>::Create(equationType);
-        model->init(config, modelCoordinates);
+        if (survey.useStreamConfig)
+            model->init(configBig, survey.modelCoordinatesBig);
+        else
+            model->init(config, modelCoordinates);
         HOST_PRINT("", "Finished initializing model in " << now() - start_t << " sec.\n\n")
 
         /* shot domains: block distribution of the shots over min(NumShotDomains, GPUs) domains; the GPUs of a domain share
            one shot as y-slabs.  A slab should keep enough planes to hide the halo exchange behind its interior, so by
            default a domain uses at most NY / 64 GPUs (key GPUsPerShotDomain overrides, WS_NUM_GPUS limits the box). */
-        IndexType numShotDomains = std::max<IndexType>(1, config.getAndCatch("NumShotDomains", 1));
-        numShotDomains = std::min(numShotDomains, std::min(numshots, nDevices));
+        IndexType numShotDomains = std::min(wantedDomains, std::min(numshots, nDevices));
         IndexType gpusPerDomain = std::max<IndexType>(1, nDevices / numShotDomains);
         {
             const IndexType NY = config.get<IndexType>("NY");
@@ -191,19 +272,38 @@ int main(int argc, const char *argv[])
                 gpusPerDomain = std::min(gpusPerDomain, std::max<IndexType>(1, NY / 64));
         }
         HOST_PRINT(" " << numShotDomains << " shot domain(s) x " << gpusPerDomain << " GPU(s) per domain (y-slabs), " << nDevices << " GPU(s) visible\n\n")
+        // which shots a domain works on.  Plain / encoded: its block of the shot list (the reference walks that block numshots /
+        // NumShotDomains times, Simulation.cpp:345-362, and writes the same files every time: once is enough).  useRandomSource:
+        // numshots / NumShotDomains passes, every pass draws NumShotDomains shots, one per configured domain (Simulation.cpp:339-369);
+        // with fewer GPUs than domains a GPU group takes the shots of several configured domains.
+        std::vector<std::vector<IndexType>> shotsOfDomain(numShotDomains);
+        if (useRandomSource != 0) {
+            std::vector<IndexType> shotHistory(numshots, 0);
+            const IndexType numRand = numshots / wantedDomains, maxcount = 1;
+            for (IndexType randInd = 0; randInd < numRand; randInd++) {
+                sources.calcUniqueShotInds(config, shotHistory, maxcount, seedtime);
+                auto const &inds = sources.getUniqueShotInds();
+                for (IndexType k = 0; k < (IndexType)inds.size(); k++)
+                    shotsOfDomain[k % numShotDomains].push_back(inds[k]);
+            }
+        } else {
+            for (IndexType dom = 0; dom < numShotDomains; dom++) {
+                const IndexType base = numshots / numShotDomains, rem = numshots % numShotDomains;
+                const IndexType lb = dom * base + std::min(dom, rem), ub = lb + base + (dom < rem ? 1 : 0);
+                for (IndexType k = lb; k < ub; k++)
+                    shotsOfDomain[dom].push_back(k);
+            }
+        }
         std::vector<std::thread> threads;
         std::vector<std::string> errors(numShotDomains);
         for (IndexType dom = 0; dom < numShotDomains; dom++) {
-            const IndexType base = numshots / numShotDomains, rem = numshots % numShotDomains;
-            const IndexType lb = dom * base + std::min(dom, rem), ub = lb + base + (dom < rem ? 1 : 0);
             std::vector<IndexType> devices;
             for (IndexType r = 0; r < gpusPerDomain; r++)
                 devices.push_back(dom * gpusPerDomain + r);
             if (numShotDomains == 1)
-                runShotDomain(config, dom, devices, lb, ub, sourceSettings, uniqueShotNos, model, modelCoordinates, globalStart_t, &errors[dom]);
+                runShotDomain(config, dom, devices, shotsOfDomain[dom], survey, model, modelCoordinates, globalStart_t, &errors[dom]);
             else
-                threads.emplace_back(runShotDomain, std::cref(config), dom, devices, lb, ub, std::cref(sourceSettings), std::cref(uniqueShotNos), model, std::cref(modelCoordinates),
-                                     globalStart_t, &errors[dom]);
+                threads.emplace_back(runShotDomain, std::cref(config), dom, devices, shotsOfDomain[dom], std::cref(survey), model, std::cref(modelCoordinates), globalStart_t, &errors[dom]);
         }
         for (auto &t : threads)
             t.join();
