@@ -807,3 +807,88 @@ def test_driver_stream_config_model_per_shot(driver, tmp_path):
         vp = read_mtx(os.path.join(tmp, "model", "model.shot_%d.vp.mtx" % shot)).ravel()
         assert np.array_equal(vp.astype(np.float32), case.materials["velocityP"])
     assert not np.allclose(got[1], got[2], rtol=1e-3)  # the lateral gradient makes the two cut-outs differ
+
+
+# frequency filters and Hilbert transform (Filter/Filter.cpp, Common/HilbertFFT.cpp)
+def run_filter_tool(tmp_path, data, dt, *op):
+    subprocess.check_call(["make", "-s", "-C", HOST, "libSimulation_host.a"])
+    exe = str(tmp_path / "test_filter")
+    if not os.path.exists(exe):
+        subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-I" + HOST, os.path.join(ROOT, "tests", "host", "test_filter.cpp"),
+                               os.path.join(HOST, "libSimulation_host.a"), "-o", exe])
+    fin, fout = str(tmp_path / "in.f32"), str(tmp_path / "out.f32")
+    np.ascontiguousarray(data, np.float32).tofile(fin)
+    p = subprocess.run([exe, fin, fout, str(data.shape[0]), str(data.shape[1]), repr(dt)] + [str(x) for x in op], capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
+    return np.fromfile(fout, np.float32).reshape(data.shape)
+
+
+def read_mtx_coordinate(path):
+    with open(path) as f:
+        lines = [ln for ln in f if not ln.startswith("%")]
+    r, c, nnz = (int(x) for x in lines[0].split())
+    m = np.zeros((r, c))
+    for ln in lines[1:1 + nnz]:
+        i, j, v = ln.split()
+        m[int(i) - 1, int(j) - 1] = float(v)
+    return m
+
+
+def test_filter_reproduces_the_reference_fixture(tmp_path):
+    """The reference's own known answer (Tests/UnitTest/FilterUnitTest.cpp): Butterworth low pass, order 4, 15 Hz, dt 1 ms, 500 samples,
+    21 traces; its gate is ||filtered - ref||_2 < 0.005."""
+    gold = os.path.join(ROOT, "tests", "golden")
+    sig, ref = read_mtx_coordinate(os.path.join(gold, "filterTest_signal.mtx")), read_mtx_coordinate(os.path.join(gold, "filterTest_signalFiltRef.mtx"))
+    assert sig.shape == ref.shape == (21, 500)
+    for op in ("filter", "filter1"):
+        out = run_filter_tool(tmp_path, sig, 1e-3, op, "butterworth", "lp", 4, 15.0)
+        assert np.linalg.norm(out - ref) < 0.005, np.linalg.norm(out - ref)
+    assert np.linalg.norm(sig - ref) > 0.1  # the filter does something to this signal
+
+
+def butter_transfer(nt, dt, kind, order, fc):
+    n = 1 << int(np.ceil(np.log2(nt - 1)))
+    f = np.fft.fftfreq(n, dt)
+    f[n // 2] = abs(f[n // 2])  # Filter.cpp:25-31 lists the Nyquist bin with a positive frequency
+    k = np.arange(1, order // 2 + 1)
+    poly = np.poly1d([1.0])
+    for c in -2.0 * np.cos((2.0 * k + order - 1.0) / (2.0 * order) * np.pi):
+        poly = poly * np.poly1d([1.0, c, 1.0])
+    if order % 2:
+        poly = poly * np.poly1d([1.0, 1.0])
+    with np.errstate(divide="ignore", invalid="ignore"):
+        s = 1j * f / fc if kind == "lp" else -1j * fc / f
+        h = 1.0 / poly(s)
+    h[0] = 1.0 if kind == "lp" else 0.0
+    return n, h
+
+
+def test_filter_and_hilbert_against_numpy(tmp_path):
+    rng = np.random.default_rng(5)
+    nt, dt = 700, 2e-3
+    t = np.arange(nt) * dt
+    sig = np.stack([np.sin(2 * np.pi * 5 * t) + 0.5 * np.sin(2 * np.pi * 60 * t + 1.0), rng.standard_normal(nt), np.exp(-((t - 0.5) / 0.05) ** 2)])
+    for kind, order, fc in (("lp", 3, 20.0), ("hp", 4, 30.0), ("lp", 6, 45.0)):
+        n, h = butter_transfer(nt, dt, kind, order, fc)
+        want = np.real(np.fft.ifft(np.fft.fft(sig, n, axis=1) * h, axis=1))[:, :nt]
+        out = run_filter_tool(tmp_path, sig, dt, "filter", "butterworth", kind, order, fc)
+        assert np.abs(out - want).max() <= 2e-6 * np.abs(want).max(), (kind, order)
+    n, hl = butter_transfer(nt, dt, "lp", 4, 50.0)
+    _, hh = butter_transfer(nt, dt, "hp", 4, 10.0)
+    want = np.real(np.fft.ifft(np.fft.fft(sig, n, axis=1) * hl * hh, axis=1))[:, :nt]
+    out = run_filter_tool(tmp_path, sig, dt, "filter", "butterworth", "bp", 4, 10.0, 50.0)
+    assert np.abs(out - want).max() <= 2e-6 * np.abs(want).max()
+    # ideal band pass, order 0: only the FFT bin of the frequency passes
+    out = run_filter_tool(tmp_path, sig, dt, "filter", "ideal", "bp", 0, 5.0)
+    df = 1.0 / (n * dt)
+    k = int(np.ceil(5.0 / df))
+    spec = np.fft.fft(sig, n, axis=1)
+    mask = np.zeros(n)
+    mask[[k, n - k]] = 1.0
+    want = np.real(np.fft.ifft(spec * mask, axis=1))[:, :nt]
+    assert np.abs(out - want).max() <= 2e-6 * np.abs(sig).max()
+    # Hilbert transform = imaginary part of the analytic signal of the zero-padded trace (scipy.signal.hilbert)
+    from scipy.signal import hilbert
+    out = run_filter_tool(tmp_path, sig, dt, "hilbert")
+    want = np.imag(hilbert(sig, N=n, axis=1))[:, :nt]
+    assert np.abs(out - want).max() <= 2e-6 * np.abs(want).max()

@@ -443,6 +443,18 @@ template <typename ValueType> static void readSourceSettingsFromSU(std::vector<A
     SCAI_ASSERT_ERROR(!all.empty(), "No file with name: " << filename << ".'comp'.su could be read")
 }
 
+template <typename ValueType> void Acquisition::Seismogram<ValueType>::filterTraces(Filter::Filter<ValueType> const &freqFilter)
+{
+    if (getNumSamples() != 0 && getNumTraces() != 0)
+        freqFilter.apply(data, getNumTraces(), getNumSamples());
+}
+
+template <typename ValueType> void Acquisition::SeismogramHandler<ValueType>::filter(Filter::Filter<ValueType> const &freqFilter)
+{
+    for (auto &s : seismo)
+        s.filterTraces(freqFilter);
+}
+
 template <typename ValueType> void Acquisition::Sources<ValueType>::getAcquisitionSettings(Configuration::Configuration const &config, ValueType shotIncr)
 {
     // Sources.cpp:502-514: with useStreamConfig the sources are those of the big model

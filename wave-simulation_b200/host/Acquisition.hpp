@@ -10,6 +10,7 @@
 #include "Common.hpp"
 #include "Configuration.hpp"
 #include "Coordinates.hpp"
+#include "Filter.hpp"
 #include <array>
 
 namespace KITGPI
@@ -89,6 +90,7 @@ namespace KITGPI
             void setTraceType(IndexType t, bool seismic) { type = t; isSeismic = seismic; }
             IndexType getTraceType() const { return type; }
             void normalizeTrace(IndexType normalizeTraces);
+            void filterTraces(Filter::Filter<ValueType> const &freqFilter); // Seismogram.cpp:509-520
             bool isFinite() const;
             //! SeismogramFormat 1 = mtx, 2 = lmf, 4 = SU (needs the model coordinates for the trace headers, Seismogram.cpp:82-147)
             void write(IndexType seismogramFormat, std::string const &filename, Coordinates<ValueType> const *modelCoordinates = nullptr) const;
@@ -118,6 +120,7 @@ namespace KITGPI
             void setSeismoDT(ValueType dt);
             void resetData();
             void normalize(IndexType normalizeTraces);
+            void filter(Filter::Filter<ValueType> const &freqFilter); // SeismogramHandler.cpp:76-86
             bool isFinite() const;
             void write(IndexType seismogramFormat, std::string const &filename, Coordinates<ValueType> const *modelCoordinates = nullptr) const;
             void setSourceCoordinate(IndexType sourceCoord); // SeismogramHandler.cpp:340
