@@ -306,7 +306,7 @@ def main():
             ck, cw = max(1, min(K, 20)), max(1, args.warmup)
             r = cpu_reference_sample(cpu_sample_size(args.ref_n, ck, cw), ck, cw)
             cpu = {"value": r["gpts"], "unit": "Gpt/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
-        cfg = {"workload": m["workload"], "l2": m["l2"], "kernels": m["kernels"], "finite": m["finite"]}
+        cfg = {"workload": m["workload"], "l2": m["l2"], "kernels": m["kernels"], "finite": m["finite"], "halo": m["halo"]}
         if others is not None:
             cfg["others"] = others
         line = {
@@ -408,6 +408,7 @@ def measure(wlname, nx, nyl, nz, K, W, variant, damping, free_surface, world, ra
         "workload": "%s %dx%dx%d per GPU (global NY %d), %sCPML(20), y-slab decomposition" % (wl["name"], nx, nyl, nz, gny, "free surface + " if free_surface else ""),
         "l2": "inputs (%.1f GB/GPU of wavefields+model) exceed the 126 MB L2" % (ws_bytes / 1e9),
         "kernels": ["per-point", "marching", "tma-tiled", "tma-marching", "tma-tile2d"][s.kernel_path()], "finite": bool(finite),
+        "halo": ["none", "nccl send/recv", "external", "kernels over peer memory"][s.halo_transport()],
         "value": npts * K / (ms * 1e-3) / 1e9, "ms_per_step": ms / K, "launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "traffic_source": "committed ncu capture of this configuration (profiles/traffic_1024.json), not measured in this run" if traffic else None,

@@ -157,6 +157,12 @@ int ws_set_step_scaling(ws_solver *s, const float *host, size_t n);
  * with the interior kernels.                                                                                      */
 int ws_comm_unique_id(void *id128);
 int ws_comm_init(ws_solver *s, const void *id128);
+/* Where every neighbour's memory can be mapped (GPUs of one NVLink / NVSwitch node: peer access inside a process, CUDA IPC between
+ * processes) ws_comm_init switches the halo planes of the time loop from ncclSend / ncclRecv to the library's own kernels: the sender
+ * stores its edge planes straight into the neighbour's ghost planes and raises a counter there, the neighbour's edge-slab kernels wait
+ * for the counter.  NCCL stays for the collectives (isFinite, set-up exchanges).  env WS_P2P=0 keeps NCCL for everything.
+ * 0 = single rank, 1 = NCCL send / recv, 2 = external transport, 3 = kernels over peer memory                                     */
+int ws_halo_transport(const ws_solver *s);
 /* Bring-your-own transport instead of NCCL (e.g. CUDA-aware MPI, the dmemo::Communicator role; gloo in the CPU tests):
  * `fn` must send `count` floats from `send` to rank `peer` and receive `count` floats from it into `recv` (device
  * pointers on this handle's GPU), returning 0 on success.  Synchronous: the library drains its streams before each

@@ -1,5 +1,7 @@
-"""y-slab decomposition over NCCL on real GPUs (needs >= 2 devices, skipped otherwise): tiled and general kernels, result
-bit-identical to the single-GPU run (every grid point sees the same arithmetic whatever the decomposition)."""
+"""y-slab decomposition on real GPUs (needs >= 2 devices, skipped otherwise), with both halo transports — the library's own kernels
+over peer memory (CUDA IPC between the processes here; the default where the GPUs can map each other) and ncclSend / ncclRecv
+(WS_P2P=0): every kernel family, result bit-identical to the single-GPU run (every grid point sees the same arithmetic whatever
+the decomposition)."""
 import numpy as np
 import pytest
 import torch
@@ -21,7 +23,7 @@ def _worker(rank, world, uid, cfg, nt, variant, out):
     s.run(0, nt)
     s.sync()
     assert s.is_finite()
-    out.put((rank, s.y0, s.nyl, s.seismogram(), {f: s.wavefield(f) for f in fields_of(eq, dim, L)}, s.uses_fast_kernels()))
+    out.put((rank, s.y0, s.nyl, s.seismogram(), {f: s.wavefield(f) for f in fields_of(eq, dim, L)}, s.halo_transport()))
     s.close()
 
 
@@ -33,14 +35,25 @@ CASES = [
     (("elastic", 3, 128, 96, 48, 8, 0, 1, 2, 10, 0), 2),   # marching kernels forced (4 x points per thread)
     (("viscoelastic", 3, 72, 64, 24, 8, 0, 1, 2, 8, 2), 0),  # marching kernels, one x point per thread in the stress half-step
     (("viscoemem", 3, 40, 64, 24, 4, 1, 0, 2, 6, 1), 0),
+    (("elastic", 2, 300, 200, 1, 8, 0, 1, 2, 10, 0), 0),    # 2-D tile kernels
+    (("viscotmem", 2, 260, 130, 1, 8, 1, 0, 1, 8, 2), 0),
 ]
+
+
+def _peer_access(world):
+    return all(torch.cuda.can_device_access_peer(a, b) for a in range(world) for b in range(world) if a != b)
 
 
 @pytest.mark.parametrize("cfg,variant", CASES, ids=["%s%dD-v%d" % (c[0][0], c[0][1], c[1]) for c in CASES])
 @pytest.mark.parametrize("world", [2, 4])
-def test_nccl_slabs_equal_single_gpu(cfg, variant, world):
+@pytest.mark.parametrize("transport", ["peer", "nccl"])
+def test_slabs_equal_single_gpu(cfg, variant, world, transport, monkeypatch):
     if torch.cuda.device_count() < world:
         pytest.skip("needs %d GPUs" % world)
+    if transport == "nccl":
+        monkeypatch.setenv("WS_P2P", "0")
+    else:
+        monkeypatch.delenv("WS_P2P", raising=False)
     from wsharness import Solver
     eq, dim, nx, ny, nz, q, pol, fs, damp, W, L = cfg
     nt = 30
@@ -63,7 +76,8 @@ def test_nccl_slabs_equal_single_gpu(cfg, variant, world):
         assert p.exitcode == 0
     plane = nx * (nz if dim == 3 else 1)
     seis = np.zeros_like(ref_seis)
-    for rank, y0, nyl, sg, fields, fast in results:
+    for rank, y0, nyl, sg, fields, tr in results:
+        assert tr == (1 if transport == "nccl" or not _peer_access(world) else 3), tr
         seis += sg  # rows of receivers on other ranks are zero
         for f, a in fields.items():
             assert np.array_equal(a, ref_fields[f][y0 * plane:(y0 + nyl) * plane]), (rank, f)
@@ -115,9 +129,14 @@ def _worker_reset(rank, world, uid, cfg, nt, out):
     s.close()
 
 
-def test_run_reset_run_on_two_ranks_equals_single_gpu():
+@pytest.mark.parametrize("transport", ["peer", "nccl"])
+def test_run_reset_run_on_two_ranks_equals_single_gpu(transport, monkeypatch):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
+    if transport == "nccl":
+        monkeypatch.setenv("WS_P2P", "0")
+    else:
+        monkeypatch.delenv("WS_P2P", raising=False)
     from wsharness import Solver
     cfg = ("elastic", 3, 128, 96, 48, 8, 0, 1, 2, 10, 0)
     eq, dim, nx, ny, nz, q, pol, fs, damp, W, L = cfg

@@ -147,6 +147,8 @@ def _load_ws_lib(path):
     lib.ws_stream.argtypes = [C.c_void_p]
     lib.ws_uses_fast_kernels.argtypes = [C.c_void_p]
     lib.ws_kernel_path.argtypes = [C.c_void_p]
+    if hasattr(lib, "ws_halo_transport"):
+        lib.ws_halo_transport.argtypes = [C.c_void_p]
     if hasattr(lib, "ws_wavefields_create"):
         lib.ws_wavefields_destroy.argtypes = [C.c_void_p]
         lib.ws_wavefields_destroy.restype = None
@@ -271,6 +273,10 @@ class Solver(SolverBase):
         f = C.c_int32()
         self._check(self.lib.ws_is_finite(self.h, C.byref(f)), "is_finite")
         return bool(f.value)
+
+    def halo_transport(self):
+        """0 single rank, 1 NCCL send / recv, 2 external transport, 3 the library's kernels over peer memory"""
+        return int(self.lib.ws_halo_transport(self.h))
 
     def comm_init(self, id_bytes):
         buf = (C.c_char * 128).from_buffer_copy(id_bytes)

@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
+#include <unistd.h>
 #include <exception>
 #include <map>
 #include <memory>
@@ -57,6 +58,7 @@ struct NcclApi {
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
     void load()
     {
@@ -80,6 +82,7 @@ struct NcclApi {
         NCCL_SYM(GroupStart, "ncclGroupStart")
         NCCL_SYM(GroupEnd, "ncclGroupEnd")
         NCCL_SYM(AllReduce, "ncclAllReduce")
+        NCCL_SYM(AllGather, "ncclAllGather")
         NCCL_SYM(GetErrorString, "ncclGetErrorString")
 #undef NCCL_SYM
     }
@@ -92,6 +95,7 @@ struct NcclApi {
 NcclApi g_nccl;
 constexpr int kNcclFloat = 7; // ncclFloat32
 constexpr int kNcclInt = 2;   // ncclInt32
+constexpr int kNcclChar = 0;  // ncclInt8
 constexpr int kNcclMax = 2;   // ncclMax
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -264,6 +268,84 @@ __global__ void kWfScaleVecAll(WsFieldTable t, const float *__restrict__ vec, si
         t.p[k][first + i] = __fmul_rn(t.p[k][first + i], v);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// halo exchange over peer memory (NVLink / NVSwitch): the sender's kernel stores its edge planes straight into the ghost planes of
+// the neighbour's arrays and then raises a counter in the neighbour's memory; the neighbour's edge-slab kernels are preceded by a
+// one-thread kernel that waits for that counter.  No send / recv pairing, no host involvement, nothing but kernels: the exchange is
+// captured in the step graph like any other launch.  Counters (one int each, device memory of the RECEIVER, written by its
+// neighbours; P2P_* below) count exchanges since the solver was created; who expects which count lives in device memory too, so
+// the captured graph is step-invariant.  Write-after-read on the ghost planes needs no acknowledgement: a rank can only push
+// exchange A of step n after it has received exchange B of step n-1, which its neighbour sends after the kernels that read the
+// previous ghost planes (and likewise for B after A).
+// ---------------------------------------------------------------------------------------------------------------------
+enum { P2P_FLAG_UP_A = 0, P2P_FLAG_UP_B = 1, P2P_FLAG_DOWN_A = 2, P2P_FLAG_DOWN_B = 3, P2P_WAIT_A = 4, P2P_WAIT_B = 5, P2P_PUSH_A = 6, P2P_PUSH_B = 7,
+       P2P_DONE = 8, P2P_ERROR = 9, P2P_NINTS = 16 };
+#ifndef WS_EMULATE
+constexpr int WS_P2P_MAXF = 6;
+struct WsPushArgs {
+    const float *src[2][WS_P2P_MAXF]; // [0: to the upper neighbour (rank - 1), 1: to the lower neighbour][field]
+    float *dst[2][WS_P2P_MAXF];       // ghost planes inside the neighbour's arrays (peer-mapped)
+    int *peerFlag[2];                 // the counter this exchange raises at the neighbour (null: no neighbour on that side)
+    int *local;                       // this rank's P2P_* block
+    int nf, type;                     // fields, 0 = exchange A (after the first half-step), 1 = exchange B
+    size_t count4;                    // float4 per field and direction
+};
+__device__ __forceinline__ int ldAcquireSys(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void stReleaseSys(int *p, int v) { asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__global__ void __launch_bounds__(256) kHaloPush(const WsPushArgs a)
+{
+    const int dir = blockIdx.y / a.nf, f = blockIdx.y - dir * a.nf;
+    if (a.peerFlag[dir]) {
+        const float4 *__restrict__ src = reinterpret_cast<const float4 *>(a.src[dir][f]);
+        float4 *__restrict__ dst = reinterpret_cast<float4 *>(a.dst[dir][f]);
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.count4; i += (size_t)gridDim.x * blockDim.x)
+            dst[i] = src[i];
+    }
+    __threadfence_system(); // the planes are visible at the neighbour before the counter is
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int total = gridDim.x * gridDim.y;
+        if (atomicAdd(a.local + P2P_DONE, 1) == total - 1) { // the last thread block of the grid raises the counters
+            __threadfence_system();
+            const int n = a.local[P2P_PUSH_A + a.type] + 1;
+            // at the upper neighbour this rank is the "down" side, at the lower neighbour the "up" side
+            if (a.peerFlag[0])
+                stReleaseSys(a.peerFlag[0] + P2P_FLAG_DOWN_A + a.type, n);
+            if (a.peerFlag[1])
+                stReleaseSys(a.peerFlag[1] + P2P_FLAG_UP_A + a.type, n);
+            a.local[P2P_PUSH_A + a.type] = n;
+            a.local[P2P_DONE] = 0;
+        }
+    }
+}
+// waits until the ghost planes of exchange `type` have landed from both neighbours: A is expected once more than the waits done so
+// far (the exchange of this step), B as often as the waits done so far (the exchange of the step before; none before the first step)
+__global__ void kHaloWait(int *local, int type, int hasUp, int hasDown)
+{
+    const int e = type == 0 ? local[P2P_WAIT_A] + 1 : local[P2P_WAIT_B];
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        const bool up = !hasUp || ldAcquireSys(local + P2P_FLAG_UP_A + type) >= e;
+        const bool down = !hasDown || ldAcquireSys(local + P2P_FLAG_DOWN_A + type) >= e;
+        if (up && down)
+            break;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 20000000000ull) { // 20 s: a neighbour is gone; report instead of hanging the GPU
+            local[P2P_ERROR] = 1;
+            break;
+        }
+        __nanosleep(200);
+    }
+    local[P2P_WAIT_A + type] = type == 0 ? e : e + 1;
+}
+#endif
+
 template <typename T>
 struct DevBuf {
     T *p = nullptr;
@@ -387,6 +469,13 @@ struct ws_solver {
     // halo exchange lists
     std::vector<int> exchA, exchB; // field slots whose y-ghost planes are needed after pass A / pass B
     void *ncclComm = nullptr;
+    // halo exchange over peer memory (ws_comm_init sets it up when every neighbour's memory can be mapped)
+    bool p2p = false;
+    DevBuf<int> p2pLocal;                      // P2P_* block of this rank
+    float *peerArena[2] = {nullptr, nullptr};  // wavefield arena of the upper / lower neighbour, mapped into this process
+    int *peerFlags[2] = {nullptr, nullptr};    // their P2P_* blocks
+    bool peerIpc[2] = {false, false};          // opened with cudaIpcOpenMemHandle (another process)
+    int peerNyl[2] = {0, 0};
     ws_sendrecv_fn extFn = nullptr; // bring-your-own transport (ws_comm_init_external)
     void *extUser = nullptr;
     // instrumentation
@@ -438,6 +527,11 @@ struct ws_solver {
             cudaEventDestroy(evComputeG);
         if (evCommG)
             cudaEventDestroy(evCommG);
+        for (int d = 0; d < 2; d++)
+            if (peerIpc[d]) {
+                cudaIpcCloseMemHandle(peerArena[d]);
+                cudaIpcCloseMemHandle(peerFlags[d]);
+            }
         if (ncclComm && g_nccl.CommDestroy)
             g_nccl.CommDestroy(ncclComm);
         if (pinSrc)
@@ -718,6 +812,145 @@ void exchangeHalos(ws_solver *s, const std::vector<float *> &arrays, int h, cuda
     }
     g_nccl.check(g_nccl.GroupEnd(), "ncclGroupEnd");
 }
+
+#ifndef WS_EMULATE
+// start of local plane 0 of an array (the ghost planes lie right before it and after plane nyl - 1)
+float *planeZero(const ws_solver *s, float *a) { return a + s->base - WS_PADX - (long long)(s->nzp > 1 ? WS_HALO : 0) * s->pitch; }
+
+// exchange `type` (0 = A: after the first half-step, 1 = B: after the step) of the wavefield slots `slots` over peer memory
+void pushHalos(ws_solver *s, const std::vector<int> &slots, int type, cudaStream_t st)
+{
+    WS_REQUIRE((int)slots.size() <= WS_P2P_MAXF, WS_EINVAL, "too many fields in a halo exchange");
+    WsPushArgs a{};
+    const int h = s->h;
+    a.nf = (int)slots.size();
+    a.type = type;
+    a.local = s->p2pLocal.p;
+    a.count4 = (size_t)h * (size_t)s->plane / 4;
+    const bool up = s->d.rank > 0, down = s->d.rank + 1 < s->d.nranks;
+    a.peerFlag[0] = up ? s->peerFlags[0] : nullptr;
+    a.peerFlag[1] = down ? s->peerFlags[1] : nullptr;
+    for (int k = 0; k < a.nf; k++) {
+        float *mine = planeZero(s, s->fld[slots[k]].p);
+        const long long pos = s->ainfo.fldPos[slots[k]];
+        WS_REQUIRE(pos >= 0, WS_ESTATE, "halo exchange over peer memory: the wavefield is not part of the arena");
+        if (up) { // my planes [0, h) -> the upper neighbour's planes [nyl', nyl' + h)
+            const long long peerTotal = s->plane * (long long)(s->peerNyl[0] + 2 * WS_HALO);
+            a.src[0][k] = mine;
+            a.dst[0][k] = planeZero(s, s->peerArena[0] + pos * peerTotal) + (long long)s->peerNyl[0] * s->plane;
+        }
+        if (down) { // my planes [nyl - h, nyl) -> the lower neighbour's planes [-h, 0)
+            const long long peerTotal = s->plane * (long long)(s->peerNyl[1] + 2 * WS_HALO);
+            a.src[1][k] = mine + (long long)(s->nyl - h) * s->plane;
+            a.dst[1][k] = planeZero(s, s->peerArena[1] + pos * peerTotal) - (long long)h * s->plane;
+        }
+    }
+    // enough thread blocks to keep the NVLink ports busy next to the interior kernel, few enough not to crowd it out
+    const unsigned nb = (unsigned)std::max<size_t>(1, std::min<size_t>(32, (a.count4 + 2047) / 2048));
+    kHaloPush<<<dim3(nb, 2 * a.nf), 256, 0, st>>>(a);
+    s->launches++;
+}
+
+void waitHalos(ws_solver *s, int type, cudaStream_t st)
+{
+    kHaloWait<<<1, 1, 0, st>>>(s->p2pLocal.p, type, s->d.rank > 0 ? 1 : 0, s->d.rank + 1 < s->d.nranks ? 1 : 0);
+    s->launches++;
+}
+
+// every rank publishes where its wavefield arena and its counters live; neighbours in the same process use the pointers directly
+// (peer access enabled), neighbours in other processes open CUDA IPC handles.  Collective over the NCCL communicator; the exchange
+// over peer memory is used only if EVERY rank could map its neighbours.
+struct P2PInfo {
+    int pid, device, nyl, pad;
+    unsigned long long arena, flags;
+    cudaIpcMemHandle_t arenaHandle, flagsHandle;
+};
+void p2pSetup(ws_solver *s)
+{
+    s->p2p = false;
+    if (s->d.nranks <= 1 || !s->ncclComm || s->sparse)
+        return;
+    if (const char *e = getenv("WS_P2P"))
+        if (atoi(e) == 0)
+            return;
+    float *arena = s->fldArena.p ? s->fldArena.p : s->arena.p;
+    s->p2pLocal.alloc(P2P_NINTS);
+    s->p2pLocal.zero(s->stream);
+    P2PInfo mine{};
+    mine.pid = (int)getpid();
+    mine.device = s->d.device;
+    mine.nyl = s->nyl;
+    mine.arena = (unsigned long long)arena;
+    mine.flags = (unsigned long long)s->p2pLocal.p;
+    int okLocal = arena ? 1 : 0;
+    if (okLocal && (cudaIpcGetMemHandle(&mine.arenaHandle, arena) != cudaSuccess || cudaIpcGetMemHandle(&mine.flagsHandle, s->p2pLocal.p) != cudaSuccess)) {
+        cudaGetLastError();
+        okLocal = 0;
+    }
+    const int n = s->d.nranks;
+    DevBuf<char> sendb, recvb;
+    sendb.alloc(sizeof(P2PInfo));
+    recvb.alloc(sizeof(P2PInfo) * n);
+    WS_CUDA_CHECK(cudaMemcpyAsync(sendb.p, &mine, sizeof(P2PInfo), cudaMemcpyHostToDevice, s->stream));
+    g_nccl.check(g_nccl.AllGather(sendb.p, recvb.p, sizeof(P2PInfo), kNcclChar, s->ncclComm, s->stream), "ncclAllGather");
+    std::vector<P2PInfo> all(n);
+    WS_CUDA_CHECK(cudaMemcpyAsync(all.data(), recvb.p, sizeof(P2PInfo) * n, cudaMemcpyDeviceToHost, s->stream));
+    WS_CUDA_CHECK(cudaStreamSynchronize(s->stream));
+    for (int d = 0; d < 2 && okLocal; d++) {
+        const int peer = d == 0 ? s->d.rank - 1 : s->d.rank + 1;
+        if (peer < 0 || peer >= n)
+            continue;
+        const P2PInfo &pi = all[peer];
+        s->peerNyl[d] = pi.nyl;
+        if (pi.arena == 0) {
+            okLocal = 0;
+        } else if (pi.pid == mine.pid) {
+            int can = 0;
+            if (pi.device != mine.device && (cudaDeviceCanAccessPeer(&can, mine.device, pi.device) != cudaSuccess || !can)) {
+                okLocal = 0;
+                continue;
+            }
+            if (pi.device != mine.device) {
+                const cudaError_t e = cudaDeviceEnablePeerAccess(pi.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                    okLocal = 0;
+                cudaGetLastError();
+            }
+            s->peerArena[d] = reinterpret_cast<float *>(pi.arena);
+            s->peerFlags[d] = reinterpret_cast<int *>(pi.flags);
+        } else {
+            void *pa = nullptr, *pf = nullptr;
+            if (cudaIpcOpenMemHandle(&pa, pi.arenaHandle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+                cudaIpcOpenMemHandle(&pf, pi.flagsHandle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();
+                if (pa)
+                    cudaIpcCloseMemHandle(pa);
+                okLocal = 0;
+                continue;
+            }
+            s->peerArena[d] = static_cast<float *>(pa);
+            s->peerFlags[d] = static_cast<int *>(pf);
+            s->peerIpc[d] = true;
+        }
+    }
+    // all or nothing: a rank that pushes needs a neighbour that waits for counters instead of an ncclRecv
+    int bad = okLocal ? 0 : 1;
+    WS_CUDA_CHECK(cudaMemcpyAsync(s->flag.p, &bad, sizeof(int), cudaMemcpyHostToDevice, s->stream));
+    g_nccl.check(g_nccl.AllReduce(s->flag.p, s->flag.p, 1, kNcclInt, kNcclMax, s->ncclComm, s->stream), "ncclAllReduce");
+    WS_CUDA_CHECK(cudaMemcpyAsync(&bad, s->flag.p, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    WS_CUDA_CHECK(cudaStreamSynchronize(s->stream));
+    s->p2p = bad == 0;
+}
+
+// every rank has passed this point before any rank goes on (ws_reset in the peer-memory mode)
+void rankBarrier(ws_solver *s)
+{
+    const int zero = 0;
+    WS_CUDA_CHECK(cudaMemcpyAsync(s->flag.p, &zero, sizeof(int), cudaMemcpyHostToDevice, s->stream));
+    g_nccl.check(g_nccl.AllReduce(s->flag.p, s->flag.p, 1, kNcclInt, kNcclMax, s->ncclComm, s->stream), "ncclAllReduce");
+    WS_CUDA_CHECK(cudaStreamSynchronize(s->stream));
+}
+#endif
 
 void refreshParams(ws_solver *s)
 {
@@ -1242,6 +1475,13 @@ void enqueueStep(ws_solver *s, const float *srcStepDev, float *recStepDev, cudaE
         return;
     }
     const bool multi = s->d.nranks > 1;
+#ifdef WS_EMULATE
+    const bool p2p = false;
+    auto pushHalos = [](ws_solver *, const std::vector<int> &, int, cudaStream_t) {};
+    auto waitHalos = [](ws_solver *, int, cudaStream_t) {};
+#else
+    const bool p2p = s->p2p;
+#endif
     const int h = s->h, n = s->nyl;
     const cudaEvent_t evCompute = s->capturing ? s->evComputeG : s->evCompute, evComm = s->capturing ? s->evCommG : s->evComm;
     int fA[3];
@@ -1259,13 +1499,18 @@ void enqueueStep(ws_solver *s, const float *srcStepDev, float *recStepDev, cudaE
     } else {
         // interior first (needs no ghost planes), then the edge slabs once the previous exchange has landed
         launchPass(s, 0, h, n - h);
-        if (!haloLanded)
+        if (p2p)
+            waitHalos(s, 1, s->stream); // the counters tell when exchange B of the step before has landed
+        else if (!haloLanded)
             WS_CUDA_CHECK(cudaStreamWaitEvent(s->stream, evComm, 0));
         launchPass(s, 0, 0, std::min(h, n));
         launchPass(s, 0, std::max(n - h, h), n);
         WS_CUDA_CHECK(cudaEventRecord(evCompute, s->stream));
         WS_CUDA_CHECK(cudaStreamWaitEvent(s->commStream, evCompute, 0));
-        exchangeHalos(s, gather(s->exchA), h, s->commStream);
+        if (p2p)
+            pushHalos(s, s->exchA, 0, s->commStream);
+        else
+            exchangeHalos(s, gather(s->exchA), h, s->commStream);
         WS_CUDA_CHECK(cudaEventRecord(evComm, s->commStream));
     }
     if (ev) {
@@ -1276,7 +1521,10 @@ void enqueueStep(ws_solver *s, const float *srcStepDev, float *recStepDev, cudaE
         launchPass(s, 1, 0, n);
     } else {
         launchPass(s, 1, h, n - h);
-        WS_CUDA_CHECK(cudaStreamWaitEvent(s->stream, evComm, 0));
+        if (p2p)
+            waitHalos(s, 0, s->stream);
+        else
+            WS_CUDA_CHECK(cudaStreamWaitEvent(s->stream, evComm, 0));
         launchPass(s, 1, 0, std::min(h, n));
         launchPass(s, 1, std::max(n - h, h), n);
     }
@@ -1292,7 +1540,10 @@ void enqueueStep(ws_solver *s, const float *srcStepDev, float *recStepDev, cudaE
     if (multi) {
         WS_CUDA_CHECK(cudaEventRecord(evCompute, s->stream));
         WS_CUDA_CHECK(cudaStreamWaitEvent(s->commStream, evCompute, 0));
-        exchangeHalos(s, gather(s->exchB), h, s->commStream);
+        if (p2p)
+            pushHalos(s, s->exchB, 1, s->commStream);
+        else
+            exchangeHalos(s, gather(s->exchB), h, s->commStream);
         WS_CUDA_CHECK(cudaEventRecord(evComm, s->commStream));
     }
 }
@@ -1808,6 +2059,12 @@ int ws_reset(ws_solver *s)
         // the neighbour sends): the memsets below must come after it
         WS_CUDA_CHECK(cudaStreamSynchronize(s->commStream));
         WS_CUDA_CHECK(cudaStreamSynchronize(s->stream));
+#ifndef WS_EMULATE
+        // peer-memory exchange: the NEIGHBOURS write this rank's ghost planes, so every rank must have finished its last step
+        // before anybody clears (and everybody must have cleared before anybody pushes again: second barrier below)
+        if (s->p2p)
+            rankBarrier(s);
+#endif
         for (int k = 0; k < F_COUNT; k++)
             s->fld[k].zero(s->stream); // Wavefields::resetWavefields (Wavefields3Delastic.cpp:111-122)
         for (int k = 0; k < PSI_COUNT; k++)
@@ -1817,6 +2074,10 @@ int ws_reset(ws_solver *s)
         s->seis.zero(s->stream);
         s->tdev.zero(s->stream);
         WS_CUDA_CHECK(cudaStreamSynchronize(s->stream));
+#ifndef WS_EMULATE
+        if (s->p2p)
+            rankBarrier(s);
+#endif
     });
 }
 
@@ -1968,6 +2229,11 @@ int ws_sync(ws_solver *s)
         WS_CUDA_CHECK(cudaStreamSynchronize(s->stream));
         WS_CUDA_CHECK(cudaStreamSynchronize(s->commStream));
         WS_CUDA_CHECK(cudaGetLastError());
+        if (s->p2p) {
+            int err = 0;
+            WS_CUDA_CHECK(cudaMemcpy(&err, s->p2pLocal.p + P2P_ERROR, sizeof(int), cudaMemcpyDeviceToHost));
+            WS_REQUIRE(err == 0, WS_ECOMM, "halo exchange over peer memory: a neighbour did not deliver its planes within 20 s");
+        }
     });
 }
 
@@ -2393,7 +2659,17 @@ int ws_comm_init(ws_solver *s, const void *id128)
         NcclApi::UniqueId id;
         std::memcpy(&id, id128, 128);
         g_nccl.check(g_nccl.CommInitRank(&s->ncclComm, s->d.nranks, id, s->d.rank), "ncclCommInitRank");
+#ifndef WS_EMULATE
+        p2pSetup(s); // halo planes over peer memory where every neighbour can be mapped (NCCL stays for the collectives)
+#endif
     });
+}
+
+int ws_halo_transport(const ws_solver *s)
+{
+    if (!s || s->d.nranks <= 1)
+        return 0;
+    return s->p2p ? 3 : (s->extFn ? 2 : (s->ncclComm ? 1 : 0));
 }
 
 int ws_comm_init_external(ws_solver *s, ws_sendrecv_fn fn, void *user)

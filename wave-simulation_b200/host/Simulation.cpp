@@ -242,8 +242,7 @@ int main(int argc, const char *argv[])
             SCAI_ASSERT_ERROR(numshots <= wantedDomains, "more supershots than NumShotDomains")
         }
         SCAI_ASSERT_ERROR(numshots >= wantedDomains || survey.useSourceEncode != 0, "numshots = " << numshots << ", numShotDomains = " << wantedDomains)
-        if (survey.useSourceEncode == 0 && useRandomSource == 0 && wantedDomains <= nDevices)
-            SCAI_ASSERT_ERROR(numshots % wantedDomains == 0, "numshots = " << numshots << ", numShotDomains = " << wantedDomains)
+        // (Simulation.cpp:270-272 insists on numshots % NumShotDomains == 0; the block distribution below copes with a remainder)
         sources.writeShotIndsIncr(config, uniqueShotNos);
         sources.writeSourceEncode(config);
         if (survey.useStreamConfig)
