@@ -527,11 +527,13 @@ struct ws_solver {
             cudaEventDestroy(evComputeG);
         if (evCommG)
             cudaEventDestroy(evCommG);
+#ifndef WS_EMULATE
         for (int d = 0; d < 2; d++)
             if (peerIpc[d]) {
                 cudaIpcCloseMemHandle(peerArena[d]);
                 cudaIpcCloseMemHandle(peerFlags[d]);
             }
+#endif
         if (ncclComm && g_nccl.CommDestroy)
             g_nccl.CommDestroy(ncclComm);
         if (pinSrc)
