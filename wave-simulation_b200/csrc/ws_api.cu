@@ -27,6 +27,7 @@ struct WsError : public std::exception {
 };
 
 #include "ws_common.cuh"
+#include "ws_acquisition.cuh"
 #include "ws_launch.hpp"
 #include "ws_prepare.cuh"
 #include "ws_tables.hpp"
@@ -102,63 +103,6 @@ constexpr int kNcclMax = 2;   // ncclMax
 // acquisition kernels (SourceReceiverImpl.cpp:12-37, FDTD3Delastic.cpp:12-53, FDTD2Delastic.cpp, FDTDacoustic.cpp,
 // ForwardSolverEM/SourceReceiverImpl/SourceReceiverImplEM.cpp)
 // ---------------------------------------------------------------------------------------------------------------------
-struct WsAcq {
-    int nsrc, nrec, nt;
-    const int *srcType;
-    const long long *srcOff; // padded offset, -1 if the source is not on this rank
-    const float *srcSig;     // nsrc x nt
-    const float *srcStep;    // nsrc samples of the current step (ws_step_host) or null
-    const int *recType;
-    const long long *recOff;
-    float *seis;             // nrec x nt
-    float *recStep;          // nrec samples of the current step
-    int *tdev;               // device-resident time-step counter
-};
-
-__device__ __forceinline__ void wsInject(const WsParams &P, int type, long long off, float v)
-{
-    const int eq = P.eq;
-    if (eq <= WS_EQ_VISCOSH) {
-        switch (type) {
-        case WS_TYPE_P:
-            if (eq == WS_EQ_ACOUSTIC)
-                P.fld[F_P][off] = __fadd_rn(P.fld[F_P][off], v);
-            else {
-                P.fld[F_SXX][off] = __fadd_rn(P.fld[F_SXX][off], v);
-                P.fld[F_SYY][off] = __fadd_rn(P.fld[F_SYY][off], v);
-                if (P.dim == 3)
-                    P.fld[F_SZZ][off] = __fadd_rn(P.fld[F_SZZ][off], v);
-            }
-            break;
-        case WS_TYPE_VX: P.fld[F_VX][off] = __fadd_rn(P.fld[F_VX][off], v); break;
-        case WS_TYPE_VY: P.fld[F_VY][off] = __fadd_rn(P.fld[F_VY][off], v); break;
-        case WS_TYPE_VZ: P.fld[F_VZ][off] = __fadd_rn(P.fld[F_VZ][off], v); break;
-        }
-    } else {
-        const int slot = type == WS_TYPE_EZ ? F_EZ : (type == WS_TYPE_EX ? F_EX : (type == WS_TYPE_EY ? F_EY : F_HZ));
-        P.fld[slot][off] = __fadd_rn(P.fld[slot][off], v);
-    }
-}
-
-// sequential = 1: one thread applies all sources in reference order (types P,VX,VY,VZ; ascending trace) so that
-// coincident sources accumulate deterministically; sequential = 0: all (target,index) pairs are distinct -> parallel.
-__device__ __forceinline__ void wsSourcesSequential(const WsParams &P, const WsAcq &a, int t)
-{
-    for (int type = 1; type <= 4; type++)
-        for (int s = 0; s < a.nsrc; s++) {
-            if (a.srcType[s] != type || a.srcOff[s] < 0)
-                continue;
-            const float v = a.srcStep ? a.srcStep[s] : a.srcSig[(size_t)s * a.nt + t];
-            wsInject(P, type, a.srcOff[s], v);
-        }
-}
-__device__ __forceinline__ void wsSourceOne(const WsParams &P, const WsAcq &a, int t, int s)
-{
-    if (s >= a.nsrc || a.srcOff[s] < 0)
-        return;
-    const float v = a.srcStep ? a.srcStep[s] : a.srcSig[(size_t)s * a.nt + t];
-    wsInject(P, a.srcType[s], a.srcOff[s], v);
-}
 __global__ void kSources(const __grid_constant__ WsParams P, WsAcq a, int sequential)
 {
     const int t = *a.tdev;
@@ -170,39 +114,6 @@ __global__ void kSources(const __grid_constant__ WsParams P, WsAcq a, int sequen
         wsSourceOne(P, a, t, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
-__device__ __forceinline__ void wsReceiverOne(const WsParams &P, const WsAcq &a, int t, int r)
-{
-    if (r >= a.nrec || a.recOff[r] < 0)
-        return;
-    const long long off = a.recOff[r];
-    const int type = a.recType[r];
-    float v = 0.0f;
-    if (P.eq <= WS_EQ_VISCOSH) {
-        switch (type) {
-        case WS_TYPE_P:
-            if (P.eq == WS_EQ_ACOUSTIC)
-                v = __fmul_rn(P.fld[F_P][off], 1.0f);
-            else if (P.dim == 3) {
-                v = __fadd_rn(P.fld[F_SXX][off], P.fld[F_SYY][off]);
-                v = __fadd_rn(v, P.fld[F_SZZ][off]);
-                v = __fdiv_rn(v, 3.0f);
-            } else {
-                v = __fadd_rn(P.fld[F_SXX][off], P.fld[F_SYY][off]);
-                v = __fmul_rn(v, 0.5f);
-            }
-            break;
-        case WS_TYPE_VX: v = P.fld[F_VX][off]; break;
-        case WS_TYPE_VY: v = P.fld[F_VY][off]; break;
-        case WS_TYPE_VZ: v = P.fld[F_VZ][off]; break;
-        }
-    } else {
-        const int slot = type == WS_TYPE_EZ ? F_EZ : (type == WS_TYPE_EX ? F_EX : (type == WS_TYPE_EY ? F_EY : F_HZ));
-        v = P.fld[slot][off];
-    }
-    a.seis[(size_t)r * a.nt + t] = v;
-    if (a.recStep)
-        a.recStep[r] = v;
-}
 __global__ void kReceivers(const __grid_constant__ WsParams P, WsAcq a) { wsReceiverOne(P, a, *a.tdev, blockIdx.x * blockDim.x + threadIdx.x); }
 // the time index lives in device memory so that a captured CUDA graph is step-invariant
 __global__ void kAdvance(int *tdev) { *tdev = *tdev + 1; }
@@ -213,22 +124,10 @@ __global__ void kAdvance(int *tdev) { *tdev = *tdev + 1; }
 constexpr int WS_ACQ_THREADS = 512, WS_ACQ_MAX_SRC = 2048, WS_ACQ_MAX_REC = 8192;
 __global__ void __launch_bounds__(WS_ACQ_THREADS) kAcquisition(const __grid_constant__ WsParams P, WsAcq a, int sequential)
 {
-    const int t = *a.tdev;
-    if (a.nsrc > 0) {
-        if (sequential) {
-            if (threadIdx.x == 0)
-                wsSourcesSequential(P, a, t);
-        } else {
-            for (int s = threadIdx.x; s < a.nsrc; s += blockDim.x)
-                wsSourceOne(P, a, t, s);
-        }
-        __threadfence();
-    }
-    __syncthreads();
-    for (int r = threadIdx.x; r < a.nrec; r += blockDim.x)
-        wsReceiverOne(P, a, t, r);
-    if (threadIdx.x == 0)
-        *a.tdev = t + 1;
+    // programmatic dependent launch (see ws_kernels_tile2d.cuh): scheduled while the second half-step drains, waits for it here
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    wsAcquisitionBlock(P, a, sequential);
 }
 #endif
 
@@ -1358,7 +1257,17 @@ void launchAcquisition(ws_solver *s, const float *srcStepDev, float *recStepDev)
     a.recStep = recStepDev;
 #ifndef WS_EMULATE /* (the host emulation runs the threads of a block one after the other: no block barriers) */
     if (s->nsrc <= WS_ACQ_MAX_SRC && s->nrec <= WS_ACQ_MAX_REC && !(s->srcSequential && s->nsrc > 64)) {
-        WS_LAUNCH(kAcquisition, 1, WS_ACQ_THREADS, 0, s->stream, s->P, a, s->srcSequential ? 1 : 0);
+        static const bool pdl = !(getenv("WS_PDL") && atoi(getenv("WS_PDL")) == 0);
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(1);
+        cfg.blockDim = dim3(WS_ACQ_THREADS);
+        cfg.stream = s->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = (pdl && s->useTile) ? 1 : 0; // (only next to kernels that wait themselves: the 2-D tile kernels)
+        cudaLaunchKernelEx(&cfg, kAcquisition, s->P, a, s->srcSequential ? 1 : 0);
         s->launches++;
         return;
     }
@@ -2175,14 +2084,17 @@ int ws_run(ws_solver *s, int32_t t0, int32_t t1)
         static const bool multiGraph = !(getenv("WS_MULTI_GRAPH") && atoi(getenv("WS_MULTI_GRAPH")) == 0);
         const bool canGraph = !multi || (multiGraph && s->ncclComm && !s->extFn);
 #endif
-        if (!canGraph || nsteps < 4) {
+        if (!canGraph || nsteps < 4 || (getenv("WS_NO_GRAPH") && atoi(getenv("WS_NO_GRAPH")) != 0)) {
             for (int k = 0; k < nsteps; k++)
                 enqueueStep(s, nullptr, nullptr, nullptr);
             WS_CUDA_CHECK(cudaGetLastError());
             return;
         }
         // CUDA graph of G consecutive steps (the time index lives in device memory, so the graph is step-invariant)
-        const int G = 8;
+        // (steps per graph: the launch of a graph costs a few microseconds on the device, which 8 steps of a 0.25 ms 2-D step do not
+        // amortise as well as 8 steps of a 29 ms 3-D step; developer switch WS_GRAPH_STEPS)
+        static const int graphStepsEnv = getenv("WS_GRAPH_STEPS") ? atoi(getenv("WS_GRAPH_STEPS")) : 0;
+        const int G = graphStepsEnv >= 2 && graphStepsEnv <= 256 ? graphStepsEnv : 8;
         if (!s->graphExec) {
             cudaGraph_t graph;
             if (multi) // nothing of an earlier exchange may be pending when the capture forks the communication stream

@@ -23,7 +23,20 @@ template <int EQ, int Q, int PASS, int TY> void launchK(const WsParams &P, const
     if (wsOptInSmem(reinterpret_cast<const void *>(k), kTileMaxSmem) != cudaSuccess)
         return; // the error stays pending: ws_step / ws_run report it through cudaGetLastError
     const int tilesX = (P.nx + G::TX - 1) / G::TX, tilesY = (P.yhi - P.ylo + TY - 1) / TY;
-    k<<<(unsigned)tilesX * (unsigned)tilesY, G::NTHR, (size_t)prog.totalFloats * sizeof(float), st>>>(P, prog, tilesX);
+    // programmatic stream serialization: the thread blocks may be scheduled while the previous kernel of the stream drains (they wait
+    // for its completion inside, before their first fetch): takes the launch latency out of the 0.1 ms half-steps
+    static const bool pdl = !(getenv("WS_PDL") && atoi(getenv("WS_PDL")) == 0);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)tilesX * (unsigned)tilesY);
+    cfg.blockDim = dim3(G::NTHR);
+    cfg.dynamicSmemBytes = (size_t)prog.totalFloats * sizeof(float);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, k, P, prog, tilesX);
 }
 
 template <int EQ, int Q> void launchT(const WsParams &P, int pass, const wstile::TileProg &prog, cudaStream_t st)

@@ -102,6 +102,12 @@ __global__ void __launch_bounds__(Geo<Q, TY>::NTHR) kTile2D(const __grid_constan
     if (tid == 0) {
         wstma::barInit(barA, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // programmatic dependent launch (ws_kernels_tile2d.cu): the thread blocks of the NEXT kernel of the step may be scheduled
+        // while this grid drains, and this thread block may have been scheduled while the previous kernel drained: its first read
+        // of that kernel's output is the TMA fetch below, so the fetch waits for the previous grid to complete (no-ops when the
+        // kernel was launched without the attribute).  Every later access of the thread block follows the fetch's mbarrier.
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        asm volatile("griddepcontrol.wait;" ::: "memory");
         wstma::barExpectTx(barA, prog.bytes);
         const char *maps = reinterpret_cast<const char *>(P.tileMaps);
         const uint32_t smBase = wstma::smemAddr(sm);
@@ -124,9 +130,8 @@ __global__ void __launch_bounds__(Geo<Q, TY>::NTHR) kTile2D(const __grid_constan
     V q[NQ][Q + 1]; // no register queues here: never read (YSM)
     __syncthreads(); // the barrier is initialised before anybody polls it
     wstma::barWait(barA, 0);
-    if (P.marchDebug == 1) // developer switch: staging only (memory-side ceiling of the tiling)
-        return;
-    if (tileIn) {
+    if (P.marchDebug == 1) { // developer switch: staging only (memory-side ceiling of the tiling)
+    } else if (tileIn) {
         MPI t(P, x0, 0, nAct, so, op, q);
         t.setPlane(ly, i);
         t.st = st;

@@ -1,4 +1,5 @@
 #include "DeviceGroup.hpp"
+#include <algorithm>
 #include <cstring>
 
 using namespace KITGPI;
@@ -26,6 +27,7 @@ ForwardSolver::DeviceGroup::DeviceGroup(std::vector<IndexType> const &devs) : de
 
 ForwardSolver::DeviceGroup::~DeviceGroup()
 {
+    *alive = false;
     destroy();
     {
         std::lock_guard<std::mutex> lock(m);
@@ -133,6 +135,9 @@ void ForwardSolver::DeviceGroup::destroy()
         any = any || h != nullptr;
     if (!any)
         return;
+    for (auto *w : liveSets) // stored wavefield objects whose owner is still around: their memory goes with the solver
+        ws_wavefields_destroy(w);
+    liveSets.clear();
     forEach([&](IndexType r) {
         if (handles[r])
             ws_destroy(handles[r]);
@@ -173,13 +178,19 @@ ForwardSolver::DeviceGroup::FieldSet ForwardSolver::DeviceGroup::createFieldSet(
 {
     FieldSet set(size(), nullptr);
     forEach([&](IndexType r) { check(ws_wavefields_create(handles[r], &set[r])); });
+    liveSets.insert(liveSets.end(), set.begin(), set.end());
     return set;
 }
 
 void ForwardSolver::DeviceGroup::destroyFieldSet(FieldSet &set)
 {
-    for (auto *w : set)
+    for (auto *w : set) {
+        auto it = std::find(liveSets.begin(), liveSets.end(), w);
+        if (it == liveSets.end())
+            continue; // already released with the solver
+        liveSets.erase(it);
         ws_wavefields_destroy(w);
+    }
     set.clear();
 }
 

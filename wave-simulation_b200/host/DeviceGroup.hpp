@@ -10,6 +10,7 @@
 #include "../../include/wavesim.h"
 #include <condition_variable>
 #include <functional>
+#include <memory>
 #include <mutex>
 #include <thread>
 
@@ -47,6 +48,8 @@ namespace KITGPI
             //! a second set of wavefield components on the GPUs of the group (ws_wavefields, one per rank); the operators below take
             //! nullptr for the solvers' own wavefields (Wavefields/Wavefields.hpp:62-80)
             typedef std::vector<ws_wavefields *> FieldSet;
+            //! false once the group (the forward solver) is gone: a stored wavefield object that outlives its solver must not touch it
+            std::shared_ptr<bool> const &aliveToken() const { return alive; }
             FieldSet createFieldSet();
             void destroyFieldSet(FieldSet &set);
             //! op 0: dst = src, 1: dst += src, 2: dst -= src
@@ -72,6 +75,8 @@ namespace KITGPI
             IndexType pending = 0;
             bool stop = false;
             std::vector<std::string> errors;
+            std::shared_ptr<bool> alive = std::make_shared<bool>(true);
+            std::vector<ws_wavefields *> liveSets; // released with the group if their owner has not done it
         };
     }
 }

@@ -58,9 +58,10 @@ template <typename ValueType> void Wavefields::Wavefields<ValueType>::init(Wavef
 {
     SCAI_ASSERT_ERROR(like.h, "The wavefields are not bound to a forward solver yet (initForwardSolver)")
     SCAI_ASSERT_ERROR(like.equationType == equationType && like.numDimension == numDimension, "wavefield objects of different type")
-    if (stored && h)
+    if (stored && h && groupAlive && *groupAlive)
         h->destroyFieldSet(own);
     h = like.h;
+    groupAlive = h->aliveToken();
     memory = like.memory;
     all = like.all;
     own = h->createFieldSet();
@@ -69,7 +70,7 @@ template <typename ValueType> void Wavefields::Wavefields<ValueType>::init(Wavef
 
 template <typename ValueType> Wavefields::Wavefields<ValueType>::~Wavefields()
 {
-    if (stored && h)
+    if (stored && h && groupAlive && *groupAlive) // (a solver that went first has released the components itself)
         h->destroyFieldSet(own);
 }
 
@@ -78,6 +79,7 @@ namespace
     typedef KITGPI::ForwardSolver::DeviceGroup::FieldSet FieldSet;
 }
 #define WS_WF_CHECK(rhs)                                                                                                                  \
+    SCAI_ASSERT_ERROR(!stored || (groupAlive && *groupAlive), "the forward solver of this wavefield object is gone")                              \
     SCAI_ASSERT_ERROR(h && (rhs).h == h, "wavefield operators need two objects on the same forward solver (Wavefields::init(like))")
 
 template <typename ValueType> Wavefields::Wavefields<ValueType> &Wavefields::Wavefields<ValueType>::operator=(Wavefields<ValueType> &rhs)

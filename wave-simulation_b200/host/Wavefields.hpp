@@ -56,6 +56,7 @@ namespace KITGPI
             //! empty: this object IS the solver's wavefields; else its own component set per GPU of the group
             std::vector<ws_wavefields *> own;
             bool stored = false;
+            std::shared_ptr<bool> groupAlive; // a stored object may outlive the solver it was created on
         };
 
         template <typename ValueType> class Factory
