@@ -28,6 +28,24 @@ constexpr int NSTMAX = 4; // deepest stage ring of any tiled kernel
 constexpr int NGROUPS = 3;
 constexpr int UNR = WS_UNR;
 
+// Register budget of the warp-specialised kernels.  The register file is handed out per SM sub-partition (16384 registers each):
+// with 12 consumer warps + 1 producer warp one partition holds 4 warps, which caps EVERY thread at 128 registers — the consumers sit
+// at that cap (the CPML-layer variant of the stress half-step spills).  With a whole producer warpgroup (4 warps, three of them idle)
+// the warpgroups can trade registers (setmaxnreg): the producer side keeps 40, the three consumer warpgroups take 152 each
+// (384 x 152 + 128 x 40 = 63488 <= 65536).  WS_FAST_MAXNREG=0 builds the 13-warp form of round 1.
+#ifndef WS_FAST_MAXNREG
+#define WS_FAST_MAXNREG 1
+#endif
+#if WS_FAST_MAXNREG
+constexpr int WS_FAST_PRODUCER_THREADS = 128;
+__device__ __forceinline__ void wsConsumerRegs() { asm volatile("setmaxnreg.inc.sync.aligned.u32 152;" ::: "memory"); }
+__device__ __forceinline__ void wsProducerRegs() { asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory"); }
+#else
+constexpr int WS_FAST_PRODUCER_THREADS = 32;
+__device__ __forceinline__ void wsConsumerRegs() {}
+__device__ __forceinline__ void wsProducerRegs() {}
+#endif
+
 template <int Q> struct Cfg {
     static constexpr int H = Q / 2;
     static constexpr int HX = (H <= 4) ? 4 : 8; // x halo rounded to a float4

@@ -293,7 +293,7 @@ __device__ __forceinline__ void velConsumer(const WsParams &P, const float *sm, 
     }
 }
 
-template <int Q, bool CPML, bool EDGE, bool POL1 = false> __global__ void __launch_bounds__(NGROUPS *Cfg<Q>::NTG + 32, 1) kFastVel(const __grid_constant__ WsParams P)
+template <int Q, bool CPML, bool EDGE, bool POL1 = false> __global__ void __launch_bounds__(NGROUPS *Cfg<Q>::NTG + WS_FAST_PRODUCER_THREADS, 1) kFastVel(const __grid_constant__ WsParams P)
 {
     using C = Cfg<Q>;
     using S = StageV<Q>;
@@ -329,6 +329,7 @@ template <int Q, bool CPML, bool EDGE, bool POL1 = false> __global__ void __laun
 
     const int grp = tid / C::NTG;
     if (grp < NGROUPS) {
+        wsConsumerRegs();
         Thr t;
         const int tg = tid - grp * C::NTG;
         t.lx = tg % C::LXN;
@@ -345,7 +346,7 @@ template <int Q, bool CPML, bool EDGE, bool POL1 = false> __global__ void __laun
         t.oPX = t.oPZ = t.oPZ2 = 0;
         velConsumer<Q, CPML, EDGE, POL1>(P, sm, t, grp, yc0, yc1);
         traceEnd(P, 0, t.lane);
-    } else if (tid == NGROUPS * C::NTG) {
+    } else if (wsProducerRegs(), tid == NGROUPS * C::NTG) {
         // ---- producer: one elected thread streams the planes ----
         const int HZP = (P.nzp > 1) ? WS_HALO : 0;
         const int cx = WS_PADX + tx0, cz = HZP + tz0;
@@ -667,7 +668,7 @@ __device__ __forceinline__ void strConsumer(const WsParams &P, const float *sm, 
     }
 }
 
-template <int Q, bool CPML, bool EDGE, bool POL1 = false> __global__ void __launch_bounds__(NGROUPS *Cfg<Q>::NTG + 32, 1) kFastStress(const __grid_constant__ WsParams P)
+template <int Q, bool CPML, bool EDGE, bool POL1 = false> __global__ void __launch_bounds__(NGROUPS *Cfg<Q>::NTG + WS_FAST_PRODUCER_THREADS, 1) kFastStress(const __grid_constant__ WsParams P)
 {
     using C = Cfg<Q>;
     using S = StageS<Q>;
@@ -706,6 +707,7 @@ template <int Q, bool CPML, bool EDGE, bool POL1 = false> __global__ void __laun
     const int stride = S::SIZE + (XZC ? psiStageFloats(P.psiBoxX) : 0);
     const int grp = tid / C::NTG;
     if (grp < NGROUPS) {
+        wsConsumerRegs();
         Thr t;
         const int tg = tid - grp * C::NTG;
         t.lx = tg % C::LXN;
@@ -723,7 +725,7 @@ template <int Q, bool CPML, bool EDGE, bool POL1 = false> __global__ void __laun
         t.oPX = t.oPZ = t.oPZ2 = 0;
         strConsumer<Q, CPML, EDGE, POL1>(P, sm, sm + NSTS * stride, t, grp, yc0, yc1);
         traceEnd(P, 1, t.lane);
-    } else if (tid == NGROUPS * C::NTG) {
+    } else if (wsProducerRegs(), tid == NGROUPS * C::NTG) {
         const int HZP = (P.nzp > 1) ? WS_HALO : 0;
         const int cx = WS_PADX + tx0, cz = HZP + tz0;
         const int nIter = (Q - 1) + (yc1 - yc0);
@@ -807,7 +809,7 @@ template <int Q> int launchQ(const WsParams &P, int pass, cudaStream_t st)
     int launched = 0;
     const int ny = P.yhi - P.ylo;
     const bool cpml = P.damping == 2;
-    const int nt = NGROUPS * Cfg<Q>::NTG + 32;
+    const int nt = NGROUPS * Cfg<Q>::NTG + WS_FAST_PRODUCER_THREADS;
     // Tiles that touch an x / z CPML layer move up to 1.5x the bytes of an interior tile.  Launched together, the slow
     // tiles desynchronise the marches of neighbouring thread blocks, and halo rows that neighbours would share in L2
     // are fetched from HBM twice (measured: +20 % DRAM reads).  So the layer tiles (longest first) and the interior
