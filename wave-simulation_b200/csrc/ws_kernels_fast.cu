@@ -921,8 +921,11 @@ void *wsFastPrepare(WsParams &P, int nyp)
         maps[TM_PZ] = makeMapG(P.psiZArena, P.nx, W2, P.nyl, APS_COUNT, TX, TZ, 3);
     }
     // bit 0 = L2 eviction-priority hints on the TMA loads, bit 1 = layer tiles in a launch of their own.  With 64-plane chunks
-    // the hints no longer pay (36.7 Gpt/s with, 37.1 without at 1024^3), the separate launch still does (32.0 without)
-    P.fastFlags = getenv("WS_FAST_FLAGS") ? atoi(getenv("WS_FAST_FLAGS")) : 2;
+    // the hints no longer pay (36.7 Gpt/s with, 37.1 without at 1024^3).  The separate launch of the layer tiles paid as long as the
+    // consumers sat at 128 registers and the layer variant spilled (37.1 against 32.0 Gpt/s); with the producer warpgroup and the
+    // register trade (ws_fast_common.cuh) ONE launch per half-step is faster again: 40.0 against 38.8 Gpt/s
+    // (profiles/r02_northstar_notes.txt)
+    P.fastFlags = getenv("WS_FAST_FLAGS") ? atoi(getenv("WS_FAST_FLAGS")) : 0;
     // tile list: layer tiles first (z layers and corners, then x layers: longest first; neighbours adjacent), then interior
     const int ntx = (P.nx + TX - 1) / TX, ntz = (P.nz + TZ - 1) / TZ;
     std::vector<int> tilesCorner, tilesZ, tilesX, tilesIn;
