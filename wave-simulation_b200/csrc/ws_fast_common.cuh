@@ -17,16 +17,21 @@
 
 namespace {
 
-// planes per trip of the unrolled march: the y queue holds Q + UNR - 1 planes and is shifted by UNR once per trip
-// (full rotation, UNR = Q, needs no moves but its code overflows the instruction cache: measured; 1 is fastest)
-#ifndef WS_UNR
-#define WS_UNR 1
+// planes per trip of the unrolled march: the y queue holds Q + UNR - 1 planes and is shifted by UNR once per trip.  Round 1 (128
+// registers): 1 was fastest for both half-steps (full rotation, UNR = Q, needs no moves but its code overflows the instruction cache).
+// With the register trade (152 registers) the stress half-step gains from 4 planes per trip (15.44 -> 15.23 ms at 1024^3), the
+// velocity half-step still loses (11.36 -> 11.66 ms): one constant per half-step (profiles/r02_northstar_notes.txt).
+#ifndef WS_UNRV
+#define WS_UNRV 1
+#endif
+#ifndef WS_UNRS
+#define WS_UNRS 4
 #endif
 constexpr int TX = 64, TZ = 8;
 constexpr int WS_TRACE_MAX = 1 << 16; // thread blocks per half-step covered by the developer trace
 constexpr int NSTMAX = 4; // deepest stage ring of any tiled kernel
 constexpr int NGROUPS = 3;
-constexpr int UNR = WS_UNR;
+constexpr int UNRV = WS_UNRV, UNRS = WS_UNRS, UNRMAX = UNRV > UNRS ? UNRV : UNRS;
 
 // Register budget of the warp-specialised kernels.  The register file is handed out per SM sub-partition (16384 registers each):
 // with 12 consumer warps + 1 producer warp one partition holds 4 warps, which caps EVERY thread at 128 registers — the consumers sit
@@ -58,8 +63,8 @@ template <int Q> struct Cfg {
     static constexpr int N_P = TX * TZ, N_X = TXH * TZ, N_Z = TX * TZH, N_XZ = TXH * TZH;
     static_assert(NTG % 32 == 0, "consumer groups must be whole warps");
     static_assert(N_P % 32 == 0 && N_X % 32 == 0 && N_Z % 32 == 0 && N_XZ % 32 == 0, "TMA destinations must stay 128-byte aligned");
-    static constexpr int QL = Q + UNR - 1; // physical length of the y queue
-    static_assert(Q % UNR == 0 && NSTMAX % UNR == 0, "trips must tile the queue prologue and the stage ring");
+    static constexpr int QL = Q + UNRMAX - 1; // physical length of the y queue (the half-step with the shorter trips leaves the tail unused)
+    static_assert(Q % UNRV == 0 && NSTMAX % UNRV == 0 && Q % UNRS == 0 && NSTMAX % UNRS == 0, "trips must tile the queue prologue and the stage ring");
 };
 
 __device__ __forceinline__ uint32_t smemU32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }

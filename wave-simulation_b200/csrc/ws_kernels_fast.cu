@@ -150,7 +150,7 @@ __device__ __forceinline__ void velPlane(const WsParams &P, const Thr &t, const 
     }
 }
 
-// UNR consecutive planes of a trip (template recursion keeps the queue offset R a compile-time constant)
+// UNRV consecutive planes of a trip (template recursion keeps the queue offset R a compile-time constant)
 template <int Q, bool XZ, bool POL1, int R> struct VelUnroll {
     static __device__ __forceinline__ void run(const WsParams &P, const Thr &t, const CpT &cpt, const VRole &ro, F4 (&q)[Cfg<Q>::QL], const float *sm, int stage0,
                                                uint32_t parity, float *gout, float *psx, float *psz, long long sxStride, long long szStride)
@@ -171,7 +171,7 @@ template <int Q, bool XZ, bool POL1, int R> struct VelUnroll {
         VelUnroll<Q, XZ, POL1, R + 1>::run(P, t, cpt, ro, q, sm, stage0, parity, gout + P.plane, XZ ? psx + sxStride : psx, XZ ? psz + szStride : psz, sxStride, szStride);
     }
 };
-template <int Q, bool XZ, bool POL1> struct VelUnroll<Q, XZ, POL1, UNR> {
+template <int Q, bool XZ, bool POL1> struct VelUnroll<Q, XZ, POL1, UNRV> {
     static __device__ __forceinline__ void run(const WsParams &, const Thr &, const CpT &, const VRole &, F4 (&)[Cfg<Q>::QL], const float *, int, uint32_t, float *,
                                                float *, float *, long long, long long)
     {
@@ -272,8 +272,8 @@ __device__ __forceinline__ void velConsumer(const WsParams &P, const float *sm, 
     int it = 0;
     while (it < nIter) {
         const int ly0 = yc0 - (Q - 1) + it, gy0 = P.gy0 + ly0;
-        // the first Q iterations (queue prologue + first plane) are generic; afterwards aligned trips of UNR planes
-        if (it >= Q && it % UNR == 0 && it + UNR <= nIter && !needsGeneric<CPML>(P, gy0, gy0 + UNR - 1, H, true)) {
+        // the first Q iterations (queue prologue + first plane) are generic; afterwards aligned trips of UNRV planes
+        if (it >= Q && it % UNRV == 0 && it + UNRV <= nIter && !needsGeneric<CPML>(P, gy0, gy0 + UNRV - 1, H, true)) {
             float *gout = ro.out + (long long)ly0 * P.plane;
             const int stage0 = it % NSTV;
             const uint32_t parity = (it / NSTV) & 1;
@@ -284,8 +284,8 @@ __device__ __forceinline__ void velConsumer(const WsParams &P, const float *sm, 
                 VelUnroll<Q, false, POL1, 0>::run(P, t, cpt, ro, q, sm, stage0, parity, gout, nullptr, nullptr, 0, 0);
 #pragma unroll
             for (int k = 0; k < Q - 1; k++)
-                q[k] = q[k + UNR];
-            it += UNR;
+                q[k] = q[k + UNRV];
+            it += UNRV;
         } else {
             generic(it);
             it++;
@@ -539,7 +539,7 @@ template <int Q, bool XZ, bool POL1, int R> struct StrUnroll {
                                      szStride);
     }
 };
-template <int Q, bool XZ, bool POL1> struct StrUnroll<Q, XZ, POL1, UNR> {
+template <int Q, bool XZ, bool POL1> struct StrUnroll<Q, XZ, POL1, UNRS> {
     static __device__ __forceinline__ void run(const WsParams &, const Thr &, const CpT &, const SRole &, F4 (&)[Cfg<Q>::QL], const float *, float *, int, int, uint32_t,
                                                long long, float *, float *, long long, long long)
     {
@@ -647,7 +647,7 @@ __device__ __forceinline__ void strConsumer(const WsParams &P, const float *sm, 
     while (it < nIter) {
         const int ly0 = yc0 - (Q - 1) + it, gy0 = P.gy0 + ly0;
         // the first Q iterations (queue prologue + first plane, which may be the free-surface plane) are generic
-        if (it >= Q && it % UNR == 0 && it + UNR <= nIter && !needsGeneric<CPML>(P, gy0, gy0 + UNR - 1, H, false)) {
+        if (it >= Q && it % UNRS == 0 && it + UNRS <= nIter && !needsGeneric<CPML>(P, gy0, gy0 + UNRS - 1, H, false)) {
             const long long o = rowOff + (long long)ly0 * P.plane;
             const int stage0 = it % NSTS;
             const uint32_t parity = (it / NSTS) & 1;
@@ -656,11 +656,11 @@ __device__ __forceinline__ void strConsumer(const WsParams &P, const float *sm, 
                                           szStride);
             else
                 StrUnroll<Q, false, POL1, 0>::run(P, t, cpt, ro, q, sm, xch, n, stage0, parity, o, nullptr, nullptr, 0, 0);
-            n += UNR;
+            n += UNRS;
 #pragma unroll
             for (int k = 0; k < Q - 1; k++)
-                q[k] = q[k + UNR];
-            it += UNR;
+                q[k] = q[k + UNRS];
+            it += UNRS;
         } else {
             generic(it);
             it++;
