@@ -1,0 +1,16 @@
+#!/bin/bash
+mkdir -p gpurun_out; rm -f gpurun_out/r02A_*
+(WAVESIM_LIB=$PWD/gpurun_ab_tz4.so timeout 600 python -m pytest tests/test_gpu_parity.py -q -x -k "marching and tma and (viscoelastic3D or viscoemem3D)" 2>&1 | tail -3)
+timeout 300 python bench.py --workload cfg4 --steps 10 --warmup 3 --no-cpu --no-others 2>&1 | tail -1 >> gpurun_out/r02A_tz8.json
+WAVESIM_LIB=$PWD/gpurun_ab_tz4.so timeout 300 python bench.py --workload cfg4 --steps 10 --warmup 3 --no-cpu --no-others 2>&1 | tail -1 >> gpurun_out/r02A_tz4.json
+WAVESIM_LIB=$PWD/gpurun_ab_tz4.so WS_TMA_STAGES=3 timeout 300 python bench.py --workload cfg4 --steps 10 --warmup 3 --no-cpu --no-others 2>&1 | tail -1 >> gpurun_out/r02A_tz4_st3.json
+for f in gpurun_out/r02A_*.json; do python - "$f" <<'PY'
+import json,sys
+for ln in open(sys.argv[1]).read().strip().splitlines():
+    try:
+        d=json.loads(ln)
+        r=d["roofline"]; print("%-28s %.2f Gpt/s  ms/step %.3f  kernels %.3f/%.3f  frac %.3f whole %.3f finite %s" % (sys.argv[1][11:], d["value"], d["ms_per_step"], r["ms_first"], r["ms_second"], r["frac"], r["whole_step_frac"], d["config"]["finite"]))
+    except Exception as e:
+        print(sys.argv[1], "parse error", e, ln[-300:])
+PY
+done

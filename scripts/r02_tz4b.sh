@@ -1,0 +1,15 @@
+#!/bin/bash
+mkdir -p gpurun_out; rm -f gpurun_out/r02B_*
+(timeout 1200 python -m pytest tests/test_gpu_parity.py tests/test_gpu_long.py -q -x 2>&1 | tail -4) > gpurun_out/r02_tz4_tests.log 2>&1
+cat gpurun_out/r02_tz4_tests.log
+for i in 1 2; do timeout 300 python bench.py --workload cfg4 --steps 10 --warmup 3 --no-cpu --no-others 2>&1 | tail -1 >> gpurun_out/r02B_cfg4.json; done
+for f in gpurun_out/r02B_*.json; do python - "$f" <<'PY'
+import json,sys
+for ln in open(sys.argv[1]).read().strip().splitlines():
+    try:
+        d=json.loads(ln)
+        r=d["roofline"]; print("%-28s %.2f Gpt/s  ms/step %.3f  kernels %.3f/%.3f  frac %.3f whole %.3f finite %s" % (sys.argv[1][11:], d["value"], d["ms_per_step"], r["ms_first"], r["ms_second"], r["frac"], r["whole_step_frac"], d["config"]["finite"]))
+    except Exception as e:
+        print(sys.argv[1], "parse error", e, ln[-300:])
+PY
+done

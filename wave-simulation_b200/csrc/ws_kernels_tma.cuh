@@ -43,11 +43,19 @@ struct TmaProg {
 };
 
 // tile geometry; NL = x points per thread (4: 128-bit accesses; 2 / 1: more threads per staged byte)
+// rows of a 3-D tile with one x point per thread (the half-steps with ~200 B of operands per point: 3-D viscoelastic stress, 3-D viscoEM
+// E): 32 x 4.  These half-steps are bound by the instruction issue of the resident warps, and shared memory decides how many are
+// resident: 32 x 8 tiles leave 2 thread blocks (16 consumer warps) per SM, 32 x 4 tiles 5 (20).  BASELINE config 4 (768^3, L = 2): stress
+// half-step 20.66 -> 19.37 ms, 17.7 -> 18.7 Gpt/s, although a 4-row tile fetches 3 halo rows per own row of the velocities
+// (from L2; profiles/r02_tma_sweep.txt)
+#ifndef WS_TMA_TZ1
+#define WS_TMA_TZ1 4
+#endif
 template <int DIM, int Q, int NL> struct Geo {
     static constexpr int H = Q / 2;
     static constexpr int HX = H <= 4 ? 4 : 8; // x halo rounded to whole 16-byte units
     static constexpr int TX = DIM == 3 ? (NL == 4 ? 64 : 32) : 128;
-    static constexpr int TZ = DIM == 3 ? (NL == 4 ? 16 : 8) : 1;
+    static constexpr int TZ = DIM == 3 ? (NL == 4 ? 16 : WS_TMA_TZ1) : 1;
     static constexpr int NS = DIM == 3 ? 1 : 4; // strips per thread block (2-D)
     static constexpr int PB = 1;                // planes per stage
     static constexpr int HZ = DIM == 3 ? H : 0;
@@ -74,7 +82,7 @@ inline GeoRT geoOf(int dim, int q, int nl)
     g.H = q / 2;
     g.HX = g.H <= 4 ? 4 : 8;
     g.TX = dim == 3 ? (nl == 4 ? 64 : 32) : 128;
-    g.TZ = dim == 3 ? (nl == 4 ? 16 : 8) : 1;
+    g.TZ = dim == 3 ? (nl == 4 ? 16 : WS_TMA_TZ1) : 1;
     g.NS = dim == 3 ? 1 : 4;
     g.PB = 1;
     g.HZ = dim == 3 ? g.H : 0;
