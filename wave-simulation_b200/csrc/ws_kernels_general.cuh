@@ -264,6 +264,7 @@ __device__ __forceinline__ typename PT::V viscoShear(const WsParams &P, const PT
     using A = Ar<EXACT>;
     using V = typename PT::V;
     u = A::mul(u, muAvg);
+#pragma unroll 1
     for (int l = 0; l < P.L; l++) {
         V R = t.template rget<RC>(l);
         S = A::madd(P.DThalf, R, S);
@@ -356,7 +357,8 @@ __device__ __forceinline__ void passB(const WsParams &P, const PT &t)
             if (DIM == 3)
                 u = A::add(u, vzz);
             u = A::mul(u, pi);
-            for (int l = 0; l < P.L; l++) {
+        #pragma unroll 1
+    for (int l = 0; l < P.L; l++) {
                 V u2 = A::mul(P.invRelaxTime[l], u);
                 u2 = A::mul(u2, tauP);
                 V r = t.template rget<RC_XX>(l);
@@ -380,7 +382,8 @@ __device__ __forceinline__ void passB(const WsParams &P, const PT &t)
                 constexpr int RC = decltype(rc)::value;
                 V uu = A::mul(e, mu);
                 uu = A::mul(uu, 2.0f);
-                for (int l = 0; l < P.L; l++) {
+            #pragma unroll 1
+    for (int l = 0; l < P.L; l++) {
                     V u2 = A::mul(P.invRelaxTime[l], uu);
                     u2 = A::mul(u2, tauS);
                     V R = A::add(t.template rget<RC>(l), u2);
@@ -454,7 +457,8 @@ __device__ __forceinline__ void passB(const WsParams &P, const PT &t)
                 syy = A::mul(syy, 0.0f);
             } else {
                 // FreeSurface3Dviscoelastic.cpp:17-75, FreeSurface2Dviscoelastic.cpp:15-63
-                for (int l = 0; l < P.L; l++) {
+            #pragma unroll 1
+    for (int l = 0; l < P.L; l++) {
                     sxx = A::msub(P.DThalf, A::mul(1.0f, t.template rget<RC_XX>(l)), sxx);
                     if (DIM == 3)
                         szz = A::msub(P.DThalf, A::mul(1.0f, t.template rget<RC_ZZ>(l)), szz);
@@ -467,7 +471,8 @@ __device__ __forceinline__ void passB(const WsParams &P, const PT &t)
                 sxx = A::sub(sxx, tmp);
                 if (DIM == 3)
                     szz = A::sub(szz, tmp);
-                for (int l = 0; l < P.L; l++) {
+            #pragma unroll 1
+    for (int l = 0; l < P.L; l++) {
                     const V th = A::mul(t.sRH(l), hor);
                     const V tv = A::mul(t.sRV(l), vyy);
                     V R = A::sub(A::add(t.template rget<RC_XX>(l), th), tv);
@@ -513,12 +518,14 @@ __device__ __forceinline__ void passB(const WsParams &P, const PT &t)
         auto updateE = [&](auto fslot, auto axisTag, V curl) {
             constexpr int FS = decltype(fslot)::value, AXIS = decltype(axisTag)::value;
             V e = t.template fld<FS>();
-            for (int l = 0; l < P.L; l++) {
+        #pragma unroll 1
+    for (int l = 0; l < P.L; l++) {
                 const V a = A::mul(P.Cc[l], t.template rget<AXIS>(l));
                 const V b = A::mul(t.template cd<AXIS>(l), e);
                 t.template rput<AXIS>(l, A::add(b, a));
             }
-            for (int l = 0; l < P.L; l++)
+        #pragma unroll 1
+    for (int l = 0; l < P.L; l++)
                 curl = A::msub(P.DT, t.template rget<AXIS>(l), curl);
             curl = A::mul(curl, t.template mat<M_CBX + AXIS>());
             const V ca = A::mul(t.template mat<M_CAX + AXIS>(), e);
