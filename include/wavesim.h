@@ -205,7 +205,8 @@ int ws_set_timing(ws_solver *s, int enable);
 /* 1 if the tiled TMA kernels (not the general per-point kernels) serve this configuration */
 int ws_uses_fast_kernels(const ws_solver *s);
 /* which kernel family serves this configuration: 0 per-point (general), 1 marching (register queue + cp.async-staged
- * planes), 2 warp-specialised TMA kernels of the 3-D elastic case, 3 warp-specialised TMA marching kernels (all solvers) */
+ * planes), 2 warp-specialised TMA kernels of the 3-D elastic case, 3 warp-specialised TMA marching kernels (all solvers),
+ * 4 2-D tile kernels (one thread block per 128 x 8 tile, operands by TMA onto one mbarrier; all 2-D solvers) */
 int ws_kernel_path(const ws_solver *s);
 
 #ifdef __cplusplus
