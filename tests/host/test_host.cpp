@@ -126,6 +126,90 @@ int main(int argc, char **argv)
         EXPECT_THROW(Acquisition::readAllSettings(rec, dir + "/bad.txt"));
         EXPECT_THROW(Acquisition::readAllSettings(rec, dir + "/missing.txt"));
     }
+    // ---- receivers by mark matrix, supershots decoded into their shots and encoded again (Receivers.cpp:250-300, 353-576)
+    for (int commonOffset = 0; commonOffset < 2; commonOffset++) {
+        const IndexType numrecs = commonOffset ? 3 : 4, NT = 5;
+        {
+            std::ofstream c(dir + "/enc.txt");
+            c << "dimension=2D\nequationType=elastic\nNX=50\nNY=20\nNZ=1\nDH=10\nDT=0.1\nT=0.5\nseismoDT=0.1\nUseVariableGrid=0\nuseSourceEncode=2\nuseReceiversPerShot=2\n"
+                 "SeismogramFormat=1\nSourceFilename=" << dir << "/encsrc\nReceiverFilename=" << dir << "/encrec\n";
+            std::ofstream f(dir + "/encsrc.txt");
+            f << "1 5 1 0 1 1 1 5 1 0\n2 15 1 0 1 1 1 5 1 0\n3 25 1 0 1 1 1 5 1 0\n";
+            std::ofstream r(dir + "/encrec.txt");
+            r << "10 2 0 3\n20 2 0 1\n30 2 0 3\n";
+            if (!commonOffset)
+                r << "40 2 0 3\n";
+            std::ofstream m(dir + "/encrec.mark.mtx"); // coordinate format, as LAMA writes a sparse matrix
+            if (commonOffset)
+                m << "%%MatrixMarket matrix coordinate real general\n3 4 6\n1 1 1\n1 2 1\n2 1 2\n2 3 1\n3 1 3\n3 4 1\n";
+            else // shot 1: receivers 1, 2, 4;  shot 2: receiver 3;  shot 3: receivers 2 (p), 3, 4
+                m << "%%MatrixMarket matrix coordinate real general\n3 5 10\n1 1 1\n1 2 1\n1 3 1\n1 5 1\n2 1 2\n2 4 1\n3 1 3\n3 3 1\n3 4 1\n3 5 1\n";
+        }
+        Configuration::Configuration config(dir + "/enc.txt");
+        Acquisition::Coordinates<ValueType> coords(config);
+        // supershot 20001 = shots 1 and 3 (3 with negative polarity), supershot 20002 = shot 2
+        std::vector<Acquisition::sourceSettings<ValueType>> enc;
+        Acquisition::readAllSettings(enc, dir + "/encsrc.txt");
+        enc[0].sourceNo = 20001;
+        enc[1].sourceNo = 20002;
+        enc[2].sourceNo = 20001;
+        enc[2].amp = -1;
+        const std::vector<IndexType> rows = {0, 1, 2};
+        Acquisition::Receivers<ValueType> receivers;
+        receivers.init(config, coords, 20001, 3, rows, enc);
+        auto const &mark = receivers.getReceiverMarkVector();
+        auto &vy = receivers.getSeismogramHandler().getSeismogram(Acquisition::VY).getData();
+        auto &p = receivers.getSeismogramHandler().getSeismogram(Acquisition::P).getData();
+        auto const fill = [&]() {
+            for (size_t k = 0; k < vy.size(); k++)
+                vy[k] = (ValueType)(100 * (k / NT) + k % NT + 1);
+            for (size_t k = 0; k < p.size(); k++)
+                p[k] = (ValueType)(-7 - (ValueType)k);
+        };
+        fill();
+        if (commonOffset) {
+            // the union of rows 1 and 3: receivers 1 and 3 (both vy); one trace per shot
+            EXPECT(mark.size() == 4 && mark[0] == 20001 && mark[1] == 1 && mark[2] == 0 && mark[3] == 1 && vy.size() == (size_t)2 * NT && p.empty());
+            receivers.decode(config, dir + "/encseis", 20001, enc, 0);
+            auto const &dec = receivers.getSeismogramHandler().getSeismogram(Acquisition::VY).getDataDecode();
+            EXPECT(dec.size() == 2 && dec[0].size() == (size_t)NT && dec[0][0] == 1 && dec[0][4] == 5 && dec[1][0] == -101 && dec[1][4] == -105);
+            std::fill(vy.begin(), vy.end(), ValueType(9));
+            receivers.encode(config, dir + "/encseis", 20001, enc, 0);
+            EXPECT(vy[0] == 1 && vy[4] == 5 && vy[5] == 101 && vy[9] == 105);
+            continue;
+        }
+        EXPECT(mark.size() == (size_t)numrecs + 1 && mark[1] == 1 && mark[2] == 1 && mark[3] == 1 && mark[4] == 1 && vy.size() == (size_t)3 * NT && p.size() == (size_t)NT);
+        receivers.decode(config, dir + "/encseis", 20001, enc, 1); // to getDataDecode and to files
+        auto const &dec = receivers.getSeismogramHandler().getSeismogram(Acquisition::VY).getDataDecode();
+        auto const &decP = receivers.getSeismogramHandler().getSeismogram(Acquisition::P).getDataDecode();
+        // shot 1 marks 3 receivers (2 of them vy: traces 0 and 2 of the supershot), shot 3 marks 3 (vy traces 1 and 2), sign -1; a matrix keeps
+        // one row per marked receiver of ANY type (Receivers.cpp:507-512), the rows of the other types stay zero
+        EXPECT(dec.size() == 2 && dec[0].size() == (size_t)3 * NT && dec[0][0] == 1 && dec[0][NT] == 201 && dec[0][2 * NT] == 0);
+        EXPECT(dec[1].size() == (size_t)3 * NT && dec[1][0] == -101 && dec[1][NT + 4] == -205 && dec[1][2 * NT] == 0);
+        EXPECT(decP.size() == 2 && decP[0][0] == -7 && decP[0][NT] == 0 && decP[1][0] == 7);
+        std::vector<ValueType> file;
+        IndexType r = 0, c = 0;
+        IO::readMatrix(file, r, c, dir + "/encseis.shot_3.vy", 1);
+        EXPECT(r == 3 && c == NT && file == dec[1]);
+        IO::readMatrix(file, r, c, dir + "/encseis.shot_1.p", 1);
+        EXPECT(r == 3 && c == NT && file == decP[0]);
+        for (IndexType encodeType = 0; encodeType < 2; encodeType++) { // back: from getDataDecode, from the files
+            std::fill(vy.begin(), vy.end(), ValueType(9));
+            std::fill(p.begin(), p.end(), ValueType(9));
+            receivers.encode(config, dir + "/encseis", 20001, enc, encodeType);
+            // receiver 1 (trace 0) is shot 1's alone, receiver 3 (trace 1) shot 3's alone, receiver 4 (trace 2) and the p receiver are shared: twice
+            EXPECT(vy[0] == 1 && vy[NT] == 101 && vy[2 * NT + 1] == 2 * 202 && p[0] == -14);
+        }
+        receivers.writeReceiverMark(config, 20001);
+        std::vector<ValueType> mv(numrecs + 1);
+        IO::readVector(mv, dir + "/encrec.shot_20001.mark", 1);
+        EXPECT(mv == mark);
+        // a plain shot takes its own row; a shot that has no row is refused
+        receivers.init(config, coords, 2, 3, rows, {});
+        EXPECT(receivers.getNumTracesGlobal() == 1 && receivers.getReceiverMarkVector()[3] == 1);
+        EXPECT_THROW(receivers.init(config, coords, 7, 3, rows, {}));
+        EXPECT_THROW(receivers.init(config, coords, 2, 4, rows, {})); // numshots does not fit the matrix
+    }
     // ---- file formats: mtx and lmf round trips, resampling (Common.hpp:202-233)
     {
         std::vector<ValueType> m = {1, 2, 3, 4, 5, 6}, back;

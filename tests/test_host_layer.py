@@ -716,28 +716,54 @@ def with_keys(cfg, **kw):
     return cfg
 
 
+def write_mark(tmp, rows, coordinate=False):
+    """<ReceiverFilename>.mark.mtx: one row per shot of the source file, [shot number | one mark per receiver of the receiver file]
+    (Receivers.cpp:262-276); dense MatrixMarket array or, as LAMA writes a sparse matrix, coordinate format."""
+    rows = np.asarray(rows)
+    with open(os.path.join(tmp, "acq", "receiver.mark.mtx"), "w") as f:
+        if coordinate:
+            nz = [(i + 1, j + 1, rows[i, j]) for i in range(rows.shape[0]) for j in range(rows.shape[1]) if rows[i, j] != 0]
+            f.write("%%%%MatrixMarket matrix coordinate real general\n%d %d %d\n" % (rows.shape[0], rows.shape[1], len(nz)))
+            f.write("".join("%d %d %g\n" % e for e in nz))
+        else:
+            f.write("%%%%MatrixMarket matrix array real general\n%d %d\n" % rows.shape)
+            f.write("".join("%g\n" % v for v in rows.T.ravel()))
+
+
+TWO_RECEIVERS = "30 2 0 3\n70 3 0 3\n"
+MARKS = [[1, 1, 1], [2, 1, 0], [3, 0, 1], [4, 1, 1]]  # shots 1 and 4 record both receivers, shot 2 the first, shot 3 the second
+
+
 def test_driver_source_encoding(driver, tmp_path):
     """useSourceEncode: the shots fire together in NumShotDomains supershots (numbers NumShotDomains*1e4+1+k).  The equations are
-    linear, so a supershot's seismogram is the (signed) sum of the seismograms of its shots."""
+    linear, so a supershot's seismogram is the (signed) sum of the seismograms of its shots.  The reference couples the encoding to
+    useReceiversPerShot = 2 (Receivers.cpp:365): a supershot records the union of the receivers its shots mark, and is decoded into
+    per-shot seismograms (the marked receivers of the shot, polarity undone) after the time loop (Simulation.cpp:531-533)."""
     plain = str(tmp_path / "plain")
-    run(driver, setup_case(plain, sources=FOUR_SHOTS, receivers="30 2 0 3\n70 3 0 3\n", T=0.5), plain)
+    run(driver, setup_case(plain, sources=FOUR_SHOTS, receivers=TWO_RECEIVERS, T=0.5), plain)
     single = seismograms_of(plain)
     assert sorted(single) == [1, 2, 3, 4]
     for mode, groups in ((2, {20001: [1, 3], 20002: [2, 4]}), (3, {20001: [1, 2], 20002: [3, 4]})):
         tmp = str(tmp_path / ("mode%d" % mode))
-        cfg = with_keys(setup_case(tmp, sources=FOUR_SHOTS, receivers="30 2 0 3\n70 3 0 3\n", T=0.5), useSourceEncode=mode, NumShotDomains=2, seedtime=7)
+        cfg = with_keys(setup_case(tmp, sources=FOUR_SHOTS, receivers=TWO_RECEIVERS, T=0.5, rps=2), useSourceEncode=mode, NumShotDomains=2, seedtime=7)
+        write_mark(tmp, MARKS, coordinate=(mode == 3))
         run(driver, cfg, tmp)
         enc = seismograms_of(tmp)
-        assert sorted(enc) == sorted(groups)
+        assert sorted(enc) == [1, 2, 3, 4] + sorted(groups)
         for no, members in groups.items():
             assert rel_l2(enc[no], sum(single[m] for m in members)) <= 2.0e-5, (mode, no)
+            for m in members:  # the decoded shot = the traces of the supershot at the receivers the shot marks
+                assert np.array_equal(enc[m], enc[no][np.array(MARKS[m - 1][1:]) != 0]), (mode, no, m)
+            mark = read_mtx(os.path.join(tmp, "acq", "receiver.shot_%d.mark.mtx" % no)).ravel()
+            assert list(mark) == [no, 1, 1]
         lines = [ln.split() for ln in open(os.path.join(tmp, "acq", "sources.encode.txt")) if not ln.startswith("#")]
         assert {int(ln[0]): [int(x) for x in ln[1:]] for ln in lines} == groups
     # mode 1: random assignment (every supershot holds numshots / NumShotDomains shots) with random polarity; a given seed repeats
     res = []
     for rep in range(2):
         tmp = str(tmp_path / ("mode1_%d" % rep))
-        cfg = with_keys(setup_case(tmp, sources=FOUR_SHOTS, receivers="30 2 0 3\n70 3 0 3\n", T=0.5), useSourceEncode=1, NumShotDomains=2, seedtime=11)
+        cfg = with_keys(setup_case(tmp, sources=FOUR_SHOTS, receivers=TWO_RECEIVERS, T=0.5, rps=2), useSourceEncode=1, NumShotDomains=2, seedtime=11)
+        write_mark(tmp, [[k + 1, 1, 1] for k in range(4)])
         run(driver, cfg, tmp)
         enc = seismograms_of(tmp)
         lines = [ln.split() for ln in open(os.path.join(tmp, "acq", "sources.encode.txt")) if not ln.startswith("#")]
@@ -747,8 +773,44 @@ def test_driver_source_encoding(driver, tmp_path):
             basis = np.stack([single[m].ravel() for m in members], axis=1)
             coef = np.linalg.lstsq(basis, enc[no].ravel(), rcond=None)[0]
             assert np.allclose(np.abs(coef), 1.0, atol=1e-3), coef  # +-1: the random polarity
+            for m, c in zip(members, coef):  # decoding undoes the polarity of the shot
+                assert np.array_equal(enc[m], enc[no] if c > 0 else -enc[no])
         res.append((groups, {k: v.copy() for k, v in enc.items()}))
     assert res[0][0] == res[1][0] and all(np.array_equal(res[0][1][k], res[1][1][k]) for k in res[0][1])
+    # the reference's assertion: the encoding cannot be decoded without the mark matrix
+    tmp = str(tmp_path / "nomark")
+    p = run(driver, with_keys(setup_case(tmp, sources=FOUR_SHOTS, receivers=TWO_RECEIVERS, T=0.1), useSourceEncode=2, NumShotDomains=2), tmp, expect_ok=False)
+    assert p.returncode != 0 and "useReceiversPerShot != 2" in p.stdout + p.stderr
+
+
+def test_driver_receivers_by_mark_matrix(driver, tmp_path):
+    """useReceiversPerShot = 2: one receiver file and a mark matrix; every shot records the receivers its row marks (here also with the
+    shot increment: the rows of the mark matrix are those of the source file, not of the selection)."""
+    plain = str(tmp_path / "plain")
+    run(driver, setup_case(plain, sources=FOUR_SHOTS, receivers=TWO_RECEIVERS, T=0.3), plain)
+    single = seismograms_of(plain)
+    tmp = str(tmp_path / "marks")
+    write_mark_for = setup_case(tmp, sources=FOUR_SHOTS, receivers=TWO_RECEIVERS, T=0.3, rps=2)
+    write_mark(tmp, MARKS)
+    run(driver, write_mark_for, tmp)
+    got = seismograms_of(tmp)
+    assert sorted(got) == [1, 2, 3, 4]
+    for no in got:
+        assert np.array_equal(got[no], single[no][np.array(MARKS[no - 1][1:]) != 0]), no
+    assert not [f for f in os.listdir(os.path.join(tmp, "acq")) if f.endswith(".mark.mtx") and "shot_" in f]  # marks are written with the encoding only
+    tmp = str(tmp_path / "incr")  # shots 12 grid points = 600 m apart: shotIncr 1200 keeps shots 1 and 3 (rows 0 and 2)
+    cfg = with_keys(setup_case(tmp, sources=FOUR_SHOTS, receivers=TWO_RECEIVERS, T=0.3, rps=2), shotIncr=1200)
+    write_mark(tmp, MARKS, coordinate=True)
+    run(driver, cfg, tmp)
+    got = seismograms_of(tmp)
+    assert sorted(got) == [1, 3]
+    assert np.array_equal(got[3], single[3][1:2]) and np.array_equal(got[1], single[1])
+    # a mark matrix of the wrong shape is refused
+    tmp = str(tmp_path / "bad")
+    cfg = setup_case(tmp, sources=FOUR_SHOTS, receivers=TWO_RECEIVERS, T=0.1, rps=2)
+    write_mark(tmp, [r[:2] for r in MARKS])
+    p = run(driver, cfg, tmp, expect_ok=False)
+    assert p.returncode != 0 and "mark matrix" in p.stdout + p.stderr
 
 
 def test_driver_random_shots_and_shot_increment(driver, tmp_path):

@@ -843,6 +843,240 @@ void Acquisition::Receivers<ValueType>::init(Configuration::Configuration const 
     init(all, config, modelCoordinates);
 }
 
+// Receivers.cpp:219-227 + 262-276: the receivers of the whole survey (txt or SU headers) and the mark matrix `<ReceiverFilename>.mark.mtx`
+template <typename ValueType>
+void Acquisition::Receivers<ValueType>::readMarkMatrix(Configuration::Configuration const &config, std::vector<receiverSettings> &all, std::vector<ValueType> &mark, IndexType numshots) const
+{
+    all.clear();
+    if (config.getAndCatch("initReceiverFromSU", false))
+        readReceiverSettingsFromSU<ValueType>(all, config.get<std::string>("ReceiverFilename"), config.get<ValueType>("DH"));
+    else
+        readAllSettings(all, config.get<std::string>("ReceiverFilename") + ".txt");
+    std::string markName = config.get<std::string>("ReceiverFilename") + ".mark";
+    if (config.getAndCatch("useStreamConfig", false)) {
+        Configuration::Configuration configBig(config.get<std::string>("streamConfigFilename"));
+        markName = configBig.get<std::string>("ReceiverFilename") + ".mark";
+    }
+    IndexType rows = 0, cols = 0;
+    IO::readMatrix(mark, rows, cols, markName, 1);
+    SCAI_ASSERT_ERROR(rows == numshots && cols == (IndexType)all.size() + 1,
+                      "the receiver mark matrix must have numshots = " << numshots << " rows and numrecs + 1 = " << all.size() + 1 << " columns")
+}
+
+template <typename ValueType>
+void Acquisition::Receivers<ValueType>::init(Configuration::Configuration const &config, Coordinates<ValueType> const &modelCoordinates, IndexType shotNumber, IndexType numshots,
+                                             std::vector<IndexType> const &shotIndsIncr, std::vector<sourceSettings<ValueType>> const &sourceSettingsEncode)
+{
+    std::vector<receiverSettings> active;
+    getAcquisitionSettings(config, active, shotNumber, numshots, shotIndsIncr, sourceSettingsEncode);
+    init(active, config, modelCoordinates);
+}
+
+template <typename ValueType>
+void Acquisition::Receivers<ValueType>::getAcquisitionSettings(Configuration::Configuration const &config, std::vector<receiverSettings> &active, IndexType shotNumber, IndexType numshots,
+                                                               std::vector<IndexType> const &shotIndsIncr, std::vector<sourceSettings<ValueType>> const &sourceSettingsEncode)
+{
+    std::vector<receiverSettings> all;
+    std::vector<ValueType> mark;
+    readMarkMatrix(config, all, mark, numshots);
+    const IndexType numrecs = (IndexType)all.size(), cols = numrecs + 1;
+    receiverMarkVector.assign(cols, ValueType(0));
+    if (sourceSettingsEncode.empty()) { // a plain shot: its own row
+        bool found = false;
+        for (IndexType row : shotIndsIncr) {
+            SCAI_ASSERT_ERROR(row >= 0 && row < numshots, "shot index outside the mark matrix")
+            if ((IndexType)mark[(size_t)row * cols] == shotNumber) {
+                std::copy(mark.begin() + (size_t)row * cols, mark.begin() + (size_t)(row + 1) * cols, receiverMarkVector.begin());
+                found = true;
+                break;
+            }
+        }
+        SCAI_ASSERT_ERROR(found, "receiverMarkVector[0] != shotNumber")
+    } else { // a supershot: the union of the rows of its shots
+        SCAI_ASSERT_ERROR(sourceSettingsEncode.size() == shotIndsIncr.size(), "sourceSettingsEncode.size() != shotIndsIncr.size()")
+        for (size_t k = 0; k < shotIndsIncr.size(); k++)
+            if (std::abs(sourceSettingsEncode[k].sourceNo) == shotNumber)
+                for (IndexType c = 0; c < cols; c++)
+                    receiverMarkVector[c] += mark[(size_t)shotIndsIncr[k] * cols + c];
+    }
+    for (auto &v : receiverMarkVector) // UnaryOp::SIGN
+        v = v > 0 ? ValueType(1) : (v < 0 ? ValueType(-1) : ValueType(0));
+    receiverMarkVector[0] = (ValueType)shotNumber;
+    active.clear();
+    for (IndexType r = 0; r < numrecs; r++)
+        if (receiverMarkVector[r + 1] != 0)
+            active.push_back(all[r]);
+}
+
+template <typename ValueType>
+void Acquisition::Receivers<ValueType>::writeReceiverMark(Configuration::Configuration const &config, IndexType shotNumber, IndexType stage, IndexType iteration) const
+{
+    if (config.getAndCatch("useSourceEncode", 0) == 0)
+        return;
+    std::string name = config.get<std::string>("ReceiverFilename");
+    if (config.getAndCatch("useStreamConfig", false)) {
+        Configuration::Configuration configBig(config.get<std::string>("streamConfigFilename"));
+        name = configBig.get<std::string>("ReceiverFilename");
+    }
+    if (stage != 0)
+        name += ".stage_" + std::to_string(stage) + ".It_" + std::to_string(iteration);
+    IO::writeVector(receiverMarkVector, name + ".shot_" + std::to_string(shotNumber) + ".mark", 1);
+}
+
+template <typename ValueType>
+void Acquisition::Receivers<ValueType>::decode(Configuration::Configuration const &config, std::string const &filename, IndexType shotNumber,
+                                               std::vector<sourceSettings<ValueType>> const &sourceSettingsEncode, IndexType encodeType)
+{
+    encode(config, filename, shotNumber, sourceSettingsEncode, encodeType + 2); // Receivers.cpp:569-573
+}
+
+template <typename ValueType>
+void Acquisition::Receivers<ValueType>::encode(Configuration::Configuration const &config, std::string const &filename, IndexType shotNumber,
+                                               std::vector<sourceSettings<ValueType>> const &sourceSettingsEncode, IndexType encodeType)
+{
+    if (config.getAndCatch("useSourceEncode", 0) == 0)
+        return;
+    SCAI_ASSERT_ERROR(config.get<IndexType>("useReceiversPerShot") == 2, "useReceiversPerShot != 2")
+    const bool toSuper = encodeType == 0 || encodeType == 1;
+    // the shots of the source file, and the rows the shotIncr selection keeps
+    Sources<ValueType> allSources;
+    allSources.getAcquisitionSettings(config, ValueType(0));
+    std::vector<IndexType> uniqueShotNos;
+    calcuniqueShotNo(uniqueShotNos, allSources.getSourceSettings());
+    const IndexType numshots = (IndexType)uniqueShotNos.size();
+    allSources.getAcquisitionSettings(config, config.getAndCatch("shotIncr", ValueType(0)));
+    std::vector<IndexType> const shotIndsIncr = allSources.getShotIndsIncr();
+    SCAI_ASSERT_ERROR(sourceSettingsEncode.size() == shotIndsIncr.size(), "sourceSettingsEncode.size() != shotIndsIncr.size()")
+
+    std::vector<receiverSettings> all;
+    std::vector<ValueType> mark;
+    readMarkMatrix(config, all, mark, numshots);
+    const IndexType numrecs = (IndexType)all.size(), cols = numrecs + 1;
+    SCAI_ASSERT_ERROR((IndexType)receiverMarkVector.size() == cols, "the receivers of the supershot were not set up from the mark matrix")
+    std::vector<IndexType> receiverTypes; // types among the receivers of the supershot, in order of appearance
+    for (IndexType r = 0; r < numrecs; r++)
+        if (receiverMarkVector[r + 1] != 0 && std::find(receiverTypes.begin(), receiverTypes.end(), all[r].receiverType) == receiverTypes.end())
+            receiverTypes.push_back(all[r].receiverType);
+
+    const IndexType seismoFormat = config.get<IndexType>("SeismogramFormat");
+    const IndexType gradientDomain = config.getAndCatch("gradientDomain", 0);
+    Filter::Filter<ValueType> freqFilter;
+    if (gradientDomain != 0)
+        freqFilter.init(config.get<ValueType>("DT"), static_cast<IndexType>((config.get<ValueType>("T") / config.get<ValueType>("DT")) + 0.5));
+    auto const &names = this->getSeismogramHandler().getIsSeismic() ? SeismogramTypeString : SeismogramTypeStringEM;
+    auto const markOf = [&](IndexType shotRow, IndexType col) { return mark[(size_t)shotRow * cols + col]; };
+
+    for (IndexType type : receiverTypes) {
+        Seismogram<ValueType> &seismo = this->getSeismogramHandler().getSeismogram(type - 1);
+        std::vector<ValueType> &data = seismo.getData();
+        std::vector<std::vector<ValueType>> &dataDecode = seismo.getDataDecode();
+        const IndexType NT = seismo.getNumSamples();
+        IndexType countDecode = 0;
+        if (toSuper)
+            std::fill(data.begin(), data.end(), ValueType(0));
+        else {
+            dataDecode.clear();
+            for (size_t k = 0; k < shotIndsIncr.size(); k++)
+                if (std::abs(sourceSettingsEncode[k].sourceNo) == shotNumber)
+                    dataDecode.emplace_back();
+        }
+        auto const finish = [&](std::vector<ValueType> &traces, IndexType rows, sourceSettings<ValueType> const &enc) { // polarity and frequency of the shot
+            if (enc.amp < 0)
+                for (auto &v : traces)
+                    v = -v;
+            if (gradientDomain != 0) {
+                freqFilter.calc("ideal", "bp", 1, enc.fc);
+                freqFilter.apply(traces, rows, NT);
+            }
+        };
+        if (numshots == numrecs) { // common-offset data: receiver k belongs to shot k, one trace per shot
+            std::vector<ValueType> dataSingle((size_t)NT, ValueType(0));
+            IndexType countEncode = 0;
+            for (size_t k = 0; k < shotIndsIncr.size(); k++) {
+                const IndexType row = shotIndsIncr[k];
+                if (receiverMarkVector[row + 1] == 0 || all[row].receiverType != type)
+                    continue;
+                if (toSuper && std::abs(sourceSettingsEncode[k].sourceNo) != shotNumber)
+                    continue;
+                SCAI_ASSERT_ERROR((size_t)(countEncode + 1) * NT <= data.size(), "more marked shots than traces of the supershot")
+                if (toSuper) {
+                    if (encodeType == 1) { // row `row` of the gather <filename>.<type>
+                        std::vector<ValueType> gather;
+                        IndexType r = 0, c = 0;
+                        IO::readMatrix(gather, r, c, filename + "." + names[type - 1], seismoFormat);
+                        SCAI_ASSERT_ERROR(row < r && c == NT, "common-offset gather " << filename << "." << names[type - 1] << " does not fit")
+                        std::copy(gather.begin() + (size_t)row * NT, gather.begin() + (size_t)(row + 1) * NT, dataSingle.begin());
+                    } else {
+                        SCAI_ASSERT_ERROR(countDecode < (IndexType)dataDecode.size() && dataDecode[countDecode].size() == (size_t)NT, "no decoded data to encode")
+                        dataSingle = dataDecode[countDecode];
+                    }
+                    if (markOf(row, row + 1) != 0) {
+                        std::vector<ValueType> trace(dataSingle);
+                        finish(trace, 1, sourceSettingsEncode[k]);
+                        for (IndexType t = 0; t < NT; t++)
+                            data[(size_t)countEncode * NT + t] += trace[t];
+                    }
+                } else {
+                    SCAI_ASSERT_ERROR(countDecode < (IndexType)dataDecode.size(), "more marked shots than shots of the supershot")
+                    if (markOf(row, row + 1) != 0) {
+                        std::vector<ValueType> trace(data.begin() + (size_t)countEncode * NT, data.begin() + (size_t)(countEncode + 1) * NT);
+                        finish(trace, 1, sourceSettingsEncode[k]);
+                        dataSingle = trace;
+                    }
+                    dataDecode[countDecode] = dataSingle;
+                }
+                countEncode++;
+                countDecode++;
+            }
+            continue;
+        }
+        for (size_t k = 0; k < shotIndsIncr.size(); k++) { // multi-offset data
+            if (std::abs(sourceSettingsEncode[k].sourceNo) != shotNumber)
+                continue;
+            const IndexType row = shotIndsIncr[k];
+            const IndexType sourceNo = (IndexType)markOf(row, 0);
+            IndexType numrecSingle = 0; // every receiver the shot marks, whatever its type: the matrix of a type keeps that many rows
+            for (IndexType r = 0; r < numrecs; r++)
+                numrecSingle += (IndexType)markOf(row, r + 1);
+            const std::string single = filename + ".shot_" + std::to_string(sourceNo) + "." + names[type - 1];
+            std::vector<ValueType> dataSingle((size_t)numrecSingle * NT, ValueType(0));
+            IndexType count = 0, countEncode = 0;
+            if (toSuper) {
+                if (encodeType == 1) {
+                    IndexType r = 0, c = 0;
+                    IO::readMatrix(dataSingle, r, c, single, seismoFormat);
+                    SCAI_ASSERT_ERROR(r == numrecSingle && c == NT, single << " must hold " << numrecSingle << " traces of " << NT << " samples")
+                } else {
+                    SCAI_ASSERT_ERROR(countDecode < (IndexType)dataDecode.size() && dataDecode[countDecode].size() == dataSingle.size(), "no decoded data to encode")
+                    dataSingle = dataDecode[countDecode];
+                }
+                finish(dataSingle, numrecSingle, sourceSettingsEncode[k]);
+            }
+            for (IndexType r = 0; r < numrecs; r++) {
+                if (receiverMarkVector[r + 1] == 0 || all[r].receiverType != type)
+                    continue;
+                if (markOf(row, r + 1) != 0) {
+                    SCAI_ASSERT_ERROR((size_t)(countEncode + 1) * NT <= data.size() && count < numrecSingle, "mark matrix and seismogram do not fit")
+                    if (toSuper)
+                        for (IndexType t = 0; t < NT; t++)
+                            data[(size_t)countEncode * NT + t] += dataSingle[(size_t)count * NT + t];
+                    else
+                        std::copy(data.begin() + (size_t)countEncode * NT, data.begin() + (size_t)(countEncode + 1) * NT, dataSingle.begin() + (size_t)count * NT);
+                    count++;
+                }
+                countEncode++;
+            }
+            if (!toSuper) {
+                finish(dataSingle, numrecSingle, sourceSettingsEncode[k]);
+                dataDecode[countDecode] = dataSingle;
+                if (encodeType == 3)
+                    IO::writeMatrix(dataSingle, numrecSingle, NT, single, seismoFormat);
+            }
+            countDecode++;
+        }
+    }
+}
+
 template void Acquisition::readAllSettings<float>(std::vector<sourceSettings<float>> &, std::string);
 template void Acquisition::calcuniqueShotNo<float>(std::vector<IndexType> &, std::vector<sourceSettings<float>> const &);
 template void Acquisition::getuniqueShotInd<float>(IndexType &, std::vector<sourceSettings<float>> const &, IndexType);

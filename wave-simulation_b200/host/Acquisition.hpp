@@ -97,8 +97,12 @@ namespace KITGPI
             void read(IndexType seismogramFormat, std::string const &filename);
             void setSourceCoordinate(IndexType sourceCoord) { sourceCoordinate1D = sourceCoord; } // Seismogram.cpp:561
             IndexType getSourceCoordinate() const { return sourceCoordinate1D; }
+            //! the traces of the single shots a supershot was decoded into (Seismogram.hpp getDataDecode): row-major matrices, traces x NT
+            std::vector<std::vector<ValueType>> &getDataDecode() { return dataDecode; }
+            std::vector<std::vector<ValueType>> const &getDataDecode() const { return dataDecode; }
 
           private:
+            std::vector<std::vector<ValueType>> dataDecode;
             std::vector<ValueType> data;
             std::vector<IndexType> coordinates1D;
             IndexType sourceCoordinate1D = 0;
@@ -182,7 +186,31 @@ namespace KITGPI
             void init(Configuration::Configuration const &config, Coordinates<ValueType> const &modelCoordinates);                       // <ReceiverFilename>.txt
             void init(Configuration::Configuration const &config, Coordinates<ValueType> const &modelCoordinates, IndexType shotNumber); // .shot_<n>.txt
             void init(std::vector<receiverSettings> const &allSettings, Configuration::Configuration const &config, Coordinates<ValueType> const &modelCoordinates);
+            //! useReceiversPerShot = 2 (Receivers.cpp:250-300): ONE receiver file for the survey and a mark matrix `<ReceiverFilename>.mark.mtx`
+            //! of numshots rows [shot number | one mark per receiver]: a shot records the receivers its row marks; a supershot
+            //! (sourceSettingsEncode not empty) those any of its shots marks.  shotIndsIncr = the rows of the selected shots (shotIncr).
+            void init(Configuration::Configuration const &config, Coordinates<ValueType> const &modelCoordinates, IndexType shotNumber, IndexType numshots,
+                      std::vector<IndexType> const &shotIndsIncr, std::vector<sourceSettings<ValueType>> const &sourceSettingsEncode);
+            //! the receivers of the survey file the marks select for the shot / supershot (Receivers.cpp:250-300); sets the mark vector
+            void getAcquisitionSettings(Configuration::Configuration const &config, std::vector<receiverSettings> &active, IndexType shotNumber, IndexType numshots,
+                                        std::vector<IndexType> const &shotIndsIncr, std::vector<sourceSettings<ValueType>> const &sourceSettingsEncode);
+            std::vector<ValueType> const &getReceiverMarkVector() const { return receiverMarkVector; }
+            //! Receivers.cpp:353-576, the time-domain part: `decode` splits the seismograms of supershot `shotNumber` into those of its
+            //! shots (the receivers the mark matrix gives each shot, polarity of the encoding undone; with gradientDomain != 0 the
+            //! ideal band pass at the shot's frequency) and writes them as `<filename>.shot_<n>.<type>` (encodeType 1; 0 keeps them in
+            //! getDataDecode only); `encode` is the way back (encodeType 1 reads the single-shot files, 0 takes getDataDecode).
+            //! Common-offset surveys (as many shots as receivers) keep one trace per shot and write nothing, as the reference.
+            void decode(Configuration::Configuration const &config, std::string const &filename, IndexType shotNumber, std::vector<sourceSettings<ValueType>> const &sourceSettingsEncode,
+                        IndexType encodeType);
+            void encode(Configuration::Configuration const &config, std::string const &filename, IndexType shotNumber, std::vector<sourceSettings<ValueType>> const &sourceSettingsEncode,
+                        IndexType encodeType);
+            //! `<ReceiverFilename>.shot_<n>.mark.mtx`: the mark vector of the supershot (Receivers.cpp:308-328; only with useSourceEncode)
+            void writeReceiverMark(Configuration::Configuration const &config, IndexType shotNumber, IndexType stage = 0, IndexType iteration = 0) const;
             IndexType getRowOfEntry(IndexType k) const { return this->traceOfEntry[k]; }
+
+          private:
+            void readMarkMatrix(Configuration::Configuration const &config, std::vector<receiverSettings> &all, std::vector<ValueType> &mark, IndexType numshots) const;
+            std::vector<ValueType> receiverMarkVector; // [shot number | 0 / 1 per receiver of the file]
         };
     }
 }

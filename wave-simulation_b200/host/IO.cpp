@@ -67,12 +67,14 @@ namespace
         if (!in.good())
             COMMON_THROWEXCEPTION("Could not open " << filename)
         std::string line;
-        bool vectorHeader = false;
+        bool vectorHeader = false, coordinate = false;
         while (std::getline(in, line)) {
             if (line.empty() || line[0] != '%')
                 break;
             if (line.find("vector") != std::string::npos)
                 vectorHeader = true;
+            if (line.find("coordinate") != std::string::npos)
+                coordinate = true;
         }
         std::istringstream sz(line);
         numRows = numCols = 0;
@@ -81,6 +83,19 @@ namespace
             numCols = 1;
         SCAI_ASSERT_ERROR(numRows > 0 && numCols > 0, filename << ": bad MatrixMarket size line")
         rowMajor.assign((size_t)numRows * numCols, 0.0f);
+        if (coordinate) { // sparse: "rows cols nnz", then one "i j value" per entry (1-based)
+            long long nnz = 0;
+            sz >> nnz;
+            for (long long e = 0; e < nnz; e++) {
+                long long i, j;
+                double v;
+                if (!(in >> i >> j >> v))
+                    COMMON_THROWEXCEPTION(filename << " holds fewer than " << nnz << " entries")
+                SCAI_ASSERT_ERROR(i >= 1 && i <= numRows && j >= 1 && j <= numCols, filename << ": entry outside the matrix")
+                rowMajor[(size_t)(i - 1) * numCols + (j - 1)] = (float)v;
+            }
+            return;
+        }
         for (IndexType c = 0; c < numCols; c++)
             for (IndexType r = 0; r < numRows; r++) {
                 double v;

@@ -38,6 +38,8 @@ struct Survey {
     std::vector<Acquisition::coordinate3D> cutCoordinates;
     Acquisition::Coordinates<ValueType> modelCoordinatesBig;
     IndexType useSourceEncode = 0;
+    IndexType numshotsAll = 0;            // shots of the source file before the shotIncr selection (rows of the receiver mark matrix)
+    std::vector<IndexType> shotIndsIncr;  // rows of the selected shots
 };
 
 // one shot domain = one group of GPUs: the shots `shotInds` (indices into the unique shot list; block distribution of the shots or,
@@ -111,10 +113,15 @@ static void runShotDomain(Configuration::Configuration const &config, IndexType 
             if (survey.useStreamConfig) {
                 // Receivers.cpp:86-121: the receivers of the shot are given in the big model and moved into its cut-out
                 std::vector<Acquisition::receiverSettings> bigSettings, shotSettings;
-                Acquisition::readAllSettings(bigSettings, config.get<std::string>("ReceiverFilename") + ".shot_" + std::to_string(shotNumber) + ".txt");
+                if (config.get<IndexType>("useReceiversPerShot") == 2)
+                    receivers.getAcquisitionSettings(config, bigSettings, shotNumber, survey.numshotsAll, survey.shotIndsIncr, survey.sourceSettingsEncode);
+                else
+                    Acquisition::readAllSettings(bigSettings, config.get<std::string>("ReceiverFilename") + ".shot_" + std::to_string(shotNumber) + ".txt");
                 Acquisition::getSettingsPerShot<ValueType>(shotSettings, bigSettings, survey.cutCoordinates.at(shotIndPerShot), modelCoordinates, config.get<IndexType>("BoundaryWidth"));
                 receivers.init(shotSettings, config, modelCoordinates);
-            } else if (config.get<IndexType>("useReceiversPerShot") != 0)
+            } else if (config.get<IndexType>("useReceiversPerShot") == 2)
+                receivers.init(config, modelCoordinates, shotNumber, survey.numshotsAll, survey.shotIndsIncr, survey.sourceSettingsEncode);
+            else if (config.get<IndexType>("useReceiversPerShot") != 0)
                 receivers.init(config, modelCoordinates, shotNumber);
             receivers.getSeismogramHandler().resetData();
 
@@ -162,6 +169,9 @@ static void runShotDomain(Configuration::Configuration const &config, IndexType 
             receivers.getSeismogramHandler().setSourceCoordinate(sources.get1DCoordinates().size() == 1 ? sources.get1DCoordinates()[0] : 0);
             receivers.getSeismogramHandler().write(config.get<IndexType>("SeismogramFormat"), config.get<std::string>("SeismogramFilename") + ".shot_" + std::to_string(shotNumber),
                                                    &modelCoordinates);
+            // Simulation.cpp:531-533: a supershot is split into the seismograms of its shots (files <SeismogramFilename>.shot_<n>.<type>), its marks are written
+            receivers.decode(config, config.get<std::string>("SeismogramFilename"), shotNumber, survey.sourceSettingsEncode, 1);
+            receivers.writeReceiverMark(config, shotNumber);
         }
     } catch (std::exception const &e) {
         *error = e.what();
@@ -187,7 +197,7 @@ int main(int argc, const char *argv[])
         if (survey.useStreamConfig) { // Simulation.cpp:60-65: the big model the shots cut their sub-models from
             configBig.readFromFile(config.get<std::string>("streamConfigFilename"));
             survey.modelCoordinatesBig.init(configBig);
-            SCAI_ASSERT_ERROR(config.get<IndexType>("useReceiversPerShot") == 1, "useStreamConfig needs useReceiversPerShot = 1 here (Receivers.cpp:104-111; mode 2 is not available)")
+            SCAI_ASSERT_ERROR(config.get<IndexType>("useReceiversPerShot") != 0, "useStreamConfig = 1 is not possible when useReceiversPerShot = 0!") // Receivers.cpp:104-105
         }
 
         HOST_PRINT("\nWAVE-Simulation " << dimension << " " << equationType << " - LAMA-free host layer on " << ws_version() << "\n\n")
@@ -213,7 +223,15 @@ int main(int argc, const char *argv[])
         /* acquisition geometry (Simulation.cpp:233-282): shot selection (shotIncr), per-shot cut-outs (useStreamConfig), source encoding */
         IndexType seedtime = config.getAndCatch("seedtime", (IndexType)time(nullptr)); // Simulation.cpp:46 takes the clock; the key makes a run repeatable
         Acquisition::Sources<ValueType> sources;
+        {   // Receivers.cpp:128-138: the receiver mark matrix has one row per shot of the source file
+            Acquisition::Sources<ValueType> all;
+            all.getAcquisitionSettings(config, ValueType(0));
+            std::vector<IndexType> nos;
+            Acquisition::calcuniqueShotNo(nos, all.getSourceSettings());
+            survey.numshotsAll = (IndexType)nos.size();
+        }
         sources.getAcquisitionSettings(config, config.getAndCatch("shotIncr", ValueType(0)));
+        survey.shotIndsIncr = sources.getShotIndsIncr();
         std::vector<Acquisition::sourceSettings<ValueType>> sourceSettings;
         if (survey.useStreamConfig) {
             std::vector<Acquisition::sourceSettings<ValueType>> sourceSettingsBig = sources.getSourceSettings();
