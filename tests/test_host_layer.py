@@ -700,11 +700,22 @@ def test_product_driver_compensation_on_gpu(tmp_path):
 FOUR_SHOTS = "".join("%d %d 0 0 2 1 1 5.0 %.1f 0.0\n" % (k + 1, 20 + 12 * k, 5.0 + k) for k in range(4))
 
 
-def seismograms_of(tmp, comp="vy"):
+def seismograms_of(tmp, comp="vy", cop=None):
+    """Seismograms by shot number.  cop = the shot numbers of a survey whose shots have one source and record one trace each: the
+    reference gathers such traces into ONE common-offset profile `<SeismogramFilename>.<comp>` (row = shot index) and writes no
+    per-shot files (Simulation.cpp:356-361, 535-560; Seismogram.cpp:84-96)."""
     out = {}
     for f in os.listdir(os.path.join(tmp, "seismograms")):
         if f.endswith("." + comp + ".mtx"):
-            out[int(f.split("shot_")[1].split(".")[0])] = read_mtx(os.path.join(tmp, "seismograms", f))
+            if "shot_" in f:
+                out[int(f.split("shot_")[1].split(".")[0])] = read_mtx(os.path.join(tmp, "seismograms", f))
+            else:
+                assert cop is not None and f == "seismogram.%s.mtx" % comp, f
+                profile = read_mtx(os.path.join(tmp, "seismograms", f))
+                assert profile.shape[0] == len(cop)
+                out.update({no: profile[k:k + 1] for k, no in enumerate(cop)})
+    if cop is not None:
+        assert not [f for f in os.listdir(os.path.join(tmp, "seismograms")) if "shot_" in f]
     return out
 
 
@@ -800,11 +811,11 @@ def test_driver_receivers_by_mark_matrix(driver, tmp_path):
     assert not [f for f in os.listdir(os.path.join(tmp, "acq")) if f.endswith(".mark.mtx") and "shot_" in f]  # marks are written with the encoding only
     tmp = str(tmp_path / "incr")  # shots 12 grid points = 600 m apart: shotIncr 1200 keeps shots 1 and 3 (rows 0 and 2)
     cfg = with_keys(setup_case(tmp, sources=FOUR_SHOTS, receivers=TWO_RECEIVERS, T=0.3, rps=2), shotIncr=1200)
-    write_mark(tmp, MARKS, coordinate=True)
+    write_mark(tmp, [[1, 0, 1], [2, 1, 0], [3, 1, 1], [4, 1, 1]], coordinate=True)
     run(driver, cfg, tmp)
     got = seismograms_of(tmp)
     assert sorted(got) == [1, 3]
-    assert np.array_equal(got[3], single[3][1:2]) and np.array_equal(got[1], single[1])
+    assert np.array_equal(got[1], single[1][1:2]) and np.array_equal(got[3], single[3])
     # a mark matrix of the wrong shape is refused
     tmp = str(tmp_path / "bad")
     cfg = setup_case(tmp, sources=FOUR_SHOTS, receivers=TWO_RECEIVERS, T=0.1, rps=2)
@@ -814,20 +825,34 @@ def test_driver_receivers_by_mark_matrix(driver, tmp_path):
 
 
 def test_driver_random_shots_and_shot_increment(driver, tmp_path):
+    """Four shots of one source each, recorded by two receivers (a file per shot) or by one (the traces are gathered into a
+    common-offset profile, summed over the shot domains: SeismogramHandler::sumShotDomain)."""
     plain = str(tmp_path / "plain")
-    run(driver, setup_case(plain, sources=FOUR_SHOTS, T=0.3), plain)
+    run(driver, setup_case(plain, sources=FOUR_SHOTS, receivers=TWO_RECEIVERS, T=0.3), plain)
     single = seismograms_of(plain)
+    assert sorted(single) == [1, 2, 3, 4] and single[1].shape == (2, 150)
     for mode in (1, 2, 3):  # two passes of two shots each: every shot exactly once (maxcount = 1)
         tmp = str(tmp_path / ("rand%d" % mode))
-        run(driver, with_keys(setup_case(tmp, sources=FOUR_SHOTS, T=0.3), useRandomSource=mode, NumShotDomains=2, seedtime=3), tmp)
+        run(driver, with_keys(setup_case(tmp, sources=FOUR_SHOTS, receivers=TWO_RECEIVERS, T=0.3), useRandomSource=mode, NumShotDomains=2, seedtime=3), tmp)
         got = seismograms_of(tmp)
         assert sorted(got) == [1, 2, 3, 4]
         assert all(np.array_equal(got[k], single[k]) for k in got)
+    # one receiver: common-offset profile (and the profile of the source signals with writeSource), one and two shot domains
+    for domains in (1, 2):
+        tmp = str(tmp_path / ("cop%d" % domains))
+        cfg = with_keys(setup_case(tmp, sources=FOUR_SHOTS, receivers="30 2 0 3\n", T=0.3), NumShotDomains=domains, writeSource=1, writeSourceFilename="seismograms/source")
+        run(driver, cfg, tmp)
+        assert sorted(os.listdir(os.path.join(tmp, "seismograms"))) == ["seismogram.vy.mtx", "source.vx.mtx"]
+        got = seismograms_of(tmp, cop=[1, 2, 3, 4])
+        assert all(np.array_equal(got[k], single[k][0:1]) for k in got)
+        src = read_mtx(os.path.join(tmp, "seismograms", "source.vx.mtx"))
+        from wsharness import ricker
+        assert src.shape == (4, 150) and all(rel_l2(src[k], ricker(150, 2e-3, 5.0, 5.0 + k, 0.0)) <= 1e-6 for k in range(4))
     # shotIncr = 200 m on a line of shots 2 grid points (100 m) apart: every second shot (Sources.cpp:516-553)
     tmp = str(tmp_path / "incr")
     six = "".join("%d %d 0 0 2 1 1 5.0 5.0 0.0\n" % (k + 1, 20 + 2 * k) for k in range(6))
     run(driver, with_keys(setup_case(tmp, sources=six, T=0.1), shotIncr=200), tmp)
-    assert sorted(seismograms_of(tmp)) == [1, 3, 5]
+    assert sorted(seismograms_of(tmp, cop=[1, 3, 5])) == [1, 3, 5]
     lines = [ln.split() for ln in open(os.path.join(tmp, "acq", "sources.shotIncr.txt")) if not ln.startswith("#")]
     assert lines == [["1", "1"], ["3", "3"], ["5", "5"]]
 
@@ -850,7 +875,7 @@ def test_driver_stream_config_model_per_shot(driver, tmp_path):
     open(os.path.join(tmp, "acq", "receiver.shot_1.txt"), "w").write("50 12 0 3\n")
     open(os.path.join(tmp, "acq", "receiver.shot_2.txt"), "w").write("100 12 0 3\n")
     run(driver, cfg, tmp)
-    got = seismograms_of(tmp)
+    got = seismograms_of(tmp, cop=[1, 2])  # one source and one trace per shot: a common-offset profile
     assert sorted(got) == [1, 2]
     cut = [ln.split() for ln in open(os.path.join(tmp, "acq", "sources.cut.txt")) if not ln.startswith("#")]
     assert cut == [[str(nx * ny), str(nx), str(ny), "1"], ["1", "0", "0", "0"], ["2", "50", "0", "0"]]
@@ -869,6 +894,71 @@ def test_driver_stream_config_model_per_shot(driver, tmp_path):
         vp = read_mtx(os.path.join(tmp, "model", "model.shot_%d.vp.mtx" % shot)).ravel()
         assert np.array_equal(vp.astype(np.float32), case.materials["velocityP"])
     assert not np.allclose(got[1], got[2], rtol=1e-3)  # the lateral gradient makes the two cut-outs differ
+
+
+def test_driver_trace_gain_and_instantaneous_outputs(driver, tmp_path):
+    """normalizeTraces = 3 (automatic gain control, the gain function written as .inverseAGC) and 4 (envelope with a water level),
+    instantaneousTraces = 1 / 2 (a second file with the envelope / the reference's phase) against numpy restatements of
+    Seismogram.cpp:215-385 and Common.hpp:272-340."""
+    from scipy.signal import hilbert
+    raw_dir = str(tmp_path / "raw")
+    run(driver, setup_case(raw_dir, receivers=TWO_RECEIVERS, T=0.5), raw_dir)
+    raw = seismograms_of(raw_dir)[1].astype(np.float64)
+    nt = raw.shape[1]
+    unit = raw / np.linalg.norm(raw, axis=1, keepdims=True)
+
+    def envelope(x):  # zero-padded to the next power of two of nt - 1, like Common::calcEnvelope
+        n = 1 << int(np.ceil(np.log2(nt - 1)))
+        return np.abs(hilbert(np.concatenate([x, np.zeros((x.shape[0], n - nt))], axis=1), axis=1))[:, :nt]
+
+    # automatic gain control: mean square over the window [t - NAGC, t + NAGC - 1] (clipped) of the l2-normalised trace plus a water
+    # level, kept as a RUNNING fp32 sum from the end of the trace backwards (its cancellation error is part of the reference's result)
+    tmp = str(tmp_path / "agc")
+    run(driver, setup_case(tmp, receivers=TWO_RECEIVERS, T=0.5, norm=3), tmp)
+    nagc = min(int(round(1.0 / (5.0 * 2e-3))), nt // 2)
+    f32 = np.float32
+    unit32 = (raw.astype(f32) / np.sqrt((raw ** 2).sum(axis=1, keepdims=True)).astype(f32)).astype(f32)
+    gain = np.empty_like(unit32)
+    exact = np.empty_like(unit)
+    for r in range(unit32.shape[0]):
+        x2 = (unit32[r] * unit32[r]).astype(f32)
+        norm = f32(np.sqrt((unit32[r].astype(np.float64) ** 2).sum()))
+        level = f32(f32(f32(norm * norm) / f32(nt)) * f32(1e-3))
+        total, nwin = f32(0), f32(nagc)
+        for t in range(nt - nagc, nt):
+            total = f32(f32(total + x2[t]) + level)
+        for t in range(nt - 1, -1, -1):
+            if t >= nt - nagc:
+                total = f32(f32(total + x2[t - nagc]) + level)
+                nwin += f32(1)
+            elif t >= nagc:
+                total = f32(f32(total + x2[t - nagc]) - x2[t + nagc])
+            else:
+                total = f32(f32(total - x2[t + nagc]) - level)
+                nwin -= f32(1)
+            mean = f32(total / nwin)
+            gain[r, t] = f32(1) / np.sqrt(mean) if mean > 0 else 0
+            w = unit[r, max(0, t - nagc):min(nt, t + nagc)]
+            exact[r, t] = 1.0 / np.sqrt((w ** 2).mean() + 1e-3 * (unit[r] ** 2).sum() / nt)
+    assert rel_l2(gain, exact) <= 2.0e-2  # the window formula the running sum stands for
+    got_gain = read_mtx(os.path.join(tmp, "seismograms", "seismogram.shot_1.vy.inverseAGC.mtx"))
+    assert rel_l2(got_gain, gain) <= 1.0e-4
+    assert rel_l2(seismograms_of(tmp)[1], unit32 * gain) <= 1.0e-4
+    # envelope normalisation, and the envelope of the written traces as a second file
+    tmp = str(tmp_path / "env")
+    run(driver, with_keys(setup_case(tmp, receivers=TWO_RECEIVERS, T=0.5, norm=4), instantaneousTraces=1), tmp)
+    env = envelope(unit)
+    want = unit / (env + 1e-3 * env.max(axis=1, keepdims=True))
+    got = read_mtx(os.path.join(tmp, "seismograms", "seismogram.shot_1.vy.mtx"))
+    assert rel_l2(got, want) <= 1.0e-4
+    got_env = read_mtx(os.path.join(tmp, "seismograms", "seismogram.shot_1.vy.envelope.mtx"))
+    assert rel_l2(got_env, envelope(got)) <= 1.0e-4
+    # instantaneousTraces = 2: atan2(-x, x), the reference leaves the Hilbert transform out (Common.hpp:299-302)
+    tmp = str(tmp_path / "phase")
+    run(driver, with_keys(setup_case(tmp, receivers=TWO_RECEIVERS, T=0.5), instantaneousTraces=2), tmp)
+    got = read_mtx(os.path.join(tmp, "seismograms", "seismogram.shot_1.vy.mtx"))
+    phase = read_mtx(os.path.join(tmp, "seismograms", "seismogram.shot_1.vy.instantaneousPhase.mtx"))
+    assert np.allclose(phase, np.arctan2(-got, got), atol=1e-5)
 
 
 # frequency filters and Hilbert transform (Filter/Filter.cpp, Common/HilbertFFT.cpp)

@@ -283,7 +283,6 @@ template <typename ValueType> void Acquisition::Seismogram<ValueType>::normalize
 {
     if (data.empty() || normalizeTraces <= 0)
         return;
-    SCAI_ASSERT_ERROR(normalizeTraces <= 2, "normalizeTraces = 3 (AGC) and 4 (envelope) belong to the inversion workflow and are not available here")
     for (IndexType i = 0; i < getNumTraces(); i++) {
         ValueType *row = &data[(size_t)i * numSamples];
         ValueType norm = 0;
@@ -301,6 +300,126 @@ template <typename ValueType> void Acquisition::Seismogram<ValueType>::normalize
         for (IndexType k = 0; k < numSamples; k++)
             row[k] /= norm;
     }
+    if (normalizeTraces == 3 && useAGC) { // Seismogram.cpp:235-237
+        SCAI_ASSERT_ERROR(inverseAGC.size() == data.size(), "calcInverseAGC first")
+        for (size_t k = 0; k < data.size(); k++)
+            data[k] *= inverseAGC[k];
+        useAGC = false;
+    } else if (normalizeTraces == 4) { // Seismogram.cpp:238-258
+        std::vector<ValueType> envelope(data);
+        Common::calcEnvelope(envelope, getNumTraces(), numSamples);
+        const ValueType waterLevel = 1e-3;
+        for (IndexType i = 0; i < getNumTraces(); i++) {
+            ValueType *row = &data[(size_t)i * numSamples], *env = &envelope[(size_t)i * numSamples];
+            ValueType envMax = 0;
+            for (IndexType k = 0; k < numSamples; k++)
+                envMax = std::max(envMax, std::abs(env[k]));
+            const ValueType level = envMax != 0 ? waterLevel * envMax : waterLevel * waterLevel;
+            for (IndexType k = 0; k < numSamples; k++)
+                row[k] /= env[k] + level;
+        }
+    }
+}
+
+namespace
+{
+    // the window walk both AGC functions share (Seismogram.cpp:283-313, 341-381): `term(t)` is what sample t adds to the running sum
+    template <typename ValueType, typename Term, typename Result>
+    void agcWalk(IndexType NT, IndexType NAGC, ValueType waterLevel, Term term, Result result)
+    {
+        ValueType sumTemp = 0, NWIN = (ValueType)NAGC;
+        for (IndexType t = NT - NAGC; t < NT; t++) {
+            sumTemp += term(t);
+            sumTemp += waterLevel;
+        }
+        for (IndexType t = NT - 1; t >= 0; t--) {
+            if (t >= NT - NAGC) { // ramping on
+                sumTemp += term(t - NAGC);
+                sumTemp += waterLevel;
+                NWIN += 1;
+            } else if (t >= NAGC && t < NT - NAGC) { // full window
+                sumTemp += term(t - NAGC);
+                sumTemp -= term(t + NAGC);
+            } else if (t < NAGC) { // ramping off
+                sumTemp -= term(t + NAGC);
+                sumTemp -= waterLevel;
+                NWIN -= 1;
+            }
+            result(t, sumTemp / NWIN);
+        }
+    }
+}
+
+template <typename ValueType> std::vector<ValueType> Acquisition::Seismogram<ValueType>::getAGCSum()
+{
+    std::vector<ValueType> AGCSum;
+    if (data.empty())
+        return AGCSum;
+    std::vector<ValueType> const original(data);
+    normalizeTrace(2);
+    std::vector<ValueType> const dataNorm(data);
+    data = original;
+    AGCSum.assign(data.size(), ValueType(0));
+    const IndexType NT = numSamples;
+    IndexType NAGC = (IndexType)std::round(1.0 / (frequencyAGC * DT));
+    NAGC = std::min(NAGC, NT / 2);
+    for (IndexType i = 0; i < getNumTraces(); i++) {
+        ValueType const *row = &dataNorm[(size_t)i * NT];
+        ValueType *out = &AGCSum[(size_t)i * NT];
+        agcWalk<ValueType>(NT, NAGC, ValueType(0), [&](IndexType t) { return row[t]; }, [&](IndexType t, ValueType mean) { out[t] = mean; });
+    }
+    return AGCSum;
+}
+
+template <typename ValueType> void Acquisition::Seismogram<ValueType>::calcInverseAGC()
+{
+    if (data.empty())
+        return;
+    useAGC = true;
+    std::vector<ValueType> const original(data);
+    normalizeTrace(2);
+    std::vector<ValueType> const dataNorm(data);
+    data = original;
+    inverseAGC.assign(data.size(), ValueType(0));
+    const IndexType NT = numSamples;
+    IndexType NAGC = (IndexType)std::round(1.0 / (frequencyAGC * DT));
+    NAGC = std::min(NAGC, NT / 2);
+    double all = 0;
+    for (ValueType v : dataNorm)
+        all += (double)v * v;
+    for (IndexType i = 0; i < getNumTraces(); i++) {
+        ValueType const *row = &dataNorm[(size_t)i * NT];
+        ValueType *out = &inverseAGC[(size_t)i * NT];
+        double s = 0;
+        for (IndexType t = 0; t < NT; t++)
+            s += (double)row[t] * row[t];
+        ValueType waterLevel = (ValueType)std::sqrt(s);
+        waterLevel *= waterLevel;
+        waterLevel /= NT;
+        if (waterLevel != 0)
+            waterLevel *= ValueType(1e-3);
+        else
+            waterLevel = ValueType(1e-3) * (ValueType)std::sqrt(all) / NT / getNumTraces();
+        agcWalk<ValueType>(NT, NAGC, waterLevel, [&](IndexType t) { return row[t] * row[t]; },
+                           [&](IndexType t, ValueType meanSquare) { out[t] = meanSquare > 0 ? 1 / std::sqrt(meanSquare) : ValueType(0); });
+    }
+}
+
+template <typename ValueType> void Acquisition::Seismogram<ValueType>::allocateCOP(IndexType numshots, IndexType NT)
+{
+    numshotsCOP = numshots;
+    dataCOP.assign((size_t)numshots * NT, ValueType(0));
+    inverseAGCCOP.assign((size_t)numshots * NT, ValueType(0));
+}
+
+template <typename ValueType> void Acquisition::Seismogram<ValueType>::assignCOP()
+{
+    SCAI_ASSERT_ERROR(numSamples > 0 && dataCOP.size() == (size_t)numshotsCOP * numSamples, "no common-offset profile of " << numSamples << " samples per trace")
+    data = dataCOP;
+    inverseAGC = inverseAGCCOP;
+    coordinates1D.resize(numshotsCOP, coordinates1D.empty() ? 0 : coordinates1D[0]); // one trace per shot (SU headers: the geometry of the last shot)
+    std::fill(dataCOP.begin(), dataCOP.end(), ValueType(0));
+    std::fill(inverseAGCCOP.begin(), inverseAGCCOP.end(), ValueType(0));
 }
 
 template <typename ValueType> bool Acquisition::Seismogram<ValueType>::isFinite() const
@@ -312,22 +431,49 @@ template <typename ValueType> bool Acquisition::Seismogram<ValueType>::isFinite(
 }
 
 template <typename ValueType>
-void Acquisition::Seismogram<ValueType>::write(IndexType seismogramFormat, std::string const &filename, Coordinates<ValueType> const *modelCoordinates) const
+void Acquisition::Seismogram<ValueType>::write(IndexType seismogramFormat, std::string const &filename, Coordinates<ValueType> const *modelCoordinates)
 {
     if (data.empty())
         return;
-    SCAI_ASSERT_ERROR(seismogramFormat == 1 || seismogramFormat == 2 || seismogramFormat == 4,
-                      "SeismogramFormat " << seismogramFormat << " (3 = frv, 5 = inverse AGC of the inversion workflow) is not available in the B200 host layer")
-    const std::string name = filename + "." + (isSeismic ? SeismogramTypeString[type] : SeismogramTypeStringEM[type]);
-    std::vector<ValueType> out(data);
+    if (getNumTraces() == 1 && numshotsCOP > 1) { // Seismogram.cpp:84-96: the trace of this shot joins the common-offset profile
+        SCAI_ASSERT_ERROR(shotInd >= 0 && shotInd < numshotsCOP && dataCOP.size() == (size_t)numshotsCOP * numSamples, "common-offset profile: shot index " << shotInd)
+        std::vector<ValueType> const &from = seismogramFormat != 5 ? data : inverseAGC;
+        std::vector<ValueType> &to = seismogramFormat != 5 ? dataCOP : inverseAGCCOP;
+        SCAI_ASSERT_ERROR(from.size() == (size_t)numSamples, "no inverse AGC function to write")
+        std::copy(from.begin(), from.end(), to.begin() + (size_t)shotInd * numSamples);
+        return;
+    }
+    SCAI_ASSERT_ERROR(seismogramFormat == 1 || seismogramFormat == 2 || seismogramFormat == 4 || seismogramFormat == 5,
+                      "SeismogramFormat " << seismogramFormat << " (3 = frv) is not available in the B200 host layer")
+    std::string name = filename + "." + (isSeismic ? SeismogramTypeString[type] : SeismogramTypeStringEM[type]);
+    IndexType seismoFormat = seismogramFormat;
+    std::vector<ValueType> out(seismogramFormat != 5 ? data : inverseAGC);
+    if (seismogramFormat == 5) { // Seismogram.cpp:112-116
+        SCAI_ASSERT_ERROR(out.size() == data.size(), "no inverse AGC function to write")
+        seismoFormat = 1;
+        name += ".inverseAGC";
+    }
     IndexType ns = numSamples;
     if (outputDT > 0 && DT > 0)
         Common::resampleRows(out, getNumTraces(), numSamples, outputDT / DT, ns); // Seismogram.cpp:610-618 setSeismoDT
-    if (seismogramFormat == 4) { // Seismogram.cpp:119-121
-        SCAI_ASSERT_ERROR(modelCoordinates, "SeismogramFormat 4 (SU) needs the model coordinates for the trace headers")
-        SUIO::writeSU(name, out, getNumTraces(), ns, coordinates1D, outputDT > 0 ? outputDT : DT, sourceCoordinate1D, *modelCoordinates);
-    } else
-        IO::writeMatrix(out, getNumTraces(), ns, name, seismogramFormat);
+    auto const put = [&](std::string const &file) {
+        if (seismoFormat == 4) { // Seismogram.cpp:119-121
+            SCAI_ASSERT_ERROR(modelCoordinates, "SeismogramFormat 4 (SU) needs the model coordinates for the trace headers")
+            SUIO::writeSU(file, out, getNumTraces(), ns, coordinates1D, outputDT > 0 ? outputDT : DT, sourceCoordinate1D, *modelCoordinates);
+        } else
+            IO::writeMatrix(out, getNumTraces(), ns, file, seismoFormat);
+    };
+    put(name);
+    if (outputInstantaneous != 0 && seismogramFormat != 5) { // Seismogram.cpp:127-145: a second file with the instantaneous property
+        if (outputInstantaneous == 1) {
+            Common::calcEnvelope(out, getNumTraces(), ns);
+            name += ".envelope";
+        } else if (outputInstantaneous == 2) {
+            Common::calcInstantaneousPhase(out, getNumTraces(), ns, 2);
+            name += ".instantaneousPhase";
+        }
+        put(name);
+    }
 }
 
 template <typename ValueType> void Acquisition::Seismogram<ValueType>::read(IndexType seismogramFormat, std::string const &filename)
@@ -368,6 +514,51 @@ template <typename ValueType> void Acquisition::SeismogramHandler<ValueType>::no
     for (auto &s : seismo)
         s.normalizeTrace(normalizeTraces);
 }
+template <typename ValueType> void Acquisition::SeismogramHandler<ValueType>::setFrequencyAGC(ValueType f)
+{
+    for (auto &s : seismo)
+        s.setFrequencyAGC(f);
+}
+template <typename ValueType> void Acquisition::SeismogramHandler<ValueType>::calcInverseAGC()
+{
+    for (auto &s : seismo)
+        s.calcInverseAGC();
+}
+template <typename ValueType> void Acquisition::SeismogramHandler<ValueType>::setInstantaneousTrace(IndexType instantaneousTraces)
+{
+    for (auto &s : seismo)
+        s.setInstantaneousTrace(instantaneousTraces);
+}
+template <typename ValueType> void Acquisition::SeismogramHandler<ValueType>::allocateCOP(IndexType numshots, IndexType NT)
+{
+    for (auto &s : seismo)
+        s.allocateCOP(numshots, NT);
+}
+template <typename ValueType> void Acquisition::SeismogramHandler<ValueType>::setShotInd(IndexType shotIndTrue, IndexType shotIndIncr)
+{
+    for (auto &s : seismo)
+        s.setShotInd(shotIndTrue, shotIndIncr);
+}
+template <typename ValueType> void Acquisition::SeismogramHandler<ValueType>::sumShotDomain(SeismogramHandler<ValueType> &other)
+{
+    for (IndexType t = 0; t < NUM_ELEMENTS_SEISMOGRAMTYPE; t++) {
+        auto &a = seismo[t].getDataCOP(), &b = other.seismo[t].getDataCOP();
+        auto &c = seismo[t].getInverseAGCCOP(), &d = other.seismo[t].getInverseAGCCOP();
+        SCAI_ASSERT_ERROR(a.size() == b.size() && c.size() == d.size(), "common-offset profiles of the shot domains differ in size")
+        for (size_t k = 0; k < a.size(); k++)
+            a[k] += b[k];
+        for (size_t k = 0; k < c.size(); k++)
+            c[k] += d[k];
+    }
+}
+template <typename ValueType> void Acquisition::SeismogramHandler<ValueType>::assignCOP()
+{
+    for (auto &s : seismo)
+        if (s.getNumTraces() > 0) {
+            s.assignCOP();
+            break;
+        }
+}
 template <typename ValueType> bool Acquisition::SeismogramHandler<ValueType>::isFinite() const
 {
     for (auto const &s : seismo)
@@ -376,9 +567,9 @@ template <typename ValueType> bool Acquisition::SeismogramHandler<ValueType>::is
     return true;
 }
 template <typename ValueType>
-void Acquisition::SeismogramHandler<ValueType>::write(IndexType seismogramFormat, std::string const &filename, Coordinates<ValueType> const *modelCoordinates) const
+void Acquisition::SeismogramHandler<ValueType>::write(IndexType seismogramFormat, std::string const &filename, Coordinates<ValueType> const *modelCoordinates)
 {
-    for (auto const &s : seismo)
+    for (auto &s : seismo)
         s.write(seismogramFormat, filename, modelCoordinates);
 }
 template <typename ValueType> void Acquisition::SeismogramHandler<ValueType>::setSourceCoordinate(IndexType sourceCoord)
@@ -794,6 +985,7 @@ void Acquisition::Receivers<ValueType>::init(std::vector<receiverSettings> const
     this->setAcquisition(allSettings, modelCoordinates, NT);
     this->seismograms.setDT(config.get<ValueType>("DT"));
     this->seismograms.setSeismoDT(config.get<ValueType>("seismoDT"));
+    this->seismograms.setInstantaneousTrace(config.getAndCatch("instantaneousTraces", 0)); // Receivers.cpp:31
 }
 
 // receiver geometry from the trace headers of <filename>.<component>.su (suHandler.cpp:33-52,88-107): grid coordinates

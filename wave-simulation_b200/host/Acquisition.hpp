@@ -89,11 +89,29 @@ namespace KITGPI
             void setSeismoDT(ValueType dt) { outputDT = dt; }
             void setTraceType(IndexType t, bool seismic) { type = t; isSeismic = seismic; }
             IndexType getTraceType() const { return type; }
+            //! 1 maximum, 2 l2 norm, 3 l2 norm and automatic gain control (after calcInverseAGC), 4 l2 norm and envelope with a water
+            //! level (Seismogram.cpp:215-260)
             void normalizeTrace(IndexType normalizeTraces);
+            //! automatic gain control (Seismogram.cpp:262-385): running mean of the l2-normalised trace / inverse running rms over a window of
+            //! 1 / (frequencyAGC DT) samples each side, evaluated from the end of the trace backwards
+            void setFrequencyAGC(ValueType f) { frequencyAGC = f; }
+            std::vector<ValueType> getAGCSum();
+            void calcInverseAGC();
+            std::vector<ValueType> &getInverseAGC() { return inverseAGC; }
+            void setInstantaneousTrace(IndexType instantaneousTraces) { outputInstantaneous = instantaneousTraces; } // Seismogram.cpp write: 1 envelope, 2 phase
+            //! common-offset profile: a survey of single-trace shots is gathered into ONE matrix, row = shot index, written once at the
+            //! end instead of a file per shot (Seismogram.cpp:84-96, SeismogramHandler.cpp:489-516, Simulation.cpp:356-361, 535-560)
+            std::vector<ValueType> &getDataCOP() { return dataCOP; }
+            std::vector<ValueType> &getInverseAGCCOP() { return inverseAGCCOP; }
+            void allocateCOP(IndexType numshots, IndexType NT);
+            void setShotInd(IndexType shotIndTrue, IndexType shotIndIncr_) { shotInd = shotIndTrue; shotIndIncr = shotIndIncr_; }
+            IndexType getNumShotsCOP() const { return numshotsCOP; }
+            void assignCOP(); // data = dataCOP (numshots traces), dataCOP = 0
             void filterTraces(Filter::Filter<ValueType> const &freqFilter); // Seismogram.cpp:509-520
             bool isFinite() const;
             //! SeismogramFormat 1 = mtx, 2 = lmf, 4 = SU (needs the model coordinates for the trace headers, Seismogram.cpp:82-147)
-            void write(IndexType seismogramFormat, std::string const &filename, Coordinates<ValueType> const *modelCoordinates = nullptr) const;
+            //! 5 = the inverse AGC function as `<filename>.<type>.inverseAGC.mtx`.  A single trace goes into the common-offset profile when one is allocated.
+            void write(IndexType seismogramFormat, std::string const &filename, Coordinates<ValueType> const *modelCoordinates = nullptr);
             void read(IndexType seismogramFormat, std::string const &filename);
             void setSourceCoordinate(IndexType sourceCoord) { sourceCoordinate1D = sourceCoord; } // Seismogram.cpp:561
             IndexType getSourceCoordinate() const { return sourceCoordinate1D; }
@@ -103,6 +121,10 @@ namespace KITGPI
 
           private:
             std::vector<std::vector<ValueType>> dataDecode;
+            std::vector<ValueType> inverseAGC, dataCOP, inverseAGCCOP;
+            ValueType frequencyAGC = 0;
+            bool useAGC = false;
+            IndexType outputInstantaneous = 0, shotInd = 0, shotIndIncr = 0, numshotsCOP = 0;
             std::vector<ValueType> data;
             std::vector<IndexType> coordinates1D;
             IndexType sourceCoordinate1D = 0;
@@ -124,9 +146,17 @@ namespace KITGPI
             void setSeismoDT(ValueType dt);
             void resetData();
             void normalize(IndexType normalizeTraces);
+            void setFrequencyAGC(ValueType f);
+            void calcInverseAGC();
+            void setInstantaneousTrace(IndexType instantaneousTraces);
+            void allocateCOP(IndexType numshots, IndexType NT);
+            void setShotInd(IndexType shotIndTrue, IndexType shotIndIncr);
+            //! adds the common-offset profiles another shot domain has gathered (SeismogramHandler.cpp:479-487: the reduction over commInterShot)
+            void sumShotDomain(SeismogramHandler<ValueType> &other);
+            void assignCOP(); // first type that has traces (SeismogramHandler.cpp:505-516)
             void filter(Filter::Filter<ValueType> const &freqFilter); // SeismogramHandler.cpp:76-86
             bool isFinite() const;
-            void write(IndexType seismogramFormat, std::string const &filename, Coordinates<ValueType> const *modelCoordinates = nullptr) const;
+            void write(IndexType seismogramFormat, std::string const &filename, Coordinates<ValueType> const *modelCoordinates = nullptr);
             void setSourceCoordinate(IndexType sourceCoord); // SeismogramHandler.cpp:340
 
           private:

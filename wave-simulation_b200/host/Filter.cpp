@@ -240,6 +240,56 @@ template <typename ValueType> void Hilbert::HilbertFFT<ValueType>::hilbert(std::
     }
 }
 
+template <typename ValueType> void Common::calcEnvelope(std::vector<ValueType> &data, IndexType numRows, IndexType nt)
+{
+    SCAI_ASSERT_ERROR(data.size() == (size_t)numRows * nt, "matrix size")
+    if (data.empty())
+        return;
+    Hilbert::HilbertFFT<ValueType> hilbertHandler;
+    IndexType kernelSize = calcNextPowTwo<ValueType>(nt - 1);
+    while (kernelSize < nt) // nt = 2^k + 1
+        kernelSize *= 2;
+    hilbertHandler.setCoefficientLength(kernelSize);
+    hilbertHandler.calcHilbertCoefficient();
+    std::vector<ValueType> imag(data);
+    hilbertHandler.hilbert(imag, numRows, nt);
+    for (size_t k = 0; k < data.size(); k++)
+        data[k] = std::sqrt(data[k] * data[k] + imag[k] * imag[k]);
+}
+
+template <typename ValueType> void Common::calcInstantaneousPhase(std::vector<ValueType> &data, IndexType numRows, IndexType nt, IndexType phaseType)
+{
+    SCAI_ASSERT_ERROR(data.size() == (size_t)numRows * nt, "matrix size")
+    for (IndexType r = 0; r < numRows; r++) {
+        ValueType *re = &data[(size_t)r * nt];
+        std::vector<ValueType> im(re, re + nt);
+        for (auto &v : im)
+            v = -v;
+        if (phaseType == 1) {
+            for (IndexType t = 0; t < nt; t++)
+                re[t] = std::atan(im[t] / re[t]);
+        } else if (phaseType == 2) {
+            for (IndexType t = 0; t < nt; t++)
+                re[t] = std::atan2(im[t], re[t]);
+        } else if (phaseType == 3 && nt > 0) {
+            ValueType phase = std::atan2(im[0], re[0]);
+            re[0] = phase;
+            im[0] = phase;
+            for (IndexType t = 1; t < nt; t++) {
+                phase = std::atan2(im[t], re[t]);
+                im[t] = phase;
+                ValueType d = phase - im[t - 1];
+                d = d > M_PI ? d - 2 * M_PI : (d < -M_PI ? d + 2 * M_PI : d);
+                re[t] = re[t - 1] + d;
+            }
+        }
+    }
+}
+
+template void Common::calcEnvelope<float>(std::vector<float> &, IndexType, IndexType);
+template void Common::calcEnvelope<double>(std::vector<double> &, IndexType, IndexType);
+template void Common::calcInstantaneousPhase<float>(std::vector<float> &, IndexType, IndexType, IndexType);
+template void Common::calcInstantaneousPhase<double>(std::vector<double> &, IndexType, IndexType, IndexType);
 template IndexType Common::calcNextPowTwo<float>(IndexType);
 template IndexType Common::calcNextPowTwo<double>(IndexType);
 template class Filter::Filter<float>;

@@ -15,6 +15,11 @@ namespace KITGPI
         template <typename ValueType> IndexType calcNextPowTwo(IndexType nt);
         //! in-place radix-2 transform of a power-of-two length; inverse = conjugate kernel WITHOUT the 1/n factor (as lama::fft / ifft)
         void fft(std::vector<std::complex<double>> &a, bool inverse);
+        //! envelope sqrt(x^2 + H(x)^2) of the rows of a row-major numRows x nt matrix (Common.hpp:272-290)
+        template <typename ValueType> void calcEnvelope(std::vector<ValueType> &data, IndexType numRows, IndexType nt);
+        //! "instantaneous phase" of the rows as Common.hpp:297-340 computes it: the imaginary part is -x (the Hilbert transform is
+        //! commented out there); phaseType 1 atan(im / re), 2 atan2(im, re), 3 unwrapped
+        template <typename ValueType> void calcInstantaneousPhase(std::vector<ValueType> &data, IndexType numRows, IndexType nt, IndexType phaseType);
     }
 
     namespace Filter

@@ -40,13 +40,21 @@ struct Survey {
     IndexType useSourceEncode = 0;
     IndexType numshotsAll = 0;            // shots of the source file before the shotIncr selection (rows of the receiver mark matrix)
     std::vector<IndexType> shotIndsIncr;  // rows of the selected shots
+    // common-offset profiles (Simulation.cpp:356-361): every shot has ONE source and there are several shots -> the source signals
+    // (writeSource) and, when a shot records one trace, the seismograms are gathered into one matrix of numshots traces
+    bool copCondition = false, copSources = false, copReceivers = false;
+};
+
+// what a shot domain hands back for the reduction over the domains (sumShotDomain, Simulation.cpp:535-560)
+struct DomainResult {
+    Acquisition::SeismogramHandler<ValueType> sources, receivers;
 };
 
 // one shot domain = one group of GPUs: the shots `shotInds` (indices into the unique shot list; block distribution of the shots or,
 // with useRandomSource, one shot of every pass: dmemo::blockDistribution(..., commInterShot), Simulation.cpp:339-344, 362-369)
 static void runShotDomain(Configuration::Configuration const &config, IndexType shotDomain, std::vector<IndexType> devices, std::vector<IndexType> shotInds, Survey const &survey,
                           Modelparameter::Modelparameter<ValueType>::ModelparameterPtr model, Acquisition::Coordinates<ValueType> const &modelCoordinates, double globalStart_t,
-                          std::string *error)
+                          std::string *error, DomainResult *result)
 {
     auto const &sourceSettings = survey.sourceSettings;
     auto const &uniqueShotNos = survey.uniqueShotNos;
@@ -83,6 +91,10 @@ static void runShotDomain(Configuration::Configuration const &config, IndexType 
         Acquisition::Receivers<ValueType> receivers;
         if (config.get<IndexType>("useReceiversPerShot") == 0)
             receivers.init(config, modelCoordinates);
+        if (survey.copSources)
+            sources.getSeismogramHandler().allocateCOP(numshots, tStepEnd);
+        if (survey.copReceivers)
+            receivers.getSeismogramHandler().allocateCOP(numshots, tStepEnd);
 
         const IndexType snapType = config.get<IndexType>("snapType");
         const double tInit = now() - globalStart_t;
@@ -92,6 +104,9 @@ static void runShotDomain(Configuration::Configuration const &config, IndexType 
             std::vector<Acquisition::sourceSettings<ValueType>> sourceSettingsShot;
             Acquisition::createSettingsForShot(sourceSettingsShot, sourceSettings, shotNumber);
             sources.init(sourceSettingsShot, config, modelCoordinates);
+            const IndexType shotIndIncr = survey.useSourceEncode == 0 && shotInd < (IndexType)survey.shotIndsIncr.size() ? survey.shotIndsIncr[shotInd] : shotInd;
+            if (survey.copSources)
+                sources.getSeismogramHandler().setShotInd(shotInd, shotIndIncr); // Simulation.cpp:384-386
             IndexType shotIndPerShot = shotInd;
             if (survey.useStreamConfig) {
                 // Simulation.cpp:387-398: switch to the model subset of this shot
@@ -124,6 +139,8 @@ static void runShotDomain(Configuration::Configuration const &config, IndexType 
             else if (config.get<IndexType>("useReceiversPerShot") != 0)
                 receivers.init(config, modelCoordinates, shotNumber);
             receivers.getSeismogramHandler().resetData();
+            if (survey.copCondition && receivers.getNumTracesGlobal() == 1)
+                receivers.getSeismogramHandler().setShotInd(shotInd, shotIndIncr); // Simulation.cpp:421-423
 
             {
                 std::lock_guard<std::mutex> lock(printMutex);
@@ -164,14 +181,23 @@ static void runShotDomain(Configuration::Configuration const &config, IndexType 
                 std::lock_guard<std::mutex> lock(printMutex);
                 HOST_PRINT("Finished time stepping for shot number: " << shotNumber << " in " << now() - start_t << " sec.\n")
             }
-            receivers.getSeismogramHandler().normalize(config.get<IndexType>("normalizeTraces"));
             // the SU trace headers refer to the source position when the shot has a single source (Simulation.cpp, Seismogram.cpp:939)
             receivers.getSeismogramHandler().setSourceCoordinate(sources.get1DCoordinates().size() == 1 ? sources.get1DCoordinates()[0] : 0);
+            if (config.get<IndexType>("normalizeTraces") == 3) { // Simulation.cpp:520-525: automatic gain control; the gain function is written too
+                receivers.getSeismogramHandler().setFrequencyAGC(config.get<ValueType>("CenterFrequencyCPML"));
+                receivers.getSeismogramHandler().calcInverseAGC();
+                receivers.getSeismogramHandler().write(5, config.get<std::string>("SeismogramFilename") + ".shot_" + std::to_string(shotNumber), &modelCoordinates);
+            }
+            receivers.getSeismogramHandler().normalize(config.get<IndexType>("normalizeTraces"));
             receivers.getSeismogramHandler().write(config.get<IndexType>("SeismogramFormat"), config.get<std::string>("SeismogramFilename") + ".shot_" + std::to_string(shotNumber),
                                                    &modelCoordinates);
             // Simulation.cpp:531-533: a supershot is split into the seismograms of its shots (files <SeismogramFilename>.shot_<n>.<type>), its marks are written
             receivers.decode(config, config.get<std::string>("SeismogramFilename"), shotNumber, survey.sourceSettingsEncode, 1);
             receivers.writeReceiverMark(config, shotNumber);
+        }
+        if (result) {
+            result->sources = sources.getSeismogramHandler();
+            result->receivers = receivers.getSeismogramHandler();
         }
     } catch (std::exception const &e) {
         *error = e.what();
@@ -259,6 +285,25 @@ int main(int argc, const char *argv[])
             numshots = (IndexType)survey.uniqueShotNos.size();
             SCAI_ASSERT_ERROR(numshots <= wantedDomains, "more supershots than NumShotDomains")
         }
+        // common-offset profiles (Simulation.cpp:356-361).  The receiver count the reference looks at before the shot loop is that of
+        // <ReceiverFilename>.txt or, with receivers per shot, of the last shot Receivers::getModelPerShotSize samples (Receivers.cpp:627-662).
+        // (With useSourceEncode the reference compares it with the shots per supershot and would write a profile of zeros: not done.)
+        survey.copCondition = survey.useSourceEncode == 0 && uniqueShotNos.size() == sourceSettings.size() && uniqueShotNos.size() > 1;
+        if (survey.copCondition) {
+            survey.copSources = config.getAndCatch("writeSource", false);
+            Acquisition::Receivers<ValueType> probe;
+            const IndexType rps = config.get<IndexType>("useReceiversPerShot");
+            std::vector<Acquisition::receiverSettings> probeSettings;
+            const size_t shotSkip = std::max<size_t>(1, sourceSettings.size() / 10), last = (sourceSettings.size() - 1) / shotSkip * shotSkip;
+            const IndexType lastNo = std::abs(sourceSettings[last].sourceNo);
+            if (rps == 0 && !config.getAndCatch("initReceiverFromSU", false))
+                Acquisition::readAllSettings(probeSettings, config.get<std::string>("ReceiverFilename") + ".txt");
+            else if (rps == 1 && !config.getAndCatch("initReceiverFromSU", false))
+                Acquisition::readAllSettings(probeSettings, config.get<std::string>("ReceiverFilename") + ".shot_" + std::to_string(lastNo) + ".txt");
+            else if (rps == 2)
+                probe.getAcquisitionSettings(config, probeSettings, lastNo, survey.numshotsAll, survey.shotIndsIncr, survey.sourceSettingsEncode);
+            survey.copReceivers = probeSettings.size() == 1;
+        }
         SCAI_ASSERT_ERROR(numshots >= wantedDomains || survey.useSourceEncode != 0, "numshots = " << numshots << ", numShotDomains = " << wantedDomains)
         // (Simulation.cpp:270-272 insists on numshots % NumShotDomains == 0; the block distribution below copes with a remainder)
         sources.writeShotIndsIncr(config, uniqueShotNos);
@@ -313,20 +358,34 @@ int main(int argc, const char *argv[])
         }
         std::vector<std::thread> threads;
         std::vector<std::string> errors(numShotDomains);
+        std::vector<DomainResult> results(numShotDomains);
         for (IndexType dom = 0; dom < numShotDomains; dom++) {
             std::vector<IndexType> devices;
             for (IndexType r = 0; r < gpusPerDomain; r++)
                 devices.push_back(dom * gpusPerDomain + r);
             if (numShotDomains == 1)
-                runShotDomain(config, dom, devices, shotsOfDomain[dom], survey, model, modelCoordinates, globalStart_t, &errors[dom]);
+                runShotDomain(config, dom, devices, shotsOfDomain[dom], survey, model, modelCoordinates, globalStart_t, &errors[dom], &results[dom]);
             else
-                threads.emplace_back(runShotDomain, std::cref(config), dom, devices, shotsOfDomain[dom], std::cref(survey), model, std::cref(modelCoordinates), globalStart_t, &errors[dom]);
+                threads.emplace_back(runShotDomain, std::cref(config), dom, devices, shotsOfDomain[dom], std::cref(survey), model, std::cref(modelCoordinates), globalStart_t, &errors[dom], &results[dom]);
         }
         for (auto &t : threads)
             t.join();
         for (auto const &e : errors)
             if (!e.empty())
                 COMMON_THROWEXCEPTION(e)
+        // Simulation.cpp:535-560: the common-offset profiles of the shot domains are summed and written by the first domain
+        if (survey.copSources) {
+            for (IndexType dom = 1; dom < numShotDomains; dom++)
+                results[0].sources.sumShotDomain(results[dom].sources);
+            results[0].sources.assignCOP();
+            results[0].sources.write(config.get<IndexType>("SeismogramFormat"), config.get<std::string>("writeSourceFilename"), &modelCoordinates);
+        }
+        if (survey.copReceivers && results[0].receivers.getNumTracesTotal() == 1) {
+            for (IndexType dom = 1; dom < numShotDomains; dom++)
+                results[0].receivers.sumShotDomain(results[dom].receivers);
+            results[0].receivers.assignCOP();
+            results[0].receivers.write(config.get<IndexType>("SeismogramFormat"), config.get<std::string>("SeismogramFilename"), &modelCoordinates);
+        }
         HOST_PRINT("\nTotal runtime of WAVE-Simulation: " << now() - globalStart_t << " sec.\nWAVE-Simulation finished!\n\n")
     } catch (std::exception const &e) {
         std::cerr << "\nERROR: " << e.what() << std::endl;
