@@ -1,11 +1,13 @@
 // Unit tests of the LAMA-free host layer (wave-simulation_b200/host), modelled on the reference's googletest cases
 // (src/Tests/UnitTest/{Configuration,Coordinates,Ricker,...}UnitTest.cpp): same known answers, plain asserts.
-// Built and run by tests/test_host_layer.py; needs no GPU and no solver library.
+// Built and run by tests/test_host_layer.py; needs no GPU (linked against the emulation build of the solver library, which the
+// model classes reference; nothing of it runs here).
 #include "Acquisition.hpp"
 #include "Configuration.hpp"
 #include "Coordinates.hpp"
 #include "Derivatives.hpp"
 #include "IO.hpp"
+#include "Modelparameter.hpp"
 #include <cstdio>
 #include <fstream>
 
@@ -209,6 +211,106 @@ int main(int argc, char **argv)
         EXPECT(receivers.getNumTracesGlobal() == 1 && receivers.getReceiverMarkVector()[3] == 1);
         EXPECT_THROW(receivers.init(config, coords, 7, 3, rows, {}));
         EXPECT_THROW(receivers.init(config, coords, 2, 4, rows, {})); // numshots does not fit the matrix
+    }
+    // ---- EM model files: relative values on disk, the visco types hold the real EFFECTIVE permittivity / conductivity (ViscoTMEM.cpp:320-402)
+    {
+        const char *base = "dimension=2D\nNX=6\nNY=5\nNZ=1\nDH=0.02\nUseVariableGrid=0\nfileFormat=1\nnumRelaxationMechanisms=2\nrelaxationFrequency=5.0e7\n"
+                           "relaxationFrequency2=3.0e8\nCenterFrequencyCPML=1.0e8\nmur=1.5\nsigma=0.01\nepsilonr=6\ntauSigmar=0.3\ntauEpsilon=0.2\n";
+        {
+            std::ofstream c0(dir + "/em0.txt"), c1(dir + "/em1.txt");
+            c0 << base << "equationType=viscotmem\nModelRead=0\nModelFilename=" << dir << "/emmodel\n";
+            c1 << base << "equationType=viscotmem\nModelRead=1\nModelFilename=" << dir << "/emmodel\n";
+        }
+        Configuration::Configuration c0(dir + "/em0.txt"), c1(dir + "/em1.txt");
+        Acquisition::Coordinates<ValueType> coords(c0);
+        Modelparameter::Modelparameter<ValueType> a("viscotmem"), b("viscotmem");
+        a.init(c0, coords);
+        std::vector<ValueType> epsStatic = a.getDielectricPermittivity(), sigStatic = a.getElectricConductivity();
+        for (size_t i = 0; i < epsStatic.size(); i++) { // a heterogeneous model
+            epsStatic[i] *= 1 + 0.05f * (i % 7);
+            sigStatic[i] *= 1 + 0.1f * (i % 5);
+        }
+        a.init("dielectricPermittivity", epsStatic);
+        a.init("electricConductivity", sigStatic);
+        a.write(dir + "/emmodel", 1);
+        std::vector<ValueType> file(30);
+        IO::readVector(file, dir + "/emmodel.mur", 1);
+        EXPECT(std::abs(file[3] - 1.5f) < 1e-6);
+        IO::readVector(file, dir + "/emmodel.tauSigmar", 1);
+        EXPECT(std::abs(file[3] - 0.3f) < 1e-6);
+        IO::readVector(file, dir + "/emmodel.epsilonr", 1);
+        {   // independent evaluation of the effective permittivity of point 3 in double precision
+            const double w = 2 * M_PI * 1e8, t1 = 1 / (2 * M_PI * 5e7), t2 = 1 / (2 * M_PI * 3e8);
+            const double aAv = 0.5 * (w * w * t1 * t1 / (1 + w * w * t1 * t1) + w * w * t2 * t2 / (1 + w * w * t2 * t2));
+            const double tauSig = 0.3 / w;
+            const double want = ((double)epsStatic[3] * (1 - aAv * 0.2) + (double)sigStatic[3] * tauSig) / 8.8541878176e-12;
+            EXPECT(std::abs(file[3] - want) < 1e-4 * want);
+            EXPECT(file[3] > 6.0f * 0.8f && std::abs(file[3] - 6.0f * 1.15f) > 1e-2); // relative, and not the static value
+        }
+        b.init(c1, coords);
+        double worst = 0;
+        for (size_t i = 0; i < epsStatic.size(); i++) {
+            worst = std::max(worst, std::abs((double)b.getDielectricPermittivity()[i] / epsStatic[i] - 1));
+            worst = std::max(worst, std::abs((double)b.getElectricConductivity()[i] / sigStatic[i] - 1));
+            worst = std::max(worst, std::abs((double)b.getMagneticPermeability()[i] / a.getMagneticPermeability()[i] - 1));
+        }
+        EXPECT(worst < 2e-5); // effective -> static undoes static -> effective (9 significant digits in the mtx file)
+        // the non-dispersive type writes its parameters as relative values only
+        {
+            std::ofstream c2(dir + "/em2.txt");
+            c2 << base << "equationType=tmem\nModelRead=0\nModelFilename=" << dir << "/emmodel2\n";
+        }
+        Configuration::Configuration c2(dir + "/em2.txt");
+        Modelparameter::Modelparameter<ValueType> t("tmem");
+        t.init(c2, coords);
+        t.write(dir + "/emmodel2", 1);
+        IO::readVector(file, dir + "/emmodel2.epsilonr", 1);
+        EXPECT(std::abs(file[7] - 6.0f) < 1e-5);
+        IO::readVector(file, dir + "/emmodel2.sigma", 1);
+        EXPECT(std::abs(file[7] - 0.01f) < 1e-8);
+    }
+    // ---- models on a variable grid: ModelRead = 1 maps the REGULAR model file onto the grid, ModelRead = 2 reads the grid itself (Acoustic.cpp init)
+    {
+        {
+            std::ofstream g(dir + "/vgGrid.txt");
+            g << "# interface dhFactor\n0 1\n4 3\n10 1\n";
+            std::ofstream c(dir + "/vg.txt");
+            c << "dimension=2D\nequationType=acoustic\nNX=9\nNY=12\nNZ=1\nDH=10\nUseVariableGrid=1\nfileFormat=1\nModelRead=1\nModelFilename=" << dir << "/vgmodel\n"
+              << "gridConfigurationFilename=" << dir << "/vgGrid.txt\n";
+        }
+        Configuration::Configuration c(dir + "/vg.txt");
+        Acquisition::Coordinates<ValueType> coords(c), regular(9, 12, 1, 10);
+        const IndexType n = coords.getNGridpoints();
+        EXPECT(n < 9 * 12 && n > 0);
+        std::vector<ValueType> vp(9 * 12), rho(9 * 12);
+        for (size_t i = 0; i < vp.size(); i++) {
+            vp[i] = 1500 + (ValueType)i;
+            rho[i] = 2000 - (ValueType)i;
+        }
+        IO::writeVector(vp, dir + "/vgmodel.vp", 1);
+        IO::writeVector(rho, dir + "/vgmodel.density", 1);
+        Modelparameter::Modelparameter<ValueType> m("acoustic");
+        m.init(c, coords);
+        bool ok = (IndexType)m.getVelocityP().size() == n;
+        for (IndexType i = 0; ok && i < n; i++) {
+            const IndexType r = regular.coordinate2index(coords.index2coordinate(i));
+            ok = m.getVelocityP()[i] == vp[r] && m.getDensity()[i] == rho[r];
+        }
+        EXPECT(ok);
+        // written on the variable grid and read back as such
+        m.write(dir + "/vgmodel2", 1);
+        {
+            std::ofstream c2(dir + "/vg2.txt");
+            c2 << "dimension=2D\nequationType=acoustic\nNX=9\nNY=12\nNZ=1\nDH=10\nUseVariableGrid=1\nfileFormat=1\nModelRead=2\nModelFilename=" << dir << "/vgmodel2\n"
+               << "gridConfigurationFilename=" << dir << "/vgGrid.txt\n";
+            std::ofstream c3(dir + "/vg3.txt");
+            c3 << "dimension=2D\nequationType=acoustic\nNX=9\nNY=12\nNZ=1\nDH=10\nUseVariableGrid=0\nfileFormat=1\nModelRead=2\nModelFilename=" << dir << "/vgmodel2\n";
+        }
+        Configuration::Configuration c2(dir + "/vg2.txt"), c3(dir + "/vg3.txt");
+        Modelparameter::Modelparameter<ValueType> m2("acoustic"), m3("acoustic");
+        m2.init(c2, coords);
+        EXPECT(m2.getVelocityP() == m.getVelocityP() && m2.getDensity() == m.getDensity());
+        EXPECT_THROW(m3.init(c3, regular)); // "Read variable model (ModelRead=2) not available if regular grid is chosen!"
     }
     // ---- file formats: mtx and lmf round trips, resampling (Common.hpp:202-233)
     {

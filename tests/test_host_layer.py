@@ -123,10 +123,11 @@ def run(driver, cfg, cwd, expect_ok=True):
 
 
 def test_host_unit_tests(tmp_path):
+    build_emu()  # the model classes reference the solver library (device-side averaging); nothing of it runs in these tests
     subprocess.check_call(["make", "-s", "-C", HOST, "libSimulation_host.a"])
     exe = str(tmp_path / "test_host")
-    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-I" + HOST, os.path.join(ROOT, "tests", "host", "test_host.cpp"),
-                           os.path.join(HOST, "libSimulation_host.a"), "-o", exe])
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-pthread", "-I" + HOST, os.path.join(ROOT, "tests", "host", "test_host.cpp"),
+                           os.path.join(HOST, "libSimulation_host.a"), "-L" + EMU_DIR, "-lwavesim_emu", "-Wl,-rpath," + EMU_DIR, "-fopenmp", "-o", exe])
     out = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout
     assert "host unit tests OK" in out.stdout

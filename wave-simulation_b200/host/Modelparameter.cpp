@@ -41,7 +41,18 @@ template <typename ValueType>
 void Modelparameter::Modelparameter<ValueType>::init(Configuration::Configuration const &config, Acquisition::Coordinates<ValueType> const &modelCoordinates)
 {
     const IndexType modelRead = config.get<IndexType>("ModelRead");
-    SCAI_ASSERT_ERROR(modelRead == 0 || modelRead == 1, "ModelRead=" << modelRead << ": variable-grid models are not available in the B200 path")
+    const bool variableGrid = config.getAndCatch("UseVariableGrid", 0) == 1;
+    SCAI_ASSERT_ERROR(modelRead >= 0 && modelRead <= 2, "ModelRead=" << modelRead)
+    SCAI_ASSERT_ERROR(modelRead != 2 || variableGrid, "Read variable model (ModelRead=2) not available if regular grid is chosen!") // Elastic.cpp:164
+    // ModelRead = 1 on a variable grid (Elastic.cpp:174-184, Acoustic.cpp likewise): the file holds the model on the REGULAR grid NX x NY x NZ;
+    // every point of the variable grid takes the value of the regular point at its coordinate.  ModelRead = 2 reads the variable grid itself.
+    std::vector<IndexType> regularIndex;
+    if (modelRead == 1 && variableGrid) {
+        Acquisition::Coordinates<ValueType> regularCoordinates(config.get<IndexType>("NX"), config.get<IndexType>("NY"), config.get<IndexType>("NZ"), config.get<ValueType>("DH"));
+        regularIndex.resize((size_t)modelCoordinates.getNGridpoints());
+        for (IndexType i = 0; i < modelCoordinates.getNGridpoints(); i++)
+            regularIndex[i] = regularCoordinates.coordinate2index(modelCoordinates.index2coordinate(i));
+    }
     const bool visco = equationType.compare(0, 5, "visco") == 0;
     relaxationFrequency.clear();
     if (visco) {
@@ -55,9 +66,15 @@ void Modelparameter::Modelparameter<ValueType>::init(Configuration::Configuratio
     raw = std::make_shared<std::map<std::string, std::vector<ValueType>>>();
     for (auto const &p : parsOf(equationType)) {
         std::vector<ValueType> v(N);
-        if (modelRead == 1) {
-            SCAI_ASSERT_ERROR(seismic || !visco, "ModelRead=1 for visco-EM models (effective -> static conversion, ViscoTMEM.cpp:320-350) is not available yet")
-            IO::readVector(v, config.get<std::string>("ModelFilename") + "." + p.suffix, config.get<IndexType>("FileFormat"));
+        if (modelRead != 0) {
+            if (regularIndex.empty())
+                IO::readVector(v, config.get<std::string>("ModelFilename") + "." + p.suffix, config.get<IndexType>("FileFormat"));
+            else {
+                std::vector<ValueType> regular((size_t)config.get<IndexType>("NX") * config.get<IndexType>("NY") * config.get<IndexType>("NZ"));
+                IO::readVector(regular, config.get<std::string>("ModelFilename") + "." + p.suffix, config.get<IndexType>("FileFormat"));
+                for (size_t i = 0; i < N; i++)
+                    v[i] = regular[(size_t)regularIndex[i]];
+            }
         } else
             std::fill(v.begin(), v.end(), config.get<ValueType>(p.key));
         // EM inputs are relative: scale to SI (TMEM.cpp:262-292, ViscoTMEM.cpp:274-293)
@@ -70,7 +87,43 @@ void Modelparameter::Modelparameter<ValueType>::init(Configuration::Configuratio
                 x *= scale;
         (*raw)[p.name] = std::move(v);
     }
+    centerFrequencyCPML = !seismic && visco ? config.get<ValueType>("CenterFrequencyCPML") : ValueType(0);
+    if (!seismic && visco && modelRead != 0) {
+        // ViscoTMEM.cpp:320-350, ViscoEMEM.cpp:290-306: the files hold the real EFFECTIVE permittivity and conductivity at the reference
+        // frequency; the solver works on the static ones (ModelparameterEM.cpp:473-554 with calculateType = 2)
+        ValueType aAverage, bAverage;
+        relaxationAverages(aAverage, bAverage);
+        auto &eps = (*raw)["dielectricPermittivity"], &sig = (*raw)["electricConductivity"];
+        auto const &tauEps = (*raw)["tauDielectricPermittivity"], &tauSig = (*raw)["tauElectricConductivity"];
+        for (size_t i = 0; i < N; i++) {
+            ValueType b = bAverage * tauEps[i];
+            ValueType a = ValueType(1) - aAverage * tauEps[i];
+            a -= b * tauSig[i];
+            ValueType epsStatic = (eps[i] - sig[i] * tauSig[i]) / a;
+            if (epsStatic < DielectricPermittivityVacuum) // searchAndReplace(.., eps0, eps0, 1)
+                epsStatic = DielectricPermittivityVacuum;
+            ValueType sigStatic = sig[i] - b * epsStatic;
+            if (sigStatic < 0)
+                sigStatic = 0;
+            eps[i] = epsStatic;
+            sig[i] = sigStatic;
+        }
+    }
     dirtyFlag = true;
+}
+
+// a = mean_l (w tau_l)^2 / (1 + (w tau_l)^2), b = mean_l w^2 tau_l / (1 + (w tau_l)^2) at w = 2 pi CenterFrequencyCPML (ModelparameterEM.cpp:417-423, 448-454)
+template <typename ValueType> void Modelparameter::Modelparameter<ValueType>::relaxationAverages(ValueType &aAverage, ValueType &bAverage) const
+{
+    aAverage = bAverage = 0;
+    const ValueType w_ref = 2.0 * M_PI * centerFrequencyCPML;
+    for (ValueType f : relaxationFrequency) {
+        const ValueType relaxationTime = 1.0 / (2.0 * M_PI * f);
+        aAverage += (w_ref * w_ref * relaxationTime * relaxationTime / (1 + w_ref * w_ref * relaxationTime * relaxationTime));
+        bAverage += (w_ref * w_ref * relaxationTime / (1 + w_ref * w_ref * relaxationTime * relaxationTime));
+    }
+    aAverage /= relaxationFrequency.size();
+    bAverage /= relaxationFrequency.size();
 }
 
 template <typename ValueType> void Modelparameter::Modelparameter<ValueType>::init(std::string const &name, std::vector<ValueType> const &values)
@@ -83,9 +136,39 @@ template <typename ValueType> void Modelparameter::Modelparameter<ValueType>::in
 
 template <typename ValueType> void Modelparameter::Modelparameter<ValueType>::write(std::string filename, IndexType fileFormat) const
 {
-    for (auto const &p : parsOf(equationType)) {
-        SCAI_ASSERT_ERROR(seismic, "Modelparameter::write is implemented for seismic models")
-        IO::writeVector(at(p.name), filename + "." + p.suffix, fileFormat);
+    if (seismic) {
+        for (auto const &p : parsOf(equationType))
+            IO::writeVector(at(p.name), filename + "." + p.suffix, fileFormat);
+        return;
+    }
+    // EM models are written as they are read: relative permeability / permittivity, tauSigmar relative to the reference relaxation time and,
+    // for the visco types, the real effective permittivity and conductivity (TMEM.cpp:312-330, ViscoTMEM.cpp:382-402, ModelparameterEM.cpp:410-467)
+    const bool visco = equationType.compare(0, 5, "visco") == 0;
+    std::vector<ValueType> mu(at("magneticPermeability")), eps(at("dielectricPermittivity")), sig(at("electricConductivity"));
+    for (auto &x : mu)
+        x /= MagneticPermeabilityVacuum;
+    if (visco) {
+        ValueType aAverage, bAverage;
+        relaxationAverages(aAverage, bAverage);
+        auto const &tauEps = at("tauDielectricPermittivity"), &tauSig = at("tauElectricConductivity");
+        for (size_t i = 0; i < eps.size(); i++) {
+            const ValueType epsStatic = eps[i], sigStatic = sig[i];
+            sig[i] = std::max(epsStatic * (bAverage * tauEps[i]) + sigStatic, ValueType(0));
+            eps[i] = std::max(epsStatic * (ValueType(1) - aAverage * tauEps[i]) + sigStatic * tauSig[i], DielectricPermittivityVacuum);
+        }
+    }
+    for (auto &x : eps)
+        x /= DielectricPermittivityVacuum;
+    IO::writeVector(mu, filename + ".mur", fileFormat);
+    IO::writeVector(sig, filename + ".sigma", fileFormat);
+    IO::writeVector(eps, filename + ".epsilonr", fileFormat);
+    if (visco) {
+        std::vector<ValueType> tauSig(at("tauElectricConductivity"));
+        const ValueType relaxationTime_ref = 1.0 / (2.0 * M_PI * centerFrequencyCPML);
+        for (auto &x : tauSig)
+            x /= relaxationTime_ref;
+        IO::writeVector(tauSig, filename + ".tauSigmar", fileFormat);
+        IO::writeVector(at("tauDielectricPermittivity"), filename + ".tauEpsilon", fileFormat);
     }
 }
 
@@ -159,6 +242,7 @@ void Modelparameter::Modelparameter<ValueType>::getModelPerShot(Modelparameter<V
     }
     modelPerShot.raw = out;
     modelPerShot.relaxationFrequency = relaxationFrequency;
+    modelPerShot.centerFrequencyCPML = centerFrequencyCPML;
     modelPerShot.dirtyFlag = true;
 }
 

@@ -70,6 +70,8 @@ namespace KITGPI
             //! changes a parameter gets its own map (init)
             std::shared_ptr<std::map<std::string, std::vector<ValueType>>> raw = std::make_shared<std::map<std::string, std::vector<ValueType>>>();
             std::vector<ValueType> relaxationFrequency;
+            ValueType centerFrequencyCPML = 0; // visco-EM: reference frequency of the effective <-> static conversion
+            void relaxationAverages(ValueType &aAverage, ValueType &bAverage) const;
             ForwardSolver::DeviceGroup *h = nullptr;
         };
 

@@ -118,8 +118,7 @@ static void runShotDomain(Configuration::Configuration const &config, IndexType 
                     modelLocal.prepareForModelling();
                     solver->prepareForModelling(modelLocal, DT);
                 }
-                if (modelLocal.isSeismic())
-                    modelLocal.write(config.get<std::string>("ModelFilename") + ".shot_" + std::to_string(shotNumber), config.get<IndexType>("FileFormat"));
+                modelLocal.write(config.get<std::string>("ModelFilename") + ".shot_" + std::to_string(shotNumber), config.get<IndexType>("FileFormat"));
             }
             firstShot = false;
             CheckParameter::checkNumericalArtefactsAndInstabilities<ValueType>(config, sourceSettingsShot, modelLocal, modelCoordinates, shotNumber);
