@@ -283,6 +283,24 @@ def test_driver_error_behaviour(driver, tmp_path):
     assert p.returncode != 0 and "Parameter NX: Not found in Configuration file!" in p.stderr
     p = subprocess.run([driver], capture_output=True, text=True)
     assert p.returncode != 0 and "No configuration file given" in p.stdout
+    open(cfg, "w").write(text.replace("useStencilMatrix=1", "useStencilMatrix=0\nuseHybridFreeSurface=1"))
+    p = run(driver, cfg, tmp, expect_ok=False)
+    assert p.returncode != 0 and "hybrid matrix without stencil matrix" in p.stderr
+    open(cfg, "w").write(text + "ShotDomainDefinition=2\n")
+    p = run(driver, cfg, tmp, expect_ok=False)
+    assert p.returncode != 0 and "ShotDomainDefinition" in p.stderr
+
+
+def test_driver_coordinate_files_and_domain_definition(driver, tmp_path):
+    """writeCoordinate (Simulation.cpp:151-154): the grid coordinates of every point as three vectors; ShotDomainDefinition = 1 (one
+    domain per node) and useHybridFreeSurface = 1 (the image-method operator as stencil + sparse part) are accepted."""
+    tmp = str(tmp_path)
+    cfg = with_keys(setup_case(tmp, T=0.05), writeCoordinate=1, coordinateFilename="model/coordinates", ShotDomainDefinition=1, NumShotDomains=4, useHybridFreeSurface=1)
+    log = run(driver, cfg, tmp).stdout
+    assert "1 shot domain(s)" in log
+    x, y, z = (read_mtx(os.path.join(tmp, "model", "coordinates%s.mtx" % a)).ravel() for a in "XYZ")
+    k = np.arange(100 * 100)
+    assert np.array_equal(x, k % 100) and np.array_equal(y, k // 100) and not z.any()
 
 
 @pytest.mark.gpu

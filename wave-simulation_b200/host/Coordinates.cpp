@@ -1,4 +1,5 @@
 #include "Coordinates.hpp"
+#include "IO.hpp"
 #include <fstream>
 #include <sstream>
 
@@ -247,6 +248,21 @@ template <typename ValueType> Acquisition::coordinate3D Acquisition::Coordinates
     d.y = std::min(c.y, NY - 1 - c.y);
     d.z = std::min(c.z, NZ - 1 - c.z);
     return d;
+}
+
+template <typename ValueType> void Acquisition::Coordinates<ValueType>::writeCoordinates(std::string const &filename, IndexType fileFormat) const
+{
+    const IndexType n = getNGridpoints();
+    std::vector<float> x((size_t)n), y((size_t)n), z((size_t)n);
+    for (IndexType i = 0; i < n; i++) {
+        const coordinate3D c = index2coordinate(i);
+        x[i] = (float)c.x;
+        y[i] = (float)c.y;
+        z[i] = (float)c.z;
+    }
+    IO::writeVector(x, filename + "X", fileFormat);
+    IO::writeVector(y, filename + "Y", fileFormat);
+    IO::writeVector(z, filename + "Z", fileFormat);
 }
 
 template class KITGPI::Acquisition::Coordinates<float>;

@@ -33,6 +33,8 @@ namespace KITGPI
             ValueType getDH() const { return DH; }
             ValueType getX0() const { return x0; } // origin of the model in metres (key x0, Coordinates.cpp:40): places a sub-model in the big one
             IndexType getNGridpoints() const { return layered ? nGridpoints : NX * NY * NZ; }
+            //! <filename>X / Y / Z: the grid coordinates of every point as three vectors (Coordinates.cpp:545-590; key writeCoordinate)
+            void writeCoordinates(std::string const &filename, IndexType fileFormat) const;
             //! true when the model vector is layered (useVariableGrid or useVariableFDoperators): the operators are assembled point by point
             bool isVariable() const { return layered; }
             bool hasVariableSpacing() const { return variableSpacing; }

@@ -32,6 +32,10 @@ template <typename ValueType> void Derivatives<ValueType>::init(Configuration::C
     spatialFDorder = config.get<IndexType>("spatialFDorder");
     FDCoef = calcFDCoef(spatialFDorder);
     useStencilMatrix = config.getAndCatch("useStencilMatrix", 0) != 0;
+    // Derivatives.cpp:35-44: the hybrid free-surface operator (stencil + sparse image corrections) is the image-method operator the
+    // stencil kernels apply in one pass; the key is accepted with the reference's precondition
+    if (config.getAndCatch("useHybridFreeSurface", 0) != 0)
+        SCAI_ASSERT_ERROR(useStencilMatrix, "It is not possible to use the hybrid matrix without stencil matrix!")
     spatialFDorderVec.clear();
     if (config.getAndCatch("useVariableFDoperators", 0) != 0) { // Derivatives.cpp:47-53
         SCAI_ASSERT_ERROR(!useStencilMatrix, "Variable FD operators are not available for stencil matrices")

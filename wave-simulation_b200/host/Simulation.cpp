@@ -235,6 +235,8 @@ int main(int argc, const char *argv[])
             nDevices = std::max<IndexType>(1, std::min<IndexType>(nDevices, std::atoi(e)));
 
         Acquisition::Coordinates<ValueType> modelCoordinates(config);
+        if (config.getAndCatch("writeCoordinate", false)) // Simulation.cpp:151-154
+            modelCoordinates.writeCoordinates(config.get<std::string>("coordinateFilename"), config.get<IndexType>("FileFormat"));
         const IndexType numRelaxationMechanisms = config.getAndCatch("numRelaxationMechanisms", 0);
         (void)numRelaxationMechanisms;
 
@@ -271,6 +273,14 @@ int main(int argc, const char *argv[])
         survey.useSourceEncode = config.getAndCatch("useSourceEncode", 0);
         const IndexType useRandomSource = config.getAndCatch("useRandomSource", 0);
         IndexType wantedDomains = std::max<IndexType>(1, config.getAndCatch("NumShotDomains", 1));
+        {   // Partitioning.hpp:43-81 getShotDomain: 0 = NumShotDomains groups of equal size, 1 = the processors of a node form one domain (this
+            // process drives the GPUs of ONE node: one domain over all of them), 2 = per-process environment variable DOMAIN (an MPI notion)
+            const IndexType shotDomainDefinition = config.getAndCatch("ShotDomainDefinition", 0);
+            SCAI_ASSERT_ERROR(shotDomainDefinition == 0 || shotDomainDefinition == 1,
+                              "ShotDomainDefinition = " << shotDomainDefinition << ": the DOMAIN environment variable of an MPI process has no counterpart in the single-process driver")
+            if (shotDomainDefinition == 1)
+                wantedDomains = 1;
+        }
         sources.calcSourceSettingsEncode(config, seedtime);
         IndexType numshots;
         if (survey.useSourceEncode == 0) {
