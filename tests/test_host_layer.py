@@ -980,6 +980,43 @@ def test_driver_trace_gain_and_instantaneous_outputs(driver, tmp_path):
     assert np.allclose(phase, np.arctan2(-got, got), atol=1e-5)
 
 
+@pytest.mark.gpu
+def test_product_driver_marks_encoding_profiles_and_gain_on_gpu(tmp_path):
+    """The seismogram bookkeeping of the driver on the real library: receivers by mark matrix, a supershot = the signed sum of its
+    shots and decoded back into them, the common-offset profile of single-trace shots over two shot domains (when two GPUs are
+    there), automatic gain control with its gain function written."""
+    subprocess.check_call(["make", "-s", "-C", HOST])
+    plain = str(tmp_path / "plain")
+    _run_product(setup_case(plain, sources=FOUR_SHOTS, receivers=TWO_RECEIVERS, T=0.5, kvar=0), plain, {"WS_NUM_GPUS": "1"})
+    single = seismograms_of(plain)
+    assert sorted(single) == [1, 2, 3, 4]
+    tmp = str(tmp_path / "marks")
+    cfg = setup_case(tmp, sources=FOUR_SHOTS, receivers=TWO_RECEIVERS, T=0.5, rps=2, kvar=0)
+    write_mark(tmp, MARKS)
+    _run_product(cfg, tmp, {"WS_NUM_GPUS": "1"})
+    got = seismograms_of(tmp)
+    assert all(np.array_equal(got[no], single[no][np.array(MARKS[no - 1][1:]) != 0]) for no in (1, 2, 3, 4))
+    tmp = str(tmp_path / "encode")
+    cfg = with_keys(setup_case(tmp, sources=FOUR_SHOTS, receivers=TWO_RECEIVERS, T=0.5, rps=2, kvar=0), useSourceEncode=2, NumShotDomains=2, seedtime=7)
+    write_mark(tmp, MARKS, coordinate=True)
+    _run_product(cfg, tmp)
+    enc = seismograms_of(tmp)
+    for no, members in {20001: [1, 3], 20002: [2, 4]}.items():
+        assert rel_l2(enc[no], sum(single[m] for m in members)) <= 2.0e-5
+        assert all(np.array_equal(enc[m], enc[no][np.array(MARKS[m - 1][1:]) != 0]) for m in members)
+    tmp = str(tmp_path / "cop")
+    cfg = with_keys(setup_case(tmp, sources=FOUR_SHOTS, receivers="30 2 0 3\n", T=0.5, kvar=0), NumShotDomains=2, writeSource=1, writeSourceFilename="seismograms/source")
+    _run_product(cfg, tmp)
+    assert sorted(os.listdir(os.path.join(tmp, "seismograms"))) == ["seismogram.vy.mtx", "source.vx.mtx"]
+    got = seismograms_of(tmp, cop=[1, 2, 3, 4])
+    assert all(np.array_equal(got[k], single[k][0:1]) for k in got)
+    tmp = str(tmp_path / "agc")
+    _run_product(setup_case(tmp, sources=FOUR_SHOTS, receivers=TWO_RECEIVERS, T=0.5, norm=3, kvar=0), tmp, {"WS_NUM_GPUS": "1"})
+    gain = read_mtx(os.path.join(tmp, "seismograms", "seismogram.shot_2.vy.inverseAGC.mtx"))
+    unit = single[2] / np.linalg.norm(single[2], axis=1, keepdims=True)
+    assert rel_l2(seismograms_of(tmp)[2], unit * gain) <= 1.0e-5
+
+
 # frequency filters and Hilbert transform (Filter/Filter.cpp, Common/HilbertFFT.cpp)
 def run_filter_tool(tmp_path, data, dt, *op):
     subprocess.check_call(["make", "-s", "-C", HOST, "libSimulation_host.a"])
