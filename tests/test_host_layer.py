@@ -813,6 +813,41 @@ def test_driver_source_encoding(driver, tmp_path):
     assert p.returncode != 0 and "useReceiversPerShot != 2" in p.stdout + p.stderr
 
 
+def test_driver_frequency_encoded_supershots(driver, tmp_path):
+    """gradientDomain != 0 with source encoding (Sources.cpp:584-674): every shot of a supershot fires a sine of its own frequency drawn
+    from every second FFT bin up to 2 CenterFrequencyCPML; the frequencies go to <SourceFilename>.sourceFC.txt; decoding looks at
+    every shot through the one-frequency DFT at its frequency (Receivers.cpp:531-540, Filter.cpp:257-275, 331-341)."""
+    tmp = str(tmp_path / "fenc")
+    cfg = with_keys(setup_case(tmp, sources=FOUR_SHOTS, receivers=TWO_RECEIVERS, T=0.5, rps=2), useSourceEncode=2, NumShotDomains=2, seedtime=5, gradientDomain=1)
+    write_mark(tmp, [[k + 1, 1, 1] for k in range(4)])
+    run(driver, cfg, tmp)
+    nt, dt = 250, 2e-3
+    df = 1.0 / (256 * dt)
+    lines = [ln.split() for ln in open(os.path.join(tmp, "acq", "sources.sourceFC.txt")) if not ln.startswith("#")]
+    fcs = {int(ln[0]): [float(x) for x in ln[1:]] for ln in lines}
+    assert sorted(fcs) == [20001, 20002]
+    allowed = [2 * df, 4 * df, 6 * df]
+    for no, f in fcs.items():
+        assert len(f) == 2 and f[0] != f[1] and all(min(abs(x - a) for a in allowed) < 1e-3 for x in f)
+    groups = {20001: [1, 3], 20002: [2, 4]}
+    enc = seismograms_of(tmp)
+    t = np.arange(nt) * dt
+    for no, members in groups.items():
+        # the supershot = the sum of its shots fired alone with their sines (waveletShape 9)
+        alone = str(tmp_path / ("alone%d" % no))
+        src = "".join("%d %d 0 0 2 1 9 %.7g %.1f 0.0\n" % (m, 20 + 12 * (m - 1), f, 5.0 + (m - 1)) for m, f in zip(members, fcs[no]))
+        run(driver, setup_case(alone, sources=src, receivers=TWO_RECEIVERS, T=0.5), alone)
+        parts = seismograms_of(alone)
+        assert rel_l2(enc[no], sum(parts[m] for m in members)) <= 1.0e-4  # (the file carries the frequencies with 6 digits)
+        for m, f in zip(members, fcs[no]):  # the decoded shot: one-frequency DFT of the supershot at the bin of the shot, scaled to maximum 1
+            k = int(np.ceil(np.float32(f) / np.float32(df)))
+            ph = 2 * np.pi * k * df * t
+            coef = (enc[no] * np.exp(-1j * ph)).sum(axis=1, keepdims=True) * (2.0 / 256)
+            want = np.real(coef * np.exp(1j * ph))
+            want /= np.abs(want).max()
+            assert rel_l2(enc[m], want) <= 1.0e-4, (no, m)
+
+
 def test_driver_receivers_by_mark_matrix(driver, tmp_path):
     """useReceiversPerShot = 2: one receiver file and a mark matrix; every shot records the receivers its row marks (here also with the
     shot increment: the rows of the mark matrix are those of the source file, not of the selection)."""

@@ -700,7 +700,7 @@ template <typename ValueType> void Acquisition::Sources<ValueType>::getAcquisiti
     }
 }
 
-template <typename ValueType> void Acquisition::Sources<ValueType>::calcSourceSettingsEncode(Configuration::Configuration const &config, IndexType &seedtime)
+template <typename ValueType> void Acquisition::Sources<ValueType>::calcSourceSettingsEncode(Configuration::Configuration const &config, IndexType &seedtime, ValueType fc1, ValueType fc2)
 {
     const IndexType numshotsIncr = (IndexType)shotIndsIncr.size();
     const IndexType useSourceEncode = config.getAndCatch("useSourceEncode", 0), useRandomSource = config.getAndCatch("useRandomSource", 0);
@@ -708,13 +708,45 @@ template <typename ValueType> void Acquisition::Sources<ValueType>::calcSourceSe
     SCAI_ASSERT_ERROR(useSourceEncode * config.getAndCatch("useSourceSignalTaper", 0) == 0, "useSourceEncode and useSourceSignalTaper are not compatible!")
     if (config.getAndCatch("useStreamConfig", 0) != 0)
         SCAI_ASSERT_ERROR(useSourceEncode == 0 || useSourceEncode == 3, "useSourceEncode must be 0 or 3 when useStreamConfig != 0!")
-    SCAI_ASSERT_ERROR(config.getAndCatch("gradientDomain", 0) == 0, "gradientDomain != 0 (frequency selection of the inversion) is not available in the forward driver")
+    // gradientDomain != 0 (Sources.cpp:584-612): the frequencies the shots are looked at, multiples of the FFT bin width between fc1 and fc2
+    // (default 2 CenterFrequencyCPML).  Without encoding every shot gets the whole (widened) list; with it, every second bin from an even one
+    // ("ensure steady-state wavefields"), one per shot of a supershot.
+    const IndexType gradientDomain = config.getAndCatch("gradientDomain", 0);
+    std::vector<ValueType> fc12;
+    sourceFC.clear();
+    if (gradientDomain != 0) {
+        if (fc2 == 0)
+            fc2 = config.get<ValueType>("CenterFrequencyCPML") * 2;
+        const IndexType NT = static_cast<IndexType>((config.get<ValueType>("T") / config.get<ValueType>("DT")) + 0.5);
+        const IndexType nFFT = Common::calcNextPowTwo<ValueType>(NT - 1);
+        const ValueType df = 1 / (nFFT * config.get<ValueType>("DT"));
+        IndexType fc1Ind = (IndexType)std::ceil(fc1 / df), fc2Ind = (IndexType)std::ceil(fc2 / df);
+        if (useSourceEncode == 0) {
+            fc1Ind = (IndexType)std::ceil((ValueType)fc1Ind / 2);
+            fc2Ind *= 2;
+            if (fc1Ind == 0)
+                fc1Ind = 1;
+            for (IndexType k = 0; k < fc2Ind - fc1Ind + 1; k++)
+                fc12.push_back(fc1Ind * df + k * df);
+            sourceFC.assign(numshotsIncr, fc12);
+        } else {
+            if (fc1Ind == 0)
+                fc1Ind = 2;
+            if (fc1Ind % 2 == 1)
+                fc1Ind += 1;
+            const IndexType nfc12 = (IndexType)std::ceil(ValueType(fc2Ind - fc1Ind + 1) / 2);
+            for (IndexType k = 0; k < nfc12; k++)
+                fc12.push_back(fc1Ind * df + k * 2 * df);
+        }
+    }
     sourceSettingsEncode.clear();
     if (useSourceEncode == 0)
         return;
     sourceSettingsEncode = allSourceSettings;
     const IndexType numShotDomains = config.get<IndexType>("NumShotDomains"); // the number of supershots
     const IndexType numShotPerSuperShot = (IndexType)std::ceil(ValueType(numshotsIncr) / numShotDomains);
+    if (gradientDomain != 0)
+        SCAI_ASSERT_ERROR((IndexType)fc12.size() >= numShotPerSuperShot, "The number of frequency is less than numShotPerSuperShot!")
     std::srand(seedtime);
     seedtime++;
     std::vector<IndexType> shotHistory(numShotDomains, 0);
@@ -744,6 +776,62 @@ template <typename ValueType> void Acquisition::Sources<ValueType>::calcSourceSe
             sourceSettingsEncode[shotInd].sourceNo = base + shotInd / numShotPerSuperShot;
     } else
         COMMON_THROWEXCEPTION("useSourceEncode must be 0, 1, 2 or 3")
+    if (gradientDomain != 0) { // Sources.cpp:648-674: every shot of a supershot fires a sine of its own, randomly drawn frequency
+        std::vector<IndexType> uniqueShotNosEncode;
+        calcuniqueShotNo(uniqueShotNosEncode, sourceSettingsEncode);
+        std::vector<ValueType> uniqueFC(numShotPerSuperShot, ValueType(0));
+        const IndexType nfc12 = (IndexType)fc12.size();
+        for (IndexType shotIndEncode = 0; shotIndEncode < numShotDomains && shotIndEncode < (IndexType)uniqueShotNosEncode.size(); shotIndEncode++) {
+            std::vector<IndexType> fc12History(nfc12, 0);
+            IndexType jf = 0;
+            for (IndexType shotInd = 0; shotInd < numshotsIncr; shotInd++) {
+                if (std::abs(sourceSettingsEncode[shotInd].sourceNo) != uniqueShotNosEncode[shotIndEncode])
+                    continue;
+                sourceSettingsEncode[shotInd].waveletType = 1;  // synthetic signal
+                sourceSettingsEncode[shotInd].waveletShape = 9; // sin(t)
+                IndexType fcInd = std::rand() % nfc12;
+                while (fc12History[fcInd] > 0)
+                    fcInd = std::rand() % nfc12;
+                fc12History[fcInd]++;
+                sourceSettingsEncode[shotInd].fc = fc12[fcInd];
+                uniqueFC[jf++] = fc12[fcInd];
+            }
+            sourceFC.push_back(uniqueFC);
+        }
+    }
+}
+
+// <SourceFilename>.sourceFC.txt (Sources.cpp:801-846)
+template <typename ValueType> void Acquisition::Sources<ValueType>::writeSourceFC(Configuration::Configuration const &config, IndexType stage, IndexType iteration) const
+{
+    const IndexType gradientDomain = config.getAndCatch("gradientDomain", 0), useSourceEncode = config.getAndCatch("useSourceEncode", 0);
+    if (gradientDomain == 0 || sourceFC.empty())
+        return;
+    std::string filename = config.get<std::string>("SourceFilename");
+    if (config.getAndCatch("useStreamConfig", false))
+        filename = Configuration::Configuration(config.get<std::string>("streamConfigFilename")).get<std::string>("SourceFilename");
+    if (stage != 0)
+        filename += ".stage_" + std::to_string(stage) + ".It_" + std::to_string(iteration);
+    std::ofstream out(filename + ".sourceFC.txt");
+    out << "# Shot frequency used in the frequency domain gradient (gradientDomain = " << gradientDomain << ", useSourceEncode = " << useSourceEncode
+        << ", numShotDomains = " << config.get<IndexType>("NumShotDomains") << ", NF = " << sourceFC[0].size() << ")\n# Shot number | frequency (Hz)\n";
+    if (useSourceEncode == 0) {
+        out << std::setw(13) << allSourceSettings[0].sourceNo;
+        for (ValueType f : sourceFC[0])
+            out << std::setw(14) << f;
+        out << "\n";
+        return;
+    }
+    std::vector<IndexType> uniqueShotNosEncode;
+    calcuniqueShotNo(uniqueShotNosEncode, sourceSettingsEncode);
+    SCAI_ASSERT_ERROR(sourceSettingsEncode.size() == shotIndsIncr.size(), "sourceSettingsEncode.size() != shotIndsIncr.size()")
+    for (auto no : uniqueShotNosEncode) {
+        out << std::setw(13) << no;
+        for (auto const &e : sourceSettingsEncode)
+            if (std::abs(e.sourceNo) == no)
+                out << std::setw(14) << e.fc;
+        out << "\n";
+    }
 }
 
 void Acquisition::getRandomShotInds(std::vector<IndexType> &uniqueShotInds, std::vector<IndexType> &shotHistory, IndexType numshots, IndexType maxcount, IndexType useRandomSource,
@@ -1172,13 +1260,18 @@ void Acquisition::Receivers<ValueType>::encode(Configuration::Configuration cons
                 if (std::abs(sourceSettingsEncode[k].sourceNo) == shotNumber)
                     dataDecode.emplace_back();
         }
-        auto const finish = [&](std::vector<ValueType> &traces, IndexType rows, sourceSettings<ValueType> const &enc) { // polarity and frequency of the shot
+        // polarity and frequency of the shot; rows = 0: ONE trace through the vector form of the filter (common-offset branch of the reference),
+        // else the matrix form (which scales the decoded matrix to maximum amplitude 1, Filter.cpp:331-341)
+        auto const finish = [&](std::vector<ValueType> &traces, IndexType rows, sourceSettings<ValueType> const &enc) {
             if (enc.amp < 0)
                 for (auto &v : traces)
                     v = -v;
             if (gradientDomain != 0) {
                 freqFilter.calc("ideal", "bp", 1, enc.fc);
-                freqFilter.apply(traces, rows, NT);
+                if (rows == 0)
+                    freqFilter.apply(traces);
+                else
+                    freqFilter.apply(traces, rows, NT);
             }
         };
         if (numshots == numrecs) { // common-offset data: receiver k belongs to shot k, one trace per shot
@@ -1204,7 +1297,7 @@ void Acquisition::Receivers<ValueType>::encode(Configuration::Configuration cons
                     }
                     if (markOf(row, row + 1) != 0) {
                         std::vector<ValueType> trace(dataSingle);
-                        finish(trace, 1, sourceSettingsEncode[k]);
+                        finish(trace, 0, sourceSettingsEncode[k]);
                         for (IndexType t = 0; t < NT; t++)
                             data[(size_t)countEncode * NT + t] += trace[t];
                     }
@@ -1212,7 +1305,7 @@ void Acquisition::Receivers<ValueType>::encode(Configuration::Configuration cons
                     SCAI_ASSERT_ERROR(countDecode < (IndexType)dataDecode.size(), "more marked shots than shots of the supershot")
                     if (markOf(row, row + 1) != 0) {
                         std::vector<ValueType> trace(data.begin() + (size_t)countEncode * NT, data.begin() + (size_t)(countEncode + 1) * NT);
-                        finish(trace, 1, sourceSettingsEncode[k]);
+                        finish(trace, 0, sourceSettingsEncode[k]);
                         dataSingle = trace;
                     }
                     dataDecode[countDecode] = dataSingle;

@@ -193,7 +193,11 @@ namespace KITGPI
             std::vector<IndexType> const &getShotIndsIncr() const { return shotIndsIncr; }
             //! useSourceEncode 1 / 2 / 3: the shots are merged into NumShotDomains supershots (random with random polarity / interleaved
             //! / blockwise; Sources.cpp:568-646, time-domain part)
-            void calcSourceSettingsEncode(Configuration::Configuration const &config, IndexType &seedtime);
+            //! gradientDomain != 0 adds the frequency bookkeeping of the inversion's frequency-domain gradient (Sources.cpp:584-612, 648-674): the
+            //! frequency list per shot (getSourceFC) and, with encoding, a sine source of its own frequency for every shot of a supershot
+            void calcSourceSettingsEncode(Configuration::Configuration const &config, IndexType &seedtime, ValueType fc1 = 0, ValueType fc2 = 0);
+            std::vector<std::vector<ValueType>> const &getSourceFC() const { return sourceFC; }
+            void writeSourceFC(Configuration::Configuration const &config, IndexType stage = 0, IndexType iteration = 0) const; // <SourceFilename>.sourceFC.txt
             std::vector<sourceSettings<ValueType>> const &getSourceSettingsEncode() const { return sourceSettingsEncode; }
             //! the shot indices one pass over the shot domains works on (Sources.cpp:687-714)
             void calcUniqueShotInds(Configuration::Configuration const &config, std::vector<IndexType> &shotHistory, IndexType maxcount, IndexType &seedtime);
@@ -207,6 +211,7 @@ namespace KITGPI
           private:
             std::vector<sourceSettings<ValueType>> allSourceSettings; // after the shotIncr selection (sourceSettingsShotIncr of the reference)
             std::vector<sourceSettings<ValueType>> sourceSettingsEncode;
+            std::vector<std::vector<ValueType>> sourceFC;
             std::vector<IndexType> shotIndsIncr, uniqueShotInds;
         };
 

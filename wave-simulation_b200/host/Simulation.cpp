@@ -316,6 +316,7 @@ int main(int argc, const char *argv[])
         SCAI_ASSERT_ERROR(numshots >= wantedDomains || survey.useSourceEncode != 0, "numshots = " << numshots << ", numShotDomains = " << wantedDomains)
         // (Simulation.cpp:270-272 insists on numshots % NumShotDomains == 0; the block distribution below copes with a remainder)
         sources.writeShotIndsIncr(config, uniqueShotNos);
+        sources.writeSourceFC(config); // Simulation.cpp:273
         sources.writeSourceEncode(config);
         if (survey.useStreamConfig)
             Acquisition::writeCutCoordToFile(config, configBig.get<std::string>("SourceFilename"), survey.cutCoordinates, uniqueShotNos, config.get<IndexType>("NX"));
