@@ -107,6 +107,23 @@ int main(int argc, char **argv)
         EXPECT(std::abs(mx - AMP) < 1e-4 && s[50] == 0);
         EXPECT_THROW(Acquisition::SourceSignal::calc(17, s, NT, DT, FC, AMP, TS));
     }
+    // ---- AcquisitionUnitTest.cpp:9-32, AcousticUnitTest.cpp:12-25, ReceiversUnitTest.cpp:11-25: enumeration and names of the seismogram
+    //      types; model / receiver initialisation from a configuration that lacks their keys throws
+    {
+        EXPECT(Acquisition::P == 0 && Acquisition::VX == 1 && Acquisition::VY == 2 && Acquisition::VZ == 3);
+        EXPECT(std::string(Acquisition::SeismogramTypeString[Acquisition::P]) == "p" && std::string(Acquisition::SeismogramTypeString[Acquisition::VX]) == "vx" &&
+               std::string(Acquisition::SeismogramTypeString[Acquisition::VY]) == "vy" && std::string(Acquisition::SeismogramTypeString[Acquisition::VZ]) == "vz");
+        EXPECT(Acquisition::NUM_ELEMENTS_SEISMOGRAMTYPE == 4);
+        std::ofstream f(dir + "/configuration_bare.txt");
+        f << "NX=10\nNY=10\nNZ=1\nDH=50\n";
+        f.close();
+        Configuration::Configuration bare(dir + "/configuration_bare.txt");
+        Acquisition::Coordinates<ValueType> coords(bare.get<IndexType>("NX"), bare.get<IndexType>("NY"), bare.get<IndexType>("NZ"), bare.get<ValueType>("DH"));
+        Modelparameter::Modelparameter<ValueType> acoustic("acoustic");
+        EXPECT_THROW(acoustic.init(bare, coords));
+        Acquisition::Receivers<ValueType> receivers;
+        EXPECT_THROW(receivers.init(bare, coords));
+    }
     // ---- acquisition files
     {
         std::ofstream f(dir + "/sources.txt");
