@@ -58,7 +58,8 @@ typedef struct ws_desc {
     int32_t fd_order;       /* 2,4,...,12                             key: spatialFDorder                      */
     int32_t edge_policy;    /* 0 = off-grid taps dropped (useStencilMatrix=1, Derivatives.cpp:112-121)
                                1 = order reduced towards the edge (sparse matrices, Derivatives.cpp:129-186)  */
-    int32_t free_surface;   /* 1 = image method (FreeSurface==1), else 0                                       */
+    int32_t free_surface;   /* key FreeSurface: 0 off | 1 image method | 2 improved vacuum formulation (plain operators;
+                               like 1, no absorbing frame at the top: ABS3D.cpp:197, CPML3D.cpp tests == 0)    */
     int32_t damping;        /* 0 none | 1 ABS | 2 CPML                key: DampingBoundary                     */
     int32_t boundary_width; /*                                        key: BoundaryWidth                       */
     float damping_coeff;    /*                                        key: DampingCoeff                        */

@@ -92,6 +92,9 @@ SWEEP = [
     ("tmem", 2, 40, 36, 1, 8, 0, 0, 2, 8, 0), ("viscotmem", 2, 40, 36, 1, 4, 1, 0, 2, 8, 2), ("tmem", 2, 40, 36, 1, 2, 1, 0, 1, 8, 0),
     ("emem", 2, 40, 36, 1, 8, 0, 0, 2, 8, 0), ("viscoemem", 2, 40, 36, 1, 4, 1, 0, 2, 8, 2), ("emem", 3, 20, 22, 18, 4, 0, 0, 2, 6, 0),
     ("viscoemem", 3, 20, 22, 18, 8, 1, 0, 2, 6, 2), ("emem", 3, 20, 22, 18, 2, 1, 0, 1, 6, 0),
+    # FreeSurface = 2 (improved vacuum formulation: no image method, no absorbing frame at the top; ABS*/CPML*::init test useFreeSurface == 0)
+    ("elastic", 2, 40, 36, 1, 8, 1, 2, 2, 8, 0), ("elastic", 3, 20, 22, 18, 4, 0, 2, 1, 6, 0), ("acoustic", 2, 40, 36, 1, 4, 0, 2, 2, 8, 0),
+    ("viscoelastic", 3, 20, 22, 18, 4, 0, 2, 2, 6, 1),
 ]
 
 

@@ -36,7 +36,7 @@ def test_emulated_kernels_fma_mode(cfg):
 
 
 # every equation type once (the GPU suite runs the whole sweep)
-MARCH_EMU = [c for k, c in enumerate(SWEEP) if k in (0, 2, 3, 6, 8, 9, 11, 12, 14, 15, 17, 18, 19, 20)]
+MARCH_EMU = [c for k, c in enumerate(SWEEP) if k in (0, 2, 3, 6, 8, 9, 11, 12, 14, 15, 17, 18, 19, 20, 22, 23)]
 
 
 @pytest.mark.parametrize("cfg", MARCH_EMU, ids=[sweep_id(c) for c in MARCH_EMU])

@@ -157,6 +157,29 @@ def test_driver_sparse_policy_lmf_and_oracle(driver, tmp_path):
     assert rel_l2(s, o.seismogram()) <= 1.0e-5
 
 
+def test_driver_free_surface_vacuum_formulation(driver, tmp_path):
+    """FreeSurface = 2 (improved vacuum formulation): plain derivative operators and, as with the image method, no absorbing frame at the
+    top (ABS2D.cpp:158 tests useFreeSurface == 0); compared with the oracle run with the same setting and told apart from FreeSurface = 1."""
+    tmp = str(tmp_path)
+    cfg = setup_case(tmp, T=0.8)
+    text = open(cfg).read()
+    open(cfg, "w").write(text.replace("FreeSurface=1", "FreeSurface=2"))
+    run(driver, cfg, tmp)
+    s = read_mtx(os.path.join(tmp, "seismograms", "seismogram.shot_1.vy.mtx"))
+    case = ci_case("2D.elastic", nt=400)
+    case.desc.edge_policy = 0
+    image = case.setup(Oracle(case.desc))
+    image.run(0, 400)
+    case.desc.free_surface = 2
+    o = case.setup(Oracle(case.desc))
+    o.run(0, 400)
+    assert rel_l2(s, o.seismogram()) <= 1.0e-5
+    assert rel_l2(s, image.seismogram()) > 1.0e-2
+    open(cfg, "w").write(text.replace("FreeSurface=1", "FreeSurface=3"))
+    p = run(driver, cfg, tmp, expect_ok=False)
+    assert p.returncode != 0 and "FreeSurface must be" in p.stderr
+
+
 def test_driver_multishot_receivers_per_shot_resampling_normalisation_snapshots(driver, tmp_path):
     tmp = str(tmp_path)
     src = "1 20 0 0 2 1 1 5.0 5.0 0.0\n2 40 5 0 1 1 1 8.0 1.0 0.0\n-2 60 5 0 3 1 4 6.0 2.0 0.05\n"

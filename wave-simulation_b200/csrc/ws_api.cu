@@ -477,6 +477,7 @@ void validateDesc(const ws_desc &d)
     WS_REQUIRE(d.fd_order >= 2 && d.fd_order <= WS_MAXQ && d.fd_order % 2 == 0, WS_EINVAL,
                "spatialFDorder = " + std::to_string(d.fd_order) + " Unsupported spatialFDorder value.");
     WS_REQUIRE(d.edge_policy == 0 || d.edge_policy == 1, WS_EINVAL, "edge_policy must be 0 or 1");
+    WS_REQUIRE(d.free_surface >= 0 && d.free_surface <= 2, WS_EINVAL, "FreeSurface must be 0, 1 or 2");
     WS_REQUIRE(d.damping >= 0 && d.damping <= 2, WS_EINVAL, "DampingBoundary must be 0, 1 or 2");
     if (d.damping) {
         WS_REQUIRE(d.boundary_width > 0, WS_EINVAL, "BoundaryWidth must be positive");
@@ -1819,9 +1820,9 @@ int ws_prepare(ws_solver *s)
             s->tmaMaps = nullptr;
         }
         s->P.tmaMaps = nullptr;
-        // (2-D grids stay on the cp.async marching kernels by default: their strips stage 512 bytes per array and plane, and the
+        // (2-D grids do not take the TMA MARCHING kernels by default: their strips stage 512 bytes per array and plane, and the
         // TMA ring then holds fewer resident warps per SM than the cp.async kernels do; measured 30 against 41 Gpt/s on 2-D elastic
-        // 4096^2, profiles/r02_tma_sweep.txt)
+        // 4096^2, profiles/r02_tma_sweep.txt.  They run on the 2-D tile kernels below.)
         s->useTma = ((!s->useFast && s->d.kernel_variant == 0 && s->d.dim == 3) || s->d.kernel_variant == 3) && wsTmaSupported(s->P, s->ainfo, s->exact);
         if (s->useTma) {
             s->useFast = false;

@@ -48,7 +48,7 @@ template <typename ValueType> void Derivatives<ValueType>::init(Configuration::C
     edgePolicy = config.getAndCatch("edgePolicy", useStencilMatrix ? 0 : 1);
     SCAI_ASSERT_ERROR(edgePolicy == 0 || edgePolicy == 1, "edgePolicy must be 0 or 1")
     useFreeSurface = config.get<IndexType>("FreeSurface");
-    SCAI_ASSERT_ERROR(useFreeSurface == 0 || useFreeSurface == 1, "FreeSurface=" << useFreeSurface << " (improved vacuum formulation) is not available in the B200 path")
+    SCAI_ASSERT_ERROR(useFreeSurface >= 0 && useFreeSurface <= 2, "FreeSurface must be 0, 1 (image method) or 2 (improved vacuum formulation)")
 }
 
 template <typename ValueType> typename Derivatives<ValueType>::DerivativesPtr Factory<ValueType>::Create(std::string dimension)

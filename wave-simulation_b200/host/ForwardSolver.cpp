@@ -35,7 +35,10 @@ namespace
         d.nt = Common::time2index(config.get<ValueType>("T"), d.dt); // Simulation.cpp:304
         d.fd_order = config.get<IndexType>("spatialFDorder");
         d.edge_policy = config.getAndCatch("edgePolicy", config.getAndCatch("useStencilMatrix", 0) ? 0 : 1);
-        d.free_surface = config.get<IndexType>("FreeSurface") == 1 ? 1 : 0;
+        // 0 = off, 1 = image method, 2 = improved vacuum formulation: plain operators (the vacuum is part of the model: averaged shear moduli
+        // below 4 Pa become 0, ModelparameterSeismic.cpp:430) and, as with 1, no absorbing frame at the top (ABS*::init / CPML*::init test == 0)
+        d.free_surface = config.get<IndexType>("FreeSurface");
+        SCAI_ASSERT_ERROR(d.free_surface >= 0 && d.free_surface <= 2, "FreeSurface must be 0, 1 or 2")
         d.damping = config.get<IndexType>("DampingBoundary");
         d.boundary_width = config.getAndCatch("BoundaryWidth", 0);
         d.damping_coeff = config.getAndCatch("DampingCoeff", ValueType(0));
@@ -147,7 +150,7 @@ void ForwardSolver::ForwardSolver<ValueType>::initIrregular(Configuration::Confi
     if (d.damping == 2)
         for (IndexType axis = 0; axis < (d3 ? 3 : 2); axis++) {
             const IndexType ax = (!d3 && axis == 1) ? 1 : axis; // 2-D: axes x, y
-            const CpmlProfile p = ops.cpml(ax, d.boundary_width, d.npower, d.fc_cpml, d.vmax_cpml, fs);
+            const CpmlProfile p = ops.cpml(ax, d.boundary_width, d.npower, d.fc_cpml, d.vmax_cpml, d.free_surface != 0);
             check(ws_set_cpml_profile(h, (int32_t)ax, (int64_t)p.idx.size(), p.idx.data(), p.a.data(), p.b.data(), p.aHalf.data(), p.bHalf.data()));
         }
     if (fs) {
