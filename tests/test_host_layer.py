@@ -261,6 +261,13 @@ def test_driver_su_seismograms(driver, tmp_path):
     run(driver, cfg, tmp)
     again = read_mtx(os.path.join(tmp, "seismograms", "seismogram.shot_1.vy.mtx"))
     assert np.array_equal(again, mtx)
+    # ... and with receivers per shot from <ReceiverFilename>.shot_<n>.<comp>.su (Receivers.cpp:229-246)
+    os.rename(os.path.join(tmp, "acq_su", "rec.vy.su"), os.path.join(tmp, "acq_su", "rec.shot_1.vy.su"))
+    os.remove(os.path.join(tmp, "seismograms", "seismogram.shot_1.vy.mtx"))
+    text = open(cfg).read().replace("useReceiversPerShot=0", "useReceiversPerShot=1")
+    open(cfg, "w").write(text)
+    run(driver, cfg, tmp)
+    assert np.array_equal(read_mtx(os.path.join(tmp, "seismograms", "seismogram.shot_1.vy.mtx")), mtx)
 
 
 def test_two_layer_tool_feeds_the_driver(driver, tmp_path):
@@ -793,12 +800,12 @@ def test_driver_source_encoding(driver, tmp_path):
     useReceiversPerShot = 2 (Receivers.cpp:365): a supershot records the union of the receivers its shots mark, and is decoded into
     per-shot seismograms (the marked receivers of the shot, polarity undone) after the time loop (Simulation.cpp:531-533)."""
     plain = str(tmp_path / "plain")
-    run(driver, setup_case(plain, sources=FOUR_SHOTS, receivers=TWO_RECEIVERS, T=0.5), plain)
+    run(driver, setup_case(plain, sources=FOUR_SHOTS, receivers=TWO_RECEIVERS, T=0.4), plain)
     single = seismograms_of(plain)
     assert sorted(single) == [1, 2, 3, 4]
     for mode, groups in ((2, {20001: [1, 3], 20002: [2, 4]}), (3, {20001: [1, 2], 20002: [3, 4]})):
         tmp = str(tmp_path / ("mode%d" % mode))
-        cfg = with_keys(setup_case(tmp, sources=FOUR_SHOTS, receivers=TWO_RECEIVERS, T=0.5, rps=2), useSourceEncode=mode, NumShotDomains=2, seedtime=7)
+        cfg = with_keys(setup_case(tmp, sources=FOUR_SHOTS, receivers=TWO_RECEIVERS, T=0.4, rps=2), useSourceEncode=mode, NumShotDomains=2, seedtime=7)
         write_mark(tmp, MARKS, coordinate=(mode == 3))
         run(driver, cfg, tmp)
         enc = seismograms_of(tmp)
@@ -815,7 +822,7 @@ def test_driver_source_encoding(driver, tmp_path):
     res = []
     for rep in range(2):
         tmp = str(tmp_path / ("mode1_%d" % rep))
-        cfg = with_keys(setup_case(tmp, sources=FOUR_SHOTS, receivers=TWO_RECEIVERS, T=0.5, rps=2), useSourceEncode=1, NumShotDomains=2, seedtime=11)
+        cfg = with_keys(setup_case(tmp, sources=FOUR_SHOTS, receivers=TWO_RECEIVERS, T=0.4, rps=2), useSourceEncode=1, NumShotDomains=2, seedtime=11)
         write_mark(tmp, [[k + 1, 1, 1] for k in range(4)])
         run(driver, cfg, tmp)
         enc = seismograms_of(tmp)
@@ -875,10 +882,10 @@ def test_driver_receivers_by_mark_matrix(driver, tmp_path):
     """useReceiversPerShot = 2: one receiver file and a mark matrix; every shot records the receivers its row marks (here also with the
     shot increment: the rows of the mark matrix are those of the source file, not of the selection)."""
     plain = str(tmp_path / "plain")
-    run(driver, setup_case(plain, sources=FOUR_SHOTS, receivers=TWO_RECEIVERS, T=0.3), plain)
+    run(driver, setup_case(plain, sources=FOUR_SHOTS, receivers=TWO_RECEIVERS, T=0.12), plain)
     single = seismograms_of(plain)
     tmp = str(tmp_path / "marks")
-    write_mark_for = setup_case(tmp, sources=FOUR_SHOTS, receivers=TWO_RECEIVERS, T=0.3, rps=2)
+    write_mark_for = setup_case(tmp, sources=FOUR_SHOTS, receivers=TWO_RECEIVERS, T=0.12, rps=2)
     write_mark(tmp, MARKS)
     run(driver, write_mark_for, tmp)
     got = seismograms_of(tmp)
@@ -887,7 +894,7 @@ def test_driver_receivers_by_mark_matrix(driver, tmp_path):
         assert np.array_equal(got[no], single[no][np.array(MARKS[no - 1][1:]) != 0]), no
     assert not [f for f in os.listdir(os.path.join(tmp, "acq")) if f.endswith(".mark.mtx") and "shot_" in f]  # marks are written with the encoding only
     tmp = str(tmp_path / "incr")  # shots 12 grid points = 600 m apart: shotIncr 1200 keeps shots 1 and 3 (rows 0 and 2)
-    cfg = with_keys(setup_case(tmp, sources=FOUR_SHOTS, receivers=TWO_RECEIVERS, T=0.3, rps=2), shotIncr=1200)
+    cfg = with_keys(setup_case(tmp, sources=FOUR_SHOTS, receivers=TWO_RECEIVERS, T=0.12, rps=2), shotIncr=1200)
     write_mark(tmp, [[1, 0, 1], [2, 1, 0], [3, 1, 1], [4, 1, 1]], coordinate=True)
     run(driver, cfg, tmp)
     got = seismograms_of(tmp)
@@ -905,26 +912,26 @@ def test_driver_random_shots_and_shot_increment(driver, tmp_path):
     """Four shots of one source each, recorded by two receivers (a file per shot) or by one (the traces are gathered into a
     common-offset profile, summed over the shot domains: SeismogramHandler::sumShotDomain)."""
     plain = str(tmp_path / "plain")
-    run(driver, setup_case(plain, sources=FOUR_SHOTS, receivers=TWO_RECEIVERS, T=0.3), plain)
+    run(driver, setup_case(plain, sources=FOUR_SHOTS, receivers=TWO_RECEIVERS, T=0.12), plain)
     single = seismograms_of(plain)
-    assert sorted(single) == [1, 2, 3, 4] and single[1].shape == (2, 150)
+    assert sorted(single) == [1, 2, 3, 4] and single[1].shape == (2, 60)
     for mode in (1, 2, 3):  # two passes of two shots each: every shot exactly once (maxcount = 1)
         tmp = str(tmp_path / ("rand%d" % mode))
-        run(driver, with_keys(setup_case(tmp, sources=FOUR_SHOTS, receivers=TWO_RECEIVERS, T=0.3), useRandomSource=mode, NumShotDomains=2, seedtime=3), tmp)
+        run(driver, with_keys(setup_case(tmp, sources=FOUR_SHOTS, receivers=TWO_RECEIVERS, T=0.12), useRandomSource=mode, NumShotDomains=2, seedtime=3), tmp)
         got = seismograms_of(tmp)
         assert sorted(got) == [1, 2, 3, 4]
         assert all(np.array_equal(got[k], single[k]) for k in got)
     # one receiver: common-offset profile (and the profile of the source signals with writeSource), one and two shot domains
     for domains in (1, 2):
         tmp = str(tmp_path / ("cop%d" % domains))
-        cfg = with_keys(setup_case(tmp, sources=FOUR_SHOTS, receivers="30 2 0 3\n", T=0.3), NumShotDomains=domains, writeSource=1, writeSourceFilename="seismograms/source")
+        cfg = with_keys(setup_case(tmp, sources=FOUR_SHOTS, receivers="30 2 0 3\n", T=0.12), NumShotDomains=domains, writeSource=1, writeSourceFilename="seismograms/source")
         run(driver, cfg, tmp)
         assert sorted(os.listdir(os.path.join(tmp, "seismograms"))) == ["seismogram.vy.mtx", "source.vx.mtx"]
         got = seismograms_of(tmp, cop=[1, 2, 3, 4])
         assert all(np.array_equal(got[k], single[k][0:1]) for k in got)
         src = read_mtx(os.path.join(tmp, "seismograms", "source.vx.mtx"))
         from wsharness import ricker
-        assert src.shape == (4, 150) and all(rel_l2(src[k], ricker(150, 2e-3, 5.0, 5.0 + k, 0.0)) <= 1e-6 for k in range(4))
+        assert src.shape == (4, 60) and all(rel_l2(src[k], ricker(60, 2e-3, 5.0, 5.0 + k, 0.0)) <= 1e-6 for k in range(4))
     # shotIncr = 200 m on a line of shots 2 grid points (100 m) apart: every second shot (Sources.cpp:516-553)
     tmp = str(tmp_path / "incr")
     six = "".join("%d %d 0 0 2 1 1 5.0 5.0 0.0\n" % (k + 1, 20 + 2 * k) for k in range(6))

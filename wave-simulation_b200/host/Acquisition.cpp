@@ -1118,8 +1118,13 @@ template <typename ValueType> void Acquisition::Receivers<ValueType>::init(Confi
 template <typename ValueType>
 void Acquisition::Receivers<ValueType>::init(Configuration::Configuration const &config, Coordinates<ValueType> const &modelCoordinates, IndexType shotNumber)
 {
+    // Receivers.cpp:229-246: <ReceiverFilename>.shot_<n> as a text file or, with initReceiverFromSU, as SU files per component
     std::vector<receiverSettings> all;
-    readAllSettings(all, config.get<std::string>("ReceiverFilename") + ".shot_" + std::to_string(shotNumber) + ".txt");
+    const std::string name = config.get<std::string>("ReceiverFilename") + ".shot_" + std::to_string(shotNumber);
+    if (config.getAndCatch("initReceiverFromSU", false))
+        readReceiverSettingsFromSU<ValueType>(all, name, config.get<ValueType>("DH"));
+    else
+        readAllSettings(all, name + ".txt");
     init(all, config, modelCoordinates);
 }
 
