@@ -89,10 +89,19 @@ def read_lmf_matrix(path):
 
 
 @pytest.fixture(scope="module")
-def driver():
+def driver(tmp_path_factory):
     build_emu()
     subprocess.check_call(["make", "-s", "-C", HOST, "libSimulation_host.a", "Simulation.o"])
     subprocess.check_call(["make", "-s", "-C", HOST, "emu"])
+    if os.environ.get("WS_HOST_SANITIZE"):
+        # WS_HOST_SANITIZE=1 pytest tests/test_host_layer.py -m "not gpu": the same driver tests on a build of the host layer with the address,
+        # leak and undefined-behaviour sanitizers (any report ends the run with a non-zero exit code, which the tests check)
+        out = str(tmp_path_factory.mktemp("sanitize"))
+        srcs = [f for f in sorted(os.listdir(HOST)) if f.endswith(".cpp")]
+        subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-fno-omit-frame-pointer", "-pthread",
+                               "-I" + HOST] + [os.path.join(HOST, f) for f in srcs] + ["-L" + EMU_DIR, "-lwavesim_emu", "-Wl,-rpath," + EMU_DIR, "-fopenmp", "-o",
+                                                                                      os.path.join(out, "Simulation_sanitize")])
+        return os.path.join(out, "Simulation_sanitize")
     return os.path.join(EMU_DIR, "Simulation_emu")
 
 
