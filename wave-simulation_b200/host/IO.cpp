@@ -179,10 +179,10 @@ namespace
                              {"gelev", 40, 'i'},  {"selev", 44, 'i'},  {"sdepth", 48, 'i'},  {"gdel", 52, 'i'},   {"sdel", 56, 'i'},    {"swdep", 60, 'i'},
                              {"gwdep", 64, 'i'},  {"scalel", 68, 'h'}, {"scalco", 70, 'h'},  {"sx", 72, 'i'},     {"sy", 76, 'i'},      {"gx", 80, 'i'},
                              {"gy", 84, 'i'},     {"counit", 88, 'h'}, {"ns", 114, 'u'},     {"dt", 116, 'u'},    {"d1", 180, 'f'},     {"ntr", 204, 'i'}};
-    const SuKey &suKey(std::string const &name)
+    const SuKey &suKey(const char *name) // a reference into the static table above
     {
         for (auto const &k : kSuKeys)
-            if (name == k.name)
+            if (std::strcmp(name, k.name) == 0)
                 return k;
         COMMON_THROWEXCEPTION("unknown SU header word " << name)
     }
@@ -288,7 +288,7 @@ double KITGPI::SUIO::readHeaderWordSU(std::string const &filename, IndexType tra
     in.seekg((std::streamoff)trace * (240 + (std::streamoff)sizeof(float) * ns));
     in.read(reinterpret_cast<char *>(hdr), 240);
     SCAI_ASSERT_ERROR(in.good(), name << " has no trace " << trace)
-    return suGet(hdr, suKey(key));
+    return suGet(hdr, suKey(key.c_str()));
 }
 
 IndexType KITGPI::SUIO::numTracesSU(std::string const &filename)
