@@ -191,6 +191,9 @@ int ws_set_operator(ws_solver *s, const char *name, int32_t max_taps, const int3
 int ws_set_interpolation(ws_solver *s, const char *name, int64_t n_rows, const int32_t *rows, int32_t max_taps, const int32_t *cols, const float *vals);
 /* CPML coefficients of one axis (0 x, 1 y, 2 z) as the reference's sparse vectors a, b, a_half, b_half on the points idx[]        */
 int ws_set_cpml_profile(ws_solver *s, int32_t axis, int64_t n, const int32_t *idx, const float *a, const float *b, const float *a_half, const float *b_half);
+/* ABS frame (DampingBoundary = 1) as the reference's sparse vector `damping` (ABS2D.cpp:110-178, ABS3D.cpp:154-218): the wavefields
+ * are multiplied by damping[k] on the points idx[k] after the pressure update                                                   */
+int ws_set_abs_profile(ws_solver *s, int64_t n, const int32_t *idx, const float *damping);
 /* points of the free surface (FreeSurface::setSurfaceZero, FreeSurface.cpp:13-20)                                                 */
 int ws_set_surface(ws_solver *s, int64_t n, const int32_t *idx);
 

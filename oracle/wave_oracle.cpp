@@ -1245,7 +1245,8 @@ struct Oracle {
     // ABS3D.cpp:154-218, ABS2D.cpp:115-178
     void initABS()
     {
-        ORACLE_REQUIRE(!vg.active, "variable grid: the ABS frame is not restated (the reference's CI uses CPML there)");
+        // variable grid: the same rule on the coordinates of the points (index2coordinate + edgeDistance work in units of the finest spacing, so a
+        // coarse layer picks every dhFactor-th coefficient)
         const int W = d.boundary_width;
         damping.assign(N, (T)1.0);
         vector<T> coeff(W);

@@ -559,9 +559,9 @@ def setup_vargrid_case(tmp, dim, T, pol=0, exact=1):
     return cfg
 
 
-def _oracle_vargrid(dim, nt, pol=0):
+def _oracle_vargrid(dim, nt, pol=0, **kw):
     from test_oracle_golden import vargrid_ci_case
-    o, gname = vargrid_ci_case(dim, nt, edge_policy=pol)
+    o, gname = vargrid_ci_case(dim, nt, edge_policy=pol, **kw)
     o.run(0, nt)
     s = o.seismogram()
     o.close()
@@ -587,6 +587,40 @@ def test_driver_variable_grid_2d_reproduces_oracle_and_golden(driver, tmp_path):
     run(driver, cfg, tmp)
     s = read_lmf_matrix(os.path.join(tmp, "seismograms", "seismogram.shot_0.p.lmf"))
     ref, _ = _oracle_vargrid(2, 300, pol=1)
+    assert np.array_equal(s, ref)
+
+
+def _vargrid_abs_case(tmp, free_surface, T=1.0):
+    cfg = setup_vargrid_case(tmp, 2, T)
+    text = open(cfg).read().replace("DampingBoundary=2", "DampingBoundary=1").replace("FreeSurface=1", "FreeSurface=%d" % free_surface)
+    open(cfg, "w").write(text)
+    return cfg
+
+
+def test_driver_variable_grid_abs_frame(driver, tmp_path):
+    """DampingBoundary = 1 on a variable grid: the Cerjan frame as the reference's sparse vector (ABS2D.cpp:110-178 on the coordinates of the
+    points: a coarse layer picks every third coefficient), applied before the interpolation of the pressure; bit-identical to the oracle
+    in exact-arithmetic mode, with and without a free surface."""
+    for fs in (1, 0):
+        tmp = str(tmp_path / ("fs%d" % fs))
+        os.makedirs(tmp)
+        run(driver, _vargrid_abs_case(tmp, fs), tmp)
+        s = read_lmf_matrix(os.path.join(tmp, "seismograms", "seismogram.shot_0.p.lmf"))
+        ref, _ = _oracle_vargrid(2, 500, damping=1, free_surface=fs)
+        assert s.shape == (4, 500) and np.abs(s).max() > 0
+        assert np.array_equal(s, ref), fs
+    undamped, _ = _oracle_vargrid(2, 500, damping=0, free_surface=0)
+    assert rel_l2(ref, undamped) > 1.0e-3  # the wave has reached the frame
+
+
+@pytest.mark.gpu
+def test_product_driver_variable_grid_abs_frame_on_gpu(tmp_path):
+    """The same on the CUDA library (operator-given mode with ws_set_abs_profile)."""
+    subprocess.check_call(["make", "-s", "-C", HOST])
+    tmp = str(tmp_path)
+    _run_product(_vargrid_abs_case(tmp, 1), tmp, {"WS_NUM_GPUS": "1"})
+    s = read_lmf_matrix(os.path.join(tmp, "seismograms", "seismogram.shot_0.p.lmf"))
+    ref, _ = _oracle_vargrid(2, 500, damping=1, free_surface=1)
     assert np.array_equal(s, ref)
 
 

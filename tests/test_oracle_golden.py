@@ -34,11 +34,12 @@ def test_oracle_reproduces_reference_golden(name, nt):
 VARGRID = dict(interfaces=[0, 30, 150, 200], dh_factors=[1, 3, 1, 3], fd_orders=[2, 6, 2, 6])  # par/ci/gridConfig.txt
 
 
-def vargrid_ci_case(dim, nt, edge_policy=0):
+def vargrid_ci_case(dim, nt, edge_policy=0, damping=2, free_surface=1):
     """par/ci/configuration_ci.{2D,3D}.acoustic.varGrid.txt: variable grid (dhFactor 1/3/1/3) with variable FD order (2/6/2/6),
     free surface + CPML(30), DH 17, homogeneous vp 3500 / rho 2000, P source and four P receivers at increasing depth."""
     from wsharness import OracleVarGrid, make_desc, ricker
-    common = dict(dh=17.0, dt=2e-3, nt=nt, fd_order=2, edge_policy=edge_policy, free_surface=1, damping=2, boundary_width=30, vmax_cpml=3500.0, fc_cpml=5.0, npower=4.0)
+    common = dict(dh=17.0, dt=2e-3, nt=nt, fd_order=2, edge_policy=edge_policy, free_surface=free_surface, damping=damping, boundary_width=30, damping_coeff=8.0,
+                  vmax_cpml=3500.0, fc_cpml=5.0, npower=4.0)
     if dim == 2:
         d = make_desc(2, "acoustic", 305, 303, 1, **common)
         src, recs, g = (150, 20, 0), [(150, 20, 0), (150, 90, 0), (150, 170, 0), (150, 239, 0)], "seismogram.2D.acoustic.varGrid.ref.p.mtx"

@@ -398,6 +398,9 @@ struct ws_solver {
     DevBuf<float> spVal[wssparse::SP_NOPS], spCa[3], spCb[3], spCah[3], spCbh[3], spPsi[wssparse::SPSI_COUNT], spTmp;
     int spTaps[wssparse::SP_NOPS] = {};
     long long spSurfN = 0;
+    DevBuf<int> spAbsIdx; // ABS frame in operator-given mode (ws_set_abs_profile)
+    DevBuf<float> spAbsVal;
+    long long spAbsN = 0;
     Interp spInterp[3]; // full grid, staggered in x, staggered in z
     // CUDA graph of one time step
     cudaGraphExec_t graphExec = nullptr;
@@ -1367,6 +1370,14 @@ void enqueueSparseStep(ws_solver *s, const float *srcStepDev, float *recStepDev,
     else
         WS_LAUNCH(wssparse::kPressure<false>, nb, 256, 0, s->stream, Q);
     s->launches++;
+    if (s->spAbsN > 0) { // DampingBoundary.apply(p, vX, vY[, vZ]) comes before the interpolation of p (ForwardSolver2Dacoustic.cpp:176-185)
+        const unsigned nba = (unsigned)((s->spAbsN + 255) / 256);
+        if (s->exact)
+            WS_LAUNCH(wssparse::kAbsDamp<true>, nba, 256, 0, s->stream, s->spAbsN, s->spAbsIdx.p, s->spAbsVal.p, Q.p, Q.vx, Q.vy, Q.dim == 3 ? Q.vz : nullptr);
+        else
+            WS_LAUNCH(wssparse::kAbsDamp<false>, nba, 256, 0, s->stream, s->spAbsN, s->spAbsIdx.p, s->spAbsVal.p, Q.p, Q.vx, Q.vy, Q.dim == 3 ? Q.vz : nullptr);
+        s->launches++;
+    }
     sparseInterpolate(s, 0, Q.p);
     if (s->spSurfN > 0) {
         WS_LAUNCH(wssparse::kSurfaceZero, (unsigned)((s->spSurfN + 255) / 256), 256, 0, s->stream, s->spSurfN, s->spSurf.p, Q.p);
@@ -1544,7 +1555,7 @@ static int createImpl(const ws_desc *desc, long long sparseN, ws_solver **out)
             WS_REQUIRE(sparseN < (1LL << 31), WS_EINVAL, "n_points exceeds int32 indices (scai::IndexType)");
             WS_REQUIRE(local.eq == WS_EQ_ACOUSTIC, WS_EINVAL, "operator-given mode (variable grid) is available for the acoustic solvers");
             WS_REQUIRE(local.nranks <= 1, WS_EINVAL, "operator-given mode runs on one GPU per shot");
-            WS_REQUIRE(local.damping == 0 || local.damping == 2, WS_EINVAL, "operator-given mode: DampingBoundary must be 0 or 2 (CPML)");
+            WS_REQUIRE(local.damping >= 0 && local.damping <= 2, WS_EINVAL, "DampingBoundary must be 0, 1 or 2");
             local.nx = (int32_t)sparseN;
             local.ny = 1;
             local.nz = 1;
@@ -2386,6 +2397,24 @@ int ws_set_cpml_profile(ws_solver *s, int32_t axis, int64_t n, const int32_t *id
             s->spPsi[slot].zero(s->stream);
         }
         WS_CUDA_CHECK(cudaStreamSynchronize(s->stream));
+    });
+}
+
+int ws_set_abs_profile(ws_solver *s, int64_t n, const int32_t *idx, const float *damping)
+{
+    return guarded([&] {
+        WS_REQUIRE(s && (n == 0 || (idx && damping)), WS_EINVAL, "null argument");
+        WS_REQUIRE(s->sparse, WS_ESTATE, "ws_set_abs_profile needs a solver created with ws_create_sparse");
+        WS_REQUIRE(s->d.damping == 1 || n == 0, WS_ESTATE, "ws_set_abs_profile: the solver was not created with DampingBoundary = 1");
+        setDevice(s);
+        invalidateGraph(s);
+        for (int64_t e = 0; e < n; e++)
+            WS_REQUIRE(idx[e] >= 0 && idx[e] < s->nx, WS_EINVAL, "damping index out of range");
+        s->spAbsN = n;
+        if (n > 0) {
+            s->spAbsIdx.upload(std::vector<int>(idx, idx + n));
+            s->spAbsVal.upload(std::vector<float>(damping, damping + n));
+        }
     });
 }
 

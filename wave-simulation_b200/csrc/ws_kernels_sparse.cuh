@@ -132,4 +132,21 @@ __global__ void __launch_bounds__(256) kSurfaceZero(long long n, const int *__re
         p[idx[r]] = __fmul_rn(p[idx[r]], 0.0f);
 }
 
+// ABS2D.cpp / ABS3D.cpp apply: p, vx, vy (, vz) *= damping on the points of the frame (every other entry of the sparse vector is 1)
+template <bool EXACT> __global__ void __launch_bounds__(256) kAbsDamp(long long n, const int *__restrict__ idx, const float *__restrict__ damp, float *__restrict__ p, float *__restrict__ vx,
+                                                                       float *__restrict__ vy, float *__restrict__ vz)
+{
+    using A = Ar<EXACT>;
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n)
+        return;
+    const int i = idx[r];
+    const float d = damp[r];
+    p[i] = A::mul(p[i], d);
+    vx[i] = A::mul(vx[i], d);
+    vy[i] = A::mul(vy[i], d);
+    if (vz)
+        vz[i] = A::mul(vz[i], d);
+}
+
 } // namespace wssparse

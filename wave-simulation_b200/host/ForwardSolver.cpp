@@ -124,7 +124,6 @@ void ForwardSolver::ForwardSolver<ValueType>::initIrregular(Configuration::Confi
                                                             Acquisition::Coordinates<ValueType> const &mc)
 {
     SCAI_ASSERT_ERROR(equationType == "acoustic", "variable grids / variable FD orders are available for the acoustic solvers (equationType=" << equationType << ")")
-    SCAI_ASSERT_ERROR(d.damping == 0 || d.damping == 2, "variable grid: DampingBoundary must be 0 or 2 (CPML)")
     const size_t N = (size_t)mc.getNGridpoints();
     group->createSparse(d, N);
     NT = d.nt;
@@ -153,6 +152,10 @@ void ForwardSolver::ForwardSolver<ValueType>::initIrregular(Configuration::Confi
             const CpmlProfile p = ops.cpml(ax, d.boundary_width, d.npower, d.fc_cpml, d.vmax_cpml, d.free_surface != 0);
             check(ws_set_cpml_profile(h, (int32_t)ax, (int64_t)p.idx.size(), p.idx.data(), p.a.data(), p.b.data(), p.aHalf.data(), p.bHalf.data()));
         }
+    if (d.damping == 1) {
+        const AbsProfile p = ops.abs(d.boundary_width, d.damping_coeff, d.free_surface, d3);
+        check(ws_set_abs_profile(h, (int64_t)p.idx.size(), p.idx.data(), p.damping.data()));
+    }
     if (fs) {
         const std::vector<int32_t> surf = ops.surfacePoints();
         check(ws_set_surface(h, (int64_t)surf.size(), surf.data()));

@@ -250,6 +250,38 @@ CpmlProfile IrregularOperators<ValueType>::cpml(IndexType axis, IndexType bounda
     return p;
 }
 
+template <typename ValueType> AbsProfile IrregularOperators<ValueType>::abs(IndexType boundaryWidth, ValueType dampingCoeff, IndexType useFreeSurface, bool threeD) const
+{
+    const IndexType W = boundaryWidth;
+    std::vector<float> coeff(W);
+    const float amp = (float)(1.0 - dampingCoeff / 100.0);
+    const float a = (float)std::sqrt(-std::log(amp) / (float)(W * W));
+    for (IndexType j = 0; j < W; j++)
+        coeff[j] = (float)std::exp(-(a * a * (W - j) * (W - j)));
+    AbsProfile p;
+    for (IndexType row = 0; row < mc.getNGridpoints(); row++) {
+        const Acquisition::coordinate3D c = mc.index2coordinate(row), g = mc.edgeDistance(c);
+        IndexType mn = g.x < g.y ? g.x : g.y;
+        if (threeD && g.z < mn)
+            mn = g.z;
+        IndexType k = -1;
+        if (useFreeSurface == 0) {
+            if (mn < W)
+                k = mn;
+        } else if (c.y < W) { // below a free surface only the side frames damp
+            const IndexType side = threeD ? (!(g.x < g.z) ? g.z : g.x) : g.x;
+            if (side < W)
+                k = side;
+        } else if (mn < W)
+            k = mn;
+        if (k >= 0) {
+            p.idx.push_back((int32_t)row);
+            p.damping.push_back(coeff[k]);
+        }
+    }
+    return p;
+}
+
 template <typename ValueType> std::vector<int32_t> IrregularOperators<ValueType>::surfacePoints() const
 {
     std::vector<int32_t> s;

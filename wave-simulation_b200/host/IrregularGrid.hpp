@@ -25,6 +25,11 @@ namespace KITGPI
             std::vector<float> a, b, aHalf, bHalf;
         };
 
+        struct AbsProfile {
+            std::vector<int32_t> idx;
+            std::vector<float> damping;
+        };
+
         template <typename ValueType> class IrregularOperators
         {
           public:
@@ -39,6 +44,9 @@ namespace KITGPI
             //! 1 / (average of `par` over the two points of the staggered position), Inf / NaN -> 0 (Modelparameter.cpp:633-639)
             std::vector<ValueType> inverseAverage(std::vector<ValueType> const &par, IndexType axis) const;
             CpmlProfile cpml(IndexType axis, IndexType boundaryWidth, ValueType NPower, ValueType centerFrequency, ValueType vMax, bool freeSurface) const;
+            //! the sparse vector `damping` of ABS2D::init / ABS3D::init (ABS2D.cpp:110-178, ABS3D.cpp:154-218): the Cerjan coefficient of the distance
+            //! to the nearest edge, measured on the coordinates of the points (units of the finest spacing); useFreeSurface != 0: no frame at the top
+            AbsProfile abs(IndexType boundaryWidth, ValueType dampingCoeff, IndexType useFreeSurface, bool threeD) const;
             std::vector<int32_t> surfacePoints() const;
 
           private:
