@@ -2268,13 +2268,306 @@ struct Oracle {
         gatherSeismogram(t);
     }
 
+    // ------------------------------------------------------------------------------------------------------------
+    // Second CPU baseline ("the fused matrix-free CPU oracle as a second, stronger CPU number"): the 3-D elastic step
+    // with the operators applied as 1-D coefficient rows (taken from the assembled matrices: a row of D_x depends on x only, of D_y
+    // on y, of D_z on z) and all statements of a half-step fused per grid point.  Same operations in the same order as stepElastic,
+    // so the wavefields are bit-identical to the matrix formulation (tests/test_oracle_golden.py::test_fused_backend_*).
+    // ------------------------------------------------------------------------------------------------------------
+    bool fused = false, fusedReady = false;
+    struct Rows1D {
+        vector<int> cnt, off;
+        vector<T> val;
+    };
+    Rows1D fXf, fXb, fYf, fYb, fYfS, fYbS, fZf, fZb;
+    vector<Idx> fkx, fky, fkz; // grid point -> entry of the CPML pattern of the axis (-1 outside the layer)
+
+    Rows1D rows1d(const Csr<T> &A, Idx count, Idx stride) const
+    {
+        Rows1D R;
+        R.cnt.assign(count, 0);
+        R.off.assign((size_t)count * MAXROW, 0);
+        R.val.assign((size_t)count * MAXROW, (T)0);
+        if (A.empty())
+            return R;
+        for (Idx c = 0; c < count; c++) {
+            const Idx i = c * stride;
+            int k = 0;
+            for (int64_t e = A.ia[i]; e < A.ia[i + 1]; e++, k++) {
+                const Idx delta = A.ja[e] - i;
+                ORACLE_REQUIRE(k < MAXROW && delta % stride == 0, "fused back-end: operator row is not one-dimensional");
+                R.off[(size_t)c * MAXROW + k] = (int)(delta / stride);
+                R.val[(size_t)c * MAXROW + k] = A.va[e];
+            }
+            R.cnt[c] = k;
+        }
+        return R;
+    }
+    void fusedSetup()
+    {
+        ORACLE_REQUIRE(d.eq == WS_EQ_ELASTIC && d.dim == 3 && !vg.active && d.damping != 1,
+                       "the fused back-end serves the 3-D elastic solver on a regular grid without an ABS frame");
+        const Idx plane = NX * NZ;
+        fXf = rows1d(Dxf, NX, 1);
+        fXb = rows1d(Dxb, NX, 1);
+        fYf = rows1d(Dyf, NY, plane);
+        fYb = rows1d(Dyb, NY, plane);
+        fYfS = rows1d(DyfFS, NY, plane);
+        fYbS = rows1d(DybFS, NY, plane);
+        fZf = rows1d(Dzf, NZ, NX);
+        fZb = rows1d(Dzb, NZ, NX);
+        auto mapOf = [&](const Profile<T> &p, vector<Idx> &m) {
+            m.assign(d.damping == 2 ? N : 0, (Idx)-1);
+            if (d.damping == 2)
+                for (size_t k = 0; k < p.idx.size(); k++)
+                    m[p.idx[k]] = (Idx)k;
+        };
+        mapOf(px, fkx);
+        mapOf(py, fky);
+        mapOf(pz, fkz);
+        fusedReady = true;
+    }
+    // out += w * src over a line: the one hot loop of the derivative rows, compiled for the vector units the host has (function
+    // multi-versioning; the arithmetic stays one multiplication and one addition per element, no contraction)
+    __attribute__((target_clones("avx512f", "avx2", "default"), optimize("O3"))) static void axpyLine(T *__restrict__ out, T w, const T *__restrict__ src, Idx n)
+    {
+        for (Idx k = 0; k < n; k++)
+            out[k] += w * src[k];
+    }
+    // one x-line of a derivative into a line buffer; taps outermost so that the loops over x vectorise, every x accumulating its taps
+    // in ascending column order from 0 like the sparse matrix-vector product
+    static void lineYZ(const Rows1D &R, Idx c, const T *x, Idx i0, Idx stride, Idx n, T *__restrict__ out)
+    {
+        const int *o = &R.off[(size_t)c * MAXROW];
+        const T *v = &R.val[(size_t)c * MAXROW];
+        for (Idx k = 0; k < n; k++)
+            out[k] = (T)0;
+        for (int t = 0; t < R.cnt[c]; t++)
+            axpyLine(out, v[t], x + i0 + (Idx)o[t] * stride, n);
+    }
+    // rows of D_x: identical between the edge zones [0, fEdge) and [NX - fEdge, NX)
+    static inline void lineX(const Rows1D &R, Idx fEdge, const T *x, Idx i0, Idx n, T *out)
+    {
+        auto scalar = [&](Idx c) {
+            const int *o = &R.off[(size_t)c * MAXROW];
+            const T *v = &R.val[(size_t)c * MAXROW];
+            T sum = 0;
+            for (int t = 0; t < R.cnt[c]; t++)
+                sum += v[t] * x[i0 + c + o[t]];
+            out[c] = sum;
+        };
+        if (n <= 2 * fEdge) {
+            for (Idx c = 0; c < n; c++)
+                scalar(c);
+            return;
+        }
+        for (Idx c = 0; c < fEdge; c++)
+            scalar(c);
+        for (Idx c = n - fEdge; c < n; c++)
+            scalar(c);
+        const int *o = &R.off[(size_t)fEdge * MAXROW];
+        const T *v = &R.val[(size_t)fEdge * MAXROW];
+        const int cnt = R.cnt[fEdge];
+        for (Idx c = fEdge; c < n - fEdge; c++)
+            out[c] = (T)0;
+        for (int t = 0; t < cnt; t++)
+            axpyLine(out + fEdge, v[t], x + i0 + o[t] + fEdge, n - 2 * fEdge);
+    }
+    // applyCPML on an x-line.  y / z axis: the whole line lies in the layer or not, its entries are consecutive in the pattern;
+    // x axis: the two ends of the line.   temp = a; psi *= b; temp *= u; psi += temp; u += psi
+    static inline void cpEntry(T &u, T *ps, const Profile<T> &p, Idx k, bool half)
+    {
+        T temp = half ? p.ah[k] : p.a[k];
+        ps[k] = ps[k] * (half ? p.bh[k] : p.b[k]);
+        temp = temp * u;
+        ps[k] = ps[k] + temp;
+        u = u + ps[k];
+    }
+    static inline void cpLine(T *u, T *ps, const Profile<T> &p, const vector<Idx> &map, Idx i0, Idx n, bool half)
+    {
+        if (map.empty())
+            return;
+        const Idx k0 = map[i0];
+        if (k0 < 0)
+            return;
+        const T *A = (half ? p.ah : p.a).data() + k0, *B = (half ? p.bh : p.b).data() + k0;
+        T *q = ps + k0;
+        for (Idx k = 0; k < n; k++) {
+            T temp = A[k];
+            q[k] = q[k] * B[k];
+            temp = temp * u[k];
+            q[k] = q[k] + temp;
+            u[k] = u[k] + q[k];
+        }
+    }
+    static inline void cpLineX(T *u, T *ps, const Profile<T> &p, const vector<Idx> &map, Idx i0, Idx n, Idx W, bool half)
+    {
+        if (map.empty())
+            return;
+        for (Idx c = 0; c < n; c++) {
+            if (c == W && n > 2 * W)
+                c = n - W;
+            const Idx k = map[i0 + c];
+            if (k >= 0)
+                cpEntry(u[c], ps, p, k, half);
+        }
+    }
+    Idx fEdge = 0, fW = 0;
+    void fusedCheckLayout()
+    {
+        // (a) rows of the x operators are identical away from the edges; (b) a line of the y / z layer is consecutive in the pattern
+        fEdge = std::min<Idx>(NX, (Idx)(d.fd_order / 2 + 1));
+        for (const Rows1D *R : {&fXf, &fXb})
+            for (Idx c = fEdge; c + fEdge < NX; c++) {
+                ORACLE_REQUIRE(R->cnt[c] == R->cnt[fEdge], "fused back-end: interior rows of D_x differ");
+                for (int t = 0; t < R->cnt[c]; t++)
+                    ORACLE_REQUIRE(R->off[(size_t)c * MAXROW + t] == R->off[(size_t)fEdge * MAXROW + t] && R->val[(size_t)c * MAXROW + t] == R->val[(size_t)fEdge * MAXROW + t],
+                                   "fused back-end: interior rows of D_x differ");
+            }
+        fW = d.damping == 2 ? (Idx)d.boundary_width : 0;
+        if (d.damping == 2) {
+            for (const vector<Idx> *m : {&fky, &fkz})
+                for (Idx i0 = 0; i0 < N; i0 += NX)
+                    for (Idx c = 1; c < NX; c++)
+                        ORACLE_REQUIRE(((*m)[i0] < 0 && (*m)[i0 + c] < 0) || ((*m)[i0] >= 0 && (*m)[i0 + c] == (*m)[i0] + c), "fused back-end: CPML pattern is not line-wise");
+            for (Idx i0 = 0; i0 < N; i0 += NX)
+                for (Idx c = fW; c + fW < NX; c++)
+                    ORACLE_REQUIRE(fkx[i0 + c] < 0, "fused back-end: x layer wider than BoundaryWidth");
+        }
+    }
+    void stepElasticFused(Idx t)
+    {
+        if (!fusedReady) {
+            fusedSetup();
+            fusedCheckLayout();
+        }
+        const bool fs = d.free_surface == 1;
+        const Idx plane = NX * NZ, n = NX;
+        T *vX = F("VX").data(), *vY = F("VY").data(), *vZ = F("VZ").data();
+        T *Sxx = F("Sxx").data(), *Syy = F("Syy").data(), *Szz = F("Szz").data(), *Sxy = F("Sxy").data(), *Sxz = F("Sxz").data(), *Syz = F("Syz").data();
+        const T *rix = M("inverseDensityAverageX").data(), *riy = M("inverseDensityAverageY").data(), *riz = M("inverseDensityAverageZ").data();
+        const T *pw = M("pWaveModulus").data(), *sw = M("sWaveModulus").data();
+        const T *mxy = M("sWaveModulusAverageXY").data(), *mxz = M("sWaveModulusAverageXZ").data(), *myz = M("sWaveModulusAverageYZ").data();
+        auto P = [&](const char *name, const Profile<T> &p) -> T * { return d.damping == 2 ? psiOf(name, p).data() : nullptr; };
+        T *p_sxx_x = P("sxx_x", px), *p_sxy_y = P("sxy_y", py), *p_sxz_z = P("sxz_z", pz), *p_sxy_x = P("sxy_x", px), *p_syy_y = P("syy_y", py), *p_syz_z = P("syz_z", pz);
+        T *p_sxz_x = P("sxz_x", px), *p_syz_y = P("syz_y", py), *p_szz_z = P("szz_z", pz);
+        T *p_vxx = P("vxx", px), *p_vyy = P("vyy", py), *p_vzz = P("vzz", pz), *p_vxy = P("vxy", py), *p_vyx = P("vyx", px), *p_vxz = P("vxz", pz), *p_vzx = P("vzx", px);
+        T *p_vyz = P("vyz", pz), *p_vzy = P("vzy", py);
+        const Rows1D &Yb1 = fs ? fYbS : fYb, &Yf1 = fs ? fYfS : fYf;
+        const T *sHp = sH.data(), *sVp = sV.data();
+#pragma omp parallel
+        {
+            vector<T> bufA(n), bufB(n), bufC(n);
+            T *a = bufA.data(), *b = bufB.data(), *c = bufC.data();
+            // particle velocities (velocityElastic): v_a += rho_a^-1 ((P(D_x .) + P(D_y .)) + P(D_z .))
+            auto velocity = [&](Idx y, Idx z, Idx i0, const Rows1D &RX, const T *fx, T *psx, bool hx, const Rows1D &RY, const T *fy, T *psy, bool hy, const Rows1D &RZ,
+                                const T *fz, T *psz, bool hz, const T *ri, T *v) {
+                lineX(RX, fEdge, fx, i0, n, a);
+                cpLineX(a, psx, px, fkx, i0, n, fW, hx);
+                lineYZ(RY, y, fy, i0, plane, n, b);
+                cpLine(b, psy, py, fky, i0, n, hy);
+                lineYZ(RZ, z, fz, i0, NX, n, c);
+                cpLine(c, psz, pz, fkz, i0, n, hz);
+                for (Idx k = 0; k < n; k++) {
+                    T u = a[k] + b[k];
+                    u = u + c[k];
+                    u = u * ri[i0 + k];
+                    v[i0 + k] = v[i0 + k] + u;
+                }
+            };
+#pragma omp for collapse(2) schedule(static)
+            for (Idx y = 0; y < NY; y++)
+                for (Idx z = 0; z < NZ; z++) {
+                    const Idx i0 = y * plane + z * NX;
+                    velocity(y, z, i0, fXf, Sxx, p_sxx_x, true, Yb1, Sxy, p_sxy_y, false, fZb, Sxz, p_sxz_z, false, rix, vX);
+                    velocity(y, z, i0, fXb, Sxy, p_sxy_x, false, Yf1, Syy, p_syy_y, true, fZb, Syz, p_syz_z, false, riy, vY);
+                    velocity(y, z, i0, fXb, Sxz, p_sxz_x, false, Yb1, Syz, p_syz_y, false, fZf, Szz, p_szz_z, true, riz, vZ);
+                }
+            // stresses (normalStrainRates, stepElastic incl. the free surface); the implicit barrier of the loop above orders the passes
+            auto shear = [&](Idx i0, Idx c1, const Rows1D &R1, const T *f1, Idx stride1, T *ps1, const Profile<T> &pr1, const vector<Idx> &m1, bool x1, Idx c2, const Rows1D &R2,
+                             const T *f2, Idx stride2, T *ps2, const Profile<T> &pr2, const vector<Idx> &m2, bool x2, const T *mu, T *S) {
+                if (x1) {
+                    lineX(R1, fEdge, f1, i0, n, a);
+                    cpLineX(a, ps1, pr1, m1, i0, n, fW, true);
+                } else {
+                    lineYZ(R1, c1, f1, i0, stride1, n, a);
+                    cpLine(a, ps1, pr1, m1, i0, n, true);
+                }
+                if (x2) {
+                    lineX(R2, fEdge, f2, i0, n, b);
+                    cpLineX(b, ps2, pr2, m2, i0, n, fW, true);
+                } else {
+                    lineYZ(R2, c2, f2, i0, stride2, n, b);
+                    cpLine(b, ps2, pr2, m2, i0, n, true);
+                }
+                for (Idx k = 0; k < n; k++) {
+                    T u = a[k] + b[k];
+                    u = u * mu[i0 + k];
+                    S[i0 + k] = S[i0 + k] + u;
+                }
+            };
+#pragma omp for collapse(2) schedule(static)
+            for (Idx y = 0; y < NY; y++)
+                for (Idx z = 0; z < NZ; z++) {
+                    const Idx i0 = y * plane + z * NX;
+                    lineX(fXb, fEdge, vX, i0, n, a);
+                    lineYZ(fYb, y, vY, i0, plane, n, b);
+                    lineYZ(fZb, z, vZ, i0, NX, n, c);
+                    cpLineX(a, p_vxx, px, fkx, i0, n, fW, false);
+                    cpLine(b, p_vyy, py, fky, i0, n, false);
+                    cpLine(c, p_vzz, pz, fkz, i0, n, false);
+                    const bool surface = fs && y == 0;
+                    for (Idx k = 0; k < n; k++) {
+                        const Idx i = i0 + k;
+                        const T exx = a[k], eyy = b[k], ezz = c[k];
+                        T u = exx + eyy;
+                        u = u + ezz;
+                        u = u * pw[i];
+                        T sxx = Sxx[i] + u, syy = Syy[i] + u, szz = Szz[i] + u;
+                        u = eyy + ezz;
+                        u = u * sw[i];
+                        sxx = sxx - (T)2.0 * u;
+                        u = exx + ezz;
+                        u = u * sw[i];
+                        syy = syy - (T)2.0 * u;
+                        u = exx + eyy;
+                        u = u * sw[i];
+                        szz = szz - (T)2.0 * u;
+                        if (surface) { // FreeSurface3Delastic.cpp:15-47 (surface point k = x + z NX = i)
+                            u = exx + ezz;
+                            syy = syy * (T)0;
+                            T temp = sHp[i] * u;
+                            sxx = sxx + temp;
+                            szz = szz + temp;
+                            temp = sVp[i] * eyy;
+                            sxx = sxx - temp;
+                            szz = szz - temp;
+                        }
+                        Sxx[i] = sxx;
+                        Syy[i] = syy;
+                        Szz[i] = szz;
+                    }
+                    shear(i0, y, fYf, vX, plane, p_vxy, py, fky, false, 0, fXf, vY, 1, p_vyx, px, fkx, true, mxy, Sxy);
+                    shear(i0, z, fZf, vX, NX, p_vxz, pz, fkz, false, 0, fXf, vZ, 1, p_vzx, px, fkx, true, mxz, Sxz);
+                    shear(i0, z, fZf, vY, NX, p_vyz, pz, fkz, false, y, fYf, vZ, plane, p_vzy, py, fky, false, myz, Syz);
+                }
+        }
+        applySource(t);
+        gatherSeismogram(t);
+    }
+
     void step(Idx t)
     {
         ORACLE_REQUIRE(prepared, "call prepare before step");
         ORACLE_REQUIRE(t >= 0 && t < d.nt, "time step out of range");
         switch (d.eq) {
         case WS_EQ_ACOUSTIC: stepAcoustic(t); break;
-        case WS_EQ_ELASTIC: stepElastic(t); break;
+        case WS_EQ_ELASTIC:
+            if (fused)
+                stepElasticFused(t);
+            else
+                stepElastic(t);
+            break;
         case WS_EQ_VISCOELASTIC: stepViscoelastic(t); break;
         case WS_EQ_SH:
         case WS_EQ_VISCOSH: stepSH(t); break;
@@ -2453,6 +2746,12 @@ int wso_reset(wso_solver *s)
 {
     Handle *h = reinterpret_cast<Handle *>(s);
     return guard([&] { DISPATCH(h, o.reset()); });
+}
+/* 1 = fused matrix-free back-end (3-D elastic, regular grid, no ABS frame): the second CPU baseline of bench.py */
+int wso_set_fused(wso_solver *s, int32_t on)
+{
+    Handle *h = reinterpret_cast<Handle *>(s);
+    return guard([&] { DISPATCH(h, o.fused = on != 0); });
 }
 int wso_step(wso_solver *s, int32_t t)
 {

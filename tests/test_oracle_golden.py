@@ -129,3 +129,23 @@ def test_fp64_oracle_brackets_fp32():
     o32.run(0, 600)
     o64.run(0, 600)
     assert rel_l2(o32.seismogram(), o64.seismogram()) < 1.0e-5
+
+
+@pytest.mark.parametrize("pol,fs,damp", [(0, 1, 2), (1, 1, 2), (0, 0, 0), (1, 2, 2)])
+def test_fused_backend_of_the_oracle_is_bit_identical(pol, fs, damp):
+    """The second CPU baseline of bench.py: the 3-D elastic step with 1-D coefficient rows and all statements of a
+    half-step fused per grid point performs the operations of the matrix formulation in the same order: identical bits."""
+    from cases import fields_of, make_case
+    res = []
+    for fused in (False, True):
+        case = make_case("elastic", 3, 26, 24, 22, 8, pol, fs, damp, 6, 0, nt=20, exact=1)
+        o = case.setup(Oracle(case.desc))
+        if fused:
+            o.set_fused(True)
+        o.run(0, 20)
+        res.append((o.seismogram(), {f: o.wavefield(f) for f in fields_of("elastic", 3, 0)}))
+        o.close()
+    assert np.abs(res[0][0]).max() > 0
+    assert np.array_equal(res[0][0], res[1][0])
+    for f in res[0][1]:
+        assert np.array_equal(res[0][1][f], res[1][1][f]), f

@@ -67,6 +67,10 @@ class Oracle(SolverBase):
         self.n_rec = 0
         self._check(self.lib.wso_create(C.byref(desc), precision, C.byref(self.h)), "create")
 
+    def set_fused(self, on=True):
+        """the fused matrix-free back-end of the 3-D elastic solver (second CPU baseline of bench.py); bit-identical to the matrix formulation"""
+        self._check(self.lib.wso_set_fused(self.h, 1 if on else 0), "set_fused")
+
     def deriv_row(self, which, row):
         cols = np.zeros(16, dtype=np.int32)
         vals = np.zeros(16, dtype=np.float32)
