@@ -191,3 +191,55 @@ def test_error_behaviour():
         s.prepare()
     with pytest.raises(RuntimeError, match="ws_prepare must be called"):
         s.step(0)
+
+
+def test_abi_edge_cases_empty_acquisition_and_error_codes():
+    """Edge cases of the C ABI on the emulation build (the host code of the entry points is the product's): no sources, no receivers,
+    an empty time range, indices outside the grid, stepping before ws_prepare, a time range beyond NT, a bad descriptor."""
+    from wsharness import make_desc
+    case = make_case("elastic", 2, 40, 36, 1, 4, 0, 1, 2, 8, 0, nt=12, exact=1)
+    o = case.setup(Oracle(case.desc))
+    e = case.setup(EmuSolver(case.desc))
+    # an empty time range is a no-op
+    e.run(5, 5)
+    assert not e.wavefield("VX").any()
+    # no sources: nothing moves; the receivers record zeros
+    types, idx = case.rec
+    e.set_sources([], [], np.zeros((0, 12), np.float32))
+    e.reset()
+    e.run(0, 12)
+    assert not e.seismogram().any() and not e.wavefield("Sxx").any() and e.is_finite()
+    # no receivers: an empty seismogram, the wavefields as with receivers
+    st, sidx, sig = case.src
+    e.set_sources(st, sidx, sig)
+    e.set_receivers([], [])
+    e.reset()
+    e.run(0, 12)
+    o.run(0, 12)
+    assert e.seismogram().shape == (0, 12)
+    assert np.array_equal(e.wavefield("VY"), o.wavefield("VY"))
+    # indices outside the grid are refused with the reference's kind of message, the acquisition in place stays
+    with pytest.raises(RuntimeError, match="(?i)index|coordinate|range|grid"):
+        e.set_receivers([1], [40 * 36])
+    with pytest.raises(RuntimeError, match="(?i)index|coordinate|range|grid"):
+        e.set_sources([1], [-1], np.zeros((1, 12), np.float32))
+    with pytest.raises(RuntimeError, match="(?i)type"):
+        e.set_receivers([7], [0])
+    # time range beyond NT
+    with pytest.raises(RuntimeError, match="time range"):
+        e.run(0, 13)
+    e.close()
+    o.close()
+    # stepping before ws_prepare
+    fresh = EmuSolver(case.desc)
+    with pytest.raises(RuntimeError, match="ws_prepare"):
+        fresh.run(0, 1)
+    fresh.close()
+    # descriptors the reference rejects too
+    for bad in (dict(fd_order=7), dict(damping=3), dict(free_surface=3)):
+        kw = dict(dh=10.0, dt=8e-4, nt=4, fd_order=4, edge_policy=0, free_surface=0, damping=0, boundary_width=0)
+        kw.update(bad)
+        with pytest.raises(RuntimeError):
+            EmuSolver(make_desc(2, "elastic", 20, 20, 1, **kw))
+    with pytest.raises(RuntimeError, match="2D only"):
+        EmuSolver(make_desc(3, "sh", 20, 20, 20, dh=10.0, dt=8e-4, nt=4, fd_order=4, edge_policy=0, free_surface=0, damping=0, boundary_width=0))
