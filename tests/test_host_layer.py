@@ -576,7 +576,9 @@ def test_driver_variable_grid_2d_reproduces_oracle_and_golden(driver, tmp_path):
     from wsharness import reference_gate
     tmp = str(tmp_path)
     cfg = setup_vargrid_case(tmp, 2, 2)
-    run(driver, cfg, tmp)
+    log = run(driver, cfg, tmp).stdout
+    # Simulation.cpp:100-108, CheckParameter.hpp:22-49: what the grid fitting did to the configuration
+    assert "Number of gridpoints in layer: 3 =" in log and "Percentage of gridpoints" in log
     s = read_lmf_matrix(os.path.join(tmp, "seismograms", "seismogram.shot_0.p.lmf"))
     ref, gname = _oracle_vargrid(2, 1000)
     assert s.shape == (4, 1000) and np.abs(s).max() > 0

@@ -7,6 +7,25 @@ namespace KITGPI
 {
     namespace CheckParameter
     {
+        //! tells how the model dimensions and the interfaces were moved to fit the variable grid (CheckParameter.hpp:22-49)
+        template <typename ValueType> void checkVariableGrid(Configuration::Configuration const &config, Acquisition::Coordinates<ValueType> const &modelCoordinates)
+        {
+            const IndexType NX = config.get<IndexType>("NX"), NY = config.get<IndexType>("NY"), NZ = config.get<IndexType>("NZ");
+            const IndexType newNX = modelCoordinates.getNX(), newNY = modelCoordinates.getNY(), newNZ = modelCoordinates.getNZ();
+            if (NX != newNX || NY != newNY || NZ != newNZ)
+                HOST_PRINT("\nIn order to fit the variable grid, the model dimension had been altered from:" << NX << " X " << NY << " X " << NZ << " to " << newNX << " X " << newNY << " X "
+                                                                                                            << newNZ << " \n")
+            auto const &newInterfaces = modelCoordinates.getInterfaceVec();
+            std::vector<IndexType> interface = Acquisition::readColumnFromFile(config.get<std::string>("gridConfigurationFilename"), 0);
+            if (!interface.empty() && interface.at(0) == 0)
+                interface.erase(interface.begin());
+            else
+                COMMON_THROWEXCEPTION("First interface must by at y=0 ")
+            for (size_t i = 0; i < interface.size() && i + 1 < newInterfaces.size(); i++)
+                if (interface[i] != newInterfaces[i + 1])
+                    HOST_PRINT("In order to fit the variable grid, the interface Nr." << i + 1 << " has benn moved from Y=" << interface[i] << " to Y=" << newInterfaces[i + 1] << "\n\n")
+        }
+
         //! Courant-Friedrichs-Lewy criterion.  The reference's h factors (7/6, 149/120, ...) are integer divisions and
         //! evaluate to 1 (CheckParameter.hpp:73-98), so the enforced bound is dt <= DH / (sqrt(D) vpMax) for every order.
         template <typename ValueType>

@@ -27,6 +27,7 @@ namespace KITGPI
             //! `interfaces` without the leading 0 of the gridConfig file
             void init(IndexType nx, IndexType ny, IndexType nz, ValueType dh, std::vector<IndexType> const &dhFactors, std::vector<IndexType> const &interfaces);
 
+            std::vector<IndexType> const &getInterfaceVec() const { return interface; } // [-1, interfaces as moved to fit the grid, NY - 1]
             IndexType getNX() const { return NX; }
             IndexType getNY() const { return NY; }
             IndexType getNZ() const { return NZ; }
@@ -38,6 +39,7 @@ namespace KITGPI
             //! true when the model vector is layered (useVariableGrid or useVariableFDoperators): the operators are assembled point by point
             bool isVariable() const { return layered; }
             bool hasVariableSpacing() const { return variableSpacing; }
+            IndexType getNGridpoints(IndexType layer) const { return layered ? nGridpointsPerLayer.at(layer) : NX * NY * NZ; }
             IndexType getNumLayers() const { return layered ? (IndexType)dhFactor.size() : 1; }
             IndexType getLayer(IndexType y) const;                    // Coordinates.cpp:383-398
             IndexType getDHFactor(IndexType layer) const { return layered ? dhFactor[layer] : 1; }

@@ -235,6 +235,14 @@ int main(int argc, const char *argv[])
             nDevices = std::max<IndexType>(1, std::min<IndexType>(nDevices, std::atoi(e)));
 
         Acquisition::Coordinates<ValueType> modelCoordinates(config);
+        if (config.getAndCatch("useVariableGrid", 0) != 0) { // Simulation.cpp:100-108
+            CheckParameter::checkVariableGrid(config, modelCoordinates);
+            for (IndexType layer = 0; layer < modelCoordinates.getNumLayers(); layer++)
+                HOST_PRINT("\n Number of gridpoints in layer: " << layer << " = " << modelCoordinates.getNGridpoints(layer))
+            const double numGridpointsRegular = (double)config.get<IndexType>("NX") * config.get<IndexType>("NY") * config.get<IndexType>("NZ");
+            HOST_PRINT("\n Number of gripoints total: " << modelCoordinates.getNGridpoints())
+            HOST_PRINT("\n Percentage of gridpoints of the underlying regular grid given by NX*NY*NZ: " << (float)(modelCoordinates.getNGridpoints() / numGridpointsRegular * 100) << "% \n\n")
+        }
         if (config.getAndCatch("writeCoordinate", false)) // Simulation.cpp:151-154
             modelCoordinates.writeCoordinates(config.get<std::string>("coordinateFilename"), config.get<IndexType>("FileFormat"));
         const IndexType numRelaxationMechanisms = config.getAndCatch("numRelaxationMechanisms", 0);
