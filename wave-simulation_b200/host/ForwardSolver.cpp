@@ -71,9 +71,21 @@ template <typename ValueType> ForwardSolver::ForwardSolver<ValueType>::ForwardSo
 template <typename ValueType> ForwardSolver::ForwardSolver<ValueType>::~ForwardSolver() {}
 
 template <typename ValueType>
-ValueType ForwardSolver::ForwardSolver<ValueType>::estimateMemory(Configuration::Configuration const &config, Acquisition::Coordinates<ValueType> const &)
+ValueType ForwardSolver::ForwardSolver<ValueType>::estimateMemory(Configuration::Configuration const &config, Acquisition::Coordinates<ValueType> const &modelCoordinates)
 {
     ws_desc d = makeDesc(config, dimension, equationType, deviceIds[0]);
+    if (modelCoordinates.isVariable()) {
+        // operator-given mode: wavefields, model vectors and scratch as plain vectors of N points, the 2 x dim operators in ELL form
+        // (column + value per tap, as many taps as the highest FD order), CPML / interpolation lists are O(surface)
+        const double N = (double)modelCoordinates.getNGridpoints();
+        const int dim = d.dim;
+        IndexType taps = d.fd_order;
+        if (config.getAndCatch("useVariableFDoperators", 0) != 0)
+            for (IndexType o : Acquisition::readColumnFromFile(config.get<std::string>("gridConfigurationFilename"), 2))
+                taps = std::max(taps, o);
+        const double vectors = (dim + 1) + (dim + 1) + 2 + 1; // p, v;  pWaveModulus, inverse density averages;  vp, rho;  scratch
+        return (ValueType)((vectors * 4.0 + 2.0 * dim * taps * 8.0) * N / 1024.0 / 1024.0);
+    }
     d.nranks = (int32_t)deviceIds.size(); // memory of the first slab (the largest one)
     return (ValueType)(ws_estimate_memory(&d) / 1024.0 / 1024.0);
 }

@@ -252,7 +252,9 @@ int main(int argc, const char *argv[])
         {
             auto solver = ForwardSolver::Factory<ValueType>::Create(dimension, equationType);
             HOST_PRINT(" ========== " << dimension << " " << equationType << " Memory Estimation: ===========\n\n")
-            HOST_PRINT(" Wavefields, model and boundary slabs in HBM: " << solver->estimateMemory(config, modelCoordinates) << " MB per shot domain (derivatives are matrix-free: 0 MB)\n\n")
+            HOST_PRINT(" Wavefields, model and boundary slabs in HBM: " << solver->estimateMemory(config, modelCoordinates) << " MB per shot domain "
+                                                                        << (modelCoordinates.isVariable() ? "(variable grid: incl. the derivative operators in ELL form)" : "(derivatives are matrix-free: 0 MB)")
+                                                                        << "\n\n")
         }
 
         /* acquisition geometry (Simulation.cpp:233-282): shot selection (shotIncr), per-shot cut-outs (useStreamConfig), source encoding */
