@@ -2334,6 +2334,37 @@ struct Oracle {
         for (Idx k = 0; k < n; k++)
             out[k] += w * src[k];
     }
+    // v += ri * ((a + b) + c)  and  S += mu * (a + b)  over a line (same operations in the same order as the vector statements)
+    __attribute__((target_clones("avx512f", "avx2", "default"), optimize("O3"))) static void combine3(T *__restrict__ v, const T *__restrict__ a, const T *__restrict__ b,
+                                                                                                     const T *__restrict__ c, const T *__restrict__ ri, Idx n)
+    {
+        for (Idx k = 0; k < n; k++) {
+            T u = a[k] + b[k];
+            u = u + c[k];
+            u = u * ri[k];
+            v[k] = v[k] + u;
+        }
+    }
+    __attribute__((target_clones("avx512f", "avx2", "default"), optimize("O3"))) static void combine2(T *__restrict__ S, const T *__restrict__ a, const T *__restrict__ b,
+                                                                                                     const T *__restrict__ mu, Idx n)
+    {
+        for (Idx k = 0; k < n; k++) {
+            T u = a[k] + b[k];
+            u = u * mu[k];
+            S[k] = S[k] + u;
+        }
+    }
+    // applyCPML over consecutive entries: temp = a; psi *= b; temp *= u; psi += temp; u += psi
+    __attribute__((target_clones("avx512f", "avx2", "default"), optimize("O3"))) static void cpRun(T *__restrict__ u, T *__restrict__ q, const T *__restrict__ A, const T *__restrict__ B, Idx n)
+    {
+        for (Idx k = 0; k < n; k++) {
+            T temp = A[k];
+            q[k] = q[k] * B[k];
+            temp = temp * u[k];
+            q[k] = q[k] + temp;
+            u[k] = u[k] + q[k];
+        }
+    }
     // one x-line of a derivative into a line buffer; taps outermost so that the loops over x vectorise, every x accumulating its taps
     // in ascending column order from 0 like the sparse matrix-vector product
     static void lineYZ(const Rows1D &R, Idx c, const T *x, Idx i0, Idx stride, Idx n, T *__restrict__ out)
@@ -2390,15 +2421,7 @@ struct Oracle {
         const Idx k0 = map[i0];
         if (k0 < 0)
             return;
-        const T *A = (half ? p.ah : p.a).data() + k0, *B = (half ? p.bh : p.b).data() + k0;
-        T *q = ps + k0;
-        for (Idx k = 0; k < n; k++) {
-            T temp = A[k];
-            q[k] = q[k] * B[k];
-            temp = temp * u[k];
-            q[k] = q[k] + temp;
-            u[k] = u[k] + q[k];
-        }
+        cpRun(u, ps + k0, (half ? p.ah : p.a).data() + k0, (half ? p.bh : p.b).data() + k0, n);
     }
     static inline void cpLineX(T *u, T *ps, const Profile<T> &p, const vector<Idx> &map, Idx i0, Idx n, Idx W, bool half)
     {
@@ -2468,12 +2491,7 @@ struct Oracle {
                 cpLine(b, psy, py, fky, i0, n, hy);
                 lineYZ(RZ, z, fz, i0, NX, n, c);
                 cpLine(c, psz, pz, fkz, i0, n, hz);
-                for (Idx k = 0; k < n; k++) {
-                    T u = a[k] + b[k];
-                    u = u + c[k];
-                    u = u * ri[i0 + k];
-                    v[i0 + k] = v[i0 + k] + u;
-                }
+                combine3(v + i0, a, b, c, ri + i0, n);
             };
 #pragma omp for collapse(2) schedule(static)
             for (Idx y = 0; y < NY; y++)
@@ -2500,11 +2518,7 @@ struct Oracle {
                     lineYZ(R2, c2, f2, i0, stride2, n, b);
                     cpLine(b, ps2, pr2, m2, i0, n, true);
                 }
-                for (Idx k = 0; k < n; k++) {
-                    T u = a[k] + b[k];
-                    u = u * mu[i0 + k];
-                    S[i0 + k] = S[i0 + k] + u;
-                }
+                combine2(S + i0, a, b, mu + i0, n);
             };
 #pragma omp for collapse(2) schedule(static)
             for (Idx y = 0; y < NY; y++)
