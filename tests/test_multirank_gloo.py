@@ -17,6 +17,7 @@ CASES = [
     ("acoustic", 2, 30, 40, 1, 4, 1, 1, 2, 6, 0, 2),
     ("viscoelastic", 2, 24, 37, 1, 6, 1, 1, 1, 5, 2, 3),
     ("viscotmem", 2, 26, 36, 1, 4, 0, 0, 2, 6, 1, 2),
+    ("elastic", 2, 30, 40, 1, 8, 1, 2, 2, 6, 0, 2),  # FreeSurface = 2: no frame at the top, plain operators on the first slab
 ]
 
 
@@ -56,7 +57,7 @@ def _worker(rank, world, port, cfg, nt, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("cfg", CASES, ids=["%s%dD-q%d-w%d" % (c[0], c[1], c[5], c[11]) for c in CASES])
+@pytest.mark.parametrize("cfg", CASES, ids=["%s%dD-q%d-fs%d-w%d" % (c[0], c[1], c[5], c[7], c[11]) for c in CASES])
 def test_yslab_decomposition_equals_single_rank(cfg):
     from wsharness import EmuSolver
     world, cfg = cfg[11], cfg[:11]
