@@ -329,6 +329,59 @@ int main(int argc, char **argv)
         EXPECT(m2.getVelocityP() == m.getVelocityP() && m2.getDensity() == m.getDensity());
         EXPECT_THROW(m3.init(c3, regular)); // "Read variable model (ModelRead=2) not available if regular grid is chosen!"
     }
+    // ---- Seismogram::write / read: common-offset profile rows, the inverse AGC function (Seismogram.cpp:82-207)
+    {
+        Acquisition::Seismogram<ValueType> one;
+        one.setTraceType(Acquisition::VY, true);
+        one.getCoordinates1D().assign(1, 7);
+        one.allocate(1, 6);
+        one.setDT(0.1f);
+        one.setSeismoDT(0.1f);
+        one.allocateCOP(3, 6);
+        for (IndexType shot = 0; shot < 3; shot++) { // three single-trace shots land in rows 0..2 of the profile, no per-shot file
+            for (IndexType k = 0; k < 6; k++)
+                one.getData()[k] = (ValueType)(10 * shot + k);
+            one.setShotInd(shot, 2 - shot);
+            one.write(1, dir + "/cop.shot_" + std::to_string(shot));
+        }
+        EXPECT(!std::ifstream(dir + "/cop.shot_1.vy.mtx").good());
+        Acquisition::Seismogram<ValueType> all(one);
+        all.assignCOP();
+        EXPECT(all.getNumTraces() == 3 && all.getData()[6 + 2] == 12);
+        all.write(1, dir + "/cop");
+        // a single-trace shot reads its row back: row shotInd, or row shotIndIncr of the original numbering
+        one.setShotInd(1, 2);
+        one.read(1, dir + "/cop.shot_1");
+        EXPECT(one.getNumTraces() == 1 && one.getData()[3] == 13);
+        one.read(1, dir + "/cop.shot_1", true);
+        EXPECT(one.getData()[3] == 23);
+        // the inverse AGC function travels through format 5 and is applied by the next normalizeTrace(3)
+        Acquisition::Seismogram<ValueType> g;
+        g.setTraceType(Acquisition::P, true);
+        g.getCoordinates1D().assign(2, 3);
+        g.allocate(2, 40);
+        g.setDT(0.01f);
+        g.setSeismoDT(0.01f);
+        for (IndexType k = 0; k < 80; k++)
+            g.getData()[k] = std::sin(0.3f * k) * (1 + k % 7);
+        g.setFrequencyAGC(10);
+        g.calcInverseAGC();
+        const std::vector<ValueType> gain = g.getInverseAGC();
+        g.write(5, dir + "/agc");
+        Acquisition::Seismogram<ValueType> h(g);
+        std::fill(h.getInverseAGC().begin(), h.getInverseAGC().end(), ValueType(0));
+        h.read(5, dir + "/agc");
+        double worst = 0;
+        for (size_t k = 0; k < gain.size(); k++)
+            worst = std::max(worst, std::abs((double)h.getInverseAGC()[k] / gain[k] - 1));
+        EXPECT(gain.size() == 80 && worst < 1e-6);
+        g.normalizeTrace(3);
+        h.normalizeTrace(3);
+        worst = 0;
+        for (size_t k = 0; k < 80; k++)
+            worst = std::max(worst, std::abs((double)h.getData()[k] - g.getData()[k]));
+        EXPECT(worst < 1e-5);
+    }
     // ---- file formats: mtx and lmf round trips, resampling (Common.hpp:202-233)
     {
         std::vector<ValueType> m = {1, 2, 3, 4, 5, 6}, back;

@@ -476,15 +476,42 @@ void Acquisition::Seismogram<ValueType>::write(IndexType seismogramFormat, std::
     }
 }
 
-template <typename ValueType> void Acquisition::Seismogram<ValueType>::read(IndexType seismogramFormat, std::string const &filename)
+template <typename ValueType> void Acquisition::Seismogram<ValueType>::read(IndexType seismogramFormat, std::string const &filename, bool readOriginal)
 {
-    const std::string name = filename + "." + (isSeismic ? SeismogramTypeString[type] : SeismogramTypeStringEM[type]);
-    IndexType r, c;
-    if (seismogramFormat == 4)
-        SUIO::readDataSU(name, data, r, c); // Seismogram.cpp:180-193
+    const bool readSingleTrace = getNumTraces() == 1 && numshotsCOP > 1;
+    std::string base = filename;
+    if (readSingleTrace) {
+        const size_t pos = filename.find(".shot");
+        if (pos != std::string::npos)
+            base = filename.substr(0, pos);
+    }
+    std::string name = base + "." + (isSeismic ? SeismogramTypeString[type] : SeismogramTypeStringEM[type]);
+    IndexType seismoFormat = seismogramFormat;
+    if (seismogramFormat == 5) {
+        seismoFormat = 1;
+        name += ".inverseAGC";
+        useAGC = true;
+    }
+    std::vector<ValueType> in;
+    IndexType r = 0, c = 0;
+    if (seismoFormat == 4)
+        SUIO::readDataSU(name, in, r, c); // Seismogram.cpp:180-193
     else
-        IO::readMatrix(data, r, c, name, seismogramFormat);
-    numSamples = c;
+        IO::readMatrix(in, r, c, name, seismoFormat);
+    if (readSingleTrace && r > 1) { // one row of the profile
+        const IndexType row = readOriginal ? shotIndIncr : shotInd;
+        SCAI_ASSERT_ERROR(row >= 0 && row < r, name << " holds " << r << " traces, trace " << row << " was asked for")
+        in = std::vector<ValueType>(in.begin() + (size_t)row * c, in.begin() + (size_t)(row + 1) * c);
+        r = 1;
+    }
+    if (!coordinates1D.empty())
+        SCAI_ASSERT_ERROR(r == getNumTraces(), name << " holds " << r << " traces, the acquisition has " << getNumTraces())
+    if (seismogramFormat == 5)
+        inverseAGC = in;
+    else {
+        data = in;
+        numSamples = c;
+    }
 }
 
 template <typename ValueType> IndexType Acquisition::SeismogramHandler<ValueType>::getNumTracesTotal() const

@@ -112,7 +112,10 @@ namespace KITGPI
             //! SeismogramFormat 1 = mtx, 2 = lmf, 4 = SU (needs the model coordinates for the trace headers, Seismogram.cpp:82-147)
             //! 5 = the inverse AGC function as `<filename>.<type>.inverseAGC.mtx`.  A single trace goes into the common-offset profile when one is allocated.
             void write(IndexType seismogramFormat, std::string const &filename, Coordinates<ValueType> const *modelCoordinates = nullptr);
-            void read(IndexType seismogramFormat, std::string const &filename);
+            //! Seismogram.cpp:158-207.  5 = the inverse AGC function `<filename>.<type>.inverseAGC.mtx` (used by the next normalizeTrace(3)).  When a common-offset
+            //! profile is allocated and this seismogram holds ONE trace, `filename` (`...shot_<n>`) is cut at ".shot" and the trace is row shotInd of the
+            //! profile file (row shotIndIncr with readOriginal: the numbering of the original, unselected shots)
+            void read(IndexType seismogramFormat, std::string const &filename, bool readOriginal = false);
             void setSourceCoordinate(IndexType sourceCoord) { sourceCoordinate1D = sourceCoord; } // Seismogram.cpp:561
             IndexType getSourceCoordinate() const { return sourceCoordinate1D; }
             //! the traces of the single shots a supershot was decoded into (Seismogram.hpp getDataDecode): row-major matrices, traces x NT
